@@ -1,0 +1,226 @@
+/*
+ * frz_cuda.h — C ABI of the B200-native `match_list` path of saghen/frizbee.
+ *
+ * This header is the drop-in boundary.  Every entry point
+ * names the reference interface it replaces (paths relative to the reference
+ * crate root).  Plain pointers and sizes only: no torch, no C++ types.
+ *
+ * Reference interfaces replaced:
+ *   trait Specialized::match_list            src/matcher/algo.rs:14-22
+ *   Matcher::{new,from_patterns,from_query}  src/matcher/mod.rs:90-136
+ *   Matcher::match_list                      src/matcher/mod.rs:212-222
+ *   Matcher::match_list_parallel             src/matcher/parallel.rs:18-89
+ *   Pattern::{parse,parse_query}             src/pattern.rs:100-222
+ *   radix_sort_matches                       src/sort.rs:6-40
+ *   Match / Config / Scoring / enums         src/lib.rs:141-153,236-271,313-323,439-478
+ *
+ * There is NO CPU fallback behind this ABI: every compute entry point fails
+ * with FRZ_ERR_NO_DEVICE / FRZ_ERR_CUDA when no sm_100 device is usable.
+ */
+#ifndef FRZ_CUDA_H
+#define FRZ_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FRZ_ABI_VERSION 1
+
+/* ------------------------------------------------------------------ status */
+
+typedef enum frz_status {
+    FRZ_OK = 0,
+    FRZ_ERR_INVALID_ARG = 1,
+    /* reference panics: "needle too long and could overflow the u16 score" (src/lib.rs:524-527) */
+    FRZ_ERR_NEEDLE_TOO_LONG = 2,
+    /* reference panics: "gap penalties too large" (src/lib.rs:532-536) */
+    FRZ_ERR_GAP_OVERFLOW = 3,
+    /* reference panics: "too many items in haystack, will overflow the u32 index" (src/matcher/mod.rs:438-446) */
+    FRZ_ERR_TOO_MANY_ITEMS = 4,
+    /* reference panics: "threads must be positive" (src/matcher/parallel.rs:24) */
+    FRZ_ERR_THREADS_ZERO = 5,
+    /* caller-provided output buffer too small; *n_out holds the required count */
+    FRZ_ERR_CAPACITY = 6,
+    FRZ_ERR_CUDA = 7,
+    FRZ_ERR_NO_DEVICE = 8,
+    /* feature of the reference not built on the GPU path yet (never a silent CPU fallback) */
+    FRZ_ERR_UNSUPPORTED = 9,
+    FRZ_ERR_OOM = 10
+} frz_status;
+
+/* thread-local, human-readable detail for the last non-OK status */
+const char* frz_last_error(void);
+const char* frz_status_str(frz_status s);
+int frz_abi_version(void);
+
+/* ------------------------------------------------------------------- types */
+
+/* `Match` (src/lib.rs:141-153).  The reference struct is default-repr Rust; the shim converts. */
+typedef struct frz_match {
+    uint32_t index; /* index in the original haystack list (+ index_offset) */
+    uint16_t score;
+    uint8_t exact;  /* 0/1 */
+    uint8_t _pad;   /* always 0 */
+} frz_match;
+
+/* `Scoring` (src/lib.rs:439-478), defaults from src/const.rs:1-10 */
+typedef struct frz_scoring {
+    uint16_t match_score;          /* 12 */
+    uint16_t mismatch_penalty;     /*  6 */
+    uint16_t gap_open_penalty;     /*  5 */
+    uint16_t gap_extend_penalty;   /*  1 */
+    uint16_t prefix_bonus;         /* 12 */
+    uint16_t capitalization_bonus; /*  4 */
+    uint16_t matching_case_bonus;  /*  4 */
+    uint16_t exact_match_bonus;    /*  8 */
+    uint16_t delimiter_bonus;      /*  4 */
+} frz_scoring;
+
+/* `CaseMatching` (src/lib.rs:353-377) */
+enum { FRZ_CASE_IGNORE = 0, FRZ_CASE_SMART = 1, FRZ_CASE_RESPECT = 2 };
+/* `UnicodeMatching` (src/lib.rs:379-402) */
+enum { FRZ_UNICODE_IGNORE = 0, FRZ_UNICODE_SMART = 1, FRZ_UNICODE_ALWAYS = 2 };
+/* `Matching` (src/lib.rs:413-436) */
+enum { FRZ_MATCHING_FUZZY = 0, FRZ_MATCHING_EXACT = 1, FRZ_MATCHING_PREFIX = 2,
+       FRZ_MATCHING_SUFFIX = 3, FRZ_MATCHING_SUBSTRING = 4 };
+/* `SortStrategy` (src/lib.rs:311-351) */
+enum { FRZ_SORT_SCORE_THEN_INDEX_ASC = 0, FRZ_SORT_SCORE_THEN_INDEX_DESC = 1,
+       FRZ_SORT_INDEX_ASC = 2, FRZ_SORT_INDEX_DESC = 3 };
+
+#define FRZ_MAX_TYPOS_NONE (-1)
+
+/* `Config` (src/lib.rs:236-271) */
+typedef struct frz_config {
+    int32_t max_typos;     /* FRZ_MAX_TYPOS_NONE (= Rust `None`) or 0..65535; default 0 */
+    uint8_t casing;        /* FRZ_CASE_*;     default SMART */
+    uint8_t unicode;       /* FRZ_UNICODE_*;  default SMART */
+    uint8_t matching;      /* FRZ_MATCHING_*; default FUZZY */
+    uint8_t sort;          /* FRZ_SORT_*;     default SCORE_THEN_INDEX_ASC */
+    frz_scoring scoring;
+    /* Which reference SIMD backend the integer results are bit-exact with
+     * (SURVEY.md §8 finding 1: scores depend on the lane count).
+     * 0 = auto: the backend `Matcher::get_backend` (src/matcher/mod.rs:448-498)
+     * would select on THIS host's CPU; else 16 (SSE/NEON/scalar), 32 (AVX2),
+     * 64 (AVX-512+VBMI) = lane count of the u8 family; the u16 family
+     * (needle too long for u8 scores) uses half of it. */
+    uint8_t emulate_lanes;
+    uint8_t _pad;
+} frz_config;
+
+/* `Pattern` + `PatternConfig` (src/pattern.rs:9-18, 230-246).  Overrides use -1 = inherit. */
+typedef struct frz_pattern {
+    const uint8_t* needle;
+    size_t needle_len;
+    uint8_t negated;
+    uint8_t has_scoring;       /* 1 → `scoring` overrides Config::scoring */
+    int8_t casing;             /* -1 inherit, else FRZ_CASE_* */
+    int8_t unicode;            /* -1 inherit, else FRZ_UNICODE_* */
+    int8_t matching;           /* -1 inherit, else FRZ_MATCHING_* */
+    int8_t _pad[3];
+    int32_t max_typos;         /* -1 inherit (PatternConfig cannot express "unlimited"), else 0..65535 */
+    frz_scoring scoring;
+} frz_pattern;
+
+void frz_config_default(frz_config* out);   /* Config::default()  src/lib.rs:260-271 */
+void frz_scoring_default(frz_scoring* out); /* Scoring::default() src/lib.rs:461-478 */
+
+/* ------------------------------------------------------- query-atom parser */
+
+/* Owned parse result of Pattern::parse_query (src/pattern.rs:190-222). */
+typedef struct frz_query frz_query;
+frz_status frz_parse_query(const uint8_t* query, size_t len, frz_query** out);
+/* Pattern::parse (src/pattern.rs:100-165) on one atom; result holds exactly one pattern
+ * (even when its needle is empty, as in the reference). */
+frz_status frz_parse_atom(const uint8_t* atom, size_t len, frz_query** out);
+size_t frz_query_len(const frz_query* q);
+/* The returned pattern's `needle` points into `q`; valid until frz_query_destroy. */
+frz_status frz_query_get(const frz_query* q, size_t i, frz_pattern* out);
+void frz_query_destroy(frz_query* q);
+
+/* ----------------------------------------------------------------- corpus */
+
+/* A haystack list, packed and resident in HBM on one device.  Immutable after create,
+ * reusable across matchers/needles (the interactive use: haystacks fixed, needle changes).
+ * Replaces the `&[S: AsRef<str>]` argument of Matcher::match_list (src/matcher/mod.rs:212).
+ * Input is Arrow-style: `bytes` = concatenated UTF-8, `offsets[n+1]` monotone byte offsets. */
+typedef struct frz_corpus frz_corpus;
+
+frz_status frz_corpus_create(const uint8_t* bytes, const uint64_t* offsets, uint64_t n,
+                             int device, frz_corpus** out);
+/* same, from a pointer array + lengths (the layout a Rust `&[&str]` has) */
+frz_status frz_corpus_create_ptrs(const uint8_t* const* ptrs, const uint32_t* lens, uint64_t n,
+                                  int device, frz_corpus** out);
+/* same, but `d_bytes`/`d_offsets` are already device pointers on `device` */
+frz_status frz_corpus_create_device(const uint8_t* d_bytes, const uint64_t* d_offsets, uint64_t n,
+                                    uint64_t total_bytes, int device, void* stream, frz_corpus** out);
+uint64_t frz_corpus_len(const frz_corpus* c);
+uint64_t frz_corpus_total_bytes(const frz_corpus* c);   /* sum of haystack lengths */
+uint64_t frz_corpus_device_bytes(const frz_corpus* c);  /* HBM footprint of the packed form */
+int frz_corpus_device(const frz_corpus* c);
+void frz_corpus_destroy(frz_corpus* c);
+
+/* ---------------------------------------------------------------- matcher */
+
+/* `Matcher` (src/matcher/mod.rs:76-188). */
+typedef struct frz_matcher frz_matcher;
+
+/* Matcher::from_patterns (src/matcher/mod.rs:105-111); n_patterns == 1 ⇔ Matcher::new */
+frz_status frz_matcher_create(const frz_pattern* patterns, size_t n_patterns,
+                              const frz_config* config, frz_matcher** out);
+/* Matcher::from_query (src/matcher/mod.rs:136-138) */
+frz_status frz_matcher_from_query(const uint8_t* query, size_t len, const frz_config* config,
+                                  frz_matcher** out);
+/* Matcher::set_config (src/matcher/mod.rs:154-160) */
+frz_status frz_matcher_set_config(frz_matcher* m, const frz_config* config);
+void frz_matcher_destroy(frz_matcher* m);
+
+/* Introspection of what `get_backend` selected for pattern i (src/matcher/mod.rs:448-498):
+ * lanes ∈ {8,16,32,64}; score_bits ∈ {8,16}; prefilter_lanes ∈ {16,32,64}; is_literal 0/1. */
+frz_status frz_matcher_backend_info(const frz_matcher* m, size_t i, int* lanes, int* score_bits,
+                                    int* prefilter_lanes, int* is_literal);
+size_t frz_matcher_num_patterns(const frz_matcher* m); /* compiled (non-empty-needle) patterns */
+
+/* Matcher::match_list (src/matcher/mod.rs:212-222): all patterns, ordered per config.sort.
+ * `out` is HOST memory with room for `cap` matches.  On FRZ_ERR_CAPACITY *n_out = needed. */
+frz_status frz_match_list(frz_matcher* m, const frz_corpus* corpus,
+                          frz_match* out, uint64_t cap, uint64_t* n_out);
+
+/* Specialized::match_list / Matcher::match_list_into (src/matcher/algo.rs:17-22,
+ * src/matcher/mod.rs:373-392): matches appended in input (index-ascending) order,
+ * indices offset by `index_offset`, no sort. */
+frz_status frz_match_list_into(frz_matcher* m, const frz_corpus* corpus, uint32_t index_offset,
+                               frz_match* out, uint64_t cap, uint64_t* n_out);
+
+/* End-to-end convenience: Matcher::match_list on HOST Arrow buffers (pack + H2D + match + D2H
+ * in one call; nothing stays resident). */
+frz_status frz_match_list_host(frz_matcher* m, const uint8_t* bytes, const uint64_t* offsets,
+                               uint64_t n, int device, frz_match* out, uint64_t cap, uint64_t* n_out);
+
+/* Device-resident variant used by the multi-GPU path (Matcher::match_list_parallel,
+ * src/matcher/parallel.rs:18-89): this rank's shard → a locally ordered run left in HBM.
+ * `d_out` (cap matches) and `d_count` (one uint64) are device pointers; `stream` is a
+ * cudaStream_t (NULL = default stream).  Asynchronous: returns after enqueueing. */
+frz_status frz_match_shard_device(frz_matcher* m, const frz_corpus* shard, uint32_t index_offset,
+                                  frz_match* d_out, uint64_t cap, uint64_t* d_count, void* stream);
+
+/* k_merge_matches_by (src/k_merge.rs:90-131) on device: `d_runs` holds `n_runs` runs, run r at
+ * d_runs + r*run_stride with run_counts_host[r] valid entries, each already ordered per `sort`.
+ * Writes the merged sequence to d_out (may not alias d_runs). */
+frz_status frz_merge_runs_device(const frz_match* d_runs, uint64_t run_stride,
+                                 const uint64_t* run_counts_host, int n_runs, uint8_t sort,
+                                 frz_match* d_out, int device, void* stream);
+
+/* radix_sort_matches (src/sort.rs:6-40): stable, descending score; `matches` is host memory. */
+frz_status frz_radix_sort_matches(frz_match* matches, uint64_t n, int device);
+
+/* Per-stage device timings (ms) of the most recent frz_match_list* call on this matcher:
+ * [0]=prefilter [1]=smith-waterman [2]=sort/emit [3]=total device; bytes = algorithmic bytes. */
+frz_status frz_matcher_last_timings(const frz_matcher* m, float* ms4, uint64_t* launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FRZ_CUDA_H */

@@ -1,0 +1,819 @@
+// frz_oracle.cpp — CPU restatement of the reference's match_list path.
+//
+// TEST INFRASTRUCTURE ONLY.  This file is the parity checker for the CUDA path.
+// Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+// leg may load it.  The product (frizbee_b200/, libfrz_cuda.so) never links or calls it.
+//
+// PARITY PINNING: the reference is a Rust crate and no Rust toolchain exists in this
+// image, so the reference itself cannot be run here.  The oracle is pinned against
+// every known-answer vector the reference's own tests hold for this path
+// (tests/test_oracle_kat.py lists each with its source file:line).  The crate has no
+// third-party algorithmic dependency (Cargo.toml:33-34), so the algorithm is entirely
+// restated from /root/reference/src.
+//
+// Each function cites the reference file:line it follows (paths relative to the
+// reference crate root).  Vectors are restated with *real* u8 / u16 lane arithmetic
+// (wrapping add, zero-saturating sub, `value as u8` truncation of constants) and a
+// runtime LANES so that any reference backend (LANES, width) can be emulated:
+//   Scalar 8xu16 / 16xu8, SSE 8xu16 / 16xu8, AVX2 16xu16 / 32xu8, AVX-512 32xu16 / 64xu8
+//   (src/smith_waterman/backend/scalar.rs:440-455, avx.rs, avx512.rs).
+#include <algorithm>
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "../include/frz_cuda.h"
+
+namespace {
+
+constexpr int kMaxLanes = 64;
+constexpr size_t kMaxHaystackLen = 1024;  // src/smith_waterman/algo/mod.rs:18
+
+struct Pair {
+    uint8_t c, flip;
+};
+
+// src/prefilter/mod.rs:49-65 (case_needle)
+static std::vector<Pair> case_needle(const uint8_t* needle, size_t n, bool case_sensitive) {
+    std::vector<Pair> out(n);
+    for (size_t i = 0; i < n; i++) {
+        uint8_t c = needle[i];
+        uint8_t f;
+        if (case_sensitive) f = c;
+        else if (c >= 'a' && c <= 'z') f = (uint8_t)(c - 32);
+        else if (c >= 'A' && c <= 'Z') f = (uint8_t)(c + 32);
+        else f = c;
+        out[i] = {c, f};
+    }
+    return out;
+}
+
+// ---------------------------------------------------------------------------------
+// Prefilter.  Masks are restated as uint64_t holding LANES meaningful low bits
+// (u16/u32/u64 in the reference: src/prefilter/backend/mod.rs:45-114).
+// ---------------------------------------------------------------------------------
+struct Pf {
+    int lanes;
+    const std::vector<Pair>& needle;
+    const uint8_t* hay;
+    size_t len;
+
+    uint64_t all() const { return lanes == 64 ? ~0ull : ((1ull << lanes) - 1); }
+    // BitMaskOps::first_n (backend/mod.rs:71-77)
+    uint64_t first_n(size_t n) const { return n >= (size_t)lanes ? all() : ((1ull << n) - 1); }
+    // leading_zeros of the LANES-bit mask type
+    int lz(uint64_t m) const { return __builtin_clzll(m) - (64 - lanes); }
+    static int tz(uint64_t m) { return __builtin_ctzll(m); }
+    // clear_through_lowest (backend/mod.rs:105-107)
+    static uint64_t ctl(uint64_t mask, uint64_t hit) { return mask & ~(hit ^ (hit - 1)); }
+    // load_window (src/prefilter/algo/load.rs:4-26): returns the chunk mask; the chunk bytes are
+    // read through occ() with the same masking effect (lanes >= remaining never survive `& mask`).
+    uint64_t chunk_mask(size_t start) const { return first_n(len - start); }
+    // Backend::occ (backend/scalar.rs:51-59): either-case equality bitmask of the chunk at `start`.
+    // Lanes past the end of the haystack are garbage in the reference (over-read) and always
+    // masked by chunk_mask by every caller; we return 0 there.
+    uint64_t occ(size_t start, Pair p) const {
+        uint64_t m = 0;
+        for (int i = 0; i < lanes; i++) {
+            size_t pos = start + i;
+            if (pos >= len) break;
+            uint8_t b = hay[pos];
+            if (b == p.c || b == p.flip) m |= 1ull << i;
+        }
+        return m;
+    }
+};
+
+// src/prefilter/algo/ascii.rs:57-72 (find_last_char_pos) on the sub-slice hay[off..]
+static size_t find_last_char_pos(const Pf& base, Pair last, size_t off) {
+    Pf s{base.lanes, base.needle, base.hay + off, base.len - off};
+    size_t len = s.len;
+    size_t start = len > (size_t)s.lanes ? len - s.lanes : 0;
+    for (;;) {
+        uint64_t mask = s.occ(start, last) & s.chunk_mask(start);
+        if (mask) return start + s.lanes - s.lz(mask);
+        start = start > (size_t)s.lanes ? start - s.lanes : 0;
+    }
+}
+
+// src/prefilter/algo/ascii.rs:6-54 (match_haystack, 0 typos)
+static bool prefilter_k0(const Pf& p, size_t* ostart, size_t* oend) {
+    size_t len = p.len;
+    if (len == 0) { *ostart = 0; *oend = 0; return false; }
+    bool can_skip = true;
+    size_t match_start = 0;
+    size_t ni = 0;
+    size_t n = p.needle.size();
+    Pair nc = p.needle[0];
+    size_t start = 0;
+    while (start < len) {
+        uint64_t chunk_mask = p.chunk_mask(start);
+        for (;;) {
+            uint64_t mask = p.occ(start, nc) & chunk_mask;
+            if (!mask) break;
+            chunk_mask = Pf::ctl(chunk_mask, mask);
+            if (can_skip) { match_start = start + Pf::tz(mask); can_skip = false; }
+            if (ni + 1 < n) {
+                ni++;
+                nc = p.needle[ni];
+            } else if (start + p.lanes >= len) {
+                *ostart = match_start;
+                *oend = start + p.lanes - p.lz(mask);
+                return true;
+            } else {
+                *ostart = match_start;
+                *oend = start + find_last_char_pos(p, p.needle[n - 1], start);
+                return true;
+            }
+        }
+        start += p.lanes;
+    }
+    *ostart = match_start;
+    *oend = len;
+    return false;
+}
+
+// src/prefilter/algo/ascii_typos.rs:375-397 (find_end_pos_with_typos)
+static size_t find_end_pos_with_typos(const Pf& p, size_t max_typos) {
+    size_t len = p.len, n = p.needle.size();
+    size_t first = n - 1 - max_typos;
+    size_t start = (len - 1) / p.lanes * p.lanes;
+    for (;;) {
+        uint64_t mask = 0;
+        for (size_t i = first; i < n; i++) mask |= p.occ(start, p.needle[i]);
+        mask &= p.chunk_mask(start);
+        if (mask) return start + p.lanes - p.lz(mask);
+        if (start == 0) break;
+        start -= p.lanes;
+    }
+    return len;
+}
+
+// src/prefilter/algo/ascii_typos.rs:15-110 (match_haystack_1_typo)
+static bool prefilter_k1(const Pf& p, size_t* ostart, size_t* oend) {
+    size_t len = p.len, n = p.needle.size();
+    if (n <= 1) { *ostart = 0; *oend = len; return true; }
+    if (len == 0) { *ostart = 0; *oend = 0; return false; }
+    size_t f = 0, s = 1;
+    size_t ms = SIZE_MAX;
+    for (size_t start = 0; start < len; start += p.lanes) {
+        uint64_t cm = p.chunk_mask(start);
+        uint64_t fm = p.occ(start, p.needle[f]);
+        uint64_t sm = p.occ(start, p.needle[s]);
+        uint64_t fc = cm, sc = cm;
+        for (;;) {
+            bool advanced = false;
+            size_t cand = f + 1;
+            if (cand > s) {
+                if (cand == n) { *ostart = ms; *oend = find_end_pos_with_typos(p, 1); return true; }
+                s = cand;
+                sc = fc;
+                sm = p.occ(start, p.needle[s]);
+            } else if (cand == s && fc > sc) {
+                sc = fc;
+            }
+            uint64_t x = fm & fc;
+            if (x) {
+                ms = std::min(ms, start + (size_t)Pf::tz(x));
+                f++;
+                fc = Pf::ctl(fc, x);
+                fm = p.occ(start, p.needle[f]);
+                advanced = true;
+            }
+            uint64_t y = sm & sc;
+            if (y) {
+                ms = std::min(ms, start + (size_t)Pf::tz(y));
+                s++;
+                if (s >= n) { *ostart = ms; *oend = find_end_pos_with_typos(p, 1); return true; }
+                sc = Pf::ctl(sc, y);
+                sm = p.occ(start, p.needle[s]);
+                advanced = true;
+            }
+            if (!advanced) break;
+        }
+    }
+    *ostart = ms == SIZE_MAX ? 0 : ms;
+    *oend = len;
+    return false;
+}
+
+// src/prefilter/algo/ascii_typos.rs:113-251 (match_haystack_2_typos)
+static bool prefilter_k2(const Pf& p, size_t* ostart, size_t* oend) {
+    size_t len = p.len, n = p.needle.size();
+    if (n <= 2) { *ostart = 0; *oend = len; return true; }
+    if (len == 0) { *ostart = 0; *oend = 0; return false; }
+    size_t i1 = 0, i2 = 1, i3 = 2;
+    size_t ms = SIZE_MAX;
+    auto found = [&]() { *ostart = ms; *oend = find_end_pos_with_typos(p, 2); return true; };
+    for (size_t start = 0; start < len; start += p.lanes) {
+        uint64_t cm = p.chunk_mask(start);
+        uint64_t m1 = p.occ(start, p.needle[i1]);
+        uint64_t m2 = p.occ(start, p.needle[i2]);
+        uint64_t m3 = p.occ(start, p.needle[i3]);
+        uint64_t c1 = cm, c2 = cm, c3 = cm;
+        for (;;) {
+            bool advanced = false;
+            size_t cand2 = i1 + 1;
+            if (cand2 > i2) {
+                if (cand2 == n) return found();
+                i2 = cand2; c2 = c1; m2 = p.occ(start, p.needle[i2]);
+            } else if (cand2 == i2 && c1 > c2) {
+                c2 = c1;
+            }
+            size_t cand3 = i2 + 1;
+            if (cand3 > i3) {
+                if (cand3 == n) return found();
+                i3 = cand3; c3 = c2; m3 = p.occ(start, p.needle[i3]);
+            } else if (cand3 == i3 && c2 > c3) {
+                c3 = c2;
+            }
+            uint64_t x1 = m1 & c1;
+            if (x1) {
+                ms = std::min(ms, start + (size_t)Pf::tz(x1));
+                i1++;
+                c1 = Pf::ctl(c1, x1);
+                m1 = p.occ(start, p.needle[i1]);
+                advanced = true;
+            }
+            uint64_t x2 = m2 & c2;
+            if (x2) {
+                ms = std::min(ms, start + (size_t)Pf::tz(x2));
+                i2++;
+                if (i2 >= n) return found();
+                c2 = Pf::ctl(c2, x2);
+                m2 = p.occ(start, p.needle[i2]);
+                advanced = true;
+            }
+            uint64_t x3 = m3 & c3;
+            if (x3) {
+                ms = std::min(ms, start + (size_t)Pf::tz(x3));
+                i3++;
+                if (i3 >= n) return found();
+                c3 = Pf::ctl(c3, x3);
+                m3 = p.occ(start, p.needle[i3]);
+                advanced = true;
+            }
+            if (!advanced) break;
+        }
+    }
+    *ostart = ms == SIZE_MAX ? 0 : ms;
+    *oend = len;
+    return false;
+}
+
+// src/prefilter/algo/ascii_typos.rs:254-360 (match_haystack_many_typos_impl)
+static bool prefilter_many(const Pf& p, size_t max_typos, size_t* ostart, size_t* oend) {
+    size_t len = p.len, n = p.needle.size();
+    if (n <= max_typos) { *ostart = 0; *oend = len; return true; }
+    if (len == 0) { *ostart = 0; *oend = 0; return false; }
+    size_t path_count = max_typos + 1;
+    std::vector<size_t> idx(path_count, 0);
+    std::vector<uint64_t> nm(path_count, 0);
+    size_t ms = SIZE_MAX;
+    auto found = [&]() { *ostart = ms; *oend = find_end_pos_with_typos(p, max_typos); return true; };
+    for (size_t start = 0; start < len; start += p.lanes) {
+        uint64_t chunk_mask = p.chunk_mask(start);
+        for (size_t k = 0; k < path_count; k++) nm[k] = p.occ(start, p.needle[idx[k]]);
+        for (;;) {
+            for (size_t k = 1; k < path_count; k++) {
+                size_t cand = idx[k - 1] + 1;
+                if (cand > idx[k]) {
+                    if (cand == n) return found();
+                    idx[k] = cand;
+                    nm[k] = p.occ(start, p.needle[cand]);
+                }
+            }
+            uint64_t mm = 0;
+            for (size_t k = 0; k < path_count; k++) mm |= nm[k];
+            uint64_t matches = mm & chunk_mask;
+            if (!matches) break;
+            size_t hit_pos = Pf::tz(matches);
+            uint64_t hit = matches & p.first_n(hit_pos + 1);
+            ms = std::min(ms, start + hit_pos);
+            for (size_t k = 0; k < path_count; k++) {
+                if (!(nm[k] & hit)) continue;
+                idx[k]++;
+                if (idx[k] == n) return found();
+                nm[k] = p.occ(start, p.needle[idx[k]]);
+            }
+            chunk_mask = Pf::ctl(chunk_mask, hit);
+        }
+    }
+    *ostart = ms == SIZE_MAX ? 0 : ms;
+    *oend = len;
+    return false;
+}
+
+// src/matcher/algo.rs:171-193 (prefilter_haystack dispatch); max_typos < 0 == NO_PREFILTER
+static bool prefilter(const std::vector<Pair>& needle, const uint8_t* hay, size_t len, int max_typos,
+                      int lanes, size_t* s, size_t* e) {
+    if (max_typos < 0) { *s = 0; *e = len; return true; }
+    Pf p{lanes, needle, hay, len};
+    switch (max_typos) {
+        case 0: return prefilter_k0(p, s, e);
+        case 1: return prefilter_k1(p, s, e);
+        case 2: return prefilter_k2(p, s, e);
+        default: return prefilter_many(p, (size_t)max_typos, s, e);
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// Smith-Waterman.  ScoreVec with a runtime lane count and element width
+// (src/smith_waterman/backend/mod.rs:205-274, scalar.rs:163-354).
+// ---------------------------------------------------------------------------------
+struct SV {
+    uint16_t v[kMaxLanes];
+};
+
+struct Arith {
+    int lanes;
+    bool u8;
+    uint16_t trunc(uint16_t x) const { return u8 ? (uint16_t)(x & 0xFF) : x; }
+    SV zero() const { SV r; memset(&r, 0, sizeof r); return r; }
+    SV splat(uint16_t x) const { SV r = zero(); for (int i = 0; i < lanes; i++) r.v[i] = trunc(x); return r; }
+    SV first_lane(uint16_t x) const { SV r = zero(); r.v[0] = trunc(x); return r; }
+    SV add(const SV& a, const SV& b) const {  // wrapping
+        SV r = zero();
+        for (int i = 0; i < lanes; i++) r.v[i] = trunc((uint16_t)(a.v[i] + b.v[i]));
+        return r;
+    }
+    SV subs(const SV& a, const SV& b) const {  // saturating at zero
+        SV r = zero();
+        for (int i = 0; i < lanes; i++) r.v[i] = a.v[i] > b.v[i] ? (uint16_t)(a.v[i] - b.v[i]) : 0;
+        return r;
+    }
+    SV max(const SV& a, const SV& b) const {
+        SV r = zero();
+        for (int i = 0; i < lanes; i++) r.v[i] = std::max(a.v[i], b.v[i]);
+        return r;
+    }
+    SV band(const SV& a, const SV& b) const {
+        SV r = zero();
+        for (int i = 0; i < lanes; i++) r.v[i] = a.v[i] & b.v[i];
+        return r;
+    }
+    // shift_right_padded::<L> (scalar.rs:223-232)
+    SV srp(const SV& a, const SV& prev, int L) const {
+        SV r = zero();
+        for (int i = 0; i < L; i++) r.v[i] = prev.v[lanes - L + i];
+        for (int i = L; i < lanes; i++) r.v[i] = a.v[i - L];
+        return r;
+    }
+    uint16_t hmax(const SV& a) const {
+        uint16_t m = 0;
+        for (int i = 0; i < lanes; i++) m = std::max(m, a.v[i]);
+        return m;
+    }
+    uint16_t full() const { return u8 ? 0xFF : 0xFFFF; }
+};
+
+// src/smith_waterman/algo/ascii_gap.rs:11-105 (gap_step! / propagate_N_lane)
+static SV propagate(const Arith& A, SV row, const SV& adj, const SV& mm, const SV& amm, const SV& gop, SV gex) {
+    for (int s = 1; s < A.lanes; s <<= 1) {
+        SV shifted_row = A.srp(row, adj, s);
+        SV shifted_mm = A.srp(mm, amm, s);
+        SV pen = A.add(gex, A.band(gop, shifted_mm));
+        SV decayed = A.subs(shifted_row, pen);
+        row = A.max(row, decayed);
+        gex = A.add(gex, gex);
+    }
+    return row;
+}
+
+// src/smith_waterman/greedy.rs:7-91 (match_greedy); returns -1 for None
+static int match_greedy(const uint8_t* needle_raw, size_t n, const uint8_t* hay, size_t hl, const frz_scoring& sc,
+                        bool case_sensitive, bool include_prefix) {
+    std::vector<Pair> needle = case_needle(needle_raw, n, case_sensitive);
+    if (n > hl) return -1;
+    auto sat_add = [](uint16_t a, uint16_t b) { uint32_t r = (uint32_t)a + b; return (uint16_t)(r > 0xFFFF ? 0xFFFF : r); };
+    auto sat_sub = [](uint16_t a, uint16_t b) { return (uint16_t)(a > b ? a - b : 0); };
+    auto sat_mul = [](uint16_t a, uint16_t b) { uint32_t r = (uint32_t)a * b; return (uint16_t)(r > 0xFFFF ? 0xFFFF : r); };
+    uint16_t score = 0;
+    size_t hi = 0;
+    bool delim_enabled = false, prev_lower = false, prev_delim = false;
+    for (size_t ni = 0; ni < n; ni++) {
+        size_t hstart = hi;
+        bool matched = false;
+        while (hi <= hl - n + ni) {
+            uint8_t hc = hay[hi];
+            bool is_digit = hc >= '0' && hc <= '9';
+            bool is_upper = hc >= 'A' && hc <= 'Z';
+            bool is_lower = hc >= 'a' && hc <= 'z';
+            bool is_delim = hc < 128 && !(is_lower || is_upper || is_digit);
+            if (!is_delim) delim_enabled = true;
+            if (needle[ni].c != hc && needle[ni].flip != hc) {
+                prev_delim = delim_enabled && is_delim;
+                prev_lower = is_lower;
+                hi++;
+                continue;
+            }
+            score = sat_add(score, sc.match_score);
+            if (hi != hstart && ni != 0) {
+                size_t gl = hi - hstart;
+                gl = gl > 0 ? gl - 1 : 0;
+                uint16_t gap_len = (uint16_t)std::min<size_t>(gl, 0xFFFF);
+                score = sat_sub(score, sat_add(sc.gap_open_penalty, sat_mul(sc.gap_extend_penalty, gap_len)));
+            }
+            if (needle[ni].c == hc) score = sat_add(score, sc.matching_case_bonus);
+            if (is_upper && prev_lower) score = sat_add(score, sc.capitalization_bonus);
+            if (include_prefix && hi == 0) score = sat_add(score, sc.prefix_bonus);
+            if (prev_delim && !is_delim) score = sat_add(score, sc.delimiter_bonus);
+            prev_delim = delim_enabled && is_delim;
+            prev_lower = is_lower;
+            hi++;
+            matched = true;
+            break;
+        }
+        if (!matched) return -1;
+    }
+    return score;
+}
+
+// src/smith_waterman/algo/ascii.rs:10-158 (score_haystack), chunk-major exactly as the reference,
+// with the full score / match-mask matrices.
+static uint16_t sw_score(const uint8_t* needle_raw, size_t n, const frz_scoring& sc, bool case_sensitive,
+                         const uint8_t* hay, size_t hl, bool include_prefix, int lanes, bool u8) {
+    if (hl > kMaxHaystackLen) {
+        int g = match_greedy(needle_raw, n, hay, hl, sc, case_sensitive, include_prefix);
+        return g < 0 ? 0 : (uint16_t)g;
+    }
+    Arith A{lanes, u8};
+    std::vector<Pair> needle = case_needle(needle_raw, n, case_sensitive);
+    size_t chunks = (hl + lanes - 1) / lanes + 1;
+    // row 0 and column 0 are zero (ascii.rs:27-31)
+    std::vector<SV> H((n + 1) * chunks, A.zero());
+    std::vector<SV> M((n + 1) * chunks, A.zero());
+    auto sat_sub16 = [](uint16_t a, uint16_t b) { return (uint16_t)(a > b ? a - b : 0); };
+    auto sat_add16 = [](uint16_t a, uint16_t b) { uint32_t r = (uint32_t)a + b; return (uint16_t)(r > 0xFFFF ? 0xFFFF : r); };
+    SV gex = A.splat(sc.gap_extend_penalty);
+    SV gop = A.splat(sat_sub16(sc.gap_open_penalty, sc.gap_extend_penalty));
+    SV match_score = A.splat(sat_add16(sc.match_score, sc.mismatch_penalty));
+    SV mismatch = A.splat(sc.mismatch_penalty);
+    SV case_bonus = A.splat(sc.matching_case_bonus);
+    SV cap_bonus = A.splat(sc.capitalization_bonus);
+    SV delim_bonus = A.splat(sc.delimiter_bonus);
+    SV prefix_masked = include_prefix ? A.first_lane(sc.prefix_bonus) : A.zero();
+    bool prev_chunk_last_delim = false, prev_chunk_last_lower = false;
+    SV maxv = A.zero();
+    const uint16_t FULL = A.full();
+    for (size_t col = 1; col < chunks; col++) {
+        // load_partial: zero-filled tail (scalar.rs:78-85)
+        uint8_t b[kMaxLanes];
+        for (int i = 0; i < lanes; i++) {
+            size_t pos = (col - 1) * lanes + i;
+            b[i] = pos < hl ? hay[pos] : 0;
+        }
+        bool up[kMaxLanes], lo[kMaxLanes], dl[kMaxLanes];
+        for (int i = 0; i < lanes; i++) {
+            up[i] = b[i] < 'Z' + 1 && b[i] > 'A' - 1;
+            lo[i] = b[i] < 'z' + 1 && b[i] > 'a' - 1;
+            bool digit = b[i] > '0' - 1 && b[i] < '9' + 1;
+            dl[i] = !(up[i] || lo[i] || digit || b[i] > 127);
+        }
+        SV cap_m = A.zero(), delim_m = A.zero();
+        for (int i = 0; i < lanes; i++) {
+            bool prev_lower = i == 0 ? prev_chunk_last_lower : lo[i - 1];
+            bool prev_delim = i == 0 ? prev_chunk_last_delim : dl[i - 1];
+            cap_m.v[i] = (up[i] && prev_lower) ? FULL : 0;
+            delim_m.v[i] = (prev_delim && !dl[i]) ? FULL : 0;
+        }
+        prev_chunk_last_lower = lo[lanes - 1];
+        prev_chunk_last_delim = dl[lanes - 1];
+        SV bonuses = A.add(A.add(A.add(A.band(delim_m, delim_bonus), A.band(cap_m, cap_bonus)), prefix_masked), match_score);
+
+        SV up_gap_mask = A.zero();
+        SV prev_row = A.zero();
+        SV row = A.zero();
+        for (size_t r = 1; r <= n; r++) {
+            SV mm = A.zero(), ex = A.zero();
+            for (int i = 0; i < lanes; i++) {
+                bool e = b[i] == needle[r - 1].c;
+                bool f = b[i] == needle[r - 1].flip;
+                mm.v[i] = (e || f) ? FULL : 0;
+                ex.v[i] = e ? FULL : 0;
+            }
+            SV diag = A.srp(prev_row, H[(r - 1) * chunks + (col - 1)], 1);
+            diag = A.add(diag, A.band(mm, bonuses));
+            diag = A.subs(diag, mismatch);
+            diag = A.add(diag, A.band(ex, case_bonus));
+            SV upv = A.subs(A.subs(prev_row, gex), A.band(up_gap_mask, gop));
+            row = propagate(A, A.max(diag, upv), H[r * chunks + (col - 1)], mm, M[r * chunks + (col - 1)], gop, gex);
+            H[r * chunks + col] = row;
+            M[r * chunks + col] = mm;
+            prev_row = row;
+            up_gap_mask = mm;
+        }
+        maxv = A.max(maxv, row);
+        prefix_masked = A.zero();
+    }
+    return A.hmax(maxv);
+}
+
+// src/smith_waterman/mod.rs:91-116 (score_fits_in_u8)
+static size_t max_per_char_bonus(const frz_scoring& s) {  // src/lib.rs:488-494
+    uint16_t bonus = std::max(s.delimiter_bonus, s.capitalization_bonus);
+    uint16_t amort = std::max<uint16_t>((uint16_t)((bonus + 1) / 2), bonus > s.gap_open_penalty ? bonus - s.gap_open_penalty : 0);
+    uint32_t r = (uint32_t)amort + s.matching_case_bonus;
+    return r > 0xFFFF ? 0xFFFF : r;
+}
+static size_t max_one_time_bonus(const frz_scoring& s) {  // src/lib.rs:497-503
+    uint16_t bonus = std::max(s.delimiter_bonus, s.capitalization_bonus);
+    uint16_t amort = std::max<uint16_t>((uint16_t)((bonus + 1) / 2), bonus > s.gap_open_penalty ? bonus - s.gap_open_penalty : 0);
+    return bonus - amort;
+}
+static bool score_fits_in_u8(size_t needle_len, const frz_scoring& s) {
+    size_t max_constant = (size_t)s.match_score + s.mismatch_penalty;
+    max_constant = std::max<size_t>(max_constant, s.gap_open_penalty);
+    max_constant = std::max<size_t>(max_constant, s.gap_extend_penalty);
+    max_constant = std::max<size_t>(max_constant, s.matching_case_bonus);
+    max_constant = std::max<size_t>(max_constant, s.capitalization_bonus);
+    max_constant = std::max<size_t>(max_constant, s.delimiter_bonus);
+    max_constant = std::max<size_t>(max_constant, s.prefix_bonus);
+    if (max_constant > 255) return false;
+    size_t max_gap = 64 * (size_t)s.gap_extend_penalty + s.gap_open_penalty;
+    if (max_gap > 255) return false;
+    size_t max_per_char = (size_t)s.match_score + max_per_char_bonus(s);
+    size_t max_matrix = max_per_char * needle_len + max_one_time_bonus(s) + s.prefix_bonus;
+    return max_matrix + s.mismatch_penalty <= 255;
+}
+
+// src/lib.rs:368-377 (CaseMatching::respects_case_for); ASCII needles only
+static bool respects_case(int casing, const uint8_t* needle, size_t n) {
+    if (casing == FRZ_CASE_IGNORE) return false;
+    if (casing == FRZ_CASE_RESPECT) return true;
+    for (size_t i = 0; i < n; i++)
+        if (needle[i] >= 'A' && needle[i] <= 'Z') return true;
+    return false;
+}
+
+// ---------------------------------------------------------------------------------
+// Literal matcher (ASCII path): src/literal/algo.rs:159-255
+// ---------------------------------------------------------------------------------
+static bool lit_is_delim(uint8_t b) {  // literal/algo.rs:327-330
+    bool alnum = (b >= '0' && b <= '9') || (b >= 'a' && b <= 'z') || (b >= 'A' && b <= 'Z');
+    return b <= 127 && !alnum;
+}
+static bool lit_matches_at(const std::vector<Pair>& nd, const uint8_t* hay, size_t pos) {
+    for (size_t k = 0; k < nd.size(); k++) {
+        uint8_t b = hay[pos + k];
+        if (b != nd[k].c && b != nd[k].flip) return false;
+    }
+    return true;
+}
+static uint16_t lit_score_at(const std::vector<Pair>& nd, const frz_scoring& s, const uint8_t* hay, size_t hl, size_t pos) {
+    uint16_t score = 0;
+    for (size_t k = 0; k < nd.size(); k++) {
+        size_t st = pos + k;
+        uint16_t sc = s.match_score;
+        if (hay[st] == nd[k].c) sc += s.matching_case_bonus;
+        if (st == 0) sc += s.prefix_bonus;
+        else {
+            uint8_t byte = hay[st], prev = hay[st - 1];
+            if (byte >= 'A' && byte <= 'Z' && prev >= 'a' && prev <= 'z') sc += s.capitalization_bonus;
+            if (lit_is_delim(prev) && !lit_is_delim(byte)) sc += s.delimiter_bonus;
+        }
+        score += sc;
+    }
+    if (pos == 0 && nd.size() == hl) score += s.exact_match_bonus;
+    return score;
+}
+// returns false when no match; else pos/score.  Substring: best score, earliest on ties
+// (find_substring, literal/algo.rs:262-313 — the seed prefilter only prunes candidates that
+// matches_at would reject, so a plain scan over every start position is equivalent).
+static bool lit_find(int mode, const std::vector<Pair>& nd, const frz_scoring& s, const uint8_t* hay, size_t hl,
+                     size_t* opos, uint16_t* oscore) {
+    size_t n = nd.size();
+    if (hl < n) return false;
+    switch (mode) {
+        case FRZ_MATCHING_EXACT:
+            if (hl == n && lit_matches_at(nd, hay, 0)) { *opos = 0; *oscore = lit_score_at(nd, s, hay, hl, 0); return true; }
+            return false;
+        case FRZ_MATCHING_PREFIX:
+            if (lit_matches_at(nd, hay, 0)) { *opos = 0; *oscore = lit_score_at(nd, s, hay, hl, 0); return true; }
+            return false;
+        case FRZ_MATCHING_SUFFIX: {
+            size_t pos = hl - n;
+            if (lit_matches_at(nd, hay, pos)) { *opos = pos; *oscore = lit_score_at(nd, s, hay, hl, pos); return true; }
+            return false;
+        }
+        case FRZ_MATCHING_SUBSTRING: {
+            bool have = false;
+            for (size_t pos = 0; pos + n <= hl; pos++) {
+                if (!lit_matches_at(nd, hay, pos)) continue;
+                uint16_t sc = lit_score_at(nd, s, hay, hl, pos);
+                if (!have || sc > *oscore) { have = true; *opos = pos; *oscore = sc; }
+            }
+            return have;
+        }
+    }
+    return false;
+}
+
+// One compiled pattern (src/matcher/mod.rs:193-205 compile + get_backend :448-498)
+struct OPattern {
+    std::vector<uint8_t> needle;
+    bool negated;
+    int max_typos;  // -1 = None
+    int matching;
+    bool case_sensitive;
+    frz_scoring scoring;
+    int lanes;        // SW lanes for the selected width
+    int pf_lanes;     // prefilter lanes
+    bool u8;
+    size_t min_hay_len;
+    bool unsupported;
+};
+
+// src/matcher/algo.rs:78-103 (match_list_into_impl) + :229-263 (smith_waterman_one) + :331-338 (trim)
+// and src/literal/algo.rs:84-116 for literal modes.
+static void match_list_into(const OPattern& p, const uint8_t* bytes, const uint64_t* offsets, uint64_t n,
+                            uint32_t index_offset, std::vector<frz_match>& out) {
+    std::vector<Pair> nd = case_needle(p.needle.data(), p.needle.size(), p.case_sensitive);
+    for (uint64_t i = 0; i < n; i++) {
+        const uint8_t* hay = bytes + offsets[i];
+        size_t hl = (size_t)(offsets[i + 1] - offsets[i]);
+        uint32_t index = index_offset + (uint32_t)i;
+        if (p.matching != FRZ_MATCHING_FUZZY) {
+            size_t pos; uint16_t sc;
+            if (lit_find(p.matching, nd, p.scoring, hay, hl, &pos, &sc))
+                out.push_back({index, sc, (uint8_t)(pos == 0 && nd.size() == hl), 0});
+            continue;
+        }
+        if (hl < p.min_hay_len) continue;
+        size_t s, e;
+        if (!prefilter(nd, hay, hl, p.max_typos, p.pf_lanes, &s, &e)) continue;
+        s = s > 0 ? s - 1 : 0;
+        bool include_exact = s == 0 && e == hl;
+        const uint8_t* w = hay + s;
+        size_t wl = e - s;
+        uint16_t score = sw_score(p.needle.data(), p.needle.size(), p.scoring, p.case_sensitive, w, wl, s == 0, p.lanes, p.u8);
+        bool exact = include_exact && wl == p.needle.size() && memcmp(w, p.needle.data(), wl) == 0;
+        if (exact) score = (uint16_t)(score + p.scoring.exact_match_bonus);
+        out.push_back({index, score, (uint8_t)exact, 0});
+    }
+}
+
+// src/sort.rs:6-40 (radix_sort_matches) — literal 2-pass LSD radix
+static void radix_sort_matches(frz_match* m, size_t n) {
+    std::vector<frz_match> b(n);
+    uint32_t hist[256] = {0}, off[256] = {0};
+    for (size_t i = 0; i < n; i++) hist[m[i].score & 0xFF]++;
+    for (int idx = 255; idx >= 1; idx--) off[idx - 1] = off[idx] + hist[idx];
+    for (size_t i = 0; i < n; i++) b[off[m[i].score & 0xFF]++] = m[i];
+    memset(hist, 0, sizeof hist);
+    for (size_t i = 0; i < n; i++) hist[(b[i].score >> 8) & 0xFF]++;
+    off[255] = 0;
+    for (int idx = 255; idx >= 1; idx--) off[idx - 1] = off[idx] + hist[idx];
+    for (size_t i = 0; i < n; i++) m[off[(b[i].score >> 8) & 0xFF]++] = b[i];
+}
+
+// src/matcher/multi.rs:84-152 (match_list_multi_into)
+static void match_list_multi_into(const std::vector<OPattern>& pats, const uint8_t* bytes, const uint64_t* offsets,
+                                  uint64_t n, uint32_t index_offset, std::vector<frz_match>& out) {
+    int base = -1;
+    for (size_t i = 0; i < pats.size(); i++)
+        if (!pats[i].negated) { base = (int)i; break; }
+    std::vector<frz_match> cand;
+    if (base >= 0) match_list_into(pats[base], bytes, offsets, n, index_offset, cand);
+    else
+        for (uint64_t i = 0; i < n; i++) cand.push_back({index_offset + (uint32_t)i, 0, 0, 0});
+    for (size_t pi = 0; pi < pats.size(); pi++) {
+        if ((int)pi == base || cand.empty()) continue;
+        // gather candidates
+        std::vector<uint8_t> gb;
+        std::vector<uint64_t> go{0};
+        for (auto& c : cand) {
+            uint64_t i = c.index - index_offset;
+            gb.insert(gb.end(), bytes + offsets[i], bytes + offsets[i + 1]);
+            go.push_back(gb.size());
+        }
+        std::vector<frz_match> hits;
+        match_list_into(pats[pi], gb.data(), go.data(), cand.size(), 0, hits);
+        if (pats[pi].negated) {
+            std::vector<frz_match> keep;
+            size_t h = 0;
+            for (size_t pos = 0; pos < cand.size(); pos++) {
+                bool matched = h < hits.size() && hits[h].index == pos;
+                if (matched) h++;
+                else keep.push_back(cand[pos]);
+            }
+            cand.swap(keep);
+        } else {
+            std::vector<frz_match> next;
+            for (auto hit : hits) {
+                frz_match c = cand[hit.index];
+                hit.index = c.index;
+                uint32_t s = (uint32_t)hit.score + c.score;
+                hit.score = (uint16_t)(s > 0xFFFF ? 0xFFFF : s);
+                hit.exact |= c.exact;
+                next.push_back(hit);
+            }
+            cand.swap(next);
+        }
+    }
+    out.insert(out.end(), cand.begin(), cand.end());
+}
+
+// src/matcher/mod.rs:193-205,448-498 + src/pattern.rs:250-262 (resolve)
+static bool compile(const frz_pattern& src, const frz_config& cfg, OPattern* o) {
+    if (src.needle_len == 0) return false;
+    o->needle.assign(src.needle, src.needle + src.needle_len);
+    o->negated = src.negated != 0;
+    o->max_typos = src.max_typos >= 0 ? src.max_typos : cfg.max_typos;
+    int casing = src.casing >= 0 ? src.casing : cfg.casing;
+    o->matching = src.matching >= 0 ? src.matching : cfg.matching;
+    o->scoring = src.has_scoring ? src.scoring : cfg.scoring;
+    o->case_sensitive = respects_case(casing, src.needle, src.needle_len);
+    int unicode = src.unicode >= 0 ? src.unicode : cfg.unicode;
+    bool ascii = true;
+    size_t nchars = 0;
+    for (size_t i = 0; i < src.needle_len; i++) {
+        if (src.needle[i] >= 0x80) ascii = false;
+        if ((src.needle[i] & 0xC0) != 0x80) nchars++;
+    }
+    // UnicodeMatching::respects_unicode_for (src/lib.rs:394-401): the unicode kernels are not restated
+    o->unsupported = (unicode == FRZ_UNICODE_ALWAYS) || (unicode == FRZ_UNICODE_SMART && !ascii);
+    int lanes8 = cfg.emulate_lanes ? cfg.emulate_lanes : 64;
+    o->u8 = score_fits_in_u8(src.needle_len, o->scoring);
+    o->lanes = o->u8 ? lanes8 : lanes8 / 2;
+    o->pf_lanes = lanes8;  // Prefilter{AVX512,AVX,SSE,Scalar} LANES = 64/32/16/16
+    // min_haystack_len (src/matcher/algo.rs:62-65): needle.chars().count() - max_typos
+    o->min_hay_len = o->max_typos >= 0 ? (nchars > (size_t)o->max_typos ? nchars - o->max_typos : 0) : 0;
+    return true;
+}
+
+}  // namespace
+
+extern "C" {
+
+// ---- unit-level entry points (used by the KAT tests) ----
+
+int frzo_prefilter(const uint8_t* needle, size_t n, int case_sensitive, const uint8_t* hay, size_t len,
+                   int max_typos, int lanes, uint64_t* start, uint64_t* end) {
+    std::vector<Pair> nd = case_needle(needle, n, case_sensitive != 0);
+    size_t s = 0, e = 0;
+    bool ok = prefilter(nd, hay, len, max_typos, lanes, &s, &e);
+    *start = s;
+    *end = e;
+    return ok ? 1 : 0;
+}
+
+uint16_t frzo_sw_score(const uint8_t* needle, size_t n, const frz_scoring* sc, int case_sensitive,
+                       const uint8_t* hay, size_t len, int include_prefix, int lanes, int score_bits) {
+    return sw_score(needle, n, *sc, case_sensitive != 0, hay, len, include_prefix != 0, lanes, score_bits == 8);
+}
+
+int frzo_match_greedy(const uint8_t* needle, size_t n, const frz_scoring* sc, int case_sensitive,
+                      const uint8_t* hay, size_t len, int include_prefix) {
+    return match_greedy(needle, n, hay, len, *sc, case_sensitive != 0, include_prefix != 0);
+}
+
+int frzo_score_fits_in_u8(size_t needle_len, const frz_scoring* sc) { return score_fits_in_u8(needle_len, *sc) ? 1 : 0; }
+
+void frzo_radix_sort_matches(frz_match* m, uint64_t n) { radix_sort_matches(m, (size_t)n); }
+
+// ---- pipeline entry points ----
+
+// Matcher::match_list_into on all patterns (index order, no sort).  Returns the number of
+// matches (which may exceed cap; only the first cap are written).
+uint64_t frzo_match_list_into(const frz_pattern* patterns, size_t np, const frz_config* cfg, const uint8_t* bytes,
+                              const uint64_t* offsets, uint64_t n, uint32_t index_offset, frz_match* out, uint64_t cap) {
+    std::vector<OPattern> pats;
+    for (size_t i = 0; i < np; i++) {
+        OPattern o;
+        if (compile(patterns[i], *cfg, &o)) {
+            if (o.unsupported) return UINT64_MAX;  // unicode-needle path not restated
+            pats.push_back(o);
+        }
+    }
+    std::vector<frz_match> res;
+    if (pats.empty()) {  // CompiledPatterns::Empty (src/matcher/mod.rs:380-383)
+        for (uint64_t i = 0; i < n; i++) res.push_back({index_offset + (uint32_t)i, 0, 0, 0});
+    } else if (pats.size() == 1 && !pats[0].negated) {
+        match_list_into(pats[0], bytes, offsets, n, index_offset, res);
+    } else {
+        match_list_multi_into(pats, bytes, offsets, n, index_offset, res);
+    }
+    for (uint64_t i = 0; i < res.size() && i < cap; i++) out[i] = res[i];
+    return res.size();
+}
+
+// Matcher::match_list (src/matcher/mod.rs:212-222): into + reverse? + radix sort?
+uint64_t frzo_match_list(const frz_pattern* patterns, size_t np, const frz_config* cfg, const uint8_t* bytes,
+                         const uint64_t* offsets, uint64_t n, frz_match* out, uint64_t cap) {
+    std::vector<frz_match> tmp(n ? n : 1);
+    uint64_t cnt = frzo_match_list_into(patterns, np, cfg, bytes, offsets, n, 0, tmp.data(), n);
+    if (cnt == UINT64_MAX) return cnt;
+    bool empty = true;
+    for (size_t i = 0; i < np; i++)
+        if (patterns[i].needle_len) empty = false;
+    bool reversed = cfg->sort == FRZ_SORT_INDEX_DESC || cfg->sort == FRZ_SORT_SCORE_THEN_INDEX_DESC;
+    bool by_score = cfg->sort == FRZ_SORT_SCORE_THEN_INDEX_ASC || cfg->sort == FRZ_SORT_SCORE_THEN_INDEX_DESC;
+    if (reversed) std::reverse(tmp.begin(), tmp.begin() + cnt);
+    if (!empty && by_score) radix_sort_matches(tmp.data(), cnt);
+    for (uint64_t i = 0; i < cnt && i < cap; i++) out[i] = tmp[i];
+    return cnt;
+}
+
+}  // extern "C"

@@ -1,0 +1,407 @@
+"""Pins the CPU oracle (oracle/frz_oracle.cpp) against every known-answer vector the reference's
+own tests hold for the match_list path.  Each block names the reference test it restates
+(paths relative to the reference crate root).  CPU-only."""
+import itertools
+import random
+
+import numpy as np
+import pytest
+
+from frizbee_b200.types import (CaseMatching, Config, Match, Matching, Pattern, Scoring, SortStrategy,
+                                UnicodeMatching)
+from oracle import pyoracle as O
+
+MATCH, MISMATCH, GAP_OPEN, GAP_EXT = 12, 6, 5, 1
+PREFIX, DELIM, CAP, CASE, EXACT = 12, 4, 4, 4, 8
+CHAR = MATCH + CASE
+
+# every (lanes, score_bits) pair a reference backend has (src/smith_waterman/backend/scalar.rs:440-497,
+# avx.rs, avx512.rs, sse.rs, neon.rs)
+ALL_BACKENDS = [(8, 16), (16, 16), (32, 16), (16, 8), (32, 8), (64, 8)]
+
+
+def score(needle, hay, lanes=8, bits=16, **kw):
+    return O.sw_score(needle, hay, lanes=lanes, score_bits=bits, **kw)
+
+
+# ---- src/smith_waterman/mod.rs:208-299, 421-440 (symbolic KATs, BackendScalar8 == 8 x u16) ----
+SW_KATS = [
+    ("b", "abc", CHAR), ("c", "abc", CHAR),
+    ("a", "abc", CHAR + PREFIX), ("a", "aabc", CHAR + PREFIX), ("a", "babc", CHAR),
+    ("a", "a", CHAR + PREFIX), ("abc", "abc", 3 * CHAR + PREFIX),
+    ("-", "a--bc", CHAR), ("b", "a-b", CHAR + DELIM), ("a", "a-b-c", CHAR + PREFIX),
+    ("b", "a--b", CHAR + DELIM), ("c", "a--bc", CHAR), ("a", "-a--bc", CHAR + DELIM),
+    ("-", "a-bc", CHAR),
+    ("test", "Uteost", CHAR * 4 - GAP_OPEN),
+    ("test", "Uteoost", CHAR * 4 - GAP_OPEN - GAP_EXT),
+    ("test", "Utooooeoooosoooot", CHAR * 4 - GAP_OPEN * 3 - GAP_EXT * 9),
+    ("test", "Utooooooeoooooosoooooot", CHAR * 4 - GAP_OPEN * 3 - GAP_EXT * 15),
+    ("a", "A", MATCH + PREFIX), ("A", "Aa", CHAR + PREFIX),
+    ("D", "forDist", CHAR + CAP), ("D", "foRDist", CHAR), ("D", "FOR_DIST", CHAR + DELIM),
+    # test_score_typos (score half only; typo counting needs traceback which match_list never does)
+    ("foo", "Ufooo", CHAR * 3), ("foo", "Ufo", CHAR * 2 - GAP_OPEN),
+    ("foo", "Uf", CHAR - GAP_OPEN - GAP_EXT), ("foo", "U", 0),
+]
+
+
+@pytest.mark.parametrize("needle,hay,want", SW_KATS)
+def test_sw_symbolic_kats(needle, hay, want):
+    assert score(needle, hay) == want
+
+
+def test_sw_inequalities():
+    # src/smith_waterman/mod.rs:254,303-325,343-361
+    assert score("a_b", "a_bb") > score("a_b", "a__b")
+    assert score("swap", "swap(test)") > score("swap", "iter_swap(test)")
+    assert score("_", "_private_member") > score("_", "public_member")
+    assert score("H", "HELLO") > score("H", "fooHello")
+    assert score("foo", "fooo") > score("foo", "f_o_o_o")
+    assert score("fo", "foo") > score("fo", "faOo")
+    assert score("abc", "a111bc") > score("abc", "a1b1c")
+    assert score("b", "b") > score("b", "a-b") > score("b", "ab")
+    assert score("B", "aB") > score("b", "aB")
+    # case_sensitive_scoring_rejects_folded_bytes (:363-374), score half
+    assert score("A", "A", case_sensitive=True) == CHAR + PREFIX
+    assert score("A", "a", case_sensitive=False) == MATCH + PREFIX
+
+
+def test_sw_long_input_boundaries():
+    # src/smith_waterman/mod.rs:498-511: 1023/1024 use the matrix, 1025 the greedy fallback
+    for ln in (1023, 1024, 1025):
+        hay = "x" * (ln - 3) + "abc"
+        assert score("abc", hay) == 3 * CHAR, ln
+
+
+# ---- src/smith_waterman/backend/tests/parity.rs:95-124,184-190: every backend == Scalar-u16 ----
+PARITY_CASES = [
+    ("a", "abc"), ("abc", "abc"), ("foo", "fooBar"), ("foo", "012345foo"), ("foo", "01234567foo"),
+    ("foo", "0123456789foo"), ("foo", "0123456789012345foo"), ("foo", "0123456789012345678901234567foo"),
+    ("test", "Utooooeoooosoooot"), ("test", "Utooooooeoooooosoooooot"), ("foo", "Ufooo"), ("foo", "Ufo"),
+    ("hw", "hello_world"), ("fBr", "fooBar"), ("D", "FOR_DIST"), ("needle", "____________needle____________"),
+    ("abcdefghij", "abcdefghij"), ("abcdefghijklmnopqrst", "abcdefghijklmnopqrst"),
+]
+# SURVEY.md §8(c) restatement-derived values for the same list
+PARITY_VALUES = {("a", "abc"): 28, ("abc", "abc"): 60, ("foo", "fooBar"): 60, ("foo", "012345foo"): 48,
+                 ("test", "Utooooeoooosoooot"): 40, ("test", "Utooooooeoooooosoooooot"): 34,
+                 ("foo", "Ufooo"): 48, ("foo", "Ufo"): 27, ("hw", "hello_world"): 39, ("fBr", "fooBar"): 53,
+                 ("D", "FOR_DIST"): 20, ("needle", "____________needle____________"): 100,
+                 ("abcdefghij", "abcdefghij"): 172}
+
+
+@pytest.mark.parametrize("needle,hay", PARITY_CASES)
+def test_sw_cross_backend_parity(needle, hay):
+    want = score(needle, hay, 8, 16)
+    if (needle, hay) in PARITY_VALUES:
+        assert want == PARITY_VALUES[(needle, hay)]
+    for lanes, bits in ALL_BACKENDS:
+        if bits == 8 and not O.score_fits_in_u8(len(needle)):
+            continue
+        assert score(needle, hay, lanes, bits) == want, (lanes, bits)
+
+
+def test_score_fits_in_u8():
+    # src/smith_waterman/mod.rs:522-532, src/matcher/mod.rs:751-785
+    assert O.score_fits_in_u8(4)
+    assert O.score_fits_in_u8(3) and O.score_fits_in_u8(13)
+    assert not O.score_fits_in_u8(14) and not O.score_fits_in_u8(20)
+    assert not O.score_fits_in_u8(4, Scoring(gap_extend_penalty=8))
+
+
+# ---- lane-dependence evidence; the oracle must show it, not hide it ----
+def test_sw_is_lane_dependent_on_known_vectors():
+    a = [score("ab_", "-1Abb1-aabB1-bbaAa-_bb/b0ABB/-0/Aa-a0a/1_/", l, 8) for l in (16, 32, 64)]
+    assert a == [35, 34, 34]
+    b = [score("eyqoof", "eA21viFrVA1k7gylcKJMa0amSvnEEVFU2YBOO9UgbFmrjkBzK0jo6ge", l, 8) for l in (16, 32, 64)]
+    assert b == [45, 45, 42]
+    # padding lanes can hold the maximum
+    assert score("babb0_", "Bab", 64, 8) == 48
+
+
+# ---- src/prefilter/mod.rs:188-278 ----
+PF_ORDERED = [
+    ("foo", "foo", 0, True), ("foo", "f_o_o", 0, True), ("foo", "FOO", 0, True), ("abc", "xaxbxcx", 0, True),
+    ("fo", "_______________fo", 0, True), ("foo", "f_______________o_______________o", 0, True),
+    ("foo", "oof", 0, False), ("abc", "cba", 0, False), ("foo", "fo", 0, False),
+    ("foo", "f_________________________o______", 0, False), ("a", "", 0, False), ("\0", "abc", 0, False),
+    ("aa", "a", 0, False),
+]
+PF_TYPOS = [
+    ("abc", "", 2, False), ("abc", "", 3, True), ("abc", "bc", 1, True), ("abc", "ac", 1, True),
+    ("abc", "ab", 1, True), ("bar", "ba", 1, True), ("bar", "ar", 1, True), ("hello", "hll", 2, True),
+    ("abcdef", "abdf", 2, True), ("TeSt", "ES", 2, True), ("abc", "c", 2, True), ("a\0b", "ab", 1, True),
+    ("foo", "fo", 5, True), ("abc", "a_______________b", 1, True),
+    ("test", "t_______________s_______________t", 1, True),
+    ("d63NacaDJaaaa", "63aeeaaaeeaaaaaaaNacaDJaaAa", 1, True), ("bar", "rb", 1, False),
+    ("abcdef", "fcda", 2, False), ("TeSt", "ES", 1, False), ("abc", "cba", 1, False), ("abc", "cba", 2, True),
+    ("aaa", "aa", 0, False), ("aaa", "aa", 1, True), ("aba", "aa", 1, True), ("aaba", "aba", 1, True),
+]
+PF_SENSITIVE = [
+    ("foo", "foo", 0, True), ("foo", "FOO", 0, False), ("FoO", "xxFoOxx", 0, True), ("abc", "xaxbxcx", 0, True),
+    ("abc", "xAxBxCx", 0, False), ("TeSt", "eS", 2, True), ("TeSt", "ES", 2, False), ("Ab", "b", 1, True),
+    ("Ab", "ab", 0, False), ("Ab", "ab", 1, True),
+]
+
+
+@pytest.mark.parametrize("lanes", [16, 32, 64])
+def test_prefilter_boolean_kats(lanes):
+    for needle, hay, k, want in PF_ORDERED + PF_TYPOS:
+        assert O.prefilter(needle, hay, k, lanes)[0] == want, (needle, hay, k)
+    for needle, hay, k, want in PF_SENSITIVE:
+        assert O.prefilter(needle, hay, k, lanes, case_sensitive=True)[0] == want, (needle, hay, k)
+
+
+@pytest.mark.parametrize("lanes", [16, 32, 64])
+def test_prefilter_windows(lanes):
+    # returned_windows_are_conservative (src/prefilter/mod.rs:272-278)
+    assert O.prefilter("foo", "xxfooxfoo", 0, lanes) == (True, 2, 9)
+    assert O.prefilter("abc", "xxaybzczz", 0, lanes) == (True, 2, 7)
+    assert O.prefilter("abcd", "xxaydz", 2, lanes) == (True, 2, 5)
+    assert O.prefilter("abc", "xyz", 3, lanes) == (True, 0, 3)
+
+
+def _lcs(needle: bytes, hay: bytes, case_sensitive: bool) -> int:
+    # src/prefilter/mod.rs:1025-1047
+    def eq(a, b):
+        if a == b:
+            return True
+        if case_sensitive:
+            return False
+        return bytes([a]).lower() == bytes([b]).lower() and (65 <= a <= 90 or 97 <= a <= 122)
+    prev = [0] * (len(hay) + 1)
+    for nb in needle:
+        cur = [0] * (len(hay) + 1)
+        for i, hb in enumerate(hay):
+            cur[i + 1] = prev[i] + 1 if eq(nb, hb) else max(prev[i + 1], cur[i])
+        prev = cur
+    return prev[len(hay)]
+
+
+def _lcs_oracle(needle, hay, k, cs):
+    return True if k >= len(needle) else _lcs(needle, hay, cs) + k >= len(needle)
+
+
+def test_prefilter_lcs_oracle_chunk_boundaries():
+    # reference_oracle_chunk_boundaries (src/prefilter/mod.rs:472-503)
+    for prefix_len in (0, 1, 7, 8, 15, 16, 31, 32, 63, 64):
+        hay = b"x" * prefix_len + b"abc"
+        for needle, k, want in (("abc", 0, True), ("ac", 0, True), ("abcd", 0, False), ("abcd", 1, True)):
+            assert _lcs_oracle(needle.encode(), hay, k, False) == want
+            for lanes in (16, 32, 64):
+                assert O.prefilter(needle, hay, k, lanes)[0] == want, (prefix_len, needle, k, lanes)
+
+
+def _cursor_case(rng):
+    """Structured random case in the spirit of ByteCursor (generator.rs:20-119): dense fuzz alphabet,
+    lengths biased toward chunk boundaries."""
+    alpha = b"a /.,_-:" + bytes(range(97, 123)) + bytes(range(65, 91)) + b"0123456789"
+    bounds = [0, 1, 7, 8, 15, 16, 31, 32, 63, 64, 65, 127, 128]
+    nlen = max(1, rng.choice(bounds[:9]) if rng.random() < 0.25 else rng.randint(1, 24))
+    hlen = rng.choice(bounds) if rng.random() < 0.25 else rng.randint(0, 160)
+    dense = rng.random() < 0.5
+    pool = b"abAB_/-ab01" if dense else alpha
+    needle = bytes(rng.choice(pool) for _ in range(nlen))
+    hay = bytes(rng.choice(pool) for _ in range(hlen))
+    return needle, hay
+
+
+def test_prefilter_randomized_vs_lcs_and_cross_lane_membership():
+    # randomized_backend_parity_and_oracle (src/prefilter/mod.rs:894-908) asserts matched ⇔ LCS + k ≥ len
+    # on 256 proptest cases.  Restated literally, the k ≥ 1 state machines are greedy path trackers:
+    # they never accept a haystack the LCS test rejects, but on dense adversarial alphabets they miss a
+    # few it accepts, and WHICH ones depends on LANES (SURVEY.md §8(a) found the same, independently).
+    # So: k = 0 must equal LCS exactly at every LANES; k ≥ 1 must be sound, and nearly complete.
+    rng = random.Random(1234)
+    misses = lane_dependent = total_typo = 0
+    for _ in range(4000):
+        needle, hay = _cursor_case(rng)
+        k = rng.choice([0, 0, 1, 1, 2, 3, 5])
+        cs = rng.random() < 0.3
+        want = _lcs_oracle(needle, hay, k, cs)
+        res = [O.prefilter(needle, hay, k, lanes, case_sensitive=cs) for lanes in (16, 32, 64)]
+        for r in res:
+            if r[0]:
+                assert want, (needle, hay, k, cs, res)  # sound at every k
+                assert r[1] <= r[2] <= len(hay)
+            if k == 0:
+                assert r[0] == want, (needle, hay, k, cs, res)
+        if k == 0 and want:
+            assert len(set(res)) == 1, (needle, hay, res)  # k=0 window is lane-independent (closed form)
+        if k > 0 and want:
+            total_typo += 1
+            misses += sum(1 for r in res if not r[0])
+            lane_dependent += len({r[0] for r in res}) != 1
+    assert total_typo > 500
+    assert misses / (3 * total_typo) < 0.02, (misses, total_typo)
+
+
+def test_prefilter_k0_closed_form():
+    # the chunked 0-typo prefilter equals a chunk-independent closed form
+    rng = random.Random(99)
+    for _ in range(3000):
+        needle, hay = _cursor_case(rng)
+        pairs = [(c, c ^ 0x20 if (65 <= c <= 90 or 97 <= c <= 122) else c) for c in needle]
+        ni, start = 0, None
+        for j, b in enumerate(hay):
+            if ni < len(needle) and b in pairs[ni]:
+                if ni == 0:
+                    start = j
+                ni += 1
+        ok = ni == len(needle) and len(hay) > 0
+        for lanes in (16, 32, 64):
+            got = O.prefilter(needle, hay, 0, lanes)
+            assert got[0] == ok
+            if ok:
+                end = 1 + max(j for j, b in enumerate(hay) if b in pairs[-1])
+                assert got == (True, start, end)
+
+
+# ---- src/smith_waterman/greedy.rs:112-192 ----
+def test_greedy_kats():
+    g = O.match_greedy
+    assert g("b", "abc") == CHAR and g("c", "abc") == CHAR
+    assert g("a", "abc") == CHAR + PREFIX and g("a", "babc") == CHAR
+    assert g("abc", "ab") is None
+
+
+# ---- src/matcher/mod.rs:533-593 ----
+HAY4 = ["deadbeef", "deadbf", "deadbeefg", "deadbe"]
+
+
+@pytest.mark.parametrize("lanes", [16, 32, 64])
+def test_matcher_basic(lanes):
+    cfg = Config(max_typos=None, emulate_lanes=lanes)
+    m = O.match_list("deadbe", HAY4, cfg)
+    assert [x.index for x in m] == [3, 0, 2, 1]
+    assert [x.score for x in m] == [116, 108, 108, 87]  # SURVEY.md §8(c) restated scores
+    m0 = O.match_list("deadbe", HAY4, Config(max_typos=0, emulate_lanes=lanes))
+    assert len(m0) == 3
+    ex = [x for x in m0 if x.exact]
+    assert len(ex) == 1 and ex[0].index == 3
+    hay7 = ["deadbe", "deadbeef", "deadbe", "deadbf", "deadbe", "deadbeefg", "deadbe"]
+    m7 = O.match_list("deadbe", hay7, Config(emulate_lanes=lanes))
+    assert sorted(x.index for x in m7 if x.exact) == [0, 2, 4, 6]
+    m1 = O.match_list("1", ["1"], Config(max_typos=2, emulate_lanes=lanes))
+    assert len(m1) == 1 and m1[0].index == 0 and m1[0].exact
+
+
+def test_matcher_case_modes():
+    # test_case_sensitive_matching (src/matcher/mod.rs:618-654)
+    hay = ["foo", "FOO", "fOo", "xxfooxx"]
+    idx = lambda ms: [m.index for m in ms]
+    assert idx(O.match_list("foo", hay, Config(sort=SortStrategy.IndexAsc))) == [0, 1, 2, 3]
+    assert idx(O.match_list("foo", hay, Config(sort=SortStrategy.IndexAsc, casing=CaseMatching.Respect))) == [0, 3]
+    assert idx(O.match_list("FoO", ["foo", "FOO", "FoO", "xxFoOxx"], Config(sort=SortStrategy.IndexAsc))) == [2, 3]
+    # unsorted_output_preserves_candidate_order (src/matcher/algo.rs:443-456)
+    assert idx(O.match_list("foo", ["foo", "nomatch", "xfoo", "f_o_o", "bar"], Config(sort=SortStrategy.IndexAsc))) == [0, 2, 3]
+    # test_empty_needle (src/matcher/mod.rs:731-747)
+    assert idx(O.match_list("", ["foo", "bar"])) == [0, 1]
+
+
+def test_config1_expected_output():
+    # BASELINE.json configs[0]; SURVEY.md §8(c) "C1 expected output"
+    hay = ["fooBar", "foo_bar", "barfoo", "prelude", "println!"]
+    for lanes in (16, 32, 64):
+        assert O.match_list("fBr", hay, Config(emulate_lanes=lanes)) == [Match(score=53, index=0, exact=False)]
+
+
+def test_scoring_edge_cases():
+    # src/matcher/algo.rs:344-436
+    zero = Scoring(0, 0, 0, 0, 0, 0, 0, 0, 0)
+    O.match_list("foo", ["foobar"], Config(scoring=zero))
+    O.match_list("foo", ["foobar", "fabco"], Config(scoring=Scoring(gap_open_penalty=1, gap_extend_penalty=5)))
+    sc = lambda mp: O.match_list("abc", ["aXc"], Config(max_typos=1, scoring=Scoring(mismatch_penalty=mp)))[0].score
+    assert sc(260) <= sc(255)
+    cap = Scoring(match_score=40, capitalization_bonus=40, mismatch_penalty=0, gap_open_penalty=0,
+                  gap_extend_penalty=0, prefix_bonus=0, matching_case_bonus=0, exact_match_bonus=0, delimiter_bonus=0)
+    assert O.match_list("BBBB", ["aBaBaBaB"], Config(scoring=cap))[0].score == 4 * 80
+    # greedy_fallback_membership (…:394-408): window > 1024 → greedy can't find 'c' → score 0, still listed
+    hay = "a" + "z" * 1100 + "b"
+    m = O.match_list("abc", [hay], Config(max_typos=1))
+    assert len(m) == 1 and m[0].score == 0
+
+
+# ---- src/matcher/multi.rs:172-229 and doc-test src/matcher/mod.rs:101-103 ----
+def P(needle, negated=False, matching=None, **kw):
+    return Pattern(needle=needle, negated=negated, matching=matching, **kw)
+
+
+def test_multi_pattern():
+    asc = Config(sort=SortStrategy.IndexAsc)
+    idx = lambda ms: [m.index for m in ms]
+    hay = ["foobar", "foo", "barfoo", "bar", "qux"]
+    assert idx(O.match_list([P("foo"), P("bar", True, Matching.Substring)], hay, asc)) == [1]
+    hay = ["foo/bar", "bar/foo", "foo", "foobar"]
+    assert idx(O.match_list([P("foo"), P("bar", True, Matching.Prefix)], hay, asc)) == [0, 2, 3]
+    assert idx(O.match_list([P("foo"), P("bar", True, Matching.Suffix)], hay, asc)) == [1, 2]
+    hay = ["foo", "xfoox", "bar"]
+    single = O.match_list("foo", hay, asc)
+    comb = O.match_list([P("foo"), P("foo")], hay, asc)
+    assert [(c.index, c.score, c.exact) for c in comb] == [(s.index, 2 * s.score, s.exact) for s in single]
+    hay = ["foo", "bar", "xfoox", "qux"]
+    m = O.match_list([P("foo", True, Matching.Substring)], hay, asc)
+    assert idx(m) == [1, 3] and all(x.score == 0 for x in m)
+    assert idx(O.match_list([P("foo", True, Matching.Substring), P("qux", True, Matching.Substring)], hay, asc)) == [1]
+    assert O.match_list([P("foo"), P("foo", True, Matching.Substring)], ["foo", "foobar"]) == []
+    m = O.match_list([P("foo"), P("bar")], ["xfoobarx", "foobar", "zzz"])
+    assert len(m) == 2 and m[0].index == 1 and m[0].score >= m[1].score
+    assert len(O.match_list([P("foo"), P("bar", True, Matching.Prefix)], ["foo", "barfoo", "foobar"])) == 2
+    # pattern_max_typos_override_* (…:333-366), multi_pattern_smart_case_per_pattern (:386-394)
+    cfg0 = Config(max_typos=0, sort=SortStrategy.IndexAsc)
+    assert O.match_list([P("helloz")], ["hello", "world"], cfg0) == []
+    assert idx(O.match_list([P("helloz", max_typos=1)], ["hello", "world"], cfg0)) == [0]
+    assert idx(O.match_list([P("foo"), P("barz", max_typos=1)], ["foo bar", "fox bar"], cfg0)) == [0]
+    assert idx(O.match_list([P("Foo"), P("bar")], ["Foo BAR", "foo bar"], asc)) == [0]
+    # from_patterns_empty_patterns_match_everything (:405-413)
+    assert len(O.match_list([], ["foo", "bar"])) == 2
+
+
+# ---- src/literal/mod.rs:54-200 ----
+def test_literal_modes():
+    asc = lambda mode, **kw: Config(matching=mode, sort=SortStrategy.IndexAsc, **kw)
+    idx = lambda ms: [m.index for m in ms]
+    m = O.match_list("foo", ["foo", "foobar", "xfoo", "FOO"], asc(Matching.Exact))
+    assert idx(m) == [0, 3] and all(x.exact for x in m)
+    hay = ["foobar", "barfoo", "foo", "xfoobar"]
+    assert idx(O.match_list("foo", hay, asc(Matching.Prefix))) == [0, 2]
+    assert idx(O.match_list("foo", hay, asc(Matching.Suffix))) == [1, 2]
+    assert idx(O.match_list("bar", ["xxbarxx", "bar", "nope", "foo_bar"], asc(Matching.Substring))) == [0, 1, 3]
+    for needle, hay in (("foo", "foo"), ("foo", "foobar"), ("fooBar", "fooBarBaz"), ("a", "abc")):
+        fz = O.match_list(needle, [hay])[0].score
+        assert O.match_list(needle, [hay], Config(matching=Matching.Prefix))[0].score == fz
+    assert O.match_list("foo", ["foo"], Config(matching=Matching.Exact))[0].score == O.match_list("foo", ["foo"])[0].score
+    sub = lambda n, h: O.match_list(n, [h], asc(Matching.Substring))[0].score
+    assert sub("bar", "foobar") == 3 * CHAR and sub("bar", "foo_bar") == 3 * CHAR + DELIM
+    assert sub("ab", "ab_ab") == 2 * CHAR + PREFIX
+    hay = ["foo", "FOO", "fOo"]
+    assert idx(O.match_list("foo", hay, asc(Matching.Prefix, casing=CaseMatching.Respect))) == [0]
+    assert idx(O.match_list("foo", hay, asc(Matching.Prefix))) == [0, 1, 2]
+    for mode in (Matching.Substring, Matching.Prefix, Matching.Suffix, Matching.Exact):
+        assert O.match_list("abcd", ["abc"], asc(mode)) == []
+    for pl in (0, 1, 7, 8, 15, 16, 31, 32, 63, 64, 65):
+        assert idx(O.match_list("bar", ["x" * pl + "bar"], asc(Matching.Substring))) == [0]
+
+
+# ---- src/sort.rs:47-65, src/lib.rs:172-185, tests/api_properties.rs:690-741 ----
+def test_radix_sort_and_strategies():
+    rng = np.random.default_rng(7)
+    n = 1 << 16
+    arr = np.zeros(n, dtype=O.MATCH_DTYPE)
+    arr["index"] = np.arange(n)
+    arr["score"] = rng.integers(0, 65536, n)
+    out = O.radix_sort_matches(arr)
+    key = (65535 - out["score"].astype(np.int64)) * (1 << 32) + out["index"]
+    assert np.all(np.diff(key) > 0)
+    hay = ["foo", "xfoo", "foo", "f_o_o", "nomatch", "foo"]
+    asc = O.match_list("foo", hay, Config(sort=SortStrategy.ScoreThenIndexAsc))
+    desc = O.match_list("foo", hay, Config(sort=SortStrategy.ScoreThenIndexDesc))
+    assert sorted(asc, key=lambda m: (-m.score, m.index)) == asc
+    assert sorted(desc, key=lambda m: (-m.score, -m.index)) == desc
+    assert [m.index for m in O.match_list("foo", hay, Config(sort=SortStrategy.IndexDesc))] == [5, 3, 2, 1, 0]
+
+
+def test_unicode_needle_is_flagged_not_faked():
+    with pytest.raises(NotImplementedError):
+        O.match_list("é다😀", ["é다😀"])
+    # UnicodeMatching::Ignore takes the byte path (src/lib.rs:394-399)
+    m = O.match_list("é", ["xxé"], Config(unicode=UnicodeMatching.Ignore, sort=SortStrategy.IndexAsc))
+    assert len(m) == 1
