@@ -1,0 +1,115 @@
+// frz_device.cuh — data layout shared by the kernels and the host runtime.
+//
+// HBM layout of a packed corpus:
+//   * haystacks are taken in input order in TILES of FRZ_TILE = 1024;
+//   * inside a tile the haystacks are stably sorted by their 16-byte unit count
+//     (length bucketing) and laid out in GROUPS of 32 slots — one slot per warp lane;
+//   * a group is stored unit-interleaved (SoA): unit k of lanes 0..31 is one contiguous
+//     512-byte line, so the warp's k-th load is a single fully coalesced LDG.128 and every
+//     lane gets its bytes 16-byte aligned in registers (no alignment fix-ups, no shared memory);
+//   * a group holds `gunits` units per lane = the longest haystack of the group (zero padded);
+//     after bucketing almost every group is uniform, so padding is the 16-byte rounding only.
+//   Per slot: one u32 of metadata (len << 10 | index-within-tile).  Per group: 8 bytes.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define FRZ_TILE 1024          // haystacks per tile
+#define FRZ_TILE_SHIFT 10
+#define FRZ_GROUP 32           // slots per group (= warp)
+#define FRZ_GROUPS_PER_TILE (FRZ_TILE / FRZ_GROUP)
+#define FRZ_UNIT 16            // bytes per unit
+#define FRZ_MAX_HAY_LEN ((1u << 22) - 1)  // slot meta keeps len in 22 bits
+#define FRZ_INVALID_SLOT 0xFFFFFFFFu      // slot meta of an unused slot (last tile)
+#define FRZ_MAX_NEEDLE 64      // needle bytes handled by the kernels (longer → FRZ_ERR_UNSUPPORTED)
+#define FRZ_SW_MAX_WINDOW 1024 // src/smith_waterman/algo/mod.rs:18 (MAX_HAYSTACK_LEN)
+
+struct FrzGroupDesc {
+    uint32_t unit_off;  // first unit of the group, in 16-byte units from the tile's data base
+    uint32_t gunits;    // units per lane in this group
+};
+
+// Device view of a packed corpus.
+struct FrzCorpusView {
+    const uint4* data;            // packed units
+    const uint64_t* tile_base;    // [n_tiles] first unit index (16-byte units) of each tile
+    const FrzGroupDesc* groups;   // [n_tiles * 32]
+    const uint32_t* slot_meta;    // [n_tiles * 1024]  len << 10 | local index, or FRZ_INVALID_SLOT
+    const uint16_t* slot_of;      // [n_tiles * 1024]  inverse permutation: local index → slot
+    uint64_t n;                   // haystacks
+    uint32_t n_tiles;
+};
+
+// typo-mode keys (src/matcher/algo.rs:6-7, src/matcher/mod.rs:58-73)
+enum { FRZ_T_0 = 0, FRZ_T_1 = 1, FRZ_T_2 = 2, FRZ_T_MANY = 3, FRZ_T_NONE = 4, FRZ_T_LITERAL = 5 };
+
+// One compiled pattern as the kernels see it (passed by value as a kernel parameter →
+// constant bank, ~600 bytes).
+struct FrzPatternDev {
+    // case_needle pairs (src/prefilter/mod.rs:49-65)
+    uint8_t c[FRZ_MAX_NEEDLE];
+    uint8_t flip[FRZ_MAX_NEEDLE];
+    // word-parallel probe: byte b matches needle[i] ⇔ ((b | om[i]) == tg[i]); om = 0x20 for a
+    // case-insensitive letter, else 0
+    uint8_t om[FRZ_MAX_NEEDLE];
+    uint8_t tg[FRZ_MAX_NEEDLE];
+    int32_t n;              // needle bytes
+    int32_t typo_mode;      // FRZ_T_*
+    int32_t max_typos;      // runtime budget for FRZ_T_MANY
+    int32_t min_hay_len;    // src/matcher/algo.rs:62-65
+    int32_t pf_lanes;       // prefilter chunk width being emulated: 16 / 32 / 64
+    int32_t sw_lanes;       // Smith-Waterman chunk width being emulated: 8 / 16 / 32 / 64
+    int32_t score_bits;     // 8 or 16 (reference backend family)
+    int32_t wrap8;          // 1 → emulate u8 wrap-around explicitly (no-wrap bound not provable)
+    int32_t matching;       // FRZ_MATCHING_*
+    int32_t case_sensitive;
+    // scoring constants as the reference splats them (u8 truncated in the u8 family;
+    // src/smith_waterman/algo/ascii.rs:35-46)
+    int32_t gap_extend;     // gap_extend_penalty
+    int32_t gap_open_x;     // gap_open_penalty -sat gap_extend_penalty
+    int32_t match_x;        // match_score +sat mismatch_penalty
+    int32_t mismatch;
+    int32_t case_bonus;
+    int32_t cap_bonus;
+    int32_t delim_bonus;
+    int32_t prefix_bonus;
+    int32_t exact_bonus;    // full u16
+    // untruncated scoring for the literal matcher / greedy fallback (u16 arithmetic)
+    int32_t raw_match, raw_mismatch, raw_gap_open, raw_gap_extend, raw_prefix, raw_cap, raw_case, raw_delim;
+};
+
+// Survivor of the prefilter, input of the Smith-Waterman stage (16 bytes).
+struct __align__(16) FrzSurvivor {
+    uint32_t tile;      // tile index
+    uint32_t slot_rank; // slot (10 bits) | rank-by-index inside the tile << 16
+    uint32_t start;     // trimmed window start (bytes)
+    uint32_t end;       // window end (exclusive)
+};
+
+// SW work classes (which kernel variant scores the window)
+enum { FRZ_C_COLS64 = 0, FRZ_C_COLS128 = 1, FRZ_C_GENERIC = 2, FRZ_N_CLASSES = 3 };
+
+struct __align__(8) FrzMatchDev {  // == frz_match
+    uint32_t index;
+    uint16_t score;
+    uint8_t exact;
+    uint8_t pad;
+};
+
+// Per-call scratch counters (device), zeroed before each call.
+struct FrzCounters {
+    unsigned long long class_count[FRZ_N_CLASSES];  // survivors per SW class
+    unsigned long long total;                       // total matches (after scan)
+    unsigned int max_score;
+    unsigned int error;                             // sticky device-side error flags
+};
+
+#define FRZ_DEVERR_SURVIVOR_OVERFLOW 1u
+
+__device__ __forceinline__ uint32_t frz_lane() { return threadIdx.x & 31; }
+
+// address of unit k of (tile, slot)
+__device__ __forceinline__ const uint4* frz_unit_ptr(const FrzCorpusView& cv, uint32_t tile, uint32_t slot, uint32_t k) {
+    FrzGroupDesc gd = cv.groups[tile * FRZ_GROUPS_PER_TILE + (slot >> 5)];
+    return cv.data + cv.tile_base[tile] + gd.unit_off + (uint64_t)k * FRZ_GROUP + (slot & 31);
+}

@@ -1,0 +1,104 @@
+// frz_host.h — internal host-side declarations shared by the .cu translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/frz_cuda.h"
+#include "frz_device.cuh"
+
+frz_status frz_fail(frz_status s, const char* fmt, ...);
+
+#define FRZ_CUDA_TRY(expr)                                                                         \
+    do {                                                                                           \
+        cudaError_t _e = (expr);                                                                   \
+        if (_e != cudaSuccess) {                                                                   \
+            cudaGetLastError();                                                                    \
+            return frz_fail(_e == cudaErrorMemoryAllocation ? FRZ_ERR_OOM : FRZ_ERR_CUDA,          \
+                            "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+        }                                                                                          \
+    } while (0)
+
+#define FRZ_TRY(expr)                         \
+    do {                                      \
+        frz_status _s = (expr);               \
+        if (_s != FRZ_OK) return _s;          \
+    } while (0)
+
+// Owned device buffers of a packed corpus.
+struct FrzCorpusStorage {
+    uint4* data = nullptr;
+    uint64_t* tile_base = nullptr;
+    FrzGroupDesc* groups = nullptr;
+    uint32_t* slot_meta = nullptr;
+    uint16_t* slot_of = nullptr;
+    uint64_t n = 0;
+    uint32_t n_tiles = 0;
+    uint64_t total_units = 0;
+    uint64_t total_bytes = 0;
+    int device = 0;
+
+    FrzCorpusView view() const {
+        FrzCorpusView v;
+        v.data = data;
+        v.tile_base = tile_base;
+        v.groups = groups;
+        v.slot_meta = slot_meta;
+        v.slot_of = slot_of;
+        v.n = n;
+        v.n_tiles = n_tiles;
+        return v;
+    }
+    void release() {
+        cudaFree(data); cudaFree(tile_base); cudaFree(groups); cudaFree(slot_meta); cudaFree(slot_of);
+        data = nullptr; tile_base = nullptr; groups = nullptr; slot_meta = nullptr; slot_of = nullptr;
+    }
+};
+
+struct frz_corpus {
+    FrzCorpusStorage st;
+};
+
+// pack.cu
+frz_status frz_pack_corpus_device(const uint8_t* d_bytes, const uint64_t* d_offsets, uint64_t n, uint64_t total_bytes,
+                                  cudaStream_t stream, FrzCorpusStorage* out);
+
+// Per-matcher device workspace (grown on demand, reused across calls).
+struct FrzWorkspace {
+    int device = -1;
+    FrzCounters* counters = nullptr;        // device
+    FrzCounters* h_counters = nullptr;      // pinned host mirror
+    FrzSurvivor* survivors[FRZ_N_CLASSES] = {nullptr, nullptr, nullptr};
+    uint64_t survivor_cap = 0;              // per class
+    uint32_t* tile_count = nullptr;         // [n_tiles] matches per tile
+    uint64_t* tile_out_base = nullptr;      // [n_tiles] exclusive scan of tile_count
+    uint32_t tiles_cap = 0;
+    FrzMatchDev* matches_a = nullptr;       // index-ordered matches
+    FrzMatchDev* matches_b = nullptr;       // sort ping-pong / final
+    uint64_t match_cap = 0;
+    uint32_t* sort_hist = nullptr;          // [256 * n_sort_blocks]
+    uint64_t sort_hist_cap = 0;
+    uint32_t* cand_bitmap = nullptr;        // multi-pattern candidate bitmap [n/32]
+    uint64_t cand_cap = 0;
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    void release();
+};
+
+// kernels (prefilter.cu / sw.cu / sort.cu) — all asynchronous on `stream`
+struct FrzLaunchStats {
+    uint64_t launches = 0;
+};
+
+frz_status frz_launch_prefilter(const FrzCorpusView& cv, const FrzPatternDev& pat, const uint32_t* cand_bitmap,
+                                FrzWorkspace& ws, cudaStream_t stream, FrzLaunchStats* st);
+frz_status frz_launch_tile_scan(const FrzCorpusView& cv, FrzWorkspace& ws, cudaStream_t stream, FrzLaunchStats* st);
+frz_status frz_launch_sw(const FrzCorpusView& cv, const FrzPatternDev& pat, uint32_t index_offset, bool reversed,
+                         FrzWorkspace& ws, FrzMatchDev* d_out, cudaStream_t stream, FrzLaunchStats* st);
+// stable sort by descending score; the element count is read from device memory (*n_ptr).
+// d_tmp is only used when score_bound >= 1024 (two 8-bit passes); result always lands in d_out.
+frz_status frz_launch_sort_by_score_dev(const FrzMatchDev* d_in, FrzMatchDev* d_tmp, FrzMatchDev* d_out,
+                                        const unsigned long long* n_ptr, uint32_t score_bound, FrzWorkspace& ws,
+                                        cudaStream_t stream, FrzLaunchStats* st);
+size_t frz_sort_hist_words();

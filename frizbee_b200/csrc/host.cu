@@ -1,0 +1,1088 @@
+// host.cu — the C ABI (include/frz_cuda.h): host-side mirror of the reference's Matcher / Pattern /
+// Config logic for the match_list path, orchestrating the CUDA stages.  No CPU compute fallback.
+//
+// Reference logic mirrored here (file:line relative to the reference crate):
+//   Pattern::parse / parse_query          src/pattern.rs:100-222
+//   PatternConfig::resolve                src/pattern.rs:250-262
+//   Matcher::build_patterns / compile     src/matcher/mod.rs:178-205
+//   Matcher::get_backend                  src/matcher/mod.rs:448-498
+//   score_fits_in_u8                      src/smith_waterman/mod.rs:91-116
+//   Scoring::guard_against_score_overflow src/lib.rs:506-537
+//   Matcher::match_list / match_list_into src/matcher/mod.rs:212-222, 373-392
+//   match_list_multi_into                 src/matcher/multi.rs:84-152
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <memory>
+
+#include "frz_device.cuh"
+#include "frz_host.h"
+
+// ------------------------------------------------------------------------------------ errors
+
+static thread_local char g_err[512] = "";
+
+frz_status frz_fail(frz_status s, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return s;
+}
+
+extern "C" const char* frz_last_error(void) { return g_err; }
+extern "C" int frz_abi_version(void) { return FRZ_ABI_VERSION; }
+extern "C" const char* frz_status_str(frz_status s) {
+    switch (s) {
+        case FRZ_OK: return "ok";
+        case FRZ_ERR_INVALID_ARG: return "invalid argument";
+        case FRZ_ERR_NEEDLE_TOO_LONG: return "needle too long and could overflow the u16 score";
+        case FRZ_ERR_GAP_OVERFLOW: return "gap penalties too large and could overflow the u16 score";
+        case FRZ_ERR_TOO_MANY_ITEMS: return "too many items in haystack, will overflow the u32 index";
+        case FRZ_ERR_THREADS_ZERO: return "threads must be positive";
+        case FRZ_ERR_CAPACITY: return "output capacity too small";
+        case FRZ_ERR_CUDA: return "CUDA error";
+        case FRZ_ERR_NO_DEVICE: return "no usable CUDA device";
+        case FRZ_ERR_UNSUPPORTED: return "not supported on the GPU path";
+        case FRZ_ERR_OOM: return "out of device memory";
+    }
+    return "?";
+}
+
+extern "C" void frz_scoring_default(frz_scoring* s) {
+    *s = frz_scoring{12, 6, 5, 1, 12, 4, 4, 8, 4};  // src/const.rs:1-10
+}
+extern "C" void frz_config_default(frz_config* c) {
+    memset(c, 0, sizeof *c);
+    c->max_typos = 0;
+    c->casing = FRZ_CASE_SMART;
+    c->unicode = FRZ_UNICODE_SMART;
+    c->matching = FRZ_MATCHING_FUZZY;
+    c->sort = FRZ_SORT_SCORE_THEN_INDEX_ASC;
+    frz_scoring_default(&c->scoring);
+    c->emulate_lanes = 0;
+}
+
+static frz_status ensure_device(int device) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return frz_fail(FRZ_ERR_NO_DEVICE, "no CUDA device available (%s); this library has no CPU fallback",
+                        e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    }
+    if (device < 0 || device >= n) return frz_fail(FRZ_ERR_INVALID_ARG, "device %d out of range (have %d)", device, n);
+    FRZ_CUDA_TRY(cudaSetDevice(device));
+    return FRZ_OK;
+}
+
+// ----------------------------------------------------------------------------- query parser
+
+struct OwnedPattern {
+    std::string needle;
+    std::string raw;
+    bool negated = false;
+    int matching = -1, casing = -1, unicode = -1, max_typos = -1;
+    bool has_scoring = false;
+    frz_scoring scoring{};
+};
+
+struct frz_query {
+    std::vector<OwnedPattern> pats;
+};
+
+namespace {
+
+// Decodes one UTF-8 scalar starting at s[i] (input is a Rust &str, so valid UTF-8; be lenient).
+uint32_t utf8_next(const uint8_t* s, size_t len, size_t* i) {
+    uint8_t b = s[*i];
+    int extra = b < 0x80 ? 0 : (b >> 5) == 6 ? 1 : (b >> 4) == 14 ? 2 : (b >> 3) == 30 ? 3 : 0;
+    uint32_t cp = extra == 0 ? b : extra == 1 ? (b & 0x1f) : extra == 2 ? (b & 0x0f) : (b & 0x07);
+    size_t j = *i + 1;
+    for (int k = 0; k < extra && j < len; k++, j++) cp = (cp << 6) | (s[j] & 0x3f);
+    *i = j;
+    return cp;
+}
+void utf8_push(std::string& out, uint32_t cp) {
+    if (cp < 0x80) out.push_back((char)cp);
+    else if (cp < 0x800) { out.push_back((char)(0xC0 | (cp >> 6))); out.push_back((char)(0x80 | (cp & 0x3f))); }
+    else if (cp < 0x10000) {
+        out.push_back((char)(0xE0 | (cp >> 12))); out.push_back((char)(0x80 | ((cp >> 6) & 0x3f))); out.push_back((char)(0x80 | (cp & 0x3f)));
+    } else {
+        out.push_back((char)(0xF0 | (cp >> 18))); out.push_back((char)(0x80 | ((cp >> 12) & 0x3f)));
+        out.push_back((char)(0x80 | ((cp >> 6) & 0x3f))); out.push_back((char)(0x80 | (cp & 0x3f)));
+    }
+}
+// char::is_whitespace (Unicode White_Space)
+bool is_ws(uint32_t c) {
+    return (c >= 9 && c <= 13) || c == 0x20 || c == 0x85 || c == 0xA0 || c == 0x1680 || (c >= 0x2000 && c <= 0x200A) ||
+           c == 0x2028 || c == 0x2029 || c == 0x202F || c == 0x205F || c == 0x3000;
+}
+
+// Pattern::parse (src/pattern.rs:100-165)
+OwnedPattern parse_atom(const uint8_t* atom, size_t len) {
+    struct Tok { uint32_t c; bool escaped; };
+    std::vector<Tok> toks;
+    size_t i = 0;
+    while (i < len) {
+        uint32_t c = utf8_next(atom, len, &i);
+        if (c == '\\' && i < len) toks.push_back({utf8_next(atom, len, &i), true});
+        else toks.push_back({c, false});
+    }
+    size_t lo = 0, hi = toks.size();
+    auto strip_first = [&](uint32_t op) {
+        if (lo < hi && !toks[lo].escaped && toks[lo].c == op) { lo++; return true; }
+        return false;
+    };
+    auto strip_last = [&](uint32_t op) {
+        if (lo < hi && !toks[hi - 1].escaped && toks[hi - 1].c == op) { hi--; return true; }
+        return false;
+    };
+    OwnedPattern p;
+    p.raw.assign((const char*)atom, len);
+    p.negated = strip_first('!');
+    bool prefix = strip_first('^');
+    bool substring = !prefix && strip_first('\'');
+    bool suffix = strip_last('$');
+    auto is_special = [](uint32_t c) { return c == '!' || c == '^' || c == '\'' || c == '$' || is_ws(c); };
+    for (size_t k = lo; k < hi; k++) {
+        if (toks[k].escaped && !is_special(toks[k].c)) p.needle.push_back('\\');
+        utf8_push(p.needle, toks[k].c);
+    }
+    if (prefix && suffix) p.matching = FRZ_MATCHING_EXACT;
+    else if (prefix) p.matching = FRZ_MATCHING_PREFIX;
+    else if (suffix) p.matching = FRZ_MATCHING_SUFFIX;
+    else if (substring) p.matching = FRZ_MATCHING_SUBSTRING;
+    else if (p.negated) p.matching = FRZ_MATCHING_SUBSTRING;
+    else p.matching = -1;
+    return p;
+}
+
+// Pattern::parse_query (src/pattern.rs:190-222)
+std::vector<OwnedPattern> parse_query(const uint8_t* q, size_t len) {
+    std::vector<OwnedPattern> out;
+    bool have_start = false, escaped = false;
+    size_t start = 0;
+    auto push = [&](size_t a, size_t b) {
+        OwnedPattern p = parse_atom(q + a, b - a);
+        if (!p.needle.empty()) out.push_back(std::move(p));
+    };
+    size_t i = 0;
+    while (i < len) {
+        size_t at = i;
+        uint32_t c = utf8_next(q, len, &i);
+        if (escaped) escaped = false;
+        else if (c == '\\') { if (!have_start) { have_start = true; start = at; } escaped = true; }
+        else if (is_ws(c)) { if (have_start) { push(start, at); have_start = false; } }
+        else if (!have_start) { have_start = true; start = at; }
+    }
+    if (have_start) push(start, len);
+    return out;
+}
+
+void fill_c_pattern(const OwnedPattern& o, frz_pattern* out) {
+    memset(out, 0, sizeof *out);
+    out->needle = (const uint8_t*)o.needle.data();
+    out->needle_len = o.needle.size();
+    out->negated = o.negated;
+    out->has_scoring = o.has_scoring;
+    out->casing = (int8_t)o.casing;
+    out->unicode = (int8_t)o.unicode;
+    out->matching = (int8_t)o.matching;
+    out->max_typos = o.max_typos;
+    out->scoring = o.scoring;
+}
+
+}  // namespace
+
+extern "C" frz_status frz_parse_query(const uint8_t* query, size_t len, frz_query** out) {
+    if (!out || (!query && len)) return frz_fail(FRZ_ERR_INVALID_ARG, "null argument");
+    auto* q = new frz_query();
+    q->pats = parse_query(query, len);
+    *out = q;
+    return FRZ_OK;
+}
+extern "C" frz_status frz_parse_atom(const uint8_t* atom, size_t len, frz_query** out) {
+    if (!out || (!atom && len)) return frz_fail(FRZ_ERR_INVALID_ARG, "null argument");
+    auto* q = new frz_query();
+    q->pats.push_back(parse_atom(atom, len));
+    *out = q;
+    return FRZ_OK;
+}
+extern "C" size_t frz_query_len(const frz_query* q) { return q ? q->pats.size() : 0; }
+extern "C" frz_status frz_query_get(const frz_query* q, size_t i, frz_pattern* out) {
+    if (!q || !out || i >= q->pats.size()) return frz_fail(FRZ_ERR_INVALID_ARG, "pattern index out of range");
+    fill_c_pattern(q->pats[i], out);
+    return FRZ_OK;
+}
+extern "C" void frz_query_destroy(frz_query* q) { delete q; }
+
+// ---------------------------------------------------------------------------------- corpus
+
+extern "C" frz_status frz_corpus_create_device(const uint8_t* d_bytes, const uint64_t* d_offsets, uint64_t n,
+                                               uint64_t total_bytes, int device, void* stream, frz_corpus** out) {
+    if (!out) return frz_fail(FRZ_ERR_INVALID_ARG, "null out");
+    if (n > 0xFFFFFFFFull) return frz_fail(FRZ_ERR_TOO_MANY_ITEMS, "too many items in haystack: %llu", (unsigned long long)n);
+    FRZ_TRY(ensure_device(device));
+    auto c = std::make_unique<frz_corpus>();
+    c->st.device = device;
+    frz_status s = frz_pack_corpus_device(d_bytes, d_offsets, n, total_bytes, (cudaStream_t)stream, &c->st);
+    if (s != FRZ_OK) { c->st.release(); return s; }
+    *out = c.release();
+    return FRZ_OK;
+}
+
+extern "C" frz_status frz_corpus_create(const uint8_t* bytes, const uint64_t* offsets, uint64_t n, int device, frz_corpus** out) {
+    if (!out || !offsets) return frz_fail(FRZ_ERR_INVALID_ARG, "null argument");
+    if (n > 0xFFFFFFFFull) return frz_fail(FRZ_ERR_TOO_MANY_ITEMS, "too many items in haystack: %llu", (unsigned long long)n);
+    FRZ_TRY(ensure_device(device));
+    const uint64_t total = offsets[n] - offsets[0];
+    uint8_t* d_bytes = nullptr;
+    uint64_t* d_off = nullptr;
+    cudaStream_t stream = nullptr;
+    FRZ_CUDA_TRY(cudaMalloc(&d_bytes, total + 16));
+    if (cudaMalloc(&d_off, (n + 1) * sizeof(uint64_t)) != cudaSuccess) { cudaFree(d_bytes); return frz_fail(FRZ_ERR_OOM, "offsets alloc"); }
+    frz_status s = FRZ_OK;
+    do {
+        if (total && cudaMemcpyAsync(d_bytes, bytes + offsets[0], total, cudaMemcpyHostToDevice, stream) != cudaSuccess) { s = frz_fail(FRZ_ERR_CUDA, "H2D bytes"); break; }
+        if (cudaMemcpyAsync(d_off, offsets, (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, stream) != cudaSuccess) { s = frz_fail(FRZ_ERR_CUDA, "H2D offsets"); break; }
+        // offsets are rebased on device by the plan/copy kernels via (offsets[i] - offsets[0]) only if needed
+        if (offsets[0] != 0) { s = frz_fail(FRZ_ERR_INVALID_ARG, "offsets[0] must be 0"); break; }
+        s = frz_corpus_create_device(d_bytes, d_off, n, total, device, stream, out);
+        if (s == FRZ_OK && cudaStreamSynchronize(stream) != cudaSuccess) s = frz_fail(FRZ_ERR_CUDA, "pack failed: %s", cudaGetErrorString(cudaGetLastError()));
+    } while (0);
+    cudaFree(d_bytes);
+    cudaFree(d_off);
+    return s;
+}
+
+extern "C" frz_status frz_corpus_create_ptrs(const uint8_t* const* ptrs, const uint32_t* lens, uint64_t n, int device,
+                                             frz_corpus** out) {
+    if (!out || (n && (!ptrs || !lens))) return frz_fail(FRZ_ERR_INVALID_ARG, "null argument");
+    std::vector<uint64_t> off(n + 1, 0);
+    for (uint64_t i = 0; i < n; i++) off[i + 1] = off[i] + lens[i];
+    std::vector<uint8_t> bytes(off[n] ? off[n] : 1);
+    for (uint64_t i = 0; i < n; i++)
+        if (lens[i]) memcpy(bytes.data() + off[i], ptrs[i], lens[i]);
+    return frz_corpus_create(bytes.data(), off.data(), n, device, out);
+}
+
+extern "C" uint64_t frz_corpus_len(const frz_corpus* c) { return c ? c->st.n : 0; }
+extern "C" uint64_t frz_corpus_total_bytes(const frz_corpus* c) { return c ? c->st.total_bytes : 0; }
+extern "C" uint64_t frz_corpus_device_bytes(const frz_corpus* c) {
+    if (!c) return 0;
+    const auto& s = c->st;
+    return (s.total_units + 1) * 16 + (uint64_t)s.n_tiles * (8 + FRZ_GROUPS_PER_TILE * 8 + FRZ_TILE * 6);
+}
+extern "C" int frz_corpus_device(const frz_corpus* c) { return c ? c->st.device : -1; }
+extern "C" void frz_corpus_destroy(frz_corpus* c) {
+    if (!c) return;
+    cudaSetDevice(c->st.device);
+    c->st.release();
+    delete c;
+}
+
+// --------------------------------------------------------------------------------- matcher
+
+namespace {
+
+struct CpuIsa {
+    bool avx512_pf, avx512_sw, avx512_sw_u8, avx2, sse;
+};
+CpuIsa detect_isa() {
+    CpuIsa r{false, false, false, false, false};
+#if defined(__x86_64__)
+    __builtin_cpu_init();
+    bool f = __builtin_cpu_supports("avx512f"), bw = __builtin_cpu_supports("avx512bw");
+    bool bmi1 = __builtin_cpu_supports("bmi"), bmi2 = __builtin_cpu_supports("bmi2");
+    bool vbmi = __builtin_cpu_supports("avx512vbmi");
+    r.avx512_pf = f && bw && bmi1 && bmi2;       // src/prefilter/backend/avx512.rs:14-19
+    r.avx512_sw = f && bw;                       // src/smith_waterman/backend/avx512.rs:44-46
+    r.avx512_sw_u8 = f && bw && vbmi;            // src/smith_waterman/backend/avx512.rs:112-116
+    r.avx2 = __builtin_cpu_supports("avx2");
+    r.sse = __builtin_cpu_supports("sse2") && __builtin_cpu_supports("ssse3") && __builtin_cpu_supports("sse4.1");
+#endif
+    return r;
+}
+
+uint16_t sat_add16(uint32_t a, uint32_t b) { uint32_t r = a + b; return (uint16_t)(r > 0xFFFF ? 0xFFFF : r); }
+uint16_t sat_sub16(uint32_t a, uint32_t b) { return (uint16_t)(a > b ? a - b : 0); }
+
+uint32_t max_per_char_bonus(const frz_scoring& s) {  // src/lib.rs:488-494
+    uint32_t bonus = std::max(s.delimiter_bonus, s.capitalization_bonus);
+    uint32_t amort = std::max((bonus + 1) / 2, bonus > s.gap_open_penalty ? bonus - s.gap_open_penalty : 0u);
+    return sat_add16(amort, s.matching_case_bonus);
+}
+uint32_t max_one_time_bonus(const frz_scoring& s) {  // src/lib.rs:497-503
+    uint32_t bonus = std::max(s.delimiter_bonus, s.capitalization_bonus);
+    uint32_t amort = std::max((bonus + 1) / 2, bonus > s.gap_open_penalty ? bonus - s.gap_open_penalty : 0u);
+    return bonus - amort;
+}
+bool score_fits_in_u8(size_t needle_len, const frz_scoring& s) {  // src/smith_waterman/mod.rs:91-116
+    size_t mc = (size_t)s.match_score + s.mismatch_penalty;
+    mc = std::max<size_t>(mc, s.gap_open_penalty);
+    mc = std::max<size_t>(mc, s.gap_extend_penalty);
+    mc = std::max<size_t>(mc, s.matching_case_bonus);
+    mc = std::max<size_t>(mc, s.capitalization_bonus);
+    mc = std::max<size_t>(mc, s.delimiter_bonus);
+    mc = std::max<size_t>(mc, s.prefix_bonus);
+    if (mc > 255) return false;
+    if (64 * (size_t)s.gap_extend_penalty + s.gap_open_penalty > 255) return false;
+    size_t per_char = (size_t)s.match_score + max_per_char_bonus(s);
+    size_t max_matrix = per_char * needle_len + max_one_time_bonus(s) + s.prefix_bonus;
+    return max_matrix + s.mismatch_penalty <= 255;
+}
+// Scoring::guard_against_score_overflow (src/lib.rs:506-537)
+frz_status guard_against_score_overflow(const frz_scoring& s, size_t needle_len, uint32_t max_bonus_per_char, uint32_t one_time) {
+    uint32_t per_char = sat_add16(s.match_score, max_bonus_per_char);
+    if (per_char == 0) return FRZ_OK;
+    uint32_t headroom = sat_sub16(sat_sub16(sat_sub16(sat_sub16(0xFFFF, s.prefix_bonus), s.exact_match_bonus), s.mismatch_penalty), one_time);
+    uint32_t max_len = headroom / per_char;
+    if (needle_len > max_len)
+        return frz_fail(FRZ_ERR_NEEDLE_TOO_LONG, "needle too long and could overflow the u16 score: %zu > %u", needle_len, max_len);
+    size_t max_gap = 32 * (size_t)s.gap_extend_penalty + s.gap_open_penalty;
+    if (max_gap > 0xFFFF)
+        return frz_fail(FRZ_ERR_GAP_OVERFLOW, "gap penalties too large and could overflow the u16 score: %zu > 65535", max_gap);
+    return FRZ_OK;
+}
+
+struct Compiled {
+    FrzPatternDev dev;
+    bool negated = false;
+    bool literal = false;
+    uint32_t score_bound = 0;  // host-side upper bound of any score this pattern can emit
+};
+
+// Matcher::compile + get_backend (src/matcher/mod.rs:193-205, 448-498) → device pattern
+frz_status compile_pattern(const OwnedPattern& src, const frz_config& mcfg, bool* is_none, Compiled* out) {
+    *is_none = src.needle.empty();
+    if (*is_none) return FRZ_OK;
+    // PatternConfig::resolve (src/pattern.rs:250-262)
+    const int max_typos = src.max_typos >= 0 ? src.max_typos : mcfg.max_typos;
+    const int casing = src.casing >= 0 ? src.casing : mcfg.casing;
+    const int unicode = src.unicode >= 0 ? src.unicode : mcfg.unicode;
+    const int matching = src.matching >= 0 ? src.matching : mcfg.matching;
+    const frz_scoring sc = src.has_scoring ? src.scoring : mcfg.scoring;
+    const uint8_t* nd = (const uint8_t*)src.needle.data();
+    const size_t n = src.needle.size();
+    bool ascii = true;
+    size_t nchars = 0;
+    for (size_t i = 0; i < n; i++) {
+        if (nd[i] >= 0x80) ascii = false;
+        if ((nd[i] & 0xC0) != 0x80) nchars++;
+    }
+    // UnicodeMatching::respects_unicode_for (src/lib.rs:394-401)
+    const bool needs_unicode = unicode == FRZ_UNICODE_ALWAYS || (unicode == FRZ_UNICODE_SMART && !ascii);
+    if (needs_unicode)
+        return frz_fail(FRZ_ERR_UNSUPPORTED, "the unicode-aware kernels (non-ASCII needle or UnicodeMatching::Always) are not on the GPU path yet");
+    // CaseMatching::respects_case_for (src/lib.rs:368-377)
+    bool case_sensitive;
+    if (casing == FRZ_CASE_IGNORE) case_sensitive = false;
+    else if (casing == FRZ_CASE_RESPECT) case_sensitive = true;
+    else {
+        if (!ascii) return frz_fail(FRZ_ERR_UNSUPPORTED, "CaseMatching::Smart with a non-ASCII needle needs Unicode case tables");
+        case_sensitive = false;
+        for (size_t i = 0; i < n; i++) if (nd[i] >= 'A' && nd[i] <= 'Z') case_sensitive = true;
+    }
+    if (n > FRZ_MAX_NEEDLE) return frz_fail(FRZ_ERR_UNSUPPORTED, "needle of %zu bytes exceeds the GPU kernels' limit of %d", n, FRZ_MAX_NEEDLE);
+
+    Compiled c;
+    FrzPatternDev& d = c.dev;
+    memset(&d, 0, sizeof d);
+    c.negated = src.negated;
+    c.literal = matching != FRZ_MATCHING_FUZZY;
+    d.n = (int)n;
+    d.matching = matching;
+    d.case_sensitive = case_sensitive;
+    for (size_t i = 0; i < n; i++) {  // case_needle (src/prefilter/mod.rs:49-65)
+        uint8_t ch = nd[i], fl;
+        if (case_sensitive) fl = ch;
+        else if (ch >= 'a' && ch <= 'z') fl = (uint8_t)(ch - 32);
+        else if (ch >= 'A' && ch <= 'Z') fl = (uint8_t)(ch + 32);
+        else fl = ch;
+        d.c[i] = ch; d.flip[i] = fl;
+        d.om[i] = fl != ch ? 0x20 : 0;
+        d.tg[i] = fl != ch ? (uint8_t)(ch | 0x20) : ch;
+    }
+    d.raw_match = sc.match_score; d.raw_mismatch = sc.mismatch_penalty; d.raw_gap_open = sc.gap_open_penalty;
+    d.raw_gap_extend = sc.gap_extend_penalty; d.raw_prefix = sc.prefix_bonus; d.raw_cap = sc.capitalization_bonus;
+    d.raw_case = sc.matching_case_bonus; d.raw_delim = sc.delimiter_bonus; d.exact_bonus = sc.exact_match_bonus;
+
+    const CpuIsa isa = detect_isa();
+    const int em = mcfg.emulate_lanes;
+    if (em != 0 && em != 16 && em != 32 && em != 64) return frz_fail(FRZ_ERR_INVALID_ARG, "emulate_lanes must be 0, 16, 32 or 64");
+    // per-char bound used for the sort's digit width
+    const uint32_t maxb = std::max(sc.capitalization_bonus, sc.delimiter_bonus);
+
+    if (c.literal) {
+        // LiteralImpl::guard_against_score_overflow (src/literal/algo.rs:316-324)
+        FRZ_TRY(guard_against_score_overflow(sc, n, sat_add16(maxb, sc.matching_case_bonus), 0));
+        d.typo_mode = FRZ_T_LITERAL;
+        d.min_hay_len = 0;
+        d.pf_lanes = 64; d.sw_lanes = 64; d.score_bits = 16;
+        uint64_t b = (uint64_t)n * ((uint64_t)sc.match_score + sc.matching_case_bonus + maxb) + sc.prefix_bonus + sc.exact_match_bonus;
+        c.score_bound = (uint32_t)std::min<uint64_t>(b, 0xFFFF);
+        *out = c;
+        return FRZ_OK;
+    }
+    // MatcherImpl::guard_against_score_overflow (src/matcher/algo.rs:311-325): byte length on the ascii path
+    FRZ_TRY(guard_against_score_overflow(sc, n, max_per_char_bonus(sc), max_one_time_bonus(sc)));
+    const bool use_u8 = score_fits_in_u8(n, sc);
+    int pf_lanes, sw_lanes;
+    if (em == 0) {
+        if (use_u8) {
+            if (isa.avx512_pf && isa.avx512_sw_u8) { pf_lanes = 64; sw_lanes = 64; }
+            else if (isa.avx2) { pf_lanes = 32; sw_lanes = 32; }
+            else { pf_lanes = 16; sw_lanes = 16; }   // SSE / NEON / scalar
+        } else {
+            if (isa.avx512_pf && isa.avx512_sw) { pf_lanes = 64; sw_lanes = 32; }
+            else if (isa.avx2) { pf_lanes = 32; sw_lanes = 16; }
+            else { pf_lanes = 16; sw_lanes = 8; }
+        }
+    } else {
+        pf_lanes = em;
+        sw_lanes = use_u8 ? em : em / 2;
+    }
+    d.pf_lanes = pf_lanes; d.sw_lanes = sw_lanes; d.score_bits = use_u8 ? 8 : 16;
+    // constants exactly as the reference splats them (ascii.rs:35-46); `as u8` truncation in the u8 family
+    const uint32_t tm = use_u8 ? 0xFF : 0xFFFF;
+    d.gap_extend = sc.gap_extend_penalty & tm;
+    d.gap_open_x = sat_sub16(sc.gap_open_penalty, sc.gap_extend_penalty) & tm;
+    d.match_x = sat_add16(sc.match_score, sc.mismatch_penalty) & tm;
+    d.mismatch = sc.mismatch_penalty & tm;
+    d.case_bonus = sc.matching_case_bonus & tm;
+    d.cap_bonus = sc.capitalization_bonus & tm;
+    d.delim_bonus = sc.delimiter_bonus & tm;
+    d.prefix_bonus = sc.prefix_bonus & tm;
+    // the kernels keep cells in signed 16-bit lanes: every intermediate must stay below 2^15
+    const uint64_t cell_bound = (uint64_t)n * ((uint64_t)sc.match_score + maxb + sc.matching_case_bonus) + sc.prefix_bonus +
+                                (uint64_t)sc.mismatch_penalty + sc.match_score;
+    const uint64_t pen_bound = (uint64_t)sw_lanes * sc.gap_extend_penalty + sc.gap_open_penalty;
+    if (cell_bound > 32767 || pen_bound > 32767)
+        return frz_fail(FRZ_ERR_UNSUPPORTED, "scoring/needle combination exceeds the kernels' signed 16-bit cell range");
+    d.wrap8 = use_u8 && cell_bound > 255;  // cannot prove "no u8 add ever wraps" → emulate the wrap
+    if (max_typos < 0) d.typo_mode = FRZ_T_NONE;
+    else if (max_typos == 0) d.typo_mode = FRZ_T_0;
+    else if (max_typos == 1) d.typo_mode = FRZ_T_1;
+    else if (max_typos == 2) d.typo_mode = FRZ_T_2;
+    else {
+        d.typo_mode = FRZ_T_MANY;
+        if (max_typos > 15 && (size_t)max_typos < n)
+            return frz_fail(FRZ_ERR_UNSUPPORTED, "max_typos > 15 is not on the GPU path yet");
+    }
+    d.max_typos = max_typos < 0 ? 0 : std::min(max_typos, (int)n);  // budget >= needle length matches everything
+    // min_haystack_len (src/matcher/algo.rs:62-65)
+    d.min_hay_len = max_typos >= 0 ? (int)(nchars > (size_t)max_typos ? nchars - max_typos : 0) : 0;
+    uint64_t b = std::min<uint64_t>(cell_bound, use_u8 ? 255 : 0xFFFF) + sc.exact_match_bonus;
+    c.score_bound = (uint32_t)std::min<uint64_t>(b, 0xFFFF);
+    *out = c;
+    return FRZ_OK;
+}
+
+}  // namespace
+
+void FrzWorkspace::release() {
+    if (device >= 0) cudaSetDevice(device);
+    cudaFree(counters);
+    if (h_counters) cudaFreeHost(h_counters);
+    for (auto& s : survivors) { cudaFree(s); s = nullptr; }
+    cudaFree(tile_count); cudaFree(tile_out_base); cudaFree(matches_a); cudaFree(matches_b); cudaFree(sort_hist); cudaFree(cand_bitmap);
+    for (auto& e : ev) { if (e) cudaEventDestroy(e); e = nullptr; }
+    counters = nullptr; h_counters = nullptr; tile_count = nullptr; tile_out_base = nullptr; matches_a = matches_b = nullptr;
+    sort_hist = nullptr; cand_bitmap = nullptr;
+    survivor_cap = match_cap = sort_hist_cap = cand_cap = 0; tiles_cap = 0; device = -1;
+}
+
+struct frz_matcher {
+    frz_config config;
+    std::vector<OwnedPattern> raw;
+    std::vector<Compiled> compiled;   // build_patterns: patterns with non-empty needles
+    FrzWorkspace ws;
+    FrzMatchDev* multi_a = nullptr;   // multi-pattern candidate ping-pong
+    FrzMatchDev* multi_b = nullptr;
+    uint64_t multi_cap = 0;
+    float last_ms[4] = {0, 0, 0, 0};
+    uint64_t last_launches = 0;
+    ~frz_matcher() {
+        if (ws.device >= 0) { cudaSetDevice(ws.device); cudaFree(multi_a); cudaFree(multi_b); }
+        ws.release();
+    }
+};
+
+namespace {
+
+frz_status build_patterns(frz_matcher* m) {
+    std::vector<Compiled> comp;
+    for (const auto& p : m->raw) {
+        bool none = false;
+        Compiled c;
+        FRZ_TRY(compile_pattern(p, m->config, &none, &c));
+        if (!none) comp.push_back(c);
+    }
+    m->compiled.swap(comp);
+    return FRZ_OK;
+}
+
+frz_status validate_config(const frz_config* c) {
+    if (!c) return frz_fail(FRZ_ERR_INVALID_ARG, "null config");
+    if (c->max_typos < -1 || c->max_typos > 65535) return frz_fail(FRZ_ERR_INVALID_ARG, "max_typos out of range");
+    if (c->casing > 2 || c->unicode > 2 || c->matching > 4 || c->sort > 3) return frz_fail(FRZ_ERR_INVALID_ARG, "bad enum value in config");
+    return FRZ_OK;
+}
+
+}  // namespace
+
+extern "C" frz_status frz_matcher_create(const frz_pattern* patterns, size_t n_patterns, const frz_config* config, frz_matcher** out) {
+    if (!out || (n_patterns && !patterns)) return frz_fail(FRZ_ERR_INVALID_ARG, "null argument");
+    FRZ_TRY(validate_config(config));
+    auto m = std::make_unique<frz_matcher>();
+    m->config = *config;
+    for (size_t i = 0; i < n_patterns; i++) {
+        const frz_pattern& p = patterns[i];
+        OwnedPattern o;
+        o.needle.assign((const char*)p.needle, p.needle_len);
+        o.raw = o.needle;
+        o.negated = p.negated != 0;
+        o.matching = p.matching; o.casing = p.casing; o.unicode = p.unicode; o.max_typos = p.max_typos;
+        o.has_scoring = p.has_scoring != 0; o.scoring = p.scoring;
+        m->raw.push_back(std::move(o));
+    }
+    FRZ_TRY(build_patterns(m.get()));
+    *out = m.release();
+    return FRZ_OK;
+}
+
+extern "C" frz_status frz_matcher_from_query(const uint8_t* query, size_t len, const frz_config* config, frz_matcher** out) {
+    if (!out || (!query && len)) return frz_fail(FRZ_ERR_INVALID_ARG, "null argument");
+    FRZ_TRY(validate_config(config));
+    auto m = std::make_unique<frz_matcher>();
+    m->config = *config;
+    m->raw = parse_query(query, len);
+    FRZ_TRY(build_patterns(m.get()));
+    *out = m.release();
+    return FRZ_OK;
+}
+
+extern "C" frz_status frz_matcher_set_config(frz_matcher* m, const frz_config* config) {
+    if (!m) return frz_fail(FRZ_ERR_INVALID_ARG, "null matcher");
+    FRZ_TRY(validate_config(config));
+    if (memcmp(&m->config, config, sizeof *config) == 0) return FRZ_OK;
+    frz_config old = m->config;
+    m->config = *config;
+    frz_status s = build_patterns(m);
+    if (s != FRZ_OK) { m->config = old; build_patterns(m); }
+    return s;
+}
+
+extern "C" void frz_matcher_destroy(frz_matcher* m) { delete m; }
+extern "C" size_t frz_matcher_num_patterns(const frz_matcher* m) { return m ? m->compiled.size() : 0; }
+extern "C" frz_status frz_matcher_backend_info(const frz_matcher* m, size_t i, int* lanes, int* score_bits, int* prefilter_lanes, int* is_literal) {
+    if (!m || i >= m->compiled.size()) return frz_fail(FRZ_ERR_INVALID_ARG, "pattern index out of range");
+    const auto& c = m->compiled[i];
+    if (lanes) *lanes = c.dev.sw_lanes;
+    if (score_bits) *score_bits = c.dev.score_bits;
+    if (prefilter_lanes) *prefilter_lanes = c.dev.pf_lanes;
+    if (is_literal) *is_literal = c.literal;
+    return FRZ_OK;
+}
+extern "C" frz_status frz_matcher_last_timings(const frz_matcher* m, float* ms4, uint64_t* launches) {
+    if (!m) return frz_fail(FRZ_ERR_INVALID_ARG, "null matcher");
+    if (ms4) memcpy(ms4, m->last_ms, sizeof m->last_ms);
+    if (launches) *launches = m->last_launches;
+    return FRZ_OK;
+}
+
+// ------------------------------------------------------------------------ small helper kernels
+
+namespace {
+
+__global__ void k_fill_all(FrzMatchDev* out, uint64_t n, uint32_t index_offset, FrzCounters* ctr) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+        out[i] = FrzMatchDev{index_offset + (uint32_t)i, 0, 0, 0};
+    if (blockIdx.x == 0 && threadIdx.x == 0) ctr->total = n;
+}
+__global__ void k_reverse(const FrzMatchDev* in, FrzMatchDev* out, const unsigned long long* n_ptr) {
+    const unsigned long long n = *n_ptr;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x)
+        out[n - 1 - i] = in[i];
+}
+// candidate bitmap over haystack indices (relative to index_offset)
+__global__ void k_bitmap_set(const FrzMatchDev* cand, uint64_t n, uint32_t index_offset, uint32_t* bitmap) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint32_t idx = cand[i].index - index_offset;
+        atomicOr(&bitmap[idx >> 5], 1u << (idx & 31));
+    }
+}
+// keep[i] = candidate i is (not) hit; hits are index-ordered → binary search
+__device__ __forceinline__ long long find_hit(const FrzMatchDev* hits, uint64_t nh, uint32_t index) {
+    uint64_t lo = 0, hi = nh;
+    while (lo < hi) {
+        uint64_t mid = (lo + hi) >> 1;
+        if (hits[mid].index < index) lo = mid + 1; else hi = mid;
+    }
+    return (lo < nh && hits[lo].index == index) ? (long long)lo : -1;
+}
+// non-negated extra pattern: every hit is a surviving candidate; add the candidate's score
+// (hit.score saturating_add, exact |=; src/matcher/multi.rs:133-147)
+__global__ void k_combine_hits(const FrzMatchDev* cand, uint64_t nc, FrzMatchDev* hits, uint64_t nh) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nh; i += (uint64_t)gridDim.x * blockDim.x) {
+        FrzMatchDev h = hits[i];
+        long long j = find_hit(cand, nc, h.index);
+        if (j >= 0) {
+            uint32_t s = (uint32_t)h.score + cand[j].score;
+            h.score = (uint16_t)(s > 0xFFFF ? 0xFFFF : s);
+            h.exact |= cand[j].exact;
+        }
+        hits[i] = h;
+    }
+}
+// negated extra pattern: retain candidates that were NOT hit (src/matcher/multi.rs:124-132).
+// Stable compaction: per-block ballot counts → single-block scan → scatter.
+constexpr int kCompactBlock = 1024;
+__global__ void __launch_bounds__(kCompactBlock) k_retain_count(const FrzMatchDev* cand, uint64_t nc, const FrzMatchDev* hits, uint64_t nh,
+                                                                uint32_t* block_count, uint8_t* keep) {
+    __shared__ uint32_t wc[32];
+    uint64_t i = (uint64_t)blockIdx.x * kCompactBlock + threadIdx.x;
+    bool k = i < nc && find_hit(hits, nh, cand[i].index) < 0;
+    if (i < nc) keep[i] = k;
+    uint32_t b = __ballot_sync(0xffffffffu, k);
+    if ((threadIdx.x & 31) == 0) wc[threadIdx.x >> 5] = __popc(b);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t s = 0;
+        for (int w = 0; w < 32; w++) s += wc[w];
+        block_count[blockIdx.x] = s;
+    }
+}
+__global__ void __launch_bounds__(kCompactBlock) k_retain_scatter(const FrzMatchDev* cand, uint64_t nc, const uint8_t* keep,
+                                                                  const uint64_t* block_base, FrzMatchDev* out) {
+    __shared__ uint32_t wc[32];
+    uint64_t i = (uint64_t)blockIdx.x * kCompactBlock + threadIdx.x;
+    bool k = i < nc && keep[i];
+    uint32_t b = __ballot_sync(0xffffffffu, k);
+    uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) wc[warp] = __popc(b);
+    __syncthreads();
+    uint32_t pre = 0;
+    for (uint32_t w = 0; w < warp; w++) pre += wc[w];
+    if (k) out[block_base[blockIdx.x] + pre + __popc(b & ((1u << lane) - 1))] = cand[i];
+}
+__global__ void __launch_bounds__(1024) k_scan_blocks(const uint32_t* cnt, uint64_t* base, uint32_t n, FrzCounters* ctr) {
+    __shared__ uint64_t carry;
+    __shared__ uint64_t ws[32];
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (uint32_t b0 = 0; b0 < n; b0 += blockDim.x) {
+        uint32_t i = b0 + threadIdx.x;
+        uint64_t v = i < n ? cnt[i] : 0, x = v;
+        for (int d = 1; d < 32; d <<= 1) { uint64_t y = __shfl_up_sync(0xffffffffu, x, d); if ((threadIdx.x & 31) >= (unsigned)d) x += y; }
+        if ((threadIdx.x & 31) == 31) ws[threadIdx.x >> 5] = x;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            uint64_t w = ws[threadIdx.x], xs = w;
+            for (int d = 1; d < 32; d <<= 1) { uint64_t y = __shfl_up_sync(0xffffffffu, xs, d); if (threadIdx.x >= (unsigned)d) xs += y; }
+            ws[threadIdx.x] = xs - w;
+        }
+        __syncthreads();
+        uint64_t incl = carry + ws[threadIdx.x >> 5] + x;
+        if (i < n) base[i] = incl - v;
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) carry = incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) ctr->total = carry;
+}
+
+frz_status ensure_workspace(frz_matcher* m, const FrzCorpusStorage& cs, uint64_t survivor_cap) {
+    FrzWorkspace& ws = m->ws;
+    if (ws.device != cs.device) {
+        if (ws.device >= 0) { cudaSetDevice(ws.device); cudaFree(m->multi_a); cudaFree(m->multi_b); m->multi_a = m->multi_b = nullptr; m->multi_cap = 0; }
+        ws.release();
+        FRZ_CUDA_TRY(cudaSetDevice(cs.device));
+        ws.device = cs.device;
+        FRZ_CUDA_TRY(cudaMalloc(&ws.counters, sizeof(FrzCounters)));
+        FRZ_CUDA_TRY(cudaMallocHost(&ws.h_counters, sizeof(FrzCounters)));
+        for (auto& e : ws.ev) FRZ_CUDA_TRY(cudaEventCreate(&e));
+        size_t words = frz_sort_hist_words();
+        FRZ_CUDA_TRY(cudaMalloc(&ws.sort_hist, words * sizeof(uint32_t)));
+        ws.sort_hist_cap = words;
+    }
+    if (ws.tiles_cap < cs.n_tiles) {
+        cudaFree(ws.tile_count); cudaFree(ws.tile_out_base);
+        ws.tile_count = nullptr; ws.tile_out_base = nullptr; ws.tiles_cap = 0;
+        FRZ_CUDA_TRY(cudaMalloc(&ws.tile_count, (size_t)cs.n_tiles * sizeof(uint32_t)));
+        FRZ_CUDA_TRY(cudaMalloc(&ws.tile_out_base, (size_t)cs.n_tiles * sizeof(uint64_t)));
+        ws.tiles_cap = cs.n_tiles;
+    }
+    if (ws.survivor_cap < survivor_cap) {
+        for (auto& s : ws.survivors) { cudaFree(s); s = nullptr; }
+        ws.survivor_cap = 0;
+        for (auto& s : ws.survivors) FRZ_CUDA_TRY(cudaMalloc(&s, (size_t)survivor_cap * sizeof(FrzSurvivor)));
+        ws.survivor_cap = survivor_cap;
+    }
+    if (ws.match_cap < cs.n) {
+        cudaFree(ws.matches_a); cudaFree(ws.matches_b);
+        ws.matches_a = ws.matches_b = nullptr; ws.match_cap = 0;
+        FRZ_CUDA_TRY(cudaMalloc(&ws.matches_a, (size_t)std::max<uint64_t>(cs.n, 1) * sizeof(FrzMatchDev)));
+        FRZ_CUDA_TRY(cudaMalloc(&ws.matches_b, (size_t)std::max<uint64_t>(cs.n, 1) * sizeof(FrzMatchDev)));
+        ws.match_cap = cs.n;
+    }
+    return FRZ_OK;
+}
+
+uint64_t initial_survivor_cap(const FrzCorpusStorage& cs, const FrzPatternDev& d) {
+    if (d.typo_mode == FRZ_T_NONE) return std::max<uint64_t>(cs.n, 1);
+    return std::min<uint64_t>(std::max<uint64_t>(cs.n / 4, 1 << 16), std::max<uint64_t>(cs.n, 1));
+}
+
+// One pattern over the corpus (optionally restricted to a candidate bitmap) → index-ordered matches in
+// d_out (reversed order if `reversed`); the count is left in ws.counters->total (device).
+frz_status run_pattern(frz_matcher* m, const FrzCorpusStorage& cs, const Compiled& c, const uint32_t* cand_bitmap,
+                       uint32_t index_offset, bool reversed, FrzMatchDev* d_out, cudaStream_t stream, FrzLaunchStats* st,
+                       bool record_events) {
+    FrzWorkspace& ws = m->ws;
+    const FrzCorpusView cv = cs.view();
+    uint64_t cap = std::max(ws.survivor_cap, initial_survivor_cap(cs, c.dev));
+    for (int attempt = 0; attempt < 2; attempt++) {
+        FRZ_TRY(ensure_workspace(m, cs, cap));
+        FRZ_CUDA_TRY(cudaMemsetAsync(ws.counters, 0, sizeof(FrzCounters), stream));
+        if (record_events) cudaEventRecord(ws.ev[0], stream);
+        FRZ_TRY(frz_launch_prefilter(cv, c.dev, cand_bitmap, ws, stream, st));
+        FRZ_TRY(frz_launch_tile_scan(cv, ws, stream, st));
+        if (record_events) cudaEventRecord(ws.ev[1], stream);
+        // overflow of the survivor lists is detected before scoring (cheap: one small D2H only if the
+        // list was sized by the heuristic rather than the worst case)
+        if (ws.survivor_cap < cs.n) {
+            FRZ_CUDA_TRY(cudaMemcpyAsync(ws.h_counters, ws.counters, sizeof(FrzCounters), cudaMemcpyDeviceToHost, stream));
+            FRZ_CUDA_TRY(cudaStreamSynchronize(stream));
+            if (ws.h_counters->error & FRZ_DEVERR_SURVIVOR_OVERFLOW) { cap = std::max<uint64_t>(cs.n, 1); continue; }
+        }
+        FRZ_TRY(frz_launch_sw(cv, c.dev, index_offset, reversed, ws, d_out, stream, st));
+        if (record_events) cudaEventRecord(ws.ev[2], stream);
+        return FRZ_OK;
+    }
+    return frz_fail(FRZ_ERR_CUDA, "survivor list overflow persisted");
+}
+
+frz_status read_counters(frz_matcher* m, cudaStream_t stream) {
+    FrzWorkspace& ws = m->ws;
+    FRZ_CUDA_TRY(cudaMemcpyAsync(ws.h_counters, ws.counters, sizeof(FrzCounters), cudaMemcpyDeviceToHost, stream));
+    FRZ_CUDA_TRY(cudaStreamSynchronize(stream));
+    return FRZ_OK;
+}
+
+int grid_for(uint64_t n, int block) {
+    uint64_t g = (n + block - 1) / block;
+    return (int)std::max<uint64_t>(1, std::min<uint64_t>(g, 148 * 16));
+}
+
+// match_list_into over all compiled patterns → index-ordered device list; returns pointer + leaves the
+// count in ws.counters->total.  `final_reversed` asks for the list in descending index order.
+frz_status match_into_device(frz_matcher* m, const FrzCorpusStorage& cs, uint32_t index_offset, bool final_reversed,
+                             FrzMatchDev** d_result, uint32_t* score_bound, cudaStream_t stream, FrzLaunchStats* st) {
+    FrzWorkspace& ws = m->ws;
+    if ((uint64_t)cs.n + index_offset > 0xFFFFFFFFull)
+        return frz_fail(FRZ_ERR_TOO_MANY_ITEMS, "too many items in haystack, will overflow the u32 index: %llu > %u (index offset: %u)",
+                        (unsigned long long)cs.n + index_offset, 0xFFFFFFFFu, index_offset);
+    const auto& pats = m->compiled;
+    *score_bound = 0;
+    if (pats.empty()) {  // CompiledPatterns::Empty (src/matcher/mod.rs:380-383)
+        FRZ_TRY(ensure_workspace(m, cs, 1));
+        FRZ_CUDA_TRY(cudaMemsetAsync(ws.counters, 0, sizeof(FrzCounters), stream));
+        k_fill_all<<<grid_for(cs.n, 256), 256, 0, stream>>>(ws.matches_a, cs.n, index_offset, ws.counters);
+        st->launches++;
+        if (final_reversed) {
+            k_reverse<<<grid_for(cs.n, 256), 256, 0, stream>>>(ws.matches_a, ws.matches_b, &ws.counters->total);
+            st->launches++;
+            *d_result = ws.matches_b;
+        } else *d_result = ws.matches_a;
+        FRZ_CUDA_TRY(cudaGetLastError());
+        return FRZ_OK;
+    }
+    if (pats.size() == 1 && !pats[0].negated) {  // CompiledPatterns::Single
+        FRZ_TRY(ensure_workspace(m, cs, initial_survivor_cap(cs, pats[0].dev)));
+        FRZ_TRY(run_pattern(m, cs, pats[0], nullptr, index_offset, final_reversed, ws.matches_a, stream, st, true));
+        *d_result = ws.matches_a;
+        *score_bound = pats[0].score_bound;
+        return FRZ_OK;
+    }
+    // CompiledPatterns::Multi (src/matcher/multi.rs:84-152).  Counts are read back between patterns.
+    FRZ_TRY(ensure_workspace(m, cs, initial_survivor_cap(cs, pats[0].dev)));
+    if (m->multi_cap < cs.n) {
+        cudaFree(m->multi_a); cudaFree(m->multi_b);
+        m->multi_a = m->multi_b = nullptr; m->multi_cap = 0;
+        FRZ_CUDA_TRY(cudaMalloc(&m->multi_a, (size_t)std::max<uint64_t>(cs.n, 1) * sizeof(FrzMatchDev)));
+        FRZ_CUDA_TRY(cudaMalloc(&m->multi_b, (size_t)std::max<uint64_t>(cs.n, 1) * sizeof(FrzMatchDev)));
+        m->multi_cap = cs.n;
+    }
+    const size_t bm_words = (size_t)((cs.n + 31) / 32) + 1;
+    if (ws.cand_cap < bm_words) {
+        cudaFree(ws.cand_bitmap); ws.cand_bitmap = nullptr; ws.cand_cap = 0;
+        FRZ_CUDA_TRY(cudaMalloc(&ws.cand_bitmap, bm_words * sizeof(uint32_t)));
+        ws.cand_cap = bm_words;
+    }
+    int base = -1;
+    for (size_t i = 0; i < pats.size(); i++) if (!pats[i].negated) { base = (int)i; break; }
+    FrzMatchDev* cand = m->multi_a;
+    FrzMatchDev* spare = m->multi_b;
+    uint64_t nc = 0;
+    uint64_t bound = 0;
+    if (base >= 0) {
+        FRZ_TRY(run_pattern(m, cs, pats[base], nullptr, index_offset, false, cand, stream, st, true));
+        FRZ_TRY(read_counters(m, stream));
+        nc = ws.h_counters->total;
+        bound = pats[base].score_bound;
+    } else {
+        FRZ_CUDA_TRY(cudaMemsetAsync(ws.counters, 0, sizeof(FrzCounters), stream));
+        k_fill_all<<<grid_for(cs.n, 256), 256, 0, stream>>>(cand, cs.n, index_offset, ws.counters);
+        st->launches++;
+        nc = cs.n;
+    }
+    uint32_t* d_block_cnt = nullptr;
+    uint64_t* d_block_base = nullptr;
+    uint8_t* d_keep = nullptr;
+    frz_status status = FRZ_OK;
+    for (size_t pi = 0; pi < pats.size() && status == FRZ_OK; pi++) {
+        if ((int)pi == base || nc == 0) continue;
+        status = [&]() -> frz_status {
+            FRZ_CUDA_TRY(cudaMemsetAsync(ws.cand_bitmap, 0, bm_words * sizeof(uint32_t), stream));
+            k_bitmap_set<<<grid_for(nc, 256), 256, 0, stream>>>(cand, nc, index_offset, ws.cand_bitmap);
+            st->launches++;
+            // hits land in ws.matches_a, index-ordered, with real indices
+            FRZ_TRY(run_pattern(m, cs, pats[pi], ws.cand_bitmap, index_offset, false, ws.matches_a, stream, st, false));
+            FRZ_TRY(read_counters(m, stream));
+            const uint64_t nh = ws.h_counters->total;
+            if (pats[pi].negated) {
+                const uint32_t nb = (uint32_t)((nc + kCompactBlock - 1) / kCompactBlock);
+                if (!d_keep) {
+                    const uint32_t nb_max = (uint32_t)((cs.n + kCompactBlock - 1) / kCompactBlock) + 1;
+                    FRZ_CUDA_TRY(cudaMalloc(&d_block_cnt, nb_max * sizeof(uint32_t)));
+                    FRZ_CUDA_TRY(cudaMalloc(&d_block_base, nb_max * sizeof(uint64_t)));
+                    FRZ_CUDA_TRY(cudaMalloc(&d_keep, std::max<uint64_t>(cs.n, 1)));
+                }
+                k_retain_count<<<nb, kCompactBlock, 0, stream>>>(cand, nc, ws.matches_a, nh, d_block_cnt, d_keep);
+                k_scan_blocks<<<1, 1024, 0, stream>>>(d_block_cnt, d_block_base, nb, ws.counters);
+                k_retain_scatter<<<nb, kCompactBlock, 0, stream>>>(cand, nc, d_keep, d_block_base, spare);
+                st->launches += 3;
+                FRZ_TRY(read_counters(m, stream));
+                nc = ws.h_counters->total;
+                std::swap(cand, spare);
+            } else {
+                k_combine_hits<<<grid_for(nh, 256), 256, 0, stream>>>(cand, nc, ws.matches_a, nh);
+                st->launches++;
+                FRZ_CUDA_TRY(cudaMemcpyAsync(spare, ws.matches_a, nh * sizeof(FrzMatchDev), cudaMemcpyDeviceToDevice, stream));
+                std::swap(cand, spare);
+                nc = nh;
+                bound += pats[pi].score_bound;
+            }
+            return FRZ_OK;
+        }();
+    }
+    cudaFree(d_block_cnt); cudaFree(d_block_base); cudaFree(d_keep);
+    FRZ_TRY(status);
+    // publish: count → counters.total, list → matches_a (reversed if asked)
+    ws.h_counters->total = nc;
+    FRZ_CUDA_TRY(cudaMemcpyAsync(&ws.counters->total, &ws.h_counters->total, sizeof(unsigned long long), cudaMemcpyHostToDevice, stream));
+    if (final_reversed) {
+        k_reverse<<<grid_for(nc, 256), 256, 0, stream>>>(cand, ws.matches_a, &ws.counters->total);
+        st->launches++;
+    } else {
+        FRZ_CUDA_TRY(cudaMemcpyAsync(ws.matches_a, cand, nc * sizeof(FrzMatchDev), cudaMemcpyDeviceToDevice, stream));
+    }
+    FRZ_CUDA_TRY(cudaGetLastError());
+    *d_result = ws.matches_a;
+    *score_bound = (uint32_t)std::min<uint64_t>(bound, 0xFFFF);
+    return FRZ_OK;
+}
+
+// Matcher::match_list on device: into (+reverse) (+stable score sort).  Result pointer + device count.
+frz_status match_list_device(frz_matcher* m, const FrzCorpusStorage& cs, uint32_t index_offset, uint8_t sort,
+                             FrzMatchDev** d_result, cudaStream_t stream, FrzLaunchStats* st) {
+    FrzWorkspace& ws = m->ws;
+    const bool reversed = sort == FRZ_SORT_INDEX_DESC || sort == FRZ_SORT_SCORE_THEN_INDEX_DESC;
+    const bool by_score = sort == FRZ_SORT_SCORE_THEN_INDEX_ASC || sort == FRZ_SORT_SCORE_THEN_INDEX_DESC;
+    FrzMatchDev* d_list = nullptr;
+    uint32_t bound = 0;
+    FRZ_TRY(match_into_device(m, cs, index_offset, reversed, &d_list, &bound, stream, st));
+    // `!self.patterns.is_empty() && sort.is_by_score()` (src/matcher/mod.rs:218)
+    if (by_score && !m->compiled.empty()) {
+        FrzMatchDev* other = d_list == ws.matches_a ? ws.matches_b : ws.matches_a;
+        FrzMatchDev* tmp = m->multi_a ? m->multi_a : nullptr;
+        if (bound >= 1024 && !tmp) {
+            if (m->multi_cap < cs.n) {
+                FRZ_CUDA_TRY(cudaMalloc(&m->multi_a, (size_t)std::max<uint64_t>(cs.n, 1) * sizeof(FrzMatchDev)));
+                FRZ_CUDA_TRY(cudaMalloc(&m->multi_b, (size_t)std::max<uint64_t>(cs.n, 1) * sizeof(FrzMatchDev)));
+                m->multi_cap = cs.n;
+            }
+            tmp = m->multi_a;
+        }
+        FRZ_TRY(frz_launch_sort_by_score_dev(d_list, tmp, other, &ws.counters->total, bound, ws, stream, st));
+        d_list = other;
+    }
+    cudaEventRecord(ws.ev[3], stream);
+    *d_result = d_list;
+    return FRZ_OK;
+}
+
+void collect_timings(frz_matcher* m, const FrzLaunchStats& st) {
+    FrzWorkspace& ws = m->ws;
+    float a = 0, b = 0, c = 0, t = 0;
+    if (cudaEventElapsedTime(&a, ws.ev[0], ws.ev[1]) != cudaSuccess) a = 0;
+    if (cudaEventElapsedTime(&b, ws.ev[1], ws.ev[2]) != cudaSuccess) b = 0;
+    if (cudaEventElapsedTime(&c, ws.ev[2], ws.ev[3]) != cudaSuccess) c = 0;
+    if (cudaEventElapsedTime(&t, ws.ev[0], ws.ev[3]) != cudaSuccess) t = 0;
+    cudaGetLastError();
+    m->last_ms[0] = a; m->last_ms[1] = b; m->last_ms[2] = c; m->last_ms[3] = t;
+    m->last_launches = st.launches;
+}
+
+frz_status copy_out(frz_matcher* m, FrzMatchDev* d_list, frz_match* out, uint64_t cap, uint64_t* n_out, cudaStream_t stream) {
+    FRZ_TRY(read_counters(m, stream));
+    if (m->ws.h_counters->error) return frz_fail(FRZ_ERR_CUDA, "device-side error flags 0x%x", m->ws.h_counters->error);
+    const uint64_t n = m->ws.h_counters->total;
+    if (n_out) *n_out = n;
+    if (n > cap) return frz_fail(FRZ_ERR_CAPACITY, "output capacity %llu < %llu matches", (unsigned long long)cap, (unsigned long long)n);
+    if (n) {
+        if (!out) return frz_fail(FRZ_ERR_INVALID_ARG, "null out");
+        static_assert(sizeof(frz_match) == sizeof(FrzMatchDev), "layout");
+        FRZ_CUDA_TRY(cudaMemcpyAsync(out, d_list, n * sizeof(frz_match), cudaMemcpyDeviceToHost, stream));
+        FRZ_CUDA_TRY(cudaStreamSynchronize(stream));
+    }
+    return FRZ_OK;
+}
+
+}  // namespace
+
+extern "C" frz_status frz_match_list(frz_matcher* m, const frz_corpus* corpus, frz_match* out, uint64_t cap, uint64_t* n_out) {
+    if (!m || !corpus) return frz_fail(FRZ_ERR_INVALID_ARG, "null argument");
+    FRZ_TRY(ensure_device(corpus->st.device));
+    cudaStream_t stream = nullptr;
+    FrzLaunchStats st;
+    FrzMatchDev* d_list = nullptr;
+    FRZ_TRY(match_list_device(m, corpus->st, 0, m->config.sort, &d_list, stream, &st));
+    frz_status s = copy_out(m, d_list, out, cap, n_out, stream);
+    collect_timings(m, st);
+    return s;
+}
+
+extern "C" frz_status frz_match_list_into(frz_matcher* m, const frz_corpus* corpus, uint32_t index_offset, frz_match* out,
+                                          uint64_t cap, uint64_t* n_out) {
+    if (!m || !corpus) return frz_fail(FRZ_ERR_INVALID_ARG, "null argument");
+    FRZ_TRY(ensure_device(corpus->st.device));
+    cudaStream_t stream = nullptr;
+    FrzLaunchStats st;
+    FrzMatchDev* d_list = nullptr;
+    FRZ_TRY(match_list_device(m, corpus->st, index_offset, FRZ_SORT_INDEX_ASC, &d_list, stream, &st));
+    frz_status s = copy_out(m, d_list, out, cap, n_out, stream);
+    collect_timings(m, st);
+    return s;
+}
+
+extern "C" frz_status frz_match_list_host(frz_matcher* m, const uint8_t* bytes, const uint64_t* offsets, uint64_t n, int device,
+                                          frz_match* out, uint64_t cap, uint64_t* n_out) {
+    frz_corpus* c = nullptr;
+    FRZ_TRY(frz_corpus_create(bytes, offsets, n, device, &c));
+    frz_status s = frz_match_list(m, c, out, cap, n_out);
+    frz_corpus_destroy(c);
+    return s;
+}
+
+extern "C" frz_status frz_match_shard_device(frz_matcher* m, const frz_corpus* shard, uint32_t index_offset, frz_match* d_out,
+                                             uint64_t cap, uint64_t* d_count, void* stream_) {
+    if (!m || !shard || !d_out || !d_count) return frz_fail(FRZ_ERR_INVALID_ARG, "null argument");
+    FRZ_TRY(ensure_device(shard->st.device));
+    cudaStream_t stream = (cudaStream_t)stream_;
+    FrzLaunchStats st;
+    FrzMatchDev* d_list = nullptr;
+    FRZ_TRY(match_list_device(m, shard->st, index_offset, m->config.sort, &d_list, stream, &st));
+    // the run can never exceed the shard size; the caller sizes d_out as >= shard length
+    if (cap < shard->st.n) return frz_fail(FRZ_ERR_CAPACITY, "d_out must hold the whole shard (%llu)", (unsigned long long)shard->st.n);
+    FRZ_CUDA_TRY(cudaMemcpyAsync(d_out, d_list, shard->st.n * sizeof(frz_match), cudaMemcpyDeviceToDevice, stream));
+    FRZ_CUDA_TRY(cudaMemcpyAsync(d_count, &m->ws.counters->total, sizeof(uint64_t), cudaMemcpyDeviceToDevice, stream));
+    m->last_launches = st.launches;
+    return FRZ_OK;
+}
+
+namespace {
+__global__ void k_gather_runs(const FrzMatchDev* runs, uint64_t stride, const uint64_t* counts, const uint64_t* bases, int n_runs,
+                              int reverse_runs, FrzMatchDev* out) {
+    for (int r = 0; r < n_runs; r++) {
+        const int src_run = reverse_runs ? n_runs - 1 - r : r;
+        const FrzMatchDev* src = runs + (uint64_t)src_run * stride;
+        const uint64_t cnt = counts[src_run], base = bases[r];
+        for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += (uint64_t)gridDim.x * blockDim.x)
+            out[base + i] = src[i];
+    }
+}
+}  // namespace
+
+// k_merge_matches_by (src/k_merge.rs:90-131).  Runs are index-range shards in rank order, each already
+// ordered per `sort`; concatenating them in (reverse) rank order and stable-sorting by score yields
+// exactly the reference's k-way merge (ties resolve by index because the shards are index-ordered).
+extern "C" frz_status frz_merge_runs_device(const frz_match* d_runs, uint64_t run_stride, const uint64_t* run_counts_host,
+                                            int n_runs, uint8_t sort, frz_match* d_out, int device, void* stream_) {
+    if (!d_runs || !run_counts_host || !d_out || n_runs <= 0 || n_runs > 64) return frz_fail(FRZ_ERR_INVALID_ARG, "bad argument");
+    FRZ_TRY(ensure_device(device));
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const bool reversed = sort == FRZ_SORT_INDEX_DESC || sort == FRZ_SORT_SCORE_THEN_INDEX_DESC;
+    const bool by_score = sort == FRZ_SORT_SCORE_THEN_INDEX_ASC || sort == FRZ_SORT_SCORE_THEN_INDEX_DESC;
+    uint64_t h[2 * 64 + 1];
+    uint64_t total = 0;
+    for (int r = 0; r < n_runs; r++) {
+        h[r] = run_counts_host[r];
+        const int src_run = reversed ? n_runs - 1 - r : r;
+        h[64 + r] = total;
+        total += run_counts_host[src_run];
+    }
+    h[128] = total;
+    uint64_t* d_meta = nullptr;
+    FrzMatchDev* d_cat = nullptr;
+    FrzMatchDev* d_tmp = nullptr;
+    FrzWorkspace ws;  // only the sort scratch is used
+    frz_status s = [&]() -> frz_status {
+        FRZ_CUDA_TRY(cudaMalloc(&d_meta, sizeof h));
+        FRZ_CUDA_TRY(cudaMemcpyAsync(d_meta, h, sizeof h, cudaMemcpyHostToDevice, stream));
+        FrzMatchDev* dst = by_score ? nullptr : reinterpret_cast<FrzMatchDev*>(d_out);
+        if (by_score) { FRZ_CUDA_TRY(cudaMalloc(&d_cat, std::max<uint64_t>(total, 1) * sizeof(FrzMatchDev))); dst = d_cat; }
+        k_gather_runs<<<grid_for(total / std::max(n_runs, 1) + 1, 256), 256, 0, stream>>>(
+            reinterpret_cast<const FrzMatchDev*>(d_runs), run_stride, d_meta, d_meta + 64, n_runs, reversed ? 1 : 0, dst);
+        if (by_score) {
+            FRZ_CUDA_TRY(cudaMalloc(&ws.sort_hist, frz_sort_hist_words() * sizeof(uint32_t)));
+            FRZ_CUDA_TRY(cudaMalloc(&d_tmp, std::max<uint64_t>(total, 1) * sizeof(FrzMatchDev)));
+            FRZ_TRY(frz_launch_sort_by_score_dev(d_cat, d_tmp, reinterpret_cast<FrzMatchDev*>(d_out),
+                                                 reinterpret_cast<const unsigned long long*>(d_meta + 128), 0xFFFF, ws, stream, nullptr));
+        }
+        FRZ_CUDA_TRY(cudaStreamSynchronize(stream));
+        return FRZ_OK;
+    }();
+    cudaFree(d_meta); cudaFree(d_cat); cudaFree(d_tmp); cudaFree(ws.sort_hist);
+    return s;
+}
+
+extern "C" frz_status frz_radix_sort_matches(frz_match* matches, uint64_t n, int device) {
+    if (n == 0) return FRZ_OK;
+    if (!matches) return frz_fail(FRZ_ERR_INVALID_ARG, "null matches");
+    FRZ_TRY(ensure_device(device));
+    FrzMatchDev *d_a = nullptr, *d_b = nullptr, *d_c = nullptr;
+    unsigned long long* d_n = nullptr;
+    FrzWorkspace ws;
+    cudaStream_t stream = nullptr;
+    frz_status s = [&]() -> frz_status {
+        FRZ_CUDA_TRY(cudaMalloc(&d_a, n * sizeof(FrzMatchDev)));
+        FRZ_CUDA_TRY(cudaMalloc(&d_b, n * sizeof(FrzMatchDev)));
+        FRZ_CUDA_TRY(cudaMalloc(&d_c, n * sizeof(FrzMatchDev)));
+        FRZ_CUDA_TRY(cudaMalloc(&d_n, sizeof(unsigned long long)));
+        FRZ_CUDA_TRY(cudaMalloc(&ws.sort_hist, frz_sort_hist_words() * sizeof(uint32_t)));
+        unsigned long long hn = n;
+        FRZ_CUDA_TRY(cudaMemcpyAsync(d_n, &hn, sizeof hn, cudaMemcpyHostToDevice, stream));
+        FRZ_CUDA_TRY(cudaMemcpyAsync(d_a, matches, n * sizeof(FrzMatchDev), cudaMemcpyHostToDevice, stream));
+        FRZ_TRY(frz_launch_sort_by_score_dev(d_a, d_b, d_c, d_n, 0xFFFF, ws, stream, nullptr));
+        FRZ_CUDA_TRY(cudaMemcpyAsync(matches, d_c, n * sizeof(FrzMatchDev), cudaMemcpyDeviceToHost, stream));
+        FRZ_CUDA_TRY(cudaStreamSynchronize(stream));
+        return FRZ_OK;
+    }();
+    cudaFree(d_a); cudaFree(d_b); cudaFree(d_c); cudaFree(d_n); cudaFree(ws.sort_hist);
+    return s;
+}

@@ -1,0 +1,627 @@
+// prefilter.cu — stage 1 of match_list: length gate → ordered char-mask prefilter → window trim
+// → survivor records, one thread block per corpus tile.
+//
+// Reference path replaced (per haystack, src/matcher/algo.rs:85-100):
+//     if len >= min_haystack_len { (matched,start,end) = prefilter_haystack(..); trim_haystack(..) }
+// with Prefilter::match_haystack (src/prefilter/algo/ascii.rs:6-54), match_haystack_1_typo /
+// _2_typos / _many_typos (src/prefilter/algo/ascii_typos.rs:15-360) and trim_haystack
+// (src/matcher/algo.rs:331-338).  Literal modes (src/literal/algo.rs:234-255) are decided here too.
+//
+// Structure (one block = one tile of 1024 slots, 4 rounds of 8 groups):
+//   phase A  warp per group, lane per haystack: coalesced LDG.128 of the interleaved units and a
+//            word-parallel "does it contain needle[0] (or needle[1])" probe — a necessary condition
+//            that rejects most haystacks at ~3 integer ops per 4 bytes; passing lanes park their
+//            bytes in a private shared-memory slice.
+//   phase B  thread per candidate: the exact reference window (chunk-emulating for k >= 1),
+//            on the shared-memory copy.
+//   phase C  survivors are emitted in slot order per SW class with their index-order rank, so
+//            that the scoring stage can write matches straight to their index-ordered position.
+#include "frz_device.cuh"
+#include "frz_host.h"
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+constexpr int kRounds = FRZ_GROUPS_PER_TILE / kWarps;  // 4
+constexpr int kSliceUnits = 8;                         // haystacks up to 128 bytes are staged in smem
+constexpr int kSliceWords = kSliceUnits * 4 + 1;       // +1 word: conflict-free stride, and a zero guard
+
+struct SliceAcc {
+    const uint32_t* s;
+    __device__ __forceinline__ uint32_t word(uint32_t w) const { return s[w]; }
+};
+struct GlobalAcc {
+    const uint4* base;  // unit 0 of this slot; unit k at base + 32*k
+    __device__ __forceinline__ uint32_t word(uint32_t w) const {
+        return reinterpret_cast<const uint32_t*>(base + (size_t)(w >> 2) * FRZ_GROUP)[w & 3];
+    }
+};
+
+__device__ __forceinline__ uint32_t splat4(uint32_t b) { return b * 0x01010101u; }
+
+// first position in [from, to) whose byte b satisfies (b | om) == tg, else -1
+template <class A>
+__device__ __forceinline__ int find_first(const A& a, uint32_t om4, uint32_t tg4, int from, int to) {
+    if (from >= to) return -1;
+    int w = from >> 2;
+    const int wend = (to + 3) >> 2;
+    uint32_t x = (a.word(w) | om4) ^ tg4;
+    x |= (1u << ((from & 3) * 8)) - 1;  // bytes below `from` can never look like a hit
+    for (;;) {
+        // lowest flagged byte is always a true zero byte (borrows only travel upwards)
+        uint32_t z = (x - 0x01010101u) & ~x & 0x80808080u;
+        if (z) {
+            int p = w * 4 + ((__ffs(z) - 1) >> 3);
+            return p < to ? p : -1;
+        }
+        if (++w >= wend) return -1;
+        x = (a.word(w) | om4) ^ tg4;
+    }
+}
+
+__device__ __forceinline__ uint32_t zero_bytes_exact(uint32_t x) {
+    return ~(((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x | 0x7f7f7f7fu);  // 0x80 in every zero byte
+}
+
+// last position in [from, to) matching either probe (om1,tg1) or (om2,tg2), else -1
+template <class A>
+__device__ __forceinline__ int find_last2(const A& a, uint32_t om1, uint32_t tg1, uint32_t om2, uint32_t tg2, int from, int to) {
+    if (from >= to) return -1;
+    int w = (to - 1) >> 2;
+    const int w0 = from >> 2;
+    for (;;) {
+        uint32_t v = a.word(w);
+        uint32_t z = zero_bytes_exact((v | om1) ^ tg1) | zero_bytes_exact((v | om2) ^ tg2);
+        int lo = w * 4;
+        if (to - lo < 4) z &= (1u << ((to - lo) * 8)) - 1;          // drop bytes >= to
+        if (from > lo) z &= ~((1u << ((from - lo) * 8)) - 1);       // drop bytes < from
+        if (z) return lo + ((31 - __clz(z)) >> 3);
+        if (--w < w0) return -1;
+    }
+}
+
+struct Probe {
+    uint32_t om, tg;
+};
+__device__ __forceinline__ Probe probe_of(const FrzPatternDev& p, int i) { return Probe{splat4(p.om[i]), splat4(p.tg[i])}; }
+
+// ---- Prefilter::match_haystack (0 typos): closed form of src/prefilter/algo/ascii.rs:6-54 ----
+// start = first occurrence of needle[0]; greedy in-order scan; end = 1 + last occurrence of needle[n-1]
+template <class A>
+__device__ bool window_k0(const A& a, const FrzPatternDev& p, int len, int* ostart, int* oend) {
+    if (len == 0) return false;
+    int pos = 0, start = 0, q = 0;
+    for (int i = 0; i < p.n; i++) {
+        Probe pr = probe_of(p, i);
+        q = find_first(a, pr.om, pr.tg, pos, len);
+        if (q < 0) return false;
+        if (i == 0) start = q;
+        pos = q + 1;
+    }
+    Probe last = probe_of(p, p.n - 1);
+    *ostart = start;
+    *oend = 1 + find_last2(a, last.om, last.tg, last.om, last.tg, q, len);
+    return true;
+}
+
+// find_end_pos_with_typos (src/prefilter/algo/ascii_typos.rs:375-397): 1 + last occurrence of any of
+// the last (k+1) needle bytes, else len.  Chunk-independent.
+template <class A>
+__device__ int end_pos_with_typos(const A& a, const FrzPatternDev& p, int len, int k) {
+    int best = -1;
+    int first = p.n - 1 - k;
+    for (int i = first; i < p.n; i += 2) {
+        Probe p1 = probe_of(p, i);
+        Probe p2 = probe_of(p, i + 1 < p.n ? i + 1 : i);
+        int q = find_last2(a, p1.om, p1.tg, p2.om, p2.tg, best < 0 ? 0 : best, len);
+        if (q > best) best = q;
+    }
+    return best < 0 ? len : best + 1;
+}
+
+// ---- match_haystack_1_typo (src/prefilter/algo/ascii_typos.rs:15-110), chunk-emulating ----
+// Both paths' chunk masks are always suffixes [pos, chunk_end) of the chunk, so a path is the pair
+// (needle index, position) and `first_path_chunk_mask > second_path_chunk_mask` ⇔ pf < ps.
+template <class A>
+__device__ bool window_k1(const A& a, const FrzPatternDev& p, int len, int* ostart, int* oend) {
+    const int n = p.n;
+    if (n <= 1) { *ostart = 0; *oend = len; return true; }
+    if (len == 0) return false;
+    int f = 0, s = 1;
+    int ms = 0x7fffffff;
+    const int L = p.pf_lanes;
+    for (int cs = 0; cs < len; cs += L) {
+        const int ce = min(cs + L, len);
+        int pf = cs, ps = cs;
+        bool f_dead = false, s_dead = false;  // path already failed to find its byte in [pos, ce)
+        for (;;) {
+            bool adv = false;
+            int cand = f + 1;
+            if (cand > s) {
+                if (cand == n) goto found;
+                s = cand; ps = pf; s_dead = false;
+            } else if (cand == s && pf < ps) {
+                ps = pf; s_dead = false;
+            }
+            if (!f_dead) {
+                Probe pr = probe_of(p, f);
+                int q = find_first(a, pr.om, pr.tg, pf, ce);
+                if (q >= 0) { ms = min(ms, q); f++; pf = q + 1; adv = true; }
+                else f_dead = true;
+            }
+            if (!s_dead) {
+                Probe pr = probe_of(p, s);
+                int q = find_first(a, pr.om, pr.tg, ps, ce);
+                if (q >= 0) {
+                    ms = min(ms, q); s++;
+                    if (s >= n) goto found;
+                    ps = q + 1; adv = true;
+                } else s_dead = true;
+            }
+            if (!adv) break;
+        }
+    }
+    return false;
+found:
+    *ostart = ms;
+    *oend = end_pos_with_typos(a, p, len, 1);
+    return true;
+}
+
+// ---- match_haystack_many_typos_impl (ascii_typos.rs:254-360); also used for k == 2 ----
+// NOTE the 2-typo specialisation (ascii_typos.rs:113-251) advances each path on its OWN first hit,
+// the N-typo version advances all paths on the single lowest hit; they are distinct algorithms.
+template <class A>
+__device__ bool window_k2(const A& a, const FrzPatternDev& p, int len, int* ostart, int* oend) {
+    const int n = p.n;
+    if (n <= 2) { *ostart = 0; *oend = len; return true; }
+    if (len == 0) return false;
+    int idx[3] = {0, 1, 2};
+    int ms = 0x7fffffff;
+    const int L = p.pf_lanes;
+    for (int cs = 0; cs < len; cs += L) {
+        const int ce = min(cs + L, len);
+        int pos[3] = {cs, cs, cs};
+        for (;;) {
+            bool adv = false;
+#pragma unroll
+            for (int k = 1; k < 3; k++) {
+                int cand = idx[k - 1] + 1;
+                if (cand > idx[k]) {
+                    if (cand == n) goto found;
+                    idx[k] = cand; pos[k] = pos[k - 1];
+                } else if (cand == idx[k] && pos[k - 1] < pos[k]) {
+                    pos[k] = pos[k - 1];
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                Probe pr = probe_of(p, idx[k]);
+                int q = find_first(a, pr.om, pr.tg, pos[k], ce);
+                if (q >= 0) {
+                    ms = min(ms, q); idx[k]++;
+                    if (k > 0 && idx[k] >= n) goto found;
+                    pos[k] = q + 1; adv = true;
+                }
+            }
+            if (!adv) break;
+        }
+    }
+    return false;
+found:
+    *ostart = ms;
+    *oend = end_pos_with_typos(a, p, len, 2);
+    return true;
+}
+
+constexpr int kMaxPaths = 16;  // FRZ_T_MANY supports max_typos <= 15 on the GPU path
+
+template <class A>
+__device__ bool window_many(const A& a, const FrzPatternDev& p, int len, int* ostart, int* oend) {
+    const int n = p.n, k = p.max_typos;
+    if (n <= k) { *ostart = 0; *oend = len; return true; }
+    if (len == 0) return false;
+    const int paths = k + 1;
+    int idx[kMaxPaths];
+    for (int i = 0; i < paths; i++) idx[i] = 0;
+    int ms = 0x7fffffff;
+    const int L = p.pf_lanes;
+    for (int cs = 0; cs < len; cs += L) {
+        const int ce = min(cs + L, len);
+        int pos = cs;  // one shared chunk mask (ascii_typos.rs:286,350)
+        for (;;) {
+            for (int j = 1; j < paths; j++) {
+                int cand = idx[j - 1] + 1;
+                if (cand > idx[j]) {
+                    if (cand == n) goto found;
+                    idx[j] = cand;
+                }
+            }
+            // lowest hit over all paths
+            int hit = 0x7fffffff;
+            for (int j = 0; j < paths; j++) {
+                Probe pr = probe_of(p, idx[j]);
+                int q = find_first(a, pr.om, pr.tg, pos, min(ce, hit == 0x7fffffff ? ce : hit + 1));
+                if (q >= 0 && q < hit) hit = q;
+            }
+            if (hit == 0x7fffffff) break;
+            ms = min(ms, hit);
+            uint32_t hb = a.word(hit >> 2) >> ((hit & 3) * 8) & 0xff;
+            for (int j = 0; j < paths; j++) {
+                int i = idx[j];
+                if (((hb | p.om[i]) & 0xff) != p.tg[i]) continue;
+                idx[j] = i + 1;
+                if (idx[j] == n) goto found;
+            }
+            pos = hit + 1;
+        }
+    }
+    return false;
+found:
+    *ostart = ms;
+    *oend = end_pos_with_typos(a, p, len, k);
+    return true;
+}
+
+// ---- literal matcher, ASCII path (src/literal/algo.rs:159-255) ----
+__device__ __forceinline__ bool lit_is_delim(uint32_t b) {
+    bool alnum = (b - '0' <= 9u) || (b - 'a' <= 25u) || (b - 'A' <= 25u);
+    return b <= 127 && !alnum;
+}
+template <class A>
+__device__ __forceinline__ uint32_t byte_at(const A& a, int i) { return (a.word(i >> 2) >> ((i & 3) * 8)) & 0xff; }
+
+template <class A>
+__device__ bool lit_matches_at(const A& a, const FrzPatternDev& p, int pos) {
+    for (int k = 0; k < p.n; k++) {
+        uint32_t b = byte_at(a, pos + k);
+        if (b != p.c[k] && b != p.flip[k]) return false;
+    }
+    return true;
+}
+template <class A>
+__device__ uint32_t lit_score_at(const A& a, const FrzPatternDev& p, int len, int pos) {
+    uint32_t score = 0;
+    uint32_t prev = pos > 0 ? byte_at(a, pos - 1) : 0;
+    for (int k = 0; k < p.n; k++) {
+        int st = pos + k;
+        uint32_t b = byte_at(a, st);
+        uint32_t sc = p.raw_match;
+        if (b == p.c[k]) sc += p.raw_case;
+        if (st == 0) sc += p.raw_prefix;
+        else {
+            if (b - 'A' <= 25u && prev - 'a' <= 25u) sc += p.raw_cap;
+            if (lit_is_delim(prev) && !lit_is_delim(b)) sc += p.raw_delim;
+        }
+        score += sc;
+        prev = b;
+    }
+    if (pos == 0 && p.n == len) score += p.exact_bonus;
+    return score & 0xffff;
+}
+// returns true on match; *opos, *oscore
+template <class A>
+__device__ bool lit_find(const A& a, const FrzPatternDev& p, int len, int* opos, uint32_t* oscore) {
+    const int n = p.n;
+    if (len < n) return false;
+    switch (p.matching) {
+        case FRZ_MATCHING_EXACT:
+            if (len != n || !lit_matches_at(a, p, 0)) return false;
+            *opos = 0; *oscore = lit_score_at(a, p, len, 0); return true;
+        case FRZ_MATCHING_PREFIX:
+            if (!lit_matches_at(a, p, 0)) return false;
+            *opos = 0; *oscore = lit_score_at(a, p, len, 0); return true;
+        case FRZ_MATCHING_SUFFIX:
+            if (!lit_matches_at(a, p, len - n)) return false;
+            *opos = len - n; *oscore = lit_score_at(a, p, len, len - n); return true;
+        default: {  // SUBSTRING: best score, earliest on ties (find_substring :262-313)
+            bool have = false;
+            Probe p0 = probe_of(p, 0);
+            int from = 0;
+            const int last_start = len - n + 1;
+            for (;;) {
+                int q = find_first(a, p0.om, p0.tg, from, last_start);
+                if (q < 0) break;
+                if (lit_matches_at(a, p, q)) {
+                    uint32_t sc = lit_score_at(a, p, len, q);
+                    if (!have || sc > *oscore) { have = true; *opos = q; *oscore = sc; }
+                }
+                from = q + 1;
+            }
+            return have;
+        }
+    }
+}
+
+struct TileShared {
+    uint32_t slice[kThreads * kSliceWords];   // per-candidate haystack bytes (phase A → B)
+    uint32_t cand_meta[kThreads];             // slot | (in_slice << 31)
+    uint32_t surv_start[FRZ_TILE];            // by local index
+    uint32_t surv_end[FRZ_TILE];
+    uint16_t surv_slot[FRZ_TILE];
+    uint32_t bm_class[FRZ_N_CLASSES][32];     // survivor bitmaps by local index, per SW class
+    uint32_t pre_all[33];                     // exclusive prefix popcounts
+    uint32_t pre_class[FRZ_N_CLASSES][33];
+    unsigned long long class_base[FRZ_N_CLASSES];
+    uint32_t ncand;
+};
+
+__device__ __forceinline__ int sw_class_of(int window, int sw_cols0) {
+    return window <= sw_cols0 ? FRZ_C_COLS64 : window <= 2 * sw_cols0 ? FRZ_C_COLS128 : FRZ_C_GENERIC;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kThreads) k_prefilter(const FrzCorpusView cv, const __grid_constant__ FrzPatternDev pat,
+                                                        const uint32_t* __restrict__ cand_bitmap,
+                                                        FrzSurvivor* __restrict__ surv0, FrzSurvivor* __restrict__ surv1,
+                                                        FrzSurvivor* __restrict__ surv2, unsigned long long surv_cap,
+                                                        uint32_t* __restrict__ tile_count, FrzCounters* __restrict__ ctr,
+                                                        FrzMatchDev* __restrict__ lit_out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    TileShared& sh = *reinterpret_cast<TileShared*>(smem_raw);
+    const uint32_t tile = blockIdx.x;
+    const uint32_t lane = frz_lane(), warp = threadIdx.x >> 5;
+    const uint64_t tb = cv.tile_base[tile];
+
+    for (int i = threadIdx.x; i < FRZ_N_CLASSES * 32; i += kThreads) (&sh.bm_class[0][0])[i] = 0;
+
+    // probes for phase A
+    const uint32_t om0 = splat4(pat.om[0]), tg0 = splat4(pat.tg[0]);
+    const uint32_t om1 = splat4(pat.om[pat.n > 1 ? 1 : 0]), tg1 = splat4(pat.tg[pat.n > 1 ? 1 : 0]);
+    const uint32_t om2 = splat4(pat.om[pat.n > 2 ? 2 : 0]), tg2 = splat4(pat.tg[pat.n > 2 ? 2 : 0]);
+
+    for (int round = 0; round < kRounds; round++) {
+        if (threadIdx.x == 0) sh.ncand = 0;
+        __syncthreads();
+        // ------------------------------------------------------------ phase A
+        {
+            const uint32_t g = round * kWarps + warp;
+            const FrzGroupDesc gd = cv.groups[tile * FRZ_GROUPS_PER_TILE + g];
+            const uint32_t slot = g * FRZ_GROUP + lane;
+            const uint32_t meta = cv.slot_meta[(uint64_t)tile * FRZ_TILE + slot];
+            const bool valid = meta != FRZ_INVALID_SLOT;
+            const uint32_t len = valid ? meta >> FRZ_TILE_SHIFT : 0;
+            bool pass = valid && (int)len >= pat.min_hay_len;
+            if (cand_bitmap != nullptr && valid) {
+                uint64_t idx = (uint64_t)tile * FRZ_TILE + (meta & (FRZ_TILE - 1));
+                pass = pass && ((cand_bitmap[idx >> 5] >> (idx & 31)) & 1);
+            }
+            const uint4* gp = cv.data + tb + gd.unit_off + lane;
+            uint4 u[kSliceUnits];
+            uint32_t acc = 0;
+            const bool probe = (MODE == FRZ_T_0 || MODE == FRZ_T_1 || MODE == FRZ_T_2);
+            if (gd.gunits <= kSliceUnits) {
+#pragma unroll
+                for (int k = 0; k < kSliceUnits; k++) {
+                    u[k] = make_uint4(0, 0, 0, 0);
+                    if (k < (int)gd.gunits) u[k] = __ldg(gp + (size_t)k * FRZ_GROUP);
+                }
+                if (probe) {
+#pragma unroll
+                    for (int k = 0; k < kSliceUnits; k++) {
+                        if (k < (int)gd.gunits) {
+                            const uint32_t w[4] = {u[k].x, u[k].y, u[k].z, u[k].w};
+#pragma unroll
+                            for (int j = 0; j < 4; j++) {
+                                uint32_t x = (w[j] | om0) ^ tg0;
+                                acc |= (x - 0x01010101u) & ~x;
+                                if (MODE >= FRZ_T_1) { x = (w[j] | om1) ^ tg1; acc |= (x - 0x01010101u) & ~x; }
+                                if (MODE >= FRZ_T_2) { x = (w[j] | om2) ^ tg2; acc |= (x - 0x01010101u) & ~x; }
+                            }
+                        }
+                    }
+                }
+            } else if (probe) {
+                for (uint32_t k = 0; k < gd.gunits; k++) {
+                    uint4 v = __ldg(gp + (size_t)k * FRZ_GROUP);
+                    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        uint32_t x = (w[j] | om0) ^ tg0;
+                        acc |= (x - 0x01010101u) & ~x;
+                        if (MODE >= FRZ_T_1) { x = (w[j] | om1) ^ tg1; acc |= (x - 0x01010101u) & ~x; }
+                        if (MODE >= FRZ_T_2) { x = (w[j] | om2) ^ tg2; acc |= (x - 0x01010101u) & ~x; }
+                    }
+                }
+            }
+            if (probe) {
+                // needle shorter than / equal to the typo budget matches everything (ascii_typos.rs:18,116)
+                bool trivially = (MODE == FRZ_T_1 && pat.n <= 1) || (MODE == FRZ_T_2 && pat.n <= 2);
+                pass = pass && (trivially || (acc & 0x80808080u) != 0);
+            }
+            const uint32_t ballot = __ballot_sync(0xffffffffu, pass);
+            if (ballot) {
+                uint32_t base = 0;
+                if (lane == 0) base = atomicAdd(&sh.ncand, __popc(ballot));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (pass) {
+                    uint32_t ci = base + __popc(ballot & ((1u << lane) - 1));
+                    bool in_slice = gd.gunits <= kSliceUnits;
+                    sh.cand_meta[ci] = slot | (in_slice ? 0x80000000u : 0u);
+                    if (in_slice) {
+                        uint32_t* dst = sh.slice + ci * kSliceWords;
+#pragma unroll
+                        for (int k = 0; k < kSliceUnits; k++) {
+                            if (k < (int)gd.gunits) { dst[4 * k] = u[k].x; dst[4 * k + 1] = u[k].y; dst[4 * k + 2] = u[k].z; dst[4 * k + 3] = u[k].w; }
+                        }
+                        dst[4 * gd.gunits] = 0;  // guard word
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        // ------------------------------------------------------------ phase B
+        if (threadIdx.x < sh.ncand) {
+            const uint32_t cm = sh.cand_meta[threadIdx.x];
+            const uint32_t slot = cm & 0x3ff;
+            const uint32_t meta = cv.slot_meta[(uint64_t)tile * FRZ_TILE + slot];
+            const int len = (int)(meta >> FRZ_TILE_SHIFT);
+            const uint32_t li = meta & (FRZ_TILE - 1);
+            int start = 0, end = len;
+            bool ok;
+            uint32_t lit_score = 0;
+            const bool in_slice = (cm >> 31) != 0;
+            SliceAcc sa{sh.slice + threadIdx.x * kSliceWords};
+            FrzGroupDesc gd = cv.groups[tile * FRZ_GROUPS_PER_TILE + (slot >> 5)];
+            GlobalAcc ga{cv.data + tb + gd.unit_off + (slot & 31)};
+            if (MODE == FRZ_T_0) ok = in_slice ? window_k0(sa, pat, len, &start, &end) : window_k0(ga, pat, len, &start, &end);
+            else if (MODE == FRZ_T_1) ok = in_slice ? window_k1(sa, pat, len, &start, &end) : window_k1(ga, pat, len, &start, &end);
+            else if (MODE == FRZ_T_2) ok = in_slice ? window_k2(sa, pat, len, &start, &end) : window_k2(ga, pat, len, &start, &end);
+            else if (MODE == FRZ_T_MANY) ok = in_slice ? window_many(sa, pat, len, &start, &end) : window_many(ga, pat, len, &start, &end);
+            else if (MODE == FRZ_T_LITERAL) {
+                int pos = 0;
+                ok = in_slice ? lit_find(sa, pat, len, &pos, &lit_score) : lit_find(ga, pat, len, &pos, &lit_score);
+                start = pos; end = pos + pat.n;
+            } else ok = true;  // FRZ_T_NONE: NO_PREFILTER (src/matcher/algo.rs:178)
+            if (ok) {
+                int cls;
+                if (MODE == FRZ_T_LITERAL) {
+                    // literal matches are final: carry (score, exact) through start/end
+                    cls = FRZ_C_COLS64;
+                    sh.surv_start[li] = lit_score;
+                    sh.surv_end[li] = (start == 0 && pat.n == len) ? 1u : 0u;
+                } else {
+                    // trim_haystack (src/matcher/algo.rs:331-338)
+                    start = start > 0 ? start - 1 : 0;
+                    int cols0 = pat.score_bits == 8 ? 64 : 32;   // columns of the small register variant
+                    int window = end - start;
+                    cls = window > FRZ_SW_MAX_WINDOW ? FRZ_C_GENERIC : sw_class_of(window, cols0);
+                    sh.surv_start[li] = (uint32_t)start;
+                    sh.surv_end[li] = (uint32_t)end | ((uint32_t)(end == len) << 31);
+                }
+                sh.surv_slot[li] = (uint16_t)slot;
+                atomicOr(&sh.bm_class[cls][li >> 5], 1u << (li & 31));
+            }
+        }
+        __syncthreads();
+    }
+    // ---------------------------------------------------------------- phase C
+    if (warp == 0) {
+        uint32_t any = 0, c[FRZ_N_CLASSES];
+#pragma unroll
+        for (int k = 0; k < FRZ_N_CLASSES; k++) { c[k] = sh.bm_class[k][lane]; any |= c[k]; }
+        auto excl_scan = [&](uint32_t v, uint32_t* total) {
+            uint32_t x = v;
+            for (int d = 1; d < 32; d <<= 1) {
+                uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
+                if (lane >= (uint32_t)d) x += y;
+            }
+            *total = __shfl_sync(0xffffffffu, x, 31);
+            return x - v;
+        };
+        uint32_t tot_all, tot_c[FRZ_N_CLASSES];
+        sh.pre_all[lane] = excl_scan(__popc(any), &tot_all);
+#pragma unroll
+        for (int k = 0; k < FRZ_N_CLASSES; k++) sh.pre_class[k][lane] = excl_scan(__popc(c[k]), &tot_c[k]);
+        if (lane == 0) {
+            tile_count[tile] = tot_all;
+            sh.pre_all[32] = tot_all;
+#pragma unroll
+            for (int k = 0; k < FRZ_N_CLASSES; k++)
+                sh.class_base[k] = tot_c[k] ? atomicAdd(&ctr->class_count[k], (unsigned long long)tot_c[k]) : 0ull;
+        }
+    }
+    __syncthreads();
+    FrzSurvivor* const lists[FRZ_N_CLASSES] = {surv0, surv1, surv2};
+    for (int li = threadIdx.x; li < FRZ_TILE; li += kThreads) {
+        const uint32_t wd = li >> 5, bit = 1u << (li & 31), below = bit - 1;
+        uint32_t any = 0;
+        int cls = -1;
+#pragma unroll
+        for (int k = 0; k < FRZ_N_CLASSES; k++) {
+            uint32_t b = sh.bm_class[k][wd];
+            any |= b;
+            if (b & bit) cls = k;
+        }
+        if (cls < 0) continue;
+        const uint32_t rank = sh.pre_all[wd] + __popc(any & below);
+        const uint32_t crank = sh.pre_class[cls][wd] + __popc(sh.bm_class[cls][wd] & below);
+        if (MODE == FRZ_T_LITERAL) {
+            // written by the emit kernel after the tile scan: stash in the survivor list as well
+        }
+        const unsigned long long pos = sh.class_base[cls] + crank;
+        if (pos >= surv_cap) { atomicOr(&ctr->error, FRZ_DEVERR_SURVIVOR_OVERFLOW); continue; }
+        FrzSurvivor s;
+        s.tile = tile;
+        s.slot_rank = (uint32_t)sh.surv_slot[li] | ((uint32_t)li << 10) | (rank << 20);
+        s.start = sh.surv_start[li];
+        s.end = sh.surv_end[li];
+        lists[cls][pos] = s;
+    }
+    (void)lit_out;
+}
+
+// exclusive scan of tile_count → tile_out_base; total → counters.total
+__global__ void __launch_bounds__(1024) k_tile_scan(const uint32_t* __restrict__ tile_count, uint64_t* __restrict__ out,
+                                                    uint32_t n, FrzCounters* __restrict__ ctr) {
+    __shared__ uint64_t warp_sum[32];
+    __shared__ uint64_t carry_s;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < n; base += blockDim.x) {
+        uint32_t i = base + threadIdx.x;
+        uint64_t v = i < n ? tile_count[i] : 0;
+        uint64_t x = v;
+        for (int d = 1; d < 32; d <<= 1) {
+            uint64_t y = __shfl_up_sync(0xffffffffu, x, d);
+            if (frz_lane() >= (uint32_t)d) x += y;
+        }
+        if (frz_lane() == 31) warp_sum[threadIdx.x >> 5] = x;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            uint64_t w = warp_sum[threadIdx.x], xs = w;
+            for (int d = 1; d < 32; d <<= 1) {
+                uint64_t y = __shfl_up_sync(0xffffffffu, xs, d);
+                if (frz_lane() >= (uint32_t)d) xs += y;
+            }
+            warp_sum[threadIdx.x] = xs - w;
+        }
+        __syncthreads();
+        uint64_t incl = carry_s + warp_sum[threadIdx.x >> 5] + x;
+        if (i < n) out[i] = incl - v;
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) carry_s = incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) ctr->total = carry_s;
+}
+
+}  // namespace
+
+frz_status frz_launch_prefilter(const FrzCorpusView& cv, const FrzPatternDev& pat, const uint32_t* cand_bitmap,
+                                FrzWorkspace& ws, cudaStream_t stream, FrzLaunchStats* st) {
+    if (cv.n_tiles == 0) return FRZ_OK;
+    const size_t smem = sizeof(TileShared);
+#define FRZ_PF_LAUNCH(MODE)                                                                                     \
+    do {                                                                                                        \
+        static bool attr_set = false;                                                                           \
+        if (!attr_set) {                                                                                        \
+            FRZ_CUDA_TRY(cudaFuncSetAttribute(k_prefilter<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            attr_set = true;                                                                                    \
+        }                                                                                                       \
+        k_prefilter<MODE><<<cv.n_tiles, kThreads, smem, stream>>>(cv, pat, cand_bitmap, ws.survivors[0], ws.survivors[1], \
+                                                                  ws.survivors[2], ws.survivor_cap, ws.tile_count,     \
+                                                                  ws.counters, nullptr);                        \
+    } while (0)
+    switch (pat.typo_mode) {
+        case FRZ_T_0: FRZ_PF_LAUNCH(FRZ_T_0); break;
+        case FRZ_T_1: FRZ_PF_LAUNCH(FRZ_T_1); break;
+        case FRZ_T_2: FRZ_PF_LAUNCH(FRZ_T_2); break;
+        case FRZ_T_MANY: FRZ_PF_LAUNCH(FRZ_T_MANY); break;
+        case FRZ_T_NONE: FRZ_PF_LAUNCH(FRZ_T_NONE); break;
+        case FRZ_T_LITERAL: FRZ_PF_LAUNCH(FRZ_T_LITERAL); break;
+        default: return frz_fail(FRZ_ERR_INVALID_ARG, "bad typo mode %d", pat.typo_mode);
+    }
+#undef FRZ_PF_LAUNCH
+    FRZ_CUDA_TRY(cudaGetLastError());
+    if (st) st->launches++;
+    return FRZ_OK;
+}
+
+frz_status frz_launch_tile_scan(const FrzCorpusView& cv, FrzWorkspace& ws, cudaStream_t stream, FrzLaunchStats* st) {
+    k_tile_scan<<<1, 1024, 0, stream>>>(ws.tile_count, ws.tile_out_base, cv.n_tiles, ws.counters);
+    FRZ_CUDA_TRY(cudaGetLastError());
+    if (st) st->launches++;
+    return FRZ_OK;
+}

@@ -1,0 +1,154 @@
+// sort.cu — stable descending-score sort of index-ordered matches.
+//
+// Reference replaced: radix_sort_matches (src/sort.rs:6-40): a stable 2-pass LSD radix sort on the
+// u16 score of a list that is already in index order, giving (score desc, index asc).  Any stable
+// sort by descending score yields the identical sequence; here it is a counting sort whose digit is
+// the whole score when the score bound allows it (one pass), else the reference's two 8-bit passes.
+//
+//   k_sort_hist     each "virtual warp" owns a contiguous segment and counts its digits in smem
+//   k_sort_scan     per-digit exclusive prefix over the segments + descending exclusive prefix
+//                   over digits
+//   k_sort_scatter  each virtual warp re-walks its segment IN ORDER, 32 elements at a time;
+//                   __match_any_sync gives the in-warp stable rank, a per-warp counter array the rest
+//
+// The element count lives in device memory (it is produced by the previous stage), so the whole
+// match_list pipeline runs without a host round trip until the final copy-out.
+#include "frz_device.cuh"
+#include "frz_host.h"
+
+namespace {
+
+constexpr int kSortBlocks = 32;
+constexpr int kSortWarps = 8;
+constexpr int kV = kSortBlocks * kSortWarps;  // virtual warps = segments
+constexpr int kMaxBins = 1024;
+
+__device__ __forceinline__ void segment_of(unsigned long long n, int v, unsigned long long* lo, unsigned long long* hi) {
+    unsigned long long seg = (n + kV - 1) / kV;
+    seg = (seg + 31) & ~31ull;
+    unsigned long long a = seg * v;
+    *lo = a < n ? a : n;
+    unsigned long long b = a + seg;
+    *hi = b < n ? b : n;
+}
+
+__device__ __forceinline__ uint32_t digit_of(const FrzMatchDev& m, int shift, uint32_t mask) {
+    return ((uint32_t)m.score >> shift) & mask;
+}
+
+__global__ void __launch_bounds__(kSortWarps * 32) k_sort_hist(const FrzMatchDev* __restrict__ in,
+                                                               const unsigned long long* __restrict__ n_ptr, int shift,
+                                                               int bins, uint32_t* __restrict__ hist) {
+    extern __shared__ uint32_t sm[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t* cnt = sm + warp * bins;
+    for (int d = lane; d < bins; d += 32) cnt[d] = 0;
+    __syncwarp();
+    const int v = blockIdx.x * kSortWarps + warp;
+    unsigned long long lo, hi;
+    segment_of(*n_ptr, v, &lo, &hi);
+    const uint32_t mask = (uint32_t)bins - 1;
+    for (unsigned long long i = lo + lane; i < hi; i += 32) atomicAdd(&cnt[digit_of(in[i], shift, mask)], 1u);
+    __syncwarp();
+    for (int d = lane; d < bins; d += 32) hist[(size_t)d * kV + v] = cnt[d];
+}
+
+// hist[d][v] → exclusive prefix over v (in place); digit_base[d] = #elements with digit > d
+__global__ void __launch_bounds__(1024) k_sort_scan(uint32_t* __restrict__ hist, int bins, uint32_t* __restrict__ digit_base) {
+    __shared__ uint32_t totals[kMaxBins];
+    __shared__ uint32_t wsum[32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int PER = kV / 32;  // entries per lane
+    for (int d = warp; d < bins; d += 32) {
+        uint32_t* row = hist + (size_t)d * kV;
+        uint32_t vals[PER], s = 0;
+#pragma unroll
+        for (int k = 0; k < PER; k++) { vals[k] = row[lane * PER + k]; s += vals[k]; }
+        uint32_t x = s;
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += y;
+        }
+        uint32_t run = x - s;
+#pragma unroll
+        for (int k = 0; k < PER; k++) { row[lane * PER + k] = run; run += vals[k]; }
+        if (lane == 31) totals[d] = x;
+    }
+    __syncthreads();
+    // descending exclusive prefix over digits: thread t ↔ digit bins-1-t
+    const int t = threadIdx.x;
+    uint32_t v = t < bins ? totals[bins - 1 - t] : 0;
+    uint32_t x = v;
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+    }
+    if (lane == 31) wsum[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = wsum[lane], xs = w;
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t y = __shfl_up_sync(0xffffffffu, xs, o);
+            if (lane >= o) xs += y;
+        }
+        wsum[lane] = xs - w;
+    }
+    __syncthreads();
+    if (t < bins) digit_base[bins - 1 - t] = wsum[warp] + x - v;
+}
+
+__global__ void __launch_bounds__(kSortWarps * 32) k_sort_scatter(const FrzMatchDev* __restrict__ in, FrzMatchDev* __restrict__ out,
+                                                                  const unsigned long long* __restrict__ n_ptr, int shift, int bins,
+                                                                  const uint32_t* __restrict__ hist,
+                                                                  const uint32_t* __restrict__ digit_base) {
+    extern __shared__ uint32_t sm[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t* cnt = sm + warp * bins;
+    const int v = blockIdx.x * kSortWarps + warp;
+    for (int d = lane; d < bins; d += 32) cnt[d] = digit_base[d] + hist[(size_t)d * kV + v];
+    __syncwarp();
+    unsigned long long lo, hi;
+    segment_of(*n_ptr, v, &lo, &hi);
+    const uint32_t mask = (uint32_t)bins - 1;
+    for (unsigned long long base = lo; base < hi; base += 32) {
+        const unsigned long long i = base + lane;
+        const bool valid = i < hi;
+        FrzMatchDev m;
+        uint32_t d = (uint32_t)bins + lane;  // sentinel: matches nobody
+        if (valid) { m = in[i]; d = digit_of(m, shift, mask); }
+        const uint32_t peers = __match_any_sync(0xffffffffu, d);
+        const uint32_t rank = __popc(peers & ((1u << lane) - 1));
+        uint32_t pos = 0;
+        if (valid) pos = cnt[d] + rank;
+        __syncwarp();
+        if (valid && rank == 0) cnt[d] += __popc(peers);
+        __syncwarp();
+        if (valid) out[pos] = m;
+    }
+}
+
+}  // namespace
+
+// n_ptr: device pointer to the element count.  score_bound: host-known upper bound of any score.
+frz_status frz_launch_sort_by_score_dev(const FrzMatchDev* d_in, FrzMatchDev* d_tmp, FrzMatchDev* d_out,
+                                        const unsigned long long* n_ptr, uint32_t score_bound, FrzWorkspace& ws,
+                                        cudaStream_t stream, FrzLaunchStats* st) {
+    auto pass = [&](const FrzMatchDev* src, FrzMatchDev* dst, int shift, int bins) -> frz_status {
+        const size_t smem = (size_t)kSortWarps * bins * sizeof(uint32_t);
+        k_sort_hist<<<kSortBlocks, kSortWarps * 32, smem, stream>>>(src, n_ptr, shift, bins, ws.sort_hist);
+        k_sort_scan<<<1, 1024, 0, stream>>>(ws.sort_hist, bins, ws.sort_hist + (size_t)kMaxBins * kV);
+        k_sort_scatter<<<kSortBlocks, kSortWarps * 32, smem, stream>>>(src, dst, n_ptr, shift, bins, ws.sort_hist,
+                                                                       ws.sort_hist + (size_t)kMaxBins * kV);
+        FRZ_CUDA_TRY(cudaGetLastError());
+        if (st) st->launches += 3;
+        return FRZ_OK;
+    };
+    if (score_bound < 256) return pass(d_in, d_out, 0, 256);
+    if (score_bound < 512) return pass(d_in, d_out, 0, 512);
+    if (score_bound < 1024) return pass(d_in, d_out, 0, 1024);
+    // the reference's two 8-bit LSD passes (src/sort.rs:8-39)
+    FRZ_TRY(pass(d_in, d_tmp, 0, 256));
+    return pass(d_tmp, d_out, 8, 256);
+}
+
+size_t frz_sort_hist_words() { return (size_t)kMaxBins * kV + kMaxBins; }

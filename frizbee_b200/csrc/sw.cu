@@ -1,0 +1,498 @@
+// sw.cu — stage 2 of match_list: affine-gap Smith-Waterman score of each surviving window,
+// exact flag, and the Match record written straight to its index-ordered position.
+//
+// Reference path replaced: MatcherImpl::smith_waterman_one (src/matcher/algo.rs:229-263) →
+// SmithWaterman<B>::score_haystack (src/smith_waterman/algo/ascii.rs:10-158) with
+// propagate_{8,16,32,64}_lane (src/smith_waterman/algo/ascii_gap.rs:11-105).
+//
+// One window per thread.  The score row lives in registers as packed signed 16-bit cells
+// (2 per register) and every recurrence step is one Blackwell DPX instruction:
+//     diag        max(prev_shifted + delta, 0)                 VIADDMNMX.S16x2.RELU
+//     up ⊔ diag   max(prev + up_pen, diag, 0)                  VIADDMNMX.S16x2.RELU
+//     gap step    max(row_shifted_by_s + pen_s, row, 0)        VIADDMNMX.S16x2.RELU
+// (u8x4 SIMD-in-register intrinsics compile to 5-8 instruction emulations on sm_100a; the 16x2
+// DPX forms are single instructions — see DESIGN.md §5.)
+//
+// The reference's result depends on its SIMD width: the horizontal gap propagation is a log-step
+// doubling scan over LANES-cell chunks.  The kernel is templated on that LANES and evaluates the
+// matrix row-major (bit-identical to the reference's chunk-major order: every (row, chunk) block
+// depends only on (row-1, chunk), the last lane of (row-1, chunk-1) and (row, chunk-1)).
+// Lanes past the end of the window hold zero bytes and are scanned and max-ed like real lanes,
+// exactly as in the reference (zero-filled tail loads, src/smith_waterman/backend/scalar.rs:78-85).
+//
+// u8 and u16 reference families share this kernel: u8 cell values are exact in 16-bit lanes as
+// long as no u8 add can wrap; when the host cannot prove that (pat.wrap8) the WRAP8 variant
+// re-applies the 8-bit wrap after every add.
+#include "frz_device.cuh"
+#include "frz_host.h"
+
+namespace {
+
+constexpr int kSwThreads = 128;
+
+__device__ __forceinline__ uint32_t splat16(int v) { return ((uint32_t)v & 0xffffu) * 0x00010001u; }
+
+// per-16-bit-lane: 0xFFFF where x == 0 else 0   (x lanes are in 0..255)
+__device__ __forceinline__ uint32_t eqmask16(uint32_t x) {
+    return __byte_perm(__vadd2(x, 0xFFFFFFFFu), 0, 0xBB99);  // (x-1) sign → replicate
+}
+__device__ __forceinline__ uint32_t sel(uint32_t mask, uint32_t a, uint32_t b) { return (mask & a) | (~mask & b); }
+
+// max(a + b, c, 0) per signed 16-bit lane
+__device__ __forceinline__ uint32_t addmax_relu(uint32_t a, uint32_t b, uint32_t c) { return __viaddmax_s16x2_relu(a, b, c); }
+
+// Register array, or (for the 128-column variant, whose two score rows already fill the register
+// file) a conflict-free shared-memory column [r][thread].
+template <int R, bool SMEM>
+struct RowStore;
+template <int R>
+struct RowStore<R, false> {
+    uint32_t v[R];
+    __device__ __forceinline__ RowStore(uint32_t*) {}
+    __device__ __forceinline__ uint32_t get(int r) const { return v[r]; }
+    __device__ __forceinline__ void set(int r, uint32_t x) { v[r] = x; }
+};
+template <int R>
+struct RowStore<R, true> {
+    uint32_t* base;
+    __device__ __forceinline__ RowStore(uint32_t* b) : base(b + threadIdx.x) {}
+    __device__ __forceinline__ uint32_t get(int r) const { return base[r * kSwThreads]; }
+    __device__ __forceinline__ void set(int r, uint32_t x) { base[r * kSwThreads] = x; }
+};
+
+template <int LANES, int COLS, bool WRAP8>
+struct SwCore {
+    static constexpr int R = COLS / 2;     // registers per row
+    static constexpr int RL = LANES / 2;   // registers per chunk
+    static constexpr int NCH = COLS / LANES;
+    static constexpr bool SMEM = COLS > 64;
+    static constexpr size_t smem_bytes = SMEM ? 2 * R * kSwThreads * sizeof(uint32_t) : 0;
+
+    // hw: COLS/4 words of window bytes, zero beyond W
+    static __device__ uint32_t run(const uint32_t (&hw)[COLS / 4], int W, const FrzPatternDev& p, bool include_prefix,
+                                   uint32_t* smem) {
+        RowStore<R, SMEM> h16s(smem), Bs(smem + R * kSwThreads);
+        // expand bytes to one per 16-bit lane
+#pragma unroll
+        for (int i = 0; i < COLS / 4; i++) {
+            h16s.set(2 * i, __byte_perm(hw[i], 0, 0x4140));
+            h16s.set(2 * i + 1, __byte_perm(hw[i], 0, 0x4342));
+        }
+        // ---- per-column bonus (ascii.rs:64-101) ----
+        {
+            const uint32_t capb = splat16(p.cap_bonus), delb = splat16(p.delim_bonus), base = splat16(p.match_x);
+            uint32_t prev_lower = 0, prev_delim = 0;  // masks of the previous register
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                const uint32_t b = h16s.get(r);
+                // range tests on lanes in 0..255:  lo <= b <= hi  ⇔  (b-lo) >= 0 && (b-hi-1) < 0
+                auto in_range = [&](int lo, int hi) {
+                    uint32_t t = __vadd2(b, splat16(-lo));
+                    uint32_t d = __vadd2(b, splat16(-(hi + 1)));
+                    return __byte_perm(d & ~t, 0, 0xBB99);
+                };
+                const uint32_t upper = in_range('A', 'Z');
+                const uint32_t lower = in_range('a', 'z');
+                const uint32_t digit = in_range('0', '9');
+                const uint32_t high = __byte_perm(__vadd2(b, splat16(-128)), 0, 0xBB99) ^ 0xFFFFFFFFu;  // b >= 128
+                const uint32_t delim = ~(upper | lower | digit | high);
+                const uint32_t lower_sh = __byte_perm(prev_lower, lower, 0x5432);
+                const uint32_t delim_sh = __byte_perm(prev_delim, delim, 0x5432);
+                const uint32_t cap_m = upper & lower_sh;
+                const uint32_t del_m = delim_sh & ~delim;
+                uint32_t bonus = __vadd2(__vadd2(del_m & delb, cap_m & capb), base);
+                if (r == 0 && include_prefix) bonus = __vadd2(bonus, (uint32_t)p.prefix_bonus & 0xffffu);
+                if (WRAP8) bonus &= 0x00FF00FFu;
+                Bs.set(r, bonus);
+                prev_lower = lower;
+                prev_delim = delim;
+            }
+        }
+        // ---- constants ----
+        const uint32_t neg_mis = splat16(-p.mismatch);
+        const uint32_t ex_add = splat16(p.case_bonus - p.mismatch);       // exact-case match: +case -mismatch
+        const uint32_t up_plain = splat16(-p.gap_extend);
+        const uint32_t up_open = splat16(-(p.gap_extend + p.gap_open_x));
+        uint32_t H[R], M[R];
+#pragma unroll
+        for (int r = 0; r < R; r++) { H[r] = 0; M[r] = 0; }
+
+        for (int i = 0; i < p.n; i++) {
+            const uint32_t om16 = splat16(p.om[i]), tg16 = splat16(p.tg[i]), c16 = splat16(p.c[i]);
+            const bool folded = p.om[i] != 0;  // case-insensitive letter: exact-case mask differs from match mask
+            // ---- diagonal + up, in place, high register first (H[r-1] must still hold row i-1) ----
+#pragma unroll
+            for (int r = R - 1; r >= 0; r--) {
+                const uint32_t hv = h16s.get(r), Bv = Bs.get(r);
+                const uint32_t mmn = eqmask16((hv | om16) ^ tg16);
+                const uint32_t ex = folded ? eqmask16(hv ^ c16) : mmn;
+                const uint32_t prevs = r > 0 ? __byte_perm(H[r - 1], H[r], 0x5432) : __byte_perm(0u, H[0], 0x5432);
+                uint32_t diag;
+                if (!WRAP8) {
+                    const uint32_t delta = __vadd2(mmn & Bv, sel(ex, ex_add, neg_mis));
+                    diag = addmax_relu(prevs, delta, 0u);
+                } else {
+                    uint32_t d = __vadd2(prevs, mmn & Bv) & 0x00FF00FFu;        // wrapping u8 add
+                    d = addmax_relu(d, neg_mis, 0u);                             // saturating sub
+                    diag = __vadd2(d, ex & splat16(p.case_bonus)) & 0x00FF00FFu;  // wrapping u8 add
+                }
+                const uint32_t upd = sel(M[r], up_open, up_plain);               // M[r] still row i-1
+                H[r] = addmax_relu(H[r], upd, diag);
+                M[r] = mmn;
+            }
+            // ---- horizontal gap propagation, chunk by chunk (ascii_gap.rs gap_step!) ----
+#pragma unroll
+            for (int c = 0; c < NCH; c++) {
+                const int lo = c * RL, hi = lo + RL;
+#pragma unroll
+                for (int s = 1; s < LANES; s <<= 1) {
+                    const uint32_t penA = splat16(-(s * p.gap_extend));
+                    const uint32_t penB = splat16(-(s * p.gap_extend + p.gap_open_x));
+#pragma unroll
+                    for (int r = hi - 1; r >= lo; r--) {
+                        uint32_t sh, smm;
+                        if (s == 1) {
+                            if (r == 0) { sh = __byte_perm(0u, H[0], 0x5432); smm = __byte_perm(0u, M[0], 0x5432); }
+                            else { sh = __byte_perm(H[r - 1], H[r], 0x5432); smm = __byte_perm(M[r - 1], M[r], 0x5432); }
+                        } else {
+                            const int src = r - s / 2;
+                            if (src < 0) continue;  // shifted-in lanes of the first chunk are zero: no-op
+                            sh = H[src];
+                            smm = M[src];
+                        }
+                        H[r] = addmax_relu(sh, sel(smm, penB, penA), H[r]);
+                    }
+                }
+            }
+        }
+        // ---- max over the chunks the reference actually has: ceil(W / LANES) ----
+        const int nch = (W + LANES - 1) / LANES;
+        uint32_t mx = 0;
+#pragma unroll
+        for (int r = 0; r < R; r++)
+            if (r < nch * RL) mx = __vmaxu2(mx, H[r]);
+        return max(mx & 0xffffu, mx >> 16);
+    }
+};
+
+// Loads window bytes [start, start+W) of (tile, slot) into COLS/4 zero-padded words.
+template <int COLS>
+__device__ __forceinline__ void load_window(const FrzCorpusView& cv, uint32_t tile, uint32_t slot, uint32_t start, int W,
+                                            uint32_t (&hw)[COLS / 4]) {
+    constexpr int NU = COLS / 16 + 1;
+    const uint32_t u0 = start >> 4;
+    const int last_u = W > 0 ? (int)((start + W - 1) >> 4) - (int)u0 : -1;
+    const uint4* base = frz_unit_ptr(cv, tile, slot, u0);
+    uint32_t w[NU * 4 + 4];
+#pragma unroll
+    for (int k = 0; k < NU; k++) {
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (k <= last_u) v = __ldg(base + (size_t)k * FRZ_GROUP);
+        w[4 * k] = v.x; w[4 * k + 1] = v.y; w[4 * k + 2] = v.z; w[4 * k + 3] = v.w;
+    }
+#pragma unroll
+    for (int k = NU * 4; k < NU * 4 + 4; k++) w[k] = 0;
+    const uint32_t ws = (start & 15) >> 2, bs = (start & 3) * 8;
+    if (ws & 2) {
+#pragma unroll
+        for (int k = 0; k < NU * 4 + 2; k++) w[k] = w[k + 2];
+    }
+    if (ws & 1) {
+#pragma unroll
+        for (int k = 0; k < NU * 4 + 3; k++) w[k] = w[k + 1];
+    }
+#pragma unroll
+    for (int k = 0; k < COLS / 4; k++) {
+        uint32_t v = __funnelshift_r(w[k], w[k + 1], bs);
+        int rem = W - 4 * k;
+        if (rem <= 0) v = 0;
+        else if (rem < 4) v &= (1u << (8 * rem)) - 1;
+        hw[k] = v;
+    }
+}
+
+// exact = include_exact && needle_bytes == window (src/matcher/algo.rs:245); byte-exact compare
+template <int NW>
+__device__ __forceinline__ bool window_equals_needle(const uint32_t (&hw)[NW], int W, const FrzPatternDev& p) {
+    if (W != p.n) return false;
+    bool eq = true;
+#pragma unroll
+    for (int k = 0; k < NW; k++) {
+        uint32_t nw = 0;
+#pragma unroll
+        for (int b = 0; b < 4; b++)
+            if (4 * k + b < p.n && 4 * k + b < FRZ_MAX_NEEDLE) nw |= (uint32_t)p.c[4 * k + b] << (8 * b);
+        if (4 * k < p.n) eq = eq && (hw[k] == nw);
+    }
+    return eq;
+}
+
+__device__ __forceinline__ void emit_match(const FrzSurvivor& rec, uint32_t score, bool exact, uint32_t index_offset,
+                                           bool reversed, const uint64_t* __restrict__ tile_out_base,
+                                           const FrzCounters* __restrict__ ctr, FrzMatchDev* __restrict__ out) {
+    const uint32_t li = (rec.slot_rank >> 10) & 0x3ff, rank = rec.slot_rank >> 20;
+    uint64_t pos = tile_out_base[rec.tile] + rank;
+    if (reversed) pos = ctr->total - 1 - pos;
+    FrzMatchDev m;
+    m.index = index_offset + rec.tile * FRZ_TILE + li;
+    m.score = (uint16_t)score;
+    m.exact = exact ? 1 : 0;
+    m.pad = 0;
+    out[pos] = m;
+}
+
+template <int LANES, int COLS, bool WRAP8>
+__global__ void __launch_bounds__(kSwThreads) k_sw(const FrzCorpusView cv, const __grid_constant__ FrzPatternDev pat,
+                                                   const FrzSurvivor* __restrict__ surv, int cls,
+                                                   const uint64_t* __restrict__ tile_out_base, FrzCounters* __restrict__ ctr,
+                                                   uint32_t index_offset, int reversed, FrzMatchDev* __restrict__ out) {
+    extern __shared__ __align__(16) uint32_t sw_smem[];
+    const unsigned long long count = ctr->class_count[cls];
+    uint32_t local_max = 0;
+    for (unsigned long long j = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; j < count;
+         j += (unsigned long long)gridDim.x * blockDim.x) {
+        const FrzSurvivor rec = surv[j];
+        const uint32_t slot = rec.slot_rank & 0x3ff;
+        const uint32_t start = rec.start, end = rec.end & 0x7fffffffu;
+        const bool full_end = (rec.end >> 31) != 0;
+        const int W = (int)(end - start);
+        uint32_t hw[COLS / 4];
+        load_window<COLS>(cv, rec.tile, slot, start, W, hw);
+        uint32_t score = SwCore<LANES, COLS, WRAP8>::run(hw, W, pat, start == 0, sw_smem);
+        bool exact = start == 0 && full_end && window_equals_needle(hw, W, pat);
+        if (exact) score = (score + pat.exact_bonus) & 0xffffu;
+        emit_match(rec, score, exact, index_offset, reversed != 0, tile_out_base, ctr, out);
+        local_max = max(local_max, score);
+    }
+    local_max = __reduce_max_sync(0xffffffffu, local_max);
+    if (frz_lane() == 0 && local_max) atomicMax(&ctr->max_score, local_max);
+}
+
+// ---- generic fallback: windows of 129..1024 bytes (row-major, local-memory rows) and the
+// ---- greedy scorer for windows > 1024 (src/smith_waterman/greedy.rs:7-91).  One window per thread.
+constexpr int kGenCols = FRZ_SW_MAX_WINDOW + 64;
+
+__device__ __forceinline__ uint32_t hay_byte(const uint4* base, uint32_t i) {
+    return (reinterpret_cast<const uint32_t*>(base + (size_t)(i >> 4) * FRZ_GROUP)[(i >> 2) & 3] >> ((i & 3) * 8)) & 0xff;
+}
+
+__device__ int greedy_score(const uint4* base, uint32_t start, int W, const FrzPatternDev& p, bool include_prefix) {
+    const int n = p.n;
+    if (n > W) return -1;
+    auto sat_add = [](uint32_t a, uint32_t b) { uint32_t r = a + b; return r > 0xffffu ? 0xffffu : r; };
+    auto sat_sub = [](uint32_t a, uint32_t b) { return a > b ? a - b : 0u; };
+    uint32_t score = 0;
+    int hi = 0;
+    bool delim_enabled = false, prev_lower = false, prev_delim = false;
+    for (int ni = 0; ni < n; ni++) {
+        const int hstart = hi;
+        bool matched = false;
+        while (hi <= W - n + ni) {
+            const uint32_t hc = hay_byte(base, start + hi);
+            const bool is_digit = hc - '0' <= 9u, is_upper = hc - 'A' <= 25u, is_lower = hc - 'a' <= 25u;
+            const bool is_delim = hc < 128 && !(is_lower || is_upper || is_digit);
+            if (!is_delim) delim_enabled = true;
+            if (p.c[ni] != hc && p.flip[ni] != hc) {
+                prev_delim = delim_enabled && is_delim;
+                prev_lower = is_lower;
+                hi++;
+                continue;
+            }
+            score = sat_add(score, p.raw_match);
+            if (hi != hstart && ni != 0) {
+                uint32_t gl = (uint32_t)(hi - hstart);
+                gl = gl > 0 ? gl - 1 : 0;
+                if (gl > 0xffffu) gl = 0xffffu;
+                uint32_t mul = (uint32_t)p.raw_gap_extend * gl;
+                if (mul > 0xffffu) mul = 0xffffu;
+                score = sat_sub(score, sat_add(p.raw_gap_open, mul));
+            }
+            if (p.c[ni] == hc) score = sat_add(score, p.raw_case);
+            if (is_upper && prev_lower) score = sat_add(score, p.raw_cap);
+            if (include_prefix && hi == 0) score = sat_add(score, p.raw_prefix);
+            if (prev_delim && !is_delim) score = sat_add(score, p.raw_delim);
+            prev_delim = delim_enabled && is_delim;
+            prev_lower = is_lower;
+            hi++;
+            matched = true;
+            break;
+        }
+        if (!matched) return -1;
+    }
+    return (int)score;
+}
+
+__global__ void __launch_bounds__(64) k_sw_generic(const FrzCorpusView cv, const __grid_constant__ FrzPatternDev pat,
+                                                   const FrzSurvivor* __restrict__ surv, int cls,
+                                                   const uint64_t* __restrict__ tile_out_base, FrzCounters* __restrict__ ctr,
+                                                   uint32_t index_offset, int reversed, FrzMatchDev* __restrict__ out) {
+    const unsigned long long count = ctr->class_count[cls];
+    const int L = pat.sw_lanes;
+    const uint32_t lane_mask = pat.score_bits == 8 ? 0xffu : 0xffffu;  // real element width
+    uint32_t local_max = 0;
+    for (unsigned long long j = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; j < count;
+         j += (unsigned long long)gridDim.x * blockDim.x) {
+        const FrzSurvivor rec = surv[j];
+        const uint32_t slot = rec.slot_rank & 0x3ff;
+        const uint32_t start = rec.start, end = rec.end & 0x7fffffffu;
+        const bool full_end = (rec.end >> 31) != 0;
+        const int W = (int)(end - start);
+        const uint4* base = frz_unit_ptr(cv, rec.tile, slot, 0);
+        const bool include_prefix = start == 0;
+        uint32_t score;
+        if (W > FRZ_SW_MAX_WINDOW) {
+            int g = greedy_score(base, start, W, pat, include_prefix);
+            score = g < 0 ? 0u : (uint32_t)g;
+        } else {
+            // literal row-major restatement with true element-width arithmetic
+            uint16_t Hp[kGenCols], Hc[kGenCols], bon[kGenCols];
+            uint8_t Mp[kGenCols], Mc[kGenCols], hb[kGenCols];
+            const int nch = (W + L - 1) / L, cols = nch * L;
+            bool pl = false, pd = false;
+            for (int c = 0; c < cols; c++) {
+                uint32_t b = c < W ? hay_byte(base, start + c) : 0;
+                hb[c] = (uint8_t)b;
+                bool up = b - 'A' <= 25u, lo = b - 'a' <= 25u, dg = b - '0' <= 9u;
+                bool dl = !(up || lo || dg || b > 127);
+                // wrapping adds in the element width (ascii.rs:98-101)
+                uint32_t bo = 0;
+                if (pd && !dl) bo = (bo + pat.delim_bonus) & lane_mask;
+                if (up && pl) bo = (bo + pat.cap_bonus) & lane_mask;
+                if (c == 0 && include_prefix) bo = (bo + pat.prefix_bonus) & lane_mask;
+                bo = (bo + pat.match_x) & lane_mask;
+                bon[c] = (uint16_t)bo;
+                Hp[c] = 0; Mp[c] = 0;
+                pl = lo; pd = dl;
+            }
+            auto bonus_at = [&](int c) -> uint32_t { return bon[c]; };
+            for (int i = 0; i < pat.n; i++) {
+                for (int c = 0; c < cols; c++) {
+                    uint32_t b = hb[c];
+                    bool e = b == pat.c[i], f = b == pat.flip[i];
+                    bool m = e || f;
+                    uint32_t dg = c > 0 ? Hp[c - 1] : 0;
+                    if (m) dg = (dg + bonus_at(c)) & lane_mask;
+                    dg = dg > (uint32_t)pat.mismatch ? dg - pat.mismatch : 0;
+                    if (e) dg = (dg + pat.case_bonus) & lane_mask;
+                    uint32_t upv = Hp[c];
+                    upv = upv > (uint32_t)pat.gap_extend ? upv - pat.gap_extend : 0;
+                    if (Mp[c]) upv = upv > (uint32_t)pat.gap_open_x ? upv - pat.gap_open_x : 0;
+                    Hc[c] = (uint16_t)max(dg, upv);
+                    Mc[c] = m;
+                }
+                for (int ch = 0; ch < nch; ch++) {
+                    const int lo = ch * L;
+                    uint32_t gex = pat.gap_extend;
+                    for (int s = 1; s < L; s <<= 1) {
+                        for (int c = lo + L - 1; c >= lo; c--) {
+                            int src = c - s;
+                            if (src < 0) continue;
+                            if (src < lo && src < lo - L) continue;  // only the adjacent chunk feeds in
+                            uint32_t pen = (gex + (Mc[src] ? (uint32_t)pat.gap_open_x : 0u)) & lane_mask;
+                            uint32_t v = Hc[src];
+                            v = v > pen ? v - pen : 0;
+                            if (v > Hc[c]) Hc[c] = (uint16_t)v;
+                        }
+                        gex = (gex + gex) & lane_mask;
+                    }
+                }
+                for (int c = 0; c < cols; c++) { Hp[c] = Hc[c]; Mp[c] = Mc[c]; }
+            }
+            uint32_t mx = 0;
+            for (int c = 0; c < cols; c++) mx = max(mx, (uint32_t)Hp[c]);
+            score = mx;
+        }
+        bool exact = false;
+        if (start == 0 && full_end && W == pat.n) {
+            exact = true;
+            for (int k = 0; k < pat.n; k++) exact = exact && hay_byte(base, k) == pat.c[k];
+        }
+        if (exact) score = (score + pat.exact_bonus) & 0xffffu;
+        emit_match(rec, score, exact, index_offset, reversed != 0, tile_out_base, ctr, out);
+        local_max = max(local_max, score);
+    }
+    if (local_max) atomicMax(&ctr->max_score, local_max);
+}
+
+// literal patterns: the prefilter stage already produced (score, exact); just place the match
+__global__ void __launch_bounds__(256) k_emit_literal(const FrzSurvivor* __restrict__ surv,
+                                                      const uint64_t* __restrict__ tile_out_base, FrzCounters* __restrict__ ctr,
+                                                      uint32_t index_offset, int reversed, FrzMatchDev* __restrict__ out) {
+    const unsigned long long count = ctr->class_count[FRZ_C_COLS64];
+    uint32_t local_max = 0;
+    for (unsigned long long j = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; j < count;
+         j += (unsigned long long)gridDim.x * blockDim.x) {
+        const FrzSurvivor rec = surv[j];
+        emit_match(rec, rec.start, rec.end != 0, index_offset, reversed != 0, tile_out_base, ctr, out);
+        local_max = max(local_max, rec.start);
+    }
+    if (local_max) atomicMax(&ctr->max_score, local_max);
+}
+
+int g_sm_count = 0;
+int sm_count() {
+    if (!g_sm_count) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
+        if (g_sm_count <= 0) g_sm_count = 148;
+    }
+    return g_sm_count;
+}
+
+template <int LANES, int COLS>
+frz_status launch_sw_variant(const FrzCorpusView& cv, const FrzPatternDev& pat, int cls, uint32_t index_offset, bool reversed,
+                             FrzWorkspace& ws, FrzMatchDev* d_out, cudaStream_t stream) {
+    // persistent grid: a multiple of the SM count; survivors are strided over it
+    const int blocks = sm_count() * 4;
+    const size_t smem = SwCore<LANES, COLS, false>::smem_bytes;
+    if (smem > 48 * 1024) {
+        static bool attr_set = false;
+        if (!attr_set) {
+            FRZ_CUDA_TRY(cudaFuncSetAttribute(k_sw<LANES, COLS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            FRZ_CUDA_TRY(cudaFuncSetAttribute(k_sw<LANES, COLS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attr_set = true;
+        }
+    }
+    if (pat.wrap8)
+        k_sw<LANES, COLS, true><<<blocks, kSwThreads, smem, stream>>>(cv, pat, ws.survivors[cls], cls, ws.tile_out_base, ws.counters,
+                                                                   index_offset, reversed ? 1 : 0, d_out);
+    else
+        k_sw<LANES, COLS, false><<<blocks, kSwThreads, smem, stream>>>(cv, pat, ws.survivors[cls], cls, ws.tile_out_base, ws.counters,
+                                                                    index_offset, reversed ? 1 : 0, d_out);
+    FRZ_CUDA_TRY(cudaGetLastError());
+    return FRZ_OK;
+}
+
+template <int COLS>
+frz_status launch_sw_cols(const FrzCorpusView& cv, const FrzPatternDev& pat, int cls, uint32_t index_offset, bool reversed,
+                          FrzWorkspace& ws, FrzMatchDev* d_out, cudaStream_t stream) {
+    switch (pat.sw_lanes) {
+        case 64: return launch_sw_variant<64, COLS>(cv, pat, cls, index_offset, reversed, ws, d_out, stream);
+        case 32: return launch_sw_variant<32, COLS>(cv, pat, cls, index_offset, reversed, ws, d_out, stream);
+        case 16: return launch_sw_variant<16, COLS>(cv, pat, cls, index_offset, reversed, ws, d_out, stream);
+        case 8: return launch_sw_variant<8, COLS>(cv, pat, cls, index_offset, reversed, ws, d_out, stream);
+        default: return frz_fail(FRZ_ERR_INVALID_ARG, "unsupported lane count %d", pat.sw_lanes);
+    }
+}
+
+}  // namespace
+
+frz_status frz_launch_sw(const FrzCorpusView& cv, const FrzPatternDev& pat, uint32_t index_offset, bool reversed,
+                         FrzWorkspace& ws, FrzMatchDev* d_out, cudaStream_t stream, FrzLaunchStats* st) {
+    if (cv.n_tiles == 0) return FRZ_OK;
+    if (pat.typo_mode == FRZ_T_LITERAL) {
+        k_emit_literal<<<sm_count() * 4, 256, 0, stream>>>(ws.survivors[FRZ_C_COLS64], ws.tile_out_base, ws.counters,
+                                                           index_offset, reversed ? 1 : 0, d_out);
+        FRZ_CUDA_TRY(cudaGetLastError());
+        if (st) st->launches++;
+        return FRZ_OK;
+    }
+    FRZ_TRY(launch_sw_cols<64>(cv, pat, FRZ_C_COLS64, index_offset, reversed, ws, d_out, stream));
+    FRZ_TRY(launch_sw_cols<128>(cv, pat, FRZ_C_COLS128, index_offset, reversed, ws, d_out, stream));
+    k_sw_generic<<<sm_count() * 2, 64, 0, stream>>>(cv, pat, ws.survivors[FRZ_C_GENERIC], FRZ_C_GENERIC, ws.tile_out_base,
+                                                    ws.counters, index_offset, reversed ? 1 : 0, d_out);
+    FRZ_CUDA_TRY(cudaGetLastError());
+    if (st) st->launches += 3;
+    return FRZ_OK;
+}

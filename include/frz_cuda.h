@@ -28,6 +28,11 @@ extern "C" {
 #endif
 
 #define FRZ_ABI_VERSION 1
+#if defined(__GNUC__)
+#define FRZ_API __attribute__((visibility("default")))
+#else
+#define FRZ_API
+#endif
 
 /* ------------------------------------------------------------------ status */
 
@@ -52,9 +57,9 @@ typedef enum frz_status {
 } frz_status;
 
 /* thread-local, human-readable detail for the last non-OK status */
-const char* frz_last_error(void);
-const char* frz_status_str(frz_status s);
-int frz_abi_version(void);
+FRZ_API const char* frz_last_error(void);
+FRZ_API const char* frz_status_str(frz_status s);
+FRZ_API int frz_abi_version(void);
 
 /* ------------------------------------------------------------------- types */
 
@@ -124,21 +129,21 @@ typedef struct frz_pattern {
     frz_scoring scoring;
 } frz_pattern;
 
-void frz_config_default(frz_config* out);   /* Config::default()  src/lib.rs:260-271 */
-void frz_scoring_default(frz_scoring* out); /* Scoring::default() src/lib.rs:461-478 */
+FRZ_API void frz_config_default(frz_config* out);   /* Config::default()  src/lib.rs:260-271 */
+FRZ_API void frz_scoring_default(frz_scoring* out); /* Scoring::default() src/lib.rs:461-478 */
 
 /* ------------------------------------------------------- query-atom parser */
 
 /* Owned parse result of Pattern::parse_query (src/pattern.rs:190-222). */
 typedef struct frz_query frz_query;
-frz_status frz_parse_query(const uint8_t* query, size_t len, frz_query** out);
+FRZ_API frz_status frz_parse_query(const uint8_t* query, size_t len, frz_query** out);
 /* Pattern::parse (src/pattern.rs:100-165) on one atom; result holds exactly one pattern
  * (even when its needle is empty, as in the reference). */
-frz_status frz_parse_atom(const uint8_t* atom, size_t len, frz_query** out);
-size_t frz_query_len(const frz_query* q);
+FRZ_API frz_status frz_parse_atom(const uint8_t* atom, size_t len, frz_query** out);
+FRZ_API size_t frz_query_len(const frz_query* q);
 /* The returned pattern's `needle` points into `q`; valid until frz_query_destroy. */
-frz_status frz_query_get(const frz_query* q, size_t i, frz_pattern* out);
-void frz_query_destroy(frz_query* q);
+FRZ_API frz_status frz_query_get(const frz_query* q, size_t i, frz_pattern* out);
+FRZ_API void frz_query_destroy(frz_query* q);
 
 /* ----------------------------------------------------------------- corpus */
 
@@ -148,19 +153,19 @@ void frz_query_destroy(frz_query* q);
  * Input is Arrow-style: `bytes` = concatenated UTF-8, `offsets[n+1]` monotone byte offsets. */
 typedef struct frz_corpus frz_corpus;
 
-frz_status frz_corpus_create(const uint8_t* bytes, const uint64_t* offsets, uint64_t n,
+FRZ_API frz_status frz_corpus_create(const uint8_t* bytes, const uint64_t* offsets, uint64_t n,
                              int device, frz_corpus** out);
 /* same, from a pointer array + lengths (the layout a Rust `&[&str]` has) */
-frz_status frz_corpus_create_ptrs(const uint8_t* const* ptrs, const uint32_t* lens, uint64_t n,
+FRZ_API frz_status frz_corpus_create_ptrs(const uint8_t* const* ptrs, const uint32_t* lens, uint64_t n,
                                   int device, frz_corpus** out);
 /* same, but `d_bytes`/`d_offsets` are already device pointers on `device` */
-frz_status frz_corpus_create_device(const uint8_t* d_bytes, const uint64_t* d_offsets, uint64_t n,
+FRZ_API frz_status frz_corpus_create_device(const uint8_t* d_bytes, const uint64_t* d_offsets, uint64_t n,
                                     uint64_t total_bytes, int device, void* stream, frz_corpus** out);
-uint64_t frz_corpus_len(const frz_corpus* c);
-uint64_t frz_corpus_total_bytes(const frz_corpus* c);   /* sum of haystack lengths */
-uint64_t frz_corpus_device_bytes(const frz_corpus* c);  /* HBM footprint of the packed form */
-int frz_corpus_device(const frz_corpus* c);
-void frz_corpus_destroy(frz_corpus* c);
+FRZ_API uint64_t frz_corpus_len(const frz_corpus* c);
+FRZ_API uint64_t frz_corpus_total_bytes(const frz_corpus* c);   /* sum of haystack lengths */
+FRZ_API uint64_t frz_corpus_device_bytes(const frz_corpus* c);  /* HBM footprint of the packed form */
+FRZ_API int frz_corpus_device(const frz_corpus* c);
+FRZ_API void frz_corpus_destroy(frz_corpus* c);
 
 /* ---------------------------------------------------------------- matcher */
 
@@ -168,57 +173,57 @@ void frz_corpus_destroy(frz_corpus* c);
 typedef struct frz_matcher frz_matcher;
 
 /* Matcher::from_patterns (src/matcher/mod.rs:105-111); n_patterns == 1 ⇔ Matcher::new */
-frz_status frz_matcher_create(const frz_pattern* patterns, size_t n_patterns,
+FRZ_API frz_status frz_matcher_create(const frz_pattern* patterns, size_t n_patterns,
                               const frz_config* config, frz_matcher** out);
 /* Matcher::from_query (src/matcher/mod.rs:136-138) */
-frz_status frz_matcher_from_query(const uint8_t* query, size_t len, const frz_config* config,
+FRZ_API frz_status frz_matcher_from_query(const uint8_t* query, size_t len, const frz_config* config,
                                   frz_matcher** out);
 /* Matcher::set_config (src/matcher/mod.rs:154-160) */
-frz_status frz_matcher_set_config(frz_matcher* m, const frz_config* config);
-void frz_matcher_destroy(frz_matcher* m);
+FRZ_API frz_status frz_matcher_set_config(frz_matcher* m, const frz_config* config);
+FRZ_API void frz_matcher_destroy(frz_matcher* m);
 
 /* Introspection of what `get_backend` selected for pattern i (src/matcher/mod.rs:448-498):
  * lanes ∈ {8,16,32,64}; score_bits ∈ {8,16}; prefilter_lanes ∈ {16,32,64}; is_literal 0/1. */
-frz_status frz_matcher_backend_info(const frz_matcher* m, size_t i, int* lanes, int* score_bits,
+FRZ_API frz_status frz_matcher_backend_info(const frz_matcher* m, size_t i, int* lanes, int* score_bits,
                                     int* prefilter_lanes, int* is_literal);
-size_t frz_matcher_num_patterns(const frz_matcher* m); /* compiled (non-empty-needle) patterns */
+FRZ_API size_t frz_matcher_num_patterns(const frz_matcher* m); /* compiled (non-empty-needle) patterns */
 
 /* Matcher::match_list (src/matcher/mod.rs:212-222): all patterns, ordered per config.sort.
  * `out` is HOST memory with room for `cap` matches.  On FRZ_ERR_CAPACITY *n_out = needed. */
-frz_status frz_match_list(frz_matcher* m, const frz_corpus* corpus,
+FRZ_API frz_status frz_match_list(frz_matcher* m, const frz_corpus* corpus,
                           frz_match* out, uint64_t cap, uint64_t* n_out);
 
 /* Specialized::match_list / Matcher::match_list_into (src/matcher/algo.rs:17-22,
  * src/matcher/mod.rs:373-392): matches appended in input (index-ascending) order,
  * indices offset by `index_offset`, no sort. */
-frz_status frz_match_list_into(frz_matcher* m, const frz_corpus* corpus, uint32_t index_offset,
+FRZ_API frz_status frz_match_list_into(frz_matcher* m, const frz_corpus* corpus, uint32_t index_offset,
                                frz_match* out, uint64_t cap, uint64_t* n_out);
 
 /* End-to-end convenience: Matcher::match_list on HOST Arrow buffers (pack + H2D + match + D2H
  * in one call; nothing stays resident). */
-frz_status frz_match_list_host(frz_matcher* m, const uint8_t* bytes, const uint64_t* offsets,
+FRZ_API frz_status frz_match_list_host(frz_matcher* m, const uint8_t* bytes, const uint64_t* offsets,
                                uint64_t n, int device, frz_match* out, uint64_t cap, uint64_t* n_out);
 
 /* Device-resident variant used by the multi-GPU path (Matcher::match_list_parallel,
  * src/matcher/parallel.rs:18-89): this rank's shard → a locally ordered run left in HBM.
  * `d_out` (cap matches) and `d_count` (one uint64) are device pointers; `stream` is a
  * cudaStream_t (NULL = default stream).  Asynchronous: returns after enqueueing. */
-frz_status frz_match_shard_device(frz_matcher* m, const frz_corpus* shard, uint32_t index_offset,
+FRZ_API frz_status frz_match_shard_device(frz_matcher* m, const frz_corpus* shard, uint32_t index_offset,
                                   frz_match* d_out, uint64_t cap, uint64_t* d_count, void* stream);
 
 /* k_merge_matches_by (src/k_merge.rs:90-131) on device: `d_runs` holds `n_runs` runs, run r at
  * d_runs + r*run_stride with run_counts_host[r] valid entries, each already ordered per `sort`.
  * Writes the merged sequence to d_out (may not alias d_runs). */
-frz_status frz_merge_runs_device(const frz_match* d_runs, uint64_t run_stride,
+FRZ_API frz_status frz_merge_runs_device(const frz_match* d_runs, uint64_t run_stride,
                                  const uint64_t* run_counts_host, int n_runs, uint8_t sort,
                                  frz_match* d_out, int device, void* stream);
 
 /* radix_sort_matches (src/sort.rs:6-40): stable, descending score; `matches` is host memory. */
-frz_status frz_radix_sort_matches(frz_match* matches, uint64_t n, int device);
+FRZ_API frz_status frz_radix_sort_matches(frz_match* matches, uint64_t n, int device);
 
 /* Per-stage device timings (ms) of the most recent frz_match_list* call on this matcher:
  * [0]=prefilter [1]=smith-waterman [2]=sort/emit [3]=total device; bytes = algorithmic bytes. */
-frz_status frz_matcher_last_timings(const frz_matcher* m, float* ms4, uint64_t* launches);
+FRZ_API frz_status frz_matcher_last_timings(const frz_matcher* m, float* ms4, uint64_t* launches);
 
 #ifdef __cplusplus
 }

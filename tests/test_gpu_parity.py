@@ -1,0 +1,258 @@
+"""GPU parity tests: the CUDA path (through the C ABI) vs the CPU oracle on the same inputs.
+Bit-exact (score, index, exact) triples and ordering are required.  Needs a CUDA device."""
+import random
+
+import numpy as np
+import pytest
+
+import frizbee_b200 as F
+from frizbee_b200 import synth
+from frizbee_b200.types import (CaseMatching, Config, Match, Matching, Pattern, Scoring, SortStrategy,
+                                UnicodeMatching)
+from oracle import pyoracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def gpu_vs_oracle(patterns, data, offsets, config, corpus=None):
+    if isinstance(patterns, (str, Pattern)):
+        patterns = [patterns]
+    want = O.match_list_packed(patterns, config, data, offsets)
+    own = corpus is None
+    if own:
+        corpus = F.Corpus.from_arrow(data, offsets)
+    try:
+        m = F.Matcher(patterns, config)
+        got = m.match_list_array(corpus)
+        m.close()
+    finally:
+        if own:
+            corpus.close()
+    assert len(got) == len(want), (len(got), len(want), patterns, config)
+    for f in ("index", "score", "exact"):
+        bad = np.nonzero(got[f] != want[f])[0]
+        assert bad.size == 0, (f, bad[:5], got[bad[:5]], want[bad[:5]], patterns, config)
+    return got
+
+
+def from_list(hs):
+    return O.pack(hs)
+
+
+# ---------------------------------------------------------------- reference KATs through the GPU path
+def test_config1_literal_haystacks():
+    # BASELINE.json configs[0]: needle 'fBr' vs 5 literal haystacks, max_typos=0
+    hay = ["fooBar", "foo_bar", "barfoo", "prelude", "println!"]
+    for lanes in (16, 32, 64):
+        got = F.Matcher("fBr", Config(emulate_lanes=lanes)).match_list(hay)
+        assert got == [Match(score=53, index=0, exact=False)]
+
+
+@pytest.mark.parametrize("lanes", [16, 32, 64])
+def test_matcher_basic_kats(lanes):
+    # src/matcher/mod.rs:533-593
+    hay = ["deadbeef", "deadbf", "deadbeefg", "deadbe"]
+    m = F.Matcher("deadbe", Config(max_typos=None, emulate_lanes=lanes)).match_list(hay)
+    assert [(x.index, x.score) for x in m] == [(3, 116), (0, 108), (2, 108), (1, 87)]
+    m0 = F.Matcher("deadbe", Config(max_typos=0, emulate_lanes=lanes)).match_list(hay)
+    assert len(m0) == 3 and [x.index for x in m0 if x.exact] == [3]
+    m1 = F.Matcher("1", Config(max_typos=2, emulate_lanes=lanes)).match_list(["1"])
+    assert len(m1) == 1 and m1[0].exact
+
+
+def test_case_modes_and_order():
+    # src/matcher/mod.rs:618-654, src/matcher/algo.rs:443-456
+    hay = ["foo", "FOO", "fOo", "xxfooxx"]
+    idx = lambda ms: [m.index for m in ms]
+    assert idx(F.Matcher("foo", Config(sort=SortStrategy.IndexAsc)).match_list(hay)) == [0, 1, 2, 3]
+    assert idx(F.Matcher("foo", Config(sort=SortStrategy.IndexAsc, casing=CaseMatching.Respect)).match_list(hay)) == [0, 3]
+    assert idx(F.Matcher("FoO", Config(sort=SortStrategy.IndexAsc)).match_list(["foo", "FOO", "FoO", "xxFoOxx"])) == [2, 3]
+    assert idx(F.Matcher("foo", Config(sort=SortStrategy.IndexAsc)).match_list(["foo", "nomatch", "xfoo", "f_o_o", "bar"])) == [0, 2, 3]
+    assert idx(F.Matcher("", Config()).match_list(["foo", "bar"])) == [0, 1]
+
+
+SW_PAIRS = [
+    ("a", "abc"), ("abc", "abc"), ("foo", "fooBar"), ("foo", "012345foo"), ("foo", "01234567foo"),
+    ("foo", "0123456789foo"), ("foo", "0123456789012345foo"), ("foo", "0123456789012345678901234567foo"),
+    ("test", "Utooooeoooosoooot"), ("test", "Utooooooeoooooosoooooot"), ("foo", "Ufooo"), ("foo", "Ufo"),
+    ("hw", "hello_world"), ("fBr", "fooBar"), ("D", "FOR_DIST"), ("needle", "____________needle____________"),
+    ("abcdefghij", "abcdefghij"), ("abcdefghijklmnopqrst", "abcdefghijklmnopqrst"),
+    ("b", "a-b"), ("a", "-a--bc"), ("D", "forDist"), ("test", "Uteost"), ("test", "Uteoost"),
+    ("babb0_", "Bab"), ("ab_", "-1Abb1-aabB1-bbaAa-_bb/b0ABB/-0/Aa-a0a/1_/"),
+    ("eyqoof", "eA21viFrVA1k7gylcKJMa0amSvnEEVFU2YBOO9UgbFmrjkBzK0jo6ge"),
+]
+
+
+@pytest.mark.parametrize("lanes", [16, 32, 64])
+def test_sw_kats_no_prefilter(lanes):
+    # parity.rs:95-124 and mod.rs:208-299 pairs scored through match_list with max_typos=None
+    # (NO_PREFILTER: whole haystack, include_prefix) — compared with the oracle at the same LANES
+    for needle, hay in SW_PAIRS:
+        data, off = from_list([hay])
+        gpu_vs_oracle(needle, data, off, Config(max_typos=None, emulate_lanes=lanes, sort=SortStrategy.IndexAsc))
+
+
+# ---------------------------------------------------------------- randomized parity, all typo modes
+def dense_list(rng, n, max_len, pool=b"abAB_/-ab01"):
+    return [bytes(rng.choice(pool) for _ in range(rng.randint(0, max_len))) for _ in range(n)]
+
+
+@pytest.mark.parametrize("lanes", [16, 32, 64])
+@pytest.mark.parametrize("max_typos", [0, 1, 2, 3, None])
+def test_randomized_dense_alphabet(lanes, max_typos):
+    # the adversarial 10-symbol alphabet of SURVEY.md §8(d): exposes lane dependence
+    rng = random.Random(1000 + lanes + (max_typos or 7))
+    hs = dense_list(rng, 6000, 70)
+    data, off = from_list(hs)
+    corpus = F.Corpus.from_arrow(data, off)
+    for needle in ("ab", "aB_", "ab01", "b/a-", "abABab", "a_b-a/b0"):
+        gpu_vs_oracle(needle, data, off, Config(max_typos=max_typos, emulate_lanes=lanes), corpus)
+    corpus.close()
+
+
+@pytest.mark.parametrize("lanes", [16, 32, 64])
+def test_randomized_long_haystacks(lanes):
+    # windows of 65..128 (wide register variant), 129..1024 (generic) and > 1024 (greedy fallback)
+    rng = random.Random(77 + lanes)
+    hs = []
+    for _ in range(1500):
+        ln = rng.choice([70, 100, 128, 129, 200, 400, 1023, 1024, 1025, 1500])
+        hs.append(bytes(rng.choice(b"abcdefgh_-/AB01") for _ in range(rng.randint(ln // 2, ln))))
+    data, off = from_list(hs)
+    corpus = F.Corpus.from_arrow(data, off)
+    for needle, k in (("abc", 0), ("deadbe", 1), ("a_b", 0), ("hgfedcba", 2), ("abcdefgh", None)):
+        gpu_vs_oracle(needle, data, off, Config(max_typos=k, emulate_lanes=lanes), corpus)
+    corpus.close()
+
+
+@pytest.mark.parametrize("lanes", [16, 32, 64])
+def test_u16_family_long_needles(lanes):
+    # needles too long for u8 scores select the u16 backends (src/matcher/mod.rs:751-785)
+    rng = random.Random(5)
+    hs = dense_list(rng, 3000, 90, pool=b"abcdefghijklmnopqrstuvwxyz_-")
+    hs += ["abcdefghijklmnopqrst", "xxabcdefghijklmnopqrstxx", "abcdefghij_klmnopqrst"]
+    data, off = from_list(hs)
+    for needle in ("abcdefghijklmnopqrst", "abcdefghijklmn", "zyxwvutsrqponmlkj"):
+        for k in (0, 1, None):
+            gpu_vs_oracle(needle, data, off, Config(max_typos=k, emulate_lanes=lanes))
+    m = F.Matcher("abcdefghijklmnopqrst", Config(emulate_lanes=64))
+    assert m.backend_info()["score_bits"] == 16 and m.backend_info()["lanes"] == 32
+    assert F.Matcher("abc", Config(emulate_lanes=64)).backend_info() == {"lanes": 64, "score_bits": 8, "prefilter_lanes": 64, "literal": False}
+
+
+def test_u8_wrap_emulation_adversarial_needle():
+    # 13-byte needle whose true best score exceeds what the reference's u8 bound assumes
+    # (DESIGN.md §5): the reference wraps; the GPU path must wrap identically (WRAP8 variant)
+    hs = ["aB-cD-eF-gH-i", "aB-cD-eF-gH-iJ", "xaB-cD-eF-gH-i", "aB-cD-eF-gH-"] + ["aB-cD-eF-gH-i" * 3]
+    data, off = from_list(hs)
+    for lanes in (16, 32, 64):
+        for k in (0, 1, None):
+            gpu_vs_oracle("aB-cD-eF-gH-i", data, off, Config(max_typos=k, emulate_lanes=lanes))
+
+
+def test_custom_scoring_configs():
+    rng = random.Random(11)
+    hs = dense_list(rng, 3000, 64)
+    data, off = from_list(hs)
+    for sc in (Scoring(0, 0, 0, 0, 0, 0, 0, 0, 0), Scoring(gap_open_penalty=1, gap_extend_penalty=5),
+               Scoring(match_score=40, capitalization_bonus=40, mismatch_penalty=0, gap_open_penalty=0,
+                       gap_extend_penalty=0, prefix_bonus=0, matching_case_bonus=0, exact_match_bonus=0, delimiter_bonus=0),
+               Scoring(mismatch_penalty=260), Scoring(match_score=20, delimiter_bonus=9, prefix_bonus=30, gap_extend_penalty=2)):
+        for needle in ("ab", "aB_b", "BBBB"):
+            for k in (0, 1, None):
+                gpu_vs_oracle(needle, data, off, Config(max_typos=k, scoring=sc, emulate_lanes=32))
+
+
+def test_sort_strategies_and_radix_sort():
+    rng = random.Random(3)
+    hs = dense_list(rng, 5000, 40)
+    data, off = from_list(hs)
+    for sort in SortStrategy:
+        gpu_vs_oracle("ab", data, off, Config(sort=sort, max_typos=1))
+    arr = np.zeros(1 << 18, dtype=F.MATCH_DTYPE)
+    arr["index"] = np.arange(len(arr))
+    arr["score"] = np.random.default_rng(7).integers(0, 65536, len(arr))
+    got = F.radix_sort_matches(arr)
+    want = O.radix_sort_matches(arr)
+    assert np.array_equal(got, want)
+
+
+def test_literal_modes():
+    rng = random.Random(21)
+    hs = dense_list(rng, 4000, 50, pool=b"abAB_-fo") + ["foo", "foobar", "xfoo", "FOO", "barfoo", "foo_bar", "ab_ab"]
+    data, off = from_list(hs)
+    for mode in (Matching.Exact, Matching.Prefix, Matching.Suffix, Matching.Substring):
+        for needle in ("foo", "ab", "a", "A_b", "bar"):
+            for casing in CaseMatching:
+                gpu_vs_oracle(needle, data, off, Config(matching=mode, casing=casing))
+
+
+def test_multi_pattern():
+    rng = random.Random(31)
+    hs = dense_list(rng, 4000, 60, pool=b"abrfo_/BF") + ["foo/bar", "bar/foo", "foo", "foobar", "barfoo", "Foo BAR", "foo bar"]
+    data, off = from_list(hs)
+    P = Pattern
+    sets = [
+        [P("foo"), P("bar", negated=True, matching=Matching.Prefix)],          # 'foo !^bar'  (config 5)
+        [P("foo"), P("bar", negated=True, matching=Matching.Substring)],
+        [P("foo"), P("bar", negated=True, matching=Matching.Suffix)],
+        [P("foo"), P("foo")],
+        [P("foo", negated=True, matching=Matching.Substring)],
+        [P("foo", negated=True, matching=Matching.Substring), P("ab", negated=True, matching=Matching.Substring)],
+        [P("fo"), P("ba", max_typos=1), P("r")],
+        [P("Foo"), P("bar")],
+        [P("foo"), P("foo", negated=True, matching=Matching.Substring)],
+    ]
+    for pats in sets:
+        for sort in (SortStrategy.ScoreThenIndexAsc, SortStrategy.IndexAsc, SortStrategy.IndexDesc):
+            gpu_vs_oracle(pats, data, off, Config(sort=sort))
+    # the product's own query parser end to end
+    m = F.Matcher.from_query("foo !^bar", Config(sort=SortStrategy.IndexAsc))
+    assert [x.index for x in m.match_list(["foo/bar", "bar/foo", "foo", "foobar"])] == [0, 2, 3]
+    assert len(F.Matcher.from_query("foo !^bar").match_list(["foo", "barfoo", "foobar"])) == 2
+
+
+def test_edge_shapes():
+    # empty list, empty strings, single item, exactly one tile, tile boundary +-1
+    for hs in ([], [""], ["a"], ["", "", "ab"], ["ab"] * 1024, ["ab"] * 1023 + ["ba"], ["xab"] * 1025):
+        data, off = from_list(hs)
+        for k in (0, 1, None):
+            gpu_vs_oracle("ab", data, off, Config(max_typos=k))
+    hs = ["x" * i + "ab" for i in range(0, 300)]
+    data, off = from_list(hs)
+    gpu_vs_oracle("ab", data, off, Config())
+
+
+# ---------------------------------------------------------------- bench-shaped data (BASELINE.json configs)
+@pytest.mark.parametrize("needle,n,mu,max_len,k", [
+    ("deadbe", 200_000, 24, 32, 0),     # config 2 shape
+    ("deadbeef", 300_000, 48, 64, 1),   # config 3 shape
+    ("deadbeef", 300_000, 48, 64, 0),   # config 4 shape (one shard)
+])
+@pytest.mark.parametrize("lanes", [32, 64])
+def test_bench_shaped_parity(needle, n, mu, max_len, k, lanes):
+    data, off = synth.generate(needle, n, mu, max_len)
+    gpu_vs_oracle(needle, data, off, Config(max_typos=k, emulate_lanes=lanes))
+
+
+def test_full_size_properties():
+    # BASELINE.json config 3 at full size (10M x <=64, k=1): size-independent properties —
+    # ordering, index uniqueness/range, determinism across calls, and a 200k-prefix cross-check
+    n = 10_000_000
+    data, off = synth.generate("deadbeef", n, 48, 64)
+    corpus = F.Corpus.from_arrow(data, off)
+    m = F.Matcher("deadbeef", Config(max_typos=1))
+    a = m.match_list_array(corpus).copy()
+    b = m.match_list_array(corpus).copy()
+    assert np.array_equal(a, b)
+    key = (65535 - a["score"].astype(np.int64)) * (1 << 32) + a["index"]
+    assert np.all(np.diff(key) > 0)
+    assert a["index"].max() < n
+    sub_n = 200_000
+    want = O.match_list_packed(["deadbeef"], Config(max_typos=1), data[: int(off[sub_n])], off[: sub_n + 1])
+    got = a[a["index"] < sub_n]
+    assert np.array_equal(np.sort(got, order=["index"]), np.sort(want, order=["index"]))
+    # end-to-end host call gives the same list
+    c = m.match_list_host_array(data, off)
+    assert np.array_equal(a, c)
+    corpus.close()

@@ -1,0 +1,101 @@
+"""CPU-only tests of the product's host logic (no GPU compute): the C-ABI library loads and exports
+every symbol include/frz_cuda.h declares, the query parser matches the reference's own parser tests
+(src/pattern.rs:296-383), and backend selection / guards mirror the reference."""
+import ctypes
+import os
+import re
+
+import pytest
+
+import frizbee_b200 as F
+from frizbee_b200.types import CaseMatching, Config, Matching, Pattern, Scoring, UnicodeMatching
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "frz_cuda.h")).read()
+    names = set(re.findall(r"\b(frz_[a-z0-9_]+)\s*\(", hdr))
+    names -= {"frz_status"}
+    lib = ctypes.CDLL(F.lib_path())
+    missing = [n for n in sorted(names) if not hasattr(lib, n)]
+    assert not missing, missing
+    assert F.lib().frz_abi_version() == 1
+
+
+def test_parse_atom_reference_vectors():
+    def check(atom, needle, matching, negated):
+        p = F.parse_atom(atom)
+        assert (p.needle, p.matching, p.negated) == (needle, matching, negated), atom
+    check("foo", "foo", None, False)
+    check("^foo", "foo", Matching.Prefix, False)
+    check("foo$", "foo", Matching.Suffix, False)
+    check("'foo", "foo", Matching.Substring, False)
+    check("^foo$", "foo", Matching.Exact, False)
+    check("!foo", "foo", Matching.Substring, True)
+    check("!^foo", "foo", Matching.Prefix, True)
+    check("!foo$", "foo", Matching.Suffix, True)
+    check("!'foo", "foo", Matching.Substring, True)
+    check("!^foo$", "foo", Matching.Exact, True)
+    check("\\^foo", "^foo", None, False)
+    check("foo\\$", "foo$", None, False)
+    check("\\'foo", "'foo", None, False)
+    check("\\!foo", "!foo", None, False)
+    check("foo\\ bar", "foo bar", None, False)
+    check("!\\^foo", "^foo", Matching.Substring, True)
+    check("!\\!foo", "!foo", Matching.Substring, True)
+    check("foo\\\\$", "foo\\\\", Matching.Suffix, False)
+    check("foo\\bar", "foo\\bar", None, False)
+    check("foo\\", "foo\\", None, False)
+    check("a\\\\\\ b", "a\\\\ b", None, False)
+
+
+def test_parse_query_reference_vectors():
+    ps = F.parse_query("foo !^bar")
+    assert [(p.needle, p.matching, p.negated) for p in ps] == [("foo", None, False), ("bar", Matching.Prefix, True)]
+    assert [p.needle for p in F.parse_query("  foo \t bar  ")] == ["foo", "bar"]
+    assert [p.needle for p in F.parse_query("foo\\ bar baz")] == ["foo bar", "baz"]
+    assert [p.needle for p in F.parse_query("foo\\\\ bar")] == ["foo\\\\", "bar"]
+    assert F.parse_query("") == [] and F.parse_query("   ") == [] and F.parse_query("! ^$ '") == []
+    assert [p.needle for p in F.parse_query("é다 😀x")] == ["é다", "😀x"]
+
+
+def test_backend_selection_mirrors_get_backend():
+    # src/matcher/mod.rs:448-498, :751-785; src/smith_waterman/mod.rs:522-532
+    for em, (l8, l16) in {64: (64, 32), 32: (32, 16), 16: (16, 8)}.items():
+        assert F.Matcher("abc", Config(emulate_lanes=em)).backend_info() == \
+            {"lanes": l8, "score_bits": 8, "prefilter_lanes": em, "literal": False}
+        assert F.Matcher("a" * 13, Config(emulate_lanes=em)).backend_info()["score_bits"] == 8
+        info = F.Matcher("abcdefghijklmnopqrst", Config(emulate_lanes=em)).backend_info()
+        assert info == {"lanes": l16, "score_bits": 16, "prefilter_lanes": em, "literal": False}
+    assert F.Matcher("abcd", Config(scoring=Scoring(gap_extend_penalty=8), emulate_lanes=64)).backend_info()["score_bits"] == 16
+    auto = F.Matcher("abc", Config()).backend_info()
+    flags = open("/proc/cpuinfo").read()
+    if all(f in flags for f in ("avx512f", "avx512bw", "avx512vbmi", "bmi1", "bmi2")):
+        assert auto["lanes"] == 64 and auto["prefilter_lanes"] == 64
+    elif "avx2" in flags:
+        assert auto["lanes"] == 32
+    assert F.Matcher("foo", Config(matching=Matching.Prefix)).backend_info()["literal"]
+
+
+def test_build_patterns_and_guards():
+    assert F.Matcher("", Config()).num_patterns() == 0
+    assert F.Matcher.from_query("! ^$", Config()).num_patterns() == 0
+    assert F.Matcher.from_query("foo !^bar", Config()).num_patterns() == 2
+    # huge_bonuses_report_descriptive_overflow_error (src/matcher/algo.rs:370-378)
+    with pytest.raises(F.FrizbeeError) as e:
+        F.Matcher("f", Config(scoring=Scoring(capitalization_bonus=60000, matching_case_bonus=40000)))
+    assert e.value.status_name == "FRZ_ERR_NEEDLE_TOO_LONG" and "needle too long" in str(e.value)
+    with pytest.raises(F.FrizbeeError) as e:
+        F.Matcher("é다😀", Config())
+    assert e.value.status_name == "FRZ_ERR_UNSUPPORTED"
+    F.Matcher("é", Config(unicode=UnicodeMatching.Ignore, casing=CaseMatching.Ignore))
+
+
+def test_no_cpu_fallback_without_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(F.FrizbeeError) as e:
+        F.Matcher("foo", Config()).match_list(["foo", "bar"])
+    assert e.value.status_name in ("FRZ_ERR_NO_DEVICE", "FRZ_ERR_CUDA")
