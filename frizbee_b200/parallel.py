@@ -1,0 +1,75 @@
+"""Multi-GPU `match_list_parallel` (src/matcher/parallel.rs:18-89): one process per GPU, the haystack
+list sharded by contiguous index range (shard g holds indices [offset_g, offset_g + n_g)), each rank
+scores its shard into a locally ordered run that stays in HBM, one NCCL all-gather moves the runs,
+and a device merge reproduces the reference's k-way merge (src/k_merge.rs:90-131) bit for bit.
+
+torch / torch.distributed are plumbing here (device buffers, NCCL); the compute is the C ABI.
+The shard/merge host logic is backend-agnostic and is covered on CPU with gloo (tests/test_parallel_gloo.py)
+by substituting the run producer.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Callable, List, Optional, Tuple
+
+import numpy as np
+
+from . import MATCH_DTYPE, Corpus, FrizbeeError, Matcher, _check, lib
+from .types import SortStrategy
+
+
+def shard_bounds(n: int, world: int) -> List[Tuple[int, int]]:
+    """Contiguous index ranges, shard g = [g*ceil(n/world), ...)."""
+    per = (n + world - 1) // world if world else 0
+    return [(min(g * per, n), min((g + 1) * per, n)) for g in range(world)]
+
+
+def merge_runs_host(runs: List[np.ndarray], sort: SortStrategy) -> np.ndarray:
+    """Reference semantics of k_merge_matches_by_* on host arrays (used by the gloo tests and as the
+    specification of the device merge): runs are index-range shards in rank order, each ordered per `sort`."""
+    if not runs:
+        return np.zeros(0, dtype=MATCH_DTYPE)
+    cat = np.concatenate(runs[::-1] if sort.is_reversed() else runs)
+    if not sort.is_by_score():
+        return cat
+    order = np.argsort(-cat["score"].astype(np.int64), kind="stable")
+    return cat[order]
+
+
+def match_list_parallel(matcher: Matcher, shard: Corpus, index_offset: int, group=None, device: Optional[int] = None):
+    """Runs this rank's shard, all-gathers the runs over NCCL and merges them on every rank.
+    Returns (merged matches as a uint64-viewable torch tensor on the device, total count)."""
+    import torch
+    import torch.distributed as dist
+
+    dev = torch.device("cuda", torch.cuda.current_device() if device is None else device)
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    n_local = len(shard)
+    stream = torch.cuda.current_stream(dev)
+    run = torch.empty(max(n_local, 1), dtype=torch.int64, device=dev)  # 8-byte frz_match records
+    count = torch.zeros(1, dtype=torch.int64, device=dev)
+    _check(lib().frz_match_shard_device(matcher._h, shard._h, index_offset, run.data_ptr(), run.numel(),
+                                        count.data_ptr(), stream.cuda_stream))
+    if world == 1:
+        n = int(count.item())
+        return run[:n], n
+    # one collective for the counts (8 bytes per rank) …
+    counts = torch.zeros(world, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(counts, count, group=group)
+    counts_h = counts.cpu().numpy().astype(np.uint64)
+    stride = int(counts_h.max()) if counts_h.size else 0
+    stride = max(stride, 1)
+    # … and ONE all-gather of the per-shard (score, index) buffers, padded to the longest run
+    gathered = torch.empty(world * stride, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(gathered, run[:stride].contiguous() if run.numel() >= stride else
+                                torch.nn.functional.pad(run, (0, stride - run.numel())), group=group)
+    total = int(counts_h.sum())
+    merged = torch.empty(max(total, 1), dtype=torch.int64, device=dev)
+    ch = np.ascontiguousarray(counts_h)
+    _check(lib().frz_merge_runs_device(gathered.data_ptr(), stride, ch.ctypes.data, world, int(matcher.config.sort),
+                                       merged.data_ptr(), dev.index, stream.cuda_stream))
+    return merged[:total], total
+
+
+def matches_from_tensor(t) -> np.ndarray:
+    return t.cpu().numpy().view(MATCH_DTYPE)
