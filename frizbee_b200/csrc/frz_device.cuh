@@ -74,6 +74,11 @@ struct FrzPatternDev {
     int32_t delim_bonus;
     int32_t prefix_bonus;
     int32_t exact_bonus;    // full u16
+    // pre-splatted 16x2 constants for the register SW kernel (read straight from the constant bank)
+    uint32_t k_pen_a[6];    // -(s * gap_extend)               for s = 1,2,4,8,16,32
+    uint32_t k_pen_b[6];    // -(s * gap_extend + gap_open_x)
+    uint32_t k_neg_mis, k_ex_add, k_up_plain, k_up_open, k_case, k_cap, k_delim, k_base;
+    uint32_t om16[FRZ_MAX_NEEDLE], tg16[FRZ_MAX_NEEDLE], c16[FRZ_MAX_NEEDLE];
     // untruncated scoring for the literal matcher / greedy fallback (u16 arithmetic)
     int32_t raw_match, raw_mismatch, raw_gap_open, raw_gap_extend, raw_prefix, raw_cap, raw_case, raw_delim;
 };

@@ -72,6 +72,8 @@ struct FrzWorkspace {
     FrzCounters* h_counters = nullptr;      // pinned host mirror
     FrzSurvivor* survivors[FRZ_N_CLASSES] = {nullptr, nullptr, nullptr};
     uint64_t survivor_cap = 0;              // per class
+    uint32_t* surv_bitmap = nullptr;        // [n_tiles * 32] survivor bits by index-within-tile
+    uint16_t* word_prefix = nullptr;        // [n_tiles * 32] exclusive popcount prefix of surv_bitmap words
     uint32_t* tile_count = nullptr;         // [n_tiles] matches per tile
     uint64_t* tile_out_base = nullptr;      // [n_tiles] exclusive scan of tile_count
     uint32_t tiles_cap = 0;

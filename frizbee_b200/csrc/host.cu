@@ -456,6 +456,20 @@ frz_status compile_pattern(const OwnedPattern& src, const frz_config& mcfg, bool
     d.cap_bonus = sc.capitalization_bonus & tm;
     d.delim_bonus = sc.delimiter_bonus & tm;
     d.prefix_bonus = sc.prefix_bonus & tm;
+    {
+        auto sp = [](int v) { return ((uint32_t)v & 0xffffu) * 0x00010001u; };
+        for (int k = 0; k < 6; k++) {
+            const int sft = 1 << k;
+            d.k_pen_a[k] = sp(-(sft * d.gap_extend));
+            d.k_pen_b[k] = sp(-(sft * d.gap_extend + d.gap_open_x));
+        }
+        d.k_neg_mis = sp(-d.mismatch);
+        d.k_ex_add = sp(d.case_bonus - d.mismatch);
+        d.k_up_plain = sp(-d.gap_extend);
+        d.k_up_open = sp(-(d.gap_extend + d.gap_open_x));
+        d.k_case = sp(d.case_bonus); d.k_cap = sp(d.cap_bonus); d.k_delim = sp(d.delim_bonus); d.k_base = sp(d.match_x);
+        for (size_t i = 0; i < n; i++) { d.om16[i] = sp(d.om[i]); d.tg16[i] = sp(d.tg[i]); d.c16[i] = sp(d.c[i]); }
+    }
     // the kernels keep cells in signed 16-bit lanes: every intermediate must stay below 2^15
     const uint64_t cell_bound = (uint64_t)n * ((uint64_t)sc.match_score + maxb + sc.matching_case_bonus) + sc.prefix_bonus +
                                 (uint64_t)sc.mismatch_penalty + sc.match_score;
@@ -488,6 +502,7 @@ void FrzWorkspace::release() {
     cudaFree(counters);
     if (h_counters) cudaFreeHost(h_counters);
     for (auto& s : survivors) { cudaFree(s); s = nullptr; }
+    cudaFree(surv_bitmap); cudaFree(word_prefix); surv_bitmap = nullptr; word_prefix = nullptr;
     cudaFree(tile_count); cudaFree(tile_out_base); cudaFree(matches_a); cudaFree(matches_b); cudaFree(sort_hist); cudaFree(cand_bitmap);
     for (auto& e : ev) { if (e) cudaEventDestroy(e); e = nullptr; }
     counters = nullptr; h_counters = nullptr; tile_count = nullptr; tile_out_base = nullptr; matches_a = matches_b = nullptr;
@@ -710,8 +725,10 @@ frz_status ensure_workspace(frz_matcher* m, const FrzCorpusStorage& cs, uint64_t
         ws.sort_hist_cap = words;
     }
     if (ws.tiles_cap < cs.n_tiles) {
-        cudaFree(ws.tile_count); cudaFree(ws.tile_out_base);
-        ws.tile_count = nullptr; ws.tile_out_base = nullptr; ws.tiles_cap = 0;
+        cudaFree(ws.tile_count); cudaFree(ws.tile_out_base); cudaFree(ws.surv_bitmap); cudaFree(ws.word_prefix);
+        ws.tile_count = nullptr; ws.tile_out_base = nullptr; ws.surv_bitmap = nullptr; ws.word_prefix = nullptr; ws.tiles_cap = 0;
+        FRZ_CUDA_TRY(cudaMalloc(&ws.surv_bitmap, (size_t)cs.n_tiles * 32 * sizeof(uint32_t)));
+        FRZ_CUDA_TRY(cudaMalloc(&ws.word_prefix, (size_t)cs.n_tiles * 32 * sizeof(uint16_t)));
         FRZ_CUDA_TRY(cudaMalloc(&ws.tile_count, (size_t)cs.n_tiles * sizeof(uint32_t)));
         FRZ_CUDA_TRY(cudaMalloc(&ws.tile_out_base, (size_t)cs.n_tiles * sizeof(uint64_t)));
         ws.tiles_cap = cs.n_tiles;
@@ -745,31 +762,26 @@ frz_status run_pattern(frz_matcher* m, const FrzCorpusStorage& cs, const Compile
     FrzWorkspace& ws = m->ws;
     const FrzCorpusView cv = cs.view();
     uint64_t cap = std::max(ws.survivor_cap, initial_survivor_cap(cs, c.dev));
-    for (int attempt = 0; attempt < 2; attempt++) {
-        FRZ_TRY(ensure_workspace(m, cs, cap));
-        FRZ_CUDA_TRY(cudaMemsetAsync(ws.counters, 0, sizeof(FrzCounters), stream));
-        if (record_events) cudaEventRecord(ws.ev[0], stream);
-        FRZ_TRY(frz_launch_prefilter(cv, c.dev, cand_bitmap, ws, stream, st));
-        FRZ_TRY(frz_launch_tile_scan(cv, ws, stream, st));
-        if (record_events) cudaEventRecord(ws.ev[1], stream);
-        // overflow of the survivor lists is detected before scoring (cheap: one small D2H only if the
-        // list was sized by the heuristic rather than the worst case)
-        if (ws.survivor_cap < cs.n) {
-            FRZ_CUDA_TRY(cudaMemcpyAsync(ws.h_counters, ws.counters, sizeof(FrzCounters), cudaMemcpyDeviceToHost, stream));
-            FRZ_CUDA_TRY(cudaStreamSynchronize(stream));
-            if (ws.h_counters->error & FRZ_DEVERR_SURVIVOR_OVERFLOW) { cap = std::max<uint64_t>(cs.n, 1); continue; }
-        }
-        FRZ_TRY(frz_launch_sw(cv, c.dev, index_offset, reversed, ws, d_out, stream, st));
-        if (record_events) cudaEventRecord(ws.ev[2], stream);
-        return FRZ_OK;
-    }
-    return frz_fail(FRZ_ERR_CUDA, "survivor list overflow persisted");
+    FRZ_TRY(ensure_workspace(m, cs, cap));
+    FRZ_CUDA_TRY(cudaMemsetAsync(ws.counters, 0, sizeof(FrzCounters), stream));
+    if (record_events) cudaEventRecord(ws.ev[0], stream);
+    FRZ_TRY(frz_launch_prefilter(cv, c.dev, cand_bitmap, ws, stream, st));
+    FRZ_TRY(frz_launch_tile_scan(cv, ws, stream, st));
+    if (record_events) cudaEventRecord(ws.ev[1], stream);
+    // A survivor-list overflow (lists are sized by a heuristic unless the pattern can match everything)
+    // only sets a sticky device flag; whoever reads the counters back re-runs with worst-case lists.
+    FRZ_TRY(frz_launch_sw(cv, c.dev, index_offset, reversed, ws, d_out, stream, st));
+    if (record_events) cudaEventRecord(ws.ev[2], stream);
+    return FRZ_OK;
 }
+
+constexpr frz_status kRetryOverflow = (frz_status)100;
 
 frz_status read_counters(frz_matcher* m, cudaStream_t stream) {
     FrzWorkspace& ws = m->ws;
     FRZ_CUDA_TRY(cudaMemcpyAsync(ws.h_counters, ws.counters, sizeof(FrzCounters), cudaMemcpyDeviceToHost, stream));
     FRZ_CUDA_TRY(cudaStreamSynchronize(stream));
+    if (ws.h_counters->error & FRZ_DEVERR_SURVIVOR_OVERFLOW) return kRetryOverflow;
     return FRZ_OK;
 }
 
@@ -940,7 +952,6 @@ void collect_timings(frz_matcher* m, const FrzLaunchStats& st) {
 
 frz_status copy_out(frz_matcher* m, FrzMatchDev* d_list, frz_match* out, uint64_t cap, uint64_t* n_out, cudaStream_t stream) {
     FRZ_TRY(read_counters(m, stream));
-    if (m->ws.h_counters->error) return frz_fail(FRZ_ERR_CUDA, "device-side error flags 0x%x", m->ws.h_counters->error);
     const uint64_t n = m->ws.h_counters->total;
     if (n_out) *n_out = n;
     if (n > cap) return frz_fail(FRZ_ERR_CAPACITY, "output capacity %llu < %llu matches", (unsigned long long)cap, (unsigned long long)n);
@@ -961,8 +972,14 @@ extern "C" frz_status frz_match_list(frz_matcher* m, const frz_corpus* corpus, f
     cudaStream_t stream = nullptr;
     FrzLaunchStats st;
     FrzMatchDev* d_list = nullptr;
-    FRZ_TRY(match_list_device(m, corpus->st, 0, m->config.sort, &d_list, stream, &st));
-    frz_status s = copy_out(m, d_list, out, cap, n_out, stream);
+    frz_status s = FRZ_OK;
+    for (int attempt = 0; attempt < 2; attempt++) {
+        s = match_list_device(m, corpus->st, 0, m->config.sort, &d_list, stream, &st);
+        if (s == FRZ_OK) s = copy_out(m, d_list, out, cap, n_out, stream);
+        if (s != kRetryOverflow) break;
+        FRZ_TRY(ensure_workspace(m, corpus->st, std::max<uint64_t>(corpus->st.n, 1)));  // worst-case lists, then once more
+    }
+    if (s == kRetryOverflow) s = frz_fail(FRZ_ERR_CUDA, "survivor list overflow persisted");
     collect_timings(m, st);
     return s;
 }
@@ -974,8 +991,14 @@ extern "C" frz_status frz_match_list_into(frz_matcher* m, const frz_corpus* corp
     cudaStream_t stream = nullptr;
     FrzLaunchStats st;
     FrzMatchDev* d_list = nullptr;
-    FRZ_TRY(match_list_device(m, corpus->st, index_offset, FRZ_SORT_INDEX_ASC, &d_list, stream, &st));
-    frz_status s = copy_out(m, d_list, out, cap, n_out, stream);
+    frz_status s = FRZ_OK;
+    for (int attempt = 0; attempt < 2; attempt++) {
+        s = match_list_device(m, corpus->st, index_offset, FRZ_SORT_INDEX_ASC, &d_list, stream, &st);
+        if (s == FRZ_OK) s = copy_out(m, d_list, out, cap, n_out, stream);
+        if (s != kRetryOverflow) break;
+        FRZ_TRY(ensure_workspace(m, corpus->st, std::max<uint64_t>(corpus->st.n, 1)));
+    }
+    if (s == kRetryOverflow) s = frz_fail(FRZ_ERR_CUDA, "survivor list overflow persisted");
     collect_timings(m, st);
     return s;
 }
@@ -996,6 +1019,8 @@ extern "C" frz_status frz_match_shard_device(frz_matcher* m, const frz_corpus* s
     cudaStream_t stream = (cudaStream_t)stream_;
     FrzLaunchStats st;
     FrzMatchDev* d_list = nullptr;
+    // asynchronous entry point: nobody reads the overflow flag back, so size the lists for the worst case
+    FRZ_TRY(ensure_workspace(m, shard->st, std::max<uint64_t>(shard->st.n, 1)));
     FRZ_TRY(match_list_device(m, shard->st, index_offset, m->config.sort, &d_list, stream, &st));
     // the run can never exceed the shard size; the caller sizes d_out as >= shard length
     if (cap < shard->st.n) return frz_fail(FRZ_ERR_CAPACITY, "d_out must hold the whole shard (%llu)", (unsigned long long)shard->st.n);

@@ -1,5 +1,5 @@
 // prefilter.cu — stage 1 of match_list: length gate → ordered char-mask prefilter → window trim
-// → survivor records, one thread block per corpus tile.
+// → survivor records.
 //
 // Reference path replaced (per haystack, src/matcher/algo.rs:85-100):
 //     if len >= min_haystack_len { (matched,start,end) = prefilter_haystack(..); trim_haystack(..) }
@@ -7,23 +7,26 @@
 // _2_typos / _many_typos (src/prefilter/algo/ascii_typos.rs:15-360) and trim_haystack
 // (src/matcher/algo.rs:331-338).  Literal modes (src/literal/algo.rs:234-255) are decided here too.
 //
-// Structure (one block = one tile of 1024 slots, 4 rounds of 8 groups):
+// Structure (persistent, warp-autonomous, no block barriers — the first version synchronised a
+// block per tile and spent 65% of its issue slots waiting at barriers, profiles/r01a_*):
 //   phase A  warp per group, lane per haystack: coalesced LDG.128 of the interleaved units and a
 //            word-parallel "does it contain needle[0] (or needle[1])" probe — a necessary condition
-//            that rejects most haystacks at ~3 integer ops per 4 bytes; passing lanes park their
-//            bytes in a private shared-memory slice.
-//   phase B  thread per candidate: the exact reference window (chunk-emulating for k >= 1),
-//            on the shared-memory copy.
-//   phase C  survivors are emitted in slot order per SW class with their index-order rank, so
-//            that the scoring stage can write matches straight to their index-ordered position.
+//            that rejects most haystacks at ~3 integer ops per 4 bytes; passing lanes push their
+//            bytes into the warp's private shared-memory ring.
+//   phase B  whenever 32 candidates are queued: lane per candidate, the exact reference window
+//            (chunk-emulating for k >= 1) on the shared-memory copy, all lanes busy.
+//   emit     survivors go to per-SW-class lists (warp-aggregated atomics) and set their bit in a
+//            per-tile bitmap; k_tile_rank turns the bitmap into index-order ranks so that the
+//            scoring stage can write each match straight to its index-ordered position.
 #include "frz_device.cuh"
+#include <algorithm>
+
 #include "frz_host.h"
 
 namespace {
 
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
-constexpr int kRounds = FRZ_GROUPS_PER_TILE / kWarps;  // 4
 constexpr int kSliceUnits = 8;                         // haystacks up to 128 bytes are staged in smem
 constexpr int kSliceWords = kSliceUnits * 4 + 1;       // +1 word: conflict-free stride, and a zero guard
 
@@ -334,222 +337,209 @@ __device__ bool lit_find(const A& a, const FrzPatternDev& p, int len, int* opos,
     }
 }
 
-struct TileShared {
-    uint32_t slice[kThreads * kSliceWords];   // per-candidate haystack bytes (phase A → B)
-    uint32_t cand_meta[kThreads];             // slot | (in_slice << 31)
-    uint32_t surv_start[FRZ_TILE];            // by local index
-    uint32_t surv_end[FRZ_TILE];
-    uint16_t surv_slot[FRZ_TILE];
-    uint32_t bm_class[FRZ_N_CLASSES][32];     // survivor bitmaps by local index, per SW class
-    uint32_t pre_all[33];                     // exclusive prefix popcounts
-    uint32_t pre_class[FRZ_N_CLASSES][33];
-    unsigned long long class_base[FRZ_N_CLASSES];
-    uint32_t ncand;
+constexpr int kQueueCap = 64;  // per-warp candidate queue (31 left over + 32 new at most)
+
+struct WarpQueue {
+    uint32_t slice[kQueueCap][kSliceWords];  // candidate haystack bytes (zero padded to the unit), +1 guard word
+    uint32_t meta[kQueueCap];                // tile << 10 | slot
+    uint32_t info[kQueueCap];                // len | in_slice << 31
 };
 
-__device__ __forceinline__ int sw_class_of(int window, int sw_cols0) {
-    return window <= sw_cols0 ? FRZ_C_COLS64 : window <= 2 * sw_cols0 ? FRZ_C_COLS128 : FRZ_C_GENERIC;
+__device__ __forceinline__ int sw_class_of(int window) {
+    return window <= 64 ? FRZ_C_COLS64 : window <= 128 ? FRZ_C_COLS128 : FRZ_C_GENERIC;
 }
 
+// Exact window of one queued candidate (phase B) + survivor emission.  All 32 lanes of the warp call
+// this together (`active` lanes have an entry); emission uses warp-aggregated atomics.
+template <int MODE>
+__device__ __forceinline__ void process_candidate(const FrzCorpusView& cv, const FrzPatternDev& pat, const WarpQueue& q,
+                                                  int entry, bool active, FrzSurvivor* const* lists,
+                                                  unsigned long long surv_cap, uint32_t* __restrict__ surv_bitmap,
+                                                  FrzCounters* __restrict__ ctr) {
+    const uint32_t lane = frz_lane();
+    bool ok = false;
+    int cls = 0;
+    FrzSurvivor rec;
+    rec.tile = 0; rec.slot_rank = 0; rec.start = 0; rec.end = 0;
+    if (active) {
+        const uint32_t meta = q.meta[entry], info = q.info[entry];
+        const uint32_t tile = meta >> FRZ_TILE_SHIFT, slot = meta & (FRZ_TILE - 1);
+        const int len = (int)(info & 0x7fffffffu);
+        const bool in_slice = (info >> 31) != 0;
+        const uint32_t li = cv.slot_meta[(uint64_t)tile * FRZ_TILE + slot] & (FRZ_TILE - 1);
+        int start = 0, end = len;
+        uint32_t lit_score = 0;
+        SliceAcc sa{q.slice[entry]};
+        GlobalAcc ga{nullptr};
+        if (!in_slice) {
+            FrzGroupDesc gd = cv.groups[tile * FRZ_GROUPS_PER_TILE + (slot >> 5)];
+            ga.base = cv.data + cv.tile_base[tile] + gd.unit_off + (slot & 31);
+        }
+        if (MODE == FRZ_T_0) ok = in_slice ? window_k0(sa, pat, len, &start, &end) : window_k0(ga, pat, len, &start, &end);
+        else if (MODE == FRZ_T_1) ok = in_slice ? window_k1(sa, pat, len, &start, &end) : window_k1(ga, pat, len, &start, &end);
+        else if (MODE == FRZ_T_2) ok = in_slice ? window_k2(sa, pat, len, &start, &end) : window_k2(ga, pat, len, &start, &end);
+        else if (MODE == FRZ_T_MANY) ok = in_slice ? window_many(sa, pat, len, &start, &end) : window_many(ga, pat, len, &start, &end);
+        else if (MODE == FRZ_T_LITERAL) {
+            int pos = 0;
+            ok = in_slice ? lit_find(sa, pat, len, &pos, &lit_score) : lit_find(ga, pat, len, &pos, &lit_score);
+            start = pos; end = pos + pat.n;
+        } else ok = true;  // FRZ_T_NONE: NO_PREFILTER (src/matcher/algo.rs:178)
+        if (ok) {
+            rec.tile = tile;
+            rec.slot_rank = slot | (li << 10);
+            if (MODE == FRZ_T_LITERAL) {
+                // literal matches are final: carry (score, exact) through start/end
+                cls = FRZ_C_COLS64;
+                rec.start = lit_score;
+                rec.end = (start == 0 && pat.n == len) ? 1u : 0u;
+            } else {
+                start = start > 0 ? start - 1 : 0;  // trim_haystack (src/matcher/algo.rs:331-338)
+                cls = sw_class_of(end - start);
+                rec.start = (uint32_t)start;
+                rec.end = (uint32_t)end | ((uint32_t)(end == len) << 31);
+            }
+            atomicOr(&surv_bitmap[(uint64_t)tile * 32 + (li >> 5)], 1u << (li & 31));
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < FRZ_N_CLASSES; c++) {
+        const uint32_t b = __ballot_sync(0xffffffffu, ok && cls == c);
+        if (!b) continue;
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(&ctr->class_count[c], (unsigned long long)__popc(b));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (ok && cls == c) {
+            const unsigned long long pos = base + __popc(b & ((1u << lane) - 1));
+            if (pos < surv_cap) lists[c][pos] = rec;
+            else atomicOr(&ctr->error, FRZ_DEVERR_SURVIVOR_OVERFLOW);
+        }
+    }
+}
+
+// Warp-autonomous, barrier-free: every warp strides over groups, probes (phase A), queues the
+// passing haystacks' bytes in its own shared-memory ring and, whenever 32 are queued, runs the
+// exact window on them with all lanes busy (phase B).
 template <int MODE>
 __global__ void __launch_bounds__(kThreads) k_prefilter(const FrzCorpusView cv, const __grid_constant__ FrzPatternDev pat,
                                                         const uint32_t* __restrict__ cand_bitmap,
                                                         FrzSurvivor* __restrict__ surv0, FrzSurvivor* __restrict__ surv1,
                                                         FrzSurvivor* __restrict__ surv2, unsigned long long surv_cap,
-                                                        uint32_t* __restrict__ tile_count, FrzCounters* __restrict__ ctr,
-                                                        FrzMatchDev* __restrict__ lit_out) {
+                                                        uint32_t* __restrict__ surv_bitmap, FrzCounters* __restrict__ ctr) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    TileShared& sh = *reinterpret_cast<TileShared*>(smem_raw);
-    const uint32_t tile = blockIdx.x;
     const uint32_t lane = frz_lane(), warp = threadIdx.x >> 5;
-    const uint64_t tb = cv.tile_base[tile];
+    WarpQueue& q = reinterpret_cast<WarpQueue*>(smem_raw)[warp];
+    FrzSurvivor* const lists[FRZ_N_CLASSES] = {surv0, surv1, surv2};
 
-    for (int i = threadIdx.x; i < FRZ_N_CLASSES * 32; i += kThreads) (&sh.bm_class[0][0])[i] = 0;
-
-    // probes for phase A
     const uint32_t om0 = splat4(pat.om[0]), tg0 = splat4(pat.tg[0]);
     const uint32_t om1 = splat4(pat.om[pat.n > 1 ? 1 : 0]), tg1 = splat4(pat.tg[pat.n > 1 ? 1 : 0]);
     const uint32_t om2 = splat4(pat.om[pat.n > 2 ? 2 : 0]), tg2 = splat4(pat.tg[pat.n > 2 ? 2 : 0]);
+    const bool probe = (MODE == FRZ_T_0 || MODE == FRZ_T_1 || MODE == FRZ_T_2);
+    // needle no longer than the typo budget matches everything (ascii_typos.rs:18,116)
+    const bool trivially = (MODE == FRZ_T_1 && pat.n <= 1) || (MODE == FRZ_T_2 && pat.n <= 2);
 
-    for (int round = 0; round < kRounds; round++) {
-        if (threadIdx.x == 0) sh.ncand = 0;
-        __syncthreads();
+    const uint32_t total_groups = cv.n_tiles * FRZ_GROUPS_PER_TILE;
+    const uint32_t n_warps = gridDim.x * kWarps;
+    uint32_t head = 0, count = 0;  // ring state (warp-uniform)
+
+    for (uint32_t gidx = blockIdx.x * kWarps + warp; gidx < total_groups; gidx += n_warps) {
         // ------------------------------------------------------------ phase A
-        {
-            const uint32_t g = round * kWarps + warp;
-            const FrzGroupDesc gd = cv.groups[tile * FRZ_GROUPS_PER_TILE + g];
-            const uint32_t slot = g * FRZ_GROUP + lane;
-            const uint32_t meta = cv.slot_meta[(uint64_t)tile * FRZ_TILE + slot];
-            const bool valid = meta != FRZ_INVALID_SLOT;
-            const uint32_t len = valid ? meta >> FRZ_TILE_SHIFT : 0;
-            bool pass = valid && (int)len >= pat.min_hay_len;
-            if (cand_bitmap != nullptr && valid) {
-                uint64_t idx = (uint64_t)tile * FRZ_TILE + (meta & (FRZ_TILE - 1));
-                pass = pass && ((cand_bitmap[idx >> 5] >> (idx & 31)) & 1);
-            }
-            const uint4* gp = cv.data + tb + gd.unit_off + lane;
-            uint4 u[kSliceUnits];
-            uint32_t acc = 0;
-            const bool probe = (MODE == FRZ_T_0 || MODE == FRZ_T_1 || MODE == FRZ_T_2);
-            if (gd.gunits <= kSliceUnits) {
+        const uint32_t tile = gidx >> 5, g = gidx & 31;
+        const FrzGroupDesc gd = cv.groups[gidx];
+        if (gd.gunits == 0 && MODE != FRZ_T_NONE && MODE != FRZ_T_LITERAL && pat.min_hay_len > 0) continue;  // only empty strings
+        const uint32_t slot = g * FRZ_GROUP + lane;
+        const uint32_t meta = cv.slot_meta[(uint64_t)tile * FRZ_TILE + slot];
+        const bool valid = meta != FRZ_INVALID_SLOT;
+        const uint32_t len = valid ? meta >> FRZ_TILE_SHIFT : 0;
+        bool pass = valid && (int)len >= pat.min_hay_len;
+        if (cand_bitmap != nullptr && valid) {
+            const uint64_t idx = (uint64_t)tile * FRZ_TILE + (meta & (FRZ_TILE - 1));
+            pass = pass && ((cand_bitmap[idx >> 5] >> (idx & 31)) & 1);
+        }
+        const uint4* gp = cv.data + cv.tile_base[tile] + gd.unit_off + lane;
+        uint4 u[kSliceUnits];
+        uint32_t acc = 0;
+        const bool in_slice = gd.gunits <= kSliceUnits;
+        if (in_slice) {
 #pragma unroll
-                for (int k = 0; k < kSliceUnits; k++) {
-                    u[k] = make_uint4(0, 0, 0, 0);
-                    if (k < (int)gd.gunits) u[k] = __ldg(gp + (size_t)k * FRZ_GROUP);
-                }
-                if (probe) {
-#pragma unroll
-                    for (int k = 0; k < kSliceUnits; k++) {
-                        if (k < (int)gd.gunits) {
-                            const uint32_t w[4] = {u[k].x, u[k].y, u[k].z, u[k].w};
-#pragma unroll
-                            for (int j = 0; j < 4; j++) {
-                                uint32_t x = (w[j] | om0) ^ tg0;
-                                acc |= (x - 0x01010101u) & ~x;
-                                if (MODE >= FRZ_T_1) { x = (w[j] | om1) ^ tg1; acc |= (x - 0x01010101u) & ~x; }
-                                if (MODE >= FRZ_T_2) { x = (w[j] | om2) ^ tg2; acc |= (x - 0x01010101u) & ~x; }
-                            }
-                        }
-                    }
-                }
-            } else if (probe) {
-                for (uint32_t k = 0; k < gd.gunits; k++) {
-                    uint4 v = __ldg(gp + (size_t)k * FRZ_GROUP);
-                    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        uint32_t x = (w[j] | om0) ^ tg0;
-                        acc |= (x - 0x01010101u) & ~x;
-                        if (MODE >= FRZ_T_1) { x = (w[j] | om1) ^ tg1; acc |= (x - 0x01010101u) & ~x; }
-                        if (MODE >= FRZ_T_2) { x = (w[j] | om2) ^ tg2; acc |= (x - 0x01010101u) & ~x; }
-                    }
-                }
+            for (int k = 0; k < kSliceUnits; k++) {
+                u[k] = make_uint4(0, 0, 0, 0);
+                if (k < (int)gd.gunits) u[k] = __ldg(gp + (size_t)k * FRZ_GROUP);
             }
             if (probe) {
-                // needle shorter than / equal to the typo budget matches everything (ascii_typos.rs:18,116)
-                bool trivially = (MODE == FRZ_T_1 && pat.n <= 1) || (MODE == FRZ_T_2 && pat.n <= 2);
-                pass = pass && (trivially || (acc & 0x80808080u) != 0);
-            }
-            const uint32_t ballot = __ballot_sync(0xffffffffu, pass);
-            if (ballot) {
-                uint32_t base = 0;
-                if (lane == 0) base = atomicAdd(&sh.ncand, __popc(ballot));
-                base = __shfl_sync(0xffffffffu, base, 0);
-                if (pass) {
-                    uint32_t ci = base + __popc(ballot & ((1u << lane) - 1));
-                    bool in_slice = gd.gunits <= kSliceUnits;
-                    sh.cand_meta[ci] = slot | (in_slice ? 0x80000000u : 0u);
-                    if (in_slice) {
-                        uint32_t* dst = sh.slice + ci * kSliceWords;
 #pragma unroll
-                        for (int k = 0; k < kSliceUnits; k++) {
-                            if (k < (int)gd.gunits) { dst[4 * k] = u[k].x; dst[4 * k + 1] = u[k].y; dst[4 * k + 2] = u[k].z; dst[4 * k + 3] = u[k].w; }
+                for (int k = 0; k < kSliceUnits; k++) {
+                    if (k < (int)gd.gunits) {
+                        const uint32_t w[4] = {u[k].x, u[k].y, u[k].z, u[k].w};
+#pragma unroll
+                        for (int j = 0; j < 4; j++) {
+                            uint32_t x = (w[j] | om0) ^ tg0;
+                            acc |= (x - 0x01010101u) & ~x;
+                            if (MODE >= FRZ_T_1) { x = (w[j] | om1) ^ tg1; acc |= (x - 0x01010101u) & ~x; }
+                            if (MODE >= FRZ_T_2) { x = (w[j] | om2) ^ tg2; acc |= (x - 0x01010101u) & ~x; }
                         }
-                        dst[4 * gd.gunits] = 0;  // guard word
                     }
                 }
             }
-        }
-        __syncthreads();
-        // ------------------------------------------------------------ phase B
-        if (threadIdx.x < sh.ncand) {
-            const uint32_t cm = sh.cand_meta[threadIdx.x];
-            const uint32_t slot = cm & 0x3ff;
-            const uint32_t meta = cv.slot_meta[(uint64_t)tile * FRZ_TILE + slot];
-            const int len = (int)(meta >> FRZ_TILE_SHIFT);
-            const uint32_t li = meta & (FRZ_TILE - 1);
-            int start = 0, end = len;
-            bool ok;
-            uint32_t lit_score = 0;
-            const bool in_slice = (cm >> 31) != 0;
-            SliceAcc sa{sh.slice + threadIdx.x * kSliceWords};
-            FrzGroupDesc gd = cv.groups[tile * FRZ_GROUPS_PER_TILE + (slot >> 5)];
-            GlobalAcc ga{cv.data + tb + gd.unit_off + (slot & 31)};
-            if (MODE == FRZ_T_0) ok = in_slice ? window_k0(sa, pat, len, &start, &end) : window_k0(ga, pat, len, &start, &end);
-            else if (MODE == FRZ_T_1) ok = in_slice ? window_k1(sa, pat, len, &start, &end) : window_k1(ga, pat, len, &start, &end);
-            else if (MODE == FRZ_T_2) ok = in_slice ? window_k2(sa, pat, len, &start, &end) : window_k2(ga, pat, len, &start, &end);
-            else if (MODE == FRZ_T_MANY) ok = in_slice ? window_many(sa, pat, len, &start, &end) : window_many(ga, pat, len, &start, &end);
-            else if (MODE == FRZ_T_LITERAL) {
-                int pos = 0;
-                ok = in_slice ? lit_find(sa, pat, len, &pos, &lit_score) : lit_find(ga, pat, len, &pos, &lit_score);
-                start = pos; end = pos + pat.n;
-            } else ok = true;  // FRZ_T_NONE: NO_PREFILTER (src/matcher/algo.rs:178)
-            if (ok) {
-                int cls;
-                if (MODE == FRZ_T_LITERAL) {
-                    // literal matches are final: carry (score, exact) through start/end
-                    cls = FRZ_C_COLS64;
-                    sh.surv_start[li] = lit_score;
-                    sh.surv_end[li] = (start == 0 && pat.n == len) ? 1u : 0u;
-                } else {
-                    // trim_haystack (src/matcher/algo.rs:331-338)
-                    start = start > 0 ? start - 1 : 0;
-                    int cols0 = pat.score_bits == 8 ? 64 : 32;   // columns of the small register variant
-                    int window = end - start;
-                    cls = window > FRZ_SW_MAX_WINDOW ? FRZ_C_GENERIC : sw_class_of(window, cols0);
-                    sh.surv_start[li] = (uint32_t)start;
-                    sh.surv_end[li] = (uint32_t)end | ((uint32_t)(end == len) << 31);
+        } else if (probe) {
+            for (uint32_t k = 0; k < gd.gunits; k++) {
+                const uint4 v = __ldg(gp + (size_t)k * FRZ_GROUP);
+                const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    uint32_t x = (w[j] | om0) ^ tg0;
+                    acc |= (x - 0x01010101u) & ~x;
+                    if (MODE >= FRZ_T_1) { x = (w[j] | om1) ^ tg1; acc |= (x - 0x01010101u) & ~x; }
+                    if (MODE >= FRZ_T_2) { x = (w[j] | om2) ^ tg2; acc |= (x - 0x01010101u) & ~x; }
                 }
-                sh.surv_slot[li] = (uint16_t)slot;
-                atomicOr(&sh.bm_class[cls][li >> 5], 1u << (li & 31));
             }
         }
-        __syncthreads();
-    }
-    // ---------------------------------------------------------------- phase C
-    if (warp == 0) {
-        uint32_t any = 0, c[FRZ_N_CLASSES];
+        if (probe) pass = pass && (trivially || (acc & 0x80808080u) != 0);
+        const uint32_t ballot = __ballot_sync(0xffffffffu, pass);
+        if (ballot) {
+            if (pass) {
+                const uint32_t e = (head + count + __popc(ballot & ((1u << lane) - 1))) & (kQueueCap - 1);
+                q.meta[e] = (tile << FRZ_TILE_SHIFT) | slot;
+                q.info[e] = len | (in_slice ? 0x80000000u : 0u);
+                if (in_slice) {
+                    uint32_t* dst = q.slice[e];
 #pragma unroll
-        for (int k = 0; k < FRZ_N_CLASSES; k++) { c[k] = sh.bm_class[k][lane]; any |= c[k]; }
-        auto excl_scan = [&](uint32_t v, uint32_t* total) {
-            uint32_t x = v;
-            for (int d = 1; d < 32; d <<= 1) {
-                uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
-                if (lane >= (uint32_t)d) x += y;
+                    for (int k = 0; k < kSliceUnits; k++) {
+                        if (k < (int)gd.gunits) { dst[4 * k] = u[k].x; dst[4 * k + 1] = u[k].y; dst[4 * k + 2] = u[k].z; dst[4 * k + 3] = u[k].w; }
+                    }
+                    dst[4 * gd.gunits] = 0;  // guard word
+                }
             }
-            *total = __shfl_sync(0xffffffffu, x, 31);
-            return x - v;
-        };
-        uint32_t tot_all, tot_c[FRZ_N_CLASSES];
-        sh.pre_all[lane] = excl_scan(__popc(any), &tot_all);
-#pragma unroll
-        for (int k = 0; k < FRZ_N_CLASSES; k++) sh.pre_class[k][lane] = excl_scan(__popc(c[k]), &tot_c[k]);
-        if (lane == 0) {
-            tile_count[tile] = tot_all;
-            sh.pre_all[32] = tot_all;
-#pragma unroll
-            for (int k = 0; k < FRZ_N_CLASSES; k++)
-                sh.class_base[k] = tot_c[k] ? atomicAdd(&ctr->class_count[k], (unsigned long long)tot_c[k]) : 0ull;
+            count += __popc(ballot);
+            __syncwarp();
+            // -------------------------------------------------------- phase B on full batches
+            if (count >= 32) {
+                process_candidate<MODE>(cv, pat, q, (head + lane) & (kQueueCap - 1), true, lists, surv_cap, surv_bitmap, ctr);
+                head = (head + 32) & (kQueueCap - 1);
+                count -= 32;
+                __syncwarp();
+            }
         }
     }
-    __syncthreads();
-    FrzSurvivor* const lists[FRZ_N_CLASSES] = {surv0, surv1, surv2};
-    for (int li = threadIdx.x; li < FRZ_TILE; li += kThreads) {
-        const uint32_t wd = li >> 5, bit = 1u << (li & 31), below = bit - 1;
-        uint32_t any = 0;
-        int cls = -1;
-#pragma unroll
-        for (int k = 0; k < FRZ_N_CLASSES; k++) {
-            uint32_t b = sh.bm_class[k][wd];
-            any |= b;
-            if (b & bit) cls = k;
-        }
-        if (cls < 0) continue;
-        const uint32_t rank = sh.pre_all[wd] + __popc(any & below);
-        const uint32_t crank = sh.pre_class[cls][wd] + __popc(sh.bm_class[cls][wd] & below);
-        if (MODE == FRZ_T_LITERAL) {
-            // written by the emit kernel after the tile scan: stash in the survivor list as well
-        }
-        const unsigned long long pos = sh.class_base[cls] + crank;
-        if (pos >= surv_cap) { atomicOr(&ctr->error, FRZ_DEVERR_SURVIVOR_OVERFLOW); continue; }
-        FrzSurvivor s;
-        s.tile = tile;
-        s.slot_rank = (uint32_t)sh.surv_slot[li] | ((uint32_t)li << 10) | (rank << 20);
-        s.start = sh.surv_start[li];
-        s.end = sh.surv_end[li];
-        lists[cls][pos] = s;
+    if (count) {  // flush the partial batch
+        __syncwarp();
+        process_candidate<MODE>(cv, pat, q, (head + lane) & (kQueueCap - 1), lane < count, lists, surv_cap, surv_bitmap, ctr);
     }
-    (void)lit_out;
+}
+
+// Per tile: exclusive prefix popcount of the 32 survivor-bitmap words (→ rank of a survivor among
+// its tile's survivors in index order) and the tile's survivor count.  One warp per tile.
+__global__ void __launch_bounds__(256) k_tile_rank(const uint32_t* __restrict__ surv_bitmap, uint16_t* __restrict__ word_prefix,
+                                                   uint32_t* __restrict__ tile_count, uint32_t n_tiles) {
+    const uint32_t tile = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = frz_lane();
+    if (tile >= n_tiles) return;
+    const uint32_t c = __popc(surv_bitmap[(uint64_t)tile * 32 + lane]);
+    uint32_t x = c;
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
+        if (lane >= (uint32_t)d) x += y;
+    }
+    word_prefix[(uint64_t)tile * 32 + lane] = (uint16_t)(x - c);
+    if (lane == 31) tile_count[tile] = x;
 }
 
 // exclusive scan of tile_count → tile_out_base; total → counters.total
@@ -592,7 +582,15 @@ __global__ void __launch_bounds__(1024) k_tile_scan(const uint32_t* __restrict__
 frz_status frz_launch_prefilter(const FrzCorpusView& cv, const FrzPatternDev& pat, const uint32_t* cand_bitmap,
                                 FrzWorkspace& ws, cudaStream_t stream, FrzLaunchStats* st) {
     if (cv.n_tiles == 0) return FRZ_OK;
-    const size_t smem = sizeof(TileShared);
+    const size_t smem = sizeof(WarpQueue) * kWarps;
+    int sms = 0, dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+    // persistent warps: 3 blocks of 8 warps per SM (shared-memory bound), capped by the work
+    const uint32_t total_groups = cv.n_tiles * FRZ_GROUPS_PER_TILE;
+    const uint32_t grid = std::max<uint32_t>(1, std::min<uint32_t>((uint32_t)sms * 3, (total_groups + kWarps - 1) / kWarps));
+    FRZ_CUDA_TRY(cudaMemsetAsync(ws.surv_bitmap, 0, (size_t)cv.n_tiles * 32 * sizeof(uint32_t), stream));
 #define FRZ_PF_LAUNCH(MODE)                                                                                     \
     do {                                                                                                        \
         static bool attr_set = false;                                                                           \
@@ -600,9 +598,8 @@ frz_status frz_launch_prefilter(const FrzCorpusView& cv, const FrzPatternDev& pa
             FRZ_CUDA_TRY(cudaFuncSetAttribute(k_prefilter<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
             attr_set = true;                                                                                    \
         }                                                                                                       \
-        k_prefilter<MODE><<<cv.n_tiles, kThreads, smem, stream>>>(cv, pat, cand_bitmap, ws.survivors[0], ws.survivors[1], \
-                                                                  ws.survivors[2], ws.survivor_cap, ws.tile_count,     \
-                                                                  ws.counters, nullptr);                        \
+        k_prefilter<MODE><<<grid, kThreads, smem, stream>>>(cv, pat, cand_bitmap, ws.survivors[0], ws.survivors[1],      \
+                                                            ws.survivors[2], ws.survivor_cap, ws.surv_bitmap, ws.counters); \
     } while (0)
     switch (pat.typo_mode) {
         case FRZ_T_0: FRZ_PF_LAUNCH(FRZ_T_0); break;
@@ -620,6 +617,10 @@ frz_status frz_launch_prefilter(const FrzCorpusView& cv, const FrzPatternDev& pa
 }
 
 frz_status frz_launch_tile_scan(const FrzCorpusView& cv, FrzWorkspace& ws, cudaStream_t stream, FrzLaunchStats* st) {
+    if (cv.n_tiles) {
+        k_tile_rank<<<(cv.n_tiles * 32 + 255) / 256, 256, 0, stream>>>(ws.surv_bitmap, ws.word_prefix, ws.tile_count, cv.n_tiles);
+        if (st) st->launches++;
+    }
     k_tile_scan<<<1, 1024, 0, stream>>>(ws.tile_count, ws.tile_out_base, cv.n_tiles, ws.counters);
     FRZ_CUDA_TRY(cudaGetLastError());
     if (st) st->launches++;

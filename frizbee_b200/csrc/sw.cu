@@ -24,11 +24,20 @@
 // long as no u8 add can wrap; when the host cannot prove that (pat.wrap8) the WRAP8 variant
 // re-applies the 8-bit wrap after every add.
 #include "frz_device.cuh"
+#include <stdlib.h>
+
 #include "frz_host.h"
 
 namespace {
 
 constexpr int kSwThreads = 128;
+
+struct FrzRankView {
+    const uint64_t* tile_out_base;
+    const uint32_t* surv_bitmap;
+    const uint16_t* word_prefix;
+};
+FrzRankView rank_view(const FrzWorkspace& ws) { return FrzRankView{ws.tile_out_base, ws.surv_bitmap, ws.word_prefix}; }
 
 __device__ __forceinline__ uint32_t splat16(int v) { return ((uint32_t)v & 0xffffu) * 0x00010001u; }
 
@@ -36,7 +45,12 @@ __device__ __forceinline__ uint32_t splat16(int v) { return ((uint32_t)v & 0xfff
 __device__ __forceinline__ uint32_t eqmask16(uint32_t x) {
     return __byte_perm(__vadd2(x, 0xFFFFFFFFu), 0, 0xBB99);  // (x-1) sign → replicate
 }
-__device__ __forceinline__ uint32_t sel(uint32_t mask, uint32_t a, uint32_t b) { return (mask & a) | (~mask & b); }
+// bitwise select (mask ? a : b) as ONE LOP3 (nvcc otherwise emits and / and-not / or: three)
+__device__ __forceinline__ uint32_t sel(uint32_t mask, uint32_t a, uint32_t b) {
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, 0xCA;" : "=r"(d) : "r"(mask), "r"(a), "r"(b));
+    return d;
+}
 
 // max(a + b, c, 0) per signed 16-bit lane
 __device__ __forceinline__ uint32_t addmax_relu(uint32_t a, uint32_t b, uint32_t c) { return __viaddmax_s16x2_relu(a, b, c); }
@@ -80,7 +94,7 @@ struct SwCore {
         }
         // ---- per-column bonus (ascii.rs:64-101) ----
         {
-            const uint32_t capb = splat16(p.cap_bonus), delb = splat16(p.delim_bonus), base = splat16(p.match_x);
+            const uint32_t capb = p.k_cap, delb = p.k_delim, base = p.k_base;
             uint32_t prev_lower = 0, prev_delim = 0;  // masks of the previous register
 #pragma unroll
             for (int r = 0; r < R; r++) {
@@ -109,16 +123,16 @@ struct SwCore {
             }
         }
         // ---- constants ----
-        const uint32_t neg_mis = splat16(-p.mismatch);
-        const uint32_t ex_add = splat16(p.case_bonus - p.mismatch);       // exact-case match: +case -mismatch
-        const uint32_t up_plain = splat16(-p.gap_extend);
-        const uint32_t up_open = splat16(-(p.gap_extend + p.gap_open_x));
+        const uint32_t neg_mis = p.k_neg_mis;
+        const uint32_t ex_add = p.k_ex_add;       // exact-case match: +case -mismatch
+        const uint32_t up_plain = p.k_up_plain;
+        const uint32_t up_open = p.k_up_open;
         uint32_t H[R], M[R];
 #pragma unroll
         for (int r = 0; r < R; r++) { H[r] = 0; M[r] = 0; }
 
         for (int i = 0; i < p.n; i++) {
-            const uint32_t om16 = splat16(p.om[i]), tg16 = splat16(p.tg[i]), c16 = splat16(p.c[i]);
+            const uint32_t om16 = p.om16[i], tg16 = p.tg16[i], c16 = p.c16[i];
             const bool folded = p.om[i] != 0;  // case-insensitive letter: exact-case mask differs from match mask
             // ---- diagonal + up, in place, high register first (H[r-1] must still hold row i-1) ----
 #pragma unroll
@@ -134,7 +148,7 @@ struct SwCore {
                 } else {
                     uint32_t d = __vadd2(prevs, mmn & Bv) & 0x00FF00FFu;        // wrapping u8 add
                     d = addmax_relu(d, neg_mis, 0u);                             // saturating sub
-                    diag = __vadd2(d, ex & splat16(p.case_bonus)) & 0x00FF00FFu;  // wrapping u8 add
+                    diag = __vadd2(d, ex & p.k_case) & 0x00FF00FFu;  // wrapping u8 add
                 }
                 const uint32_t upd = sel(M[r], up_open, up_plain);               // M[r] still row i-1
                 H[r] = addmax_relu(H[r], upd, diag);
@@ -145,9 +159,9 @@ struct SwCore {
             for (int c = 0; c < NCH; c++) {
                 const int lo = c * RL, hi = lo + RL;
 #pragma unroll
-                for (int s = 1; s < LANES; s <<= 1) {
-                    const uint32_t penA = splat16(-(s * p.gap_extend));
-                    const uint32_t penB = splat16(-(s * p.gap_extend + p.gap_open_x));
+                for (int s = 1, si = 0; s < LANES; s <<= 1, si++) {
+                    const uint32_t penA = p.k_pen_a[si];
+                    const uint32_t penB = p.k_pen_b[si];
 #pragma unroll
                     for (int r = hi - 1; r >= lo; r--) {
                         uint32_t sh, smm;
@@ -228,10 +242,13 @@ __device__ __forceinline__ bool window_equals_needle(const uint32_t (&hw)[NW], i
 }
 
 __device__ __forceinline__ void emit_match(const FrzSurvivor& rec, uint32_t score, bool exact, uint32_t index_offset,
-                                           bool reversed, const uint64_t* __restrict__ tile_out_base,
+                                           bool reversed, const FrzRankView& rv,
                                            const FrzCounters* __restrict__ ctr, FrzMatchDev* __restrict__ out) {
-    const uint32_t li = (rec.slot_rank >> 10) & 0x3ff, rank = rec.slot_rank >> 20;
-    uint64_t pos = tile_out_base[rec.tile] + rank;
+    const uint32_t li = (rec.slot_rank >> 10) & 0x3ff;
+    // rank among the tile's survivors in index order, from the survivor bitmap
+    const uint64_t wi = (uint64_t)rec.tile * 32 + (li >> 5);
+    const uint32_t rank = rv.word_prefix[wi] + __popc(rv.surv_bitmap[wi] & ((1u << (li & 31)) - 1));
+    uint64_t pos = rv.tile_out_base[rec.tile] + rank;
     if (reversed) pos = ctr->total - 1 - pos;
     FrzMatchDev m;
     m.index = index_offset + rec.tile * FRZ_TILE + li;
@@ -241,13 +258,13 @@ __device__ __forceinline__ void emit_match(const FrzSurvivor& rec, uint32_t scor
     out[pos] = m;
 }
 
-template <int LANES, int COLS, bool WRAP8>
-__global__ void __launch_bounds__(kSwThreads) k_sw(const FrzCorpusView cv, const __grid_constant__ FrzPatternDev pat,
-                                                   const FrzSurvivor* __restrict__ surv, int cls,
-                                                   const uint64_t* __restrict__ tile_out_base, FrzCounters* __restrict__ ctr,
+template <int LANES, int COLS, bool WRAP8, int MINB>
+__global__ void __launch_bounds__(kSwThreads, MINB) k_sw(const FrzCorpusView cv, const __grid_constant__ FrzPatternDev pat,
+                                                   const FrzSurvivor* __restrict__ surv, unsigned long long surv_cap, int cls,
+                                                   const FrzRankView rv, FrzCounters* __restrict__ ctr,
                                                    uint32_t index_offset, int reversed, FrzMatchDev* __restrict__ out) {
     extern __shared__ __align__(16) uint32_t sw_smem[];
-    const unsigned long long count = ctr->class_count[cls];
+    const unsigned long long count = min(ctr->class_count[cls], surv_cap);
     uint32_t local_max = 0;
     for (unsigned long long j = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; j < count;
          j += (unsigned long long)gridDim.x * blockDim.x) {
@@ -261,7 +278,7 @@ __global__ void __launch_bounds__(kSwThreads) k_sw(const FrzCorpusView cv, const
         uint32_t score = SwCore<LANES, COLS, WRAP8>::run(hw, W, pat, start == 0, sw_smem);
         bool exact = start == 0 && full_end && window_equals_needle(hw, W, pat);
         if (exact) score = (score + pat.exact_bonus) & 0xffffu;
-        emit_match(rec, score, exact, index_offset, reversed != 0, tile_out_base, ctr, out);
+        emit_match(rec, score, exact, index_offset, reversed != 0, rv, ctr, out);
         local_max = max(local_max, score);
     }
     local_max = __reduce_max_sync(0xffffffffu, local_max);
@@ -323,10 +340,10 @@ __device__ int greedy_score(const uint4* base, uint32_t start, int W, const FrzP
 }
 
 __global__ void __launch_bounds__(64) k_sw_generic(const FrzCorpusView cv, const __grid_constant__ FrzPatternDev pat,
-                                                   const FrzSurvivor* __restrict__ surv, int cls,
-                                                   const uint64_t* __restrict__ tile_out_base, FrzCounters* __restrict__ ctr,
+                                                   const FrzSurvivor* __restrict__ surv, unsigned long long surv_cap, int cls,
+                                                   const FrzRankView rv, FrzCounters* __restrict__ ctr,
                                                    uint32_t index_offset, int reversed, FrzMatchDev* __restrict__ out) {
-    const unsigned long long count = ctr->class_count[cls];
+    const unsigned long long count = min(ctr->class_count[cls], surv_cap);
     const int L = pat.sw_lanes;
     const uint32_t lane_mask = pat.score_bits == 8 ? 0xffu : 0xffffu;  // real element width
     uint32_t local_max = 0;
@@ -408,22 +425,22 @@ __global__ void __launch_bounds__(64) k_sw_generic(const FrzCorpusView cv, const
             for (int k = 0; k < pat.n; k++) exact = exact && hay_byte(base, k) == pat.c[k];
         }
         if (exact) score = (score + pat.exact_bonus) & 0xffffu;
-        emit_match(rec, score, exact, index_offset, reversed != 0, tile_out_base, ctr, out);
+        emit_match(rec, score, exact, index_offset, reversed != 0, rv, ctr, out);
         local_max = max(local_max, score);
     }
     if (local_max) atomicMax(&ctr->max_score, local_max);
 }
 
 // literal patterns: the prefilter stage already produced (score, exact); just place the match
-__global__ void __launch_bounds__(256) k_emit_literal(const FrzSurvivor* __restrict__ surv,
-                                                      const uint64_t* __restrict__ tile_out_base, FrzCounters* __restrict__ ctr,
+__global__ void __launch_bounds__(256) k_emit_literal(const FrzSurvivor* __restrict__ surv, unsigned long long surv_cap,
+                                                      const FrzRankView rv, FrzCounters* __restrict__ ctr,
                                                       uint32_t index_offset, int reversed, FrzMatchDev* __restrict__ out) {
-    const unsigned long long count = ctr->class_count[FRZ_C_COLS64];
+    const unsigned long long count = min(ctr->class_count[FRZ_C_COLS64], surv_cap);
     uint32_t local_max = 0;
     for (unsigned long long j = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; j < count;
          j += (unsigned long long)gridDim.x * blockDim.x) {
         const FrzSurvivor rec = surv[j];
-        emit_match(rec, rec.start, rec.end != 0, index_offset, reversed != 0, tile_out_base, ctr, out);
+        emit_match(rec, rec.start, rec.end != 0, index_offset, reversed != 0, rv, ctr, out);
         local_max = max(local_max, rec.start);
     }
     if (local_max) atomicMax(&ctr->max_score, local_max);
@@ -444,21 +461,38 @@ template <int LANES, int COLS>
 frz_status launch_sw_variant(const FrzCorpusView& cv, const FrzPatternDev& pat, int cls, uint32_t index_offset, bool reversed,
                              FrzWorkspace& ws, FrzMatchDev* d_out, cudaStream_t stream) {
     // persistent grid: a multiple of the SM count; survivors are strided over it
-    const int blocks = sm_count() * 4;
+    const int blocks = sm_count() * 2;
     const size_t smem = SwCore<LANES, COLS, false>::smem_bytes;
     if (smem > 48 * 1024) {
         static bool attr_set = false;
         if (!attr_set) {
-            FRZ_CUDA_TRY(cudaFuncSetAttribute(k_sw<LANES, COLS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            FRZ_CUDA_TRY(cudaFuncSetAttribute(k_sw<LANES, COLS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            FRZ_CUDA_TRY(cudaFuncSetAttribute(k_sw<LANES, COLS, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            FRZ_CUDA_TRY(cudaFuncSetAttribute(k_sw<LANES, COLS, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             attr_set = true;
         }
     }
+    if (LANES == 64 && COLS == 64 && !pat.wrap8) {
+        // occupancy experiment knob (register cap per thread): FRZ_SW_MINB = 2 (255 regs) | 3 (168) | 4 (128)
+        static int minb = -1;
+        if (minb < 0) { const char* e = getenv("FRZ_SW_MINB"); minb = e ? atoi(e) : 2; }
+        if (minb == 3) {
+            k_sw<64, 64, false, 3><<<sm_count() * 3, kSwThreads, 0, stream>>>(cv, pat, ws.survivors[cls], ws.survivor_cap, cls, rank_view(ws),
+                                                                          ws.counters, index_offset, reversed ? 1 : 0, d_out);
+            FRZ_CUDA_TRY(cudaGetLastError());
+            return FRZ_OK;
+        }
+        if (minb == 4) {
+            k_sw<64, 64, false, 4><<<sm_count() * 4, kSwThreads, 0, stream>>>(cv, pat, ws.survivors[cls], ws.survivor_cap, cls, rank_view(ws),
+                                                                          ws.counters, index_offset, reversed ? 1 : 0, d_out);
+            FRZ_CUDA_TRY(cudaGetLastError());
+            return FRZ_OK;
+        }
+    }
     if (pat.wrap8)
-        k_sw<LANES, COLS, true><<<blocks, kSwThreads, smem, stream>>>(cv, pat, ws.survivors[cls], cls, ws.tile_out_base, ws.counters,
+        k_sw<LANES, COLS, true, 1><<<blocks, kSwThreads, smem, stream>>>(cv, pat, ws.survivors[cls], ws.survivor_cap, cls, rank_view(ws), ws.counters,
                                                                    index_offset, reversed ? 1 : 0, d_out);
     else
-        k_sw<LANES, COLS, false><<<blocks, kSwThreads, smem, stream>>>(cv, pat, ws.survivors[cls], cls, ws.tile_out_base, ws.counters,
+        k_sw<LANES, COLS, false, 1><<<blocks, kSwThreads, smem, stream>>>(cv, pat, ws.survivors[cls], ws.survivor_cap, cls, rank_view(ws), ws.counters,
                                                                     index_offset, reversed ? 1 : 0, d_out);
     FRZ_CUDA_TRY(cudaGetLastError());
     return FRZ_OK;
@@ -482,7 +516,7 @@ frz_status frz_launch_sw(const FrzCorpusView& cv, const FrzPatternDev& pat, uint
                          FrzWorkspace& ws, FrzMatchDev* d_out, cudaStream_t stream, FrzLaunchStats* st) {
     if (cv.n_tiles == 0) return FRZ_OK;
     if (pat.typo_mode == FRZ_T_LITERAL) {
-        k_emit_literal<<<sm_count() * 4, 256, 0, stream>>>(ws.survivors[FRZ_C_COLS64], ws.tile_out_base, ws.counters,
+        k_emit_literal<<<sm_count() * 4, 256, 0, stream>>>(ws.survivors[FRZ_C_COLS64], ws.survivor_cap, rank_view(ws), ws.counters,
                                                            index_offset, reversed ? 1 : 0, d_out);
         FRZ_CUDA_TRY(cudaGetLastError());
         if (st) st->launches++;
@@ -490,7 +524,7 @@ frz_status frz_launch_sw(const FrzCorpusView& cv, const FrzPatternDev& pat, uint
     }
     FRZ_TRY(launch_sw_cols<64>(cv, pat, FRZ_C_COLS64, index_offset, reversed, ws, d_out, stream));
     FRZ_TRY(launch_sw_cols<128>(cv, pat, FRZ_C_COLS128, index_offset, reversed, ws, d_out, stream));
-    k_sw_generic<<<sm_count() * 2, 64, 0, stream>>>(cv, pat, ws.survivors[FRZ_C_GENERIC], FRZ_C_GENERIC, ws.tile_out_base,
+    k_sw_generic<<<sm_count() * 2, 64, 0, stream>>>(cv, pat, ws.survivors[FRZ_C_GENERIC], ws.survivor_cap, FRZ_C_GENERIC, rank_view(ws),
                                                     ws.counters, index_offset, reversed ? 1 : 0, d_out);
     FRZ_CUDA_TRY(cudaGetLastError());
     if (st) st->launches += 3;
