@@ -79,6 +79,10 @@ struct FrzPatternDev {
     uint32_t k_pen_b[6];    // -(s * gap_extend + gap_open_x)
     uint32_t k_neg_mis, k_ex_add, k_up_plain, k_up_open, k_case, k_cap, k_delim, k_base;
     uint32_t om16[FRZ_MAX_NEEDLE], tg16[FRZ_MAX_NEEDLE], c16[FRZ_MAX_NEEDLE];
+    // distinct needle bytes (either-case classes) for the occurrence-mask prefilter
+    int32_t n_distinct;                 // 0 → too many distinct bytes, use the scanning fallback
+    uint8_t dc_om[16], dc_tg[16];       // probe of distinct class d
+    uint8_t cid[FRZ_MAX_NEEDLE];        // needle index → distinct class
     // untruncated scoring for the literal matcher / greedy fallback (u16 arithmetic)
     int32_t raw_match, raw_mismatch, raw_gap_open, raw_gap_extend, raw_prefix, raw_cap, raw_case, raw_delim;
 };

@@ -406,6 +406,20 @@ frz_status compile_pattern(const OwnedPattern& src, const frz_config& mcfg, bool
         d.om[i] = fl != ch ? 0x20 : 0;
         d.tg[i] = fl != ch ? (uint8_t)(ch | 0x20) : ch;
     }
+    {   // distinct (om, tg) classes
+        int nd = 0;
+        bool ok = true;
+        for (size_t i = 0; i < n && ok; i++) {
+            int found = -1;
+            for (int k = 0; k < nd; k++) if (d.dc_om[k] == d.om[i] && d.dc_tg[k] == d.tg[i]) { found = k; break; }
+            if (found < 0) {
+                if (nd == 16) { ok = false; break; }
+                d.dc_om[nd] = d.om[i]; d.dc_tg[nd] = d.tg[i]; found = nd++;
+            }
+            d.cid[i] = (uint8_t)found;
+        }
+        d.n_distinct = ok ? nd : 0;
+    }
     d.raw_match = sc.match_score; d.raw_mismatch = sc.mismatch_penalty; d.raw_gap_open = sc.gap_open_penalty;
     d.raw_gap_extend = sc.gap_extend_penalty; d.raw_prefix = sc.prefix_bonus; d.raw_cap = sc.capitalization_bonus;
     d.raw_case = sc.matching_case_bonus; d.raw_delim = sc.delimiter_bonus; d.exact_bonus = sc.exact_match_bonus;

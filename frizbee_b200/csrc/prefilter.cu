@@ -25,10 +25,10 @@
 
 namespace {
 
-constexpr int kThreads = 256;
+constexpr int kThreads = 128;
 constexpr int kWarps = kThreads / 32;
 constexpr int kSliceUnits = 8;                         // haystacks up to 128 bytes are staged in smem
-constexpr int kSliceWords = kSliceUnits * 4 + 1;       // +1 word: conflict-free stride, and a zero guard
+constexpr int kSliceWords = kSliceUnits * 4 + 2;       // +2 words: 8-byte aligned, conflict-free LDS.64 stride, zero guard
 
 struct SliceAcc {
     const uint32_t* s;
@@ -337,12 +337,178 @@ __device__ bool lit_find(const A& a, const FrzPatternDev& p, int len, int* opos,
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Occurrence-mask windows (0 and 1 typo) for candidates staged in shared memory.
+//
+// The reference works on per-chunk occurrence bitmasks (`B::occ`, one compare+movemask per needle
+// byte).  A GPU lane has no movemask, and the first two versions of this stage (nested scans, then a
+// per-lane scanning automaton) spent 4500-7000 warp instructions per 32 candidates on divergent
+// byte scans (profiles/r01b, r01c).  Here each lane first builds, with uniform straight-line code,
+// the 64-bit occurrence mask of every DISTINCT needle byte class over a 64-byte block of its haystack:
+// 4 bytes per step — xor/or with the probe, exact zero-byte flags, and one DP4A that packs the four
+// flags into mask bits (weights 1,2,4,8 / 16,...,128).  After that the reference's mask state machine
+// runs literally (`clear_through_lowest`, `first_path_chunk_mask > second_path_chunk_mask`, ...),
+// every `occ` being one shared-memory load.
+// ---------------------------------------------------------------------------------------------
+constexpr int kMaxDistinct = 16;
+
+// 0x80 in every byte of x that is zero
+__device__ __forceinline__ uint32_t zero_flags(uint32_t x) {
+    const uint32_t t = (x & 0x7f7f7f7fu) + 0x7f7f7f7fu;
+    uint32_t r;
+    asm("lop3.b32 %0, %1, %2, %3, 0x10;" : "=r"(r) : "r"(0x80808080u), "r"(t), "r"(x));  // a & ~b & ~c
+    return r;
+}
+
+// occ[d][lane] = occurrence mask of distinct class d over bytes [64*blk, 64*blk+64) of the lane's slice
+__device__ __forceinline__ void build_block_masks(const uint32_t* sl, int blk, const FrzPatternDev& pat,
+                                                  uint2 (*occ)[32], uint32_t lane) {
+    uint32_t w[16];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const uint2 v = *reinterpret_cast<const uint2*>(sl + 16 * blk + 2 * k);
+        w[2 * k] = v.x; w[2 * k + 1] = v.y;
+    }
+    for (int d = 0; d < pat.n_distinct; d++) {
+        const uint32_t om4 = splat4(pat.dc_om[d]), tg4 = splat4(pat.dc_tg[d]);
+        uint32_t m[2] = {0u, 0u};
+#pragma unroll
+        for (int j = 0; j < 8; j++) {  // 8 bytes per step → 8 mask bits (scaled by 128)
+            const uint32_t f0 = zero_flags((w[2 * j] | om4) ^ tg4);
+            const uint32_t f1 = zero_flags((w[2 * j + 1] | om4) ^ tg4);
+            const uint32_t v = __dp4a(f0, 0x08040201u, __dp4a(f1, 0x80402010u, 0u));  // = 128 * bits
+            const int sh = 8 * (j & 3) - 7;
+            m[j >> 2] |= sh < 0 ? (v >> 7) : (v << sh);
+        }
+        occ[d][lane] = make_uint2(m[0], m[1]);
+    }
+}
+
+__device__ __forceinline__ uint64_t lowmask64(int n) { return n >= 64 ? ~0ull : ((1ull << n) - 1); }
+__device__ __forceinline__ uint64_t u2_to_u64(uint2 v) { return (uint64_t)v.x | ((uint64_t)v.y << 32); }
+
+// Window of the 0-typo prefilter (closed form) from block masks.  Warp-wide;
+// `active` lanes own an in-slice candidate of `len` bytes (len <= 128).
+__device__ __forceinline__ bool masks_k0(const uint32_t* sl, const FrzPatternDev& pat, const uint8_t* __restrict__ cid_s,
+                                         uint2 (*occ)[32], int len, bool active, int* ostart, int* oend) {
+    const uint32_t lane = frz_lane();
+    const int n = pat.n;
+    int ni = 0, start = 0, end = 0;
+    bool alive = active && len > 0, found = false;
+    const int max_len = __reduce_max_sync(0xffffffffu, active ? len : 0);
+    for (int blk = 0; blk * 64 < max_len; blk++) {
+        build_block_masks(sl, blk, pat, occ, lane);
+        __syncwarp();
+        const int rem = len - blk * 64;
+        const uint64_t valid = rem > 0 ? lowmask64(rem) : 0ull;
+        // 1 + last occurrence of the last needle byte (whole haystack)
+        const uint64_t lastm = u2_to_u64(occ[pat.cid[n - 1]][lane]) & valid;
+        if (lastm) end = blk * 64 + 64 - __clzll((long long)lastm);
+        uint64_t fc = valid;
+        bool in_blk = alive && !found && rem > 0;
+        while (__any_sync(0xffffffffu, in_blk)) {
+            if (in_blk) {
+                const uint64_t x = u2_to_u64(occ[cid_s[ni]][lane]) & fc;
+                if (x) {
+                    if (ni == 0) start = blk * 64 + __ffsll((long long)x) - 1;
+                    fc &= ~(x ^ (x - 1));  // clear_through_lowest
+                    if (++ni == n) { found = true; in_blk = false; }
+                } else in_blk = false;
+            }
+        }
+        __syncwarp();
+    }
+    *ostart = start;
+    *oend = end;
+    return found;
+}
+
+// match_haystack_1_typo (src/prefilter/algo/ascii_typos.rs:15-110) on block masks, chunk width L.
+__device__ __forceinline__ bool masks_k1(const uint32_t* sl, const FrzPatternDev& pat, const uint8_t* __restrict__ cid_s,
+                                         uint2 (*occ)[32], int len, bool active, int* ostart, int* oend) {
+    const uint32_t lane = frz_lane();
+    const int n = pat.n, L = pat.pf_lanes;
+    int f = 0, s = 1, ms = 0x7fffffff, end = -1;
+    // 0 running, 1 found, 2 rejected / idle
+    int state = 2;
+    if (active) state = n <= 1 ? 1 : (len == 0 ? 2 : 0);
+    if (active && n <= 1) ms = 0;
+    const int max_len = __reduce_max_sync(0xffffffffu, active ? len : 0);
+    const uint64_t lmask = lowmask64(L);
+    for (int blk = 0; blk * 64 < max_len; blk++) {
+        build_block_masks(sl, blk, pat, occ, lane);
+        __syncwarp();
+        const int rem = len - blk * 64;
+        const uint64_t valid = rem > 0 ? lowmask64(rem) : 0ull;
+        // find_end_pos_with_typos: 1 + last occurrence of either of the last two needle bytes, else len
+        if (n >= 2) {
+            const uint64_t lastm = (u2_to_u64(occ[pat.cid[n - 1]][lane]) | u2_to_u64(occ[pat.cid[n - 2]][lane])) & valid;
+            if (lastm) end = blk * 64 + 64 - __clzll((long long)lastm);
+        }
+        int cs = blk * 64;                       // chunk start (absolute)
+        bool in_blk = state == 0 && rem > 0;
+        bool init = true;
+        uint64_t fm = 0, sm = 0, fc = 0, sc = 0;
+        while (__any_sync(0xffffffffu, in_blk)) {
+            if (in_blk) {
+                const int sh = cs - blk * 64;
+                if (init) {  // new chunk: both path masks restart from the whole chunk
+                    const uint64_t cm = (valid >> sh) & lmask;
+                    fm = (u2_to_u64(occ[cid_s[f]][lane]) >> sh) & lmask;
+                    sm = (u2_to_u64(occ[cid_s[s]][lane]) >> sh) & lmask;
+                    fc = sc = cm;
+                    init = false;
+                }
+                bool adv = false;
+                const int cand = f + 1;
+                if (cand > s) {
+                    if (cand == n) { state = 1; in_blk = false; }
+                    else { s = cand; sc = fc; sm = (u2_to_u64(occ[cid_s[s]][lane]) >> sh) & lmask; }
+                } else if (cand == s && fc > sc) sc = fc;
+                if (in_blk) {
+                    const uint64_t x = fm & fc;
+                    if (x) {
+                        ms = min(ms, cs + __ffsll((long long)x) - 1);
+                        f++;
+                        fc &= ~(x ^ (x - 1));
+                        fm = (u2_to_u64(occ[cid_s[f]][lane]) >> sh) & lmask;
+                        adv = true;
+                    }
+                    const uint64_t y = sm & sc;
+                    if (y) {
+                        ms = min(ms, cs + __ffsll((long long)y) - 1);
+                        s++;
+                        if (s >= n) { state = 1; in_blk = false; }
+                        else {
+                            sc &= ~(y ^ (y - 1));
+                            sm = (u2_to_u64(occ[cid_s[s]][lane]) >> sh) & lmask;
+                            adv = true;
+                        }
+                    }
+                    if (in_blk && !adv) {  // next chunk
+                        cs += L;
+                        init = true;
+                        if (cs >= len) { state = 2; in_blk = false; }
+                        else if (cs >= blk * 64 + 64) in_blk = false;  // continues in the next block
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    }
+    *ostart = ms == 0x7fffffff ? 0 : ms;
+    *oend = end < 0 ? len : end;
+    return state == 1;
+}
+
 constexpr int kQueueCap = 64;  // per-warp candidate queue (31 left over + 32 new at most)
 
 struct WarpQueue {
     uint32_t slice[kQueueCap][kSliceWords];  // candidate haystack bytes (zero padded to the unit), +1 guard word
     uint32_t meta[kQueueCap];                // tile << 10 | slot
     uint32_t info[kQueueCap];                // len | in_slice << 31
+    uint2 occ[kMaxDistinct][32];             // per-lane occurrence masks of the distinct needle byte classes
 };
 
 __device__ __forceinline__ int sw_class_of(int window) {
@@ -352,8 +518,8 @@ __device__ __forceinline__ int sw_class_of(int window) {
 // Exact window of one queued candidate (phase B) + survivor emission.  All 32 lanes of the warp call
 // this together (`active` lanes have an entry); emission uses warp-aggregated atomics.
 template <int MODE>
-__device__ __forceinline__ void process_candidate(const FrzCorpusView& cv, const FrzPatternDev& pat, const WarpQueue& q,
-                                                  int entry, bool active, FrzSurvivor* const* lists,
+__device__ __forceinline__ void process_candidate(const FrzCorpusView& cv, const FrzPatternDev& pat, const uint8_t* __restrict__ cid_s,
+                                                  WarpQueue& q, int entry, bool active, FrzSurvivor* const* lists,
                                                   unsigned long long surv_cap, uint32_t* __restrict__ surv_bitmap,
                                                   FrzCounters* __restrict__ ctr) {
     const uint32_t lane = frz_lane();
@@ -361,6 +527,17 @@ __device__ __forceinline__ void process_candidate(const FrzCorpusView& cv, const
     int cls = 0;
     FrzSurvivor rec;
     rec.tile = 0; rec.slot_rank = 0; rec.start = 0; rec.end = 0;
+    // warp-wide flat automaton for the common case (haystack staged in the slice)
+    bool flat_done = false, flat_ok = false;
+    int flat_start = 0, flat_end = 0;
+    if ((MODE == FRZ_T_0 || MODE == FRZ_T_1) && pat.n_distinct > 0) {
+        const uint32_t info0 = active ? q.info[entry] : 0u;
+        const bool use_flat = active && (info0 >> 31) != 0;
+        const int len0 = (int)(info0 & 0x7fffffffu);
+        if (MODE == FRZ_T_0) flat_ok = masks_k0(q.slice[entry], pat, cid_s, q.occ, len0, use_flat, &flat_start, &flat_end);
+        else flat_ok = masks_k1(q.slice[entry], pat, cid_s, q.occ, len0, use_flat, &flat_start, &flat_end);
+        flat_done = use_flat;
+    }
     if (active) {
         const uint32_t meta = q.meta[entry], info = q.info[entry];
         const uint32_t tile = meta >> FRZ_TILE_SHIFT, slot = meta & (FRZ_TILE - 1);
@@ -375,7 +552,8 @@ __device__ __forceinline__ void process_candidate(const FrzCorpusView& cv, const
             FrzGroupDesc gd = cv.groups[tile * FRZ_GROUPS_PER_TILE + (slot >> 5)];
             ga.base = cv.data + cv.tile_base[tile] + gd.unit_off + (slot & 31);
         }
-        if (MODE == FRZ_T_0) ok = in_slice ? window_k0(sa, pat, len, &start, &end) : window_k0(ga, pat, len, &start, &end);
+        if (flat_done) { ok = flat_ok; start = flat_start; end = flat_end; }
+        else if (MODE == FRZ_T_0) ok = in_slice ? window_k0(sa, pat, len, &start, &end) : window_k0(ga, pat, len, &start, &end);
         else if (MODE == FRZ_T_1) ok = in_slice ? window_k1(sa, pat, len, &start, &end) : window_k1(ga, pat, len, &start, &end);
         else if (MODE == FRZ_T_2) ok = in_slice ? window_k2(sa, pat, len, &start, &end) : window_k2(ga, pat, len, &start, &end);
         else if (MODE == FRZ_T_MANY) ok = in_slice ? window_many(sa, pat, len, &start, &end) : window_many(ga, pat, len, &start, &end);
@@ -429,6 +607,10 @@ __global__ void __launch_bounds__(kThreads) k_prefilter(const FrzCorpusView cv, 
     const uint32_t lane = frz_lane(), warp = threadIdx.x >> 5;
     WarpQueue& q = reinterpret_cast<WarpQueue*>(smem_raw)[warp];
     FrzSurvivor* const lists[FRZ_N_CLASSES] = {surv0, surv1, surv2};
+    // needle index → distinct class, indexed per lane (a divergent index would serialise in the constant bank)
+    __shared__ uint8_t cid_s[FRZ_MAX_NEEDLE];
+    if (threadIdx.x < FRZ_MAX_NEEDLE) cid_s[threadIdx.x] = pat.cid[threadIdx.x];
+    __syncthreads();
 
     const uint32_t om0 = splat4(pat.om[0]), tg0 = splat4(pat.tg[0]);
     const uint32_t om1 = splat4(pat.om[pat.n > 1 ? 1 : 0]), tg1 = splat4(pat.tg[pat.n > 1 ? 1 : 0]);
@@ -441,13 +623,48 @@ __global__ void __launch_bounds__(kThreads) k_prefilter(const FrzCorpusView cv, 
     const uint32_t n_warps = gridDim.x * kWarps;
     uint32_t head = 0, count = 0;  // ring state (warp-uniform)
 
-    for (uint32_t gidx = blockIdx.x * kWarps + warp; gidx < total_groups; gidx += n_warps) {
-        // ------------------------------------------------------------ phase A
+    // Software pipeline (the warp has no other way to keep HBM busy at 16 warps/SM): descriptors of
+    // group i+2 and the haystack units of group i+1 are in flight while group i is probed.
+    struct Desc {
+        FrzGroupDesc gd;
+        uint32_t meta;
+        uint64_t tb;
+    };
+    auto load_desc = [&](uint32_t gidx, Desc& d) {
+        if (gidx < total_groups) {
+            d.gd = cv.groups[gidx];
+            d.meta = cv.slot_meta[(uint64_t)(gidx >> 5) * FRZ_TILE + (gidx & 31) * FRZ_GROUP + lane];
+            d.tb = cv.tile_base[gidx >> 5];
+        } else {
+            d.gd = FrzGroupDesc{0u, 0u};
+            d.meta = FRZ_INVALID_SLOT;
+            d.tb = 0;
+        }
+    };
+    auto load_units = [&](const Desc& d, uint4 (&u)[kSliceUnits]) {
+        const uint4* gp = cv.data + d.tb + d.gd.unit_off + lane;
+#pragma unroll
+        for (int k = 0; k < kSliceUnits; k++) {
+            if (k < (int)d.gd.gunits && d.gd.gunits <= kSliceUnits) u[k] = __ldg(gp + (size_t)k * FRZ_GROUP);
+        }
+    };
+    const uint32_t g0 = blockIdx.x * kWarps + warp;
+    Desc dc, dn;
+    uint4 u[kSliceUnits], un[kSliceUnits];
+    load_desc(g0, dc);
+    load_desc(g0 + n_warps, dn);
+    load_units(dc, u);
+
+    for (uint32_t gidx = g0; gidx < total_groups; gidx += n_warps) {
+        // ------------------------------------------------------------ pipeline: issue the next loads
+        Desc dnn;
+        load_desc(gidx + 2 * n_warps, dnn);
+        load_units(dn, un);
+        // ------------------------------------------------------------ phase A on the current group
         const uint32_t tile = gidx >> 5, g = gidx & 31;
-        const FrzGroupDesc gd = cv.groups[gidx];
-        if (gd.gunits == 0 && MODE != FRZ_T_NONE && MODE != FRZ_T_LITERAL && pat.min_hay_len > 0) continue;  // only empty strings
+        const FrzGroupDesc gd = dc.gd;
         const uint32_t slot = g * FRZ_GROUP + lane;
-        const uint32_t meta = cv.slot_meta[(uint64_t)tile * FRZ_TILE + slot];
+        const uint32_t meta = dc.meta;
         const bool valid = meta != FRZ_INVALID_SLOT;
         const uint32_t len = valid ? meta >> FRZ_TILE_SHIFT : 0;
         bool pass = valid && (int)len >= pat.min_hay_len;
@@ -455,45 +672,40 @@ __global__ void __launch_bounds__(kThreads) k_prefilter(const FrzCorpusView cv, 
             const uint64_t idx = (uint64_t)tile * FRZ_TILE + (meta & (FRZ_TILE - 1));
             pass = pass && ((cand_bitmap[idx >> 5] >> (idx & 31)) & 1);
         }
-        const uint4* gp = cv.data + cv.tile_base[tile] + gd.unit_off + lane;
-        uint4 u[kSliceUnits];
         uint32_t acc = 0;
         const bool in_slice = gd.gunits <= kSliceUnits;
-        if (in_slice) {
-#pragma unroll
-            for (int k = 0; k < kSliceUnits; k++) {
-                u[k] = make_uint4(0, 0, 0, 0);
-                if (k < (int)gd.gunits) u[k] = __ldg(gp + (size_t)k * FRZ_GROUP);
-            }
-            if (probe) {
+        const bool skip_group = gd.gunits == 0 && MODE != FRZ_T_NONE && MODE != FRZ_T_LITERAL && pat.min_hay_len > 0;
+        if (probe && !skip_group) {
+            if (in_slice) {
 #pragma unroll
                 for (int k = 0; k < kSliceUnits; k++) {
-                    if (k < (int)gd.gunits) {
-                        const uint32_t w[4] = {u[k].x, u[k].y, u[k].z, u[k].w};
+                    if (k >= (int)gd.gunits) break;  // warp-uniform
+                    const uint32_t w[4] = {u[k].x, u[k].y, u[k].z, u[k].w};
 #pragma unroll
-                        for (int j = 0; j < 4; j++) {
-                            uint32_t x = (w[j] | om0) ^ tg0;
-                            acc |= (x - 0x01010101u) & ~x;
-                            if (MODE >= FRZ_T_1) { x = (w[j] | om1) ^ tg1; acc |= (x - 0x01010101u) & ~x; }
-                            if (MODE >= FRZ_T_2) { x = (w[j] | om2) ^ tg2; acc |= (x - 0x01010101u) & ~x; }
-                        }
+                    for (int j = 0; j < 4; j++) {
+                        uint32_t x = (w[j] | om0) ^ tg0;
+                        acc |= (x - 0x01010101u) & ~x;
+                        if (MODE >= FRZ_T_1) { x = (w[j] | om1) ^ tg1; acc |= (x - 0x01010101u) & ~x; }
+                        if (MODE >= FRZ_T_2) { x = (w[j] | om2) ^ tg2; acc |= (x - 0x01010101u) & ~x; }
+                    }
+                }
+            } else {
+                const uint4* gp = cv.data + dc.tb + gd.unit_off + lane;
+                for (uint32_t k = 0; k < gd.gunits; k++) {
+                    const uint4 v = __ldg(gp + (size_t)k * FRZ_GROUP);
+                    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        uint32_t x = (w[j] | om0) ^ tg0;
+                        acc |= (x - 0x01010101u) & ~x;
+                        if (MODE >= FRZ_T_1) { x = (w[j] | om1) ^ tg1; acc |= (x - 0x01010101u) & ~x; }
+                        if (MODE >= FRZ_T_2) { x = (w[j] | om2) ^ tg2; acc |= (x - 0x01010101u) & ~x; }
                     }
                 }
             }
-        } else if (probe) {
-            for (uint32_t k = 0; k < gd.gunits; k++) {
-                const uint4 v = __ldg(gp + (size_t)k * FRZ_GROUP);
-                const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    uint32_t x = (w[j] | om0) ^ tg0;
-                    acc |= (x - 0x01010101u) & ~x;
-                    if (MODE >= FRZ_T_1) { x = (w[j] | om1) ^ tg1; acc |= (x - 0x01010101u) & ~x; }
-                    if (MODE >= FRZ_T_2) { x = (w[j] | om2) ^ tg2; acc |= (x - 0x01010101u) & ~x; }
-                }
-            }
+            pass = pass && (trivially || (acc & 0x80808080u) != 0);
         }
-        if (probe) pass = pass && (trivially || (acc & 0x80808080u) != 0);
+        if (skip_group) pass = false;
         const uint32_t ballot = __ballot_sync(0xffffffffu, pass);
         if (ballot) {
             if (pass) {
@@ -501,28 +713,46 @@ __global__ void __launch_bounds__(kThreads) k_prefilter(const FrzCorpusView cv, 
                 q.meta[e] = (tile << FRZ_TILE_SHIFT) | slot;
                 q.info[e] = len | (in_slice ? 0x80000000u : 0u);
                 if (in_slice) {
-                    uint32_t* dst = q.slice[e];
+                    uint4* dst = reinterpret_cast<uint4*>(q.slice[e]);
 #pragma unroll
                     for (int k = 0; k < kSliceUnits; k++) {
-                        if (k < (int)gd.gunits) { dst[4 * k] = u[k].x; dst[4 * k + 1] = u[k].y; dst[4 * k + 2] = u[k].z; dst[4 * k + 3] = u[k].w; }
+                        if (k >= (int)gd.gunits) break;
+                        // slices are only 8-byte aligned (136-byte stride): two 8-byte stores per unit
+                        uint2* d2 = reinterpret_cast<uint2*>(q.slice[e] + 4 * k);
+                        d2[0] = make_uint2(u[k].x, u[k].y);
+                        d2[1] = make_uint2(u[k].z, u[k].w);
                     }
-                    dst[4 * gd.gunits] = 0;  // guard word
+                    (void)dst;
+                    *reinterpret_cast<uint2*>(q.slice[e] + 4 * gd.gunits) = make_uint2(0u, 0u);  // guard words
+                    // blocks are built 64 bytes at a time: zero the tail of a half-filled block
+                    if (gd.gunits & 3) {
+                        for (uint32_t k = gd.gunits; k < ((gd.gunits + 3) & ~3u); k++) {
+                            uint2* d2 = reinterpret_cast<uint2*>(q.slice[e] + 4 * k);
+                            d2[0] = make_uint2(0u, 0u);
+                            d2[1] = make_uint2(0u, 0u);
+                        }
+                    }
                 }
             }
             count += __popc(ballot);
             __syncwarp();
             // -------------------------------------------------------- phase B on full batches
             if (count >= 32) {
-                process_candidate<MODE>(cv, pat, q, (head + lane) & (kQueueCap - 1), true, lists, surv_cap, surv_bitmap, ctr);
+                process_candidate<MODE>(cv, pat, cid_s, q, (head + lane) & (kQueueCap - 1), true, lists, surv_cap, surv_bitmap, ctr);
                 head = (head + 32) & (kQueueCap - 1);
                 count -= 32;
                 __syncwarp();
             }
         }
+        // ------------------------------------------------------------ rotate the pipeline
+        dc = dn;
+        dn = dnn;
+#pragma unroll
+        for (int k = 0; k < kSliceUnits; k++) u[k] = un[k];
     }
     if (count) {  // flush the partial batch
         __syncwarp();
-        process_candidate<MODE>(cv, pat, q, (head + lane) & (kQueueCap - 1), lane < count, lists, surv_cap, surv_bitmap, ctr);
+        process_candidate<MODE>(cv, pat, cid_s, q, (head + lane) & (kQueueCap - 1), lane < count, lists, surv_cap, surv_bitmap, ctr);
     }
 }
 
@@ -587,9 +817,9 @@ frz_status frz_launch_prefilter(const FrzCorpusView& cv, const FrzPatternDev& pa
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (sms <= 0) sms = 148;
-    // persistent warps: 3 blocks of 8 warps per SM (shared-memory bound), capped by the work
+    // persistent warps: 4 blocks of 4 warps per SM (shared-memory bound), capped by the work
     const uint32_t total_groups = cv.n_tiles * FRZ_GROUPS_PER_TILE;
-    const uint32_t grid = std::max<uint32_t>(1, std::min<uint32_t>((uint32_t)sms * 3, (total_groups + kWarps - 1) / kWarps));
+    const uint32_t grid = std::max<uint32_t>(1, std::min<uint32_t>((uint32_t)sms * 4, (total_groups + kWarps - 1) / kWarps));
     FRZ_CUDA_TRY(cudaMemsetAsync(ws.surv_bitmap, 0, (size_t)cv.n_tiles * 32 * sizeof(uint32_t), stream));
 #define FRZ_PF_LAUNCH(MODE)                                                                                     \
     do {                                                                                                        \

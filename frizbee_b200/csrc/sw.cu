@@ -74,7 +74,9 @@ struct RowStore<R, true> {
     __device__ __forceinline__ void set(int r, uint32_t x) { base[r * kSwThreads] = x; }
 };
 
-template <int LANES, int COLS, bool WRAP8>
+// VAR selects which one-lane shifts use IMAD/IMAD.HI (fma pipe) instead of PRMT (alu pipe):
+//   bit 0: diagonal shift of the previous row; bit 1: score shift of gap step 1; bit 2: mask shift of gap step 1
+template <int LANES, int COLS, bool WRAP8, int VAR = 0>
 struct SwCore {
     static constexpr int R = COLS / 2;     // registers per row
     static constexpr int RL = LANES / 2;   // registers per chunk
@@ -117,6 +119,11 @@ struct SwCore {
                 uint32_t bonus = __vadd2(__vadd2(del_m & delb, cap_m & capb), base);
                 if (r == 0 && include_prefix) bonus = __vadd2(bonus, (uint32_t)p.prefix_bonus & 0xffffu);
                 if (WRAP8) bonus &= 0x00FF00FFu;
+                // Non-wrapping variant stores D = bonus - mismatch + (exact-case bonus where the haystack byte
+                // is not an uppercase letter): for a needle byte that is not an uppercase letter, "exact case"
+                // ⇔ match && !upper(hay) (a lowercase letter matches {c, C}; a non-letter matches only itself),
+                // so a matched cell's whole diagonal increment is D and the row needs no exact-case mask.
+                if (!WRAP8) bonus = __vadd2(__vadd2(bonus, p.k_neg_mis), ~upper & p.k_case);
                 Bs.set(r, bonus);
                 prev_lower = lower;
                 prev_delim = delim;
@@ -124,35 +131,57 @@ struct SwCore {
         }
         // ---- constants ----
         const uint32_t neg_mis = p.k_neg_mis;
-        const uint32_t ex_add = p.k_ex_add;       // exact-case match: +case -mismatch
         const uint32_t up_plain = p.k_up_plain;
         const uint32_t up_open = p.k_up_open;
+        (void)up_open;
         uint32_t H[R], M[R];
 #pragma unroll
-        for (int r = 0; r < R; r++) { H[r] = 0; M[r] = 0; }
+        for (int r = 0; r < R; r++) { H[r] = 0; M[r] = WRAP8 ? 0u : 0x00010001u; }  // row 0: no matches
 
+        // fma-pipe helpers.  The ALU pipe (LOP3 / PRMT / VIADD / VIADDMNMX) issues one warp instruction
+        // every two cycles per scheduler and the first version of this loop ran it at 82% with the FMA
+        // pipe idle (profiles/r01c).  Match masks are therefore kept as 0/1 per lane so that every
+        // "penalty = base - mask * gap_open" is one IMAD, and lane shifts use IMAD / IMAD.HI too.
+        const uint32_t gopx = (uint32_t)p.gap_open_x;
+        auto shl16 = [](uint32_t lo_src, uint32_t hi_src) {
+            // lanes: result.lo = lo_src.hi, result.hi = hi_src.lo   ( == __byte_perm(lo_src, hi_src, 0x5432) )
+            return hi_src * 0x10000u + __umulhi(lo_src, 0x10000u);
+        };
         for (int i = 0; i < p.n; i++) {
             const uint32_t om16 = p.om16[i], tg16 = p.tg16[i], c16 = p.c16[i];
             const bool folded = p.om[i] != 0;  // case-insensitive letter: exact-case mask differs from match mask
+            const bool upper_row = (uint32_t)(p.c[i] - 'A') <= 25u;  // exact case ⇔ match && upper(hay)
             // ---- diagonal + up, in place, high register first (H[r-1] must still hold row i-1) ----
 #pragma unroll
             for (int r = R - 1; r >= 0; r--) {
                 const uint32_t hv = h16s.get(r), Bv = Bs.get(r);
-                const uint32_t mmn = eqmask16((hv | om16) ^ tg16);
-                const uint32_t ex = folded ? eqmask16(hv ^ c16) : mmn;
-                const uint32_t prevs = r > 0 ? __byte_perm(H[r - 1], H[r], 0x5432) : __byte_perm(0u, H[0], 0x5432);
-                uint32_t diag;
                 if (!WRAP8) {
-                    const uint32_t delta = __vadd2(mmn & Bv, sel(ex, ex_add, neg_mis));
-                    diag = addmax_relu(prevs, delta, 0u);
+                    // nm: 0 where the haystack byte matches needle[i] (either case), else 1
+                    const uint32_t nm = __vminu2((hv | om16) ^ tg16, 0x00010001u);
+                    const uint32_t nmfull = nm * 0xFFFFu;
+                    const uint32_t prevs = (VAR & 1) ? (r > 0 ? shl16(H[r - 1], H[r]) : H[0] * 0x10000u)
+                                                    : (r > 0 ? __byte_perm(H[r - 1], H[r], 0x5432) : __byte_perm(0u, H[0], 0x5432));
+                    uint32_t Dv = Bv;
+                    if (upper_row) {  // rare: move the exact-case bonus from the non-upper to the upper haystack bytes
+                        const uint32_t t = __vadd2(hv, splat16(-'A')), d = __vadd2(hv, splat16(-('Z' + 1)));
+                        const uint32_t up = __byte_perm(d & ~t, 0, 0xBB99);
+                        Dv = __vadd2(Dv, sel(up, p.k_case, splat16(-p.case_bonus)));
+                    }
+                    const uint32_t diag = addmax_relu(prevs, sel(nmfull, neg_mis, Dv), 0u);
+                    const uint32_t upd = up_open + M[r] * gopx;                      // M[r] still row i-1
+                    H[r] = addmax_relu(H[r], upd, diag);
+                    M[r] = nm;
                 } else {
+                    const uint32_t mmn = eqmask16((hv | om16) ^ tg16);
+                    const uint32_t prevs = r > 0 ? __byte_perm(H[r - 1], H[r], 0x5432) : __byte_perm(0u, H[0], 0x5432);
+                    const uint32_t ex = folded ? eqmask16(hv ^ c16) : mmn;
                     uint32_t d = __vadd2(prevs, mmn & Bv) & 0x00FF00FFu;        // wrapping u8 add
                     d = addmax_relu(d, neg_mis, 0u);                             // saturating sub
-                    diag = __vadd2(d, ex & p.k_case) & 0x00FF00FFu;  // wrapping u8 add
+                    const uint32_t diag = __vadd2(d, ex & p.k_case) & 0x00FF00FFu;  // wrapping u8 add
+                    const uint32_t upd = sel(M[r], up_open, up_plain);               // M[r] still row i-1
+                    H[r] = addmax_relu(H[r], upd, diag);
+                    M[r] = mmn;
                 }
-                const uint32_t upd = sel(M[r], up_open, up_plain);               // M[r] still row i-1
-                H[r] = addmax_relu(H[r], upd, diag);
-                M[r] = mmn;
             }
             // ---- horizontal gap propagation, chunk by chunk (ascii_gap.rs gap_step!) ----
 #pragma unroll
@@ -165,7 +194,12 @@ struct SwCore {
 #pragma unroll
                     for (int r = hi - 1; r >= lo; r--) {
                         uint32_t sh, smm;
-                        if (s == 1) {
+                        if (s == 1 && !WRAP8) {
+                            if (VAR & 2) sh = r == 0 ? H[0] * 0x10000u : shl16(H[r - 1], H[r]);
+                            else sh = r == 0 ? __byte_perm(0u, H[0], 0x5432) : __byte_perm(H[r - 1], H[r], 0x5432);
+                            if (VAR & 4) smm = r == 0 ? M[0] * 0x10000u : shl16(M[r - 1], M[r]);
+                            else smm = r == 0 ? __byte_perm(0u, M[0], 0x5432) : __byte_perm(M[r - 1], M[r], 0x5432);
+                        } else if (s == 1) {
                             if (r == 0) { sh = __byte_perm(0u, H[0], 0x5432); smm = __byte_perm(0u, M[0], 0x5432); }
                             else { sh = __byte_perm(H[r - 1], H[r], 0x5432); smm = __byte_perm(M[r - 1], M[r], 0x5432); }
                         } else {
@@ -174,7 +208,8 @@ struct SwCore {
                             sh = H[src];
                             smm = M[src];
                         }
-                        H[r] = addmax_relu(sh, sel(smm, penB, penA), H[r]);
+                        const uint32_t pen = WRAP8 ? sel(smm, penB, penA) : penB + smm * gopx;
+                        H[r] = addmax_relu(sh, pen, H[r]);
                     }
                 }
             }
@@ -258,8 +293,8 @@ __device__ __forceinline__ void emit_match(const FrzSurvivor& rec, uint32_t scor
     out[pos] = m;
 }
 
-template <int LANES, int COLS, bool WRAP8, int MINB>
-__global__ void __launch_bounds__(kSwThreads, MINB) k_sw(const FrzCorpusView cv, const __grid_constant__ FrzPatternDev pat,
+template <int LANES, int COLS, bool WRAP8, int VAR>
+__global__ void __launch_bounds__(kSwThreads) k_sw(const FrzCorpusView cv, const __grid_constant__ FrzPatternDev pat,
                                                    const FrzSurvivor* __restrict__ surv, unsigned long long surv_cap, int cls,
                                                    const FrzRankView rv, FrzCounters* __restrict__ ctr,
                                                    uint32_t index_offset, int reversed, FrzMatchDev* __restrict__ out) {
@@ -275,7 +310,7 @@ __global__ void __launch_bounds__(kSwThreads, MINB) k_sw(const FrzCorpusView cv,
         const int W = (int)(end - start);
         uint32_t hw[COLS / 4];
         load_window<COLS>(cv, rec.tile, slot, start, W, hw);
-        uint32_t score = SwCore<LANES, COLS, WRAP8>::run(hw, W, pat, start == 0, sw_smem);
+        uint32_t score = SwCore<LANES, COLS, WRAP8, VAR>::run(hw, W, pat, start == 0, sw_smem);
         bool exact = start == 0 && full_end && window_equals_needle(hw, W, pat);
         if (exact) score = (score + pat.exact_bonus) & 0xffffu;
         emit_match(rec, score, exact, index_offset, reversed != 0, rv, ctr, out);
@@ -466,33 +501,30 @@ frz_status launch_sw_variant(const FrzCorpusView& cv, const FrzPatternDev& pat, 
     if (smem > 48 * 1024) {
         static bool attr_set = false;
         if (!attr_set) {
-            FRZ_CUDA_TRY(cudaFuncSetAttribute(k_sw<LANES, COLS, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            FRZ_CUDA_TRY(cudaFuncSetAttribute(k_sw<LANES, COLS, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            FRZ_CUDA_TRY(cudaFuncSetAttribute(k_sw<LANES, COLS, true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            FRZ_CUDA_TRY(cudaFuncSetAttribute(k_sw<LANES, COLS, false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             attr_set = true;
         }
     }
     if (LANES == 64 && COLS == 64 && !pat.wrap8) {
-        // occupancy experiment knob (register cap per thread): FRZ_SW_MINB = 2 (255 regs) | 3 (168) | 4 (128)
-        static int minb = -1;
-        if (minb < 0) { const char* e = getenv("FRZ_SW_MINB"); minb = e ? atoi(e) : 2; }
-        if (minb == 3) {
-            k_sw<64, 64, false, 3><<<sm_count() * 3, kSwThreads, 0, stream>>>(cv, pat, ws.survivors[cls], ws.survivor_cap, cls, rank_view(ws),
-                                                                          ws.counters, index_offset, reversed ? 1 : 0, d_out);
-            FRZ_CUDA_TRY(cudaGetLastError());
-            return FRZ_OK;
+        // pipe-balance experiment knob: FRZ_SW_VARIANT = shift placement bits (see SwCore)
+        static int var = -1;
+        if (var < 0) { const char* e = getenv("FRZ_SW_VARIANT"); var = e ? atoi(e) : 0; }
+#define FRZ_SW_VAR_CASE(V)                                                                                              \
+        if (var == V) {                                                                                                 \
+            k_sw<64, 64, false, V><<<blocks, kSwThreads, 0, stream>>>(cv, pat, ws.survivors[cls], ws.survivor_cap, cls, rank_view(ws), \
+                                                                  ws.counters, index_offset, reversed ? 1 : 0, d_out);  \
+            FRZ_CUDA_TRY(cudaGetLastError());                                                                           \
+            return FRZ_OK;                                                                                              \
         }
-        if (minb == 4) {
-            k_sw<64, 64, false, 4><<<sm_count() * 4, kSwThreads, 0, stream>>>(cv, pat, ws.survivors[cls], ws.survivor_cap, cls, rank_view(ws),
-                                                                          ws.counters, index_offset, reversed ? 1 : 0, d_out);
-            FRZ_CUDA_TRY(cudaGetLastError());
-            return FRZ_OK;
-        }
+        FRZ_SW_VAR_CASE(1) FRZ_SW_VAR_CASE(5) FRZ_SW_VAR_CASE(3) FRZ_SW_VAR_CASE(4) FRZ_SW_VAR_CASE(6) FRZ_SW_VAR_CASE(7)
+#undef FRZ_SW_VAR_CASE
     }
     if (pat.wrap8)
-        k_sw<LANES, COLS, true, 1><<<blocks, kSwThreads, smem, stream>>>(cv, pat, ws.survivors[cls], ws.survivor_cap, cls, rank_view(ws), ws.counters,
+        k_sw<LANES, COLS, true, 0><<<blocks, kSwThreads, smem, stream>>>(cv, pat, ws.survivors[cls], ws.survivor_cap, cls, rank_view(ws), ws.counters,
                                                                    index_offset, reversed ? 1 : 0, d_out);
     else
-        k_sw<LANES, COLS, false, 1><<<blocks, kSwThreads, smem, stream>>>(cv, pat, ws.survivors[cls], ws.survivor_cap, cls, rank_view(ws), ws.counters,
+        k_sw<LANES, COLS, false, 0><<<blocks, kSwThreads, smem, stream>>>(cv, pat, ws.survivors[cls], ws.survivor_cap, cls, rank_view(ws), ws.counters,
                                                                     index_offset, reversed ? 1 : 0, d_out);
     FRZ_CUDA_TRY(cudaGetLastError());
     return FRZ_OK;

@@ -1,12 +1,8 @@
 #!/bin/bash
-# quick iteration run on the GPU box: parity tests, then short bench lines for the tuning knobs
-TAG=${1:-q}
+# quick iteration run on the GPU box: parity tests, then a short bench line with stage timings
 mkdir -p gpurun_out
 python -m pytest tests -m gpu -x -q 2>&1 | tail -15
-for mb in 2 3 4; do
-  echo "== FRZ_SW_MINB=$mb"
-  FRZ_SW_MINB=$mb python bench.py --steps 10 --warmup 3 --no-cpu-baseline --e2e-steps 2 2>&1 | tail -1 | python -c "
+python bench.py --steps 10 --warmup 3 --no-cpu-baseline --e2e-steps 2 2>&1 | tail -1 | python -c "
 import json,sys
 d=json.loads(sys.stdin.read())
 print(json.dumps({'value':d['value'],'ms_per_step':d['ms_per_step'],'stages':d['roofline']['stage_ms_per_step'],'frac':d['roofline']['frac'],'e2e':d['e2e'],'clocks':d['clocks'],'parity':d['parity']}))"
-done
