@@ -36,6 +36,34 @@ def merge_runs_host(runs: List[np.ndarray], sort: SortStrategy) -> np.ndarray:
     return cat[order]
 
 
+def all_gather_runs(run, count: int, group=None):
+    """The collective step, backend-agnostic (NCCL on device tensors, gloo on CPU tensors): one all-gather of the
+    counts and ONE all-gather of the runs padded to the longest.  `run` is a 1-D int64 tensor of 8-byte match records.
+    Returns (gathered [world * stride], counts list, stride)."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    cnt = torch.tensor([count], dtype=torch.int64, device=run.device)
+    counts = torch.zeros(world, dtype=torch.int64, device=run.device)
+    dist.all_gather_into_tensor(counts, cnt, group=group)
+    counts_h = [int(c) for c in counts.cpu().tolist()]
+    stride = max(max(counts_h), 1)
+    send = run[:stride].contiguous() if run.numel() >= stride else torch.nn.functional.pad(run, (0, stride - run.numel()))
+    gathered = torch.empty(world * stride, dtype=torch.int64, device=run.device)
+    dist.all_gather_into_tensor(gathered, send, group=group)
+    return gathered, counts_h, stride
+
+
+def match_list_parallel_host(run: np.ndarray, sort: SortStrategy, group=None) -> np.ndarray:
+    """Host/gloo form of the gather + merge (tests; the run producer is injected by the caller)."""
+    import torch
+    t = torch.from_numpy(np.ascontiguousarray(run).view(np.int64).copy())
+    gathered, counts, stride = all_gather_runs(t, len(run), group)
+    g = gathered.numpy().view(MATCH_DTYPE)
+    runs = [g[r * stride: r * stride + counts[r]] for r in range(len(counts))]
+    return merge_runs_host(runs, sort)
+
+
 def match_list_parallel(matcher: Matcher, shard: Corpus, index_offset: int, group=None, device: Optional[int] = None):
     """Runs this rank's shard, all-gathers the runs over NCCL and merges them on every rank.
     Returns (merged matches as a uint64-viewable torch tensor on the device, total count)."""
@@ -53,16 +81,10 @@ def match_list_parallel(matcher: Matcher, shard: Corpus, index_offset: int, grou
     if world == 1:
         n = int(count.item())
         return run[:n], n
-    # one collective for the counts (8 bytes per rank) …
-    counts = torch.zeros(world, dtype=torch.int64, device=dev)
-    dist.all_gather_into_tensor(counts, count, group=group)
-    counts_h = counts.cpu().numpy().astype(np.uint64)
-    stride = int(counts_h.max()) if counts_h.size else 0
-    stride = max(stride, 1)
-    # … and ONE all-gather of the per-shard (score, index) buffers, padded to the longest run
-    gathered = torch.empty(world * stride, dtype=torch.int64, device=dev)
-    dist.all_gather_into_tensor(gathered, run[:stride].contiguous() if run.numel() >= stride else
-                                torch.nn.functional.pad(run, (0, stride - run.numel())), group=group)
+    # one collective for the counts (8 bytes per rank) and ONE all-gather of the per-shard (score, index)
+    # buffers, padded to the longest run
+    gathered, counts_l, stride = all_gather_runs(run, int(count.item()), group)
+    counts_h = np.asarray(counts_l, dtype=np.uint64)
     total = int(counts_h.sum())
     merged = torch.empty(max(total, 1), dtype=torch.int64, device=dev)
     ch = np.ascontiguousarray(counts_h)
