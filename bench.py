@@ -9,7 +9,9 @@ shape (needle 'deadbeef', 10M haystacks, len <= 64, mean 48, max_typos = 1) per 
 each rank holds its own 10M-item shard; for N > 1 a step ends with the NCCL all-gather of the
 per-shard runs and the merge — Matcher::match_list_parallel).
   value : whole-job haystacks/s with the packed corpus already resident in HBM when the timed
-          region starts; the match list is copied to pinned host memory inside the timed region.
+          region starts and the ordered match list left in HBM (device in, device out; the same
+          definition at every N).  `value_host_out` (N = 1) additionally copies the list to pinned
+          host memory inside the timed region.
   e2e   : the same metric through frz_match_list_host — host Arrow buffers in pinned memory in,
           host matches out; pack + H2D + kernels + D2H all inside the timed region.
 Prints ONE JSON line on rank 0.
@@ -179,14 +181,16 @@ def run_ours(args):
     info = matcher.backend_info()
     index_offset = rank * n
 
+    runner = parallel.ShardRunner(matcher, corpus, index_offset, device=local)
+
     def step():
-        if world == 1:
-            res = matcher.match_list_array(corpus, device=local, out=out_h)
-            return len(res)
-        merged, total = parallel.match_list_parallel(matcher, corpus, index_offset, device=local)
-        if rank == 0:
-            out_pin[:total].copy_(merged, non_blocking=False)
+        # Matcher::match_list (N = 1) / match_list_parallel (N > 1): local pipeline, one all-gather of the
+        # per-shard runs, device merge; the ordered list stays in HBM
+        merged, total = runner.step()
         return total
+
+    def step_host_out():
+        return len(matcher.match_list_array(corpus, device=local, out=out_h))
 
     def barrier():
         if world > 1:
@@ -195,6 +199,8 @@ def run_ours(args):
 
     for _ in range(max(args.warmup, 3)):
         n_matches = step()
+    if world == 1:
+        n_matches = step_host_out()
 
     # ---- parity in the same run (outside the timed region): a prefix sample against the oracle
     parity = None
@@ -226,11 +232,27 @@ def run_ours(args):
     ev1.record()
     barrier()
     clocks = sampler.stop()
+    if world == 1:
+        n_matches = int(runner.count.item())
     ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms = float(ms.item())
     value = n * world * args.steps / (ms / 1e3)
+
+    # ---- N = 1 only: the same call with the match list landing in pinned host memory
+    host_out = None
+    if world == 1:
+        h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(dev)
+        h0.record()
+        for _ in range(args.steps):
+            step_host_out()
+        h1.record()
+        torch.cuda.synchronize(dev)
+        hms = h0.elapsed_time(h1)
+        host_out = {"value": n * args.steps / (hms / 1e3), "unit": "haystacks/s", "ms_per_step": hms / args.steps,
+                    "d2h_bytes_per_step": int(n_matches * 8 + 64)}
 
     # ---- timed region: end to end (host buffers in, host matches out), single-GPU API per rank
     e2e_steps = args.e2e_steps or min(args.steps, 5)
@@ -285,6 +307,7 @@ def run_ours(args):
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": "haystacks/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "steps": e2e_steps, "ms_per_step": e_ms / e2e_steps},
+                "value_host_out": host_out,
                 "gpu_launches": int(launches),
                 "roofline": roofline, "cpu_baseline": cpu, "parity": parity}
         print(json.dumps(line))

@@ -87,7 +87,9 @@ def lib():
     L.frz_match_list_into.argtypes = [vp, vp, u32, vp, u64, C.POINTER(u64)]
     L.frz_match_list_host.argtypes = [vp, vp, vp, u64, C.c_int, vp, u64, C.POINTER(u64)]
     L.frz_match_shard_device.argtypes = [vp, vp, u32, vp, u64, vp, vp]
-    L.frz_merge_runs_device.argtypes = [vp, u64, vp, C.c_int, C.c_uint8, vp, C.c_int, vp]
+    L.frz_merge_runs_device.argtypes = [vp, u64, vp, C.c_int, C.c_uint8, u32, vp, C.c_int, vp]
+    L.frz_matcher_score_bound.restype = u32
+    L.frz_matcher_score_bound.argtypes = [vp]
     L.frz_radix_sort_matches.argtypes = [vp, u64, C.c_int]
     _lib = L
     return L
@@ -241,6 +243,9 @@ class Matcher:
         lanes, bits, pf, lit = C.c_int(), C.c_int(), C.c_int(), C.c_int()
         _check(lib().frz_matcher_backend_info(self._h, i, C.byref(lanes), C.byref(bits), C.byref(pf), C.byref(lit)))
         return {"lanes": lanes.value, "score_bits": bits.value, "prefilter_lanes": pf.value, "literal": bool(lit.value)}
+
+    def score_bound(self) -> int:
+        return lib().frz_matcher_score_bound(self._h)
 
     def num_patterns(self) -> int:
         return lib().frz_matcher_num_patterns(self._h)

@@ -39,6 +39,10 @@ struct FrzCorpusStorage {
     uint64_t total_units = 0;
     uint64_t total_bytes = 0;
     int device = 0;
+    // capacities (grow-only reuse by the end-to-end path: no cudaMalloc/cudaFree per call)
+    uint32_t cap_tiles = 0;
+    uint64_t cap_units = 0;
+    uint64_t* scratch_tile_units = nullptr;  // [cap_tiles] + 2 words (total, error)
 
     FrzCorpusView view() const {
         FrzCorpusView v;
@@ -52,8 +56,9 @@ struct FrzCorpusStorage {
         return v;
     }
     void release() {
-        cudaFree(data); cudaFree(tile_base); cudaFree(groups); cudaFree(slot_meta); cudaFree(slot_of);
-        data = nullptr; tile_base = nullptr; groups = nullptr; slot_meta = nullptr; slot_of = nullptr;
+        cudaFree(data); cudaFree(tile_base); cudaFree(groups); cudaFree(slot_meta); cudaFree(slot_of); cudaFree(scratch_tile_units);
+        data = nullptr; tile_base = nullptr; groups = nullptr; slot_meta = nullptr; slot_of = nullptr; scratch_tile_units = nullptr;
+        cap_tiles = 0; cap_units = 0;
     }
 };
 

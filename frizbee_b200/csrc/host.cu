@@ -529,13 +529,25 @@ struct frz_matcher {
     std::vector<OwnedPattern> raw;
     std::vector<Compiled> compiled;   // build_patterns: patterns with non-empty needles
     FrzWorkspace ws;
+    // end-to-end (host in / host out) staging arena, grow-only: raw Arrow buffers + a reusable packed corpus
+    uint8_t* e2e_bytes = nullptr;
+    uint64_t e2e_bytes_cap = 0;
+    uint64_t* e2e_offsets = nullptr;
+    uint64_t e2e_offsets_cap = 0;
+    frz_corpus e2e_corpus;
     FrzMatchDev* multi_a = nullptr;   // multi-pattern candidate ping-pong
     FrzMatchDev* multi_b = nullptr;
     uint64_t multi_cap = 0;
     float last_ms[4] = {0, 0, 0, 0};
     uint64_t last_launches = 0;
+    bool timings_pending = false;
     ~frz_matcher() {
         if (ws.device >= 0) { cudaSetDevice(ws.device); cudaFree(multi_a); cudaFree(multi_b); }
+        if (e2e_bytes || e2e_offsets || e2e_corpus.st.data) {
+            cudaSetDevice(e2e_corpus.st.device);
+            cudaFree(e2e_bytes); cudaFree(e2e_offsets);
+            e2e_corpus.st.release();
+        }
         ws.release();
     }
 };
@@ -616,8 +628,18 @@ extern "C" frz_status frz_matcher_backend_info(const frz_matcher* m, size_t i, i
     if (is_literal) *is_literal = c.literal;
     return FRZ_OK;
 }
-extern "C" frz_status frz_matcher_last_timings(const frz_matcher* m, float* ms4, uint64_t* launches) {
+void collect_timings(frz_matcher* m, const FrzLaunchStats& st);
+extern "C" frz_status frz_matcher_last_timings(const frz_matcher* mc, float* ms4, uint64_t* launches) {
+    frz_matcher* m = const_cast<frz_matcher*>(mc);
     if (!m) return frz_fail(FRZ_ERR_INVALID_ARG, "null matcher");
+    if (m->timings_pending && m->ws.device >= 0) {
+        cudaSetDevice(m->ws.device);
+        cudaEventSynchronize(m->ws.ev[3]);
+        FrzLaunchStats st;
+        st.launches = m->last_launches;
+        collect_timings(m, st);
+        m->timings_pending = false;
+    }
     if (ms4) memcpy(ms4, m->last_ms, sizeof m->last_ms);
     if (launches) *launches = m->last_launches;
     return FRZ_OK;
@@ -807,7 +829,8 @@ int grid_for(uint64_t n, int block) {
 // match_list_into over all compiled patterns → index-ordered device list; returns pointer + leaves the
 // count in ws.counters->total.  `final_reversed` asks for the list in descending index order.
 frz_status match_into_device(frz_matcher* m, const FrzCorpusStorage& cs, uint32_t index_offset, bool final_reversed,
-                             FrzMatchDev** d_result, uint32_t* score_bound, cudaStream_t stream, FrzLaunchStats* st) {
+                             FrzMatchDev** d_result, uint32_t* score_bound, cudaStream_t stream, FrzLaunchStats* st,
+                             FrzMatchDev* prefer_out = nullptr) {
     FrzWorkspace& ws = m->ws;
     if ((uint64_t)cs.n + index_offset > 0xFFFFFFFFull)
         return frz_fail(FRZ_ERR_TOO_MANY_ITEMS, "too many items in haystack, will overflow the u32 index: %llu > %u (index offset: %u)",
@@ -829,8 +852,9 @@ frz_status match_into_device(frz_matcher* m, const FrzCorpusStorage& cs, uint32_
     }
     if (pats.size() == 1 && !pats[0].negated) {  // CompiledPatterns::Single
         FRZ_TRY(ensure_workspace(m, cs, initial_survivor_cap(cs, pats[0].dev)));
-        FRZ_TRY(run_pattern(m, cs, pats[0], nullptr, index_offset, final_reversed, ws.matches_a, stream, st, true));
-        *d_result = ws.matches_a;
+        FrzMatchDev* dst = prefer_out ? prefer_out : ws.matches_a;
+        FRZ_TRY(run_pattern(m, cs, pats[0], nullptr, index_offset, final_reversed, dst, stream, st, true));
+        *d_result = dst;
         *score_bound = pats[0].score_bound;
         return FRZ_OK;
     }
@@ -924,17 +948,25 @@ frz_status match_into_device(frz_matcher* m, const FrzCorpusStorage& cs, uint32_
 }
 
 // Matcher::match_list on device: into (+reverse) (+stable score sort).  Result pointer + device count.
+__global__ void k_copy_n(const FrzMatchDev* __restrict__ in, FrzMatchDev* __restrict__ out, const unsigned long long* n_ptr) {
+    const unsigned long long n = *n_ptr;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x)
+        out[i] = in[i];
+}
+
+// `final_out` (optional, device, >= corpus length): where the final list must land
 frz_status match_list_device(frz_matcher* m, const FrzCorpusStorage& cs, uint32_t index_offset, uint8_t sort,
-                             FrzMatchDev** d_result, cudaStream_t stream, FrzLaunchStats* st) {
+                             FrzMatchDev** d_result, cudaStream_t stream, FrzLaunchStats* st, FrzMatchDev* final_out = nullptr) {
     FrzWorkspace& ws = m->ws;
     const bool reversed = sort == FRZ_SORT_INDEX_DESC || sort == FRZ_SORT_SCORE_THEN_INDEX_DESC;
     const bool by_score = sort == FRZ_SORT_SCORE_THEN_INDEX_ASC || sort == FRZ_SORT_SCORE_THEN_INDEX_DESC;
+    const bool will_sort = by_score && !m->compiled.empty();
     FrzMatchDev* d_list = nullptr;
     uint32_t bound = 0;
-    FRZ_TRY(match_into_device(m, cs, index_offset, reversed, &d_list, &bound, stream, st));
+    FRZ_TRY(match_into_device(m, cs, index_offset, reversed, &d_list, &bound, stream, st, will_sort ? nullptr : final_out));
     // `!self.patterns.is_empty() && sort.is_by_score()` (src/matcher/mod.rs:218)
-    if (by_score && !m->compiled.empty()) {
-        FrzMatchDev* other = d_list == ws.matches_a ? ws.matches_b : ws.matches_a;
+    if (will_sort) {
+        FrzMatchDev* other = final_out ? final_out : (d_list == ws.matches_a ? ws.matches_b : ws.matches_a);
         FrzMatchDev* tmp = m->multi_a ? m->multi_a : nullptr;
         if (bound >= 1024 && !tmp) {
             if (m->multi_cap < cs.n) {
@@ -946,12 +978,17 @@ frz_status match_list_device(frz_matcher* m, const FrzCorpusStorage& cs, uint32_
         }
         FRZ_TRY(frz_launch_sort_by_score_dev(d_list, tmp, other, &ws.counters->total, bound, ws, stream, st));
         d_list = other;
+    } else if (final_out && d_list != final_out) {
+        k_copy_n<<<grid_for(cs.n, 256), 256, 0, stream>>>(d_list, final_out, &ws.counters->total);
+        st->launches++;
+        d_list = final_out;
     }
     cudaEventRecord(ws.ev[3], stream);
     *d_result = d_list;
     return FRZ_OK;
 }
 
+}  // namespace
 void collect_timings(frz_matcher* m, const FrzLaunchStats& st) {
     FrzWorkspace& ws = m->ws;
     float a = 0, b = 0, c = 0, t = 0;
@@ -963,6 +1000,7 @@ void collect_timings(frz_matcher* m, const FrzLaunchStats& st) {
     m->last_ms[0] = a; m->last_ms[1] = b; m->last_ms[2] = c; m->last_ms[3] = t;
     m->last_launches = st.launches;
 }
+namespace {
 
 frz_status copy_out(frz_matcher* m, FrzMatchDev* d_list, frz_match* out, uint64_t cap, uint64_t* n_out, cudaStream_t stream) {
     FRZ_TRY(read_counters(m, stream));
@@ -1019,11 +1057,38 @@ extern "C" frz_status frz_match_list_into(frz_matcher* m, const frz_corpus* corp
 
 extern "C" frz_status frz_match_list_host(frz_matcher* m, const uint8_t* bytes, const uint64_t* offsets, uint64_t n, int device,
                                           frz_match* out, uint64_t cap, uint64_t* n_out) {
-    frz_corpus* c = nullptr;
-    FRZ_TRY(frz_corpus_create(bytes, offsets, n, device, &c));
-    frz_status s = frz_match_list(m, c, out, cap, n_out);
-    frz_corpus_destroy(c);
-    return s;
+    if (!m || !offsets) return frz_fail(FRZ_ERR_INVALID_ARG, "null argument");
+    if (n > 0xFFFFFFFFull) return frz_fail(FRZ_ERR_TOO_MANY_ITEMS, "too many items in haystack: %llu", (unsigned long long)n);
+    if (offsets[0] != 0) return frz_fail(FRZ_ERR_INVALID_ARG, "offsets[0] must be 0");
+    FRZ_TRY(ensure_device(device));
+    cudaStream_t stream = nullptr;
+    const uint64_t total = offsets[n];
+    frz_corpus& c = m->e2e_corpus;
+    if (c.st.device != device && (m->e2e_bytes || c.st.data)) {  // arena lives on another device: drop it
+        cudaSetDevice(c.st.device);
+        cudaFree(m->e2e_bytes); cudaFree(m->e2e_offsets);
+        m->e2e_bytes = nullptr; m->e2e_offsets = nullptr; m->e2e_bytes_cap = m->e2e_offsets_cap = 0;
+        c.st.release();
+        FRZ_CUDA_TRY(cudaSetDevice(device));
+    }
+    c.st.device = device;
+    if (m->e2e_bytes_cap < total + 16) {
+        cudaFree(m->e2e_bytes); m->e2e_bytes = nullptr; m->e2e_bytes_cap = 0;
+        const uint64_t want = total + total / 16 + 4096;
+        FRZ_CUDA_TRY(cudaMalloc(&m->e2e_bytes, want));
+        m->e2e_bytes_cap = want;
+    }
+    if (m->e2e_offsets_cap < n + 1) {
+        cudaFree(m->e2e_offsets); m->e2e_offsets = nullptr; m->e2e_offsets_cap = 0;
+        const uint64_t want = n + n / 16 + 1024;
+        FRZ_CUDA_TRY(cudaMalloc(&m->e2e_offsets, want * sizeof(uint64_t)));
+        m->e2e_offsets_cap = want;
+    }
+    // H2D of the caller's Arrow buffers (fast path: pinned host memory), pack, match, D2H of the matches
+    if (total) FRZ_CUDA_TRY(cudaMemcpyAsync(m->e2e_bytes, bytes, total, cudaMemcpyHostToDevice, stream));
+    FRZ_CUDA_TRY(cudaMemcpyAsync(m->e2e_offsets, offsets, (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, stream));
+    FRZ_TRY(frz_pack_corpus_device(m->e2e_bytes, m->e2e_offsets, n, total, stream, &c.st));
+    return frz_match_list(m, &c, out, cap, n_out);
 }
 
 extern "C" frz_status frz_match_shard_device(frz_matcher* m, const frz_corpus* shard, uint32_t index_offset, frz_match* d_out,
@@ -1035,12 +1100,12 @@ extern "C" frz_status frz_match_shard_device(frz_matcher* m, const frz_corpus* s
     FrzMatchDev* d_list = nullptr;
     // asynchronous entry point: nobody reads the overflow flag back, so size the lists for the worst case
     FRZ_TRY(ensure_workspace(m, shard->st, std::max<uint64_t>(shard->st.n, 1)));
-    FRZ_TRY(match_list_device(m, shard->st, index_offset, m->config.sort, &d_list, stream, &st));
     // the run can never exceed the shard size; the caller sizes d_out as >= shard length
     if (cap < shard->st.n) return frz_fail(FRZ_ERR_CAPACITY, "d_out must hold the whole shard (%llu)", (unsigned long long)shard->st.n);
-    FRZ_CUDA_TRY(cudaMemcpyAsync(d_out, d_list, shard->st.n * sizeof(frz_match), cudaMemcpyDeviceToDevice, stream));
+    FRZ_TRY(match_list_device(m, shard->st, index_offset, m->config.sort, &d_list, stream, &st, reinterpret_cast<FrzMatchDev*>(d_out)));
     FRZ_CUDA_TRY(cudaMemcpyAsync(d_count, &m->ws.counters->total, sizeof(uint64_t), cudaMemcpyDeviceToDevice, stream));
     m->last_launches = st.launches;
+    m->timings_pending = true;   // events were recorded; frz_matcher_last_timings reads them once the stream is idle
     return FRZ_OK;
 }
 
@@ -1060,13 +1125,21 @@ __global__ void k_gather_runs(const FrzMatchDev* runs, uint64_t stride, const ui
 // k_merge_matches_by (src/k_merge.rs:90-131).  Runs are index-range shards in rank order, each already
 // ordered per `sort`; concatenating them in (reverse) rank order and stable-sorting by score yields
 // exactly the reference's k-way merge (ties resolve by index because the shards are index-ordered).
+extern "C" uint32_t frz_matcher_score_bound(const frz_matcher* m) {
+    if (!m) return 0;
+    uint64_t b = 0;
+    for (const auto& c : m->compiled) if (!c.negated) b += c.score_bound;
+    return (uint32_t)std::min<uint64_t>(b, 0xFFFF);
+}
+
 extern "C" frz_status frz_merge_runs_device(const frz_match* d_runs, uint64_t run_stride, const uint64_t* run_counts_host,
-                                            int n_runs, uint8_t sort, frz_match* d_out, int device, void* stream_) {
+                                            int n_runs, uint8_t sort, uint32_t score_bound_in, frz_match* d_out, int device, void* stream_) {
     if (!d_runs || !run_counts_host || !d_out || n_runs <= 0 || n_runs > 64) return frz_fail(FRZ_ERR_INVALID_ARG, "bad argument");
     FRZ_TRY(ensure_device(device));
     cudaStream_t stream = (cudaStream_t)stream_;
     const bool reversed = sort == FRZ_SORT_INDEX_DESC || sort == FRZ_SORT_SCORE_THEN_INDEX_DESC;
     const bool by_score = sort == FRZ_SORT_SCORE_THEN_INDEX_ASC || sort == FRZ_SORT_SCORE_THEN_INDEX_DESC;
+    const uint32_t score_bound = score_bound_in ? score_bound_in : 0xFFFF;
     uint64_t h[2 * 64 + 1];
     uint64_t total = 0;
     for (int r = 0; r < n_runs; r++) {
@@ -1076,28 +1149,38 @@ extern "C" frz_status frz_merge_runs_device(const frz_match* d_runs, uint64_t ru
         total += run_counts_host[src_run];
     }
     h[128] = total;
-    uint64_t* d_meta = nullptr;
-    FrzMatchDev* d_cat = nullptr;
-    FrzMatchDev* d_tmp = nullptr;
-    FrzWorkspace ws;  // only the sort scratch is used
-    frz_status s = [&]() -> frz_status {
-        FRZ_CUDA_TRY(cudaMalloc(&d_meta, sizeof h));
-        FRZ_CUDA_TRY(cudaMemcpyAsync(d_meta, h, sizeof h, cudaMemcpyHostToDevice, stream));
-        FrzMatchDev* dst = by_score ? nullptr : reinterpret_cast<FrzMatchDev*>(d_out);
-        if (by_score) { FRZ_CUDA_TRY(cudaMalloc(&d_cat, std::max<uint64_t>(total, 1) * sizeof(FrzMatchDev))); dst = d_cat; }
-        k_gather_runs<<<grid_for(total / std::max(n_runs, 1) + 1, 256), 256, 0, stream>>>(
-            reinterpret_cast<const FrzMatchDev*>(d_runs), run_stride, d_meta, d_meta + 64, n_runs, reversed ? 1 : 0, dst);
-        if (by_score) {
-            FRZ_CUDA_TRY(cudaMalloc(&ws.sort_hist, frz_sort_hist_words() * sizeof(uint32_t)));
-            FRZ_CUDA_TRY(cudaMalloc(&d_tmp, std::max<uint64_t>(total, 1) * sizeof(FrzMatchDev)));
-            FRZ_TRY(frz_launch_sort_by_score_dev(d_cat, d_tmp, reinterpret_cast<FrzMatchDev*>(d_out),
-                                                 reinterpret_cast<const unsigned long long*>(d_meta + 128), 0xFFFF, ws, stream, nullptr));
-        }
-        FRZ_CUDA_TRY(cudaStreamSynchronize(stream));
-        return FRZ_OK;
-    }();
-    cudaFree(d_meta); cudaFree(d_cat); cudaFree(d_tmp); cudaFree(ws.sort_hist);
-    return s;
+    // grow-only per-device scratch (no allocation on the steady-state path)
+    struct MergeScratch { uint64_t* meta = nullptr; uint64_t* h_meta = nullptr; FrzMatchDev* cat = nullptr; FrzMatchDev* tmp = nullptr;
+                          uint32_t* hist = nullptr; uint64_t cap = 0; };
+    static MergeScratch scratch[64];
+    if (device >= 64) return frz_fail(FRZ_ERR_INVALID_ARG, "device index too large");
+    MergeScratch& ms = scratch[device];
+    if (!ms.meta) {
+        FRZ_CUDA_TRY(cudaMalloc(&ms.meta, sizeof h));
+        FRZ_CUDA_TRY(cudaMallocHost(&ms.h_meta, sizeof h));
+        FRZ_CUDA_TRY(cudaMalloc(&ms.hist, frz_sort_hist_words() * sizeof(uint32_t)));
+    }
+    if (ms.cap < total) {
+        cudaFree(ms.cat); cudaFree(ms.tmp); ms.cat = ms.tmp = nullptr; ms.cap = 0;
+        const uint64_t want = total + total / 4 + 1024;
+        FRZ_CUDA_TRY(cudaMalloc(&ms.cat, want * sizeof(FrzMatchDev)));
+        FRZ_CUDA_TRY(cudaMalloc(&ms.tmp, want * sizeof(FrzMatchDev)));
+        ms.cap = want;
+    }
+    // (max_score_hint in the top 16 bits of `sort` is not part of the ABI; the bound is conservative)
+    memcpy(ms.h_meta, h, sizeof h);
+    FRZ_CUDA_TRY(cudaMemcpyAsync(ms.meta, ms.h_meta, sizeof h, cudaMemcpyHostToDevice, stream));
+    FrzMatchDev* dst = by_score ? ms.cat : reinterpret_cast<FrzMatchDev*>(d_out);
+    k_gather_runs<<<grid_for(total / std::max(n_runs, 1) + 1, 256), 256, 0, stream>>>(
+        reinterpret_cast<const FrzMatchDev*>(d_runs), run_stride, ms.meta, ms.meta + 64, n_runs, reversed ? 1 : 0, dst);
+    if (by_score) {
+        FrzWorkspace ws;  // only the sort scratch is used
+        ws.sort_hist = ms.hist;
+        FRZ_TRY(frz_launch_sort_by_score_dev(ms.cat, ms.tmp, reinterpret_cast<FrzMatchDev*>(d_out),
+                                             reinterpret_cast<const unsigned long long*>(ms.meta + 128), score_bound, ws, stream, nullptr));
+    }
+    FRZ_CUDA_TRY(cudaGetLastError());
+    return FRZ_OK;  // asynchronous on `stream`
 }
 
 extern "C" frz_status frz_radix_sort_matches(frz_match* matches, uint64_t n, int device) {

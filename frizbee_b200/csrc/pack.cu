@@ -194,16 +194,20 @@ frz_status frz_pack_corpus_device(const uint8_t* d_bytes, const uint64_t* d_offs
         return FRZ_OK;
     }
     size_t slots = (size_t)n_tiles * FRZ_TILE;
-    FRZ_CUDA_TRY(cudaMalloc(&out->slot_meta, slots * sizeof(uint32_t)));
-    FRZ_CUDA_TRY(cudaMalloc(&out->slot_of, slots * sizeof(uint16_t)));
-    FRZ_CUDA_TRY(cudaMalloc(&out->groups, (size_t)n_tiles * FRZ_GROUPS_PER_TILE * sizeof(FrzGroupDesc)));
-    FRZ_CUDA_TRY(cudaMalloc(&out->tile_base, (size_t)n_tiles * sizeof(uint64_t)));
-    uint64_t* d_tile_units = nullptr;
-    uint64_t* d_total = nullptr;
-    unsigned int* d_err = nullptr;
-    FRZ_CUDA_TRY(cudaMalloc(&d_tile_units, (size_t)n_tiles * sizeof(uint64_t)));
-    FRZ_CUDA_TRY(cudaMalloc(&d_total, 16));
-    d_err = reinterpret_cast<unsigned int*>(d_total + 1);
+    if (out->cap_tiles < n_tiles) {
+        cudaFree(out->slot_meta); cudaFree(out->slot_of); cudaFree(out->groups); cudaFree(out->tile_base); cudaFree(out->scratch_tile_units);
+        out->slot_meta = nullptr; out->slot_of = nullptr; out->groups = nullptr; out->tile_base = nullptr; out->scratch_tile_units = nullptr;
+        out->cap_tiles = 0;
+        FRZ_CUDA_TRY(cudaMalloc(&out->slot_meta, slots * sizeof(uint32_t)));
+        FRZ_CUDA_TRY(cudaMalloc(&out->slot_of, slots * sizeof(uint16_t)));
+        FRZ_CUDA_TRY(cudaMalloc(&out->groups, (size_t)n_tiles * FRZ_GROUPS_PER_TILE * sizeof(FrzGroupDesc)));
+        FRZ_CUDA_TRY(cudaMalloc(&out->tile_base, (size_t)n_tiles * sizeof(uint64_t)));
+        FRZ_CUDA_TRY(cudaMalloc(&out->scratch_tile_units, ((size_t)n_tiles + 2) * sizeof(uint64_t)));
+        out->cap_tiles = n_tiles;
+    }
+    uint64_t* d_tile_units = out->scratch_tile_units;
+    uint64_t* d_total = d_tile_units + out->cap_tiles;
+    unsigned int* d_err = reinterpret_cast<unsigned int*>(d_total + 1);
     FRZ_CUDA_TRY(cudaMemsetAsync(d_total, 0, 16, stream));
     FRZ_CUDA_TRY(cudaMemsetAsync(out->slot_of, 0, slots * sizeof(uint16_t), stream));
     k_pack_plan<<<n_tiles, 256, 0, stream>>>(d_offsets, n, out->slot_meta, out->slot_of, out->groups, d_tile_units, d_err);
@@ -211,12 +215,15 @@ frz_status frz_pack_corpus_device(const uint8_t* d_bytes, const uint64_t* d_offs
     uint64_t h[2] = {0, 0};
     FRZ_CUDA_TRY(cudaMemcpyAsync(h, d_total, 16, cudaMemcpyDeviceToHost, stream));
     FRZ_CUDA_TRY(cudaStreamSynchronize(stream));
-    cudaFree(d_tile_units);
     unsigned int err = (unsigned int)(h[1] & 0xffffffffu);
-    cudaFree(d_total);
     if (err) return frz_fail(FRZ_ERR_UNSUPPORTED, "haystack longer than 4 MiB");
     out->total_units = h[0];
-    FRZ_CUDA_TRY(cudaMalloc(&out->data, (size_t)(out->total_units + 1) * sizeof(uint4)));
+    if (out->cap_units < out->total_units + 1) {
+        cudaFree(out->data); out->data = nullptr; out->cap_units = 0;
+        const uint64_t want = out->total_units + out->total_units / 16 + 1024;
+        FRZ_CUDA_TRY(cudaMalloc(&out->data, (size_t)want * sizeof(uint4)));
+        out->cap_units = want;
+    }
     k_pack_copy<<<n_tiles, 256, 0, stream>>>(d_bytes, d_offsets, n, total_bytes, out->slot_meta, out->groups,
                                              out->tile_base, out->data);
     FRZ_CUDA_TRY(cudaGetLastError());

@@ -6,8 +6,8 @@
 // the whole score when the score bound allows it (one pass), else the reference's two 8-bit passes.
 //
 //   k_sort_hist     each "virtual warp" owns a contiguous segment and counts its digits in smem
-//   k_sort_scan     per-digit exclusive prefix over the segments + descending exclusive prefix
-//                   over digits
+//   k_sort_scan_rows / k_sort_digit_base
+//                   per-digit exclusive prefix over the segments + descending exclusive prefix over digits
 //   k_sort_scatter  each virtual warp re-walks its segment IN ORDER, 32 elements at a time;
 //                   __match_any_sync gives the in-warp stable rank, a per-warp counter array the rest
 //
@@ -18,9 +18,9 @@
 
 namespace {
 
-constexpr int kSortBlocks = 32;
+constexpr int kSortBlocks = 128;
 constexpr int kSortWarps = 8;
-constexpr int kV = kSortBlocks * kSortWarps;  // virtual warps = segments
+constexpr int kV = kSortBlocks * kSortWarps;  // 1024 virtual warps = segments (latency-bound walk: more is faster)
 constexpr int kMaxBins = 1024;
 
 __device__ __forceinline__ void segment_of(unsigned long long n, int v, unsigned long long* lo, unsigned long long* hi) {
@@ -53,29 +53,39 @@ __global__ void __launch_bounds__(kSortWarps * 32) k_sort_hist(const FrzMatchDev
     for (int d = lane; d < bins; d += 32) hist[(size_t)d * kV + v] = cnt[d];
 }
 
-// hist[d][v] → exclusive prefix over v (in place); digit_base[d] = #elements with digit > d
-__global__ void __launch_bounds__(1024) k_sort_scan(uint32_t* __restrict__ hist, int bins, uint32_t* __restrict__ digit_base) {
-    __shared__ uint32_t totals[kMaxBins];
+// hist[d][v] → exclusive prefix over v (in place), one warp per digit row; totals[d] = row sum
+__global__ void __launch_bounds__(256) k_sort_scan_rows(uint32_t* __restrict__ hist, int bins, uint32_t* __restrict__ totals) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int d = blockIdx.x * 8 + warp;
+    if (d >= bins) return;
+    constexpr int PER = kV / 32;  // contiguous entries per lane
+    uint4* row = reinterpret_cast<uint4*>(hist + (size_t)d * kV + lane * PER);
+    uint4 v[PER / 4];
+    uint32_t s = 0;
+#pragma unroll
+    for (int k = 0; k < PER / 4; k++) { v[k] = row[k]; s += v[k].x + v[k].y + v[k].z + v[k].w; }
+    uint32_t x = s;
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+    }
+    uint32_t run = x - s;
+#pragma unroll
+    for (int k = 0; k < PER / 4; k++) {
+        uint4 o4;
+        o4.x = run; run += v[k].x;
+        o4.y = run; run += v[k].y;
+        o4.z = run; run += v[k].z;
+        o4.w = run; run += v[k].w;
+        row[k] = o4;
+    }
+    if (lane == 31) totals[d] = x;
+}
+
+// digit_base[d] = #elements with digit > d (descending exclusive prefix over the row totals)
+__global__ void __launch_bounds__(1024) k_sort_digit_base(const uint32_t* __restrict__ totals, int bins, uint32_t* __restrict__ digit_base) {
     __shared__ uint32_t wsum[32];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    constexpr int PER = kV / 32;  // entries per lane
-    for (int d = warp; d < bins; d += 32) {
-        uint32_t* row = hist + (size_t)d * kV;
-        uint32_t vals[PER], s = 0;
-#pragma unroll
-        for (int k = 0; k < PER; k++) { vals[k] = row[lane * PER + k]; s += vals[k]; }
-        uint32_t x = s;
-        for (int o = 1; o < 32; o <<= 1) {
-            uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
-            if (lane >= o) x += y;
-        }
-        uint32_t run = x - s;
-#pragma unroll
-        for (int k = 0; k < PER; k++) { row[lane * PER + k] = run; run += vals[k]; }
-        if (lane == 31) totals[d] = x;
-    }
-    __syncthreads();
-    // descending exclusive prefix over digits: thread t ↔ digit bins-1-t
     const int t = threadIdx.x;
     uint32_t v = t < bins ? totals[bins - 1 - t] : 0;
     uint32_t x = v;
@@ -136,11 +146,13 @@ frz_status frz_launch_sort_by_score_dev(const FrzMatchDev* d_in, FrzMatchDev* d_
     auto pass = [&](const FrzMatchDev* src, FrzMatchDev* dst, int shift, int bins) -> frz_status {
         const size_t smem = (size_t)kSortWarps * bins * sizeof(uint32_t);
         k_sort_hist<<<kSortBlocks, kSortWarps * 32, smem, stream>>>(src, n_ptr, shift, bins, ws.sort_hist);
-        k_sort_scan<<<1, 1024, 0, stream>>>(ws.sort_hist, bins, ws.sort_hist + (size_t)kMaxBins * kV);
-        k_sort_scatter<<<kSortBlocks, kSortWarps * 32, smem, stream>>>(src, dst, n_ptr, shift, bins, ws.sort_hist,
-                                                                       ws.sort_hist + (size_t)kMaxBins * kV);
+        uint32_t* totals = ws.sort_hist + (size_t)kMaxBins * kV;
+        uint32_t* digit_base = totals + kMaxBins;
+        k_sort_scan_rows<<<(bins + 7) / 8, 256, 0, stream>>>(ws.sort_hist, bins, totals);
+        k_sort_digit_base<<<1, 1024, 0, stream>>>(totals, bins, digit_base);
+        k_sort_scatter<<<kSortBlocks, kSortWarps * 32, smem, stream>>>(src, dst, n_ptr, shift, bins, ws.sort_hist, digit_base);
         FRZ_CUDA_TRY(cudaGetLastError());
-        if (st) st->launches += 3;
+        if (st) st->launches += 4;
         return FRZ_OK;
     };
     if (score_bound < 256) return pass(d_in, d_out, 0, 256);
@@ -151,4 +163,4 @@ frz_status frz_launch_sort_by_score_dev(const FrzMatchDev* d_in, FrzMatchDev* d_
     return pass(d_tmp, d_out, 8, 256);
 }
 
-size_t frz_sort_hist_words() { return (size_t)kMaxBins * kV + kMaxBins; }
+size_t frz_sort_hist_words() { return (size_t)kMaxBins * kV + 2 * kMaxBins; }

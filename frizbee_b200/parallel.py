@@ -64,33 +64,65 @@ def match_list_parallel_host(run: np.ndarray, sort: SortStrategy, group=None) ->
     return merge_runs_host(runs, sort)
 
 
+class ShardRunner:
+    """Persistent device buffers for repeated match_list_parallel calls on one shard (no allocation per call)."""
+
+    def __init__(self, matcher: Matcher, shard: Corpus, index_offset: int, group=None, device: Optional[int] = None):
+        import torch
+        import torch.distributed as dist
+        self.matcher, self.shard, self.index_offset, self.group = matcher, shard, index_offset, group
+        self.dev = torch.device("cuda", torch.cuda.current_device() if device is None else device)
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        n_local = max(len(shard), 1)
+        self.run = torch.empty(n_local, dtype=torch.int64, device=self.dev)   # 8-byte frz_match records
+        self.count = torch.zeros(1, dtype=torch.int64, device=self.dev)
+        self.counts = torch.zeros(self.world, dtype=torch.int64, device=self.dev)
+        self.gathered = None
+        self.merged = None
+        self.bound = matcher.score_bound()
+
+    def local(self):
+        """This rank's shard → locally ordered run in HBM (asynchronous).  Returns (run tensor, count tensor)."""
+        import torch
+        stream = torch.cuda.current_stream(self.dev)
+        _check(lib().frz_match_shard_device(self.matcher._h, self.shard._h, self.index_offset, self.run.data_ptr(),
+                                            self.run.numel(), self.count.data_ptr(), stream.cuda_stream))
+        return self.run, self.count
+
+    def step(self):
+        """Matcher::match_list_parallel: local run, ONE all-gather of the padded runs, device merge.
+        Returns (merged tensor view, total)."""
+        import torch
+        import torch.distributed as dist
+        run, count = self.local()
+        if self.world == 1:
+            return run, None
+        dist.all_gather_into_tensor(self.counts, count, group=self.group)
+        counts_h = np.asarray(self.counts.cpu().tolist(), dtype=np.uint64)      # the one host sync of the step
+        stride = max(int(counts_h.max()), 1)
+        total = int(counts_h.sum())
+        need = self.world * stride
+        if self.gathered is None or self.gathered.numel() < need:
+            self.gathered = torch.empty(int(need * 1.25) + 1024, dtype=torch.int64, device=self.dev)
+        if self.merged is None or self.merged.numel() < total:
+            self.merged = torch.empty(int(total * 1.25) + 1024, dtype=torch.int64, device=self.dev)
+        g = self.gathered[:need]
+        dist.all_gather_into_tensor(g, run[:stride], group=self.group)          # run is shard-sized >= stride
+        stream = torch.cuda.current_stream(self.dev)
+        _check(lib().frz_merge_runs_device(g.data_ptr(), stride, counts_h.ctypes.data, self.world, int(self.matcher.config.sort),
+                                           self.bound, self.merged.data_ptr(), self.dev.index, stream.cuda_stream))
+        return self.merged[:total], total
+
+
 def match_list_parallel(matcher: Matcher, shard: Corpus, index_offset: int, group=None, device: Optional[int] = None):
     """Runs this rank's shard, all-gathers the runs over NCCL and merges them on every rank.
-    Returns (merged matches as a uint64-viewable torch tensor on the device, total count)."""
-    import torch
-    import torch.distributed as dist
-
-    dev = torch.device("cuda", torch.cuda.current_device() if device is None else device)
-    world = dist.get_world_size(group) if dist.is_initialized() else 1
-    n_local = len(shard)
-    stream = torch.cuda.current_stream(dev)
-    run = torch.empty(max(n_local, 1), dtype=torch.int64, device=dev)  # 8-byte frz_match records
-    count = torch.zeros(1, dtype=torch.int64, device=dev)
-    _check(lib().frz_match_shard_device(matcher._h, shard._h, index_offset, run.data_ptr(), run.numel(),
-                                        count.data_ptr(), stream.cuda_stream))
-    if world == 1:
-        n = int(count.item())
-        return run[:n], n
-    # one collective for the counts (8 bytes per rank) and ONE all-gather of the per-shard (score, index)
-    # buffers, padded to the longest run
-    gathered, counts_l, stride = all_gather_runs(run, int(count.item()), group)
-    counts_h = np.asarray(counts_l, dtype=np.uint64)
-    total = int(counts_h.sum())
-    merged = torch.empty(max(total, 1), dtype=torch.int64, device=dev)
-    ch = np.ascontiguousarray(counts_h)
-    _check(lib().frz_merge_runs_device(gathered.data_ptr(), stride, ch.ctypes.data, world, int(matcher.config.sort),
-                                       merged.data_ptr(), dev.index, stream.cuda_stream))
-    return merged[:total], total
+    Returns (merged matches as an int64 torch tensor of 8-byte records on the device, total count)."""
+    r = ShardRunner(matcher, shard, index_offset, group, device)
+    merged, total = r.step()
+    if total is None:
+        total = int(r.count.item())
+        merged = merged[:total]
+    return merged, total
 
 
 def matches_from_tensor(t) -> np.ndarray:

@@ -213,10 +213,14 @@ FRZ_API frz_status frz_match_shard_device(frz_matcher* m, const frz_corpus* shar
 
 /* k_merge_matches_by (src/k_merge.rs:90-131) on device: `d_runs` holds `n_runs` runs, run r at
  * d_runs + r*run_stride with run_counts_host[r] valid entries, each already ordered per `sort`.
- * Writes the merged sequence to d_out (may not alias d_runs). */
+ * `score_bound`: upper bound of the scores in the runs (frz_matcher_score_bound), 0 = unknown.
+ * Writes the merged sequence to d_out (may not alias d_runs).  Asynchronous on `stream`. */
 FRZ_API frz_status frz_merge_runs_device(const frz_match* d_runs, uint64_t run_stride,
                                  const uint64_t* run_counts_host, int n_runs, uint8_t sort,
-                                 frz_match* d_out, int device, void* stream);
+                                 uint32_t score_bound, frz_match* d_out, int device, void* stream);
+/* Upper bound of any score this matcher can emit (sum over its non-negated patterns, saturating at
+ * 65535); lets the device sort / merge use a single counting pass.  0 for an empty matcher. */
+FRZ_API uint32_t frz_matcher_score_bound(const frz_matcher* m);
 
 /* radix_sort_matches (src/sort.rs:6-40): stable, descending score; `matches` is host memory. */
 FRZ_API frz_status frz_radix_sort_matches(frz_match* matches, uint64_t n, int device);
