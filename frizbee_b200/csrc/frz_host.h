@@ -90,6 +90,7 @@ struct FrzWorkspace {
     uint32_t* cand_bitmap = nullptr;        // multi-pattern candidate bitmap [n/32]
     uint64_t cand_cap = 0;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    bool ev_rec[6] = {false, false, false, false, false, false};  // recorded during the current call
     void release();
 };
 

@@ -800,14 +800,14 @@ frz_status run_pattern(frz_matcher* m, const FrzCorpusStorage& cs, const Compile
     uint64_t cap = std::max(ws.survivor_cap, initial_survivor_cap(cs, c.dev));
     FRZ_TRY(ensure_workspace(m, cs, cap));
     FRZ_CUDA_TRY(cudaMemsetAsync(ws.counters, 0, sizeof(FrzCounters), stream));
-    if (record_events) cudaEventRecord(ws.ev[0], stream);
+    if (record_events) { cudaEventRecord(ws.ev[0], stream); ws.ev_rec[0] = true; }
     FRZ_TRY(frz_launch_prefilter(cv, c.dev, cand_bitmap, ws, stream, st));
     FRZ_TRY(frz_launch_tile_scan(cv, ws, stream, st));
-    if (record_events) cudaEventRecord(ws.ev[1], stream);
+    if (record_events) { cudaEventRecord(ws.ev[1], stream); ws.ev_rec[1] = true; }
     // A survivor-list overflow (lists are sized by a heuristic unless the pattern can match everything)
     // only sets a sticky device flag; whoever reads the counters back re-runs with worst-case lists.
     FRZ_TRY(frz_launch_sw(cv, c.dev, index_offset, reversed, ws, d_out, stream, st));
-    if (record_events) cudaEventRecord(ws.ev[2], stream);
+    if (record_events) { cudaEventRecord(ws.ev[2], stream); ws.ev_rec[2] = true; }
     return FRZ_OK;
 }
 
@@ -961,6 +961,7 @@ frz_status match_list_device(frz_matcher* m, const FrzCorpusStorage& cs, uint32_
     const bool reversed = sort == FRZ_SORT_INDEX_DESC || sort == FRZ_SORT_SCORE_THEN_INDEX_DESC;
     const bool by_score = sort == FRZ_SORT_SCORE_THEN_INDEX_ASC || sort == FRZ_SORT_SCORE_THEN_INDEX_DESC;
     const bool will_sort = by_score && !m->compiled.empty();
+    for (bool& f : ws.ev_rec) f = false;
     FrzMatchDev* d_list = nullptr;
     uint32_t bound = 0;
     FRZ_TRY(match_into_device(m, cs, index_offset, reversed, &d_list, &bound, stream, st, will_sort ? nullptr : final_out));
@@ -984,6 +985,7 @@ frz_status match_list_device(frz_matcher* m, const FrzCorpusStorage& cs, uint32_
         d_list = final_out;
     }
     cudaEventRecord(ws.ev[3], stream);
+    ws.ev_rec[3] = true;
     *d_result = d_list;
     return FRZ_OK;
 }
@@ -992,10 +994,11 @@ frz_status match_list_device(frz_matcher* m, const FrzCorpusStorage& cs, uint32_
 void collect_timings(frz_matcher* m, const FrzLaunchStats& st) {
     FrzWorkspace& ws = m->ws;
     float a = 0, b = 0, c = 0, t = 0;
-    if (cudaEventElapsedTime(&a, ws.ev[0], ws.ev[1]) != cudaSuccess) a = 0;
-    if (cudaEventElapsedTime(&b, ws.ev[1], ws.ev[2]) != cudaSuccess) b = 0;
-    if (cudaEventElapsedTime(&c, ws.ev[2], ws.ev[3]) != cudaSuccess) c = 0;
-    if (cudaEventElapsedTime(&t, ws.ev[0], ws.ev[3]) != cudaSuccess) t = 0;
+    const bool* r = ws.ev_rec;
+    if (r[0] && r[1] && cudaEventElapsedTime(&a, ws.ev[0], ws.ev[1]) != cudaSuccess) a = 0;
+    if (r[1] && r[2] && cudaEventElapsedTime(&b, ws.ev[1], ws.ev[2]) != cudaSuccess) b = 0;
+    if (r[2] && r[3] && cudaEventElapsedTime(&c, ws.ev[2], ws.ev[3]) != cudaSuccess) c = 0;
+    if (r[0] && r[3] && cudaEventElapsedTime(&t, ws.ev[0], ws.ev[3]) != cudaSuccess) t = 0;
     cudaGetLastError();
     m->last_ms[0] = a; m->last_ms[1] = b; m->last_ms[2] = c; m->last_ms[3] = t;
     m->last_launches = st.launches;

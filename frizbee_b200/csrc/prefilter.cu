@@ -27,8 +27,7 @@ namespace {
 
 constexpr int kThreads = 128;
 constexpr int kWarps = kThreads / 32;
-constexpr int kSliceUnits = 8;                         // haystacks up to 128 bytes are staged in smem
-constexpr int kSliceWords = kSliceUnits * 4 + 2;       // +2 words: 8-byte aligned, conflict-free LDS.64 stride, zero guard
+constexpr int kSliceUnits = 8;                         // groups of up to 8 units (128 bytes) are probed from registers
 
 struct SliceAcc {
     const uint32_t* s;
@@ -361,14 +360,17 @@ __device__ __forceinline__ uint32_t zero_flags(uint32_t x) {
     return r;
 }
 
-// occ[d][lane] = occurrence mask of distinct class d over bytes [64*blk, 64*blk+64) of the lane's slice
-__device__ __forceinline__ void build_block_masks(const uint32_t* sl, int blk, const FrzPatternDev& pat,
+// occ[d][lane] = occurrence mask of distinct class d over bytes [64*blk, 64*blk+64) of the lane's haystack.
+// `base` points at unit 0 of the lane's slot (unit k at base + 32*k); the units were streamed by this very
+// warp a few groups ago, so these loads hit L1/L2.  `units` = ceil(len / 16) bounds the reads.
+__device__ __forceinline__ void build_block_masks(const uint4* base, int units, int blk, const FrzPatternDev& pat,
                                                   uint2 (*occ)[32], uint32_t lane) {
     uint32_t w[16];
 #pragma unroll
-    for (int k = 0; k < 8; k++) {
-        const uint2 v = *reinterpret_cast<const uint2*>(sl + 16 * blk + 2 * k);
-        w[2 * k] = v.x; w[2 * k + 1] = v.y;
+    for (int k = 0; k < 4; k++) {
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (4 * blk + k < units) v = __ldg(base + (size_t)(4 * blk + k) * FRZ_GROUP);
+        w[4 * k] = v.x; w[4 * k + 1] = v.y; w[4 * k + 2] = v.z; w[4 * k + 3] = v.w;
     }
     for (int d = 0; d < pat.n_distinct; d++) {
         const uint32_t om4 = splat4(pat.dc_om[d]), tg4 = splat4(pat.dc_tg[d]);
@@ -389,16 +391,17 @@ __device__ __forceinline__ uint64_t lowmask64(int n) { return n >= 64 ? ~0ull : 
 __device__ __forceinline__ uint64_t u2_to_u64(uint2 v) { return (uint64_t)v.x | ((uint64_t)v.y << 32); }
 
 // Window of the 0-typo prefilter (closed form) from block masks.  Warp-wide;
-// `active` lanes own an in-slice candidate of `len` bytes (len <= 128).
-__device__ __forceinline__ bool masks_k0(const uint32_t* sl, const FrzPatternDev& pat, const uint8_t* __restrict__ cid_s,
+// `active` lanes own a candidate of `len` bytes starting at unit pointer `base` (any length: 64-byte blocks).
+__device__ __forceinline__ bool masks_k0(const uint4* base, const FrzPatternDev& pat, const uint8_t* __restrict__ cid_s,
                                          uint2 (*occ)[32], int len, bool active, int* ostart, int* oend) {
+    const int units = active ? (len + 15) >> 4 : 0;
     const uint32_t lane = frz_lane();
     const int n = pat.n;
     int ni = 0, start = 0, end = 0;
     bool alive = active && len > 0, found = false;
     const int max_len = __reduce_max_sync(0xffffffffu, active ? len : 0);
     for (int blk = 0; blk * 64 < max_len; blk++) {
-        build_block_masks(sl, blk, pat, occ, lane);
+        build_block_masks(base, units, blk, pat, occ, lane);
         __syncwarp();
         const int rem = len - blk * 64;
         const uint64_t valid = rem > 0 ? lowmask64(rem) : 0ull;
@@ -425,8 +428,9 @@ __device__ __forceinline__ bool masks_k0(const uint32_t* sl, const FrzPatternDev
 }
 
 // match_haystack_1_typo (src/prefilter/algo/ascii_typos.rs:15-110) on block masks, chunk width L.
-__device__ __forceinline__ bool masks_k1(const uint32_t* sl, const FrzPatternDev& pat, const uint8_t* __restrict__ cid_s,
+__device__ __forceinline__ bool masks_k1(const uint4* base, const FrzPatternDev& pat, const uint8_t* __restrict__ cid_s,
                                          uint2 (*occ)[32], int len, bool active, int* ostart, int* oend) {
+    const int units = active ? (len + 15) >> 4 : 0;
     const uint32_t lane = frz_lane();
     const int n = pat.n, L = pat.pf_lanes;
     int f = 0, s = 1, ms = 0x7fffffff, end = -1;
@@ -437,7 +441,7 @@ __device__ __forceinline__ bool masks_k1(const uint32_t* sl, const FrzPatternDev
     const int max_len = __reduce_max_sync(0xffffffffu, active ? len : 0);
     const uint64_t lmask = lowmask64(L);
     for (int blk = 0; blk * 64 < max_len; blk++) {
-        build_block_masks(sl, blk, pat, occ, lane);
+        build_block_masks(base, units, blk, pat, occ, lane);
         __syncwarp();
         const int rem = len - blk * 64;
         const uint64_t valid = rem > 0 ? lowmask64(rem) : 0ull;
@@ -505,9 +509,8 @@ __device__ __forceinline__ bool masks_k1(const uint32_t* sl, const FrzPatternDev
 constexpr int kQueueCap = 64;  // per-warp candidate queue (31 left over + 32 new at most)
 
 struct WarpQueue {
-    uint32_t slice[kQueueCap][kSliceWords];  // candidate haystack bytes (zero padded to the unit), +1 guard word
     uint32_t meta[kQueueCap];                // tile << 10 | slot
-    uint32_t info[kQueueCap];                // len | in_slice << 31
+    uint32_t info[kQueueCap];                // len
     uint2 occ[kMaxDistinct][32];             // per-lane occurrence masks of the distinct needle byte classes
 };
 
@@ -527,39 +530,34 @@ __device__ __forceinline__ void process_candidate(const FrzCorpusView& cv, const
     int cls = 0;
     FrzSurvivor rec;
     rec.tile = 0; rec.slot_rank = 0; rec.start = 0; rec.end = 0;
-    // warp-wide flat automaton for the common case (haystack staged in the slice)
+    const uint32_t meta0 = active ? q.meta[entry] : 0u;
+    const uint32_t tile = meta0 >> FRZ_TILE_SHIFT, slot = meta0 & (FRZ_TILE - 1);
+    const int len = active ? (int)q.info[entry] : 0;
+    GlobalAcc ga{nullptr};
+    if (active) {
+        const FrzGroupDesc gd = cv.groups[tile * FRZ_GROUPS_PER_TILE + (slot >> 5)];
+        ga.base = cv.data + cv.tile_base[tile] + gd.unit_off + (slot & 31);
+    }
+    // warp-wide occurrence-mask windows (uniform code) for the 0- and 1-typo modes
     bool flat_done = false, flat_ok = false;
     int flat_start = 0, flat_end = 0;
     if ((MODE == FRZ_T_0 || MODE == FRZ_T_1) && pat.n_distinct > 0) {
-        const uint32_t info0 = active ? q.info[entry] : 0u;
-        const bool use_flat = active && (info0 >> 31) != 0;
-        const int len0 = (int)(info0 & 0x7fffffffu);
-        if (MODE == FRZ_T_0) flat_ok = masks_k0(q.slice[entry], pat, cid_s, q.occ, len0, use_flat, &flat_start, &flat_end);
-        else flat_ok = masks_k1(q.slice[entry], pat, cid_s, q.occ, len0, use_flat, &flat_start, &flat_end);
-        flat_done = use_flat;
+        if (MODE == FRZ_T_0) flat_ok = masks_k0(ga.base, pat, cid_s, q.occ, len, active, &flat_start, &flat_end);
+        else flat_ok = masks_k1(ga.base, pat, cid_s, q.occ, len, active, &flat_start, &flat_end);
+        flat_done = true;
     }
     if (active) {
-        const uint32_t meta = q.meta[entry], info = q.info[entry];
-        const uint32_t tile = meta >> FRZ_TILE_SHIFT, slot = meta & (FRZ_TILE - 1);
-        const int len = (int)(info & 0x7fffffffu);
-        const bool in_slice = (info >> 31) != 0;
         const uint32_t li = cv.slot_meta[(uint64_t)tile * FRZ_TILE + slot] & (FRZ_TILE - 1);
         int start = 0, end = len;
         uint32_t lit_score = 0;
-        SliceAcc sa{q.slice[entry]};
-        GlobalAcc ga{nullptr};
-        if (!in_slice) {
-            FrzGroupDesc gd = cv.groups[tile * FRZ_GROUPS_PER_TILE + (slot >> 5)];
-            ga.base = cv.data + cv.tile_base[tile] + gd.unit_off + (slot & 31);
-        }
         if (flat_done) { ok = flat_ok; start = flat_start; end = flat_end; }
-        else if (MODE == FRZ_T_0) ok = in_slice ? window_k0(sa, pat, len, &start, &end) : window_k0(ga, pat, len, &start, &end);
-        else if (MODE == FRZ_T_1) ok = in_slice ? window_k1(sa, pat, len, &start, &end) : window_k1(ga, pat, len, &start, &end);
-        else if (MODE == FRZ_T_2) ok = in_slice ? window_k2(sa, pat, len, &start, &end) : window_k2(ga, pat, len, &start, &end);
-        else if (MODE == FRZ_T_MANY) ok = in_slice ? window_many(sa, pat, len, &start, &end) : window_many(ga, pat, len, &start, &end);
+        else if (MODE == FRZ_T_0) ok = window_k0(ga, pat, len, &start, &end);
+        else if (MODE == FRZ_T_1) ok = window_k1(ga, pat, len, &start, &end);
+        else if (MODE == FRZ_T_2) ok = window_k2(ga, pat, len, &start, &end);
+        else if (MODE == FRZ_T_MANY) ok = window_many(ga, pat, len, &start, &end);
         else if (MODE == FRZ_T_LITERAL) {
             int pos = 0;
-            ok = in_slice ? lit_find(sa, pat, len, &pos, &lit_score) : lit_find(ga, pat, len, &pos, &lit_score);
+            ok = lit_find(ga, pat, len, &pos, &lit_score);
             start = pos; end = pos + pat.n;
         } else ok = true;  // FRZ_T_NONE: NO_PREFILTER (src/matcher/algo.rs:178)
         if (ok) {
@@ -711,28 +709,7 @@ __global__ void __launch_bounds__(kThreads) k_prefilter(const FrzCorpusView cv, 
             if (pass) {
                 const uint32_t e = (head + count + __popc(ballot & ((1u << lane) - 1))) & (kQueueCap - 1);
                 q.meta[e] = (tile << FRZ_TILE_SHIFT) | slot;
-                q.info[e] = len | (in_slice ? 0x80000000u : 0u);
-                if (in_slice) {
-                    uint4* dst = reinterpret_cast<uint4*>(q.slice[e]);
-#pragma unroll
-                    for (int k = 0; k < kSliceUnits; k++) {
-                        if (k >= (int)gd.gunits) break;
-                        // slices are only 8-byte aligned (136-byte stride): two 8-byte stores per unit
-                        uint2* d2 = reinterpret_cast<uint2*>(q.slice[e] + 4 * k);
-                        d2[0] = make_uint2(u[k].x, u[k].y);
-                        d2[1] = make_uint2(u[k].z, u[k].w);
-                    }
-                    (void)dst;
-                    *reinterpret_cast<uint2*>(q.slice[e] + 4 * gd.gunits) = make_uint2(0u, 0u);  // guard words
-                    // blocks are built 64 bytes at a time: zero the tail of a half-filled block
-                    if (gd.gunits & 3) {
-                        for (uint32_t k = gd.gunits; k < ((gd.gunits + 3) & ~3u); k++) {
-                            uint2* d2 = reinterpret_cast<uint2*>(q.slice[e] + 4 * k);
-                            d2[0] = make_uint2(0u, 0u);
-                            d2[1] = make_uint2(0u, 0u);
-                        }
-                    }
-                }
+                q.info[e] = len;
             }
             count += __popc(ballot);
             __syncwarp();
