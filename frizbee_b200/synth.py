@@ -13,9 +13,17 @@ import numpy as np
 ALNUM = np.frombuffer(b"ABCDEFGHIJKLMNOPQRSTUVWXYZabcdefghijklmnopqrstuvwxyz0123456789", dtype=np.uint8)
 
 
+UNICODE_SCALARS = ["é".encode(), "ن".encode(), "다".encode(), "😀".encode()]  # generator.rs:94-106
+
+
 def generate(needle: str, n: int, mu: int, max_len: int, seed: int = 12345, p_partial: float = 0.20,
-             p_full: float = 0.05, chunk: int = 1 << 20, alphabet: bytes = None) -> Tuple[np.ndarray, np.ndarray]:
-    """Returns Arrow-style (bytes u8[total], offsets u64[n+1])."""
+             p_full: float = 0.05, chunk: int = 1 << 20, alphabet: bytes = None, unicode_frac: float = 0.0,
+             prefix_frac: float = 0.0, prefixes=(b"bar", b"Bar")) -> Tuple[np.ndarray, np.ndarray]:
+    """Returns Arrow-style (bytes u8[total], offsets u64[n+1]).
+
+    unicode_frac: fraction of items that get 1-3 multibyte scalars spliced in at byte positions that are
+    char boundaries of the (ASCII) base string; prefix_frac: fraction of items that start with one of
+    `prefixes` (BASELINE.json configs[4]: query 'foo !^bar' on mixed-unicode haystacks)."""
     rng = np.random.default_rng(seed)
     nb = np.frombuffer(needle.encode(), dtype=np.uint8)
     k = len(nb)
@@ -62,6 +70,52 @@ def generate(needle: str, n: int, mu: int, max_len: int, seed: int = 12345, p_pa
             sub[fullmask] = np.arange(k)[None, :]
             rr, cc = np.nonzero(pos_valid)
             mat[rows[rr], order[rr, cc]] = nb[np.minimum(sub[rr, cc], k - 1)]
+        if prefix_frac > 0:
+            pr = np.nonzero(rng.random(m) < prefix_frac)[0]
+            for k2, pre in enumerate(prefixes):
+                rows2 = pr[k2::len(prefixes)]
+                pb = np.frombuffer(pre, dtype=np.uint8)
+                rows2 = rows2[length[rows2] >= len(pb)]
+                mat[rows2[:, None], np.arange(len(pb))[None, :]] = pb[None, :]
+        if unicode_frac > 0:
+            # up to 3 splices per selected row, each inserting one scalar at a random byte position of the
+            # current string (the base is ASCII and scalars are inserted whole, so boundaries stay valid)
+            wide = np.zeros((m, max_len + 16), dtype=np.uint8)
+            wide[:, :max_len] = mat
+            cur = length.copy()
+            sel = rng.random(m) < unicode_frac
+            n_splice = np.where(sel, rng.integers(1, 4, m), 0)
+            for it in range(3):
+                rows3 = np.nonzero((n_splice > it) & (cur + 4 <= max_len))[0]
+                if rows3.size == 0:
+                    continue
+                which = rng.integers(0, len(UNICODE_SCALARS), rows3.size)
+                pos = (rng.random(rows3.size) * (cur[rows3] + 1)).astype(np.int64)
+                # keep earlier splices intact: only splice at ASCII/lead-byte boundaries (not before a continuation byte)
+                is_cont = (wide[rows3, np.minimum(pos, max_len + 15)] & 0xC0) == 0x80
+                pos = np.where(is_cont, cur[rows3], pos)
+                for w, sc in enumerate(UNICODE_SCALARS):
+                    r4 = rows3[which == w]
+                    if r4.size == 0:
+                        continue
+                    p4 = pos[which == w]
+                    k4 = len(sc)
+                    cols = np.arange(max_len + 16)[None, :]
+                    src = np.where(cols < p4[:, None], cols, cols - k4)
+                    moved = np.take_along_axis(wide[r4], np.clip(src, 0, max_len + 15), axis=1)
+                    ins = (cols >= p4[:, None]) & (cols < p4[:, None] + k4)
+                    scb = np.frombuffer(sc, dtype=np.uint8)
+                    moved[ins] = scb[(cols - p4[:, None])[ins]]
+                    wide[r4] = moved
+                    cur[r4] += k4
+            mat = wide[:, :max_len]
+            length = np.minimum(cur, max_len)
+            # never cut a scalar in half at max_len: back off to the previous char boundary
+            for _ in range(3):
+                over = (length < max_len + 1) & (length > 0)
+                nxt = wide[np.arange(m), np.minimum(length, max_len + 15)]
+                cut = over & ((nxt & 0xC0) == 0x80) & (cur > length)
+                length = np.where(cut, length - 1, length)
         mask = np.arange(max_len)[None, :] < length[:, None]
         parts.append(mat[mask])
         lens_all.append(length)

@@ -464,7 +464,7 @@ static uint16_t sw_score(const uint8_t* needle_raw, size_t n, const frz_scoring&
             size_t pos = (col - 1) * lanes + i;
             b[i] = pos < hl ? hay[pos] : 0;
         }
-        bool up[kMaxLanes], lo[kMaxLanes], dl[kMaxLanes];
+        bool up[kMaxLanes] = {false}, lo[kMaxLanes] = {false}, dl[kMaxLanes] = {false};
         for (int i = 0; i < lanes; i++) {
             up[i] = b[i] < 'Z' + 1 && b[i] > 'A' - 1;
             lo[i] = b[i] < 'z' + 1 && b[i] > 'a' - 1;

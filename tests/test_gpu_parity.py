@@ -256,3 +256,25 @@ def test_full_size_properties():
     c = m.match_list_host_array(data, off)
     assert np.array_equal(a, c)
     corpus.close()
+
+
+def test_config5_mixed_unicode_multi_pattern():
+    # BASELINE.json configs[4] shape: query 'foo !^bar' on mixed-unicode haystacks, len <= 128 bytes.
+    # The needles are ASCII, so the reference takes the byte path (UnicodeMatching::Smart, src/lib.rs:394-399);
+    # bytes >= 128 are "not delimiters" for the bonuses (src/smith_waterman/algo/ascii.rs:86-89).
+    data, off = synth.generate("foo", 150_000, 96, 128, unicode_frac=0.3, prefix_frac=0.1)
+    pats = [Pattern("foo"), Pattern("bar", negated=True, matching=Matching.Prefix)]
+    for lanes in (32, 64):
+        gpu_vs_oracle(pats, data, off, Config(emulate_lanes=lanes))
+    m = F.Matcher.from_query("foo !^bar", Config())
+    corpus = F.Corpus.from_arrow(data, off)
+    got = m.match_list_array(corpus)
+    want = O.match_list_packed(pats, Config(emulate_lanes=m.backend_info()["prefilter_lanes"]), data, off)
+    assert np.array_equal(got, want)
+    corpus.close()
+
+
+def test_config2_and_config4_shapes_full_prefix():
+    # configs[1]: needle len 6, 1M haystacks len <= 32, k = 0; configs[3] shard shape: len <= 64, k = 0
+    data, off = synth.generate("deadbe", 1_000_000, 24, 32)
+    gpu_vs_oracle("deadbe", data, off, Config(max_typos=0))
