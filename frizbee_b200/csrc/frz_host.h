@@ -87,8 +87,12 @@ struct FrzWorkspace {
     uint64_t match_cap = 0;
     uint32_t* sort_hist = nullptr;          // [256 * n_sort_blocks]
     uint64_t sort_hist_cap = 0;
-    uint32_t* cand_bitmap = nullptr;        // multi-pattern candidate bitmap [n/32]
+    uint32_t* cand_bitmap = nullptr;        // (unused by the list mode; kept for the bitmap-restricted scan)
     uint64_t cand_cap = 0;
+    uint32_t* retain_cnt = nullptr;         // multi-pattern stable compaction scratch
+    uint64_t* retain_base = nullptr;
+    uint8_t* retain_keep = nullptr;
+    uint64_t retain_cap = 0;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     bool ev_rec[6] = {false, false, false, false, false, false};  // recorded during the current call
     void release();
@@ -101,6 +105,9 @@ struct FrzLaunchStats {
 
 frz_status frz_launch_prefilter(const FrzCorpusView& cv, const FrzPatternDev& pat, const uint32_t* cand_bitmap,
                                 FrzWorkspace& ws, cudaStream_t stream, FrzLaunchStats* st);
+frz_status frz_launch_prefilter_list(const FrzCorpusView& cv, const FrzPatternDev& pat, const FrzMatchDev* cand,
+                                     uint64_t n_cand, uint32_t index_offset, FrzWorkspace& ws, cudaStream_t stream,
+                                     FrzLaunchStats* st);
 frz_status frz_launch_tile_scan(const FrzCorpusView& cv, FrzWorkspace& ws, cudaStream_t stream, FrzLaunchStats* st);
 frz_status frz_launch_sw(const FrzCorpusView& cv, const FrzPatternDev& pat, uint32_t index_offset, bool reversed,
                          FrzWorkspace& ws, FrzMatchDev* d_out, cudaStream_t stream, FrzLaunchStats* st);

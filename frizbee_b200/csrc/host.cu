@@ -521,6 +521,7 @@ void FrzWorkspace::release() {
     for (auto& e : ev) { if (e) cudaEventDestroy(e); e = nullptr; }
     counters = nullptr; h_counters = nullptr; tile_count = nullptr; tile_out_base = nullptr; matches_a = matches_b = nullptr;
     sort_hist = nullptr; cand_bitmap = nullptr;
+    cudaFree(retain_cnt); cudaFree(retain_base); cudaFree(retain_keep); retain_cnt = nullptr; retain_base = nullptr; retain_keep = nullptr; retain_cap = 0;
     survivor_cap = match_cap = sort_hist_cap = cand_cap = 0; tiles_cap = 0; device = -1;
 }
 
@@ -794,14 +795,15 @@ uint64_t initial_survivor_cap(const FrzCorpusStorage& cs, const FrzPatternDev& d
 // d_out (reversed order if `reversed`); the count is left in ws.counters->total (device).
 frz_status run_pattern(frz_matcher* m, const FrzCorpusStorage& cs, const Compiled& c, const uint32_t* cand_bitmap,
                        uint32_t index_offset, bool reversed, FrzMatchDev* d_out, cudaStream_t stream, FrzLaunchStats* st,
-                       bool record_events) {
+                       bool record_events, const FrzMatchDev* cand_list = nullptr, uint64_t n_cand = 0) {
     FrzWorkspace& ws = m->ws;
     const FrzCorpusView cv = cs.view();
     uint64_t cap = std::max(ws.survivor_cap, initial_survivor_cap(cs, c.dev));
     FRZ_TRY(ensure_workspace(m, cs, cap));
     FRZ_CUDA_TRY(cudaMemsetAsync(ws.counters, 0, sizeof(FrzCounters), stream));
     if (record_events) { cudaEventRecord(ws.ev[0], stream); ws.ev_rec[0] = true; }
-    FRZ_TRY(frz_launch_prefilter(cv, c.dev, cand_bitmap, ws, stream, st));
+    if (cand_list) FRZ_TRY(frz_launch_prefilter_list(cv, c.dev, cand_list, n_cand, index_offset, ws, stream, st));
+    else FRZ_TRY(frz_launch_prefilter(cv, c.dev, cand_bitmap, ws, stream, st));
     FRZ_TRY(frz_launch_tile_scan(cv, ws, stream, st));
     if (record_events) { cudaEventRecord(ws.ev[1], stream); ws.ev_rec[1] = true; }
     // A survivor-list overflow (lists are sized by a heuristic unless the pattern can match everything)
@@ -867,12 +869,6 @@ frz_status match_into_device(frz_matcher* m, const FrzCorpusStorage& cs, uint32_
         FRZ_CUDA_TRY(cudaMalloc(&m->multi_b, (size_t)std::max<uint64_t>(cs.n, 1) * sizeof(FrzMatchDev)));
         m->multi_cap = cs.n;
     }
-    const size_t bm_words = (size_t)((cs.n + 31) / 32) + 1;
-    if (ws.cand_cap < bm_words) {
-        cudaFree(ws.cand_bitmap); ws.cand_bitmap = nullptr; ws.cand_cap = 0;
-        FRZ_CUDA_TRY(cudaMalloc(&ws.cand_bitmap, bm_words * sizeof(uint32_t)));
-        ws.cand_cap = bm_words;
-    }
     int base = -1;
     for (size_t i = 0; i < pats.size(); i++) if (!pats[i].negated) { base = (int)i; break; }
     FrzMatchDev* cand = m->multi_a;
@@ -890,28 +886,29 @@ frz_status match_into_device(frz_matcher* m, const FrzCorpusStorage& cs, uint32_
         st->launches++;
         nc = cs.n;
     }
-    uint32_t* d_block_cnt = nullptr;
-    uint64_t* d_block_base = nullptr;
-    uint8_t* d_keep = nullptr;
+    if (ws.retain_cap < cs.n) {
+        cudaFree(ws.retain_cnt); cudaFree(ws.retain_base); cudaFree(ws.retain_keep);
+        ws.retain_cnt = nullptr; ws.retain_base = nullptr; ws.retain_keep = nullptr; ws.retain_cap = 0;
+        const uint32_t nb_max = (uint32_t)((cs.n + kCompactBlock - 1) / kCompactBlock) + 1;
+        FRZ_CUDA_TRY(cudaMalloc(&ws.retain_cnt, nb_max * sizeof(uint32_t)));
+        FRZ_CUDA_TRY(cudaMalloc(&ws.retain_base, nb_max * sizeof(uint64_t)));
+        FRZ_CUDA_TRY(cudaMalloc(&ws.retain_keep, std::max<uint64_t>(cs.n, 1)));
+        ws.retain_cap = cs.n;
+    }
+    uint32_t* d_block_cnt = ws.retain_cnt;
+    uint64_t* d_block_base = ws.retain_base;
+    uint8_t* d_keep = ws.retain_keep;
     frz_status status = FRZ_OK;
     for (size_t pi = 0; pi < pats.size() && status == FRZ_OK; pi++) {
         if ((int)pi == base || nc == 0) continue;
         status = [&]() -> frz_status {
-            FRZ_CUDA_TRY(cudaMemsetAsync(ws.cand_bitmap, 0, bm_words * sizeof(uint32_t), stream));
-            k_bitmap_set<<<grid_for(nc, 256), 256, 0, stream>>>(cand, nc, index_offset, ws.cand_bitmap);
-            st->launches++;
-            // hits land in ws.matches_a, index-ordered, with real indices
-            FRZ_TRY(run_pattern(m, cs, pats[pi], ws.cand_bitmap, index_offset, false, ws.matches_a, stream, st, false));
+            // evaluate the pattern on the surviving candidates only; hits land in ws.matches_a, index-ordered,
+            // with real indices
+            FRZ_TRY(run_pattern(m, cs, pats[pi], nullptr, index_offset, false, ws.matches_a, stream, st, false, cand, nc));
             FRZ_TRY(read_counters(m, stream));
             const uint64_t nh = ws.h_counters->total;
             if (pats[pi].negated) {
                 const uint32_t nb = (uint32_t)((nc + kCompactBlock - 1) / kCompactBlock);
-                if (!d_keep) {
-                    const uint32_t nb_max = (uint32_t)((cs.n + kCompactBlock - 1) / kCompactBlock) + 1;
-                    FRZ_CUDA_TRY(cudaMalloc(&d_block_cnt, nb_max * sizeof(uint32_t)));
-                    FRZ_CUDA_TRY(cudaMalloc(&d_block_base, nb_max * sizeof(uint64_t)));
-                    FRZ_CUDA_TRY(cudaMalloc(&d_keep, std::max<uint64_t>(cs.n, 1)));
-                }
                 k_retain_count<<<nb, kCompactBlock, 0, stream>>>(cand, nc, ws.matches_a, nh, d_block_cnt, d_keep);
                 k_scan_blocks<<<1, 1024, 0, stream>>>(d_block_cnt, d_block_base, nb, ws.counters);
                 k_retain_scatter<<<nb, kCompactBlock, 0, stream>>>(cand, nc, d_keep, d_block_base, spare);
@@ -930,7 +927,6 @@ frz_status match_into_device(frz_matcher* m, const FrzCorpusStorage& cs, uint32_
             return FRZ_OK;
         }();
     }
-    cudaFree(d_block_cnt); cudaFree(d_block_base); cudaFree(d_keep);
     FRZ_TRY(status);
     // publish: count → counters.total, list → matches_a (reversed if asked)
     ws.h_counters->total = nc;

@@ -733,6 +733,42 @@ __global__ void __launch_bounds__(kThreads) k_prefilter(const FrzCorpusView cv, 
     }
 }
 
+// Candidate-list mode (multi-pattern, src/matcher/multi.rs:108-120): the extra patterns are evaluated only
+// on the haystacks that survived the previous patterns.  The list is already compact, so each warp takes 32
+// candidates at a time straight to phase B.
+template <int MODE>
+__global__ void __launch_bounds__(kThreads) k_prefilter_list(const FrzCorpusView cv, const __grid_constant__ FrzPatternDev pat,
+                                                             const FrzMatchDev* __restrict__ cand, unsigned long long n_cand,
+                                                             uint32_t index_offset,
+                                                             FrzSurvivor* __restrict__ surv0, FrzSurvivor* __restrict__ surv1,
+                                                             FrzSurvivor* __restrict__ surv2, unsigned long long surv_cap,
+                                                             uint32_t* __restrict__ surv_bitmap, FrzCounters* __restrict__ ctr) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const uint32_t lane = frz_lane(), warp = threadIdx.x >> 5;
+    WarpQueue& q = reinterpret_cast<WarpQueue*>(smem_raw)[warp];
+    FrzSurvivor* const lists[FRZ_N_CLASSES] = {surv0, surv1, surv2};
+    __shared__ uint8_t cid_s[FRZ_MAX_NEEDLE];
+    if (threadIdx.x < FRZ_MAX_NEEDLE) cid_s[threadIdx.x] = pat.cid[threadIdx.x];
+    __syncthreads();
+    const unsigned long long n_warps = (unsigned long long)gridDim.x * kWarps;
+    for (unsigned long long base = ((unsigned long long)blockIdx.x * kWarps + warp) * 32; base < n_cand; base += n_warps * 32) {
+        const unsigned long long i = base + lane;
+        bool active = i < n_cand;
+        if (active) {
+            const uint32_t idx = cand[i].index - index_offset;
+            const uint32_t tile = idx >> FRZ_TILE_SHIFT, li = idx & (FRZ_TILE - 1);
+            const uint32_t slot = cv.slot_of[(uint64_t)tile * FRZ_TILE + li];
+            const uint32_t len = cv.slot_meta[(uint64_t)tile * FRZ_TILE + slot] >> FRZ_TILE_SHIFT;
+            active = (int)len >= pat.min_hay_len;   // length gate (src/matcher/algo.rs:88)
+            q.meta[lane] = (tile << FRZ_TILE_SHIFT) | slot;
+            q.info[lane] = len;
+        }
+        __syncwarp();
+        process_candidate<MODE>(cv, pat, cid_s, q, lane, active, lists, surv_cap, surv_bitmap, ctr);
+        __syncwarp();
+    }
+}
+
 // Per tile: exclusive prefix popcount of the 32 survivor-bitmap words (→ rank of a survivor among
 // its tile's survivors in index order) and the tile's survivor count.  One warp per tile.
 __global__ void __launch_bounds__(256) k_tile_rank(const uint32_t* __restrict__ surv_bitmap, uint16_t* __restrict__ word_prefix,
@@ -785,6 +821,40 @@ __global__ void __launch_bounds__(1024) k_tile_scan(const uint32_t* __restrict__
 }
 
 }  // namespace
+
+frz_status frz_launch_prefilter_list(const FrzCorpusView& cv, const FrzPatternDev& pat, const FrzMatchDev* cand,
+                                     uint64_t n_cand, uint32_t index_offset, FrzWorkspace& ws, cudaStream_t stream,
+                                     FrzLaunchStats* st) {
+    if (cv.n_tiles == 0) return FRZ_OK;
+    const size_t smem = sizeof(WarpQueue) * kWarps;
+    FRZ_CUDA_TRY(cudaMemsetAsync(ws.surv_bitmap, 0, (size_t)cv.n_tiles * 32 * sizeof(uint32_t), stream));
+    if (n_cand == 0) return FRZ_OK;
+    const uint32_t grid = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(148 * 4, (n_cand + kThreads - 1) / kThreads));
+#define FRZ_PFL_LAUNCH(MODE)                                                                                     \
+    do {                                                                                                         \
+        static bool attr_set = false;                                                                            \
+        if (!attr_set) {                                                                                         \
+            FRZ_CUDA_TRY(cudaFuncSetAttribute(k_prefilter_list<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            attr_set = true;                                                                                     \
+        }                                                                                                        \
+        k_prefilter_list<MODE><<<grid, kThreads, smem, stream>>>(cv, pat, cand, n_cand, index_offset, ws.survivors[0],    \
+                                                                 ws.survivors[1], ws.survivors[2], ws.survivor_cap,       \
+                                                                 ws.surv_bitmap, ws.counters);                            \
+    } while (0)
+    switch (pat.typo_mode) {
+        case FRZ_T_0: FRZ_PFL_LAUNCH(FRZ_T_0); break;
+        case FRZ_T_1: FRZ_PFL_LAUNCH(FRZ_T_1); break;
+        case FRZ_T_2: FRZ_PFL_LAUNCH(FRZ_T_2); break;
+        case FRZ_T_MANY: FRZ_PFL_LAUNCH(FRZ_T_MANY); break;
+        case FRZ_T_NONE: FRZ_PFL_LAUNCH(FRZ_T_NONE); break;
+        case FRZ_T_LITERAL: FRZ_PFL_LAUNCH(FRZ_T_LITERAL); break;
+        default: return frz_fail(FRZ_ERR_INVALID_ARG, "bad typo mode %d", pat.typo_mode);
+    }
+#undef FRZ_PFL_LAUNCH
+    FRZ_CUDA_TRY(cudaGetLastError());
+    if (st) st->launches++;
+    return FRZ_OK;
+}
 
 frz_status frz_launch_prefilter(const FrzCorpusView& cv, const FrzPatternDev& pat, const uint32_t* cand_bitmap,
                                 FrzWorkspace& ws, cudaStream_t stream, FrzLaunchStats* st) {
