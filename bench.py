@@ -128,8 +128,14 @@ def run_reference(args):
     data, off = synth.generate(WORKLOAD["needle"], sample, WORKLOAD["mu"], WORKLOAD["max_len"], WORKLOAD["seed"])
     lanes = args.lanes or detect_lanes(cfg)
     cfg = cfg.with_(emulate_lanes=lanes)
-    for _ in range(args.warmup):
-        cb.match_list_parallel([WORKLOAD["needle"]], cfg, data, off, threads)
+    # be generous to the CPU: the reference's final k-way merge is single-threaded, so more threads is not
+    # always faster — use the thread count (all / half / quarter of the host threads) that runs fastest
+    best = None
+    for cand_threads in sorted({threads, max(1, threads // 2), max(1, threads // 4)}, reverse=True):
+        dt, _ = cb.timed([WORKLOAD["needle"]], cfg, data, off, cand_threads, repeats=max(1, args.warmup))
+        if best is None or dt < best[0]:
+            best = (dt, cand_threads)
+    threads = best[1]
     t0 = time.perf_counter()
     for _ in range(args.steps):
         res = cb.match_list_parallel([WORKLOAD["needle"]], cfg, data, off, threads)
@@ -307,8 +313,15 @@ def run_ours(args):
         pf_ms = stage_ms[0] / args.steps
         alg_bytes = int(corpus.total_bytes + 8 * n + 8 * n_matches / world)
         achieved = alg_bytes / (pf_ms / 1e3) / 1e9 if pf_ms > 0 else None
-        roofline = {"bound": "hbm", "kernel": "k_prefilter (+ tile scan)", "achieved": achieved, "peak": peak,
-                    "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "traffic": None,
+        traffic = None
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            if (WORKLOAD["needle"], WORKLOAD["max_typos"], WORKLOAD["mu"], WORKLOAD["max_len"], n) == ("deadbeef", 1, 48, 64, 10_000_000):
+                traffic = int(tj["dram_bytes_read"] + tj["dram_bytes_write"])   # from the committed ncu capture
+        except Exception:
+            pass
+        roofline = {"bound": "hbm", "kernel": "k_prefilter (+ tile rank/scan)", "achieved": achieved, "peak": peak,
+                    "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "traffic": traffic,
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
                     "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": pf_ms,
                     "stage_ms_per_step": {"prefilter": pf_ms, "smith_waterman": stage_ms[1] / args.steps,
@@ -320,9 +333,15 @@ def run_ours(args):
             sample = args.cpu_sample or n
             ccfg = cfg.with_(emulate_lanes=info["prefilter_lanes"])
             sd, so = data_np[: int(off_np[sample])], off_np[: sample + 1]
-            dt, _ = cb.timed([WORKLOAD["needle"]], ccfg, sd, so, threads, repeats=2)
+            best = None
+            for cand_threads in sorted({threads, max(1, threads // 2), max(1, threads // 4)}, reverse=True):
+                dt_c, _ = cb.timed([WORKLOAD["needle"]], ccfg, sd, so, cand_threads, repeats=2)
+                if best is None or dt_c < best[0]:
+                    best = (dt_c, cand_threads)
+            dt, threads = best
             cpu = {"value": sample / dt, "unit": "haystacks/s", "cores": threads, "kind": "port",
-                   "sample": f"first {sample} haystacks of the same list, best of 2; {cb.describe()}, threaded like "
+                   "sample": f"first {sample} haystacks of the same list, best of 2 at the fastest of all/half/quarter "
+                             f"of the {cb.host_threads()} host threads; {cb.describe()}, threaded like "
                              f"match_list_parallel; emulating the {info['prefilter_lanes']}-lane reference backend"}
         line = {"metric": "haystacks/sec", "value": value, "unit": "haystacks/s", "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",

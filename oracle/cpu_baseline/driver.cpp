@@ -4,7 +4,6 @@
 
 #include <algorithm>
 #include <cstring>
-#include <queue>
 #include <thread>
 
 namespace {
@@ -93,7 +92,8 @@ extern "C" uint64_t frzb_match_list_parallel(const frz_pattern* patterns, size_t
     for (size_t ti = 1; ti < t; ti++) ths.emplace_back(body, ti);
     body(0);
     for (auto& th : ths) th.join();
-    // k-way merge (src/k_merge.rs:90-131) with a binary heap of run cursors
+    // k-way merge (src/k_merge.rs:90-131): binary heap of run cursors that carry their head Match inline,
+    // advance-in-place + sift-down, and a bulk copy once a single run remains — as in the reference
     auto less = [&](const frz_match& a, const frz_match& b) {
         if (by_score) {
             if (a.score != b.score) return a.score > b.score;
@@ -101,16 +101,34 @@ extern "C" uint64_t frzb_match_list_parallel(const frz_pattern* patterns, size_t
         }
         return reversed ? a.index > b.index : a.index < b.index;
     };
-    struct Cur { size_t run, pos; };
-    auto cmp = [&](const Cur& x, const Cur& y) { return less(runs[y.run][y.pos], runs[x.run][x.pos]); };
-    std::priority_queue<Cur, std::vector<Cur>, decltype(cmp)> heap(cmp);
-    for (size_t r = 0; r < t; r++) if (!runs[r].empty()) heap.push({r, 0});
+    struct Cur { size_t run, pos; frz_match head; };
+    std::vector<Cur> heap;
+    heap.reserve(t);
+    for (size_t r = 0; r < t; r++) if (!runs[r].empty()) heap.push_back({r, 0, runs[r][0]});
+    auto sift_down = [&](size_t index) {
+        size_t pos = index, child = 2 * pos + 1;
+        while (child + 1 < heap.size()) {
+            child += less(heap[child + 1].head, heap[child].head) ? 1 : 0;
+            if (!less(heap[child].head, heap[pos].head)) return;
+            std::swap(heap[pos], heap[child]);
+            pos = child;
+            child = 2 * pos + 1;
+        }
+        if (child < heap.size() && less(heap[child].head, heap[pos].head)) std::swap(heap[pos], heap[child]);
+    };
+    for (size_t i = heap.size() / 2; i-- > 0;) sift_down(i);
     uint64_t cnt = 0;
-    while (!heap.empty()) {
-        Cur c = heap.top(); heap.pop();
-        if (cnt < cap) out[cnt] = runs[c.run][c.pos];
+    while (heap.size() > 1) {
+        if (cnt < cap) out[cnt] = heap[0].head;
         cnt++;
-        if (c.pos + 1 < runs[c.run].size()) heap.push({c.run, c.pos + 1});
+        const size_t run = heap[0].run, next = heap[0].pos + 1;
+        if (next < runs[run].size()) { heap[0].pos = next; heap[0].head = runs[run][next]; }
+        else { heap[0] = heap.back(); heap.pop_back(); }
+        sift_down(0);
+    }
+    if (!heap.empty()) {
+        const auto& r = runs[heap[0].run];
+        for (size_t i = heap[0].pos; i < r.size(); i++) { if (cnt < cap) out[cnt] = r[i]; cnt++; }
     }
     return cnt;
 }
