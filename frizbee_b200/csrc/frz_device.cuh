@@ -83,6 +83,10 @@ struct FrzPatternDev {
     int32_t n_distinct;                 // 0 → too many distinct bytes, use the scanning fallback
     uint8_t dc_om[16], dc_tg[16];       // probe of distinct class d
     uint8_t cid[FRZ_MAX_NEEDLE];        // needle index → distinct class
+    // phase-A probes (host-chosen necessary condition): up to 3 byte classes, combined with AND or OR
+    int32_t probe_n;                    // 0 → no probing (every length-gated haystack is a candidate)
+    int32_t probe_and;                  // 1: all probed classes must occur; 0: at least one must
+    uint8_t probe_om[4], probe_tg[4];
     // untruncated scoring for the literal matcher / greedy fallback (u16 arithmetic)
     int32_t raw_match, raw_mismatch, raw_gap_open, raw_gap_extend, raw_prefix, raw_cap, raw_case, raw_delim;
 };

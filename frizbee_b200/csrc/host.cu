@@ -500,6 +500,30 @@ frz_status compile_pattern(const OwnedPattern& src, const frz_config& mcfg, bool
         if (max_typos > 15 && (size_t)max_typos < n)
             return frz_fail(FRZ_ERR_UNSUPPORTED, "max_typos > 15 is not on the GPU path yet");
     }
+    {   // Phase-A necessary condition.  A byte class that fills more than k needle positions must occur in the
+        // haystack (k deletions cannot remove it): probe up to two such classes, rarest first, with AND.
+        // If no class is that frequent, fall back to "one of needle[0..k] occurs" (no path of the reference's
+        // state machine can start otherwise).
+        d.probe_n = 0; d.probe_and = 0;
+        const int k = max_typos;
+        if (k >= 0 && k <= 2 && (int)n > k && d.n_distinct > 0) {
+            int cnt[16] = {0};
+            for (size_t i = 0; i < n; i++) cnt[d.cid[i]]++;
+            int order[16], no = 0;
+            for (int c2 = 0; c2 < d.n_distinct; c2++) if (cnt[c2] > k) order[no++] = c2;
+            std::sort(order, order + no, [&](int a, int b) { return cnt[a] != cnt[b] ? cnt[a] < cnt[b] : a < b; });
+            const int want = k == 0 ? 1 : 2;
+            if (no > 0) {
+                d.probe_and = 1;
+                for (int j = 0; j < no && j < want; j++) { d.probe_om[j] = d.dc_om[order[j]]; d.probe_tg[j] = d.dc_tg[order[j]]; d.probe_n++; }
+            } else {
+                d.probe_and = 0;
+                for (int j = 0; j <= k && j < 3; j++) { d.probe_om[j] = d.om[j]; d.probe_tg[j] = d.tg[j]; d.probe_n++; }
+            }
+        } else if (k >= 0 && k <= 2 && (int)n > k) {   // too many distinct classes for the table: first-bytes rule
+            for (int j = 0; j <= k && j < 3; j++) { d.probe_om[j] = d.om[j]; d.probe_tg[j] = d.tg[j]; d.probe_n++; }
+        }
+    }
     d.max_typos = max_typos < 0 ? 0 : std::min(max_typos, (int)n);  // budget >= needle length matches everything
     // min_haystack_len (src/matcher/algo.rs:62-65)
     d.min_hay_len = max_typos >= 0 ? (int)(nchars > (size_t)max_typos ? nchars - max_typos : 0) : 0;

@@ -610,12 +610,12 @@ __global__ void __launch_bounds__(kThreads) k_prefilter(const FrzCorpusView cv, 
     if (threadIdx.x < FRZ_MAX_NEEDLE) cid_s[threadIdx.x] = pat.cid[threadIdx.x];
     __syncthreads();
 
-    const uint32_t om0 = splat4(pat.om[0]), tg0 = splat4(pat.tg[0]);
-    const uint32_t om1 = splat4(pat.om[pat.n > 1 ? 1 : 0]), tg1 = splat4(pat.tg[pat.n > 1 ? 1 : 0]);
-    const uint32_t om2 = splat4(pat.om[pat.n > 2 ? 2 : 0]), tg2 = splat4(pat.tg[pat.n > 2 ? 2 : 0]);
-    const bool probe = (MODE == FRZ_T_0 || MODE == FRZ_T_1 || MODE == FRZ_T_2);
-    // needle no longer than the typo budget matches everything (ascii_typos.rs:18,116)
-    const bool trivially = (MODE == FRZ_T_1 && pat.n <= 1) || (MODE == FRZ_T_2 && pat.n <= 2);
+    // host-chosen probes (compile_pattern): NP byte classes, all (AND) or any (OR) of which must occur
+    const uint32_t om0 = splat4(pat.probe_om[0]), tg0 = splat4(pat.probe_tg[0]);
+    const uint32_t om1 = splat4(pat.probe_om[1]), tg1 = splat4(pat.probe_tg[1]);
+    const uint32_t om2 = splat4(pat.probe_om[2]), tg2 = splat4(pat.probe_tg[2]);
+    const int NP = pat.probe_n;
+    const bool probe = (MODE == FRZ_T_0 || MODE == FRZ_T_1 || MODE == FRZ_T_2) && NP > 0;
 
     const uint32_t total_groups = cv.n_tiles * FRZ_GROUPS_PER_TILE;
     const uint32_t n_warps = gridDim.x * kWarps;
@@ -670,7 +670,7 @@ __global__ void __launch_bounds__(kThreads) k_prefilter(const FrzCorpusView cv, 
             const uint64_t idx = (uint64_t)tile * FRZ_TILE + (meta & (FRZ_TILE - 1));
             pass = pass && ((cand_bitmap[idx >> 5] >> (idx & 31)) & 1);
         }
-        uint32_t acc = 0;
+        uint32_t acc = 0, acc1 = 0, acc2 = 0;
         const bool in_slice = gd.gunits <= kSliceUnits;
         const bool skip_group = gd.gunits == 0 && MODE != FRZ_T_NONE && MODE != FRZ_T_LITERAL && pat.min_hay_len > 0;
         if (probe && !skip_group) {
@@ -683,8 +683,8 @@ __global__ void __launch_bounds__(kThreads) k_prefilter(const FrzCorpusView cv, 
                     for (int j = 0; j < 4; j++) {
                         uint32_t x = (w[j] | om0) ^ tg0;
                         acc |= (x - 0x01010101u) & ~x;
-                        if (MODE >= FRZ_T_1) { x = (w[j] | om1) ^ tg1; acc |= (x - 0x01010101u) & ~x; }
-                        if (MODE >= FRZ_T_2) { x = (w[j] | om2) ^ tg2; acc |= (x - 0x01010101u) & ~x; }
+                        if (MODE >= FRZ_T_1 && NP > 1) { x = (w[j] | om1) ^ tg1; acc1 |= (x - 0x01010101u) & ~x; }
+                        if (MODE >= FRZ_T_2 && NP > 2) { x = (w[j] | om2) ^ tg2; acc2 |= (x - 0x01010101u) & ~x; }
                     }
                 }
             } else {
@@ -696,12 +696,14 @@ __global__ void __launch_bounds__(kThreads) k_prefilter(const FrzCorpusView cv, 
                     for (int j = 0; j < 4; j++) {
                         uint32_t x = (w[j] | om0) ^ tg0;
                         acc |= (x - 0x01010101u) & ~x;
-                        if (MODE >= FRZ_T_1) { x = (w[j] | om1) ^ tg1; acc |= (x - 0x01010101u) & ~x; }
-                        if (MODE >= FRZ_T_2) { x = (w[j] | om2) ^ tg2; acc |= (x - 0x01010101u) & ~x; }
+                        if (MODE >= FRZ_T_1 && NP > 1) { x = (w[j] | om1) ^ tg1; acc1 |= (x - 0x01010101u) & ~x; }
+                        if (MODE >= FRZ_T_2 && NP > 2) { x = (w[j] | om2) ^ tg2; acc2 |= (x - 0x01010101u) & ~x; }
                     }
                 }
             }
-            pass = pass && (trivially || (acc & 0x80808080u) != 0);
+            const bool h0 = (acc & 0x80808080u) != 0, h1 = (acc1 & 0x80808080u) != 0, h2 = (acc2 & 0x80808080u) != 0;
+            const bool hit = pat.probe_and ? (h0 && (NP < 2 || h1) && (NP < 3 || h2)) : (h0 || (NP > 1 && h1) || (NP > 2 && h2));
+            pass = pass && hit;
         }
         if (skip_group) pass = false;
         const uint32_t ballot = __ballot_sync(0xffffffffu, pass);
