@@ -66,6 +66,8 @@ def lib():
     L.frz_query_destroy.argtypes = [vp]
     L.frz_query_destroy.restype = None
     L.frz_corpus_create.argtypes = [vp, vp, u64, C.c_int, C.POINTER(vp)]
+    L.frz_corpus_create_arrow.argtypes = [vp, vp, C.c_int, u64, C.c_int, C.POINTER(vp)]
+    L.frz_corpus_append.argtypes = [vp, vp, vp, C.c_int, u64]
     L.frz_corpus_create_ptrs.argtypes = [vp, vp, u64, C.c_int, C.POINTER(vp)]
     L.frz_corpus_create_device.argtypes = [vp, vp, u64, u64, C.c_int, vp, C.POINTER(vp)]
     for fn in (L.frz_corpus_len, L.frz_corpus_total_bytes, L.frz_corpus_device_bytes):
@@ -86,6 +88,7 @@ def lib():
     L.frz_match_list.argtypes = [vp, vp, vp, u64, C.POINTER(u64)]
     L.frz_match_list_into.argtypes = [vp, vp, u32, vp, u64, C.POINTER(u64)]
     L.frz_match_list_host.argtypes = [vp, vp, vp, u64, C.c_int, vp, u64, C.POINTER(u64)]
+    L.frz_match_list_host_arrow.argtypes = [vp, vp, vp, C.c_int, u64, C.c_int, vp, u64, C.POINTER(u64)]
     L.frz_match_shard_device.argtypes = [vp, vp, u32, vp, u64, vp, vp]
     L.frz_merge_runs_device.argtypes = [vp, u64, vp, C.c_int, C.c_uint8, u32, vp, C.c_int, vp]
     L.frz_matcher_score_bound.restype = u32
@@ -98,6 +101,14 @@ def lib():
 def _check(status: int):
     if status != 0:
         raise FrizbeeError(status, lib().frz_last_error().decode("utf-8", "replace"))
+
+
+def _arrow_offsets(offsets: np.ndarray):
+    """(contiguous offsets, width in bytes): 32-bit integer arrays stay 32-bit (Arrow Utf8), the rest become uint64."""
+    offsets = np.asarray(offsets)
+    if offsets.dtype in (np.dtype(np.uint32), np.dtype(np.int32)):
+        return np.ascontiguousarray(offsets), 4
+    return np.ascontiguousarray(offsets, dtype=np.uint64), 8
 
 
 def _b(x) -> bytes:
@@ -165,11 +176,13 @@ class Corpus:
 
     @classmethod
     def from_arrow(cls, data: np.ndarray, offsets: np.ndarray, device: int = 0) -> "Corpus":
+        """Arrow value bytes + offsets (uint32/int32 = Utf8, otherwise 64-bit = LargeUtf8; offsets[0] may be > 0)."""
         data = np.ascontiguousarray(data, dtype=np.uint8)
-        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        offsets, width = _arrow_offsets(offsets)
         h = C.c_void_p()
         n = len(offsets) - 1
-        _check(lib().frz_corpus_create(data.ctypes.data if data.size else None, offsets.ctypes.data, n, device, C.byref(h)))
+        _check(lib().frz_corpus_create_arrow(data.ctypes.data if data.size else None, offsets.ctypes.data, width, n, device,
+                                             C.byref(h)))
         return cls(h, n)
 
     @classmethod
@@ -178,6 +191,19 @@ class Corpus:
         h = C.c_void_p()
         _check(lib().frz_corpus_create_device(d_bytes_ptr, d_offsets_ptr, n, total_bytes, device, stream, C.byref(h)))
         return cls(h, n)
+
+    def append(self, data: np.ndarray, offsets: np.ndarray) -> "Corpus":
+        """Appends haystacks (Arrow value bytes + offsets); their indices continue at len(self)."""
+        data = np.ascontiguousarray(data, dtype=np.uint8)
+        offsets, width = _arrow_offsets(offsets)
+        n_new = len(offsets) - 1
+        _check(lib().frz_corpus_append(self._h, data.ctypes.data if data.size else None, offsets.ctypes.data, width, n_new))
+        self.n += n_new
+        return self
+
+    def append_list(self, haystacks: Sequence) -> "Corpus":
+        data, offsets = pack_host(haystacks)
+        return self.append(data, offsets)
 
     def __len__(self):
         return self.n
@@ -297,8 +323,12 @@ class Matcher:
         if out is None:
             out = np.empty(max(1, n_items), dtype=MATCH_DTYPE)
         n = C.c_uint64()
-        _check(lib().frz_match_list_host(self._h, data.ctypes.data if data.size else None, offsets.ctypes.data, n_items,
-                                         device, out.ctypes.data, len(out), C.byref(n)))
+        if offsets.dtype.itemsize == 4 and offsets.flags.c_contiguous:
+            width = 4
+        else:
+            offsets, width = _arrow_offsets(offsets)
+        _check(lib().frz_match_list_host_arrow(self._h, data.ctypes.data if data.size else None, offsets.ctypes.data, width,
+                                               n_items, device, out.ctypes.data, len(out), C.byref(n)))
         return out[: n.value]
 
     def close(self):

@@ -9,7 +9,7 @@
 //     lane gets its bytes 16-byte aligned in registers (no alignment fix-ups, no shared memory);
 //   * a group holds `gunits` units per lane = the longest haystack of the group (zero padded);
 //     after bucketing almost every group is uniform, so padding is the 16-byte rounding only.
-//   Per slot: one u32 of metadata (len << 10 | index-within-tile).  Per group: 8 bytes.
+//   Per slot: one u32 of metadata (len << 10 | index-within-tile).  Per group: 16 bytes.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -24,8 +24,9 @@
 #define FRZ_MAX_NEEDLE 64      // needle bytes handled by the kernels (longer → FRZ_ERR_UNSUPPORTED)
 #define FRZ_SW_MAX_WINDOW 1024 // src/smith_waterman/algo/mod.rs:18 (MAX_HAYSTACK_LEN)
 
-struct FrzGroupDesc {
-    uint32_t unit_off;  // first unit of the group, in 16-byte units from the tile's data base
+struct __align__(16) FrzGroupDesc {
+    uint64_t abs_off;   // first unit of the group, in 16-byte units from the start of the packed data
+    uint32_t unit_off;  // same, relative to the tile's data base
     uint32_t gunits;    // units per lane in this group
 };
 
@@ -123,6 +124,6 @@ __device__ __forceinline__ uint32_t frz_lane() { return threadIdx.x & 31; }
 
 // address of unit k of (tile, slot)
 __device__ __forceinline__ const uint4* frz_unit_ptr(const FrzCorpusView& cv, uint32_t tile, uint32_t slot, uint32_t k) {
-    FrzGroupDesc gd = cv.groups[tile * FRZ_GROUPS_PER_TILE + (slot >> 5)];
-    return cv.data + cv.tile_base[tile] + gd.unit_off + (uint64_t)k * FRZ_GROUP + (slot & 31);
+    const FrzGroupDesc gd = cv.groups[tile * FRZ_GROUPS_PER_TILE + (slot >> 5)];
+    return cv.data + gd.abs_off + (uint64_t)k * FRZ_GROUP + (slot & 31);
 }

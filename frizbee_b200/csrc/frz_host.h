@@ -62,13 +62,33 @@ struct FrzCorpusStorage {
     }
 };
 
+struct FrzIngest;
 struct frz_corpus {
     FrzCorpusStorage st;
+    FrzIngest* ingest = nullptr;   // created by the first frz_corpus_append, kept for the next ones
+};
+
+// Staging arena + copy stream of the streamed ingest (pack.cu): grow-only, reused across calls.
+struct FrzIngest {
+    static constexpr int kMaxChunks = 32;
+    static constexpr uint64_t kMinChunkBytes = 8ull << 20;
+    uint8_t* d_bytes = nullptr;
+    uint64_t bytes_cap = 0;
+    void* d_offsets = nullptr;
+    uint64_t offsets_cap = 0;             // bytes
+    cudaStream_t copy_stream = nullptr;   // non-blocking: overlaps the (legacy default) compute stream
+    cudaEvent_t ev[kMaxChunks + 1] = {};  // [c] chunk c landed; [kMaxChunks] offsets landed / arena free
+    frz_status reserve(uint64_t bytes, uint64_t offset_bytes);
+    void release();
 };
 
 // pack.cu
-frz_status frz_pack_corpus_device(const uint8_t* d_bytes, const uint64_t* d_offsets, uint64_t n, uint64_t total_bytes,
+frz_status frz_pack_corpus_device(const uint8_t* d_bytes, const void* d_offsets, int offset_width, uint64_t n, uint64_t total_bytes,
                                   cudaStream_t stream, FrzCorpusStorage* out);
+frz_status frz_append_host(FrzIngest& ing, const uint8_t* h_bytes, const void* h_offsets, int offset_width, uint64_t n_new,
+                           cudaStream_t stream, FrzCorpusStorage* st);
+frz_status frz_ingest_host(FrzIngest& ing, const uint8_t* h_bytes, const void* h_offsets, int offset_width, uint64_t n,
+                           cudaStream_t stream, FrzCorpusStorage* out);
 
 // Per-matcher device workspace (grown on demand, reused across calls).
 struct FrzWorkspace {

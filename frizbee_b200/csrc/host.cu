@@ -228,34 +228,48 @@ extern "C" frz_status frz_corpus_create_device(const uint8_t* d_bytes, const uin
     FRZ_TRY(ensure_device(device));
     auto c = std::make_unique<frz_corpus>();
     c->st.device = device;
-    frz_status s = frz_pack_corpus_device(d_bytes, d_offsets, n, total_bytes, (cudaStream_t)stream, &c->st);
+    frz_status s = frz_pack_corpus_device(d_bytes, d_offsets, 8, n, total_bytes, (cudaStream_t)stream, &c->st);
+    if (s != FRZ_OK) { c->st.release(); return s; }
+    *out = c.release();
+    return FRZ_OK;
+}
+
+// Host Arrow buffers (Utf8: 32-bit offsets, LargeUtf8: 64-bit; a sliced array may start at offsets[0] != 0).
+extern "C" frz_status frz_corpus_create_arrow(const uint8_t* bytes, const void* offsets, int offset_width, uint64_t n, int device,
+                                              frz_corpus** out) {
+    if (!out || !offsets) return frz_fail(FRZ_ERR_INVALID_ARG, "null argument");
+    if (offset_width != 4 && offset_width != 8) return frz_fail(FRZ_ERR_INVALID_ARG, "offset_width must be 4 or 8");
+    if (n > 0xFFFFFFFFull) return frz_fail(FRZ_ERR_TOO_MANY_ITEMS, "too many items in haystack: %llu", (unsigned long long)n);
+    FRZ_TRY(ensure_device(device));
+    auto c = std::make_unique<frz_corpus>();
+    c->st.device = device;
+    FrzIngest ing;
+    cudaStream_t stream = nullptr;
+    frz_status s = frz_ingest_host(ing, bytes, offsets, offset_width, n, stream, &c->st);
+    if (s == FRZ_OK && cudaStreamSynchronize(stream) != cudaSuccess)
+        s = frz_fail(FRZ_ERR_CUDA, "pack failed: %s", cudaGetErrorString(cudaGetLastError()));
+    ing.release();
     if (s != FRZ_OK) { c->st.release(); return s; }
     *out = c.release();
     return FRZ_OK;
 }
 
 extern "C" frz_status frz_corpus_create(const uint8_t* bytes, const uint64_t* offsets, uint64_t n, int device, frz_corpus** out) {
-    if (!out || !offsets) return frz_fail(FRZ_ERR_INVALID_ARG, "null argument");
-    if (n > 0xFFFFFFFFull) return frz_fail(FRZ_ERR_TOO_MANY_ITEMS, "too many items in haystack: %llu", (unsigned long long)n);
-    FRZ_TRY(ensure_device(device));
-    const uint64_t total = offsets[n] - offsets[0];
-    uint8_t* d_bytes = nullptr;
-    uint64_t* d_off = nullptr;
+    return frz_corpus_create_arrow(bytes, offsets, 8, n, device, out);
+}
+
+// Incremental ingestion: the new haystacks get indices [len, len + n_new).  Synchronous; must not overlap a match
+// call on the same corpus.
+extern "C" frz_status frz_corpus_append(frz_corpus* c, const uint8_t* bytes, const void* offsets, int offset_width, uint64_t n_new) {
+    if (!c || (n_new && !offsets)) return frz_fail(FRZ_ERR_INVALID_ARG, "null argument");
+    if (offset_width != 4 && offset_width != 8) return frz_fail(FRZ_ERR_INVALID_ARG, "offset_width must be 4 or 8");
+    if (n_new == 0) return FRZ_OK;
+    FRZ_TRY(ensure_device(c->st.device));
+    if (!c->ingest) c->ingest = new FrzIngest();
     cudaStream_t stream = nullptr;
-    FRZ_CUDA_TRY(cudaMalloc(&d_bytes, total + 16));
-    if (cudaMalloc(&d_off, (n + 1) * sizeof(uint64_t)) != cudaSuccess) { cudaFree(d_bytes); return frz_fail(FRZ_ERR_OOM, "offsets alloc"); }
-    frz_status s = FRZ_OK;
-    do {
-        if (total && cudaMemcpyAsync(d_bytes, bytes + offsets[0], total, cudaMemcpyHostToDevice, stream) != cudaSuccess) { s = frz_fail(FRZ_ERR_CUDA, "H2D bytes"); break; }
-        if (cudaMemcpyAsync(d_off, offsets, (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, stream) != cudaSuccess) { s = frz_fail(FRZ_ERR_CUDA, "H2D offsets"); break; }
-        // offsets are rebased on device by the plan/copy kernels via (offsets[i] - offsets[0]) only if needed
-        if (offsets[0] != 0) { s = frz_fail(FRZ_ERR_INVALID_ARG, "offsets[0] must be 0"); break; }
-        s = frz_corpus_create_device(d_bytes, d_off, n, total, device, stream, out);
-        if (s == FRZ_OK && cudaStreamSynchronize(stream) != cudaSuccess) s = frz_fail(FRZ_ERR_CUDA, "pack failed: %s", cudaGetErrorString(cudaGetLastError()));
-    } while (0);
-    cudaFree(d_bytes);
-    cudaFree(d_off);
-    return s;
+    FRZ_TRY(frz_append_host(*c->ingest, bytes, offsets, offset_width, n_new, stream, &c->st));
+    FRZ_CUDA_TRY(cudaStreamSynchronize(stream));
+    return FRZ_OK;
 }
 
 extern "C" frz_status frz_corpus_create_ptrs(const uint8_t* const* ptrs, const uint32_t* lens, uint64_t n, int device,
@@ -274,13 +288,14 @@ extern "C" uint64_t frz_corpus_total_bytes(const frz_corpus* c) { return c ? c->
 extern "C" uint64_t frz_corpus_device_bytes(const frz_corpus* c) {
     if (!c) return 0;
     const auto& s = c->st;
-    return (s.total_units + 1) * 16 + (uint64_t)s.n_tiles * (8 + FRZ_GROUPS_PER_TILE * 8 + FRZ_TILE * 6);
+    return (s.total_units + 1) * 16 + (uint64_t)s.n_tiles * (8 + FRZ_GROUPS_PER_TILE * 16 + FRZ_TILE * 6);
 }
 extern "C" int frz_corpus_device(const frz_corpus* c) { return c ? c->st.device : -1; }
 extern "C" void frz_corpus_destroy(frz_corpus* c) {
     if (!c) return;
     cudaSetDevice(c->st.device);
     c->st.release();
+    if (c->ingest) { c->ingest->release(); delete c->ingest; }
     delete c;
 }
 
@@ -555,10 +570,7 @@ struct frz_matcher {
     std::vector<Compiled> compiled;   // build_patterns: patterns with non-empty needles
     FrzWorkspace ws;
     // end-to-end (host in / host out) staging arena, grow-only: raw Arrow buffers + a reusable packed corpus
-    uint8_t* e2e_bytes = nullptr;
-    uint64_t e2e_bytes_cap = 0;
-    uint64_t* e2e_offsets = nullptr;
-    uint64_t e2e_offsets_cap = 0;
+    FrzIngest e2e_ingest;     // staging arena + copy stream of frz_match_list_host*
     frz_corpus e2e_corpus;
     FrzMatchDev* multi_a = nullptr;   // multi-pattern candidate ping-pong
     FrzMatchDev* multi_b = nullptr;
@@ -568,9 +580,9 @@ struct frz_matcher {
     bool timings_pending = false;
     ~frz_matcher() {
         if (ws.device >= 0) { cudaSetDevice(ws.device); cudaFree(multi_a); cudaFree(multi_b); }
-        if (e2e_bytes || e2e_offsets || e2e_corpus.st.data) {
+        if (e2e_ingest.d_bytes || e2e_ingest.copy_stream || e2e_corpus.st.data) {
             cudaSetDevice(e2e_corpus.st.device);
-            cudaFree(e2e_bytes); cudaFree(e2e_offsets);
+            e2e_ingest.release();
             e2e_corpus.st.release();
         }
         ws.release();
@@ -1078,40 +1090,29 @@ extern "C" frz_status frz_match_list_into(frz_matcher* m, const frz_corpus* corp
     return s;
 }
 
-extern "C" frz_status frz_match_list_host(frz_matcher* m, const uint8_t* bytes, const uint64_t* offsets, uint64_t n, int device,
-                                          frz_match* out, uint64_t cap, uint64_t* n_out) {
+// End to end from host Arrow buffers: streamed H2D + pack (pack.cu: ingest_host_t), match, D2H of the matches.
+extern "C" frz_status frz_match_list_host_arrow(frz_matcher* m, const uint8_t* bytes, const void* offsets, int offset_width, uint64_t n,
+                                                int device, frz_match* out, uint64_t cap, uint64_t* n_out) {
     if (!m || !offsets) return frz_fail(FRZ_ERR_INVALID_ARG, "null argument");
+    if (offset_width != 4 && offset_width != 8) return frz_fail(FRZ_ERR_INVALID_ARG, "offset_width must be 4 or 8");
     if (n > 0xFFFFFFFFull) return frz_fail(FRZ_ERR_TOO_MANY_ITEMS, "too many items in haystack: %llu", (unsigned long long)n);
-    if (offsets[0] != 0) return frz_fail(FRZ_ERR_INVALID_ARG, "offsets[0] must be 0");
     FRZ_TRY(ensure_device(device));
     cudaStream_t stream = nullptr;
-    const uint64_t total = offsets[n];
     frz_corpus& c = m->e2e_corpus;
-    if (c.st.device != device && (m->e2e_bytes || c.st.data)) {  // arena lives on another device: drop it
+    if (c.st.device != device && (m->e2e_ingest.d_bytes || m->e2e_ingest.copy_stream || c.st.data)) {  // arena lives on another device
         cudaSetDevice(c.st.device);
-        cudaFree(m->e2e_bytes); cudaFree(m->e2e_offsets);
-        m->e2e_bytes = nullptr; m->e2e_offsets = nullptr; m->e2e_bytes_cap = m->e2e_offsets_cap = 0;
+        m->e2e_ingest.release();
         c.st.release();
         FRZ_CUDA_TRY(cudaSetDevice(device));
     }
     c.st.device = device;
-    if (m->e2e_bytes_cap < total + 16) {
-        cudaFree(m->e2e_bytes); m->e2e_bytes = nullptr; m->e2e_bytes_cap = 0;
-        const uint64_t want = total + total / 16 + 4096;
-        FRZ_CUDA_TRY(cudaMalloc(&m->e2e_bytes, want));
-        m->e2e_bytes_cap = want;
-    }
-    if (m->e2e_offsets_cap < n + 1) {
-        cudaFree(m->e2e_offsets); m->e2e_offsets = nullptr; m->e2e_offsets_cap = 0;
-        const uint64_t want = n + n / 16 + 1024;
-        FRZ_CUDA_TRY(cudaMalloc(&m->e2e_offsets, want * sizeof(uint64_t)));
-        m->e2e_offsets_cap = want;
-    }
-    // H2D of the caller's Arrow buffers (fast path: pinned host memory), pack, match, D2H of the matches
-    if (total) FRZ_CUDA_TRY(cudaMemcpyAsync(m->e2e_bytes, bytes, total, cudaMemcpyHostToDevice, stream));
-    FRZ_CUDA_TRY(cudaMemcpyAsync(m->e2e_offsets, offsets, (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, stream));
-    FRZ_TRY(frz_pack_corpus_device(m->e2e_bytes, m->e2e_offsets, n, total, stream, &c.st));
+    FRZ_TRY(frz_ingest_host(m->e2e_ingest, bytes, offsets, offset_width, n, stream, &c.st));
     return frz_match_list(m, &c, out, cap, n_out);
+}
+
+extern "C" frz_status frz_match_list_host(frz_matcher* m, const uint8_t* bytes, const uint64_t* offsets, uint64_t n, int device,
+                                          frz_match* out, uint64_t cap, uint64_t* n_out) {
+    return frz_match_list_host_arrow(m, bytes, offsets, 8, n, device, out, cap, n_out);
 }
 
 extern "C" frz_status frz_match_shard_device(frz_matcher* m, const frz_corpus* shard, uint32_t index_offset, frz_match* d_out,

@@ -506,7 +506,7 @@ __device__ __forceinline__ bool masks_k1(const uint4* base, const FrzPatternDev&
     return state == 1;
 }
 
-constexpr int kQueueCap = 64;  // per-warp candidate queue (31 left over + 32 new at most)
+constexpr int kQueueCap = 128;  // per-warp candidate queue (31 left over + 2 x 32 new at most per loop trip)
 
 struct WarpQueue {
     uint32_t meta[kQueueCap];                // tile << 10 | slot
@@ -536,7 +536,7 @@ __device__ __forceinline__ void process_candidate(const FrzCorpusView& cv, const
     GlobalAcc ga{nullptr};
     if (active) {
         const FrzGroupDesc gd = cv.groups[tile * FRZ_GROUPS_PER_TILE + (slot >> 5)];
-        ga.base = cv.data + cv.tile_base[tile] + gd.unit_off + (slot & 31);
+        ga.base = cv.data + gd.abs_off + (slot & 31);
     }
     // warp-wide occurrence-mask windows (uniform code) for the 0- and 1-typo modes
     bool flat_done = false, flat_ok = false;
@@ -595,8 +595,8 @@ __device__ __forceinline__ void process_candidate(const FrzCorpusView& cv, const
 // Warp-autonomous, barrier-free: every warp strides over groups, probes (phase A), queues the
 // passing haystacks' bytes in its own shared-memory ring and, whenever 32 are queued, runs the
 // exact window on them with all lanes busy (phase B).
-template <int MODE>
-__global__ void __launch_bounds__(kThreads) k_prefilter(const FrzCorpusView cv, const __grid_constant__ FrzPatternDev pat,
+template <int MODE, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB) k_prefilter(const FrzCorpusView cv, const __grid_constant__ FrzPatternDev pat,
                                                         const uint32_t* __restrict__ cand_bitmap,
                                                         FrzSurvivor* __restrict__ surv0, FrzSurvivor* __restrict__ surv1,
                                                         FrzSurvivor* __restrict__ surv2, unsigned long long surv_cap,
@@ -617,49 +617,47 @@ __global__ void __launch_bounds__(kThreads) k_prefilter(const FrzCorpusView cv, 
     const int NP = pat.probe_n;
     const bool probe = (MODE == FRZ_T_0 || MODE == FRZ_T_1 || MODE == FRZ_T_2) && NP > 0;
 
-    const uint32_t total_groups = cv.n_tiles * FRZ_GROUPS_PER_TILE;
     const uint32_t n_warps = gridDim.x * kWarps;
     uint32_t head = 0, count = 0;  // ring state (warp-uniform)
 
     // Software pipeline (the warp has no other way to keep HBM busy at 16 warps/SM): descriptors of
-    // group i+2 and the haystack units of group i+1 are in flight while group i is probed.
+    // group i+2 and the haystack units of group i+1 are in flight while group i is probed.  The loop is
+    // unrolled by two so that the unit buffers ping-pong instead of being copied.
+    // Work order.  Inside a tile the groups are sorted by length (group 31 holds the longest haystacks), so a
+    // warp striding by a multiple of 32 would see one rank for its whole life and the SMs would be unevenly
+    // loaded.  Virtual index v enumerates rank-major (v = rank * n_tiles + tile): all warps sweep the ranks
+    // together and every warp gets the same mix of short and long groups.
     struct Desc {
         FrzGroupDesc gd;
         uint32_t meta;
-        uint64_t tb;
+        uint32_t gidx;
     };
-    auto load_desc = [&](uint32_t gidx, Desc& d) {
-        if (gidx < total_groups) {
-            d.gd = cv.groups[gidx];
-            d.meta = cv.slot_meta[(uint64_t)(gidx >> 5) * FRZ_TILE + (gidx & 31) * FRZ_GROUP + lane];
-            d.tb = cv.tile_base[gidx >> 5];
+    uint32_t gen_tile = blockIdx.x * kWarps + warp, gen_rank = 0;   // state of the (v -> group) generator
+    while (gen_tile >= cv.n_tiles) { gen_tile -= cv.n_tiles; gen_rank++; }
+    auto load_desc = [&](Desc& d) {   // descriptors of this warp's next group, in v order
+        if (gen_rank < FRZ_GROUPS_PER_TILE) {
+            const uint32_t gidx = gen_tile * FRZ_GROUPS_PER_TILE + gen_rank;
+            d.gd = cv.groups[gidx];  // one 16-byte load
+            d.meta = cv.slot_meta[(uint64_t)gen_tile * FRZ_TILE + gen_rank * FRZ_GROUP + lane];
+            d.gidx = gidx;
         } else {
-            d.gd = FrzGroupDesc{0u, 0u};
+            d.gd = FrzGroupDesc{0ull, 0u, 0u};
             d.meta = FRZ_INVALID_SLOT;
-            d.tb = 0;
+            d.gidx = 0xFFFFFFFFu;
         }
+        gen_tile += n_warps;
+        while (gen_tile >= cv.n_tiles && gen_rank < FRZ_GROUPS_PER_TILE) { gen_tile -= cv.n_tiles; gen_rank++; }
     };
     auto load_units = [&](const Desc& d, uint4 (&u)[kSliceUnits]) {
-        const uint4* gp = cv.data + d.tb + d.gd.unit_off + lane;
+        const uint4* gp = cv.data + d.gd.abs_off + lane;
 #pragma unroll
         for (int k = 0; k < kSliceUnits; k++) {
             if (k < (int)d.gd.gunits && d.gd.gunits <= kSliceUnits) u[k] = __ldg(gp + (size_t)k * FRZ_GROUP);
         }
     };
-    const uint32_t g0 = blockIdx.x * kWarps + warp;
-    Desc dc, dn;
-    uint4 u[kSliceUnits], un[kSliceUnits];
-    load_desc(g0, dc);
-    load_desc(g0 + n_warps, dn);
-    load_units(dc, u);
-
-    for (uint32_t gidx = g0; gidx < total_groups; gidx += n_warps) {
-        // ------------------------------------------------------------ pipeline: issue the next loads
-        Desc dnn;
-        load_desc(gidx + 2 * n_warps, dnn);
-        load_units(dn, un);
-        // ------------------------------------------------------------ phase A on the current group
-        const uint32_t tile = gidx >> 5, g = gidx & 31;
+    // phase A on one group whose units are in `u`
+    auto phase_a = [&](const Desc& dc, const uint4 (&u)[kSliceUnits]) {
+        const uint32_t tile = dc.gidx >> 5, g = dc.gidx & 31;
         const FrzGroupDesc gd = dc.gd;
         const uint32_t slot = g * FRZ_GROUP + lane;
         const uint32_t meta = dc.meta;
@@ -671,10 +669,10 @@ __global__ void __launch_bounds__(kThreads) k_prefilter(const FrzCorpusView cv, 
             pass = pass && ((cand_bitmap[idx >> 5] >> (idx & 31)) & 1);
         }
         uint32_t acc = 0, acc1 = 0, acc2 = 0;
-        const bool in_slice = gd.gunits <= kSliceUnits;
+        const bool in_regs = gd.gunits <= kSliceUnits;  // units prefetched into registers
         const bool skip_group = gd.gunits == 0 && MODE != FRZ_T_NONE && MODE != FRZ_T_LITERAL && pat.min_hay_len > 0;
         if (probe && !skip_group) {
-            if (in_slice) {
+            if (in_regs) {
 #pragma unroll
                 for (int k = 0; k < kSliceUnits; k++) {
                     if (k >= (int)gd.gunits) break;  // warp-uniform
@@ -688,7 +686,7 @@ __global__ void __launch_bounds__(kThreads) k_prefilter(const FrzCorpusView cv, 
                     }
                 }
             } else {
-                const uint4* gp = cv.data + dc.tb + gd.unit_off + lane;
+                const uint4* gp = cv.data + gd.abs_off + lane;
                 for (uint32_t k = 0; k < gd.gunits; k++) {
                     const uint4 v = __ldg(gp + (size_t)k * FRZ_GROUP);
                     const uint32_t w[4] = {v.x, v.y, v.z, v.w};
@@ -714,24 +712,35 @@ __global__ void __launch_bounds__(kThreads) k_prefilter(const FrzCorpusView cv, 
                 q.info[e] = len;
             }
             count += __popc(ballot);
-            __syncwarp();
-            // -------------------------------------------------------- phase B on full batches
-            if (count >= 32) {
-                process_candidate<MODE>(cv, pat, cid_s, q, (head + lane) & (kQueueCap - 1), true, lists, surv_cap, surv_bitmap, ctr);
-                head = (head + 32) & (kQueueCap - 1);
-                count -= 32;
-                __syncwarp();
-            }
         }
-        // ------------------------------------------------------------ rotate the pipeline
-        dc = dn;
-        dn = dnn;
-#pragma unroll
-        for (int k = 0; k < kSliceUnits; k++) u[k] = un[k];
-    }
-    if (count) {  // flush the partial batch
-        __syncwarp();
-        process_candidate<MODE>(cv, pat, cid_s, q, (head + lane) & (kQueueCap - 1), lane < count, lists, surv_cap, surv_bitmap, ctr);
+    };
+    Desc d0, d1, d2;
+    uint4 ua[kSliceUnits], ub[kSliceUnits];
+    load_desc(d0);
+    load_desc(d1);
+    load_units(d0, ua);
+    for (;;) {
+        const bool done = d0.gidx == 0xFFFFFFFFu;
+        if (!done) {
+            load_desc(d2);
+            load_units(d1, ub);
+            phase_a(d0, ua);
+            load_desc(d0);
+            load_units(d2, ua);
+            if (d1.gidx != 0xFFFFFFFFu) phase_a(d1, ub);
+            d1 = d0;
+            d0 = d2;
+        }
+        // -------------------------------------------------------- phase B on full batches; the partial
+        // batch is flushed through the same (single inlined) call site once the groups are exhausted
+        while (count >= 32 || (done && count > 0)) {
+            __syncwarp();
+            process_candidate<MODE>(cv, pat, cid_s, q, (head + lane) & (kQueueCap - 1), lane < count, lists, surv_cap, surv_bitmap, ctr);
+            head = (head + 32) & (kQueueCap - 1);
+            count = count > 32 ? count - 32 : 0;
+            __syncwarp();
+        }
+        if (done) break;
     }
 }
 
@@ -868,21 +877,37 @@ frz_status frz_launch_prefilter(const FrzCorpusView& cv, const FrzPatternDev& pa
     if (sms <= 0) sms = 148;
     // persistent warps: 4 blocks of 4 warps per SM (shared-memory bound), capped by the work
     const uint32_t total_groups = cv.n_tiles * FRZ_GROUPS_PER_TILE;
-    const uint32_t grid = std::max<uint32_t>(1, std::min<uint32_t>((uint32_t)sms * 4, (total_groups + kWarps - 1) / kWarps));
+    static int bps = 0;  // resident blocks per SM (experiment knob FRZ_PF_BLOCKS: 4, 5 or 6)
+    if (!bps) {
+        const char* e = getenv("FRZ_PF_BLOCKS");
+        bps = e ? atoi(e) : 4;
+        if (bps < 4 || bps > 6) bps = 4;
+    }
+    const bool tuned = pat.typo_mode == FRZ_T_0 || pat.typo_mode == FRZ_T_1;
+    const int use_bps = tuned ? bps : 4;
+    const uint32_t grid = std::max<uint32_t>(1, std::min<uint32_t>((uint32_t)sms * use_bps, (total_groups + kWarps - 1) / kWarps));
     FRZ_CUDA_TRY(cudaMemsetAsync(ws.surv_bitmap, 0, (size_t)cv.n_tiles * 32 * sizeof(uint32_t), stream));
-#define FRZ_PF_LAUNCH(MODE)                                                                                     \
+#define FRZ_PF_LAUNCH_B(MODE, MINB)                                                                             \
     do {                                                                                                        \
         static bool attr_set = false;                                                                           \
         if (!attr_set) {                                                                                        \
-            FRZ_CUDA_TRY(cudaFuncSetAttribute(k_prefilter<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            FRZ_CUDA_TRY(cudaFuncSetAttribute(k_prefilter<MODE, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            FRZ_CUDA_TRY(cudaFuncSetAttribute(k_prefilter<MODE, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, 100)); \
             attr_set = true;                                                                                    \
         }                                                                                                       \
-        k_prefilter<MODE><<<grid, kThreads, smem, stream>>>(cv, pat, cand_bitmap, ws.survivors[0], ws.survivors[1],      \
+        k_prefilter<MODE, MINB><<<grid, kThreads, smem, stream>>>(cv, pat, cand_bitmap, ws.survivors[0], ws.survivors[1], \
                                                             ws.survivors[2], ws.survivor_cap, ws.surv_bitmap, ws.counters); \
     } while (0)
+#define FRZ_PF_LAUNCH(MODE) FRZ_PF_LAUNCH_B(MODE, 4)
+#define FRZ_PF_LAUNCH_TUNED(MODE)                        \
+    do {                                                 \
+        if (use_bps == 6) FRZ_PF_LAUNCH_B(MODE, 6);      \
+        else if (use_bps == 5) FRZ_PF_LAUNCH_B(MODE, 5); \
+        else FRZ_PF_LAUNCH_B(MODE, 4);                   \
+    } while (0)
     switch (pat.typo_mode) {
-        case FRZ_T_0: FRZ_PF_LAUNCH(FRZ_T_0); break;
-        case FRZ_T_1: FRZ_PF_LAUNCH(FRZ_T_1); break;
+        case FRZ_T_0: FRZ_PF_LAUNCH_TUNED(FRZ_T_0); break;
+        case FRZ_T_1: FRZ_PF_LAUNCH_TUNED(FRZ_T_1); break;
         case FRZ_T_2: FRZ_PF_LAUNCH(FRZ_T_2); break;
         case FRZ_T_MANY: FRZ_PF_LAUNCH(FRZ_T_MANY); break;
         case FRZ_T_NONE: FRZ_PF_LAUNCH(FRZ_T_NONE); break;
@@ -890,6 +915,8 @@ frz_status frz_launch_prefilter(const FrzCorpusView& cv, const FrzPatternDev& pa
         default: return frz_fail(FRZ_ERR_INVALID_ARG, "bad typo mode %d", pat.typo_mode);
     }
 #undef FRZ_PF_LAUNCH
+#undef FRZ_PF_LAUNCH_B
+#undef FRZ_PF_LAUNCH_TUNED
     FRZ_CUDA_TRY(cudaGetLastError());
     if (st) st->launches++;
     return FRZ_OK;

@@ -147,7 +147,7 @@ FRZ_API void frz_query_destroy(frz_query* q);
 
 /* ----------------------------------------------------------------- corpus */
 
-/* A haystack list, packed and resident in HBM on one device.  Immutable after create,
+/* A haystack list, packed and resident in HBM on one device.  Read-only for matchers (only frz_corpus_append mutates it),
  * reusable across matchers/needles (the interactive use: haystacks fixed, needle changes).
  * Replaces the `&[S: AsRef<str>]` argument of Matcher::match_list (src/matcher/mod.rs:212).
  * Input is Arrow-style: `bytes` = concatenated UTF-8, `offsets[n+1]` monotone byte offsets. */
@@ -155,6 +155,17 @@ typedef struct frz_corpus frz_corpus;
 
 FRZ_API frz_status frz_corpus_create(const uint8_t* bytes, const uint64_t* offsets, uint64_t n,
                              int device, frz_corpus** out);
+/* same, for either Arrow offset width (Utf8 = 4-byte, LargeUtf8 = 8-byte offsets); a sliced array may start at
+ * offsets[0] != 0.  The value bytes are streamed host->device in tile-aligned chunks on a copy stream while
+ * the bucketing kernels run (the step before Matcher::match_list, src/matcher/mod.rs:212). */
+FRZ_API frz_status frz_corpus_create_arrow(const uint8_t* bytes, const void* offsets, int offset_width, uint64_t n,
+                                   int device, frz_corpus** out);
+/* Incremental ingestion: appends n_new haystacks (host Arrow buffers, either offset width); they take the indices
+ * [frz_corpus_len, frz_corpus_len + n_new).  Only the partial last tile is re-bucketed.  Synchronous; the caller
+ * must not run it concurrently with a match on the same corpus.  (Reference side: the caller pushing onto the
+ * Vec<String> it later passes to Matcher::match_list, src/matcher/mod.rs:212.) */
+FRZ_API frz_status frz_corpus_append(frz_corpus* c, const uint8_t* bytes, const void* offsets, int offset_width,
+                             uint64_t n_new);
 /* same, from a pointer array + lengths (the layout a Rust `&[&str]` has) */
 FRZ_API frz_status frz_corpus_create_ptrs(const uint8_t* const* ptrs, const uint32_t* lens, uint64_t n,
                                   int device, frz_corpus** out);
@@ -203,6 +214,9 @@ FRZ_API frz_status frz_match_list_into(frz_matcher* m, const frz_corpus* corpus,
  * in one call; nothing stays resident). */
 FRZ_API frz_status frz_match_list_host(frz_matcher* m, const uint8_t* bytes, const uint64_t* offsets,
                                uint64_t n, int device, frz_match* out, uint64_t cap, uint64_t* n_out);
+/* same, for either Arrow offset width (4 or 8 bytes); H2D chunks overlap the pack kernels */
+FRZ_API frz_status frz_match_list_host_arrow(frz_matcher* m, const uint8_t* bytes, const void* offsets, int offset_width,
+                                     uint64_t n, int device, frz_match* out, uint64_t cap, uint64_t* n_out);
 
 /* Device-resident variant used by the multi-GPU path (Matcher::match_list_parallel,
  * src/matcher/parallel.rs:18-89): this rank's shard → a locally ordered run left in HBM.

@@ -278,3 +278,65 @@ def test_config2_and_config4_shapes_full_prefix():
     # configs[1]: needle len 6, 1M haystacks len <= 32, k = 0; configs[3] shard shape: len <= 64, k = 0
     data, off = synth.generate("deadbe", 1_000_000, 24, 32)
     gpu_vs_oracle("deadbe", data, off, Config(max_typos=0))
+
+
+# ---------------------------------------------------------------- ingestion
+def test_arrow_ingest_widths_slices_and_streaming():
+    # Arrow Utf8 (32-bit offsets) vs LargeUtf8 (64-bit), a sliced array (offsets[0] != 0), and a list large
+    # enough for the streamed ingest to split the value bytes into several H2D chunks (>= 8 MiB each)
+    n = 600_000
+    data, off = synth.generate("deadbeef", n, 48, 64, seed=777)
+    cfg = Config(max_typos=1)
+    want = O.match_list_packed(["deadbeef"], cfg, data, off)
+    m = F.Matcher("deadbeef", cfg)
+    for offsets in (off.astype(np.uint64), off.astype(np.uint32), off.astype(np.int32)):
+        c = F.Corpus.from_arrow(data, offsets)
+        got = m.match_list_array(c)
+        assert np.array_equal(got, want), offsets.dtype
+        c.close()
+        e2e = m.match_list_host_array(data, offsets)
+        assert np.array_equal(e2e, want), offsets.dtype
+    # slice [lo, hi) of the same Arrow array: same value buffer, offsets start inside it
+    lo, hi = 123_457, 523_461
+    sl = off[lo: hi + 1]
+    want_sl = O.match_list_packed(["deadbeef"], cfg, data[int(sl[0]): int(sl[-1])], sl - sl[0])
+    for offsets in (sl.astype(np.uint64), sl.astype(np.uint32)):
+        c = F.Corpus.from_arrow(data, offsets)
+        assert len(c) == hi - lo and c.total_bytes == int(sl[-1] - sl[0])
+        assert np.array_equal(m.match_list_array(c), want_sl)
+        c.close()
+        assert np.array_equal(m.match_list_host_array(data, offsets), want_sl)
+    # the arena is reused by a second, smaller list and by an empty one
+    small = off[: 1001]
+    want_small = O.match_list_packed(["deadbeef"], cfg, data[: int(small[-1])], small)
+    assert np.array_equal(m.match_list_host_array(data, small.astype(np.uint32)), want_small)
+    assert len(m.match_list_host_array(data[:0], np.zeros(1, dtype=np.uint32))) == 0
+    m.close()
+
+
+def test_corpus_append_matches_one_shot_pack():
+    # incremental ingestion: batches that end on / next to tile boundaries (1024), empty batches, both offset widths
+    n = 150_000
+    data, off = synth.generate("deadbeef", n, 40, 64, seed=4242)
+    cfg = Config(max_typos=1)
+    m = F.Matcher("deadbeef", cfg)
+    want = O.match_list_packed(["deadbeef"], cfg, data, off)
+    cuts = [0, 1, 1, 1023, 1024, 1025, 2048, 2050, 5000, 5000 + 1024 * 3, 70_001, 70_001, 149_999, n]
+    c = F.Corpus.from_arrow(data[:0], np.zeros(1, dtype=np.uint64))
+    for k, (a, b) in enumerate(zip(cuts[:-1], cuts[1:])):
+        sl = off[a: b + 1]
+        offsets = sl.astype(np.uint32) if k % 2 else sl.astype(np.uint64)   # slices of the same value buffer
+        c.append(data, offsets)
+        assert len(c) == b and c.total_bytes == int(off[b])
+        if b in (1, 1025, 5000, 70_001):
+            got = m.match_list_array(c)
+            assert np.array_equal(got, O.match_list_packed(["deadbeef"], cfg, data[: int(off[b])], off[: b + 1])), b
+    got = m.match_list_array(c)
+    assert np.array_equal(got, want)
+    # long haystack crossing the re-bucketed tail, then more appends
+    c.append_list([b"x" * 5000 + b"deadbeef", b"deadbeef"])
+    got = m.match_list_array(c)
+    assert {n, n + 1} <= set(got["index"].tolist())
+    assert got[got["index"] == n + 1]["exact"][0] == 1
+    c.close()
+    m.close()
