@@ -62,6 +62,7 @@ struct FrzPatternDev {
     int32_t sw_lanes;       // Smith-Waterman chunk width being emulated: 8 / 16 / 32 / 64
     int32_t score_bits;     // 8 or 16 (reference backend family)
     int32_t wrap8;          // 1 → emulate u8 wrap-around explicitly (no-wrap bound not provable)
+    int32_t col_classes;    // 1 → windows <= 64 may use the column-limited SW classes (no wrap, no NUL in the needle)
     int32_t matching;       // FRZ_MATCHING_*
     int32_t case_sensitive;
     // scoring constants as the reference splats them (u8 truncated in the u8 family;
@@ -100,8 +101,16 @@ struct __align__(16) FrzSurvivor {
     uint32_t end;       // window end (exclusive)
 };
 
-// SW work classes (which kernel variant scores the window)
-enum { FRZ_C_COLS64 = 0, FRZ_C_COLS128 = 1, FRZ_C_GENERIC = 2, FRZ_N_CLASSES = 3 };
+// SW work classes (which kernel variant scores the window).  Windows of <= 64 bytes are split further by
+// the number of DP columns that can influence the score, min(W + needle_len, ceil(W / LANES) * LANES)
+// (sw.cu): CC40/48/56 evaluate only that many of the reference's 64 columns.
+enum {
+    FRZ_C_CC40 = 0, FRZ_C_CC48 = 1, FRZ_C_CC56 = 2, FRZ_C_COLS64 = 3,
+    FRZ_C_COLS128 = 4, FRZ_C_GENERIC = 5, FRZ_N_CLASSES = 6
+};
+struct FrzSurvLists {
+    FrzSurvivor* p[FRZ_N_CLASSES];
+};
 
 struct __align__(8) FrzMatchDev {  // == frz_match
     uint32_t index;
@@ -116,6 +125,8 @@ struct FrzCounters {
     unsigned long long total;                       // total matches (after scan)
     unsigned int max_score;
     unsigned int error;                             // sticky device-side error flags
+    unsigned int sw_next;                           // next 32-survivor work item of the SW kernel
+    unsigned int pad_;
 };
 
 #define FRZ_DEVERR_SURVIVOR_OVERFLOW 1u

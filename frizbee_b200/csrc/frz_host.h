@@ -95,7 +95,8 @@ struct FrzWorkspace {
     int device = -1;
     FrzCounters* counters = nullptr;        // device
     FrzCounters* h_counters = nullptr;      // pinned host mirror
-    FrzSurvivor* survivors[FRZ_N_CLASSES] = {nullptr, nullptr, nullptr};
+    FrzSurvivor* survivors[FRZ_N_CLASSES] = {};
+    FrzSurvLists lists() const { FrzSurvLists l; for (int c = 0; c < FRZ_N_CLASSES; c++) l.p[c] = survivors[c]; return l; }
     uint64_t survivor_cap = 0;              // per class
     uint32_t* surv_bitmap = nullptr;        // [n_tiles * 32] survivor bits by index-within-tile
     uint16_t* word_prefix = nullptr;        // [n_tiles * 32] exclusive popcount prefix of surv_bitmap words

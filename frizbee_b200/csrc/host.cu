@@ -506,6 +506,11 @@ frz_status compile_pattern(const OwnedPattern& src, const frz_config& mcfg, bool
     if (cell_bound > 32767 || pen_bound > 32767)
         return frz_fail(FRZ_ERR_UNSUPPORTED, "scoring/needle combination exceeds the kernels' signed 16-bit cell range");
     d.wrap8 = use_u8 && cell_bound > 255;  // cannot prove "no u8 add ever wraps" → emulate the wrap
+    {   // column-limited SW classes need: padding bytes (0) never match, and plain (non-wrapping) arithmetic
+        bool has_nul = false;
+        for (int i = 0; i < d.n; i++) has_nul = has_nul || d.c[i] == 0;
+        d.col_classes = (!d.wrap8 && !has_nul) ? 1 : 0;
+    }
     if (max_typos < 0) d.typo_mode = FRZ_T_NONE;
     else if (max_typos == 0) d.typo_mode = FRZ_T_0;
     else if (max_typos == 1) d.typo_mode = FRZ_T_1;

@@ -514,15 +514,22 @@ struct WarpQueue {
     uint2 occ[kMaxDistinct][32];             // per-lane occurrence masks of the distinct needle byte classes
 };
 
-__device__ __forceinline__ int sw_class_of(int window) {
-    return window <= 64 ? FRZ_C_COLS64 : window <= 128 ? FRZ_C_COLS128 : FRZ_C_GENERIC;
+__device__ __forceinline__ int sw_class_of(int window, const FrzPatternDev& pat) {
+    if (window > 128) return FRZ_C_GENERIC;
+    if (window > 64) return FRZ_C_COLS128;
+    if (!pat.col_classes) return FRZ_C_COLS64;
+    // columns whose cells can reach the score: the window, needle_len diagonal steps past its end, and never
+    // more than the chunks the reference evaluates
+    const int chunk_cols = (window + pat.sw_lanes - 1) / pat.sw_lanes * pat.sw_lanes;
+    const int need = min(window + pat.n, chunk_cols);
+    return need <= 40 ? FRZ_C_CC40 : need <= 48 ? FRZ_C_CC48 : need <= 56 ? FRZ_C_CC56 : FRZ_C_COLS64;
 }
 
 // Exact window of one queued candidate (phase B) + survivor emission.  All 32 lanes of the warp call
 // this together (`active` lanes have an entry); emission uses warp-aggregated atomics.
 template <int MODE>
 __device__ __forceinline__ void process_candidate(const FrzCorpusView& cv, const FrzPatternDev& pat, const uint8_t* __restrict__ cid_s,
-                                                  WarpQueue& q, int entry, bool active, FrzSurvivor* const* lists,
+                                                  WarpQueue& q, int entry, bool active, const FrzSurvLists& lists,
                                                   unsigned long long surv_cap, uint32_t* __restrict__ surv_bitmap,
                                                   FrzCounters* __restrict__ ctr) {
     const uint32_t lane = frz_lane();
@@ -570,23 +577,23 @@ __device__ __forceinline__ void process_candidate(const FrzCorpusView& cv, const
                 rec.end = (start == 0 && pat.n == len) ? 1u : 0u;
             } else {
                 start = start > 0 ? start - 1 : 0;  // trim_haystack (src/matcher/algo.rs:331-338)
-                cls = sw_class_of(end - start);
+                cls = sw_class_of(end - start, pat);
                 rec.start = (uint32_t)start;
                 rec.end = (uint32_t)end | ((uint32_t)(end == len) << 31);
             }
             atomicOr(&surv_bitmap[(uint64_t)tile * 32 + (li >> 5)], 1u << (li & 31));
         }
     }
-#pragma unroll
-    for (int c = 0; c < FRZ_N_CLASSES; c++) {
-        const uint32_t b = __ballot_sync(0xffffffffu, ok && cls == c);
-        if (!b) continue;
+    // warp-aggregated append: the lowest lane of every class present reserves the slots for its peers
+    const uint32_t peers = __match_any_sync(0xffffffffu, ok ? cls : -1);
+    if (__any_sync(0xffffffffu, ok)) {
+        const int leader = __ffs(peers) - 1;
         unsigned long long base = 0;
-        if (lane == 0) base = atomicAdd(&ctr->class_count[c], (unsigned long long)__popc(b));
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (ok && cls == c) {
-            const unsigned long long pos = base + __popc(b & ((1u << lane) - 1));
-            if (pos < surv_cap) lists[c][pos] = rec;
+        if (ok && (int)lane == leader) base = atomicAdd(&ctr->class_count[cls], (unsigned long long)__popc(peers));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (ok) {
+            const unsigned long long pos = base + __popc(peers & ((1u << lane) - 1));
+            if (pos < surv_cap) lists.p[cls][pos] = rec;
             else atomicOr(&ctr->error, FRZ_DEVERR_SURVIVOR_OVERFLOW);
         }
     }
@@ -595,16 +602,14 @@ __device__ __forceinline__ void process_candidate(const FrzCorpusView& cv, const
 // Warp-autonomous, barrier-free: every warp strides over groups, probes (phase A), queues the
 // passing haystacks' bytes in its own shared-memory ring and, whenever 32 are queued, runs the
 // exact window on them with all lanes busy (phase B).
-template <int MODE, int MINB>
-__global__ void __launch_bounds__(kThreads, MINB) k_prefilter(const FrzCorpusView cv, const __grid_constant__ FrzPatternDev pat,
+template <int MODE>
+__global__ void __launch_bounds__(kThreads) k_prefilter(const FrzCorpusView cv, const __grid_constant__ FrzPatternDev pat,
                                                         const uint32_t* __restrict__ cand_bitmap,
-                                                        FrzSurvivor* __restrict__ surv0, FrzSurvivor* __restrict__ surv1,
-                                                        FrzSurvivor* __restrict__ surv2, unsigned long long surv_cap,
+                                                        const FrzSurvLists lists, unsigned long long surv_cap,
                                                         uint32_t* __restrict__ surv_bitmap, FrzCounters* __restrict__ ctr) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const uint32_t lane = frz_lane(), warp = threadIdx.x >> 5;
     WarpQueue& q = reinterpret_cast<WarpQueue*>(smem_raw)[warp];
-    FrzSurvivor* const lists[FRZ_N_CLASSES] = {surv0, surv1, surv2};
     // needle index → distinct class, indexed per lane (a divergent index would serialise in the constant bank)
     __shared__ uint8_t cid_s[FRZ_MAX_NEEDLE];
     if (threadIdx.x < FRZ_MAX_NEEDLE) cid_s[threadIdx.x] = pat.cid[threadIdx.x];
@@ -623,30 +628,24 @@ __global__ void __launch_bounds__(kThreads, MINB) k_prefilter(const FrzCorpusVie
     // Software pipeline (the warp has no other way to keep HBM busy at 16 warps/SM): descriptors of
     // group i+2 and the haystack units of group i+1 are in flight while group i is probed.  The loop is
     // unrolled by two so that the unit buffers ping-pong instead of being copied.
-    // Work order.  Inside a tile the groups are sorted by length (group 31 holds the longest haystacks), so a
-    // warp striding by a multiple of 32 would see one rank for its whole life and the SMs would be unevenly
-    // loaded.  Virtual index v enumerates rank-major (v = rank * n_tiles + tile): all warps sweep the ranks
-    // together and every warp gets the same mix of short and long groups.
     struct Desc {
         FrzGroupDesc gd;
         uint32_t meta;
         uint32_t gidx;
     };
-    uint32_t gen_tile = blockIdx.x * kWarps + warp, gen_rank = 0;   // state of the (v -> group) generator
-    while (gen_tile >= cv.n_tiles) { gen_tile -= cv.n_tiles; gen_rank++; }
-    auto load_desc = [&](Desc& d) {   // descriptors of this warp's next group, in v order
-        if (gen_rank < FRZ_GROUPS_PER_TILE) {
-            const uint32_t gidx = gen_tile * FRZ_GROUPS_PER_TILE + gen_rank;
-            d.gd = cv.groups[gidx];  // one 16-byte load
-            d.meta = cv.slot_meta[(uint64_t)gen_tile * FRZ_TILE + gen_rank * FRZ_GROUP + lane];
-            d.gidx = gidx;
+    const uint32_t total_groups = cv.n_tiles * FRZ_GROUPS_PER_TILE;
+    uint32_t gen = blockIdx.x * kWarps + warp;   // this warp's next group (stride n_warps)
+    auto load_desc = [&](Desc& d) {
+        if (gen < total_groups) {
+            d.gd = cv.groups[gen];  // one 16-byte load
+            d.meta = cv.slot_meta[(uint64_t)(gen >> 5) * FRZ_TILE + (gen & 31) * FRZ_GROUP + lane];
+            d.gidx = gen;
         } else {
             d.gd = FrzGroupDesc{0ull, 0u, 0u};
             d.meta = FRZ_INVALID_SLOT;
             d.gidx = 0xFFFFFFFFu;
         }
-        gen_tile += n_warps;
-        while (gen_tile >= cv.n_tiles && gen_rank < FRZ_GROUPS_PER_TILE) { gen_tile -= cv.n_tiles; gen_rank++; }
+        gen += n_warps;
     };
     auto load_units = [&](const Desc& d, uint4 (&u)[kSliceUnits]) {
         const uint4* gp = cv.data + d.gd.abs_off + lane;
@@ -751,13 +750,11 @@ template <int MODE>
 __global__ void __launch_bounds__(kThreads) k_prefilter_list(const FrzCorpusView cv, const __grid_constant__ FrzPatternDev pat,
                                                              const FrzMatchDev* __restrict__ cand, unsigned long long n_cand,
                                                              uint32_t index_offset,
-                                                             FrzSurvivor* __restrict__ surv0, FrzSurvivor* __restrict__ surv1,
-                                                             FrzSurvivor* __restrict__ surv2, unsigned long long surv_cap,
+                                                             const FrzSurvLists lists, unsigned long long surv_cap,
                                                              uint32_t* __restrict__ surv_bitmap, FrzCounters* __restrict__ ctr) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const uint32_t lane = frz_lane(), warp = threadIdx.x >> 5;
     WarpQueue& q = reinterpret_cast<WarpQueue*>(smem_raw)[warp];
-    FrzSurvivor* const lists[FRZ_N_CLASSES] = {surv0, surv1, surv2};
     __shared__ uint8_t cid_s[FRZ_MAX_NEEDLE];
     if (threadIdx.x < FRZ_MAX_NEEDLE) cid_s[threadIdx.x] = pat.cid[threadIdx.x];
     __syncthreads();
@@ -848,8 +845,8 @@ frz_status frz_launch_prefilter_list(const FrzCorpusView& cv, const FrzPatternDe
             FRZ_CUDA_TRY(cudaFuncSetAttribute(k_prefilter_list<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
             attr_set = true;                                                                                     \
         }                                                                                                        \
-        k_prefilter_list<MODE><<<grid, kThreads, smem, stream>>>(cv, pat, cand, n_cand, index_offset, ws.survivors[0],    \
-                                                                 ws.survivors[1], ws.survivors[2], ws.survivor_cap,       \
+        k_prefilter_list<MODE><<<grid, kThreads, smem, stream>>>(cv, pat, cand, n_cand, index_offset, ws.lists(),         \
+                                                                 ws.survivor_cap,                                         \
                                                                  ws.surv_bitmap, ws.counters);                            \
     } while (0)
     switch (pat.typo_mode) {
@@ -877,37 +874,21 @@ frz_status frz_launch_prefilter(const FrzCorpusView& cv, const FrzPatternDev& pa
     if (sms <= 0) sms = 148;
     // persistent warps: 4 blocks of 4 warps per SM (shared-memory bound), capped by the work
     const uint32_t total_groups = cv.n_tiles * FRZ_GROUPS_PER_TILE;
-    static int bps = 0;  // resident blocks per SM (experiment knob FRZ_PF_BLOCKS: 4, 5 or 6)
-    if (!bps) {
-        const char* e = getenv("FRZ_PF_BLOCKS");
-        bps = e ? atoi(e) : 4;
-        if (bps < 4 || bps > 6) bps = 4;
-    }
-    const bool tuned = pat.typo_mode == FRZ_T_0 || pat.typo_mode == FRZ_T_1;
-    const int use_bps = tuned ? bps : 4;
-    const uint32_t grid = std::max<uint32_t>(1, std::min<uint32_t>((uint32_t)sms * use_bps, (total_groups + kWarps - 1) / kWarps));
+    const uint32_t grid = std::max<uint32_t>(1, std::min<uint32_t>((uint32_t)sms * 4, (total_groups + kWarps - 1) / kWarps));
     FRZ_CUDA_TRY(cudaMemsetAsync(ws.surv_bitmap, 0, (size_t)cv.n_tiles * 32 * sizeof(uint32_t), stream));
-#define FRZ_PF_LAUNCH_B(MODE, MINB)                                                                             \
+#define FRZ_PF_LAUNCH(MODE)                                                                                     \
     do {                                                                                                        \
         static bool attr_set = false;                                                                           \
         if (!attr_set) {                                                                                        \
-            FRZ_CUDA_TRY(cudaFuncSetAttribute(k_prefilter<MODE, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-            FRZ_CUDA_TRY(cudaFuncSetAttribute(k_prefilter<MODE, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, 100)); \
+            FRZ_CUDA_TRY(cudaFuncSetAttribute(k_prefilter<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
             attr_set = true;                                                                                    \
         }                                                                                                       \
-        k_prefilter<MODE, MINB><<<grid, kThreads, smem, stream>>>(cv, pat, cand_bitmap, ws.survivors[0], ws.survivors[1], \
-                                                            ws.survivors[2], ws.survivor_cap, ws.surv_bitmap, ws.counters); \
-    } while (0)
-#define FRZ_PF_LAUNCH(MODE) FRZ_PF_LAUNCH_B(MODE, 4)
-#define FRZ_PF_LAUNCH_TUNED(MODE)                        \
-    do {                                                 \
-        if (use_bps == 6) FRZ_PF_LAUNCH_B(MODE, 6);      \
-        else if (use_bps == 5) FRZ_PF_LAUNCH_B(MODE, 5); \
-        else FRZ_PF_LAUNCH_B(MODE, 4);                   \
+        k_prefilter<MODE><<<grid, kThreads, smem, stream>>>(cv, pat, cand_bitmap, ws.lists(), ws.survivor_cap,           \
+                                                            ws.surv_bitmap, ws.counters);                                   \
     } while (0)
     switch (pat.typo_mode) {
-        case FRZ_T_0: FRZ_PF_LAUNCH_TUNED(FRZ_T_0); break;
-        case FRZ_T_1: FRZ_PF_LAUNCH_TUNED(FRZ_T_1); break;
+        case FRZ_T_0: FRZ_PF_LAUNCH(FRZ_T_0); break;
+        case FRZ_T_1: FRZ_PF_LAUNCH(FRZ_T_1); break;
         case FRZ_T_2: FRZ_PF_LAUNCH(FRZ_T_2); break;
         case FRZ_T_MANY: FRZ_PF_LAUNCH(FRZ_T_MANY); break;
         case FRZ_T_NONE: FRZ_PF_LAUNCH(FRZ_T_NONE); break;
@@ -915,8 +896,6 @@ frz_status frz_launch_prefilter(const FrzCorpusView& cv, const FrzPatternDev& pa
         default: return frz_fail(FRZ_ERR_INVALID_ARG, "bad typo mode %d", pat.typo_mode);
     }
 #undef FRZ_PF_LAUNCH
-#undef FRZ_PF_LAUNCH_B
-#undef FRZ_PF_LAUNCH_TUNED
     FRZ_CUDA_TRY(cudaGetLastError());
     if (st) st->launches++;
     return FRZ_OK;

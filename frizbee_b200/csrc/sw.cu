@@ -76,21 +76,28 @@ struct RowStore<R, true> {
 
 // VAR selects which one-lane shifts use IMAD/IMAD.HI (fma pipe) instead of PRMT (alu pipe):
 //   bit 0: diagonal shift of the previous row; bit 1: score shift of gap step 1; bit 2: mask shift of gap step 1
-template <int LANES, int COLS, bool WRAP8, int VAR = 0>
+//
+// CC (<= COLS, multiple of 8) is the number of columns actually evaluated.  Cells never depend on cells to
+// their right, and a cell in column >= W + needle_len can only hold a value that decayed from a cell to its
+// left in the same row (it is past the reach of the diagonal/up chains that start inside the window, and zero
+// padding never matches), so it can never be the unique row maximum: evaluating the first
+// min(W + n, ceil(W / LANES) * LANES) columns gives the reference's score.  Not used with WRAP8 (no monotone
+// arithmetic) or a needle containing NUL; pinned by tests/test_oracle_kat.py::test_column_limit_property.
+template <int LANES, int COLS, bool WRAP8, int VAR = 0, int CC = COLS>
 struct SwCore {
-    static constexpr int R = COLS / 2;     // registers per row
+    static constexpr int R = CC / 2;       // registers per row
     static constexpr int RL = LANES / 2;   // registers per chunk
-    static constexpr int NCH = COLS / LANES;
+    static constexpr int NCH = (CC + LANES - 1) / LANES;
     static constexpr bool SMEM = COLS > 64;
     static constexpr size_t smem_bytes = SMEM ? 2 * R * kSwThreads * sizeof(uint32_t) : 0;
 
-    // hw: COLS/4 words of window bytes, zero beyond W
-    static __device__ uint32_t run(const uint32_t (&hw)[COLS / 4], int W, const FrzPatternDev& p, bool include_prefix,
+    // hw: CC/4 words of window bytes, zero beyond W
+    static __device__ __forceinline__ uint32_t run(const uint32_t (&hw)[CC / 4], int W, const FrzPatternDev& p, bool include_prefix,
                                    uint32_t* smem) {
         RowStore<R, SMEM> h16s(smem), Bs(smem + R * kSwThreads);
         // expand bytes to one per 16-bit lane
 #pragma unroll
-        for (int i = 0; i < COLS / 4; i++) {
+        for (int i = 0; i < CC / 4; i++) {
             h16s.set(2 * i, __byte_perm(hw[i], 0, 0x4140));
             h16s.set(2 * i + 1, __byte_perm(hw[i], 0, 0x4342));
         }
@@ -186,7 +193,7 @@ struct SwCore {
             // ---- horizontal gap propagation, chunk by chunk (ascii_gap.rs gap_step!) ----
 #pragma unroll
             for (int c = 0; c < NCH; c++) {
-                const int lo = c * RL, hi = lo + RL;
+                const int lo = c * RL, hi = (lo + RL < R) ? lo + RL : R;
 #pragma unroll
                 for (int s = 1, si = 0; s < LANES; s <<= 1, si++) {
                     const uint32_t penA = p.k_pen_a[si];
@@ -228,7 +235,7 @@ struct SwCore {
 template <int COLS>
 __device__ __forceinline__ void load_window(const FrzCorpusView& cv, uint32_t tile, uint32_t slot, uint32_t start, int W,
                                             uint32_t (&hw)[COLS / 4]) {
-    constexpr int NU = COLS / 16 + 1;
+    constexpr int NU = (COLS + 15) / 16 + 1;
     const uint32_t u0 = start >> 4;
     const int last_u = W > 0 ? (int)((start + W - 1) >> 4) - (int)u0 : -1;
     const uint4* base = frz_unit_ptr(cv, tile, slot, u0);
@@ -293,7 +300,27 @@ __device__ __forceinline__ void emit_match(const FrzSurvivor& rec, uint32_t scor
     out[pos] = m;
 }
 
-template <int LANES, int COLS, bool WRAP8, int VAR>
+// One survivor: load its window, score it, write the Match at its index-ordered position.
+template <int LANES, int COLS, bool WRAP8, int CC>
+__device__ __forceinline__ uint32_t score_survivor(const FrzCorpusView& cv, const FrzPatternDev& pat, const FrzSurvivor& rec,
+                                                   const FrzRankView& rv, const FrzCounters* __restrict__ ctr, uint32_t index_offset,
+                                                   int reversed, FrzMatchDev* __restrict__ out, uint32_t* sw_smem) {
+    const uint32_t slot = rec.slot_rank & 0x3ff;
+    const uint32_t start = rec.start, end = rec.end & 0x7fffffffu;
+    const bool full_end = (rec.end >> 31) != 0;
+    const int W = (int)(end - start);
+    uint32_t hw[CC / 4];
+    load_window<CC>(cv, rec.tile, slot, start, W, hw);
+    uint32_t score = SwCore<LANES, COLS, WRAP8, 0, CC>::run(hw, W, pat, start == 0, sw_smem);
+    bool exact = start == 0 && full_end && window_equals_needle(hw, W, pat);
+    if (exact) score = (score + pat.exact_bonus) & 0xffffu;
+    emit_match(rec, score, exact, index_offset, reversed != 0, rv, ctr, out);
+    return score;
+}
+
+// Windows of 65..128 bytes: one window per thread, score rows in shared memory, survivors strided over a
+// persistent grid.
+template <int LANES, int COLS, bool WRAP8>
 __global__ void __launch_bounds__(kSwThreads) k_sw(const FrzCorpusView cv, const __grid_constant__ FrzPatternDev pat,
                                                    const FrzSurvivor* __restrict__ surv, unsigned long long surv_cap, int cls,
                                                    const FrzRankView rv, FrzCounters* __restrict__ ctr,
@@ -304,20 +331,54 @@ __global__ void __launch_bounds__(kSwThreads) k_sw(const FrzCorpusView cv, const
     for (unsigned long long j = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; j < count;
          j += (unsigned long long)gridDim.x * blockDim.x) {
         const FrzSurvivor rec = surv[j];
-        const uint32_t slot = rec.slot_rank & 0x3ff;
-        const uint32_t start = rec.start, end = rec.end & 0x7fffffffu;
-        const bool full_end = (rec.end >> 31) != 0;
-        const int W = (int)(end - start);
-        uint32_t hw[COLS / 4];
-        load_window<COLS>(cv, rec.tile, slot, start, W, hw);
-        uint32_t score = SwCore<LANES, COLS, WRAP8, VAR>::run(hw, W, pat, start == 0, sw_smem);
-        bool exact = start == 0 && full_end && window_equals_needle(hw, W, pat);
-        if (exact) score = (score + pat.exact_bonus) & 0xffffu;
-        emit_match(rec, score, exact, index_offset, reversed != 0, rv, ctr, out);
-        local_max = max(local_max, score);
+        local_max = max(local_max, score_survivor<LANES, COLS, WRAP8, COLS>(cv, pat, rec, rv, ctr, index_offset, reversed, out, sw_smem));
     }
     local_max = __reduce_max_sync(0xffffffffu, local_max);
     if (frz_lane() == 0 && local_max) atomicMax(&ctr->max_score, local_max);
+}
+
+// Windows of <= 64 bytes: the four column classes (CC64 first: longest items first) share one persistent
+// kernel.  A work item is 32 consecutive survivors of one class; warps claim items from a device counter, so
+// the load balances itself and the only tail is the last item of each warp.
+template <int LANES, bool WRAP8>
+__global__ void __launch_bounds__(kSwThreads) k_sw64(const FrzCorpusView cv, const __grid_constant__ FrzPatternDev pat,
+                                                     const FrzSurvLists lists, unsigned long long surv_cap,
+                                                     const FrzRankView rv, FrzCounters* __restrict__ ctr,
+                                                     uint32_t index_offset, int reversed, FrzMatchDev* __restrict__ out) {
+    const uint32_t lane = frz_lane();
+    unsigned long long cnt[4];
+    uint32_t items_end[4];   // cumulative item counts in processing order CC64, CC56, CC48, CC40
+    {
+        uint32_t acc = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            cnt[k] = min(ctr->class_count[FRZ_C_COLS64 - k], surv_cap);
+            acc += (uint32_t)((cnt[k] + 31) >> 5);
+            items_end[k] = acc;
+        }
+    }
+    uint32_t local_max = 0;
+    for (;;) {
+        uint32_t item = 0;
+        if (lane == 0) item = atomicAdd(&ctr->sw_next, 1u);
+        item = __shfl_sync(0xffffffffu, item, 0);
+        if (item >= items_end[3]) break;
+        const int k = item < items_end[0] ? 0 : item < items_end[1] ? 1 : item < items_end[2] ? 2 : 3;
+        const uint32_t first = k == 0 ? 0u : k == 1 ? items_end[0] : k == 2 ? items_end[1] : items_end[2];
+        const unsigned long long cnt_k = k == 0 ? cnt[0] : k == 1 ? cnt[1] : k == 2 ? cnt[2] : cnt[3];
+        const unsigned long long j = (unsigned long long)(item - first) * 32 + lane;
+        if (j < cnt_k) {
+            const FrzSurvivor rec = lists.p[FRZ_C_COLS64 - k][j];
+            uint32_t sc;
+            if (k == 0) sc = score_survivor<LANES, 64, WRAP8, 64>(cv, pat, rec, rv, ctr, index_offset, reversed, out, nullptr);
+            else if (k == 1) sc = score_survivor<LANES, 64, WRAP8, 56>(cv, pat, rec, rv, ctr, index_offset, reversed, out, nullptr);
+            else if (k == 2) sc = score_survivor<LANES, 64, WRAP8, 48>(cv, pat, rec, rv, ctr, index_offset, reversed, out, nullptr);
+            else sc = score_survivor<LANES, 64, WRAP8, 40>(cv, pat, rec, rv, ctr, index_offset, reversed, out, nullptr);
+            local_max = max(local_max, sc);
+        }
+    }
+    local_max = __reduce_max_sync(0xffffffffu, local_max);
+    if (lane == 0 && local_max) atomicMax(&ctr->max_score, local_max);
 }
 
 // ---- generic fallback: windows of 129..1024 bytes (row-major, local-memory rows) and the
@@ -492,54 +553,31 @@ int sm_count() {
     return g_sm_count;
 }
 
-template <int LANES, int COLS>
-frz_status launch_sw_variant(const FrzCorpusView& cv, const FrzPatternDev& pat, int cls, uint32_t index_offset, bool reversed,
-                             FrzWorkspace& ws, FrzMatchDev* d_out, cudaStream_t stream) {
-    // persistent grid: a multiple of the SM count; survivors are strided over it
+template <int LANES>
+frz_status launch_sw_lanes(const FrzCorpusView& cv, const FrzPatternDev& pat, uint32_t index_offset, bool reversed,
+                           FrzWorkspace& ws, FrzMatchDev* d_out, cudaStream_t stream) {
+    // persistent grids: a multiple of the SM count
     const int blocks = sm_count() * 2;
-    const size_t smem = SwCore<LANES, COLS, false>::smem_bytes;
-    if (smem > 48 * 1024) {
-        static bool attr_set = false;
-        if (!attr_set) {
-            FRZ_CUDA_TRY(cudaFuncSetAttribute(k_sw<LANES, COLS, true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            FRZ_CUDA_TRY(cudaFuncSetAttribute(k_sw<LANES, COLS, false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            attr_set = true;
-        }
-    }
-    if (LANES == 64 && COLS == 64 && !pat.wrap8) {
-        // pipe-balance experiment knob: FRZ_SW_VARIANT = shift placement bits (see SwCore)
-        static int var = -1;
-        if (var < 0) { const char* e = getenv("FRZ_SW_VARIANT"); var = e ? atoi(e) : 0; }
-#define FRZ_SW_VAR_CASE(V)                                                                                              \
-        if (var == V) {                                                                                                 \
-            k_sw<64, 64, false, V><<<blocks, kSwThreads, 0, stream>>>(cv, pat, ws.survivors[cls], ws.survivor_cap, cls, rank_view(ws), \
-                                                                  ws.counters, index_offset, reversed ? 1 : 0, d_out);  \
-            FRZ_CUDA_TRY(cudaGetLastError());                                                                           \
-            return FRZ_OK;                                                                                              \
-        }
-        FRZ_SW_VAR_CASE(1) FRZ_SW_VAR_CASE(5) FRZ_SW_VAR_CASE(3) FRZ_SW_VAR_CASE(4) FRZ_SW_VAR_CASE(6) FRZ_SW_VAR_CASE(7)
-#undef FRZ_SW_VAR_CASE
+    const int rev = reversed ? 1 : 0;
+    if (pat.wrap8)
+        k_sw64<LANES, true><<<blocks, kSwThreads, 0, stream>>>(cv, pat, ws.lists(), ws.survivor_cap, rank_view(ws), ws.counters, index_offset, rev, d_out);
+    else
+        k_sw64<LANES, false><<<blocks, kSwThreads, 0, stream>>>(cv, pat, ws.lists(), ws.survivor_cap, rank_view(ws), ws.counters, index_offset, rev, d_out);
+    const size_t smem = SwCore<LANES, 128, false>::smem_bytes;
+    static bool attr_set = false;
+    if (!attr_set) {
+        FRZ_CUDA_TRY(cudaFuncSetAttribute(k_sw<LANES, 128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        FRZ_CUDA_TRY(cudaFuncSetAttribute(k_sw<LANES, 128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
     }
     if (pat.wrap8)
-        k_sw<LANES, COLS, true, 0><<<blocks, kSwThreads, smem, stream>>>(cv, pat, ws.survivors[cls], ws.survivor_cap, cls, rank_view(ws), ws.counters,
-                                                                   index_offset, reversed ? 1 : 0, d_out);
+        k_sw<LANES, 128, true><<<blocks, kSwThreads, smem, stream>>>(cv, pat, ws.survivors[FRZ_C_COLS128], ws.survivor_cap, FRZ_C_COLS128,
+                                                                    rank_view(ws), ws.counters, index_offset, rev, d_out);
     else
-        k_sw<LANES, COLS, false, 0><<<blocks, kSwThreads, smem, stream>>>(cv, pat, ws.survivors[cls], ws.survivor_cap, cls, rank_view(ws), ws.counters,
-                                                                    index_offset, reversed ? 1 : 0, d_out);
+        k_sw<LANES, 128, false><<<blocks, kSwThreads, smem, stream>>>(cv, pat, ws.survivors[FRZ_C_COLS128], ws.survivor_cap, FRZ_C_COLS128,
+                                                                     rank_view(ws), ws.counters, index_offset, rev, d_out);
     FRZ_CUDA_TRY(cudaGetLastError());
     return FRZ_OK;
-}
-
-template <int COLS>
-frz_status launch_sw_cols(const FrzCorpusView& cv, const FrzPatternDev& pat, int cls, uint32_t index_offset, bool reversed,
-                          FrzWorkspace& ws, FrzMatchDev* d_out, cudaStream_t stream) {
-    switch (pat.sw_lanes) {
-        case 64: return launch_sw_variant<64, COLS>(cv, pat, cls, index_offset, reversed, ws, d_out, stream);
-        case 32: return launch_sw_variant<32, COLS>(cv, pat, cls, index_offset, reversed, ws, d_out, stream);
-        case 16: return launch_sw_variant<16, COLS>(cv, pat, cls, index_offset, reversed, ws, d_out, stream);
-        case 8: return launch_sw_variant<8, COLS>(cv, pat, cls, index_offset, reversed, ws, d_out, stream);
-        default: return frz_fail(FRZ_ERR_INVALID_ARG, "unsupported lane count %d", pat.sw_lanes);
-    }
 }
 
 }  // namespace
@@ -554,8 +592,13 @@ frz_status frz_launch_sw(const FrzCorpusView& cv, const FrzPatternDev& pat, uint
         if (st) st->launches++;
         return FRZ_OK;
     }
-    FRZ_TRY(launch_sw_cols<64>(cv, pat, FRZ_C_COLS64, index_offset, reversed, ws, d_out, stream));
-    FRZ_TRY(launch_sw_cols<128>(cv, pat, FRZ_C_COLS128, index_offset, reversed, ws, d_out, stream));
+    switch (pat.sw_lanes) {
+        case 64: FRZ_TRY(launch_sw_lanes<64>(cv, pat, index_offset, reversed, ws, d_out, stream)); break;
+        case 32: FRZ_TRY(launch_sw_lanes<32>(cv, pat, index_offset, reversed, ws, d_out, stream)); break;
+        case 16: FRZ_TRY(launch_sw_lanes<16>(cv, pat, index_offset, reversed, ws, d_out, stream)); break;
+        case 8: FRZ_TRY(launch_sw_lanes<8>(cv, pat, index_offset, reversed, ws, d_out, stream)); break;
+        default: return frz_fail(FRZ_ERR_INVALID_ARG, "unsupported lane count %d", pat.sw_lanes);
+    }
     k_sw_generic<<<sm_count() * 2, 64, 0, stream>>>(cv, pat, ws.survivors[FRZ_C_GENERIC], ws.survivor_cap, FRZ_C_GENERIC, rank_view(ws),
                                                     ws.counters, index_offset, reversed ? 1 : 0, d_out);
     FRZ_CUDA_TRY(cudaGetLastError());

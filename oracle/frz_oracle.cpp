@@ -432,8 +432,11 @@ static int match_greedy(const uint8_t* needle_raw, size_t n, const uint8_t* hay,
 
 // src/smith_waterman/algo/ascii.rs:10-158 (score_haystack), chunk-major exactly as the reference,
 // with the full score / match-mask matrices.
+// max_cols (test-only, tests/test_oracle_kat.py::test_column_limit_property): take the final maximum over the
+// last-row cells of columns < max_cols only.  Cells never depend on cells to their right, so this equals a
+// computation that stops at column max_cols; the reference itself always uses every lane (SIZE_MAX).
 static uint16_t sw_score(const uint8_t* needle_raw, size_t n, const frz_scoring& sc, bool case_sensitive,
-                         const uint8_t* hay, size_t hl, bool include_prefix, int lanes, bool u8) {
+                         const uint8_t* hay, size_t hl, bool include_prefix, int lanes, bool u8, size_t max_cols = SIZE_MAX) {
     if (hl > kMaxHaystackLen) {
         int g = match_greedy(needle_raw, n, hay, hl, sc, case_sensitive, include_prefix);
         return g < 0 ? 0 : (uint16_t)g;
@@ -504,6 +507,9 @@ static uint16_t sw_score(const uint8_t* needle_raw, size_t n, const frz_scoring&
             prev_row = row;
             up_gap_mask = mm;
         }
+        if (max_cols != SIZE_MAX)
+            for (int i = 0; i < lanes; i++)
+                if ((col - 1) * lanes + i >= max_cols) row.v[i] = 0;
         maxv = A.max(maxv, row);
         prefix_masked = A.zero();
     }
@@ -762,6 +768,40 @@ int frzo_prefilter(const uint8_t* needle, size_t n, int case_sensitive, const ui
 uint16_t frzo_sw_score(const uint8_t* needle, size_t n, const frz_scoring* sc, int case_sensitive,
                        const uint8_t* hay, size_t len, int include_prefix, int lanes, int score_bits) {
     return sw_score(needle, n, *sc, case_sensitive != 0, hay, len, include_prefix != 0, lanes, score_bits == 8);
+}
+
+uint16_t frzo_sw_score_col_limit(const uint8_t* needle, size_t n, const frz_scoring* sc, int case_sensitive,
+                                 const uint8_t* hay, size_t len, int include_prefix, int lanes, int score_bits, uint64_t max_cols) {
+    return sw_score(needle, n, *sc, case_sensitive != 0, hay, len, include_prefix != 0, lanes, score_bits == 8, (size_t)max_cols);
+}
+
+// Randomised search for a window whose score changes when the final maximum ignores the columns >= len + n + slack
+// (dense alphabets, the shapes that expose the reference's lane dependence).  Returns the number of counterexamples.
+uint64_t frzo_col_limit_search(uint64_t seed, uint64_t trials, int lanes, int score_bits, int slack, const frz_scoring* sc,
+                               uint8_t* bad_needle, uint8_t* bad_hay, uint32_t* bad_lens) {
+    uint64_t x = seed * 0x9E3779B97F4A7C15ull + 1, bad = 0;
+    auto rnd = [&]() { x ^= x << 13; x ^= x >> 7; x ^= x << 17; return x; };
+    static const char* pools[] = {"abAB_/-ab01", "ab", "aAbB_", "abcdefghijklmnopqrstuvwxyzABCDEFGHIJKLMNOPQRSTUVWXYZ0123456789_-/."};
+    for (uint64_t t = 0; t < trials; t++) {
+        const char* pool = pools[rnd() % 4];
+        const size_t pl = strlen(pool);
+        const size_t n = 1 + rnd() % (score_bits == 8 ? 13 : 24);
+        const size_t hl = 1 + rnd() % (size_t)(2 * lanes + 7);
+        uint8_t needle[64], hay[256];
+        for (size_t i = 0; i < n; i++) needle[i] = (uint8_t)pool[rnd() % pl];
+        for (size_t i = 0; i < hl; i++) hay[i] = (uint8_t)pool[rnd() % pl];
+        const bool cs = rnd() & 1, pref = rnd() & 1;
+        const uint16_t full = sw_score(needle, n, *sc, cs, hay, hl, pref, lanes, score_bits == 8);
+        const uint16_t lim = sw_score(needle, n, *sc, cs, hay, hl, pref, lanes, score_bits == 8, hl + n + slack);
+        if (full != lim) {
+            if (bad == 0 && bad_needle) {
+                memcpy(bad_needle, needle, n); memcpy(bad_hay, hay, hl);
+                bad_lens[0] = (uint32_t)n; bad_lens[1] = (uint32_t)hl; bad_lens[2] = full; bad_lens[3] = lim;
+            }
+            bad++;
+        }
+    }
+    return bad;
 }
 
 int frzo_match_greedy(const uint8_t* needle, size_t n, const frz_scoring* sc, int case_sensitive,

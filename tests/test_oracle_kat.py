@@ -405,3 +405,34 @@ def test_unicode_needle_is_flagged_not_faked():
     # UnicodeMatching::Ignore takes the byte path (src/lib.rs:394-399)
     m = O.match_list("é", ["xxé"], Config(unicode=UnicodeMatching.Ignore, sort=SortStrategy.IndexAsc))
     assert len(m) == 1
+
+
+# ---------------------------------------------------------------- property the column-limited SW kernels rely on
+@pytest.mark.parametrize("lanes,bits", [(16, 8), (32, 8), (64, 8), (16, 16), (32, 16)])
+def test_column_limit_property(lanes, bits):
+    """sw.cu evaluates only the first W + needle_len DP columns for short windows.  Cells never depend on cells
+    to their right, so this is equivalent to taking the reference's final maximum over those columns only; the
+    oracle (which always evaluates every lane, like src/smith_waterman/algo/ascii.rs:152-156) confirms that the
+    columns beyond never hold the unique maximum — for the default scoring and for skewed ones."""
+    import ctypes as C
+    L = O.lib()
+    L.frzo_col_limit_search.restype = C.c_uint64
+    L.frzo_col_limit_search.argtypes = [C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 4
+    scorings = [Scoring(),
+                Scoring(gap_open_penalty=0, gap_extend_penalty=0),
+                Scoring(mismatch_penalty=0, gap_open_penalty=1, gap_extend_penalty=1),
+                Scoring(match_score=3, mismatch_penalty=9, gap_open_penalty=9, gap_extend_penalty=2, delimiter_bonus=9),
+                Scoring(prefix_bonus=0, capitalization_bonus=0, delimiter_bonus=0, matching_case_bonus=0, gap_extend_penalty=3,
+                        gap_open_penalty=3)]
+    for i, sc in enumerate(scorings):
+        if bits == 8 and not O.score_fits_in_u8(13, sc):
+            continue
+        csc = O.CScoring.of(sc)
+        bad_n = np.zeros(64, np.uint8); bad_h = np.zeros(256, np.uint8); bad_l = np.zeros(4, np.uint32)
+        # slack -1: the limit W + n - 1 is the tight one (n - 1 diagonal steps past the window); the kernels use W + n
+        bad = L.frzo_col_limit_search(100 + i, 20000, lanes, bits, -1, C.byref(csc), bad_n.ctypes.data, bad_h.ctypes.data,
+                                      bad_l.ctypes.data)
+        assert bad == 0, (sc, bytes(bad_n[: bad_l[0]]), bytes(bad_h[: bad_l[1]]), bad_l[2:])
+    # sanity: the search does find counterexamples when real columns are cut off
+    csc = O.CScoring.of(Scoring())
+    assert L.frzo_col_limit_search(1, 20000, lanes, bits, -4, C.byref(csc), None, None, None) > 0
