@@ -39,6 +39,7 @@ struct FrzCorpusView {
     const uint16_t* slot_of;      // [n_tiles * 1024]  inverse permutation: local index → slot
     uint64_t n;                   // haystacks
     uint32_t n_tiles;
+    uint32_t max_gunits;          // longest haystack in 16-byte units
 };
 
 // typo-mode keys (src/matcher/algo.rs:6-7, src/matcher/mod.rs:58-73)
@@ -94,11 +95,17 @@ struct FrzPatternDev {
 };
 
 // Survivor of the prefilter, input of the Smith-Waterman stage (16 bytes).
+// A prefilter survivor.  Two layouts share the 16 bytes:
+//   generic class / literal:  slot_rank = slot | li << 10;  start, end | (end == len) << 31   (literal: score, exact)
+//   window classes (<= 128):  slot_rank = slot | li << 10 | W << 20 | (end == len) << 28 | (start == 0) << 29
+//                             start = low 32 bits of the unit index of the window's first 16-byte unit (lane-resolved)
+//                             end   = high 8 bits of that index | (window start & 15) << 8
+// li = index of the haystack inside its tile (its rank in index order).
 struct __align__(16) FrzSurvivor {
     uint32_t tile;      // tile index
-    uint32_t slot_rank; // slot (10 bits) | rank-by-index inside the tile << 16
-    uint32_t start;     // trimmed window start (bytes)
-    uint32_t end;       // window end (exclusive)
+    uint32_t slot_rank;
+    uint32_t start;
+    uint32_t end;
 };
 
 // SW work classes (which kernel variant scores the window).  Windows of <= 64 bytes are split further by

@@ -38,6 +38,7 @@ struct FrzCorpusStorage {
     uint32_t n_tiles = 0;
     uint64_t total_units = 0;
     uint64_t total_bytes = 0;
+    uint32_t max_gunits = 0;   // longest haystack of the corpus in 16-byte units
     int device = 0;
     // capacities (grow-only reuse by the end-to-end path: no cudaMalloc/cudaFree per call)
     uint32_t cap_tiles = 0;
@@ -53,6 +54,7 @@ struct FrzCorpusStorage {
         v.slot_of = slot_of;
         v.n = n;
         v.n_tiles = n_tiles;
+        v.max_gunits = max_gunits;
         return v;
     }
     void release() {

@@ -73,6 +73,7 @@ __global__ void __launch_bounds__(256) k_pack_plan(const OffT* __restrict__ offs
     __syncthreads();
     if (threadIdx.x == 0) {
         uint32_t off = 0;
+        atomicMax(err + 1, gun[FRZ_GROUPS_PER_TILE - 1]);   // longest group of the corpus, in units (groups ascend)
         for (int g = 0; g < FRZ_GROUPS_PER_TILE; g++) {
             groups[tile * FRZ_GROUPS_PER_TILE + g] = FrzGroupDesc{0ull, off, gun[g]};  // abs_off filled by k_pack_copy
             off += gun[g] * FRZ_GROUP;
@@ -301,6 +302,7 @@ frz_status pack_plan(FrzCorpusStorage* out, const OffT* d_offsets, uint64_t n, u
     FRZ_CUDA_TRY(cudaStreamSynchronize(stream));
     if ((unsigned int)(h[1] & 0xffffffffu)) return frz_fail(FRZ_ERR_UNSUPPORTED, "haystack longer than 4 MiB");
     out->total_units = h[0];
+    out->max_gunits = std::max<uint32_t>(tile0 ? out->max_gunits : 0u, (uint32_t)(h[1] >> 32));
     if (out->cap_units < out->total_units + 1) {
         const uint64_t want = out->total_units + out->total_units / (keep_data ? 2 : 16) + 1024;
         uint4* data = nullptr;

@@ -27,7 +27,7 @@ namespace {
 
 constexpr int kThreads = 128;
 constexpr int kWarps = kThreads / 32;
-constexpr int kSliceUnits = 8;                         // groups of up to 8 units (128 bytes) are probed from registers
+constexpr int kSliceUnitsMax = 8;                      // groups of up to 8 units (128 bytes) are probed from registers
 
 struct SliceAcc {
     const uint32_t* s;
@@ -578,8 +578,17 @@ __device__ __forceinline__ void process_candidate(const FrzCorpusView& cv, const
             } else {
                 start = start > 0 ? start - 1 : 0;  // trim_haystack (src/matcher/algo.rs:331-338)
                 cls = sw_class_of(end - start, pat);
-                rec.start = (uint32_t)start;
-                rec.end = (uint32_t)end | ((uint32_t)(end == len) << 31);
+                if (cls < FRZ_C_GENERIC) {
+                    // window record (frz_device.cuh): everything the SW kernel needs, including the address of the
+                    // window's first 16-byte unit, so that it never touches the group descriptors
+                    const uint64_t addr = (uint64_t)(ga.base - cv.data) + (uint64_t)(start >> 4) * FRZ_GROUP;
+                    rec.slot_rank |= (uint32_t)(end - start) << 20 | (uint32_t)(end == len) << 28 | (uint32_t)(start == 0) << 29;
+                    rec.start = (uint32_t)addr;
+                    rec.end = (uint32_t)(addr >> 32) | ((uint32_t)start & 15u) << 8;
+                } else {
+                    rec.start = (uint32_t)start;
+                    rec.end = (uint32_t)end | ((uint32_t)(end == len) << 31);
+                }
             }
             atomicOr(&surv_bitmap[(uint64_t)tile * 32 + (li >> 5)], 1u << (li & 31));
         }
@@ -602,8 +611,10 @@ __device__ __forceinline__ void process_candidate(const FrzCorpusView& cv, const
 // Warp-autonomous, barrier-free: every warp strides over groups, probes (phase A), queues the
 // passing haystacks' bytes in its own shared-memory ring and, whenever 32 are queued, runs the
 // exact window on them with all lanes busy (phase B).
-template <int MODE>
-__global__ void __launch_bounds__(kThreads) k_prefilter(const FrzCorpusView cv, const __grid_constant__ FrzPatternDev pat,
+// SLICE: units per lane held in registers per prefetched group (4 when no haystack of the corpus exceeds 64 bytes:
+// half the buffer registers, one more resident block per SM).
+template <int MODE, int SLICE>
+__global__ void __launch_bounds__(kThreads, SLICE == 4 ? 5 : 4) k_prefilter(const FrzCorpusView cv, const __grid_constant__ FrzPatternDev pat,
                                                         const uint32_t* __restrict__ cand_bitmap,
                                                         const FrzSurvLists lists, unsigned long long surv_cap,
                                                         uint32_t* __restrict__ surv_bitmap, FrzCounters* __restrict__ ctr) {
@@ -647,15 +658,15 @@ __global__ void __launch_bounds__(kThreads) k_prefilter(const FrzCorpusView cv, 
         }
         gen += n_warps;
     };
-    auto load_units = [&](const Desc& d, uint4 (&u)[kSliceUnits]) {
+    auto load_units = [&](const Desc& d, uint4 (&u)[SLICE]) {
         const uint4* gp = cv.data + d.gd.abs_off + lane;
 #pragma unroll
-        for (int k = 0; k < kSliceUnits; k++) {
-            if (k < (int)d.gd.gunits && d.gd.gunits <= kSliceUnits) u[k] = __ldg(gp + (size_t)k * FRZ_GROUP);
+        for (int k = 0; k < SLICE; k++) {
+            if (k < (int)d.gd.gunits && d.gd.gunits <= SLICE) u[k] = __ldg(gp + (size_t)k * FRZ_GROUP);
         }
     };
     // phase A on one group whose units are in `u`
-    auto phase_a = [&](const Desc& dc, const uint4 (&u)[kSliceUnits]) {
+    auto phase_a = [&](const Desc& dc, const uint4 (&u)[SLICE]) {
         const uint32_t tile = dc.gidx >> 5, g = dc.gidx & 31;
         const FrzGroupDesc gd = dc.gd;
         const uint32_t slot = g * FRZ_GROUP + lane;
@@ -668,12 +679,12 @@ __global__ void __launch_bounds__(kThreads) k_prefilter(const FrzCorpusView cv, 
             pass = pass && ((cand_bitmap[idx >> 5] >> (idx & 31)) & 1);
         }
         uint32_t acc = 0, acc1 = 0, acc2 = 0;
-        const bool in_regs = gd.gunits <= kSliceUnits;  // units prefetched into registers
+        const bool in_regs = gd.gunits <= SLICE;  // units prefetched into registers
         const bool skip_group = gd.gunits == 0 && MODE != FRZ_T_NONE && MODE != FRZ_T_LITERAL && pat.min_hay_len > 0;
         if (probe && !skip_group) {
             if (in_regs) {
 #pragma unroll
-                for (int k = 0; k < kSliceUnits; k++) {
+                for (int k = 0; k < SLICE; k++) {
                     if (k >= (int)gd.gunits) break;  // warp-uniform
                     const uint32_t w[4] = {u[k].x, u[k].y, u[k].z, u[k].w};
 #pragma unroll
@@ -714,7 +725,7 @@ __global__ void __launch_bounds__(kThreads) k_prefilter(const FrzCorpusView cv, 
         }
     };
     Desc d0, d1, d2;
-    uint4 ua[kSliceUnits], ub[kSliceUnits];
+    uint4 ua[SLICE], ub[SLICE];
     load_desc(d0);
     load_desc(d1);
     load_units(d0, ua);
@@ -874,21 +885,27 @@ frz_status frz_launch_prefilter(const FrzCorpusView& cv, const FrzPatternDev& pa
     if (sms <= 0) sms = 148;
     // persistent warps: 4 blocks of 4 warps per SM (shared-memory bound), capped by the work
     const uint32_t total_groups = cv.n_tiles * FRZ_GROUPS_PER_TILE;
-    const uint32_t grid = std::max<uint32_t>(1, std::min<uint32_t>((uint32_t)sms * 4, (total_groups + kWarps - 1) / kWarps));
+    static int slice_knob = -1;   // experiment knob: FRZ_PF_SLICE=8 forces the wide variant
+    if (slice_knob < 0) { const char* e = getenv("FRZ_PF_SLICE"); slice_knob = e ? atoi(e) : 0; }
+    const bool narrow = cv.max_gunits <= 4 && slice_knob != 8 && (pat.typo_mode == FRZ_T_0 || pat.typo_mode == FRZ_T_1);
+    const uint32_t bps = narrow ? 5 : 4;
+    const uint32_t grid = std::max<uint32_t>(1, std::min<uint32_t>((uint32_t)sms * bps, (total_groups + kWarps - 1) / kWarps));
     FRZ_CUDA_TRY(cudaMemsetAsync(ws.surv_bitmap, 0, (size_t)cv.n_tiles * 32 * sizeof(uint32_t), stream));
-#define FRZ_PF_LAUNCH(MODE)                                                                                     \
+#define FRZ_PF_LAUNCH(MODE) FRZ_PF_LAUNCH_S(MODE, 8)
+#define FRZ_PF_LAUNCH_N(MODE) do { if (narrow) FRZ_PF_LAUNCH_S(MODE, 4); else FRZ_PF_LAUNCH_S(MODE, 8); } while (0)
+#define FRZ_PF_LAUNCH_S(MODE, SL)                                                                                     \
     do {                                                                                                        \
         static bool attr_set = false;                                                                           \
         if (!attr_set) {                                                                                        \
-            FRZ_CUDA_TRY(cudaFuncSetAttribute(k_prefilter<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            FRZ_CUDA_TRY(cudaFuncSetAttribute(k_prefilter<MODE, SL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
             attr_set = true;                                                                                    \
         }                                                                                                       \
-        k_prefilter<MODE><<<grid, kThreads, smem, stream>>>(cv, pat, cand_bitmap, ws.lists(), ws.survivor_cap,           \
+        k_prefilter<MODE, SL><<<grid, kThreads, smem, stream>>>(cv, pat, cand_bitmap, ws.lists(), ws.survivor_cap,       \
                                                             ws.surv_bitmap, ws.counters);                                   \
     } while (0)
     switch (pat.typo_mode) {
-        case FRZ_T_0: FRZ_PF_LAUNCH(FRZ_T_0); break;
-        case FRZ_T_1: FRZ_PF_LAUNCH(FRZ_T_1); break;
+        case FRZ_T_0: FRZ_PF_LAUNCH_N(FRZ_T_0); break;
+        case FRZ_T_1: FRZ_PF_LAUNCH_N(FRZ_T_1); break;
         case FRZ_T_2: FRZ_PF_LAUNCH(FRZ_T_2); break;
         case FRZ_T_MANY: FRZ_PF_LAUNCH(FRZ_T_MANY); break;
         case FRZ_T_NONE: FRZ_PF_LAUNCH(FRZ_T_NONE); break;
@@ -896,6 +913,8 @@ frz_status frz_launch_prefilter(const FrzCorpusView& cv, const FrzPatternDev& pa
         default: return frz_fail(FRZ_ERR_INVALID_ARG, "bad typo mode %d", pat.typo_mode);
     }
 #undef FRZ_PF_LAUNCH
+#undef FRZ_PF_LAUNCH_N
+#undef FRZ_PF_LAUNCH_S
     FRZ_CUDA_TRY(cudaGetLastError());
     if (st) st->launches++;
     return FRZ_OK;

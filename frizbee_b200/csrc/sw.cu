@@ -24,6 +24,7 @@
 // long as no u8 add can wrap; when the host cannot prove that (pat.wrap8) the WRAP8 variant
 // re-applies the 8-bit wrap after every add.
 #include "frz_device.cuh"
+#include <cuda_pipeline.h>
 #include <stdlib.h>
 
 #include "frz_host.h"
@@ -31,6 +32,11 @@
 namespace {
 
 constexpr int kSwThreads = 128;
+#ifndef FRZ_SW64_SMEM
+#define FRZ_SW64_SMEM 0
+#endif
+constexpr bool kSw64RowsInSmem = FRZ_SW64_SMEM != 0;  // <= 64-byte windows: haystack/bonus rows in shared memory, 3 blocks per SM
+constexpr int kSw64MinBlocks = kSw64RowsInSmem ? 3 : 2;
 
 struct FrzRankView {
     const uint64_t* tile_out_base;
@@ -88,7 +94,7 @@ struct SwCore {
     static constexpr int R = CC / 2;       // registers per row
     static constexpr int RL = LANES / 2;   // registers per chunk
     static constexpr int NCH = (CC + LANES - 1) / LANES;
-    static constexpr bool SMEM = COLS > 64;
+    static constexpr bool SMEM = COLS > 64 || kSw64RowsInSmem;
     static constexpr size_t smem_bytes = SMEM ? 2 * R * kSwThreads * sizeof(uint32_t) : 0;
 
     // hw: CC/4 words of window bytes, zero beyond W
@@ -231,24 +237,17 @@ struct SwCore {
     }
 };
 
-// Loads window bytes [start, start+W) of (tile, slot) into COLS/4 zero-padded words.
+// Window bytes [startlo, startlo + W) of the NU staged 16-byte units → COLS/4 zero-padded words.
 template <int COLS>
-__device__ __forceinline__ void load_window(const FrzCorpusView& cv, uint32_t tile, uint32_t slot, uint32_t start, int W,
-                                            uint32_t (&hw)[COLS / 4]) {
+__device__ __forceinline__ void window_from_units(const uint4 (&u)[(COLS + 15) / 16 + 1], uint32_t startlo, int W,
+                                                  uint32_t (&hw)[COLS / 4]) {
     constexpr int NU = (COLS + 15) / 16 + 1;
-    const uint32_t u0 = start >> 4;
-    const int last_u = W > 0 ? (int)((start + W - 1) >> 4) - (int)u0 : -1;
-    const uint4* base = frz_unit_ptr(cv, tile, slot, u0);
     uint32_t w[NU * 4 + 4];
 #pragma unroll
-    for (int k = 0; k < NU; k++) {
-        uint4 v = make_uint4(0, 0, 0, 0);
-        if (k <= last_u) v = __ldg(base + (size_t)k * FRZ_GROUP);
-        w[4 * k] = v.x; w[4 * k + 1] = v.y; w[4 * k + 2] = v.z; w[4 * k + 3] = v.w;
-    }
+    for (int k = 0; k < NU; k++) { w[4 * k] = u[k].x; w[4 * k + 1] = u[k].y; w[4 * k + 2] = u[k].z; w[4 * k + 3] = u[k].w; }
 #pragma unroll
     for (int k = NU * 4; k < NU * 4 + 4; k++) w[k] = 0;
-    const uint32_t ws = (start & 15) >> 2, bs = (start & 3) * 8;
+    const uint32_t ws = startlo >> 2, bs = (startlo & 3) * 8;
     if (ws & 2) {
 #pragma unroll
         for (int k = 0; k < NU * 4 + 2; k++) w[k] = w[k + 2];
@@ -267,6 +266,24 @@ __device__ __forceinline__ void load_window(const FrzCorpusView& cv, uint32_t ti
     }
 }
 
+// decoded window record (FrzSurvivor, window-class layout)
+struct WindowRec {
+    uint64_t addr;      // unit index of the first unit of the window
+    uint32_t startlo;   // window start inside that unit
+    int W;
+    bool start0, full_end;
+};
+__device__ __forceinline__ WindowRec decode_window(const FrzSurvivor& rec) {
+    WindowRec r;
+    r.addr = ((uint64_t)(rec.end & 0xffu) << 32) | rec.start;
+    r.startlo = (rec.end >> 8) & 15u;
+    r.W = (int)((rec.slot_rank >> 20) & 0xffu);
+    r.full_end = ((rec.slot_rank >> 28) & 1u) != 0;
+    r.start0 = ((rec.slot_rank >> 29) & 1u) != 0;
+    return r;
+}
+__device__ __forceinline__ int window_units(const WindowRec& r) { return r.W > 0 ? (int)((r.startlo + r.W - 1) >> 4) + 1 : 0; }
+
 // exact = include_exact && needle_bytes == window (src/matcher/algo.rs:245); byte-exact compare
 template <int NW>
 __device__ __forceinline__ bool window_equals_needle(const uint32_t (&hw)[NW], int W, const FrzPatternDev& p) {
@@ -283,15 +300,20 @@ __device__ __forceinline__ bool window_equals_needle(const uint32_t (&hw)[NW], i
     return eq;
 }
 
-__device__ __forceinline__ void emit_match(const FrzSurvivor& rec, uint32_t score, bool exact, uint32_t index_offset,
-                                           bool reversed, const FrzRankView& rv,
-                                           const FrzCounters* __restrict__ ctr, FrzMatchDev* __restrict__ out) {
+// Output position of a survivor: its tile's base + its rank among the tile's survivors in index order (from
+// the survivor bitmap).  Independent of the score, so callers request it before the DP and use it after.
+__device__ __forceinline__ uint64_t match_position(const FrzSurvivor& rec, bool reversed, const FrzRankView& rv,
+                                                   const FrzCounters* __restrict__ ctr) {
     const uint32_t li = (rec.slot_rank >> 10) & 0x3ff;
-    // rank among the tile's survivors in index order, from the survivor bitmap
     const uint64_t wi = (uint64_t)rec.tile * 32 + (li >> 5);
     const uint32_t rank = rv.word_prefix[wi] + __popc(rv.surv_bitmap[wi] & ((1u << (li & 31)) - 1));
     uint64_t pos = rv.tile_out_base[rec.tile] + rank;
     if (reversed) pos = ctr->total - 1 - pos;
+    return pos;
+}
+__device__ __forceinline__ void store_match(const FrzSurvivor& rec, uint64_t pos, uint32_t score, bool exact, uint32_t index_offset,
+                                            FrzMatchDev* __restrict__ out) {
+    const uint32_t li = (rec.slot_rank >> 10) & 0x3ff;
     FrzMatchDev m;
     m.index = index_offset + rec.tile * FRZ_TILE + li;
     m.score = (uint16_t)score;
@@ -299,23 +321,44 @@ __device__ __forceinline__ void emit_match(const FrzSurvivor& rec, uint32_t scor
     m.pad = 0;
     out[pos] = m;
 }
+__device__ __forceinline__ void emit_match(const FrzSurvivor& rec, uint32_t score, bool exact, uint32_t index_offset,
+                                           bool reversed, const FrzRankView& rv,
+                                           const FrzCounters* __restrict__ ctr, FrzMatchDev* __restrict__ out) {
+    store_match(rec, match_position(rec, reversed, rv, ctr), score, exact, index_offset, out);
+}
 
-// One survivor: load its window, score it, write the Match at its index-ordered position.
+// One survivor whose window units are in registers: score it, write the Match at its index-ordered position.
+template <int LANES, int COLS, bool WRAP8, int CC>
+__device__ __forceinline__ uint32_t score_window(const FrzPatternDev& pat, const FrzSurvivor& rec, const WindowRec& wr,
+                                                 const uint4 (&u)[(CC + 15) / 16 + 1], const FrzRankView& rv,
+                                                 const FrzCounters* __restrict__ ctr, uint32_t index_offset, int reversed,
+                                                 FrzMatchDev* __restrict__ out, uint32_t* sw_smem) {
+    const uint64_t pos = match_position(rec, reversed != 0, rv, ctr);   // loads overlap the DP
+    uint32_t hw[CC / 4];
+    window_from_units<CC>(u, wr.startlo, wr.W, hw);
+    uint32_t score = SwCore<LANES, COLS, WRAP8, 0, CC>::run(hw, wr.W, pat, wr.start0, sw_smem);
+    bool exact = wr.start0 && wr.full_end && window_equals_needle(hw, wr.W, pat);
+    if (exact) score = (score + pat.exact_bonus) & 0xffffu;
+    store_match(rec, pos, score, exact, index_offset, out);
+    return score;
+}
+
+// Same, loading the units straight from the packed corpus.
 template <int LANES, int COLS, bool WRAP8, int CC>
 __device__ __forceinline__ uint32_t score_survivor(const FrzCorpusView& cv, const FrzPatternDev& pat, const FrzSurvivor& rec,
                                                    const FrzRankView& rv, const FrzCounters* __restrict__ ctr, uint32_t index_offset,
                                                    int reversed, FrzMatchDev* __restrict__ out, uint32_t* sw_smem) {
-    const uint32_t slot = rec.slot_rank & 0x3ff;
-    const uint32_t start = rec.start, end = rec.end & 0x7fffffffu;
-    const bool full_end = (rec.end >> 31) != 0;
-    const int W = (int)(end - start);
-    uint32_t hw[CC / 4];
-    load_window<CC>(cv, rec.tile, slot, start, W, hw);
-    uint32_t score = SwCore<LANES, COLS, WRAP8, 0, CC>::run(hw, W, pat, start == 0, sw_smem);
-    bool exact = start == 0 && full_end && window_equals_needle(hw, W, pat);
-    if (exact) score = (score + pat.exact_bonus) & 0xffffu;
-    emit_match(rec, score, exact, index_offset, reversed != 0, rv, ctr, out);
-    return score;
+    constexpr int NU = (CC + 15) / 16 + 1;
+    const WindowRec wr = decode_window(rec);
+    const int nu = window_units(wr);
+    const uint4* base = cv.data + wr.addr;
+    uint4 u[NU];
+#pragma unroll
+    for (int k = 0; k < NU; k++) {
+        u[k] = make_uint4(0, 0, 0, 0);
+        if (k < nu) u[k] = __ldg(base + (size_t)k * FRZ_GROUP);
+    }
+    return score_window<LANES, COLS, WRAP8, CC>(pat, rec, wr, u, rv, ctr, index_offset, reversed, out, sw_smem);
 }
 
 // Windows of 65..128 bytes: one window per thread, score rows in shared memory, survivors strided over a
@@ -340,11 +383,22 @@ __global__ void __launch_bounds__(kSwThreads) k_sw(const FrzCorpusView cv, const
 // Windows of <= 64 bytes: the four column classes (CC64 first: longest items first) share one persistent
 // kernel.  A work item is 32 consecutive survivors of one class; warps claim items from a device counter, so
 // the load balances itself and the only tail is the last item of each warp.
+//
+// The kernel is issue-bound with two warps per scheduler, so every exposed load latency costs: the loop is
+// software-pipelined two items deep.  While item i is being scored, item i+1's window units travel
+// global → shared with cp.async (no registers held) and item i+2's records are in flight.
+constexpr int kSw64Units = 5;  // 16-byte units a <= 64-byte window can straddle
+struct Sw64Stage {
+    uint4 units[kSw64Units][kSwThreads];  // [k][thread]: conflict-free 16-byte columns
+};
+
 template <int LANES, bool WRAP8>
-__global__ void __launch_bounds__(kSwThreads) k_sw64(const FrzCorpusView cv, const __grid_constant__ FrzPatternDev pat,
+__global__ void __launch_bounds__(kSwThreads, kSw64MinBlocks) k_sw64(const FrzCorpusView cv, const __grid_constant__ FrzPatternDev pat,
                                                      const FrzSurvLists lists, unsigned long long surv_cap,
                                                      const FrzRankView rv, FrzCounters* __restrict__ ctr,
                                                      uint32_t index_offset, int reversed, FrzMatchDev* __restrict__ out) {
+    __shared__ Sw64Stage stage;
+    __shared__ uint32_t rows_smem[kSw64RowsInSmem ? 2 * 32 * kSwThreads : 1];
     const uint32_t lane = frz_lane();
     unsigned long long cnt[4];
     uint32_t items_end[4];   // cumulative item counts in processing order CC64, CC56, CC48, CC40
@@ -357,26 +411,95 @@ __global__ void __launch_bounds__(kSwThreads) k_sw64(const FrzCorpusView cv, con
             items_end[k] = acc;
         }
     }
+    const uint32_t n_items = items_end[3];
+    const uint32_t opaque_zero = ctr->pad_;   // always 0 (the counters are zeroed before every call)
+    // work-item claim, split so that the atomic's round trip overlaps a whole DP: `claim_issue` returns lane 0's
+    // raw ticket (other lanes: garbage) and `claim_get` broadcasts it one iteration later
+    auto claim_issue = [&]() {
+        uint32_t t = 0xFFFFFFFFu;
+        // ptxas rewrites an atomic add on a warp-uniform address into its warp-aggregated form, whose trailing
+        // SHFL waits for the atomic right here.  Offsetting the address by tid.x * (a zero it cannot see through)
+        // makes the address formally lane-dependent: the atomic is left alone and its result stays in flight.
+        if (lane == 0)
+            asm volatile("{ .reg .u32 x; .reg .u64 a, o;\n"
+                         "  mov.u32 x, %%tid.x; mul.lo.u32 x, x, %2; mul.wide.u32 o, x, 4; add.u64 a, %1, o;\n"
+                         "  atom.global.add.u32 %0, [a], 1; }"
+                         : "=r"(t) : "l"(&ctr->sw_next), "r"(opaque_zero) : "memory");
+        return t;
+    };
+    auto claim_get = [&](uint32_t ticket) { return __shfl_sync(0xffffffffu, ticket, 0); };
+    auto class_of = [&](uint32_t item) { return item < items_end[0] ? 0 : item < items_end[1] ? 1 : item < items_end[2] ? 2 : 3; };
+    // this lane's record of `item` (tile = 0xFFFFFFFF when the lane has none)
+    auto load_rec = [&](uint32_t item) {
+        FrzSurvivor rec;
+        rec.tile = 0xFFFFFFFFu; rec.slot_rank = 0; rec.start = 0; rec.end = 0;
+        if (item < n_items) {
+            const int k = class_of(item);
+            const uint32_t first = k == 0 ? 0u : k == 1 ? items_end[0] : k == 2 ? items_end[1] : items_end[2];
+            const unsigned long long cnt_k = k == 0 ? cnt[0] : k == 1 ? cnt[1] : k == 2 ? cnt[2] : cnt[3];
+            const unsigned long long j = (unsigned long long)(item - first) * 32 + lane;
+            const FrzSurvivor* list = k == 0 ? lists.p[FRZ_C_COLS64] : k == 1 ? lists.p[FRZ_C_CC56] : k == 2 ? lists.p[FRZ_C_CC48] : lists.p[FRZ_C_CC40];
+            if (j < cnt_k) rec = list[j];
+        }
+        return rec;
+    };
+    // stage the window units of `rec` into this thread's shared-memory column
+    auto stage_units = [&](const FrzSurvivor& rec) {
+        if (rec.tile != 0xFFFFFFFFu) {
+            const WindowRec wr = decode_window(rec);
+            const int nu = window_units(wr);
+            const uint4* base = cv.data + wr.addr;
+#pragma unroll
+            for (int k = 0; k < kSw64Units; k++)
+                if (k < nu) __pipeline_memcpy_async(&stage.units[k][threadIdx.x], base + (size_t)k * FRZ_GROUP, 16);
+        }
+        __pipeline_commit();
+    };
+
     uint32_t local_max = 0;
-    for (;;) {
-        uint32_t item = 0;
-        if (lane == 0) item = atomicAdd(&ctr->sw_next, 1u);
-        item = __shfl_sync(0xffffffffu, item, 0);
-        if (item >= items_end[3]) break;
-        const int k = item < items_end[0] ? 0 : item < items_end[1] ? 1 : item < items_end[2] ? 2 : 3;
-        const uint32_t first = k == 0 ? 0u : k == 1 ? items_end[0] : k == 2 ? items_end[1] : items_end[2];
-        const unsigned long long cnt_k = k == 0 ? cnt[0] : k == 1 ? cnt[1] : k == 2 ? cnt[2] : cnt[3];
-        const unsigned long long j = (unsigned long long)(item - first) * 32 + lane;
-        if (j < cnt_k) {
-            const FrzSurvivor rec = lists.p[FRZ_C_COLS64 - k][j];
+    // pipeline: item0 = being scored (units staged), item1 = records in registers, item2 = ticket in flight
+    uint32_t item0 = claim_get(claim_issue()), item1 = claim_get(claim_issue());
+    uint32_t ticket2 = claim_issue();
+    FrzSurvivor rec0 = load_rec(item0);
+    stage_units(rec0);
+    FrzSurvivor rec1 = load_rec(item1);
+    while (item0 < n_items) {
+        // units of item0 have landed → registers
+        __pipeline_wait_prior(0);
+        const WindowRec wr = decode_window(rec0);
+        const int nu = window_units(wr);
+        uint4 u[kSw64Units];
+#pragma unroll
+        for (int k = 0; k < kSw64Units; k++) {
+            u[k] = make_uint4(0, 0, 0, 0);
+            if (k < nu && rec0.tile != 0xFFFFFFFFu) u[k] = stage.units[k][threadIdx.x];
+        }
+        // next item's units start moving; the ticket taken one iteration ago becomes item2, whose records are
+        // requested now; a new ticket is taken for the iteration after
+        stage_units(rec1);
+        const uint32_t item2 = claim_get(ticket2);
+        ticket2 = claim_issue();
+        const FrzSurvivor rec2 = load_rec(item2);
+        if (rec0.tile != 0xFFFFFFFFu) {
+            const int k = class_of(item0);
             uint32_t sc;
-            if (k == 0) sc = score_survivor<LANES, 64, WRAP8, 64>(cv, pat, rec, rv, ctr, index_offset, reversed, out, nullptr);
-            else if (k == 1) sc = score_survivor<LANES, 64, WRAP8, 56>(cv, pat, rec, rv, ctr, index_offset, reversed, out, nullptr);
-            else if (k == 2) sc = score_survivor<LANES, 64, WRAP8, 48>(cv, pat, rec, rv, ctr, index_offset, reversed, out, nullptr);
-            else sc = score_survivor<LANES, 64, WRAP8, 40>(cv, pat, rec, rv, ctr, index_offset, reversed, out, nullptr);
+            if (k == 0) {
+                sc = score_window<LANES, 64, WRAP8, 64>(pat, rec0, wr, u, rv, ctr, index_offset, reversed, out, rows_smem);
+            } else if (k == 1) {
+                sc = score_window<LANES, 64, WRAP8, 56>(pat, rec0, wr, u, rv, ctr, index_offset, reversed, out, rows_smem);
+            } else if (k == 2) {
+                const uint4 (&u4)[4] = reinterpret_cast<const uint4 (&)[4]>(u);
+                sc = score_window<LANES, 64, WRAP8, 48>(pat, rec0, wr, u4, rv, ctr, index_offset, reversed, out, rows_smem);
+            } else {
+                const uint4 (&u4)[4] = reinterpret_cast<const uint4 (&)[4]>(u);
+                sc = score_window<LANES, 64, WRAP8, 40>(pat, rec0, wr, u4, rv, ctr, index_offset, reversed, out, rows_smem);
+            }
             local_max = max(local_max, sc);
         }
+        item0 = item1; rec0 = rec1;
+        item1 = item2; rec1 = rec2;
     }
+    __pipeline_wait_prior(0);
     local_max = __reduce_max_sync(0xffffffffu, local_max);
     if (lane == 0 && local_max) atomicMax(&ctr->max_score, local_max);
 }
@@ -558,11 +681,12 @@ frz_status launch_sw_lanes(const FrzCorpusView& cv, const FrzPatternDev& pat, ui
                            FrzWorkspace& ws, FrzMatchDev* d_out, cudaStream_t stream) {
     // persistent grids: a multiple of the SM count
     const int blocks = sm_count() * 2;
+    const int blocks64 = sm_count() * kSw64MinBlocks;
     const int rev = reversed ? 1 : 0;
     if (pat.wrap8)
-        k_sw64<LANES, true><<<blocks, kSwThreads, 0, stream>>>(cv, pat, ws.lists(), ws.survivor_cap, rank_view(ws), ws.counters, index_offset, rev, d_out);
+        k_sw64<LANES, true><<<blocks64, kSwThreads, 0, stream>>>(cv, pat, ws.lists(), ws.survivor_cap, rank_view(ws), ws.counters, index_offset, rev, d_out);
     else
-        k_sw64<LANES, false><<<blocks, kSwThreads, 0, stream>>>(cv, pat, ws.lists(), ws.survivor_cap, rank_view(ws), ws.counters, index_offset, rev, d_out);
+        k_sw64<LANES, false><<<blocks64, kSwThreads, 0, stream>>>(cv, pat, ws.lists(), ws.survivor_cap, rank_view(ws), ws.counters, index_offset, rev, d_out);
     const size_t smem = SwCore<LANES, 128, false>::smem_bytes;
     static bool attr_set = false;
     if (!attr_set) {
