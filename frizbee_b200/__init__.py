@@ -90,6 +90,7 @@ def lib():
     L.frz_match_list_host.argtypes = [vp, vp, vp, u64, C.c_int, vp, u64, C.POINTER(u64)]
     L.frz_match_list_host_arrow.argtypes = [vp, vp, vp, C.c_int, u64, C.c_int, vp, u64, C.POINTER(u64)]
     L.frz_match_shard_device.argtypes = [vp, vp, u32, vp, u64, vp, vp]
+    L.frz_matcher_wait_count.argtypes = [vp, vp]
     L.frz_merge_runs_device.argtypes = [vp, u64, vp, C.c_int, C.c_uint8, u32, vp, C.c_int, vp]
     L.frz_matcher_score_bound.restype = u32
     L.frz_matcher_score_bound.argtypes = [vp]

@@ -582,9 +582,14 @@ struct frz_matcher {
     uint64_t multi_cap = 0;
     float last_ms[4] = {0, 0, 0, 0};
     uint64_t last_launches = 0;
+    // shard path: the match count is known after the tile scan, long before the scores; it is published there so
+    // that the count exchange of match_list_parallel overlaps the Smith-Waterman and sort kernels
+    uint64_t* early_count_dst = nullptr;   // device destination of the count (set for the duration of a shard call)
+    cudaEvent_t count_ev = nullptr;        // recorded once the count is in early_count_dst
+    bool count_published = false;
     bool timings_pending = false;
     ~frz_matcher() {
-        if (ws.device >= 0) { cudaSetDevice(ws.device); cudaFree(multi_a); cudaFree(multi_b); }
+        if (ws.device >= 0) { cudaSetDevice(ws.device); cudaFree(multi_a); cudaFree(multi_b); if (count_ev) cudaEventDestroy(count_ev); }
         if (e2e_ingest.d_bytes || e2e_ingest.copy_stream || e2e_corpus.st.data) {
             cudaSetDevice(e2e_corpus.st.device);
             e2e_ingest.release();
@@ -847,6 +852,12 @@ frz_status run_pattern(frz_matcher* m, const FrzCorpusStorage& cs, const Compile
     else FRZ_TRY(frz_launch_prefilter(cv, c.dev, cand_bitmap, ws, stream, st));
     FRZ_TRY(frz_launch_tile_scan(cv, ws, stream, st));
     if (record_events) { cudaEventRecord(ws.ev[1], stream); ws.ev_rec[1] = true; }
+    if (m->early_count_dst && !cand_list && !cand_bitmap && m->compiled.size() == 1) {
+        // single pattern: every survivor becomes exactly one match, so the scan total is the final count
+        FRZ_CUDA_TRY(cudaMemcpyAsync(m->early_count_dst, &ws.counters->total, sizeof(uint64_t), cudaMemcpyDeviceToDevice, stream));
+        FRZ_CUDA_TRY(cudaEventRecord(m->count_ev, stream));
+        m->count_published = true;
+    }
     // A survivor-list overflow (lists are sized by a heuristic unless the pattern can match everything)
     // only sets a sticky device flag; whoever reads the counters back re-runs with worst-case lists.
     FRZ_TRY(frz_launch_sw(cv, c.dev, index_offset, reversed, ws, d_out, stream, st));
@@ -1131,10 +1142,27 @@ extern "C" frz_status frz_match_shard_device(frz_matcher* m, const frz_corpus* s
     FRZ_TRY(ensure_workspace(m, shard->st, std::max<uint64_t>(shard->st.n, 1)));
     // the run can never exceed the shard size; the caller sizes d_out as >= shard length
     if (cap < shard->st.n) return frz_fail(FRZ_ERR_CAPACITY, "d_out must hold the whole shard (%llu)", (unsigned long long)shard->st.n);
-    FRZ_TRY(match_list_device(m, shard->st, index_offset, m->config.sort, &d_list, stream, &st, reinterpret_cast<FrzMatchDev*>(d_out)));
-    FRZ_CUDA_TRY(cudaMemcpyAsync(d_count, &m->ws.counters->total, sizeof(uint64_t), cudaMemcpyDeviceToDevice, stream));
+    if (!m->count_ev) FRZ_CUDA_TRY(cudaEventCreateWithFlags(&m->count_ev, cudaEventDisableTiming));
+    m->early_count_dst = d_count;
+    m->count_published = false;
+    const frz_status ms = match_list_device(m, shard->st, index_offset, m->config.sort, &d_list, stream, &st, reinterpret_cast<FrzMatchDev*>(d_out));
+    m->early_count_dst = nullptr;
+    FRZ_TRY(ms);
+    if (!m->count_published) {   // multi-pattern / empty pattern: the count exists only at the end
+        FRZ_CUDA_TRY(cudaMemcpyAsync(d_count, &m->ws.counters->total, sizeof(uint64_t), cudaMemcpyDeviceToDevice, stream));
+        FRZ_CUDA_TRY(cudaEventRecord(m->count_ev, stream));
+    }
     m->last_launches = st.launches;
     m->timings_pending = true;   // events were recorded; frz_matcher_last_timings reads them once the stream is idle
+    return FRZ_OK;
+}
+
+// Makes `stream` wait until the count of the last frz_match_shard_device call has been written to its d_count
+// (which happens before the scoring kernels for a single-pattern matcher).
+extern "C" frz_status frz_matcher_wait_count(frz_matcher* m, void* stream) {
+    if (!m) return frz_fail(FRZ_ERR_INVALID_ARG, "null matcher");
+    if (!m->count_ev) return frz_fail(FRZ_ERR_INVALID_ARG, "no shard call has been made on this matcher");
+    FRZ_CUDA_TRY(cudaStreamWaitEvent((cudaStream_t)stream, m->count_ev, 0));
     return FRZ_OK;
 }
 
@@ -1147,6 +1175,58 @@ __global__ void k_gather_runs(const FrzMatchDev* runs, uint64_t stride, const ui
         const uint64_t cnt = counts[src_run], base = bases[r];
         for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += (uint64_t)gridDim.x * blockDim.x)
             out[base + i] = src[i];
+    }
+}
+
+// ---- k-way merge of score-sorted runs (src/k_merge.rs:90-131) without comparing heads -------------------
+// Every run is sorted by score descending, so "the elements of run r with score s" is the index range
+// [gt[r][s], gt[r][s-1]) where gt[r][s] = #elements of run r with score > s — a binary search per (r, s).
+// The merged position of that block is  Σ_r' gt[r'][s]  (everything with a higher score)  +  the sizes of the
+// same-score blocks of the runs that come earlier in the merge order; one scatter pass places the elements.
+constexpr int kMergeMaxBins = 4096;
+
+__global__ void k_merge_bounds(const FrzMatchDev* __restrict__ runs, uint64_t stride, const uint64_t* __restrict__ counts,
+                               int n_runs, int bins, uint32_t* __restrict__ gt) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_runs * bins) return;
+    const int r = t / bins;
+    const uint32_t s = (uint32_t)(t - r * bins);
+    const FrzMatchDev* run = runs + (uint64_t)r * stride;
+    uint64_t lo = 0, hi = counts[r];   // first index whose score <= s
+    while (lo < hi) {
+        const uint64_t mid = (lo + hi) >> 1;
+        if (run[mid].score > s) lo = mid + 1; else hi = mid;
+    }
+    gt[t] = (uint32_t)lo;
+}
+
+// pos0[r][s] = merged position of the first element of run r's score-s block.  One thread per score.
+__global__ void k_merge_bases(const uint32_t* __restrict__ gt, const uint64_t* __restrict__ counts, int n_runs, int bins,
+                              int reverse_runs, uint32_t* __restrict__ pos0) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= bins) return;
+    uint32_t higher = 0;
+    for (int r = 0; r < n_runs; r++) higher += gt[r * bins + s];
+    uint32_t acc = higher;
+    for (int k = 0; k < n_runs; k++) {
+        const int r = reverse_runs ? n_runs - 1 - k : k;
+        pos0[r * bins + s] = acc;
+        const uint32_t ge = s == 0 ? (uint32_t)counts[r] : gt[r * bins + s - 1];   // #elements with score >= s
+        acc += ge - gt[r * bins + s];
+    }
+}
+
+__global__ void k_merge_scatter(const FrzMatchDev* __restrict__ runs, uint64_t stride, const uint64_t* __restrict__ counts,
+                                int n_runs, int bins, const uint32_t* __restrict__ gt, const uint32_t* __restrict__ pos0,
+                                FrzMatchDev* __restrict__ out) {
+    for (int r = 0; r < n_runs; r++) {
+        const FrzMatchDev* run = runs + (uint64_t)r * stride;
+        const uint64_t cnt = counts[r];
+        for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += (uint64_t)gridDim.x * blockDim.x) {
+            const FrzMatchDev m = run[i];
+            const uint32_t s = min((uint32_t)m.score, (uint32_t)bins - 1);
+            out[pos0[r * bins + s] + ((uint32_t)i - gt[r * bins + s])] = m;
+        }
     }
 }
 }  // namespace
@@ -1180,7 +1260,7 @@ extern "C" frz_status frz_merge_runs_device(const frz_match* d_runs, uint64_t ru
     h[128] = total;
     // grow-only per-device scratch (no allocation on the steady-state path)
     struct MergeScratch { uint64_t* meta = nullptr; uint64_t* h_meta = nullptr; FrzMatchDev* cat = nullptr; FrzMatchDev* tmp = nullptr;
-                          uint32_t* hist = nullptr; uint64_t cap = 0; };
+                          uint32_t* hist = nullptr; uint32_t* tables = nullptr; uint64_t cap = 0; };
     static MergeScratch scratch[64];
     if (device >= 64) return frz_fail(FRZ_ERR_INVALID_ARG, "device index too large");
     MergeScratch& ms = scratch[device];
@@ -1188,17 +1268,30 @@ extern "C" frz_status frz_merge_runs_device(const frz_match* d_runs, uint64_t ru
         FRZ_CUDA_TRY(cudaMalloc(&ms.meta, sizeof h));
         FRZ_CUDA_TRY(cudaMallocHost(&ms.h_meta, sizeof h));
         FRZ_CUDA_TRY(cudaMalloc(&ms.hist, frz_sort_hist_words() * sizeof(uint32_t)));
+        FRZ_CUDA_TRY(cudaMalloc(&ms.tables, (size_t)2 * 64 * kMergeMaxBins * sizeof(uint32_t)));
     }
-    if (ms.cap < total) {
+    memcpy(ms.h_meta, h, sizeof h);
+    FRZ_CUDA_TRY(cudaMemcpyAsync(ms.meta, ms.h_meta, sizeof h, cudaMemcpyHostToDevice, stream));
+    const int bins = (int)std::min<uint32_t>(score_bound, 0xFFFFu) + 1;
+    if (by_score && bins <= kMergeMaxBins && total <= 0xFFFFFFFFull) {
+        // score-sorted runs: boundaries by binary search, one scatter pass (no concatenation, no re-sort)
+        uint32_t* gt = ms.tables;
+        uint32_t* pos0 = ms.tables + (size_t)64 * kMergeMaxBins;
+        const FrzMatchDev* runs = reinterpret_cast<const FrzMatchDev*>(d_runs);
+        k_merge_bounds<<<(n_runs * bins + 255) / 256, 256, 0, stream>>>(runs, run_stride, ms.meta, n_runs, bins, gt);
+        k_merge_bases<<<(bins + 127) / 128, 128, 0, stream>>>(gt, ms.meta, n_runs, bins, reversed ? 1 : 0, pos0);
+        k_merge_scatter<<<grid_for(total / std::max(n_runs, 1) + 1, 256), 256, 0, stream>>>(runs, run_stride, ms.meta, n_runs, bins, gt,
+                                                                                           pos0, reinterpret_cast<FrzMatchDev*>(d_out));
+        FRZ_CUDA_TRY(cudaGetLastError());
+        return FRZ_OK;  // asynchronous on `stream`
+    }
+    if (by_score && ms.cap < total) {
         cudaFree(ms.cat); cudaFree(ms.tmp); ms.cat = ms.tmp = nullptr; ms.cap = 0;
         const uint64_t want = total + total / 4 + 1024;
         FRZ_CUDA_TRY(cudaMalloc(&ms.cat, want * sizeof(FrzMatchDev)));
         FRZ_CUDA_TRY(cudaMalloc(&ms.tmp, want * sizeof(FrzMatchDev)));
         ms.cap = want;
     }
-    // (max_score_hint in the top 16 bits of `sort` is not part of the ABI; the bound is conservative)
-    memcpy(ms.h_meta, h, sizeof h);
-    FRZ_CUDA_TRY(cudaMemcpyAsync(ms.meta, ms.h_meta, sizeof h, cudaMemcpyHostToDevice, stream));
     FrzMatchDev* dst = by_score ? ms.cat : reinterpret_cast<FrzMatchDev*>(d_out);
     k_gather_runs<<<grid_for(total / std::max(n_runs, 1) + 1, 256), 256, 0, stream>>>(
         reinterpret_cast<const FrzMatchDev*>(d_runs), run_stride, ms.meta, ms.meta + 64, n_runs, reversed ? 1 : 0, dst);

@@ -888,7 +888,9 @@ frz_status frz_launch_prefilter(const FrzCorpusView& cv, const FrzPatternDev& pa
     static int slice_knob = -1;   // experiment knob: FRZ_PF_SLICE=8 forces the wide variant
     if (slice_knob < 0) { const char* e = getenv("FRZ_PF_SLICE"); slice_knob = e ? atoi(e) : 0; }
     const bool narrow = cv.max_gunits <= 4 && slice_knob != 8 && (pat.typo_mode == FRZ_T_0 || pat.typo_mode == FRZ_T_1);
-    const uint32_t bps = narrow ? 5 : 4;
+    static int bps_knob = -1;     // experiment knob: FRZ_PF_BLOCKS = resident blocks per SM of the narrow variant
+    if (bps_knob < 0) { const char* e = getenv("FRZ_PF_BLOCKS"); bps_knob = e ? atoi(e) : 5; }
+    const uint32_t bps = narrow ? (uint32_t)bps_knob : 4;
     const uint32_t grid = std::max<uint32_t>(1, std::min<uint32_t>((uint32_t)sms * bps, (total_groups + kWarps - 1) / kWarps));
     FRZ_CUDA_TRY(cudaMemsetAsync(ws.surv_bitmap, 0, (size_t)cv.n_tiles * 32 * sizeof(uint32_t), stream));
 #define FRZ_PF_LAUNCH(MODE) FRZ_PF_LAUNCH_S(MODE, 8)

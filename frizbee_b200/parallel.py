@@ -80,6 +80,7 @@ class ShardRunner:
         self.gathered = None
         self.merged = None
         self.bound = matcher.score_bound()
+        self.side = torch.cuda.Stream(self.dev) if self.world > 1 else None   # count exchange overlaps scoring
 
     def local(self):
         """This rank's shard → locally ordered run in HBM (asynchronous).  Returns (run tensor, count tensor)."""
@@ -97,8 +98,12 @@ class ShardRunner:
         run, count = self.local()
         if self.world == 1:
             return run, None
-        dist.all_gather_into_tensor(self.counts, count, group=self.group)
-        counts_h = np.asarray(self.counts.cpu().tolist(), dtype=np.uint64)      # the one host sync of the step
+        # the count is final once the prefilter has run: exchange it on a side stream while the shard is scored
+        _check(lib().frz_matcher_wait_count(self.matcher._h, self.side.cuda_stream))
+        with torch.cuda.stream(self.side):
+            dist.all_gather_into_tensor(self.counts, count, group=self.group)
+            counts_h = np.asarray(self.counts.cpu().tolist(), dtype=np.uint64)  # the one host sync of the step
+        torch.cuda.current_stream(self.dev).wait_stream(self.side)
         stride = max(int(counts_h.max()), 1)
         total = int(counts_h.sum())
         need = self.world * stride

@@ -224,6 +224,10 @@ FRZ_API frz_status frz_match_list_host_arrow(frz_matcher* m, const uint8_t* byte
  * cudaStream_t (NULL = default stream).  Asynchronous: returns after enqueueing. */
 FRZ_API frz_status frz_match_shard_device(frz_matcher* m, const frz_corpus* shard, uint32_t index_offset,
                                   frz_match* d_out, uint64_t cap, uint64_t* d_count, void* stream);
+/* The count of a shard call is known before its scores (it is the prefilter's survivor count): this makes
+ * `stream` (a second cudaStream_t) wait only until d_count has been written, so the count exchange of
+ * match_list_parallel (the `Vec` lengths the reference's k-merge reads, src/k_merge.rs:96-104) overlaps scoring. */
+FRZ_API frz_status frz_matcher_wait_count(frz_matcher* m, void* stream);
 
 /* k_merge_matches_by (src/k_merge.rs:90-131) on device: `d_runs` holds `n_runs` runs, run r at
  * d_runs + r*run_stride with run_counts_host[r] valid entries, each already ordered per `sort`.

@@ -340,3 +340,45 @@ def test_corpus_append_matches_one_shot_pack():
     assert got[got["index"] == n + 1]["exact"][0] == 1
     c.close()
     m.close()
+
+
+@pytest.mark.parametrize("n_runs", [2, 3, 8])
+def test_device_k_merge_equals_single_list(n_runs):
+    # frz_match_shard_device + frz_merge_runs_device on ONE GPU (no NCCL): shards are index ranges, each scored into a
+    # locally ordered run; the device merge must reproduce Matcher::match_list on the whole list for every
+    # SortStrategy (k_merge_matches_by_*, src/k_merge.rs:56-88), through the boundary-search merge (score bound
+    # known) and through the concatenate + stable sort fallback (bound unknown → 0).
+    import ctypes as C
+    import torch
+    from frizbee_b200 import parallel
+    n = 120_011
+    data, off = synth.generate("deadbeef", n, 40, 64, seed=99)
+    full = F.Corpus.from_arrow(data, off)
+    bounds = parallel.shard_bounds(n, n_runs)
+    shards = [F.Corpus.from_arrow(data, off[lo: hi + 1]) for lo, hi in bounds]
+    dev = torch.device("cuda", 0)
+    for sort in SortStrategy:
+        cfg = Config(max_typos=1, sort=sort)
+        m = F.Matcher("deadbeef", cfg)
+        want = m.match_list_array(full).copy()
+        stride = max(hi - lo for lo, hi in bounds)
+        runs = torch.zeros(n_runs * stride, dtype=torch.int64, device=dev)
+        cnt = torch.zeros(1, dtype=torch.int64, device=dev)
+        counts = np.zeros(n_runs, dtype=np.uint64)
+        for r, ((lo, hi), sh) in enumerate(zip(bounds, shards)):
+            view = runs[r * stride: (r + 1) * stride]
+            F._check(F.lib().frz_match_shard_device(m._h, sh._h, lo, view.data_ptr(), stride, cnt.data_ptr(), None))
+            counts[r] = int(cnt.item())
+        total = int(counts.sum())
+        assert total == len(want)
+        for bound in (m.score_bound(), 0):
+            out = torch.zeros(max(total, 1), dtype=torch.int64, device=dev)
+            F._check(F.lib().frz_merge_runs_device(runs.data_ptr(), stride, counts.ctypes.data, n_runs, int(sort), bound,
+                                                   out.data_ptr(), 0, None))
+            torch.cuda.synchronize()
+            got = out[:total].cpu().numpy().view(F.MATCH_DTYPE)
+            assert np.array_equal(got, want), (sort, bound)
+        m.close()
+    for sh in shards:
+        sh.close()
+    full.close()
