@@ -305,6 +305,368 @@ static bool prefilter_many(const Pf& p, size_t max_typos, size_t* ostart, size_t
     return false;
 }
 
+// ---------------------------------------------------------------------------------
+// Unicode needle path.  src/prefilter/mod.rs:21-96 (UnicodeChar, case_needle_unicode),
+// src/prefilter/algo/unicode.rs, src/prefilter/algo/unicode_typos.rs.
+// Case mappings come from oracle/unicode_case.inc (tools/gen_unicode_case.py): the data behind Rust's
+// char::to_lowercase / to_uppercase / is_uppercase, reduced to what the reference can use.
+// ---------------------------------------------------------------------------------
+#include "unicode_case.inc"
+
+struct UChar {
+    uint8_t c[4];
+    uint8_t f[4];
+    int len;
+};
+
+static int utf8_encode(uint32_t cp, uint8_t* o) {
+    if (cp < 0x80) { o[0] = (uint8_t)cp; return 1; }
+    if (cp < 0x800) { o[0] = (uint8_t)(0xC0 | (cp >> 6)); o[1] = (uint8_t)(0x80 | (cp & 0x3F)); return 2; }
+    if (cp < 0x10000) {
+        o[0] = (uint8_t)(0xE0 | (cp >> 12)); o[1] = (uint8_t)(0x80 | ((cp >> 6) & 0x3F)); o[2] = (uint8_t)(0x80 | (cp & 0x3F));
+        return 3;
+    }
+    o[0] = (uint8_t)(0xF0 | (cp >> 18)); o[1] = (uint8_t)(0x80 | ((cp >> 12) & 0x3F));
+    o[2] = (uint8_t)(0x80 | ((cp >> 6) & 0x3F)); o[3] = (uint8_t)(0x80 | (cp & 0x3F));
+    return 4;
+}
+// one scalar from valid UTF-8 (the needle is a Rust &str)
+static uint32_t utf8_decode(const uint8_t* s, size_t n, size_t* i) {
+    uint8_t b = s[*i];
+    int extra = b < 0x80 ? 0 : b < 0xE0 ? 1 : b < 0xF0 ? 2 : 3;
+    uint32_t cp = extra == 0 ? b : extra == 1 ? (b & 0x1Fu) : extra == 2 ? (b & 0x0Fu) : (b & 0x07u);
+    (*i)++;
+    for (int k = 0; k < extra && *i < n; k++, (*i)++) cp = (cp << 6) | (s[*i] & 0x3Fu);
+    return cp;
+}
+// char::is_uppercase (used by CaseMatching::Smart, src/lib.rs:370-376)
+static bool scalar_is_uppercase(uint32_t cp) {
+    if (cp < 0x80) return cp >= 'A' && cp <= 'Z';
+    size_t lo = 0, hi = sizeof(kUnicodeUpper) / sizeof(kUnicodeUpper[0]);
+    while (lo < hi) {
+        size_t mid = (lo + hi) / 2;
+        if (cp < kUnicodeUpper[mid][0]) hi = mid;
+        else if (cp > kUnicodeUpper[mid][1]) lo = mid + 1;
+        else return true;
+    }
+    return false;
+}
+// the opposite-case scalar of src/prefilter/mod.rs:76-91, or cp itself
+static uint32_t scalar_flip(uint32_t cp) {
+    if (cp < 0x80) {
+        if (cp >= 'a' && cp <= 'z') return cp - 32;
+        if (cp >= 'A' && cp <= 'Z') return cp + 32;
+        return cp;
+    }
+    size_t lo = 0, hi = sizeof(kUnicodeFlip) / sizeof(kUnicodeFlip[0]);
+    while (lo < hi) {
+        size_t mid = (lo + hi) / 2;
+        if (kUnicodeFlip[mid][0] < cp) lo = mid + 1; else hi = mid;
+    }
+    if (lo < sizeof(kUnicodeFlip) / sizeof(kUnicodeFlip[0]) && kUnicodeFlip[lo][0] == cp) return kUnicodeFlip[lo][1];
+    return cp;
+}
+static bool needle_has_uppercase(const uint8_t* needle, size_t n) {
+    for (size_t i = 0; i < n;)
+        if (scalar_is_uppercase(utf8_decode(needle, n, &i))) return true;
+    return false;
+}
+// src/prefilter/mod.rs:71-96 (case_needle_unicode)
+static std::vector<UChar> case_needle_unicode(const uint8_t* needle, size_t n, bool case_sensitive) {
+    std::vector<UChar> out;
+    for (size_t i = 0; i < n;) {
+        uint32_t cp = utf8_decode(needle, n, &i);
+        uint32_t fl = case_sensitive ? cp : scalar_flip(cp);
+        UChar u{};
+        u.len = utf8_encode(cp, u.c);
+        int fl_len = utf8_encode(fl, u.f);
+        if (fl_len != u.len) memcpy(u.f, u.c, 4);   // (the table only holds same-length pairs)
+        out.push_back(u);
+    }
+    return out;
+}
+
+struct UPf {
+    int lanes;
+    const std::vector<UChar>& needle;
+    const uint8_t* hay;
+    size_t len;
+    uint64_t all() const { return lanes == 64 ? ~0ull : ((1ull << lanes) - 1); }
+    uint64_t first_n(size_t n) const { return n >= (size_t)lanes ? all() : ((1ull << n) - 1); }
+    int lz(uint64_t m) const { return __builtin_clzll(m) - (64 - lanes); }
+    // B::eq of the chunk loaded at `pos` (load_window / load_window_maskless, src/prefilter/algo/load.rs):
+    // lanes past the end of the haystack hold over-read garbage in the reference; every caller masks them
+    // (the last-byte window is the shortest), so they are returned as "no match" here.
+    uint64_t eq(size_t pos, uint8_t b) const {
+        uint64_t m = 0;
+        for (int i = 0; i < lanes; i++) {
+            size_t q = pos + i;
+            if (q >= len) break;
+            if (hay[q] == b) m |= 1ull << i;
+        }
+        return m;
+    }
+    // match_unicode_char_prefix (unicode.rs:8-50)
+    uint64_t prefix(size_t start, int char_len, const uint8_t* chars) const {
+        uint64_t m = all();
+        for (int k = 0; k < char_len - 1; k++) m &= eq(start + k, chars[k]);
+        return m;
+    }
+    // char_variant_mask (unicode.rs:54-70) on the window whose last-byte chunk sits at start + char_len - 1
+    uint64_t variant(size_t start, uint64_t chunk_mask, int char_len, const uint8_t* chars) const {
+        uint64_t mask = eq(start + char_len - 1, chars[char_len - 1]) & chunk_mask;
+        if (mask && char_len > 1) mask &= prefix(start, char_len, chars);
+        return mask;
+    }
+    // unicode_char_mask (unicode.rs:73-117)
+    uint64_t char_mask(size_t start, const UChar& c) const {
+        if (start + c.len > len) return 0;
+        uint64_t chunk_mask = first_n(len - (start + c.len - 1));
+        return variant(start, chunk_mask, c.len, c.c) | variant(start, chunk_mask, c.len, c.f);
+    }
+};
+
+// unicode.rs:225-275 (find_last_unicode_char_pos) on the sub-slice hay[off..]
+static size_t find_last_unicode_char_pos(const UPf& base, const UChar& nc, size_t off) {
+    UPf s{base.lanes, base.needle, base.hay + off, base.len - off};
+    size_t len = s.len;
+    int cl = nc.len;
+    size_t start = len > (size_t)(s.lanes + cl - 1) ? len - (s.lanes + cl - 1) : 0;
+    for (;;) {
+        uint64_t chunk_mask = s.first_n(len - (start + cl - 1));
+        uint64_t mask = (s.eq(start + cl - 1, nc.c[cl - 1]) | s.eq(start + cl - 1, nc.f[cl - 1])) & chunk_mask;
+        if (mask && cl > 1) mask &= s.prefix(start, cl, nc.c) | s.prefix(start, cl, nc.f);
+        if (mask) return start + s.lanes - s.lz(mask) + cl - 1;
+        if (start == 0) break;
+        start = start > (size_t)s.lanes ? start - s.lanes : 0;
+    }
+    return len;
+}
+
+// unicode.rs:120-222 (match_haystack_unicode, 0 typos)
+static bool uprefilter_k0(const UPf& p, size_t* ostart, size_t* oend) {
+    size_t len = p.len;
+    if (len == 0) { *ostart = 0; *oend = 0; return false; }
+    bool can_skip = true;
+    size_t ms = 0, ni = 0, n = p.needle.size();
+    const UChar* nc = &p.needle[0];
+    size_t start = 0;
+    while (start + nc->len <= len) {
+        int char_len = nc->len;
+        uint64_t valid = p.first_n(len - (start + char_len - 1));
+        uint64_t available = p.all();
+        for (;;) {
+            uint64_t chunk_mask = available & valid;
+            uint64_t mask = p.variant(start, chunk_mask, nc->len, nc->c) | p.variant(start, chunk_mask, nc->len, nc->f);
+            if (!mask) break;
+            available = Pf::ctl(available, mask);
+            if (can_skip) { ms = start + Pf::tz(mask); can_skip = false; }
+            if (ni + 1 < n) {
+                ni++;
+                nc = &p.needle[ni];
+                if (nc->len != char_len) {
+                    if (start + nc->len > len) break;
+                    char_len = nc->len;
+                    valid = p.first_n(len - (start + char_len - 1));
+                }
+            } else if (start + nc->len - 1 + p.lanes >= len) {
+                *ostart = ms;
+                *oend = start + p.lanes - p.lz(mask) + nc->len - 1;
+                return true;
+            } else {
+                *ostart = ms;
+                *oend = start + find_last_unicode_char_pos(p, *nc, start);
+                return true;
+            }
+        }
+        start += p.lanes;
+    }
+    *ostart = ms;
+    *oend = len;
+    return false;
+}
+
+// unicode_typos.rs:486-508 (find_end_pos_with_unicode_typos)
+static size_t find_end_pos_with_unicode_typos(const UPf& p, size_t max_typos) {
+    size_t len = p.len, n = p.needle.size();
+    size_t first = n - 1 - max_typos;
+    size_t start = len > (size_t)p.lanes ? len - p.lanes : 0;
+    for (;;) {
+        size_t end_pos = 0;
+        for (size_t i = first; i < n; i++) {
+            uint64_t mask = p.char_mask(start, p.needle[i]);
+            if (mask) end_pos = std::max(end_pos, start + p.lanes - p.lz(mask) + p.needle[i].len - 1);
+        }
+        if (end_pos) return end_pos;
+        if (start == 0) break;
+        start = start > (size_t)p.lanes ? start - p.lanes : 0;
+    }
+    return len;
+}
+
+// unicode_typos.rs:15-143 (match_haystack_unicode_1_typo)
+static bool uprefilter_k1(const UPf& p, size_t* ostart, size_t* oend) {
+    size_t len = p.len, n = p.needle.size();
+    if (n <= 1) { *ostart = 0; *oend = len; return true; }
+    if (len == 0) { *ostart = 0; *oend = 0; return false; }
+    size_t f = 0, s = 1, ms = SIZE_MAX;
+    auto found = [&]() { *ostart = ms; *oend = find_end_pos_with_unicode_typos(p, 1); return true; };
+    for (size_t start = 0; start < len; start += p.lanes) {
+        uint64_t fm = p.char_mask(start, p.needle[f]);
+        uint64_t sm = p.char_mask(start, p.needle[s]);
+        uint64_t fc = p.all(), sc = p.all();
+        for (;;) {
+            bool advanced = false;
+            size_t cand = f + 1;
+            if (cand > s) {
+                if (cand == n) return found();
+                s = cand; sc = fc; sm = p.char_mask(start, p.needle[s]);
+            } else if (cand == s && fc > sc) {
+                sc = fc;
+            }
+            uint64_t x = fm & fc;
+            if (x) {
+                ms = std::min(ms, start + (size_t)Pf::tz(x));
+                f++;
+                fc = Pf::ctl(fc, x);
+                fm = p.char_mask(start, p.needle[f]);
+                advanced = true;
+            }
+            uint64_t y = sm & sc;
+            if (y) {
+                ms = std::min(ms, start + (size_t)Pf::tz(y));
+                s++;
+                if (s >= n) return found();
+                sc = Pf::ctl(sc, y);
+                sm = p.char_mask(start, p.needle[s]);
+                advanced = true;
+            }
+            if (!advanced) break;
+        }
+    }
+    *ostart = ms == SIZE_MAX ? 0 : ms;
+    *oend = len;
+    return false;
+}
+
+// unicode_typos.rs:146-333 (match_haystack_unicode_2_typos)
+static bool uprefilter_k2(const UPf& p, size_t* ostart, size_t* oend) {
+    size_t len = p.len, n = p.needle.size();
+    if (n <= 2) { *ostart = 0; *oend = len; return true; }
+    if (len == 0) { *ostart = 0; *oend = 0; return false; }
+    size_t i1 = 0, i2 = 1, i3 = 2, ms = SIZE_MAX;
+    auto found = [&]() { *ostart = ms; *oend = find_end_pos_with_unicode_typos(p, 2); return true; };
+    for (size_t start = 0; start < len; start += p.lanes) {
+        uint64_t m1 = p.char_mask(start, p.needle[i1]);
+        uint64_t m2 = p.char_mask(start, p.needle[i2]);
+        uint64_t m3 = p.char_mask(start, p.needle[i3]);
+        uint64_t c1 = p.all(), c2 = p.all(), c3 = p.all();
+        for (;;) {
+            bool advanced = false;
+            size_t cand2 = i1 + 1;
+            if (cand2 > i2) {
+                if (cand2 == n) return found();
+                i2 = cand2; c2 = c1; m2 = p.char_mask(start, p.needle[i2]);
+            } else if (cand2 == i2 && c1 > c2) {
+                c2 = c1;
+            }
+            size_t cand3 = i2 + 1;
+            if (cand3 > i3) {
+                if (cand3 == n) return found();
+                i3 = cand3; c3 = c2; m3 = p.char_mask(start, p.needle[i3]);
+            } else if (cand3 == i3 && c2 > c3) {
+                c3 = c2;
+            }
+            uint64_t x1 = m1 & c1;
+            if (x1) {
+                ms = std::min(ms, start + (size_t)Pf::tz(x1));
+                i1++;
+                c1 = Pf::ctl(c1, x1);
+                m1 = p.char_mask(start, p.needle[i1]);
+                advanced = true;
+            }
+            uint64_t x2 = m2 & c2;
+            if (x2) {
+                ms = std::min(ms, start + (size_t)Pf::tz(x2));
+                i2++;
+                if (i2 >= n) return found();
+                c2 = Pf::ctl(c2, x2);
+                m2 = p.char_mask(start, p.needle[i2]);
+                advanced = true;
+            }
+            uint64_t x3 = m3 & c3;
+            if (x3) {
+                ms = std::min(ms, start + (size_t)Pf::tz(x3));
+                i3++;
+                if (i3 >= n) return found();
+                c3 = Pf::ctl(c3, x3);
+                m3 = p.char_mask(start, p.needle[i3]);
+                advanced = true;
+            }
+            if (!advanced) break;
+        }
+    }
+    *ostart = ms == SIZE_MAX ? 0 : ms;
+    *oend = len;
+    return false;
+}
+
+// unicode_typos.rs:336-472 (match_haystack_unicode_many_typos_impl)
+static bool uprefilter_many(const UPf& p, size_t max_typos, size_t* ostart, size_t* oend) {
+    size_t len = p.len, n = p.needle.size();
+    if (n <= max_typos) { *ostart = 0; *oend = len; return true; }
+    if (len == 0) { *ostart = 0; *oend = 0; return false; }
+    size_t path_count = max_typos + 1;
+    std::vector<size_t> idx(path_count, 0);
+    std::vector<uint64_t> nm(path_count, 0);
+    size_t ms = SIZE_MAX;
+    auto found = [&]() { *ostart = ms; *oend = find_end_pos_with_unicode_typos(p, max_typos); return true; };
+    for (size_t start = 0; start < len; start += p.lanes) {
+        uint64_t chunk_mask = p.all();
+        for (size_t k = 0; k < path_count; k++) nm[k] = p.char_mask(start, p.needle[idx[k]]);
+        for (;;) {
+            for (size_t k = 1; k < path_count; k++) {
+                size_t cand = idx[k - 1] + 1;
+                if (cand > idx[k]) {
+                    if (cand == n) return found();
+                    idx[k] = cand;
+                    nm[k] = p.char_mask(start, p.needle[cand]);
+                }
+            }
+            uint64_t mm = 0;
+            for (size_t k = 0; k < path_count; k++) mm |= nm[k];
+            uint64_t matches = mm & chunk_mask;
+            if (!matches) break;
+            size_t hit_pos = Pf::tz(matches);
+            uint64_t hit = matches & p.first_n(hit_pos + 1);
+            ms = std::min(ms, start + hit_pos);
+            for (size_t k = 0; k < path_count; k++) {
+                if (!(nm[k] & hit)) continue;
+                idx[k]++;
+                if (idx[k] == n) return found();
+                nm[k] = p.char_mask(start, p.needle[idx[k]]);
+            }
+            chunk_mask = Pf::ctl(chunk_mask, hit);
+        }
+    }
+    *ostart = ms == SIZE_MAX ? 0 : ms;
+    *oend = len;
+    return false;
+}
+
+// src/matcher/algo.rs:171-193 (prefilter_haystack dispatch), UNICODE = true
+static bool uprefilter(const std::vector<UChar>& needle, const uint8_t* hay, size_t len, int max_typos, int lanes,
+                       size_t* s, size_t* e) {
+    if (max_typos < 0) { *s = 0; *e = len; return true; }
+    UPf p{lanes, needle, hay, len};
+    switch (max_typos) {
+        case 0: return uprefilter_k0(p, s, e);
+        case 1: return uprefilter_k1(p, s, e);
+        case 2: return uprefilter_k2(p, s, e);
+        default: return uprefilter_many(p, (size_t)max_typos, s, e);
+    }
+}
+
 // src/matcher/algo.rs:171-193 (prefilter_haystack dispatch); max_typos < 0 == NO_PREFILTER
 static bool prefilter(const std::vector<Pair>& needle, const uint8_t* hay, size_t len, int max_typos,
                       int lanes, size_t* s, size_t* e) {
@@ -548,9 +910,151 @@ static bool score_fits_in_u8(size_t needle_len, const frz_scoring& s) {
 static bool respects_case(int casing, const uint8_t* needle, size_t n) {
     if (casing == FRZ_CASE_IGNORE) return false;
     if (casing == FRZ_CASE_RESPECT) return true;
-    for (size_t i = 0; i < n; i++)
-        if (needle[i] >= 'A' && needle[i] <= 'Z') return true;
-    return false;
+    return needle_has_uppercase(needle, n);   // needle.chars().any(char::is_uppercase), src/lib.rs:370-376
+}
+
+// ---------------------------------------------------------------------------------
+// Unicode Smith-Waterman: src/smith_waterman/algo/unicode.rs + unicode_gap.rs.
+// Rows are needle scalars, columns stay haystack BYTES; continuation bytes are transport lanes.
+// ---------------------------------------------------------------------------------
+// unicode_gap.rs:133-165 (unicode_gap_step)
+static void unicode_gap_step(const Arith& A, int shift, SV& row, SV& pend, const SV& adj_row, const SV& adj_pend,
+                             const SV& cgex, const SV& send, const SV& total, const SV& gop) {
+    SV shifted_row = A.srp(row, adj_row, shift);
+    SV shifted_pend = A.srp(pend, adj_pend, shift);
+    SV scalar_gex = A.subs(total, cgex);
+    SV crossed = A.band(shifted_pend, send);
+    SV pen = A.add(scalar_gex, A.band(gop, crossed));
+    SV cand = A.subs(shifted_row, pen);
+    row = A.max(row, cand);
+    SV cand_pend = A.subs(shifted_pend, send);
+    pend = A.max(pend, cand_pend);
+}
+// unicode_gap.rs:168-194 (prepare_next_unicode_gap_step)
+static void unicode_gap_prepare(const Arith& A, int shift, SV& cgex, SV& adj_cgex, SV& send, SV& adj_send, SV& total) {
+    SV zero = A.zero();
+    SV shifted_cgex = A.srp(cgex, adj_cgex, shift);
+    cgex = A.add(cgex, shifted_cgex);
+    adj_cgex = A.add(adj_cgex, A.srp(adj_cgex, zero, shift));
+    SV shifted_send = A.srp(send, adj_send, shift);
+    send = A.max(send, shifted_send);
+    adj_send = A.max(adj_send, A.srp(adj_send, zero, shift));
+    total = A.add(total, total);
+}
+// unicode_gap.rs:196-262 (unicode_propagator!: prepare shifts 1..LANES/4, final shift LANES/2)
+static void propagate_unicode(const Arith& A, SV& row, SV& pend, const SV& adj_row, const SV& adj_pend, SV cgex, SV adj_cgex,
+                              SV send, SV adj_send, const SV& gop, const SV& gex) {
+    SV total = gex;
+    int s = 1;
+    for (; s < A.lanes / 2; s <<= 1) {
+        unicode_gap_step(A, s, row, pend, adj_row, adj_pend, cgex, send, total, gop);
+        unicode_gap_prepare(A, s, cgex, adj_cgex, send, adj_send, total);
+    }
+    unicode_gap_step(A, s, row, pend, adj_row, adj_pend, cgex, send, total, gop);
+}
+
+// unicode.rs:9-224 (score_haystack_unicode)
+static uint16_t sw_score_unicode(const uint8_t* needle_raw, size_t nbytes, const frz_scoring& sc, bool case_sensitive,
+                                 const uint8_t* hay, size_t hl, bool include_prefix, int lanes, bool u8) {
+    if (hl > kMaxHaystackLen) {
+        int g = match_greedy(needle_raw, nbytes, hay, hl, sc, case_sensitive, include_prefix);
+        return g < 0 ? 0 : (uint16_t)g;
+    }
+    std::vector<UChar> needle = case_needle_unicode(needle_raw, nbytes, case_sensitive);
+    size_t n = needle.size();
+    if (n == 0) return 0;
+    Arith A{lanes, u8};
+    size_t chunks = (hl + lanes - 1) / lanes + 1;
+    std::vector<SV> H((n + 1) * chunks, A.zero());
+    std::vector<SV> pending(n + 1, A.zero());
+    auto sat_sub16 = [](uint16_t a, uint16_t b) { return (uint16_t)(a > b ? a - b : 0); };
+    auto sat_add16 = [](uint16_t a, uint16_t b) { uint32_t r = (uint32_t)a + b; return (uint16_t)(r > 0xFFFF ? 0xFFFF : r); };
+    SV gex = A.splat(sc.gap_extend_penalty);
+    SV gop = A.splat(sat_sub16(sc.gap_open_penalty, sc.gap_extend_penalty));
+    SV match_score = A.splat(sat_add16(sc.match_score, sc.mismatch_penalty));
+    SV mismatch = A.splat(sc.mismatch_penalty);
+    SV case_bonus = A.splat(sc.matching_case_bonus);
+    SV cap_bonus = A.splat(sc.capitalization_bonus);
+    SV delim_bonus = A.splat(sc.delimiter_bonus);
+    SV prefix_masked = include_prefix ? A.first_lane(sc.prefix_bonus) : A.zero();
+    const uint16_t FULL = A.full();
+    bool prev_chunk_last_delim = false, prev_chunk_last_lower = false;
+    SV prev_cgex = A.zero(), prev_sstart = A.zero();
+    SV maxv = A.zero();
+    for (size_t col = 1; col < chunks; col++) {
+        size_t cs = (col - 1) * lanes;
+        // load_partial at chunk_start + k, zero-filled past the end (scalar.rs:78-85)
+        uint8_t b[4][kMaxLanes];
+        for (int k = 0; k < 4; k++)
+            for (int i = 0; i < lanes; i++) {
+                size_t pos = cs + k + i;
+                b[k][i] = pos < hl ? hay[pos] : 0;
+            }
+        // unicode_scalar_masks (unicode.rs:243-259) + valid_haystack_lanes (:262-273)
+        size_t valid_lanes = std::min<size_t>(hl > cs ? hl - cs : 0, (size_t)lanes);
+        bool cont[kMaxLanes], sst[kMaxLanes];
+        SV sstart = A.zero(), cgex = A.zero();
+        for (int i = 0; i < lanes; i++) {
+            bool valid = (size_t)i < valid_lanes;
+            cont[i] = b[0][i] > 0x7f && b[0][i] < 0xc0 && valid;
+            sst[i] = !cont[i] && valid;
+            sstart.v[i] = sst[i] ? FULL : 0;
+            cgex.v[i] = cont[i] ? gex.v[i] : 0;
+        }
+        bool up[kMaxLanes] = {false}, lo[kMaxLanes] = {false}, dl[kMaxLanes] = {false};
+        for (int i = 0; i < lanes; i++) {
+            uint8_t c = b[0][i];
+            up[i] = c < 'Z' + 1 && c > 'A' - 1;
+            lo[i] = c < 'z' + 1 && c > 'a' - 1;
+            bool digit = c > '0' - 1 && c < '9' + 1;
+            dl[i] = !(up[i] || lo[i] || digit || c > 127);
+        }
+        SV cap_m = A.zero(), delim_m = A.zero();
+        for (int i = 0; i < lanes; i++) {
+            bool prev_lower = i == 0 ? prev_chunk_last_lower : lo[i - 1];
+            bool prev_delim = i == 0 ? prev_chunk_last_delim : dl[i - 1];
+            cap_m.v[i] = (up[i] && prev_lower) ? FULL : 0;
+            delim_m.v[i] = (prev_delim && !dl[i]) ? FULL : 0;
+        }
+        prev_chunk_last_lower = lo[lanes - 1];
+        prev_chunk_last_delim = dl[lanes - 1];
+        SV bonuses = A.add(A.add(A.add(A.band(delim_m, delim_bonus), A.band(cap_m, cap_bonus)), prefix_masked), match_score);
+        prefix_masked = A.zero();
+
+        SV up_gap_mask = A.zero(), prev_row = A.zero(), row = A.zero();
+        for (size_t r = 1; r <= n; r++) {
+            const UChar& nc = needle[r - 1];
+            // unicode_char_match_mask (unicode.rs:227-245): the scalar's bytes at lane offsets 0..len-1, scalar starts only
+            SV mm = A.zero(), ex = A.zero();
+            for (int i = 0; i < lanes; i++) {
+                bool e = sst[i], f = sst[i];
+                for (int k = 0; k < nc.len; k++) {
+                    e = e && b[k][i] == nc.c[k];
+                    f = f && b[k][i] == nc.f[k];
+                }
+                mm.v[i] = (e || f) ? FULL : 0;
+                ex.v[i] = e ? FULL : 0;
+            }
+            SV diag = A.srp(prev_row, H[(r - 1) * chunks + (col - 1)], 1);
+            diag = A.add(diag, A.band(mm, bonuses));
+            diag = A.subs(diag, mismatch);
+            diag = A.add(diag, A.band(ex, case_bonus));
+            diag = A.band(diag, sstart);
+            SV upv = A.subs(A.subs(prev_row, gex), A.band(up_gap_mask, gop));
+            upv = A.band(upv, sstart);
+            row = A.max(diag, upv);
+            SV pend = mm;
+            propagate_unicode(A, row, pend, H[r * chunks + (col - 1)], pending[r], cgex, prev_cgex, sstart, prev_sstart, gop, gex);
+            H[r * chunks + col] = row;
+            pending[r] = pend;
+            prev_row = row;
+            up_gap_mask = mm;
+        }
+        maxv = A.max(maxv, row);
+        prev_cgex = cgex;
+        prev_sstart = sstart;
+    }
+    return A.hmax(maxv);
 }
 
 // ---------------------------------------------------------------------------------
@@ -616,6 +1120,62 @@ static bool lit_find(int mode, const std::vector<Pair>& nd, const frz_scoring& s
     return false;
 }
 
+// Literal matcher, unicode path (literal/algo.rs:159-230 with UNICODE = true): whole scalars compare against the
+// original or the case-flipped encoding, and each scalar is scored once at its first byte.
+static bool ulit_matches_at(const std::vector<UChar>& nd, const uint8_t* hay, size_t pos) {
+    size_t k = pos;
+    for (const UChar& c : nd) {
+        if (memcmp(hay + k, c.c, c.len) != 0 && memcmp(hay + k, c.f, c.len) != 0) return false;
+        k += c.len;
+    }
+    return true;
+}
+static uint16_t ulit_score_at(const std::vector<UChar>& nd, size_t needle_bytes, const frz_scoring& s, const uint8_t* hay, size_t hl,
+                              size_t pos) {
+    uint16_t score = 0;
+    size_t st = pos;
+    for (const UChar& c : nd) {
+        uint16_t sc = s.match_score;
+        if (memcmp(hay + st, c.c, c.len) == 0) sc += s.matching_case_bonus;
+        if (st == 0) sc += s.prefix_bonus;
+        else {
+            uint8_t byte = hay[st], prev = hay[st - 1];
+            if (byte >= 'A' && byte <= 'Z' && prev >= 'a' && prev <= 'z') sc += s.capitalization_bonus;
+            if (lit_is_delim(prev) && !lit_is_delim(byte)) sc += s.delimiter_bonus;
+        }
+        score += sc;
+        st += c.len;
+    }
+    if (pos == 0 && needle_bytes == hl) score += s.exact_match_bonus;
+    return score;
+}
+static bool ulit_find(int mode, const std::vector<UChar>& nd, size_t n, const frz_scoring& s, const uint8_t* hay, size_t hl,
+                      size_t* opos, uint16_t* oscore) {
+    if (hl < n) return false;
+    auto at = [&](size_t pos) {
+        if (!ulit_matches_at(nd, hay, pos)) return false;
+        *opos = pos; *oscore = ulit_score_at(nd, n, s, hay, hl, pos);
+        return true;
+    };
+    switch (mode) {
+        case FRZ_MATCHING_EXACT: return hl == n && at(0);
+        case FRZ_MATCHING_PREFIX: return at(0);
+        case FRZ_MATCHING_SUFFIX: return at(hl - n);
+        case FRZ_MATCHING_SUBSTRING: {
+            bool have = false;
+            size_t bp = 0; uint16_t bs = 0;
+            for (size_t pos = 0; pos + n <= hl; pos++) {
+                if (!ulit_matches_at(nd, hay, pos)) continue;
+                uint16_t sc = ulit_score_at(nd, n, s, hay, hl, pos);
+                if (!have || sc > bs) { have = true; bp = pos; bs = sc; }
+            }
+            if (have) { *opos = bp; *oscore = bs; }
+            return have;
+        }
+    }
+    return false;
+}
+
 // One compiled pattern (src/matcher/mod.rs:193-205 compile + get_backend :448-498)
 struct OPattern {
     std::vector<uint8_t> needle;
@@ -628,7 +1188,7 @@ struct OPattern {
     int pf_lanes;     // prefilter lanes
     bool u8;
     size_t min_hay_len;
-    bool unsupported;
+    bool unicode;     // UnicodeMatching::respects_unicode_for(needle): the UNICODE = true specialisations
 };
 
 // src/matcher/algo.rs:78-103 (match_list_into_impl) + :229-263 (smith_waterman_one) + :331-338 (trim)
@@ -636,24 +1196,30 @@ struct OPattern {
 static void match_list_into(const OPattern& p, const uint8_t* bytes, const uint64_t* offsets, uint64_t n,
                             uint32_t index_offset, std::vector<frz_match>& out) {
     std::vector<Pair> nd = case_needle(p.needle.data(), p.needle.size(), p.case_sensitive);
+    std::vector<UChar> und = case_needle_unicode(p.needle.data(), p.needle.size(), p.case_sensitive);
     for (uint64_t i = 0; i < n; i++) {
         const uint8_t* hay = bytes + offsets[i];
         size_t hl = (size_t)(offsets[i + 1] - offsets[i]);
         uint32_t index = index_offset + (uint32_t)i;
         if (p.matching != FRZ_MATCHING_FUZZY) {
             size_t pos; uint16_t sc;
-            if (lit_find(p.matching, nd, p.scoring, hay, hl, &pos, &sc))
-                out.push_back({index, sc, (uint8_t)(pos == 0 && nd.size() == hl), 0});
+            bool hit = p.unicode ? ulit_find(p.matching, und, p.needle.size(), p.scoring, hay, hl, &pos, &sc)
+                                 : lit_find(p.matching, nd, p.scoring, hay, hl, &pos, &sc);
+            if (hit) out.push_back({index, sc, (uint8_t)(pos == 0 && p.needle.size() == hl), 0});
             continue;
         }
         if (hl < p.min_hay_len) continue;
         size_t s, e;
-        if (!prefilter(nd, hay, hl, p.max_typos, p.pf_lanes, &s, &e)) continue;
+        bool pass = p.unicode ? uprefilter(und, hay, hl, p.max_typos, p.pf_lanes, &s, &e)
+                              : prefilter(nd, hay, hl, p.max_typos, p.pf_lanes, &s, &e);
+        if (!pass) continue;
         s = s > 0 ? s - 1 : 0;
         bool include_exact = s == 0 && e == hl;
         const uint8_t* w = hay + s;
         size_t wl = e - s;
-        uint16_t score = sw_score(p.needle.data(), p.needle.size(), p.scoring, p.case_sensitive, w, wl, s == 0, p.lanes, p.u8);
+        uint16_t score = p.unicode
+            ? sw_score_unicode(p.needle.data(), p.needle.size(), p.scoring, p.case_sensitive, w, wl, s == 0, p.lanes, p.u8)
+            : sw_score(p.needle.data(), p.needle.size(), p.scoring, p.case_sensitive, w, wl, s == 0, p.lanes, p.u8);
         bool exact = include_exact && wl == p.needle.size() && memcmp(w, p.needle.data(), wl) == 0;
         if (exact) score = (uint16_t)(score + p.scoring.exact_match_bonus);
         out.push_back({index, score, (uint8_t)exact, 0});
@@ -738,8 +1304,8 @@ static bool compile(const frz_pattern& src, const frz_config& cfg, OPattern* o) 
         if (src.needle[i] >= 0x80) ascii = false;
         if ((src.needle[i] & 0xC0) != 0x80) nchars++;
     }
-    // UnicodeMatching::respects_unicode_for (src/lib.rs:394-401): the unicode kernels are not restated
-    o->unsupported = (unicode == FRZ_UNICODE_ALWAYS) || (unicode == FRZ_UNICODE_SMART && !ascii);
+    // UnicodeMatching::respects_unicode_for (src/lib.rs:394-401)
+    o->unicode = (unicode == FRZ_UNICODE_ALWAYS) || (unicode == FRZ_UNICODE_SMART && !ascii);
     int lanes8 = cfg.emulate_lanes ? cfg.emulate_lanes : 64;
     o->u8 = score_fits_in_u8(src.needle_len, o->scoring);
     o->lanes = o->u8 ? lanes8 : lanes8 / 2;
@@ -768,6 +1334,30 @@ int frzo_prefilter(const uint8_t* needle, size_t n, int case_sensitive, const ui
 uint16_t frzo_sw_score(const uint8_t* needle, size_t n, const frz_scoring* sc, int case_sensitive,
                        const uint8_t* hay, size_t len, int include_prefix, int lanes, int score_bits) {
     return sw_score(needle, n, *sc, case_sensitive != 0, hay, len, include_prefix != 0, lanes, score_bits == 8);
+}
+
+// unicode-needle unit entry points (src/prefilter/algo/unicode*.rs, src/smith_waterman/algo/unicode.rs)
+int frzo_prefilter_unicode(const uint8_t* needle, size_t n, int case_sensitive, const uint8_t* hay, size_t len,
+                           int max_typos, int lanes, uint64_t* start, uint64_t* end) {
+    std::vector<UChar> nd = case_needle_unicode(needle, n, case_sensitive != 0);
+    size_t s = 0, e = 0;
+    bool ok = uprefilter(nd, hay, len, max_typos, lanes, &s, &e);
+    *start = s;
+    *end = e;
+    return ok ? 1 : 0;
+}
+
+uint16_t frzo_sw_score_unicode(const uint8_t* needle, size_t n, const frz_scoring* sc, int case_sensitive,
+                               const uint8_t* hay, size_t len, int include_prefix, int lanes, int score_bits) {
+    return sw_score_unicode(needle, n, *sc, case_sensitive != 0, hay, len, include_prefix != 0, lanes, score_bits == 8);
+}
+
+// case_needle_unicode for one scalar: writes the flipped scalar's UTF-8 (same length as the input) and returns that length
+int frzo_flip_scalar(const uint8_t* utf8, size_t n, uint8_t* out) {
+    std::vector<UChar> nd = case_needle_unicode(utf8, n, false);
+    if (nd.size() != 1) return -1;
+    memcpy(out, nd[0].f, nd[0].len);
+    return nd[0].len;
 }
 
 uint16_t frzo_sw_score_col_limit(const uint8_t* needle, size_t n, const frz_scoring* sc, int case_sensitive,
@@ -823,7 +1413,6 @@ uint64_t frzo_match_list_into(const frz_pattern* patterns, size_t np, const frz_
     for (size_t i = 0; i < np; i++) {
         OPattern o;
         if (compile(patterns[i], *cfg, &o)) {
-            if (o.unsupported) return UINT64_MAX;  // unicode-needle path not restated
             pats.push_back(o);
         }
     }

@@ -42,6 +42,12 @@ def lib():
         L.frzo_sw_score.restype = C.c_uint16
         L.frzo_sw_score.argtypes = [u8p, C.c_size_t, C.POINTER(CScoring), C.c_int, u8p, C.c_size_t,
                                     C.c_int, C.c_int, C.c_int]
+        L.frzo_prefilter_unicode.restype = C.c_int
+        L.frzo_prefilter_unicode.argtypes = L.frzo_prefilter.argtypes
+        L.frzo_sw_score_unicode.restype = C.c_uint16
+        L.frzo_sw_score_unicode.argtypes = L.frzo_sw_score.argtypes
+        L.frzo_flip_scalar.restype = C.c_int
+        L.frzo_flip_scalar.argtypes = [u8p, C.c_size_t, C.POINTER(C.c_uint8)]
         L.frzo_match_greedy.restype = C.c_int
         L.frzo_match_greedy.argtypes = [u8p, C.c_size_t, C.POINTER(CScoring), C.c_int, u8p, C.c_size_t, C.c_int]
         L.frzo_score_fits_in_u8.restype = C.c_int
@@ -82,6 +88,33 @@ def sw_score(needle, haystack, scoring: Scoring = Scoring(), case_sensitive: boo
     sc = CScoring.of(scoring)
     return int(lib().frzo_sw_score(n, len(n), C.byref(sc), int(case_sensitive), h, len(h),
                                    int(include_prefix), lanes, score_bits))
+
+
+def prefilter_unicode(needle, haystack, max_typos: Optional[int] = 0, lanes: int = 16,
+                      case_sensitive: bool = False) -> Tuple[bool, int, int]:
+    """Prefilter::match_haystack_unicode* → (matched, start, end)."""
+    n, h = _b(needle), _b(haystack)
+    s, e = C.c_uint64(), C.c_uint64()
+    ok = lib().frzo_prefilter_unicode(n, len(n), int(case_sensitive), h, len(h), -1 if max_typos is None else max_typos,
+                                      lanes, C.byref(s), C.byref(e))
+    return bool(ok), int(s.value), int(e.value)
+
+
+def sw_score_unicode(needle, haystack, scoring: Scoring = Scoring(), case_sensitive: bool = False,
+                     include_prefix: bool = True, lanes: int = 8, score_bits: int = 16) -> int:
+    """SmithWaterman::<B>::score_haystack_unicode for backend B = (lanes, score_bits)."""
+    n, h = _b(needle), _b(haystack)
+    sc = CScoring.of(scoring)
+    return int(lib().frzo_sw_score_unicode(n, len(n), C.byref(sc), int(case_sensitive), h, len(h),
+                                           int(include_prefix), lanes, score_bits))
+
+
+def flip_scalar(ch: str) -> str:
+    """The opposite-case scalar case_needle_unicode pairs with `ch` (itself when there is none)."""
+    b = ch.encode("utf-8")
+    out = (C.c_uint8 * 4)()
+    n = lib().frzo_flip_scalar(b, len(b), out)
+    return bytes(out[:n]).decode("utf-8")
 
 
 def match_greedy(needle, haystack, scoring: Scoring = Scoring(), case_sensitive: bool = False,

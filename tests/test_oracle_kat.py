@@ -399,9 +399,8 @@ def test_radix_sort_and_strategies():
     assert [m.index for m in O.match_list("foo", hay, Config(sort=SortStrategy.IndexDesc))] == [5, 3, 2, 1, 0]
 
 
-def test_unicode_needle_is_flagged_not_faked():
-    with pytest.raises(NotImplementedError):
-        O.match_list("é다😀", ["é다😀"])
+def test_unicode_ignore_takes_the_byte_path():
+    assert len(O.match_list("é다😀", ["é다😀"])) == 1      # Smart + non-ASCII needle: unicode path (tests below)
     # UnicodeMatching::Ignore takes the byte path (src/lib.rs:394-399)
     m = O.match_list("é", ["xxé"], Config(unicode=UnicodeMatching.Ignore, sort=SortStrategy.IndexAsc))
     assert len(m) == 1
@@ -436,3 +435,137 @@ def test_column_limit_property(lanes, bits):
     # sanity: the search does find counterexamples when real columns are cut off
     csc = O.CScoring.of(Scoring())
     assert L.frzo_col_limit_search(1, 20000, lanes, bits, -4, C.byref(csc), None, None, None) > 0
+
+
+# ---------------------------------------------------------------- unicode-needle path
+U_LANES = [16, 32, 64]
+
+
+def _ulen(s):
+    return len(s.encode("utf-8"))
+
+
+@pytest.mark.parametrize("lanes", U_LANES)
+def test_unicode_prefilter_kats(lanes):
+    # src/prefilter/mod.rs:279-404 (unicode_prefilter_* tests; every backend must agree with the scalar one)
+    pu = lambda n, h, k=0, cs=False: O.prefilter_unicode(n, h, k, lanes, cs)
+    assert pu("إن", "xxإنyy") == (True, 2, 6)
+    assert pu("니다", "xx니__다yy") == (True, 2, 10)
+    assert pu("😀", "xx😀yy") == (True, 2, 6)
+    wrong_first, wrong_second = "ۥ", "؆"
+    fp = wrong_first + wrong_second
+    assert not pu("إن", fp)[0]
+    h = fp + "__إن"
+    assert pu("إن", h) == (True, _ulen(fp) + 2, _ulen(h))
+    assert pu("é", "٩É") == (True, 2, 4)
+    assert not pu("é", "٩É", 0, True)[0]
+    assert pu("éé", "٩É٩É٩É", 1)[0]
+    for prefix_len in [0, 1, 7, 14, 15, 16, 31, 32, 63, 64]:
+        h = "x" * prefix_len + "إن"
+        assert pu("إن", h) == (True, prefix_len, _ulen(h)), prefix_len
+    h = "xxإن" + "x" * 32 + "نzz"
+    assert pu("إن", h) == (True, 2, _ulen(h[: h.rfind("ن")]) + 2)
+    assert pu("إن", "ن", 1) == (True, 0, 2) and not pu("إن", "ن", 0)[0]
+    assert pu("éन😀", "😀", 2) == (True, 0, 4) and not pu("éन😀", "😀", 1)[0]
+    assert pu("😀éनZ", "Z", 3) == (True, 0, 1) and not pu("😀éनZ", "Z", 2)[0]
+    assert not pu("إن", wrong_first, 1)[0] and not pu("إن", wrong_second, 1)[0]
+    h = "xxé__😀" + "x" * 32 + "다zz"
+    assert pu("é다😀", h, 1) == (True, 2, _ulen(h[: h.rfind("다")]) + 3)
+    assert pu("É", "é") == (True, 0, 2) and not pu("É", "é", 0, True)[0]
+    # reference_oracle_manual_cases (:430-470), the rows with non-ASCII needles
+    assert pu("éa", "é_a")[0] and pu("ÿA", "ÿa")[0] and not pu("ÿA", "ÿa", 0, True)[0]
+
+
+def _subsequence_with_deletions(needle_chars, hay: str, k: int, cs: bool) -> bool:
+    # reference_matches_by_deleting_needle_* of the reference's tests: some needle with <= k scalars deleted is an
+    # ordered subsequence of the haystack's scalars (either case)
+    def eq(a, b):
+        return a == b or (not cs and O.flip_scalar(a) == b)
+    n = len(needle_chars)
+    best = {0: 0}   # needle idx -> min deletions, scanning the haystack greedily per deletion budget (DP over scalars)
+    INF = 10 ** 9
+    dp = [INF] * (n + 1)
+    dp[0] = 0
+    for i in range(n):          # deletions before any haystack scalar is consumed
+        dp[i + 1] = min(dp[i + 1], dp[i] + 1)
+    for ch in hay:
+        nd = dp[:]
+        for i in range(n):
+            if dp[i] < INF and eq(needle_chars[i], ch):
+                nd[i + 1] = min(nd[i + 1], dp[i])
+        for i in range(n):
+            nd[i + 1] = min(nd[i + 1], nd[i] + 1)
+        dp = nd
+    return dp[n] <= k
+
+
+@pytest.mark.parametrize("lanes", U_LANES)
+def test_unicode_prefilter_mixed_width_matches_subsequence_oracle(lanes):
+    # src/prefilter/mod.rs:521-560 (unicode_mixed_width_matches_oracle): k = 0 is exactly the subsequence test
+    needles = ["aé", "éa", "aébc", "é✓", "✓é", "a✓é", "é😀x", "aXé😀"]
+    hays = ["", "a", "é", "aé", "xaéy", "aébc", "é✓", "a✓é", "zzaé😀xx", "éeé", "aaébcbc", "✓✓é", "aXé😀qw",
+            "x" * 15 + "aé😀x", "x" * 16 + "aXé😀", "x" * 31 + "é✓", "x" * 63 + "a✓é" + "y" * 70]
+    for n in needles:
+        for h in hays:
+            for cs in (False, True):
+                got = O.prefilter_unicode(n, h, 0, lanes, cs)
+                assert got[0] == _subsequence_with_deletions(list(n), h, 0, cs), (n, h, cs, got)
+                if got[0]:
+                    hb = h.encode("utf-8")
+                    assert 0 <= got[1] < got[2] <= len(hb)
+                for k in (1, 2, 3):
+                    gk = O.prefilter_unicode(n, h, k, lanes, cs)
+                    if gk[0]:   # the typo trackers are sound (never accept what the deletion oracle rejects)
+                        assert _subsequence_with_deletions(list(n), h, k, cs), (n, h, k, cs, gk)
+
+
+@pytest.mark.parametrize("lanes,bits", ALL_BACKENDS)
+def test_unicode_sw_kats(lanes, bits):
+    # src/smith_waterman/mod.rs:228-252 (unicode_score_* / unicode_gap_propagation_*), on every backend
+    s = Scoring()
+    CHAR = s.match_score + s.matching_case_bonus
+    us = lambda n, h: O.sw_score_unicode(n, h, s, False, True, lanes, bits)
+    assert us("é", "é") == CHAR + s.prefix_bonus
+    assert us("😀", "😀") == CHAR + s.prefix_bonus
+    assert us("éx", "éx") == 2 * CHAR + s.prefix_bonus
+    assert us("éx", "ébx") == us("éx", "é😀x")
+    assert us("ab", "aéb") == 2 * CHAR + s.prefix_bonus - s.gap_open_penalty
+    assert us("ab", "aé😀b") == 2 * CHAR + s.prefix_bonus - s.gap_open_penalty - s.gap_extend_penalty
+    # ASCII needle + ASCII haystack: the unicode scorer agrees with the byte scorer when no gap is involved
+    for n, h in [("abc", "abc"), ("a", "abc"), ("fBr", "fooBar"), ("foo", "012345foo")]:
+        assert us(n, h) == O.sw_score(n, h, s, False, True, lanes, bits), (n, h)
+
+
+def test_unicode_case_table_matches_python():
+    # the generated table is what tools/gen_unicode_case.py says it is, and behaves like the reference's rule
+    assert O.flip_scalar("é") == "É" and O.flip_scalar("É") == "é"
+    assert O.flip_scalar("ß") == "ß"          # 'ß'.to_uppercase() is two scalars: ignored (src/prefilter/mod.rs:67-70)
+    assert O.flip_scalar("İ") == "İ"          # lower-cases to 'i' + combining dot: ignored
+    assert O.flip_scalar("ſ") == "ſ"          # 'ſ' (2 bytes) upper-cases to 'S' (1 byte): length differs → ignored
+    assert O.flip_scalar("я") == "Я" and O.flip_scalar("Ω") == "ω"
+    assert O.flip_scalar("다") == "다" and O.flip_scalar("😀") == "😀" and O.flip_scalar("a") == "A"
+
+
+def test_unicode_matcher_pipeline():
+    # src/matcher/mod.rs:820-840 (unicode config equivalence) and the smart rule of src/lib.rs:394-401:
+    # a non-ASCII needle under UnicodeMatching::Smart takes the unicode path; Always forces it for ASCII needles
+    from frizbee_b200.types import UnicodeMatching
+    hs = ["é다😀", "xxé__다__😀yy", "É다😀", "no match", "é다", "a-é-다-😀"]
+    smart = O.match_list(["é다😀"], hs, Config(max_typos=0))
+    always = O.match_list(["é다😀"], hs, Config(max_typos=0, unicode=UnicodeMatching.Always))
+    assert smart == always
+    assert [m.index for m in smart] == sorted([m.index for m in smart], key=lambda i: (-[x for x in smart if x.index == i][0].score, i))
+    assert {m.index for m in smart} == {0, 1, 2, 5}
+    exact = [m for m in smart if m.index == 0][0]
+    assert exact.exact and not [m for m in smart if m.index == 2][0].exact
+    one = O.match_list(["é다😀"], hs, Config(max_typos=1))
+    assert {m.index for m in one} == {0, 1, 2, 4, 5}
+    # smart case with a non-ASCII uppercase scalar is case sensitive (char::is_uppercase, src/lib.rs:373)
+    assert {m.index for m in O.match_list(["É"], ["é", "É"], Config(max_typos=0))} == {1}
+    assert {m.index for m in O.match_list(["é"], ["é", "É"], Config(max_typos=0))} == {0, 1}
+    # literal modes on the unicode path (src/literal/algo.rs:159-230)
+    from frizbee_b200.types import Matching
+    pre = O.match_list([Pattern("éa", matching=Matching.Prefix)], ["éab", "Éab", "xéa", "é"], Config())
+    assert [m.index for m in pre] == [0, 1] and pre[0].score > pre[1].score
+    sub = O.match_list([Pattern("다", matching=Matching.Substring)], ["a다", "다", "가나"], Config(sort=SortStrategy.IndexAsc))
+    assert [(m.index, m.exact) for m in sub] == [(0, False), (1, True)]
