@@ -8,6 +8,7 @@
 
 #include "../../include/frz_cuda.h"
 #include "frz_device.cuh"
+#include "unicode_path.cuh"
 
 frz_status frz_fail(frz_status s, const char* fmt, ...);
 
@@ -116,6 +117,8 @@ struct FrzWorkspace {
     uint64_t* retain_base = nullptr;
     uint8_t* retain_keep = nullptr;
     uint64_t retain_cap = 0;
+    uint16_t* unicode_scratch = nullptr;    // unicode.cu: per-thread row state of the per-scalar Smith-Waterman
+    uint64_t unicode_scratch_cap = 0;       // in uint16 elements
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     bool ev_rec[6] = {false, false, false, false, false, false};  // recorded during the current call
     void release();
@@ -128,6 +131,9 @@ struct FrzLaunchStats {
 
 frz_status frz_launch_prefilter(const FrzCorpusView& cv, const FrzPatternDev& pat, const uint32_t* cand_bitmap,
                                 FrzWorkspace& ws, cudaStream_t stream, FrzLaunchStats* st);
+frz_status frz_launch_unicode(const FrzCorpusView& cv, const FrzPatternDev& pat, const FrzUNeedle& un, const FrzUScoring& usc,
+                              const FrzMatchDev* cand, uint64_t n_cand, uint32_t index_offset, FrzWorkspace& ws,
+                              cudaStream_t stream, FrzLaunchStats* st);
 frz_status frz_launch_prefilter_list(const FrzCorpusView& cv, const FrzPatternDev& pat, const FrzMatchDev* cand,
                                      uint64_t n_cand, uint32_t index_offset, FrzWorkspace& ws, cudaStream_t stream,
                                      FrzLaunchStats* st);

@@ -19,6 +19,7 @@
 
 #include "frz_device.cuh"
 #include "frz_host.h"
+#include "unicode_needle.h"
 
 // ------------------------------------------------------------------------------------ errors
 
@@ -367,6 +368,9 @@ struct Compiled {
     FrzPatternDev dev;
     bool negated = false;
     bool literal = false;
+    bool unicode = false;      // UNICODE = true specialisations (unicode.cu)
+    FrzUNeedle un;             // case_needle_unicode (valid when `unicode`)
+    FrzUScoring usc;
     uint32_t score_bound = 0;  // host-side upper bound of any score this pattern can emit
 };
 
@@ -390,17 +394,11 @@ frz_status compile_pattern(const OwnedPattern& src, const frz_config& mcfg, bool
     }
     // UnicodeMatching::respects_unicode_for (src/lib.rs:394-401)
     const bool needs_unicode = unicode == FRZ_UNICODE_ALWAYS || (unicode == FRZ_UNICODE_SMART && !ascii);
-    if (needs_unicode)
-        return frz_fail(FRZ_ERR_UNSUPPORTED, "the unicode-aware kernels (non-ASCII needle or UnicodeMatching::Always) are not on the GPU path yet");
-    // CaseMatching::respects_case_for (src/lib.rs:368-377)
+    // CaseMatching::respects_case_for (src/lib.rs:368-377): needle.chars().any(char::is_uppercase)
     bool case_sensitive;
     if (casing == FRZ_CASE_IGNORE) case_sensitive = false;
     else if (casing == FRZ_CASE_RESPECT) case_sensitive = true;
-    else {
-        if (!ascii) return frz_fail(FRZ_ERR_UNSUPPORTED, "CaseMatching::Smart with a non-ASCII needle needs Unicode case tables");
-        case_sensitive = false;
-        for (size_t i = 0; i < n; i++) if (nd[i] >= 'A' && nd[i] <= 'Z') case_sensitive = true;
-    }
+    else case_sensitive = frz_needle_has_uppercase(nd, n);
     if (n > FRZ_MAX_NEEDLE) return frz_fail(FRZ_ERR_UNSUPPORTED, "needle of %zu bytes exceeds the GPU kernels' limit of %d", n, FRZ_MAX_NEEDLE);
 
     Compiled c;
@@ -408,6 +406,9 @@ frz_status compile_pattern(const OwnedPattern& src, const frz_config& mcfg, bool
     memset(&d, 0, sizeof d);
     c.negated = src.negated;
     c.literal = matching != FRZ_MATCHING_FUZZY;
+    c.unicode = needs_unicode;
+    if (needs_unicode && !frz_build_uneedle(nd, n, case_sensitive, &c.un))
+        return frz_fail(FRZ_ERR_INVALID_ARG, "the needle is not valid UTF-8");
     d.n = (int)n;
     d.matching = matching;
     d.case_sensitive = case_sensitive;
@@ -485,6 +486,11 @@ frz_status compile_pattern(const OwnedPattern& src, const frz_config& mcfg, bool
     d.cap_bonus = sc.capitalization_bonus & tm;
     d.delim_bonus = sc.delimiter_bonus & tm;
     d.prefix_bonus = sc.prefix_bonus & tm;
+    c.usc.gex = d.gap_extend; c.usc.gopx = d.gap_open_x; c.usc.match_x = d.match_x; c.usc.mismatch = d.mismatch;
+    c.usc.case_bonus = d.case_bonus; c.usc.cap_bonus = d.cap_bonus; c.usc.delim_bonus = d.delim_bonus; c.usc.prefix_bonus = d.prefix_bonus;
+    c.usc.raw_match = sc.match_score; c.usc.raw_gap_open = sc.gap_open_penalty; c.usc.raw_gap_extend = sc.gap_extend_penalty;
+    c.usc.raw_prefix = sc.prefix_bonus; c.usc.raw_cap = sc.capitalization_bonus; c.usc.raw_case = sc.matching_case_bonus;
+    c.usc.raw_delim = sc.delimiter_bonus; c.usc.exact_bonus = sc.exact_match_bonus;
     {
         auto sp = [](int v) { return ((uint32_t)v & 0xffffu) * 0x00010001u; };
         for (int k = 0; k < 6; k++) {
@@ -503,7 +509,7 @@ frz_status compile_pattern(const OwnedPattern& src, const frz_config& mcfg, bool
     const uint64_t cell_bound = (uint64_t)n * ((uint64_t)sc.match_score + maxb + sc.matching_case_bonus) + sc.prefix_bonus +
                                 (uint64_t)sc.mismatch_penalty + sc.match_score;
     const uint64_t pen_bound = (uint64_t)sw_lanes * sc.gap_extend_penalty + sc.gap_open_penalty;
-    if (cell_bound > 32767 || pen_bound > 32767)
+    if (!needs_unicode && (cell_bound > 32767 || pen_bound > 32767))   // (the unicode kernel uses true u8/u16 lanes)
         return frz_fail(FRZ_ERR_UNSUPPORTED, "scoring/needle combination exceeds the kernels' signed 16-bit cell range");
     d.wrap8 = use_u8 && cell_bound > 255;  // cannot prove "no u8 add ever wraps" → emulate the wrap
     {   // column-limited SW classes need: padding bytes (0) never match, and plain (non-wrapping) arithmetic
@@ -566,6 +572,7 @@ void FrzWorkspace::release() {
     counters = nullptr; h_counters = nullptr; tile_count = nullptr; tile_out_base = nullptr; matches_a = matches_b = nullptr;
     sort_hist = nullptr; cand_bitmap = nullptr;
     cudaFree(retain_cnt); cudaFree(retain_base); cudaFree(retain_keep); retain_cnt = nullptr; retain_base = nullptr; retain_keep = nullptr; retain_cap = 0;
+    cudaFree(unicode_scratch); unicode_scratch = nullptr; unicode_scratch_cap = 0;
     survivor_cap = match_cap = sort_hist_cap = cand_cap = 0; tiles_cap = 0; device = -1;
 }
 
@@ -848,7 +855,8 @@ frz_status run_pattern(frz_matcher* m, const FrzCorpusStorage& cs, const Compile
     FRZ_TRY(ensure_workspace(m, cs, cap));
     FRZ_CUDA_TRY(cudaMemsetAsync(ws.counters, 0, sizeof(FrzCounters), stream));
     if (record_events) { cudaEventRecord(ws.ev[0], stream); ws.ev_rec[0] = true; }
-    if (cand_list) FRZ_TRY(frz_launch_prefilter_list(cv, c.dev, cand_list, n_cand, index_offset, ws, stream, st));
+    if (c.unicode) FRZ_TRY(frz_launch_unicode(cv, c.dev, c.un, c.usc, cand_list, n_cand, index_offset, ws, stream, st));
+    else if (cand_list) FRZ_TRY(frz_launch_prefilter_list(cv, c.dev, cand_list, n_cand, index_offset, ws, stream, st));
     else FRZ_TRY(frz_launch_prefilter(cv, c.dev, cand_bitmap, ws, stream, st));
     FRZ_TRY(frz_launch_tile_scan(cv, ws, stream, st));
     if (record_events) { cudaEventRecord(ws.ev[1], stream); ws.ev_rec[1] = true; }
@@ -860,7 +868,14 @@ frz_status run_pattern(frz_matcher* m, const FrzCorpusStorage& cs, const Compile
     }
     // A survivor-list overflow (lists are sized by a heuristic unless the pattern can match everything)
     // only sets a sticky device flag; whoever reads the counters back re-runs with worst-case lists.
-    FRZ_TRY(frz_launch_sw(cv, c.dev, index_offset, reversed, ws, d_out, stream, st));
+    if (c.unicode) {
+        // the unicode kernel has already scored its survivors: they travel as literal-style records (score, exact)
+        FrzPatternDev emit = c.dev;
+        emit.typo_mode = FRZ_T_LITERAL;
+        FRZ_TRY(frz_launch_sw(cv, emit, index_offset, reversed, ws, d_out, stream, st));
+    } else {
+        FRZ_TRY(frz_launch_sw(cv, c.dev, index_offset, reversed, ws, d_out, stream, st));
+    }
     if (record_events) { cudaEventRecord(ws.ev[2], stream); ws.ev_rec[2] = true; }
     return FRZ_OK;
 }

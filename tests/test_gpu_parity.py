@@ -382,3 +382,53 @@ def test_device_k_merge_equals_single_list(n_runs):
     for sh in shards:
         sh.close()
     full.close()
+
+
+# ---------------------------------------------------------------- unicode-needle path
+def _unicode_haystacks(rng, n):
+    pools = ["aéAÉ_다", "abé✓😀", "éÉeE-/x", "нНaя_Я", "fooBar_/-é다😀"]
+    out = []
+    for _ in range(n):
+        pool = rng.choice(pools)
+        ln = rng.choice([0, 1, 2, 5, 9, 14, 20, 31, 40, 70, 130, 300])
+        out.append("".join(rng.choice(pool) for _ in range(ln)))
+    out += ["é다😀", "xxé__다__😀yy", "É다😀", "é다", "a-é-다-😀", "", "😀", "x" * 1100 + "é" + "y" * 50 + "다😀"]
+    return out
+
+
+@pytest.mark.parametrize("lanes", [16, 32, 64])
+def test_unicode_needle_path(lanes):
+    # UNICODE = true specialisations (src/matcher/mod.rs:58-73): unicode prefilters, per-scalar Smith-Waterman,
+    # exact flag, all typo budgets; the same code is checked on the CPU by tests/test_unicode_device_code.py
+    rng = random.Random(4100 + lanes)
+    hs = _unicode_haystacks(rng, 6000)
+    data, off = from_list(hs)
+    corpus = F.Corpus.from_arrow(data, off)
+    for needle in ["é다😀", "éa", "Я", "аб", "é", "😀x", "aÉ"]:
+        for k in (0, 1, 2, 3, None):
+            gpu_vs_oracle(needle, data, off, Config(max_typos=k, emulate_lanes=lanes), corpus)
+    # UnicodeMatching::Always routes an ASCII needle through the unicode kernels too (src/lib.rs:394-401)
+    gpu_vs_oracle("foo", data, off, Config(max_typos=1, unicode=UnicodeMatching.Always, emulate_lanes=lanes), corpus)
+    gpu_vs_oracle("fB", data, off, Config(max_typos=0, unicode=UnicodeMatching.Always, casing=CaseMatching.Respect,
+                                           emulate_lanes=lanes), corpus)
+    # u16 family (needle > 13 bytes at the default scoring) and custom scoring
+    gpu_vs_oracle("é다😀é다😀", data, off, Config(max_typos=2, emulate_lanes=lanes), corpus)
+    gpu_vs_oracle("éa", data, off, Config(max_typos=1, emulate_lanes=lanes,
+                                          scoring=Scoring(gap_open_penalty=2, gap_extend_penalty=2, delimiter_bonus=7)), corpus)
+    corpus.close()
+
+
+def test_unicode_literal_and_multi_pattern():
+    rng = random.Random(777)
+    hs = _unicode_haystacks(rng, 5000) + ["éab", "Éab", "xéa", "é", "a다", "다"]
+    data, off = from_list(hs)
+    corpus = F.Corpus.from_arrow(data, off)
+    for mode in (Matching.Exact, Matching.Prefix, Matching.Suffix, Matching.Substring):
+        for needle in ["éa", "다", "É", "aé"]:
+            gpu_vs_oracle(Pattern(needle, matching=mode), data, off, Config(), corpus)
+            gpu_vs_oracle(Pattern(needle, matching=mode), data, off, Config(casing=CaseMatching.Respect, sort=SortStrategy.IndexDesc), corpus)
+    # multi-pattern with unicode atoms: fuzzy base + negated unicode prefix, unicode base + ASCII extra
+    gpu_vs_oracle([Pattern("aé"), Pattern("é", negated=True, matching=Matching.Prefix)], data, off, Config(max_typos=1), corpus)
+    gpu_vs_oracle([Pattern("다"), Pattern("a")], data, off, Config(max_typos=0), corpus)
+    gpu_vs_oracle([Pattern("fo"), Pattern("é😀", max_typos=1)], data, off, Config(max_typos=0), corpus)
+    corpus.close()

@@ -86,10 +86,12 @@ def test_build_patterns_and_guards():
     with pytest.raises(F.FrizbeeError) as e:
         F.Matcher("f", Config(scoring=Scoring(capitalization_bonus=60000, matching_case_bonus=40000)))
     assert e.value.status_name == "FRZ_ERR_NEEDLE_TOO_LONG" and "needle too long" in str(e.value)
+    # non-ASCII needles build (the unicode path, unicode.cu); malformed UTF-8 on that path is an argument error
+    F.Matcher("é다😀", Config()).close()
+    F.Matcher("é", Config(unicode=UnicodeMatching.Ignore, casing=CaseMatching.Ignore)).close()
     with pytest.raises(F.FrizbeeError) as e:
-        F.Matcher("é다😀", Config())
-    assert e.value.status_name == "FRZ_ERR_UNSUPPORTED"
-    F.Matcher("é", Config(unicode=UnicodeMatching.Ignore, casing=CaseMatching.Ignore))
+        F.Matcher([Pattern(b"\xff\xfe")], Config(unicode=UnicodeMatching.Always))
+    assert e.value.status_name == "FRZ_ERR_INVALID_ARG"
 
 
 def test_no_cpu_fallback_without_device():
