@@ -446,6 +446,10 @@ frz_status compile_pattern(const OwnedPattern& src, const frz_config& mcfg, bool
     // per-char bound used for the sort's digit width
     const uint32_t maxb = std::max(sc.capitalization_bonus, sc.delimiter_bonus);
 
+    memset(&c.usc, 0, sizeof c.usc);   // untruncated u16 scoring (literal matcher, greedy scorer); lane constants below
+    c.usc.raw_match = sc.match_score; c.usc.raw_gap_open = sc.gap_open_penalty; c.usc.raw_gap_extend = sc.gap_extend_penalty;
+    c.usc.raw_prefix = sc.prefix_bonus; c.usc.raw_cap = sc.capitalization_bonus; c.usc.raw_case = sc.matching_case_bonus;
+    c.usc.raw_delim = sc.delimiter_bonus; c.usc.exact_bonus = sc.exact_match_bonus;
     if (c.literal) {
         // LiteralImpl::guard_against_score_overflow (src/literal/algo.rs:316-324)
         FRZ_TRY(guard_against_score_overflow(sc, n, sat_add16(maxb, sc.matching_case_bonus), 0));
@@ -488,9 +492,6 @@ frz_status compile_pattern(const OwnedPattern& src, const frz_config& mcfg, bool
     d.prefix_bonus = sc.prefix_bonus & tm;
     c.usc.gex = d.gap_extend; c.usc.gopx = d.gap_open_x; c.usc.match_x = d.match_x; c.usc.mismatch = d.mismatch;
     c.usc.case_bonus = d.case_bonus; c.usc.cap_bonus = d.cap_bonus; c.usc.delim_bonus = d.delim_bonus; c.usc.prefix_bonus = d.prefix_bonus;
-    c.usc.raw_match = sc.match_score; c.usc.raw_gap_open = sc.gap_open_penalty; c.usc.raw_gap_extend = sc.gap_extend_penalty;
-    c.usc.raw_prefix = sc.prefix_bonus; c.usc.raw_cap = sc.capitalization_bonus; c.usc.raw_case = sc.matching_case_bonus;
-    c.usc.raw_delim = sc.delimiter_bonus; c.usc.exact_bonus = sc.exact_match_bonus;
     {
         auto sp = [](int v) { return ((uint32_t)v & 0xffffu) * 0x00010001u; };
         for (int k = 0; k < 6; k++) {
