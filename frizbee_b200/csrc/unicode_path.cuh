@@ -328,7 +328,8 @@ FRZ_HD void propagate_unicode(const Ar& A, uint16_t* row, uint16_t* pend, const 
 
 // match_greedy (src/smith_waterman/greedy.rs:7-91) on needle BYTES with the ASCII case pairs; -1 = None
 template <class Hay>
-FRZ_HD int greedy_score(const FrzUNeedle& nd, const FrzUScoring& sc, const Hay& hay, int W, bool include_prefix) {
+FRZ_HD int greedy_score(const FrzUNeedle& nd, const FrzUScoring& sc, const Hay& hay, int W, bool include_prefix,
+                        uint32_t* idx_out = nullptr) {   // idx_out: haystack position of every needle byte (nbytes entries)
     const int n = nd.nbytes;
     if (n > W) return -1;
     uint32_t score = 0;
@@ -366,6 +367,7 @@ FRZ_HD int greedy_score(const FrzUNeedle& nd, const FrzUScoring& sc, const Hay& 
             if (prev_delim && !is_delim) sat_add(sc.raw_delim);
             prev_delim = delim_enabled && is_delim;
             prev_lower = is_lower;
+            if (idx_out) idx_out[ni] = (uint32_t)hi;
             hi++;
             matched = true;
             break;
@@ -377,9 +379,11 @@ FRZ_HD int greedy_score(const FrzUNeedle& nd, const FrzUScoring& sc, const Hay& 
 
 // score_haystack_unicode (unicode.rs:9-224).  `hay(i)` is byte i of the WINDOW (0 <= i < W).
 // scratch: 2 * (n + 1) * lanes uint16 (previous chunk's row vectors and the pending-gap-open vectors of every row).
+// Hfull / Mfull (optional, for the traceback): the whole score matrix and match masks, [(n + 1)][cols] with
+// cols = (chunks + 1) * lanes and chunk 0 the zero column — the layout of src/smith_waterman/matrix.rs.
 template <class Hay>
 FRZ_HD uint32_t sw_score(const FrzUNeedle& nd, const FrzUScoring& sc, const Hay& hay, int W, bool include_prefix, int lanes,
-                         bool u8, uint16_t* scratch) {
+                         bool u8, uint16_t* scratch, uint16_t* Hfull = nullptr, uint16_t* Mfull = nullptr, int cols = 0) {
     if (W > FRZ_U_MAX_WINDOW) {
         const int g = greedy_score(nd, sc, hay, W, include_prefix);
         return g < 0 ? 0u : (uint32_t)g;
@@ -391,6 +395,11 @@ FRZ_HD uint32_t sw_score(const FrzUNeedle& nd, const FrzUScoring& sc, const Hay&
     uint16_t* Hprev = scratch;                         // [(n + 1)][lanes]: row r of the previous chunk
     uint16_t* pending = scratch + (n + 1) * lanes;     // [(n + 1)][lanes]
     for (int i = 0; i < 2 * (n + 1) * lanes; i++) scratch[i] = 0;
+    if (Hfull) {
+        for (int i = 0; i < cols; i++) { Hfull[i] = 0; Mfull[i] = 0; }                       // row 0
+        for (int r = 1; r <= n; r++)
+            for (int i = 0; i < lanes; i++) { Hfull[r * cols + i] = 0; Mfull[r * cols + i] = 0; }   // chunk 0
+    }
     const uint16_t gex = (uint16_t)sc.gex, gop = (uint16_t)sc.gopx, mismatch = (uint16_t)sc.mismatch;
     bool prev_last_delim = false, prev_last_lower = false;
     uint16_t prev_cgex[FRZ_U_MAX_LANES], prev_sstart[FRZ_U_MAX_LANES], maxv[FRZ_U_MAX_LANES];
@@ -464,6 +473,7 @@ FRZ_HD uint32_t sw_score(const FrzUNeedle& nd, const FrzUScoring& sc, const Hay&
                 pending[r * lanes + i] = pend[i];
                 prev_row[i] = row[i];
                 up_gap[i] = mm[i];
+                if (Hfull) { Hfull[r * cols + (col + 1) * lanes + i] = row[i]; Mfull[r * cols + (col + 1) * lanes + i] = mm[i]; }
             }
         }
         for (int i = 0; i < lanes; i++) { maxv[i] = Ar::mx(maxv[i], row[i]); prev_cgex[i] = cgex[i]; prev_sstart[i] = sstart[i]; }

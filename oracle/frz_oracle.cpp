@@ -745,7 +745,7 @@ static SV propagate(const Arith& A, SV row, const SV& adj, const SV& mm, const S
 
 // src/smith_waterman/greedy.rs:7-91 (match_greedy); returns -1 for None
 static int match_greedy(const uint8_t* needle_raw, size_t n, const uint8_t* hay, size_t hl, const frz_scoring& sc,
-                        bool case_sensitive, bool include_prefix) {
+                        bool case_sensitive, bool include_prefix, std::vector<uint32_t>* indices = nullptr) {
     std::vector<Pair> needle = case_needle(needle_raw, n, case_sensitive);
     if (n > hl) return -1;
     auto sat_add = [](uint16_t a, uint16_t b) { uint32_t r = (uint32_t)a + b; return (uint16_t)(r > 0xFFFF ? 0xFFFF : r); };
@@ -783,6 +783,7 @@ static int match_greedy(const uint8_t* needle_raw, size_t n, const uint8_t* hay,
             if (prev_delim && !is_delim) score = sat_add(score, sc.delimiter_bonus);
             prev_delim = delim_enabled && is_delim;
             prev_lower = is_lower;
+            if (indices) indices->push_back((uint32_t)hi);
             hi++;
             matched = true;
             break;
@@ -797,8 +798,14 @@ static int match_greedy(const uint8_t* needle_raw, size_t n, const uint8_t* hay,
 // max_cols (test-only, tests/test_oracle_kat.py::test_column_limit_property): take the final maximum over the
 // last-row cells of columns < max_cols only.  Cells never depend on cells to their right, so this equals a
 // computation that stops at column max_cols; the reference itself always uses every lane (SIZE_MAX).
+struct SwMatrices {     // score_matrix / match_masks of the last call (src/smith_waterman/matrix.rs), chunk 0 = zero column
+    std::vector<SV> H, M;
+    size_t chunks = 0;
+};
+
 static uint16_t sw_score(const uint8_t* needle_raw, size_t n, const frz_scoring& sc, bool case_sensitive,
-                         const uint8_t* hay, size_t hl, bool include_prefix, int lanes, bool u8, size_t max_cols = SIZE_MAX) {
+                         const uint8_t* hay, size_t hl, bool include_prefix, int lanes, bool u8, size_t max_cols = SIZE_MAX,
+                         SwMatrices* mats = nullptr) {
     if (hl > kMaxHaystackLen) {
         int g = match_greedy(needle_raw, n, hay, hl, sc, case_sensitive, include_prefix);
         return g < 0 ? 0 : (uint16_t)g;
@@ -875,6 +882,7 @@ static uint16_t sw_score(const uint8_t* needle_raw, size_t n, const frz_scoring&
         maxv = A.max(maxv, row);
         prefix_masked = A.zero();
     }
+    if (mats) { mats->H = std::move(H); mats->M = std::move(M); mats->chunks = chunks; }
     return A.hmax(maxv);
 }
 
@@ -955,7 +963,7 @@ static void propagate_unicode(const Arith& A, SV& row, SV& pend, const SV& adj_r
 
 // unicode.rs:9-224 (score_haystack_unicode)
 static uint16_t sw_score_unicode(const uint8_t* needle_raw, size_t nbytes, const frz_scoring& sc, bool case_sensitive,
-                                 const uint8_t* hay, size_t hl, bool include_prefix, int lanes, bool u8) {
+                                 const uint8_t* hay, size_t hl, bool include_prefix, int lanes, bool u8, SwMatrices* mats = nullptr) {
     if (hl > kMaxHaystackLen) {
         int g = match_greedy(needle_raw, nbytes, hay, hl, sc, case_sensitive, include_prefix);
         return g < 0 ? 0 : (uint16_t)g;
@@ -966,6 +974,7 @@ static uint16_t sw_score_unicode(const uint8_t* needle_raw, size_t nbytes, const
     Arith A{lanes, u8};
     size_t chunks = (hl + lanes - 1) / lanes + 1;
     std::vector<SV> H((n + 1) * chunks, A.zero());
+    std::vector<SV> Mm((n + 1) * chunks, A.zero());
     std::vector<SV> pending(n + 1, A.zero());
     auto sat_sub16 = [](uint16_t a, uint16_t b) { return (uint16_t)(a > b ? a - b : 0); };
     auto sat_add16 = [](uint16_t a, uint16_t b) { uint32_t r = (uint32_t)a + b; return (uint16_t)(r > 0xFFFF ? 0xFFFF : r); };
@@ -1046,6 +1055,7 @@ static uint16_t sw_score_unicode(const uint8_t* needle_raw, size_t nbytes, const
             SV pend = mm;
             propagate_unicode(A, row, pend, H[r * chunks + (col - 1)], pending[r], cgex, prev_cgex, sstart, prev_sstart, gop, gex);
             H[r * chunks + col] = row;
+            Mm[r * chunks + col] = mm;
             pending[r] = pend;
             prev_row = row;
             up_gap_mask = mm;
@@ -1054,7 +1064,87 @@ static uint16_t sw_score_unicode(const uint8_t* needle_raw, size_t nbytes, const
         prev_cgex = cgex;
         prev_sstart = sstart;
     }
+    if (mats) { mats->H = std::move(H); mats->M = std::move(Mm); mats->chunks = chunks; }
     return A.hmax(maxv);
+}
+
+// ---------------------------------------------------------------------------------
+// Traceback: AlignmentPathIter (src/smith_waterman/alignment_iter.rs) driven by score_haystack_indices /
+// score_haystack_unicode_indices (src/smith_waterman/algo/mod.rs:49-151).  Indices come out in reverse order.
+// rows = needle bytes (ASCII path) or needle scalars (unicode path: `und` and `uhay` are set).
+// ---------------------------------------------------------------------------------
+static std::vector<uint32_t> alignment_indices(const SwMatrices& mt, int lanes, size_t rows, size_t start_pos,
+                                               const uint8_t* uhay, size_t uhay_len, const std::vector<UChar>* und,
+                                               uint16_t score, int max_typos /* < 0: None */) {
+    std::vector<uint32_t> indices;
+    auto cell = [&](const std::vector<SV>& m, size_t row, size_t col) { return m[row * mt.chunks + col / lanes].v[col % lanes]; };
+    // get_col_idx (alignment_iter.rs:73-88): first lane of the final row holding the score
+    size_t col = SIZE_MAX;
+    for (size_t ch = 1; ch < mt.chunks && col == SIZE_MAX; ch++)
+        for (int i = 0; i < lanes; i++)
+            if (mt.H[rows * mt.chunks + ch].v[i] == score) { col = ch * lanes + i; break; }
+    if (col == SIZE_MAX) return indices;   // (the reference panics; unreachable for a score produced by the same matrix)
+    size_t row = rows;
+    uint16_t cur = score;
+    int typos = 0;
+    size_t prev_hidx = SIZE_MAX;
+    for (;;) {
+        if (row == 0) break;
+        if (max_typos >= 0 && typos > max_typos) break;               // Some(None): stop collecting
+        if (col < (size_t)lanes || cur == 0) break;                   // left edge / lost alignment (both end the walk)
+        const size_t hidx = col - lanes;
+        if (uhay && hidx < uhay_len && (uhay[hidx] & 0xC0) == 0x80) {  // continuation byte: walk left
+            col -= 1;
+            cur = cell(mt.H, row, col);
+            continue;
+        }
+        if (cell(mt.M, row, col) != 0) {
+            const size_t needle_idx = row - 1, hpos = hidx + start_pos;
+            row -= 1; col -= 1;
+            cur = cell(mt.H, row, col);
+            if (und) {
+                if (prev_hidx != hpos) {
+                    const int len = (*und)[needle_idx].len;
+                    for (int o = len - 1; o >= 0; o--) indices.push_back((uint32_t)(hpos + o));
+                    prev_hidx = hpos;
+                }
+            } else {
+                indices.push_back((uint32_t)hpos);
+            }
+            continue;
+        }
+        const uint16_t diag = cell(mt.H, row - 1, col - 1), left = cell(mt.H, row, col - 1), up = cell(mt.H, row - 1, col);
+        if (diag >= left && diag >= up) { row -= 1; col -= 1; typos += 1; cur = diag; }
+        else if (left >= up) { col -= 1; cur = left; }
+        else { typos += 1; row -= 1; cur = up; }
+    }
+    return indices;
+}
+
+// score_haystack_indices / score_haystack_unicode_indices (algo/mod.rs:49-151)
+static uint16_t sw_indices(const uint8_t* needle_raw, size_t nbytes, const frz_scoring& sc, bool case_sensitive, bool unicode,
+                           const uint8_t* hay, size_t hl, size_t start_pos, int max_typos, int lanes, bool u8,
+                           std::vector<uint32_t>* out) {
+    out->clear();
+    if (hl > kMaxHaystackLen) {
+        std::vector<uint32_t> idx;
+        int g = match_greedy(needle_raw, nbytes, hay, hl, sc, case_sensitive, start_pos == 0, &idx);
+        if (g < 0) return 0;
+        for (auto it = idx.rbegin(); it != idx.rend(); ++it) out->push_back((uint32_t)(*it + start_pos));
+        return (uint16_t)g;
+    }
+    SwMatrices mt;
+    if (unicode) {
+        std::vector<UChar> und = case_needle_unicode(needle_raw, nbytes, case_sensitive);
+        uint16_t score = sw_score_unicode(needle_raw, nbytes, sc, case_sensitive, hay, hl, start_pos == 0, lanes, u8, &mt);
+        if (score == 0 || und.empty()) return score;
+        *out = alignment_indices(mt, lanes, und.size(), start_pos, hay, hl, &und, score, max_typos);
+        return score;
+    }
+    uint16_t score = sw_score(needle_raw, nbytes, sc, case_sensitive, hay, hl, start_pos == 0, lanes, u8, SIZE_MAX, &mt);
+    if (score == 0) return score;
+    *out = alignment_indices(mt, lanes, nbytes, start_pos, nullptr, 0, nullptr, score, max_typos);
+    return score;
 }
 
 // ---------------------------------------------------------------------------------
@@ -1226,6 +1316,39 @@ static void match_list_into(const OPattern& p, const uint8_t* bytes, const uint6
     }
 }
 
+// MatcherImpl::match_one_indices_impl (src/matcher/algo.rs:138-169) / LiteralImpl::match_one_indices_impl
+// (src/literal/algo.rs:134-155) for one haystack: false = no match.
+static bool match_one_indices(const OPattern& p, const uint8_t* hay, size_t hl, uint32_t index, frz_match* m,
+                              std::vector<uint32_t>* indices) {
+    indices->clear();
+    std::vector<Pair> nd = case_needle(p.needle.data(), p.needle.size(), p.case_sensitive);
+    std::vector<UChar> und = case_needle_unicode(p.needle.data(), p.needle.size(), p.case_sensitive);
+    if (p.matching != FRZ_MATCHING_FUZZY) {
+        size_t pos; uint16_t sc;
+        bool hit = p.unicode ? ulit_find(p.matching, und, p.needle.size(), p.scoring, hay, hl, &pos, &sc)
+                             : lit_find(p.matching, nd, p.scoring, hay, hl, &pos, &sc);
+        if (!hit) return false;
+        *m = {index, sc, (uint8_t)(pos == 0 && p.needle.size() == hl), 0};
+        for (size_t i = pos + p.needle.size(); i > pos; i--) indices->push_back((uint32_t)(i - 1));
+        return true;
+    }
+    if (hl < p.min_hay_len) return false;
+    size_t s, e;
+    bool pass = p.unicode ? uprefilter(und, hay, hl, p.max_typos, p.pf_lanes, &s, &e)
+                          : prefilter(nd, hay, hl, p.max_typos, p.pf_lanes, &s, &e);
+    if (!pass) return false;
+    s = s > 0 ? s - 1 : 0;
+    bool include_exact = s == 0 && e == hl;
+    const uint8_t* w = hay + s;
+    size_t wl = e - s;
+    uint16_t score = sw_indices(p.needle.data(), p.needle.size(), p.scoring, p.case_sensitive, p.unicode, w, wl, s, p.max_typos,
+                                p.lanes, p.u8, indices);
+    bool exact = include_exact && wl == p.needle.size() && memcmp(w, p.needle.data(), wl) == 0;
+    if (exact) score = (uint16_t)(score + p.scoring.exact_match_bonus);
+    *m = {index, score, (uint8_t)exact, 0};
+    return true;
+}
+
 // src/sort.rs:6-40 (radix_sort_matches) — literal 2-pass LSD radix
 static void radix_sort_matches(frz_match* m, size_t n) {
     std::vector<frz_match> b(n);
@@ -1350,6 +1473,41 @@ int frzo_prefilter_unicode(const uint8_t* needle, size_t n, int case_sensitive, 
 uint16_t frzo_sw_score_unicode(const uint8_t* needle, size_t n, const frz_scoring* sc, int case_sensitive,
                                const uint8_t* hay, size_t len, int include_prefix, int lanes, int score_bits) {
     return sw_score_unicode(needle, n, *sc, case_sensitive != 0, hay, len, include_prefix != 0, lanes, score_bits == 8);
+}
+
+// score_haystack_indices / score_haystack_unicode_indices on a window: returns the score, writes the indices (reverse order)
+uint16_t frzo_sw_indices(const uint8_t* needle, size_t n, const frz_scoring* sc, int case_sensitive, int unicode,
+                         const uint8_t* hay, size_t len, uint64_t start_pos, int max_typos, int lanes, int score_bits,
+                         uint32_t* out, uint32_t cap, uint32_t* n_out) {
+    std::vector<uint32_t> idx;
+    uint16_t score = sw_indices(needle, n, *sc, case_sensitive != 0, unicode != 0, hay, len, (size_t)start_pos, max_typos, lanes,
+                                score_bits == 8, &idx);
+    *n_out = (uint32_t)idx.size();
+    for (size_t i = 0; i < idx.size() && i < cap; i++) out[i] = idx[i];
+    return score;
+}
+
+// Matcher::match_list_indices restricted to the haystacks `which[0..n_which)` of a single-pattern matcher
+// (src/matcher/mod.rs:234-262 → match_one_indices_impl).  out_cnt[j] = number of indices, or 0xFFFFFFFF when haystack
+// which[j] does not match; out_idx[j * stride ...] in the reference's (reverse) order.  Returns 0, or -1 on a bad pattern.
+int frzo_match_indices(const frz_pattern* pattern, const frz_config* cfg, const uint8_t* bytes, const uint64_t* offsets,
+                       const uint32_t* which, uint64_t n_which, uint32_t* out_idx, uint32_t stride, uint32_t* out_cnt,
+                       frz_match* out_match) {
+    OPattern o;
+    if (!compile(*pattern, *cfg, &o)) return -1;
+    std::vector<uint32_t> idx;
+    for (uint64_t j = 0; j < n_which; j++) {
+        const uint64_t i = which[j];
+        frz_match m{};
+        if (!match_one_indices(o, bytes + offsets[i], (size_t)(offsets[i + 1] - offsets[i]), (uint32_t)i, &m, &idx)) {
+            out_cnt[j] = 0xFFFFFFFFu;
+            continue;
+        }
+        out_match[j] = m;
+        out_cnt[j] = (uint32_t)idx.size();
+        for (size_t k = 0; k < idx.size() && k < stride; k++) out_idx[j * (uint64_t)stride + k] = idx[k];
+    }
+    return 0;
 }
 
 // case_needle_unicode for one scalar: writes the flipped scalar's UTF-8 (same length as the input) and returns that length

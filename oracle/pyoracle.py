@@ -46,6 +46,12 @@ def lib():
         L.frzo_prefilter_unicode.argtypes = L.frzo_prefilter.argtypes
         L.frzo_sw_score_unicode.restype = C.c_uint16
         L.frzo_sw_score_unicode.argtypes = L.frzo_sw_score.argtypes
+        L.frzo_sw_indices.restype = C.c_uint16
+        L.frzo_sw_indices.argtypes = [u8p, C.c_size_t, C.POINTER(CScoring), C.c_int, C.c_int, u8p, C.c_size_t, C.c_uint64,
+                                      C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32)]
+        L.frzo_match_indices.restype = C.c_int
+        L.frzo_match_indices.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64,
+                                         C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
         L.frzo_flip_scalar.restype = C.c_int
         L.frzo_flip_scalar.argtypes = [u8p, C.c_size_t, C.POINTER(C.c_uint8)]
         L.frzo_match_greedy.restype = C.c_int
@@ -107,6 +113,42 @@ def sw_score_unicode(needle, haystack, scoring: Scoring = Scoring(), case_sensit
     sc = CScoring.of(scoring)
     return int(lib().frzo_sw_score_unicode(n, len(n), C.byref(sc), int(case_sensitive), h, len(h),
                                            int(include_prefix), lanes, score_bits))
+
+
+def sw_indices(needle, haystack, start_pos: int = 0, max_typos: Optional[int] = None, unicode: bool = False,
+               scoring: Scoring = Scoring(), case_sensitive: bool = False, lanes: int = 8, score_bits: int = 16):
+    """score_haystack_indices / score_haystack_unicode_indices → (score, indices in the reference's reverse order)."""
+    n, h = _b(needle), _b(haystack)
+    sc = CScoring.of(scoring)
+    out = (C.c_uint32 * 4096)()
+    cnt = C.c_uint32()
+    score = lib().frzo_sw_indices(n, len(n), C.byref(sc), int(case_sensitive), int(unicode), h, len(h), start_pos,
+                                  -1 if max_typos is None else max_typos, lanes, score_bits, out, 4096, C.byref(cnt))
+    return int(score), list(out[: cnt.value])
+
+
+def match_indices(pattern, config: Config, data: np.ndarray, offsets: np.ndarray, which, stride: int = 128):
+    """Matcher::match_list_indices of a single-pattern matcher on the chosen haystacks.
+    Returns a list of None (no match) or (score, exact, indices)."""
+    arr = pattern_array([as_pattern(pattern)])
+    cfg = CConfig.of(config)
+    which = np.ascontiguousarray(which, dtype=np.uint32)
+    out_idx = np.zeros((len(which), stride), dtype=np.uint32)
+    out_cnt = np.zeros(len(which), dtype=np.uint32)
+    out_m = np.zeros(len(which), dtype=MATCH_DTYPE)
+    data = np.ascontiguousarray(data, dtype=np.uint8)
+    offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+    rc = lib().frzo_match_indices(C.cast(arr, C.c_void_p), C.byref(cfg), data.ctypes.data if data.size else None, offsets.ctypes.data, which.ctypes.data, len(which),
+                                  out_idx.ctypes.data, stride, out_cnt.ctypes.data, out_m.ctypes.data)
+    if rc != 0:
+        raise ValueError("empty pattern")
+    res = []
+    for j in range(len(which)):
+        if out_cnt[j] == 0xFFFFFFFF:
+            res.append(None)
+        else:
+            res.append((int(out_m[j]["score"]), bool(out_m[j]["exact"]), out_idx[j, : min(int(out_cnt[j]), stride)].tolist()))
+    return res
 
 
 def flip_scalar(ch: str) -> str:

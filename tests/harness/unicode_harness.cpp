@@ -7,6 +7,7 @@
 
 #include "../../frizbee_b200/csrc/unicode_needle.h"
 #include "../../frizbee_b200/csrc/unicode_path.cuh"
+#include "../../frizbee_b200/csrc/indices_path.cuh"
 
 namespace {
 struct Flat {
@@ -45,6 +46,15 @@ int h_sw_score(const uint8_t* needle, size_t n, int case_sensitive, const uint16
     std::vector<uint16_t> scratch((size_t)2 * (nd.n + 1) * lanes);
     Flat h{hay};
     return (int)frzu::sw_score(nd, sc, h, len, include_prefix != 0, lanes, score_bits == 8, scratch.data());
+}
+int h_sw_indices(const uint8_t* needle, size_t n, int case_sensitive, int unicode, const uint16_t* scoring9, const uint8_t* hay, int len,
+                 int start_pos, int max_typos, int lanes, int score_bits, uint32_t* out, int cap, int* n_out) {
+    FrzUNeedle nd;
+    if (!frz_build_uneedle(needle, n, case_sensitive != 0, &nd)) return -1;
+    const FrzUScoring sc = scoring_of(scoring9, score_bits == 8);
+    std::vector<uint16_t> scratch(frzi::indices_scratch_elems(unicode ? nd.n : nd.nbytes, lanes));
+    Flat h{hay};
+    return (int)frzi::sw_indices(nd, unicode != 0, sc, h, len, start_pos, max_typos, lanes, score_bits == 8, scratch.data(), out, cap, n_out);
 }
 int h_lit_find(const uint8_t* needle, size_t n, int case_sensitive, const uint16_t* scoring9, const uint8_t* hay, int len, int mode,
                int* pos, uint32_t* score) {

@@ -569,3 +569,43 @@ def test_unicode_matcher_pipeline():
     assert [m.index for m in pre] == [0, 1] and pre[0].score > pre[1].score
     sub = O.match_list([Pattern("다", matching=Matching.Substring)], ["a다", "다", "가나"], Config(sort=SortStrategy.IndexAsc))
     assert [(m.index, m.exact) for m in sub] == [(0, False), (1, True)]
+
+
+# ---------------------------------------------------------------- traceback (match_list_indices)
+def test_indices_kats():
+    # src/smith_waterman/mod.rs:322-326, 443-450, 453-520 (BackendScalar8: 8 lanes, u16)
+    gi = lambda n, h: O.sw_indices(n, h)[1]
+    assert gi("aa", "aaa") == [1, 0] and gi("ab", "abab") == [1, 0] and gi("abc", "xabcabc") == [3, 2, 1]
+    assert gi("_", "abc") == [] and gi("a", "abc") == [0] and gi("b", "abc") == [1] and gi("c", "abc") == [2]
+    assert gi("ac", "________________abc") == [18, 16] and gi("foo", "Uf") == [1]
+    gu = lambda n, h, sp=0: O.sw_indices(n, h, sp, unicode=True)[1]
+    assert gu("é", "é") == [1, 0] and gu("😀", "😀") == [3, 2, 1, 0] and gu("aé", "aé") == [2, 1, 0]
+    assert gu("é", "é", 3) == [4, 3] and gu("éx", "é😀x", 3) == [9, 4, 3]
+    assert gu("ab", "aéb") == [3, 0] and gu("ab", "aé😀b") == [7, 0] and gu("éx", "é😀x") == [6, 1, 0]
+    assert gu("éé", "ééé") == [3, 2, 1, 0] and gu("😀x", "_______😀x") == [11, 10, 9, 8, 7]
+    assert gu("😀.a", "..😀a") == [6, 1] and gu("😀.é", "..😀é") == [7, 6, 1]
+    assert gu("😀 a", "  😀a") == [6, 1] and gu("😀é", "..😀é") == [7, 6, 5, 4, 3, 2]
+    s = Scoring()
+    for ln in (1023, 1024, 1025):   # matrix / greedy boundary (long_input_boundary_indices_stay_reverse_ordered)
+        h = "x" * (ln - 3) + "abc"
+        sc, idx = O.sw_indices("abc", h)
+        assert sc == 3 * (s.match_score + s.matching_case_bonus) and idx == [ln - 1, ln - 2, ln - 3], ln
+
+
+def test_match_indices_pipeline():
+    # Matcher::match_list_indices membership and scores equal match_list (src/matcher/multi.rs:253-275 checks the same)
+    hs = ["foo", "f_o_o", "xfoo", "nomatch", "FooBar", "xxé__다__😀yy", "é다😀"]
+    data, off = O.pack(hs)
+    for needle, cfg in [("foo", Config(max_typos=0)), ("foo", Config(max_typos=1)), ("é다😀", Config(max_typos=0)),
+                        (Pattern("oo", matching=Matching.Substring), Config())]:
+        ml = {m.index: m for m in O.match_list([needle], hs, cfg)}
+        mi = O.match_indices(needle, cfg, data, off, list(range(len(hs))))
+        for i, r in enumerate(mi):
+            assert (r is None) == (i not in ml), (needle, i)
+            if r is not None:
+                assert (r[0], r[1]) == (ml[i].score, ml[i].exact)
+                assert all(a > b for a, b in zip(r[2], r[2][1:])), r      # strictly descending byte offsets
+                hb = hs[i].encode()
+                assert all(0 <= x < len(hb) for x in r[2])
+    assert O.match_indices("foo", Config(max_typos=0), data, off, [0, 1, 2])[1][2] == [4, 2, 0]
+    assert O.match_indices(Pattern("oo", matching=Matching.Substring), Config(), data, off, [2])[0][2] == [3, 2]

@@ -17,6 +17,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SRC = os.path.join(ROOT, "tests", "harness", "unicode_harness.cpp")
 LIB = os.path.join(ROOT, "tests", "harness", "libunicode_harness.so")
 DEPS = [SRC, os.path.join(ROOT, "frizbee_b200", "csrc", "unicode_path.cuh"),
+        os.path.join(ROOT, "frizbee_b200", "csrc", "indices_path.cuh"),
         os.path.join(ROOT, "frizbee_b200", "csrc", "unicode_needle.h"),
         os.path.join(ROOT, "frizbee_b200", "csrc", "unicode_case.inc")]
 
@@ -32,6 +33,8 @@ def H():
     L.h_lit_find.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.c_void_p, C.c_char_p, C.c_int, C.c_int,
                              C.POINTER(C.c_int), C.POINTER(C.c_uint32)]
     L.h_needle_has_uppercase.argtypes = [C.c_char_p, C.c_size_t]
+    L.h_sw_indices.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_char_p, C.c_int, C.c_int, C.c_int,
+                               C.c_int, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_int)]
     return L
 
 
@@ -127,3 +130,37 @@ def test_literal_modes_equal_oracle(H):
         assert got == len(want), (needle, hay, mode, cs)
         if want:
             assert score.value == want[0].score and (pos.value == 0 and len(nb) == len(hb)) == want[0].exact, (needle, hay, mode, cs)
+
+
+@pytest.mark.parametrize("lanes,bits", [(8, 16), (16, 16), (32, 16), (16, 8), (32, 8), (64, 8)])
+def test_traceback_indices_equal_oracle(H, lanes, bits):
+    # frizbee_b200/csrc/indices_path.cuh (byte scorer with full matrices + AlignmentPathIter) vs the oracle
+    rng = random.Random(900 + lanes + bits)
+    s9 = scoring9(Scoring())
+    out = (C.c_uint32 * 2048)()
+    for trial in range(3000):
+        unicode = rng.random() < 0.5
+        pool = rng.choice(POOLS if unicode else ["abAB_/-ab01", "ab", "fooBar_x"])
+        needle = rand_str(rng, pool, rng.randint(1, 5))
+        if bits == 8 and not O.score_fits_in_u8(len(needle.encode()), Scoring()):
+            continue
+        hay = rand_str(rng, pool + "x_", rng.choice([1, 2, 5, 8, 15, 16, 17, 33, 64, 65, 90, 130]))
+        cs = rng.random() < 0.3
+        k = rng.choice([None, 0, 1, 2, 3])
+        sp = rng.choice([0, 0, 1, 7])
+        nb, hb = needle.encode(), hay.encode()
+        cnt = C.c_int()
+        got = H.h_sw_indices(nb, len(nb), int(cs), int(unicode), s9.ctypes.data, hb, len(hb), sp, -1 if k is None else k, lanes, bits,
+                             out, 2048, C.byref(cnt))
+        want = O.sw_indices(nb, hb, sp, k, unicode, Scoring(), cs, lanes, bits)
+        assert (got, list(out[: cnt.value])) == want, (needle, hay, unicode, cs, k, sp, lanes, bits, got, list(out[: cnt.value]), want)
+
+
+def test_traceback_greedy_over_1024(H):
+    s9 = scoring9(Scoring())
+    out = (C.c_uint32 * 64)()
+    cnt = C.c_int()
+    hay = ("x" * 700 + "a" + "y" * 400 + "bc").encode()
+    got = H.h_sw_indices(b"abc", 3, 0, 0, s9.ctypes.data, hay, len(hay), 5, -1, 16, 16, out, 64, C.byref(cnt))
+    assert (got, list(out[: cnt.value])) == O.sw_indices(b"abc", hay, 5, None, False, Scoring(), False, 16, 16)
+    assert list(out[: cnt.value]) == [len(hay) - 1 + 5, len(hay) - 2 + 5, 700 + 5]
