@@ -89,6 +89,7 @@ def lib():
     L.frz_match_list_into.argtypes = [vp, vp, u32, vp, u64, C.POINTER(u64)]
     L.frz_match_list_host.argtypes = [vp, vp, vp, u64, C.c_int, vp, u64, C.POINTER(u64)]
     L.frz_match_list_host_arrow.argtypes = [vp, vp, vp, C.c_int, u64, C.c_int, vp, u64, C.POINTER(u64)]
+    L.frz_match_indices.argtypes = [vp, vp, vp, u64, vp, vp, u32, vp]
     L.frz_match_shard_device.argtypes = [vp, vp, u32, vp, u64, vp, vp]
     L.frz_matcher_wait_count.argtypes = [vp, vp]
     L.frz_merge_runs_device.argtypes = [vp, u64, vp, C.c_int, C.c_uint8, u32, vp, C.c_int, vp]
@@ -316,6 +317,23 @@ class Matcher:
         finally:
             if owned:
                 corpus.close()
+
+    def match_indices(self, corpus: "Corpus", which, stride: int = 128):
+        """Matcher::match_list_indices for the chosen haystacks: list of None (no match) or (score, exact, indices)."""
+        which = np.ascontiguousarray(which, dtype=np.uint32)
+        n = len(which)
+        out_m = np.zeros(max(n, 1), dtype=MATCH_DTYPE)
+        out_idx = np.zeros((max(n, 1), stride), dtype=np.uint32)
+        out_cnt = np.zeros(max(n, 1), dtype=np.uint32)
+        _check(lib().frz_match_indices(self._h, corpus._h, which.ctypes.data, n, out_m.ctypes.data, out_idx.ctypes.data, stride,
+                                       out_cnt.ctypes.data))
+        res = []
+        for j in range(n):
+            if out_cnt[j] == 0xFFFFFFFF:
+                res.append(None)
+            else:
+                res.append((int(out_m[j]["score"]), bool(out_m[j]["exact"]), out_idx[j, : int(out_cnt[j])].tolist()))
+        return res
 
     def match_list_host_array(self, data: np.ndarray, offsets: np.ndarray, device: int = 0,
                               out: Optional[np.ndarray] = None) -> np.ndarray:

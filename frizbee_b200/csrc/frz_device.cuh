@@ -140,6 +140,17 @@ struct FrzCounters {
 
 __device__ __forceinline__ uint32_t frz_lane() { return threadIdx.x & 31; }
 
+// Byte accessor of one packed haystack for the per-thread correctness paths (unicode.cu, k_match_indices):
+// `base` is the lane-resolved pointer to unit 0 of the slot (unit k at base + FRZ_GROUP * k), `shift` the window start.
+struct FrzPackedHay {
+    const uint4* base;
+    int shift;
+    __device__ __forceinline__ uint8_t operator()(int i) const {
+        const uint32_t j = (uint32_t)(i + shift);
+        return (uint8_t)((reinterpret_cast<const uint32_t*>(base + (size_t)(j >> 4) * FRZ_GROUP)[(j >> 2) & 3] >> ((j & 3) * 8)) & 0xff);
+    }
+};
+
 // address of unit k of (tile, slot)
 __device__ __forceinline__ const uint4* frz_unit_ptr(const FrzCorpusView& cv, uint32_t tile, uint32_t slot, uint32_t k) {
     const FrzGroupDesc gd = cv.groups[tile * FRZ_GROUPS_PER_TILE + (slot >> 5)];

@@ -20,6 +20,7 @@
 #include "frz_device.cuh"
 #include "frz_host.h"
 #include "unicode_needle.h"
+#include "indices_path.cuh"
 
 // ------------------------------------------------------------------------------------ errors
 
@@ -407,8 +408,19 @@ frz_status compile_pattern(const OwnedPattern& src, const frz_config& mcfg, bool
     c.negated = src.negated;
     c.literal = matching != FRZ_MATCHING_FUZZY;
     c.unicode = needs_unicode;
-    if (needs_unicode && !frz_build_uneedle(nd, n, case_sensitive, &c.un))
-        return frz_fail(FRZ_ERR_INVALID_ARG, "the needle is not valid UTF-8");
+    if (needs_unicode) {
+        if (!frz_build_uneedle(nd, n, case_sensitive, &c.un)) return frz_fail(FRZ_ERR_INVALID_ARG, "the needle is not valid UTF-8");
+    } else {
+        // byte path: only the byte-level case_needle pairs are used (frz_match_indices); the needle may be any bytes
+        memset(&c.un, 0, sizeof c.un);
+        c.un.nbytes = (int32_t)n;
+        for (size_t i = 0; i < n; i++) {
+            const uint8_t ch = nd[i];
+            c.un.c[i] = ch;
+            c.un.f[i] = ch;
+            c.un.bflip[i] = case_sensitive ? ch : (ch >= 'a' && ch <= 'z') ? (uint8_t)(ch - 32) : (ch >= 'A' && ch <= 'Z') ? (uint8_t)(ch + 32) : ch;
+        }
+    }
     d.n = (int)n;
     d.matching = matching;
     d.case_sensitive = case_sensitive;
@@ -1145,6 +1157,43 @@ extern "C" frz_status frz_match_list_host_arrow(frz_matcher* m, const uint8_t* b
 extern "C" frz_status frz_match_list_host(frz_matcher* m, const uint8_t* bytes, const uint64_t* offsets, uint64_t n, int device,
                                           frz_match* out, uint64_t cap, uint64_t* n_out) {
     return frz_match_list_host_arrow(m, bytes, offsets, 8, n, device, out, cap, n_out);
+}
+
+// Matcher::match_list_indices for chosen haystacks (src/matcher/mod.rs:234-262): Match + matched byte offsets.
+extern "C" frz_status frz_match_indices(frz_matcher* m, const frz_corpus* corpus, const uint32_t* which, uint64_t n,
+                                        frz_match* out_matches, uint32_t* out_indices, uint32_t stride, uint32_t* out_counts) {
+    if (!m || !corpus || (n && (!which || !out_matches || !out_indices || !out_counts)) || stride == 0)
+        return frz_fail(FRZ_ERR_INVALID_ARG, "null argument");
+    if (m->compiled.size() != 1 || m->compiled[0].negated)
+        return frz_fail(FRZ_ERR_UNSUPPORTED, "frz_match_indices needs a matcher with exactly one non-negated pattern");
+    if (n == 0) return FRZ_OK;
+    FRZ_TRY(ensure_device(corpus->st.device));
+    const Compiled& c = m->compiled[0];
+    cudaStream_t stream = nullptr;
+    const uint32_t threads = (uint32_t)std::min<uint64_t>(n, 1024);
+    const int rows = c.unicode ? c.un.n : c.un.nbytes;
+    const uint64_t sstride = c.literal ? 1 : (uint64_t)frzi::indices_scratch_elems(rows, c.dev.sw_lanes);
+    uint32_t *d_which = nullptr, *d_idx = nullptr, *d_cnt = nullptr;
+    FrzMatchDev* d_m = nullptr;
+    uint16_t* d_scratch = nullptr;
+    frz_status st = [&]() -> frz_status {
+        FRZ_CUDA_TRY(cudaMalloc(&d_which, n * sizeof(uint32_t)));
+        FRZ_CUDA_TRY(cudaMalloc(&d_idx, n * (uint64_t)stride * sizeof(uint32_t)));
+        FRZ_CUDA_TRY(cudaMalloc(&d_cnt, n * sizeof(uint32_t)));
+        FRZ_CUDA_TRY(cudaMalloc(&d_m, n * sizeof(FrzMatchDev)));
+        FRZ_CUDA_TRY(cudaMalloc(&d_scratch, (uint64_t)threads * sstride * sizeof(uint16_t)));
+        FRZ_CUDA_TRY(cudaMemcpyAsync(d_which, which, n * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
+        FRZ_CUDA_TRY(cudaMemsetAsync(d_m, 0, n * sizeof(FrzMatchDev), stream));
+        FRZ_TRY(frz_launch_match_indices(corpus->st.view(), c.dev, c.un, c.usc, c.unicode, d_which, n, d_m, d_idx, stride, d_cnt,
+                                         d_scratch, sstride, threads, stream));
+        FRZ_CUDA_TRY(cudaMemcpyAsync(out_matches, d_m, n * sizeof(FrzMatchDev), cudaMemcpyDeviceToHost, stream));
+        FRZ_CUDA_TRY(cudaMemcpyAsync(out_indices, d_idx, n * (uint64_t)stride * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+        FRZ_CUDA_TRY(cudaMemcpyAsync(out_counts, d_cnt, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+        FRZ_CUDA_TRY(cudaStreamSynchronize(stream));
+        return FRZ_OK;
+    }();
+    cudaFree(d_which); cudaFree(d_idx); cudaFree(d_cnt); cudaFree(d_m); cudaFree(d_scratch);
+    return st;
 }
 
 extern "C" frz_status frz_match_shard_device(frz_matcher* m, const frz_corpus* shard, uint32_t index_offset, frz_match* d_out,

@@ -22,6 +22,7 @@
 #include <algorithm>
 
 #include "frz_host.h"
+#include "indices_path.cuh"
 
 namespace {
 
@@ -839,6 +840,69 @@ __global__ void __launch_bounds__(1024) k_tile_scan(const uint32_t* __restrict__
     if (threadIdx.x == 0) ctr->total = carry_s;
 }
 
+// Matcher::match_list_indices for chosen haystacks (src/matcher/mod.rs:234-262 → match_one_indices_impl,
+// src/matcher/algo.rs:138-169, src/literal/algo.rs:134-155).  One thread per requested haystack; the scoring with
+// full matrices and the traceback are in indices_path.cuh (shared with the CPU test build), the ASCII windows come
+// from the scanning prefilters above.  Not a hot path: the reference documents it as unoptimised too.
+__global__ void __launch_bounds__(128) k_match_indices(const FrzCorpusView cv, const __grid_constant__ FrzPatternDev pat,
+                                                       const __grid_constant__ FrzUNeedle un, const FrzUScoring usc, int unicode,
+                                                       const uint32_t* __restrict__ which, unsigned long long n,
+                                                       FrzMatchDev* __restrict__ out_matches, uint32_t* __restrict__ out_idx,
+                                                       uint32_t stride, uint32_t* __restrict__ out_cnt,
+                                                       uint16_t* __restrict__ scratch, unsigned long long scratch_stride) {
+    const unsigned long long tid = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned long long nthreads = (unsigned long long)gridDim.x * blockDim.x;
+    uint16_t* my_scratch = scratch + tid * scratch_stride;
+    const int max_typos = pat.typo_mode == FRZ_T_NONE ? -1 : pat.typo_mode == FRZ_T_0 ? 0 : pat.typo_mode == FRZ_T_1 ? 1
+                        : pat.typo_mode == FRZ_T_2 ? 2 : pat.max_typos;
+    for (unsigned long long j = tid; j < n; j += nthreads) {
+        const uint32_t idx = which[j];
+        out_cnt[j] = 0xFFFFFFFFu;
+        if (idx >= cv.n) continue;
+        const uint32_t tile = idx >> FRZ_TILE_SHIFT;
+        const uint32_t slot = cv.slot_of[idx];
+        const uint32_t meta = cv.slot_meta[(uint64_t)tile * FRZ_TILE + slot];
+        const int len = (int)(meta >> FRZ_TILE_SHIFT);
+        const FrzGroupDesc gd = cv.groups[tile * FRZ_GROUPS_PER_TILE + (slot >> 5)];
+        const GlobalAcc ga{cv.data + gd.abs_off + (slot & 31)};
+        const FrzPackedHay hay{ga.base, 0};
+        uint32_t* my_out = out_idx + j * (unsigned long long)stride;
+        uint32_t score = 0;
+        bool exact = false;
+        int cnt = 0;
+        if (pat.matching != FRZ_MATCHING_FUZZY) {
+            int pos = 0;
+            const bool ok = unicode ? frzu::lit_find(un, usc, hay, len, pat.matching, &pos, &score) : lit_find(ga, pat, len, &pos, &score);
+            if (!ok) continue;
+            exact = pos == 0 && pat.n == len;
+            for (int i = pos + pat.n - 1; i >= pos; i--) { if (cnt < (int)stride) my_out[cnt] = (uint32_t)i; cnt++; }
+        } else {
+            if (len < pat.min_hay_len) continue;
+            int start = 0, end = len;
+            bool ok;
+            if (unicode) ok = frzu::prefilter(un, hay, len, pat.pf_lanes, max_typos, &start, &end);
+            else if (pat.typo_mode == FRZ_T_0) ok = window_k0(ga, pat, len, &start, &end);
+            else if (pat.typo_mode == FRZ_T_1) ok = window_k1(ga, pat, len, &start, &end);
+            else if (pat.typo_mode == FRZ_T_2) ok = window_k2(ga, pat, len, &start, &end);
+            else if (pat.typo_mode == FRZ_T_MANY) ok = window_many(ga, pat, len, &start, &end);
+            else ok = true;
+            if (!ok) continue;
+            start = start > 0 ? start - 1 : 0;   // trim_haystack
+            const int W = end - start;
+            const FrzPackedHay win{ga.base, start};
+            score = frzi::sw_indices(un, unicode != 0, usc, win, W, start, max_typos, pat.sw_lanes, pat.score_bits == 8, my_scratch,
+                                     my_out, (int)stride, &cnt);
+            exact = start == 0 && end == len && W == pat.n;
+            for (int k = 0; exact && k < W; k++) exact = win(k) == pat.c[k];
+            if (exact) score = (score + (uint32_t)pat.exact_bonus) & 0xffffu;
+        }
+        FrzMatchDev m;
+        m.index = idx; m.score = (uint16_t)score; m.exact = exact ? 1 : 0; m.pad = 0;
+        out_matches[j] = m;
+        out_cnt[j] = (uint32_t)(cnt < (int)stride ? cnt : (int)stride);
+    }
+}
+
 }  // namespace
 
 frz_status frz_launch_prefilter_list(const FrzCorpusView& cv, const FrzPatternDev& pat, const FrzMatchDev* cand,
@@ -930,5 +994,17 @@ frz_status frz_launch_tile_scan(const FrzCorpusView& cv, FrzWorkspace& ws, cudaS
     k_tile_scan<<<1, 1024, 0, stream>>>(ws.tile_count, ws.tile_out_base, cv.n_tiles, ws.counters);
     FRZ_CUDA_TRY(cudaGetLastError());
     if (st) st->launches++;
+    return FRZ_OK;
+}
+
+frz_status frz_launch_match_indices(const FrzCorpusView& cv, const FrzPatternDev& pat, const FrzUNeedle& un, const FrzUScoring& usc,
+                                    bool unicode, const uint32_t* d_which, uint64_t n, FrzMatchDev* d_matches, uint32_t* d_idx,
+                                    uint32_t stride, uint32_t* d_cnt, uint16_t* d_scratch, uint64_t scratch_stride, uint32_t threads,
+                                    cudaStream_t stream) {
+    if (n == 0) return FRZ_OK;
+    const uint32_t grid = (threads + 127) / 128;
+    k_match_indices<<<grid, 128, 0, stream>>>(cv, pat, un, usc, unicode ? 1 : 0, d_which, n, d_matches, d_idx, stride, d_cnt,
+                                              d_scratch, scratch_stride);
+    FRZ_CUDA_TRY(cudaGetLastError());
     return FRZ_OK;
 }

@@ -15,15 +15,7 @@ namespace {
 
 constexpr int kUThreads = 128;
 
-// byte i of the haystack whose lane-resolved unit pointer is `base` (units of one lane are FRZ_GROUP units apart)
-struct PackedHay {
-    const uint4* base;
-    int shift;   // window start inside the haystack
-    __device__ __forceinline__ uint8_t operator()(int i) const {
-        const uint32_t j = (uint32_t)(i + shift);
-        return (uint8_t)((reinterpret_cast<const uint32_t*>(base + (size_t)(j >> 4) * FRZ_GROUP)[(j >> 2) & 3] >> ((j & 3) * 8)) & 0xff);
-    }
-};
+using PackedHay = FrzPackedHay;
 
 __global__ void __launch_bounds__(kUThreads) k_unicode(const FrzCorpusView cv, const __grid_constant__ FrzPatternDev pat,
                                                        const __grid_constant__ FrzUNeedle un, const FrzUScoring usc,

@@ -218,6 +218,14 @@ FRZ_API frz_status frz_match_list_host(frz_matcher* m, const uint8_t* bytes, con
 FRZ_API frz_status frz_match_list_host_arrow(frz_matcher* m, const uint8_t* bytes, const void* offsets, int offset_width,
                                      uint64_t n, int device, frz_match* out, uint64_t cap, uint64_t* n_out);
 
+/* Matcher::match_list_indices (src/matcher/mod.rs:234-262) for CHOSEN haystacks — the rows a UI is about to display:
+ * for haystack which[j] (corpus-relative index) writes its Match to out_matches[j] and the byte offsets of the
+ * matched characters, in the reference's descending order, to out_indices[j * stride ...]; out_counts[j] = how many
+ * (capped at stride), or UINT32_MAX when that haystack does not match.  Host pointers; matchers with exactly one
+ * non-negated pattern (fuzzy, ASCII or unicode needle, or literal).  Like the reference's, not a tuned path. */
+FRZ_API frz_status frz_match_indices(frz_matcher* m, const frz_corpus* corpus, const uint32_t* which, uint64_t n,
+                             frz_match* out_matches, uint32_t* out_indices, uint32_t stride, uint32_t* out_counts);
+
 /* Device-resident variant used by the multi-GPU path (Matcher::match_list_parallel,
  * src/matcher/parallel.rs:18-89): this rank's shard → a locally ordered run left in HBM.
  * `d_out` (cap matches) and `d_count` (one uint64) are device pointers; `stream` is a

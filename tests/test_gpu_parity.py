@@ -432,3 +432,30 @@ def test_unicode_literal_and_multi_pattern():
     gpu_vs_oracle([Pattern("다"), Pattern("a")], data, off, Config(max_typos=0), corpus)
     gpu_vs_oracle([Pattern("fo"), Pattern("é😀", max_typos=1)], data, off, Config(max_typos=0), corpus)
     corpus.close()
+
+
+def test_match_indices_traceback():
+    # frz_match_indices == Matcher::match_list_indices restricted to chosen haystacks (src/matcher/mod.rs:234-262):
+    # scores/exact flags equal match_list, indices equal the oracle's traceback (AlignmentPathIter)
+    rng = random.Random(31337)
+    hs = [rand for rand in ("".join(rng.choice("abAB_/-ab01") for _ in range(rng.choice([0, 3, 9, 20, 40, 70, 140]))) for _ in range(1500))]
+    hs += _unicode_haystacks(rng, 1500)
+    hs += ["foo", "f_o_o", "xfoo", "FooBar", "x" * 1200 + "a" + "y" * 30 + "bc", "é다😀", "xxé__다__😀yy"]
+    data, off = from_list(hs)
+    corpus = F.Corpus.from_arrow(data, off)
+    which = list(range(len(hs)))
+    cases = [("ab", Config(max_typos=0)), ("ab_", Config(max_typos=1)), ("abA", Config(max_typos=None)), ("a/b01", Config(max_typos=2)),
+             ("abc", Config(max_typos=1)), ("é다😀", Config(max_typos=1)), ("éa", Config(max_typos=0)),
+             ("foo", Config(max_typos=1, unicode=UnicodeMatching.Always)),
+             (Pattern("ab", matching=Matching.Substring), Config()), (Pattern("é", matching=Matching.Prefix), Config()),
+             ("ab", Config(max_typos=1, emulate_lanes=16)), ("abAB_/-ab01abAB", Config(max_typos=3, emulate_lanes=32))]
+    for needle, cfg in cases:
+        m = F.Matcher(needle, cfg)
+        lanes = m.backend_info()["prefilter_lanes"]
+        got = m.match_indices(corpus, which)
+        want = O.match_indices(needle, cfg.with_(emulate_lanes=lanes), data, off, which)
+        assert got == want, (needle, cfg, [(i, g, w) for i, (g, w) in enumerate(zip(got, want)) if g != w][:3])
+        ml = {int(x["index"]): x for x in m.match_list_array(corpus)}
+        assert {i for i, g in enumerate(got) if g is not None} == set(ml)
+        m.close()
+    corpus.close()
