@@ -11,6 +11,7 @@
 #include "unicode_path.cuh"
 
 frz_status frz_fail(frz_status s, const char* fmt, ...);
+inline int frz_current_device() { int d = 0; cudaGetDevice(&d); return d; }
 
 #define FRZ_CUDA_TRY(expr)                                                                         \
     do {                                                                                           \

@@ -1160,15 +1160,10 @@ extern "C" frz_status frz_match_list_host(frz_matcher* m, const uint8_t* bytes, 
 }
 
 // Matcher::match_list_indices for chosen haystacks (src/matcher/mod.rs:234-262): Match + matched byte offsets.
-extern "C" frz_status frz_match_indices(frz_matcher* m, const frz_corpus* corpus, const uint32_t* which, uint64_t n,
-                                        frz_match* out_matches, uint32_t* out_indices, uint32_t stride, uint32_t* out_counts) {
-    if (!m || !corpus || (n && (!which || !out_matches || !out_indices || !out_counts)) || stride == 0)
-        return frz_fail(FRZ_ERR_INVALID_ARG, "null argument");
-    if (m->compiled.size() != 1 || m->compiled[0].negated)
-        return frz_fail(FRZ_ERR_UNSUPPORTED, "frz_match_indices needs a matcher with exactly one non-negated pattern");
-    if (n == 0) return FRZ_OK;
-    FRZ_TRY(ensure_device(corpus->st.device));
-    const Compiled& c = m->compiled[0];
+namespace {
+// one pattern over the chosen rows: match_one_indices_impl (fuzzy / literal), results in host arrays
+frz_status match_indices_one(const Compiled& c, const frz_corpus* corpus, const uint32_t* which, uint64_t n, frz_match* out_matches,
+                             uint32_t* out_indices, uint32_t stride, uint32_t* out_counts) {
     cudaStream_t stream = nullptr;
     const uint32_t threads = (uint32_t)std::min<uint64_t>(n, 1024);
     const int rows = c.unicode ? c.un.n : c.un.nbytes;
@@ -1194,6 +1189,47 @@ extern "C" frz_status frz_match_indices(frz_matcher* m, const frz_corpus* corpus
     }();
     cudaFree(d_which); cudaFree(d_idx); cudaFree(d_cnt); cudaFree(d_m); cudaFree(d_scratch);
     return st;
+}
+}  // namespace
+
+extern "C" frz_status frz_match_indices(frz_matcher* m, const frz_corpus* corpus, const uint32_t* which, uint64_t n,
+                                        frz_match* out_matches, uint32_t* out_indices, uint32_t stride, uint32_t* out_counts) {
+    if (!m || !corpus || (n && (!which || !out_matches || !out_indices || !out_counts)) || stride == 0)
+        return frz_fail(FRZ_ERR_INVALID_ARG, "null argument");
+    if (m->compiled.empty()) return frz_fail(FRZ_ERR_INVALID_ARG, "the matcher has no pattern");
+    if (n == 0) return FRZ_OK;
+    FRZ_TRY(ensure_device(corpus->st.device));
+    if (m->compiled.size() == 1 && !m->compiled[0].negated)   // CompiledPatterns::Single
+        return match_indices_one(m->compiled[0], corpus, which, n, out_matches, out_indices, stride, out_counts);
+    // CompiledPatterns::Multi → match_one_indices_multi (src/matcher/multi.rs:56-79): a negated atom that matches drops the
+    // row, the others add their scores, OR their exact flags and pool their indices (sorted descending, de-duplicated)
+    std::vector<frz_match> pm(n);
+    std::vector<uint32_t> pi((size_t)n * stride), pc(n);
+    std::vector<std::vector<uint32_t>> pooled(n);
+    std::vector<uint8_t> alive(n, 1);
+    for (uint64_t j = 0; j < n; j++) out_matches[j] = frz_match{which[j], 0, 0, 0};
+    for (const Compiled& c : m->compiled) {
+        FRZ_TRY(match_indices_one(c, corpus, which, n, pm.data(), pi.data(), stride, pc.data()));
+        for (uint64_t j = 0; j < n; j++) {
+            if (!alive[j]) continue;
+            const bool hit = pc[j] != 0xFFFFFFFFu;
+            if (c.negated) { if (hit) alive[j] = 0; continue; }
+            if (!hit) { alive[j] = 0; continue; }
+            const uint32_t sum = (uint32_t)out_matches[j].score + pm[j].score;
+            out_matches[j].score = (uint16_t)std::min<uint32_t>(sum, 0xFFFF);
+            out_matches[j].exact |= pm[j].exact;
+            pooled[j].insert(pooled[j].end(), pi.begin() + (size_t)j * stride, pi.begin() + (size_t)j * stride + pc[j]);
+        }
+    }
+    for (uint64_t j = 0; j < n; j++) {
+        if (!alive[j]) { out_counts[j] = 0xFFFFFFFFu; continue; }
+        auto& v = pooled[j];
+        std::sort(v.begin(), v.end(), [](uint32_t a, uint32_t b) { return a > b; });
+        v.erase(std::unique(v.begin(), v.end()), v.end());
+        out_counts[j] = (uint32_t)std::min<size_t>(v.size(), stride);
+        for (uint32_t k = 0; k < out_counts[j]; k++) out_indices[(size_t)j * stride + k] = v[k];
+    }
+    return FRZ_OK;
 }
 
 extern "C" frz_status frz_match_shard_device(frz_matcher* m, const frz_corpus* shard, uint32_t index_offset, frz_match* d_out,

@@ -915,7 +915,8 @@ frz_status frz_launch_prefilter_list(const FrzCorpusView& cv, const FrzPatternDe
     const uint32_t grid = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(148 * 4, (n_cand + kThreads - 1) / kThreads));
 #define FRZ_PFL_LAUNCH(MODE)                                                                                     \
     do {                                                                                                         \
-        static bool attr_set = false;                                                                            \
+        static bool attr_set_dev[64] = {};                                                                       \
+        bool& attr_set = attr_set_dev[frz_current_device() & 63];                                                \
         if (!attr_set) {                                                                                         \
             FRZ_CUDA_TRY(cudaFuncSetAttribute(k_prefilter_list<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
             attr_set = true;                                                                                     \
@@ -961,7 +962,8 @@ frz_status frz_launch_prefilter(const FrzCorpusView& cv, const FrzPatternDev& pa
 #define FRZ_PF_LAUNCH_N(MODE) do { if (narrow) FRZ_PF_LAUNCH_S(MODE, 4); else FRZ_PF_LAUNCH_S(MODE, 8); } while (0)
 #define FRZ_PF_LAUNCH_S(MODE, SL)                                                                                     \
     do {                                                                                                        \
-        static bool attr_set = false;                                                                           \
+        static bool attr_set_dev[64] = {};                                                                      \
+        bool& attr_set = attr_set_dev[frz_current_device() & 63];                                               \
         if (!attr_set) {                                                                                        \
             FRZ_CUDA_TRY(cudaFuncSetAttribute(k_prefilter<MODE, SL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
             attr_set = true;                                                                                    \

@@ -688,7 +688,8 @@ frz_status launch_sw_lanes(const FrzCorpusView& cv, const FrzPatternDev& pat, ui
     else
         k_sw64<LANES, false><<<blocks64, kSwThreads, 0, stream>>>(cv, pat, ws.lists(), ws.survivor_cap, rank_view(ws), ws.counters, index_offset, rev, d_out);
     const size_t smem = SwCore<LANES, 128, false>::smem_bytes;
-    static bool attr_set = false;
+    static bool attr_set_dev[64] = {};   // function attributes are per device
+    bool& attr_set = attr_set_dev[frz_current_device() & 63];
     if (!attr_set) {
         FRZ_CUDA_TRY(cudaFuncSetAttribute(k_sw<LANES, 128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         FRZ_CUDA_TRY(cudaFuncSetAttribute(k_sw<LANES, 128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

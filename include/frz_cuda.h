@@ -221,8 +221,8 @@ FRZ_API frz_status frz_match_list_host_arrow(frz_matcher* m, const uint8_t* byte
 /* Matcher::match_list_indices (src/matcher/mod.rs:234-262) for CHOSEN haystacks — the rows a UI is about to display:
  * for haystack which[j] (corpus-relative index) writes its Match to out_matches[j] and the byte offsets of the
  * matched characters, in the reference's descending order, to out_indices[j * stride ...]; out_counts[j] = how many
- * (capped at stride), or UINT32_MAX when that haystack does not match.  Host pointers; matchers with exactly one
- * non-negated pattern (fuzzy, ASCII or unicode needle, or literal).  Like the reference's, not a tuned path. */
+ * (capped at stride), or UINT32_MAX when that haystack does not match.  Host pointers.  Multi-pattern matchers pool
+ * the atoms' indices like match_one_indices_multi (src/matcher/multi.rs:56-79).  Like the reference's, not a tuned path. */
 FRZ_API frz_status frz_match_indices(frz_matcher* m, const frz_corpus* corpus, const uint32_t* which, uint64_t n,
                              frz_match* out_matches, uint32_t* out_indices, uint32_t stride, uint32_t* out_counts);
 

@@ -1487,25 +1487,45 @@ uint16_t frzo_sw_indices(const uint8_t* needle, size_t n, const frz_scoring* sc,
     return score;
 }
 
-// Matcher::match_list_indices restricted to the haystacks `which[0..n_which)` of a single-pattern matcher
-// (src/matcher/mod.rs:234-262 → match_one_indices_impl).  out_cnt[j] = number of indices, or 0xFFFFFFFF when haystack
+// Matcher::match_list_indices restricted to the haystacks `which[0..n_which)`
+// (src/matcher/mod.rs:234-262 → match_one_indices_impl / match_one_indices_multi).  out_cnt[j] = number of indices, or 0xFFFFFFFF when haystack
 // which[j] does not match; out_idx[j * stride ...] in the reference's (reverse) order.  Returns 0, or -1 on a bad pattern.
-int frzo_match_indices(const frz_pattern* pattern, const frz_config* cfg, const uint8_t* bytes, const uint64_t* offsets,
+int frzo_match_indices(const frz_pattern* patterns, size_t np, const frz_config* cfg, const uint8_t* bytes, const uint64_t* offsets,
                        const uint32_t* which, uint64_t n_which, uint32_t* out_idx, uint32_t stride, uint32_t* out_cnt,
                        frz_match* out_match) {
-    OPattern o;
-    if (!compile(*pattern, *cfg, &o)) return -1;
-    std::vector<uint32_t> idx;
+    std::vector<OPattern> pats;
+    for (size_t i = 0; i < np; i++) {
+        OPattern o;
+        if (compile(patterns[i], *cfg, &o)) pats.push_back(o);
+    }
+    if (pats.empty()) return -1;
+    std::vector<uint32_t> idx, all;
     for (uint64_t j = 0; j < n_which; j++) {
         const uint64_t i = which[j];
-        frz_match m{};
-        if (!match_one_indices(o, bytes + offsets[i], (size_t)(offsets[i + 1] - offsets[i]), (uint32_t)i, &m, &idx)) {
-            out_cnt[j] = 0xFFFFFFFFu;
-            continue;
+        const uint8_t* hay = bytes + offsets[i];
+        const size_t hl = (size_t)(offsets[i + 1] - offsets[i]);
+        // Single: match_one_indices_impl; Multi: match_one_indices_multi (src/matcher/multi.rs:56-79)
+        frz_match comb{(uint32_t)i, 0, 0, 0};
+        all.clear();
+        bool alive = true;
+        for (const OPattern& o : pats) {
+            frz_match m{};
+            const bool hit = match_one_indices(o, hay, hl, (uint32_t)i, &m, &idx);
+            if (o.negated) { if (hit) { alive = false; break; } continue; }
+            if (!hit) { alive = false; break; }
+            uint32_t sum = (uint32_t)comb.score + m.score;
+            comb.score = (uint16_t)(sum > 0xFFFF ? 0xFFFF : sum);
+            comb.exact |= m.exact;
+            all.insert(all.end(), idx.begin(), idx.end());
         }
-        out_match[j] = m;
-        out_cnt[j] = (uint32_t)idx.size();
-        for (size_t k = 0; k < idx.size() && k < stride; k++) out_idx[j * (uint64_t)stride + k] = idx[k];
+        if (!alive) { out_cnt[j] = 0xFFFFFFFFu; continue; }
+        if (pats.size() > 1) {   // sort_unstable_by(b.cmp(a)) + dedup
+            std::sort(all.begin(), all.end(), [](uint32_t a, uint32_t b) { return a > b; });
+            all.erase(std::unique(all.begin(), all.end()), all.end());
+        }
+        out_match[j] = comb;
+        out_cnt[j] = (uint32_t)all.size();
+        for (size_t k = 0; k < all.size() && k < stride; k++) out_idx[j * (uint64_t)stride + k] = all[k];
     }
     return 0;
 }

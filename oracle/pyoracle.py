@@ -50,7 +50,7 @@ def lib():
         L.frzo_sw_indices.argtypes = [u8p, C.c_size_t, C.POINTER(CScoring), C.c_int, C.c_int, u8p, C.c_size_t, C.c_uint64,
                                       C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32)]
         L.frzo_match_indices.restype = C.c_int
-        L.frzo_match_indices.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64,
+        L.frzo_match_indices.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64,
                                          C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
         L.frzo_flip_scalar.restype = C.c_int
         L.frzo_flip_scalar.argtypes = [u8p, C.c_size_t, C.POINTER(C.c_uint8)]
@@ -130,7 +130,8 @@ def sw_indices(needle, haystack, start_pos: int = 0, max_typos: Optional[int] = 
 def match_indices(pattern, config: Config, data: np.ndarray, offsets: np.ndarray, which, stride: int = 128):
     """Matcher::match_list_indices of a single-pattern matcher on the chosen haystacks.
     Returns a list of None (no match) or (score, exact, indices)."""
-    arr = pattern_array([as_pattern(pattern)])
+    plist = [as_pattern(p) for p in (pattern if isinstance(pattern, (list, tuple)) else [pattern])]
+    arr = pattern_array(plist)
     cfg = CConfig.of(config)
     which = np.ascontiguousarray(which, dtype=np.uint32)
     out_idx = np.zeros((len(which), stride), dtype=np.uint32)
@@ -138,7 +139,7 @@ def match_indices(pattern, config: Config, data: np.ndarray, offsets: np.ndarray
     out_m = np.zeros(len(which), dtype=MATCH_DTYPE)
     data = np.ascontiguousarray(data, dtype=np.uint8)
     offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
-    rc = lib().frzo_match_indices(C.cast(arr, C.c_void_p), C.byref(cfg), data.ctypes.data if data.size else None, offsets.ctypes.data, which.ctypes.data, len(which),
+    rc = lib().frzo_match_indices(C.cast(arr, C.c_void_p), len(plist), C.byref(cfg), data.ctypes.data if data.size else None, offsets.ctypes.data, which.ctypes.data, len(which),
                                   out_idx.ctypes.data, stride, out_cnt.ctypes.data, out_m.ctypes.data)
     if rc != 0:
         raise ValueError("empty pattern")

@@ -448,7 +448,11 @@ def test_match_indices_traceback():
              ("abc", Config(max_typos=1)), ("é다😀", Config(max_typos=1)), ("éa", Config(max_typos=0)),
              ("foo", Config(max_typos=1, unicode=UnicodeMatching.Always)),
              (Pattern("ab", matching=Matching.Substring), Config()), (Pattern("é", matching=Matching.Prefix), Config()),
-             ("ab", Config(max_typos=1, emulate_lanes=16)), ("abAB_/-ab01abAB", Config(max_typos=3, emulate_lanes=32))]
+             ("ab", Config(max_typos=1, emulate_lanes=16)), ("abAB_/-ab01abAB", Config(max_typos=3, emulate_lanes=32)),
+             # multi-pattern queries: pooled, de-duplicated indices (match_one_indices_multi, src/matcher/multi.rs:56-79)
+             ([Pattern("ab"), Pattern("ab")], Config(max_typos=0)),
+             ([Pattern("ab"), Pattern("b0", negated=True, matching=Matching.Substring)], Config(max_typos=1)),
+             ([Pattern("é"), Pattern("a"), Pattern("다", negated=True)], Config(max_typos=0))]
     for needle, cfg in cases:
         m = F.Matcher(needle, cfg)
         lanes = m.backend_info()["prefilter_lanes"]
@@ -457,5 +461,6 @@ def test_match_indices_traceback():
         assert got == want, (needle, cfg, [(i, g, w) for i, (g, w) in enumerate(zip(got, want)) if g != w][:3])
         ml = {int(x["index"]): x for x in m.match_list_array(corpus)}
         assert {i for i, g in enumerate(got) if g is not None} == set(ml)
+        assert all(got[i][0] == int(ml[i]["score"]) and got[i][1] == bool(ml[i]["exact"]) for i in ml)
         m.close()
     corpus.close()
