@@ -28,12 +28,7 @@ namespace {
 
 constexpr int kThreads = 128;
 constexpr int kWarps = kThreads / 32;
-constexpr int kSliceUnitsMax = 8;                      // groups of up to 8 units (128 bytes) are probed from registers
 
-struct SliceAcc {
-    const uint32_t* s;
-    __device__ __forceinline__ uint32_t word(uint32_t w) const { return s[w]; }
-};
 struct GlobalAcc {
     const uint4* base;  // unit 0 of this slot; unit k at base + 32*k
     __device__ __forceinline__ uint32_t word(uint32_t w) const {
