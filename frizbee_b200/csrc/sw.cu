@@ -328,7 +328,7 @@ __device__ __forceinline__ void emit_match(const FrzSurvivor& rec, uint32_t scor
 }
 
 // One survivor whose window units are in registers: score it, write the Match at its index-ordered position.
-template <int LANES, int COLS, bool WRAP8, int CC>
+template <int LANES, int COLS, bool WRAP8, int CC, int VAR = 0>
 __device__ __forceinline__ uint32_t score_window(const FrzPatternDev& pat, const FrzSurvivor& rec, const WindowRec& wr,
                                                  const uint4 (&u)[(CC + 15) / 16 + 1], const FrzRankView& rv,
                                                  const FrzCounters* __restrict__ ctr, uint32_t index_offset, int reversed,
@@ -336,7 +336,7 @@ __device__ __forceinline__ uint32_t score_window(const FrzPatternDev& pat, const
     const uint64_t pos = match_position(rec, reversed != 0, rv, ctr);   // loads overlap the DP
     uint32_t hw[CC / 4];
     window_from_units<CC>(u, wr.startlo, wr.W, hw);
-    uint32_t score = SwCore<LANES, COLS, WRAP8, 0, CC>::run(hw, wr.W, pat, wr.start0, sw_smem);
+    uint32_t score = SwCore<LANES, COLS, WRAP8, VAR, CC>::run(hw, wr.W, pat, wr.start0, sw_smem);
     bool exact = wr.start0 && wr.full_end && window_equals_needle(hw, wr.W, pat);
     if (exact) score = (score + pat.exact_bonus) & 0xffffu;
     store_match(rec, pos, score, exact, index_offset, out);
@@ -392,7 +392,7 @@ struct Sw64Stage {
     uint4 units[kSw64Units][kSwThreads];  // [k][thread]: conflict-free 16-byte columns
 };
 
-template <int LANES, bool WRAP8>
+template <int LANES, bool WRAP8, int VAR = 0>
 __global__ void __launch_bounds__(kSwThreads, kSw64MinBlocks) k_sw64(const FrzCorpusView cv, const __grid_constant__ FrzPatternDev pat,
                                                      const FrzSurvLists lists, unsigned long long surv_cap,
                                                      const FrzRankView rv, FrzCounters* __restrict__ ctr,
@@ -484,15 +484,15 @@ __global__ void __launch_bounds__(kSwThreads, kSw64MinBlocks) k_sw64(const FrzCo
             const int k = class_of(item0);
             uint32_t sc;
             if (k == 0) {
-                sc = score_window<LANES, 64, WRAP8, 64>(pat, rec0, wr, u, rv, ctr, index_offset, reversed, out, rows_smem);
+                sc = score_window<LANES, 64, WRAP8, 64, VAR>(pat, rec0, wr, u, rv, ctr, index_offset, reversed, out, rows_smem);
             } else if (k == 1) {
-                sc = score_window<LANES, 64, WRAP8, 56>(pat, rec0, wr, u, rv, ctr, index_offset, reversed, out, rows_smem);
+                sc = score_window<LANES, 64, WRAP8, 56, VAR>(pat, rec0, wr, u, rv, ctr, index_offset, reversed, out, rows_smem);
             } else if (k == 2) {
                 const uint4 (&u4)[4] = reinterpret_cast<const uint4 (&)[4]>(u);
-                sc = score_window<LANES, 64, WRAP8, 48>(pat, rec0, wr, u4, rv, ctr, index_offset, reversed, out, rows_smem);
+                sc = score_window<LANES, 64, WRAP8, 48, VAR>(pat, rec0, wr, u4, rv, ctr, index_offset, reversed, out, rows_smem);
             } else {
                 const uint4 (&u4)[4] = reinterpret_cast<const uint4 (&)[4]>(u);
-                sc = score_window<LANES, 64, WRAP8, 40>(pat, rec0, wr, u4, rv, ctr, index_offset, reversed, out, rows_smem);
+                sc = score_window<LANES, 64, WRAP8, 40, VAR>(pat, rec0, wr, u4, rv, ctr, index_offset, reversed, out, rows_smem);
             }
             local_max = max(local_max, sc);
         }
@@ -683,7 +683,20 @@ frz_status launch_sw_lanes(const FrzCorpusView& cv, const FrzPatternDev& pat, ui
     const int blocks = sm_count() * 2;
     const int blocks64 = sm_count() * kSw64MinBlocks;
     const int rev = reversed ? 1 : 0;
-    if (pat.wrap8)
+    if (LANES == 64 && !pat.wrap8) {
+        // pipe-balance experiment knob: FRZ_SW_VARIANT = SwCore's VAR bits, default 0
+        static int var = -1;
+        if (var < 0) { const char* e = getenv("FRZ_SW_VARIANT"); var = e ? atoi(e) : 0; }
+#define FRZ_SW_VAR_CASE(V)                                                                                                    \
+        if (var == V) {                                                                                                       \
+            k_sw64<64, false, V><<<blocks64, kSwThreads, 0, stream>>>(cv, pat, ws.lists(), ws.survivor_cap, rank_view(ws),     \
+                                                                      ws.counters, index_offset, rev, d_out);                 \
+        } else
+        FRZ_SW_VAR_CASE(1) FRZ_SW_VAR_CASE(3) FRZ_SW_VAR_CASE(5) FRZ_SW_VAR_CASE(7)
+#undef FRZ_SW_VAR_CASE
+            k_sw64<64, false, 0><<<blocks64, kSwThreads, 0, stream>>>(cv, pat, ws.lists(), ws.survivor_cap, rank_view(ws), ws.counters,
+                                                                      index_offset, rev, d_out);
+    } else if (pat.wrap8)
         k_sw64<LANES, true><<<blocks64, kSwThreads, 0, stream>>>(cv, pat, ws.lists(), ws.survivor_cap, rank_view(ws), ws.counters, index_offset, rev, d_out);
     else
         k_sw64<LANES, false><<<blocks64, kSwThreads, 0, stream>>>(cv, pat, ws.lists(), ws.survivor_cap, rank_view(ws), ws.counters, index_offset, rev, d_out);
