@@ -138,6 +138,7 @@ struct FrzCounters {
 
 #define FRZ_DEVERR_SURVIVOR_OVERFLOW 1u
 
+#if defined(__CUDACC__)   // device-only helpers (the structs above are shared with host-side test builds)
 __device__ __forceinline__ uint32_t frz_lane() { return threadIdx.x & 31; }
 
 // Byte accessor of one packed haystack for the per-thread correctness paths (unicode.cu, k_match_indices):
@@ -156,3 +157,4 @@ __device__ __forceinline__ const uint4* frz_unit_ptr(const FrzCorpusView& cv, ui
     const FrzGroupDesc gd = cv.groups[tile * FRZ_GROUPS_PER_TILE + (slot >> 5)];
     return cv.data + gd.abs_off + (uint64_t)k * FRZ_GROUP + (slot & 31);
 }
+#endif  // __CUDACC__

@@ -1335,6 +1335,15 @@ __global__ void k_merge_scatter(const FrzMatchDev* __restrict__ runs, uint64_t s
 // k_merge_matches_by (src/k_merge.rs:90-131).  Runs are index-range shards in rank order, each already
 // ordered per `sort`; concatenating them in (reverse) rank order and stable-sorting by score yields
 // exactly the reference's k-way merge (ties resolve by index because the shards are index-ordered).
+// Debugging / test aid: the compiled device pattern of pattern i (the struct the kernels receive), so that host
+// builds of the kernel cores (tests/test_kernel_logic_cpu.py) run with exactly the constants the GPU gets.
+extern "C" frz_status frz_matcher_debug_pattern(const frz_matcher* m, size_t i, void* out, size_t out_size) {
+    if (!m || !out || i >= m->compiled.size()) return frz_fail(FRZ_ERR_INVALID_ARG, "pattern index out of range");
+    if (out_size != sizeof(FrzPatternDev)) return frz_fail(FRZ_ERR_INVALID_ARG, "expected a buffer of %zu bytes", sizeof(FrzPatternDev));
+    memcpy(out, &m->compiled[i].dev, sizeof(FrzPatternDev));
+    return FRZ_OK;
+}
+
 extern "C" uint32_t frz_matcher_score_bound(const frz_matcher* m) {
     if (!m) return 0;
     uint64_t b = 0;

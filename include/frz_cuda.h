@@ -248,6 +248,10 @@ FRZ_API frz_status frz_merge_runs_device(const frz_match* d_runs, uint64_t run_s
  * 65535); lets the device sort / merge use a single counting pass.  0 for an empty matcher. */
 FRZ_API uint32_t frz_matcher_score_bound(const frz_matcher* m);
 
+/* Test aid: copies the compiled device pattern (frizbee_b200/csrc/frz_device.cuh: FrzPatternDev) of pattern i; out_size
+ * must equal its size.  Lets host builds of the kernel cores run with exactly the constants the GPU receives. */
+FRZ_API frz_status frz_matcher_debug_pattern(const frz_matcher* m, size_t i, void* out, size_t out_size);
+
 /* radix_sort_matches (src/sort.rs:6-40): stable, descending score; `matches` is host memory. */
 FRZ_API frz_status frz_radix_sort_matches(frz_match* matches, uint64_t n, int device);
 

@@ -1,0 +1,130 @@
+"""The register Smith-Waterman core of the GPU kernels (frizbee_b200/csrc/sw_core.cuh: SwCore, window assembly, exact
+check) is compiled here for the CPU — same source, scalar stand-ins for the CUDA SIMD-in-register intrinsics — and run
+against the oracle with the pattern constants of the real library (frz_matcher_debug_pattern).  Covers what a GPU is
+otherwise needed for: every emulated lane width, the column-limited classes (CC 40/48/56/64), the 128-column variant,
+the u8 wrap emulation and the shift-placement variants."""
+import ctypes as C
+import os
+import random
+import subprocess
+
+import numpy as np
+import pytest
+
+import frizbee_b200 as F
+from frizbee_b200.types import CaseMatching, Config, Scoring
+from oracle import pyoracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SRC = os.path.join(ROOT, "tests", "harness", "sw_harness.cpp")
+LIB = os.path.join(ROOT, "tests", "harness", "libsw_harness.so")
+DEPS = [SRC] + [os.path.join(ROOT, "frizbee_b200", "csrc", f) for f in ("sw_core.cuh", "frz_device.cuh")]
+CUDA_INC = "/usr/local/cuda/include"
+
+
+@pytest.fixture(scope="module")
+def H():
+    if not os.path.isdir(CUDA_INC):
+        pytest.skip("CUDA headers not found")
+    if not os.path.exists(LIB) or any(os.path.getmtime(d) > os.path.getmtime(LIB) for d in DEPS):
+        subprocess.run(["g++", "-O1", "-std=c++17", "-I" + CUDA_INC, "-fPIC", "-shared", "-o", LIB, SRC], check=True)
+    L = C.CDLL(LIB)
+    L.h_pattern_size.restype = C.c_size_t
+    L.h_swcore.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                           C.POINTER(C.c_int)]
+    return L
+
+
+def device_pattern(H, needle, cfg):
+    m = F.Matcher(needle, cfg)
+    buf = (C.c_uint8 * H.h_pattern_size())()
+    F._check(F.lib().frz_matcher_debug_pattern(m._h, 0, buf, len(buf)))
+    info = m.backend_info()
+    m.close()
+    return buf, info
+
+
+def rand_bytes(rng, pool, n):
+    return bytes(rng.choice(pool) for _ in range(n))
+
+
+POOLS = [b"abAB_/-ab01", b"ab", b"abcdefghijklmnopqrstuvwxyzABCDEFGHIJKLMNOPQRSTUVWXYZ0123456789_-/.", b"aAbB_zZ9"]
+HAY_EXTRA = b"\xc3\xa9\x00"   # haystacks may hold any bytes (multi-byte scalars, NUL)
+
+
+@pytest.mark.parametrize("lanes", [16, 32, 64])
+def test_swcore_column_classes_equal_oracle(H, lanes):
+    """SwCore<LANES, 64, no-wrap, VAR, CC>: the class the prefilter would choose and every wider one give the oracle's score."""
+    rng = random.Random(5000 + lanes)
+    F.lib().frz_matcher_debug_pattern.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]
+    checked = 0
+    for trial in range(700):
+        pool = rng.choice(POOLS)
+        n = rng.randint(1, 11)
+        needle = rand_bytes(rng, pool, n)
+        if 0 in needle:
+            continue
+        cs = rng.random() < 0.3
+        cfg = Config(max_typos=None, emulate_lanes=lanes, casing=CaseMatching.Respect if cs else CaseMatching.Ignore)
+        pat, info = device_pattern(H, needle, cfg)
+        assert info["score_bits"] == 8 and info["lanes"] == lanes
+        for _ in range(6):
+            W = rng.randint(1, 64)
+            win = rand_bytes(rng, pool + (HAY_EXTRA if rng.random() < 0.3 else b""), W)
+            pre = rng.random() < 0.5
+            want = O.sw_score(needle, win, Scoring(), cs, pre, lanes, 8)
+            chunk_cols = (W + lanes - 1) // lanes * lanes
+            need = min(W + n, chunk_cols)
+            for cc in (40, 48, 56, 64):
+                if cc < need or cc < W:
+                    continue
+                eq = C.c_int()
+                var = rng.choice([0, 1, 3, 5, 7]) if lanes == 64 else 0
+                got = H.h_swcore(pat, win, W, rng.randint(0, 15), int(pre), lanes, 64, cc, 0, var, C.byref(eq))
+                assert got == want, (needle, win, cs, pre, lanes, cc, var, got, want)
+                assert bool(eq.value) == (win == needle)
+                checked += 1
+    assert checked > 3000
+
+
+@pytest.mark.parametrize("lanes,bits", [(8, 16), (16, 16), (32, 16), (16, 8), (64, 8)])
+def test_swcore_128_columns_and_u16_family(H, lanes, bits):
+    rng = random.Random(6000 + lanes + bits)
+    F.lib().frz_matcher_debug_pattern.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]
+    emulate = {(8, 16): 16, (16, 16): 32, (32, 16): 64, (16, 8): 16, (64, 8): 64}[(lanes, bits)]
+    for trial in range(150):
+        pool = rng.choice(POOLS)
+        n = rng.randint(14, 24) if bits == 16 else rng.randint(1, 10)
+        needle = rand_bytes(rng, pool, n)
+        cfg = Config(max_typos=None, emulate_lanes=emulate, casing=CaseMatching.Ignore)
+        pat, info = device_pattern(H, needle, cfg)
+        assert (info["lanes"], info["score_bits"]) == (lanes, bits)
+        for _ in range(3):
+            W = rng.randint(1, 128)
+            win = rand_bytes(rng, pool + (HAY_EXTRA if rng.random() < 0.3 else b""), W)
+            pre = rng.random() < 0.5
+            want = O.sw_score(needle, win, Scoring(), False, pre, lanes, bits)
+            eq = C.c_int()
+            got = H.h_swcore(pat, win, W, rng.randint(0, 15), int(pre), lanes, 128, 128, 0, 0, C.byref(eq))
+            assert got == want, (needle, win, pre, lanes, bits, got, want)
+            if W <= 64:
+                got64 = H.h_swcore(pat, win, W, rng.randint(0, 15), int(pre), lanes, 64, 64, 0, 0, C.byref(eq))
+                assert got64 == want
+
+
+def test_swcore_u8_wrap_emulation(H):
+    """12-13-byte needles at the default scoring can wrap the reference's u8 lanes (DESIGN.md §2 finding 3): the host
+    selects WRAP8 and the kernel core must reproduce the wrapped arithmetic."""
+    F.lib().frz_matcher_debug_pattern.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]
+    rng = random.Random(7)
+    needle = b"aB-cD-eF-gH-i"
+    pat, info = device_pattern(H, needle, Config(max_typos=None, emulate_lanes=64))
+    assert info["score_bits"] == 8
+    hays = [needle, b"x" + needle, needle + b"yy", b"aB-cD-eF-gH-i_aB-cD-eF-gH-i"]
+    hays += [rand_bytes(rng, b"aBcDeFgHi-_", rng.randint(5, 64)) for _ in range(400)]
+    for win in hays:
+        for pre in (True, False):
+            want = O.sw_score(needle, win, Scoring(), True, pre, 64, 8)   # smart case: the needle has uppercase
+            eq = C.c_int()
+            got = H.h_swcore(pat, win, len(win), 3, int(pre), 64, 64, 64, 1, 0, C.byref(eq))
+            assert got == want, (win, pre, got, want)
