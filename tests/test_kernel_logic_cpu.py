@@ -128,3 +128,50 @@ def test_swcore_u8_wrap_emulation(H):
             eq = C.c_int()
             got = H.h_swcore(pat, win, len(win), 3, int(pre), 64, 64, 64, 1, 0, C.byref(eq))
             assert got == want, (win, pre, got, want)
+
+
+# ---------------------------------------------------------------- occurrence-mask prefilter windows (prefilter_masks.cuh)
+PF_SRC = os.path.join(ROOT, "tests", "harness", "pf_harness.cpp")
+PF_LIB = os.path.join(ROOT, "tests", "harness", "libpf_harness.so")
+PF_DEPS = [PF_SRC] + [os.path.join(ROOT, "frizbee_b200", "csrc", f) for f in ("prefilter_masks.cuh", "frz_device.cuh")]
+
+
+@pytest.fixture(scope="module")
+def PF():
+    if not os.path.isdir(CUDA_INC):
+        pytest.skip("CUDA headers not found")
+    if not os.path.exists(PF_LIB) or any(os.path.getmtime(d) > os.path.getmtime(PF_LIB) for d in PF_DEPS):
+        subprocess.run(["g++", "-O1", "-std=c++17", "-I" + CUDA_INC, "-fPIC", "-shared", "-o", PF_LIB, PF_SRC], check=True)
+    L = C.CDLL(PF_LIB)
+    L.h_masks_window.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    return L
+
+
+@pytest.mark.parametrize("lanes", [16, 32, 64])
+@pytest.mark.parametrize("k", [0, 1])
+def test_mask_prefilter_windows_equal_oracle(H, PF, lanes, k):
+    """masks_k0 / masks_k1 (DP4A-packed occurrence masks + the reference's mask state machine at chunk width LANES) vs
+    Prefilter::match_haystack / match_haystack_1_typo, on haystacks of up to 200 bytes (several 64-byte blocks)."""
+    rng = random.Random(8000 + lanes + k)
+    F.lib().frz_matcher_debug_pattern.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]
+    checked = matched = 0
+    for trial in range(500):
+        pool = rng.choice(POOLS)
+        needle = rand_bytes(rng, pool, rng.randint(1, 12))
+        cs = rng.random() < 0.3
+        cfg = Config(max_typos=k, emulate_lanes=lanes, casing=CaseMatching.Respect if cs else CaseMatching.Ignore)
+        pat, info = device_pattern(H, needle, cfg)
+        assert info["prefilter_lanes"] == lanes
+        for _ in range(12):
+            ln = rng.choice([0, 1, 2, 7, 15, 16, 17, 31, 33, 50, 63, 64, 65, 100, 128, 129, 200])
+            hay = rand_bytes(rng, pool + (HAY_EXTRA if rng.random() < 0.2 else b"x"), ln)
+            s, e = C.c_int(), C.c_int()
+            got = PF.h_masks_window(pat, hay, len(hay), k, C.byref(s), C.byref(e))
+            assert got >= 0
+            want = O.prefilter(needle, hay, k, lanes, cs)
+            assert bool(got) == want[0], (needle, hay, k, lanes, cs, want)
+            if want[0]:
+                assert (s.value, e.value) == (want[1], want[2]), (needle, hay, k, lanes, cs, want, s.value, e.value)
+                matched += 1
+            checked += 1
+    assert checked > 5000 and matched > 500
