@@ -240,7 +240,8 @@ FRZ_API frz_status frz_matcher_wait_count(frz_matcher* m, void* stream);
 /* k_merge_matches_by (src/k_merge.rs:90-131) on device: `d_runs` holds `n_runs` runs, run r at
  * d_runs + r*run_stride with run_counts_host[r] valid entries, each already ordered per `sort`.
  * `score_bound`: upper bound of the scores in the runs (frz_matcher_score_bound), 0 = unknown.
- * Writes the merged sequence to d_out (may not alias d_runs).  Asynchronous on `stream`. */
+ * Writes the merged sequence to d_out (may not alias d_runs).  Asynchronous on `stream`.  Uses one grow-only scratch
+ * per device for the life of the process: calls for the same device must not overlap (one stream, or serialise). */
 FRZ_API frz_status frz_merge_runs_device(const frz_match* d_runs, uint64_t run_stride,
                                  const uint64_t* run_counts_host, int n_runs, uint8_t sort,
                                  uint32_t score_bound, frz_match* d_out, int device, void* stream);
