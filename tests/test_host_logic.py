@@ -101,3 +101,31 @@ def test_no_cpu_fallback_without_device():
     with pytest.raises(F.FrizbeeError) as e:
         F.Matcher("foo", Config()).match_list(["foo", "bar"])
     assert e.value.status_name in ("FRZ_ERR_NO_DEVICE", "FRZ_ERR_CUDA")
+
+
+def _build_ffi_demo(tmp_path):
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    F.lib()   # make sure libfrz_cuda.so exists
+    exe = str(tmp_path / "ffi_demo")
+    libdir = os.path.join(root, "frizbee_b200")
+    subprocess.run(["gcc", "-std=c11", "-Wall", "-Wextra", "-Werror", "-I" + os.path.join(root, "include"),
+                    os.path.join(root, "examples", "ffi_demo.c"), "-L" + libdir, "-lfrz_cuda", "-Wl,-rpath," + libdir, "-o", exe],
+                   check=True)
+    return exe
+
+
+def test_c_abi_from_plain_c(tmp_path):
+    """examples/ffi_demo.c uses only include/frz_cuda.h (C11, no CUDA headers, no torch types): it must compile and
+    link warning-free; without a GPU it reports the missing device instead of falling back."""
+    import subprocess
+    import torch
+    exe = _build_ffi_demo(tmp_path)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    if torch.cuda.is_available():
+        assert r.returncode == 0 and "Match { score: 53, index: 0, exact: false }" in r.stdout, (r.stdout, r.stderr)
+    else:
+        assert r.returncode == 3 and "no CPU fallback" in r.stderr, (r.stdout, r.stderr)
