@@ -203,5 +203,167 @@ FRZ_PF_FN bool masks_k1(const uint4* base, const FrzPatternDev& pat, const uint8
     return state == 1;
 }
 
+// ---- groundwork for the tuned 2-typo / N-typo paths.  Both are checked against the oracle on
+// the CPU (tests/test_kernel_logic_cpu.py) but NOT yet called by the kernels (FRZ_T_2 / FRZ_T_MANY still use the
+// scanning forms window_k2 / window_many of prefilter.cu): wiring them in needs a GPU run for registers and timing.
+
+// match_haystack_2_typos (src/prefilter/algo/ascii_typos.rs:113-251) on block masks: NP = 3 paths with their own
+// chunk masks; NP = 2 is match_haystack_1_typo again (== masks_k1, kept as a cross-check).
+template <int NP>
+FRZ_PF_FN bool masks_paths(const uint4* base, const FrzPatternDev& pat, const uint8_t* __restrict__ cid_s,
+                           uint2 (*occ)[32], int len, bool active, int* ostart, int* oend) {
+    const int units = active ? (len + 15) >> 4 : 0;
+    const uint32_t lane = FRZ_PF_LANE;
+    const int n = pat.n, L = pat.pf_lanes, K = NP - 1;
+    int idx[NP];
+#pragma unroll
+    for (int k = 0; k < NP; k++) idx[k] = k;
+    int ms = 0x7fffffff, end = -1;
+    int state = 2;   // 0 running, 1 found, 2 rejected / idle
+    if (active) state = n <= K ? 1 : (len == 0 ? 2 : 0);
+    if (active && n <= K) ms = 0;
+    const int max_len = __reduce_max_sync(0xffffffffu, active ? len : 0);
+    const uint64_t lmask = lowmask64(L);
+    for (int blk = 0; blk * 64 < max_len; blk++) {
+        build_block_masks(base, units, blk, pat, occ, lane);
+        __syncwarp();
+        const int rem = len - blk * 64;
+        const uint64_t valid = rem > 0 ? lowmask64(rem) : 0ull;
+        // find_end_pos_with_typos: 1 + last occurrence of any of the last K + 1 needle bytes, else len
+        if (n > K) {
+            uint64_t lastm = 0;
+            for (int i = n - 1 - K; i < n; i++) lastm |= u2_to_u64(occ[pat.cid[i]][lane]);
+            lastm &= valid;
+            if (lastm) end = blk * 64 + 64 - __clzll((long long)lastm);
+        }
+        int cs = blk * 64;
+        bool in_blk = state == 0 && rem > 0;
+        bool init = true;
+        uint64_t m[NP], c[NP];
+#pragma unroll
+        for (int k = 0; k < NP; k++) { m[k] = 0; c[k] = 0; }
+        while (__any_sync(0xffffffffu, in_blk)) {
+            if (in_blk) {
+                const int sh = cs - blk * 64;
+                if (init) {
+                    const uint64_t cm = (valid >> sh) & lmask;
+#pragma unroll
+                    for (int k = 0; k < NP; k++) { m[k] = (u2_to_u64(occ[cid_s[idx[k]]][lane]) >> sh) & lmask; c[k] = cm; }
+                    init = false;
+                }
+                bool adv = false;
+#pragma unroll
+                for (int k = 1; k < NP; k++) {
+                    if (!in_blk) break;
+                    const int cand = idx[k - 1] + 1;
+                    if (cand > idx[k]) {
+                        if (cand == n) { state = 1; in_blk = false; }
+                        else { idx[k] = cand; c[k] = c[k - 1]; m[k] = (u2_to_u64(occ[cid_s[cand]][lane]) >> sh) & lmask; }
+                    } else if (cand == idx[k] && c[k - 1] > c[k]) c[k] = c[k - 1];
+                }
+#pragma unroll
+                for (int k = 0; k < NP; k++) {
+                    if (!in_blk) break;
+                    const uint64_t x = m[k] & c[k];
+                    if (!x) continue;
+                    ms = min(ms, cs + __ffsll((long long)x) - 1);
+                    idx[k]++;
+                    if (k > 0 && idx[k] >= n) { state = 1; in_blk = false; break; }
+                    c[k] &= ~(x ^ (x - 1));
+                    m[k] = (u2_to_u64(occ[cid_s[idx[k]]][lane]) >> sh) & lmask;
+                    adv = true;
+                }
+                if (in_blk && !adv) {   // next chunk
+                    cs += L;
+                    init = true;
+                    if (cs >= len) { state = 2; in_blk = false; }
+                    else if (cs >= blk * 64 + 64) in_blk = false;
+                }
+            }
+        }
+        __syncwarp();
+    }
+    *ostart = ms == 0x7fffffff ? 0 : ms;
+    *oend = end < 0 ? len : end;
+    return state == 1;
+}
+
+// match_haystack_many_typos_impl (ascii_typos.rs:254-360) on block masks: k + 1 paths sharing one chunk mask, every
+// path that matches the first available hit advances.
+FRZ_PF_FN bool masks_many(const uint4* base, const FrzPatternDev& pat, const uint8_t* __restrict__ cid_s,
+                          uint2 (*occ)[32], int len, bool active, int* ostart, int* oend) {
+    const int units = active ? (len + 15) >> 4 : 0;
+    const uint32_t lane = FRZ_PF_LANE;
+    const int n = pat.n, L = pat.pf_lanes, K = pat.max_typos;   // K <= 15 (host guard)
+    const int paths = K + 1;
+    int idx[16];
+    uint64_t nm[16];
+    for (int k = 0; k < 16; k++) { idx[k] = 0; nm[k] = 0; }
+    int ms = 0x7fffffff, end = -1;
+    int state = 2;
+    if (active) state = n <= K ? 1 : (len == 0 ? 2 : 0);
+    if (active && n <= K) ms = 0;
+    const int max_len = __reduce_max_sync(0xffffffffu, active ? len : 0);
+    const uint64_t lmask = lowmask64(L);
+    for (int blk = 0; blk * 64 < max_len; blk++) {
+        build_block_masks(base, units, blk, pat, occ, lane);
+        __syncwarp();
+        const int rem = len - blk * 64;
+        const uint64_t valid = rem > 0 ? lowmask64(rem) : 0ull;
+        if (n > K) {
+            uint64_t lastm = 0;
+            for (int i = n - 1 - K; i < n; i++) lastm |= u2_to_u64(occ[pat.cid[i]][lane]);
+            lastm &= valid;
+            if (lastm) end = blk * 64 + 64 - __clzll((long long)lastm);
+        }
+        int cs = blk * 64;
+        bool in_blk = state == 0 && rem > 0;
+        bool init = true;
+        uint64_t chunk_mask = 0;
+        while (__any_sync(0xffffffffu, in_blk)) {
+            if (in_blk) {
+                const int sh = cs - blk * 64;
+                if (init) {
+                    chunk_mask = (valid >> sh) & lmask;
+                    for (int k = 0; k < paths; k++) nm[k] = (u2_to_u64(occ[cid_s[idx[k]]][lane]) >> sh) & lmask;
+                    init = false;
+                }
+                for (int k = 1; k < paths && in_blk; k++) {
+                    const int cand = idx[k - 1] + 1;
+                    if (cand > idx[k]) {
+                        if (cand == n) { state = 1; in_blk = false; }
+                        else { idx[k] = cand; nm[k] = (u2_to_u64(occ[cid_s[cand]][lane]) >> sh) & lmask; }
+                    }
+                }
+                if (in_blk) {
+                    uint64_t mm = 0;
+                    for (int k = 0; k < paths; k++) mm |= nm[k];
+                    const uint64_t matches = mm & chunk_mask;
+                    if (!matches) {   // next chunk
+                        cs += L;
+                        init = true;
+                        if (cs >= len) { state = 2; in_blk = false; }
+                        else if (cs >= blk * 64 + 64) in_blk = false;
+                    } else {
+                        const int hit_pos = __ffsll((long long)matches) - 1;
+                        const uint64_t hit = matches & lowmask64(hit_pos + 1);
+                        ms = min(ms, cs + hit_pos);
+                        for (int k = 0; k < paths && in_blk; k++) {
+                            if (!(nm[k] & hit)) continue;
+                            idx[k]++;
+                            if (idx[k] == n) { state = 1; in_blk = false; }
+                            else nm[k] = (u2_to_u64(occ[cid_s[idx[k]]][lane]) >> sh) & lmask;
+                        }
+                        chunk_mask &= ~(hit ^ (hit - 1));
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    }
+    *ostart = ms == 0x7fffffff ? 0 : ms;
+    *oend = end < 0 ? len : end;
+    return state == 1;
+}
 
 }  // namespace frzpf

@@ -11,7 +11,7 @@
 using namespace frzpf;
 
 extern "C" {
-// mode 0: masks_k0, 1: masks_k1.  Returns 1/0 = matched, -1 = the pattern has no distinct-class table.
+// mode 0: masks_k0, 1: masks_k1, 12: masks_paths<2>, 2: masks_paths<3>, 3: masks_many.  Returns 1/0 = matched, -1 = the pattern has no distinct-class table.
 int h_masks_window(const void* pat_bytes, const uint8_t* hay, int len, int mode, int* start, int* end) {
     FrzPatternDev pat;
     memcpy(&pat, pat_bytes, sizeof pat);
@@ -24,8 +24,14 @@ int h_masks_window(const void* pat_bytes, const uint8_t* hay, int len, int mode,
         memcpy(&data[(size_t)k * FRZ_GROUP], b, 16);
     }
     static uint2 occ[kMaxDistinct][32];
-    const bool ok = mode == 0 ? masks_k0(data.data(), pat, pat.cid, occ, len, true, start, end)
-                              : masks_k1(data.data(), pat, pat.cid, occ, len, true, start, end);
+    bool ok;
+    switch (mode) {
+        case 0: ok = masks_k0(data.data(), pat, pat.cid, occ, len, true, start, end); break;
+        case 1: ok = masks_k1(data.data(), pat, pat.cid, occ, len, true, start, end); break;
+        case 12: ok = masks_paths<2>(data.data(), pat, pat.cid, occ, len, true, start, end); break;
+        case 2: ok = masks_paths<3>(data.data(), pat, pat.cid, occ, len, true, start, end); break;
+        default: ok = masks_many(data.data(), pat, pat.cid, occ, len, true, start, end); break;
+    }
     return ok ? 1 : 0;
 }
 }

@@ -175,3 +175,32 @@ def test_mask_prefilter_windows_equal_oracle(H, PF, lanes, k):
                 matched += 1
             checked += 1
     assert checked > 5000 and matched > 500
+
+
+@pytest.mark.parametrize("lanes", [16, 32, 64])
+@pytest.mark.parametrize("k", [1, 2, 3, 5])
+def test_mask_prefilter_groundwork_2_and_n_typos(H, PF, lanes, k):
+    """masks_paths<NP> / masks_many (prefilter_masks.cuh, not yet wired into the kernels) vs match_haystack_1_typo /
+    _2_typos / _many_typos of the reference (src/prefilter/algo/ascii_typos.rs)."""
+    rng = random.Random(9000 + lanes + k)
+    F.lib().frz_matcher_debug_pattern.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]
+    mode = {1: 12, 2: 2}.get(k, 3)
+    checked = matched = 0
+    for trial in range(300):
+        pool = rng.choice(POOLS)
+        needle = rand_bytes(rng, pool, rng.randint(1, 12))
+        cs = rng.random() < 0.3
+        cfg = Config(max_typos=k, emulate_lanes=lanes, casing=CaseMatching.Respect if cs else CaseMatching.Ignore)
+        pat, info = device_pattern(H, needle, cfg)
+        for _ in range(12):
+            ln = rng.choice([0, 1, 2, 7, 15, 16, 17, 31, 33, 50, 63, 64, 65, 100, 128, 129, 200])
+            hay = rand_bytes(rng, pool + (HAY_EXTRA if rng.random() < 0.2 else b"x"), ln)
+            s, e = C.c_int(), C.c_int()
+            got = PF.h_masks_window(pat, hay, len(hay), mode, C.byref(s), C.byref(e))
+            want = O.prefilter(needle, hay, k, lanes, cs)
+            assert bool(got) == want[0], (needle, hay, k, lanes, cs, want)
+            if want[0]:
+                assert (s.value, e.value) == (want[1], want[2]), (needle, hay, k, lanes, cs, want, s.value, e.value)
+                matched += 1
+            checked += 1
+    assert checked > 3000 and matched > 300
