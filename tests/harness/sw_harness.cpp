@@ -32,7 +32,14 @@ uint32_t run_one(const FrzPatternDev& pat, const uint8_t* window, int W, int sta
 
 template <int LANES, bool WRAP8, int VAR>
 int dispatch_cc(const FrzPatternDev& pat, const uint8_t* w, int W, int startlo, bool pre, int cols, int cc, int* eq) {
-    if (cols == 128) return (int)run_one<LANES, 128, WRAP8, 0, 128>(pat, w, W, startlo, pre, eq);
+    if (cols == 128) {
+        switch (cc) {   // column-limited forms of the 128-column variant (groundwork)
+            case 80: return (int)run_one<LANES, 128, WRAP8, 0, 80>(pat, w, W, startlo, pre, eq);
+            case 96: return (int)run_one<LANES, 128, WRAP8, 0, 96>(pat, w, W, startlo, pre, eq);
+            case 112: return (int)run_one<LANES, 128, WRAP8, 0, 112>(pat, w, W, startlo, pre, eq);
+            default: return (int)run_one<LANES, 128, WRAP8, 0, 128>(pat, w, W, startlo, pre, eq);
+        }
+    }
     switch (cc) {
         case 40: return (int)run_one<LANES, 64, WRAP8, VAR, 40>(pat, w, W, startlo, pre, eq);
         case 48: return (int)run_one<LANES, 64, WRAP8, VAR, 48>(pat, w, W, startlo, pre, eq);

@@ -204,3 +204,31 @@ def test_mask_prefilter_groundwork_2_and_n_typos(H, PF, lanes, k):
                 matched += 1
             checked += 1
     assert checked > 3000 and matched > 300
+
+
+@pytest.mark.parametrize("lanes", [16, 32, 64])
+def test_swcore_128_column_classes_groundwork(H, lanes):
+    """SwCore<LANES, 128, ., ., CC> with CC in {80, 96, 112}: the column-limited form of the 65..128-byte window class
+    (not yet used by the kernels) gives the oracle's score whenever CC >= min(W + n, ceil(W / LANES) * LANES)."""
+    rng = random.Random(12000 + lanes)
+    F.lib().frz_matcher_debug_pattern.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]
+    checked = 0
+    for trial in range(120):
+        pool = rng.choice(POOLS)
+        n = rng.randint(1, 11)
+        needle = rand_bytes(rng, pool, n)
+        pat, info = device_pattern(H, needle, Config(max_typos=None, emulate_lanes=lanes, casing=CaseMatching.Ignore))
+        for _ in range(4):
+            W = rng.randint(40, 120)
+            win = rand_bytes(rng, pool + (HAY_EXTRA if rng.random() < 0.3 else b""), W)
+            pre = rng.random() < 0.5
+            want = O.sw_score(needle, win, Scoring(), False, pre, lanes, 8)
+            need = min(W + n, (W + lanes - 1) // lanes * lanes)
+            for cc in (80, 96, 112, 128):
+                if cc < need or cc < W:
+                    continue
+                eq = C.c_int()
+                got = H.h_swcore(pat, win, W, rng.randint(0, 15), int(pre), lanes, 128, cc, 0, 0, C.byref(eq))
+                assert got == want, (needle, win, pre, lanes, cc, got, want)
+                checked += 1
+    assert checked > 500
