@@ -57,6 +57,8 @@ int dispatch(const FrzPatternDev& pat, const uint8_t* w, int W, int startlo, boo
             case 3: return dispatch_cc<LANES, false, 3>(pat, w, W, startlo, pre, cols, cc, eq);
             case 5: return dispatch_cc<LANES, false, 5>(pat, w, W, startlo, pre, cols, cc, eq);
             case 7: return dispatch_cc<LANES, false, 7>(pat, w, W, startlo, pre, cols, cc, eq);
+            case 8: return dispatch_cc<LANES, false, 8>(pat, w, W, startlo, pre, cols, cc, eq);
+            case 11: return dispatch_cc<LANES, false, 11>(pat, w, W, startlo, pre, cols, cc, eq);
         }
     }
     return dispatch_cc<LANES, false, 0>(pat, w, W, startlo, pre, cols, cc, eq);
