@@ -351,7 +351,11 @@ __device__ __forceinline__ int sw_class_of(int window, const FrzPatternDev& pat)
     // more than the chunks the reference evaluates
     const int chunk_cols = (window + pat.sw_lanes - 1) / pat.sw_lanes * pat.sw_lanes;
     const int need = min(window + pat.n, chunk_cols);
+#ifdef FRZ_SW_TWO_CLASSES   // experiment build: two column classes, half the SW kernel's dynamic instruction footprint
+    return need <= 48 ? FRZ_C_CC48 : FRZ_C_COLS64;
+#else
     return need <= 40 ? FRZ_C_CC40 : need <= 48 ? FRZ_C_CC48 : need <= 56 ? FRZ_C_CC56 : FRZ_C_COLS64;
+#endif
 }
 
 // Exact window of one queued candidate (phase B) + survivor emission.  All 32 lanes of the warp call
@@ -382,6 +386,13 @@ __device__ __forceinline__ void process_candidate(const FrzCorpusView& cv, const
         else flat_ok = masks_k1(ga.base, pat, cid_s, q.occ, len, active, &flat_start, &flat_end);
         flat_done = true;
     }
+#ifdef FRZ_PF_MASKS_K2   // experiment build: the CPU-checked mask forms of the 2-typo / N-typo trackers (prefilter_masks.cuh)
+    if ((MODE == FRZ_T_2 || MODE == FRZ_T_MANY) && pat.n_distinct > 0) {
+        if (MODE == FRZ_T_2) flat_ok = masks_paths<3>(ga.base, pat, cid_s, q.occ, len, active, &flat_start, &flat_end);
+        else flat_ok = masks_many(ga.base, pat, cid_s, q.occ, len, active, &flat_start, &flat_end);
+        flat_done = true;
+    }
+#endif
     if (active) {
         const uint32_t li = cv.slot_meta[(uint64_t)tile * FRZ_TILE + slot] & (FRZ_TILE - 1);
         int start = 0, end = len;
