@@ -129,3 +129,30 @@ def test_c_abi_from_plain_c(tmp_path):
         assert r.returncode == 0 and "Match { score: 53, index: 0, exact: false }" in r.stdout, (r.stdout, r.stderr)
     else:
         assert r.returncode == 3 and "no CPU fallback" in r.stderr, (r.stdout, r.stderr)
+
+
+def test_host_entry_points_survive_random_input():
+    """Parser and pattern compilation are host code fed by user input: random byte strings (valid UTF-8 or not, NULs,
+    operators, escapes) must produce a status, never a crash, and compiled matchers must report sane backends."""
+    import random
+    rng = random.Random(20260923)
+    L = F.lib()
+    alphabet = [b"a", b"B", b" ", b"!", b"^", b"$", b"'", b"\\", b"\x00", b"\xc3\xa9", b"\xf0\x9f\x98\x80", b"\xff", b"\t", b"\xe2\x80\x83", b"0"]
+    for _ in range(3000):
+        q = b"".join(rng.choice(alphabet) for _ in range(rng.randint(0, 12)))
+        h = ctypes.c_void_p()
+        assert L.frz_parse_query(q, len(q), ctypes.byref(h)) == 0
+        n = L.frz_query_len(h)
+        assert 0 <= n <= len(q)
+        L.frz_query_destroy(h)
+        cfg = F.types.CConfig.of(Config(max_typos=rng.choice([None, 0, 1, 2, 5]), unicode=rng.choice(list(UnicodeMatching)),
+                                        casing=rng.choice(list(CaseMatching))))
+        m = ctypes.c_void_p()
+        st = L.frz_matcher_from_query(q, len(q), ctypes.byref(cfg), ctypes.byref(m))
+        assert st in (0, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12), st   # a status, whatever it is
+        if st == 0:
+            for i in range(L.frz_matcher_num_patterns(m)):
+                lanes, bits, pf, lit = ctypes.c_int(), ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+                assert L.frz_matcher_backend_info(m, i, ctypes.byref(lanes), ctypes.byref(bits), ctypes.byref(pf), ctypes.byref(lit)) == 0
+                assert lanes.value in (8, 16, 32, 64) and bits.value in (8, 16) and pf.value in (16, 32, 64)
+            L.frz_matcher_destroy(m)
