@@ -149,7 +149,7 @@ def test_host_entry_points_survive_random_input():
                                         casing=rng.choice(list(CaseMatching))))
         m = ctypes.c_void_p()
         st = L.frz_matcher_from_query(q, len(q), ctypes.byref(cfg), ctypes.byref(m))
-        assert st in (0, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12), st   # a status, whatever it is
+        assert 0 <= st <= 10, st   # a status, whatever it is
         if st == 0:
             for i in range(L.frz_matcher_num_patterns(m)):
                 lanes, bits, pf, lit = ctypes.c_int(), ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
