@@ -1,29 +1,33 @@
 #!/usr/bin/env python
-"""bench.py — haystacks/sec of the match_list hot path on N B200s.
+"""bench.py — haystacks/sec of the match_list / match_list_parallel hot path on N B200s.
 
     python bench.py --gpus N --steps K --warmup W            # our CUDA path
     python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (restated)
 
-A "step" is one Matcher::match_list over one synthetic haystack list of BASELINE.json configs[2]
-shape (needle 'deadbeef', 10M haystacks, len <= 64, mean 48, max_typos = 1) per GPU (weak scaling:
-each rank holds its own 10M-item shard; for N > 1 a step ends with the NCCL all-gather of the
-per-shard runs and the merge — Matcher::match_list_parallel).
-  value : whole-job haystacks/s with the packed corpus already resident in HBM when the timed
-          region starts and the ordered match list left in HBM (device in, device out; the same
-          definition at every N).  `value_host_out` (N = 1) additionally copies the list to pinned
-          host memory inside the timed region.
-  e2e   : the same metric through frz_match_list_host — host Arrow buffers in pinned memory in,
-          host matches out; pack + H2D + kernels + D2H all inside the timed region.
-Prints ONE JSON line on rank 0.
+A "step" is one blocking Matcher::match_list_parallel call (frz_match_list_parallel_rank; at N = 1 this is
+Matcher::match_list) over one synthetic haystack list of BASELINE.json configs[2] shape per GPU — needle 'deadbeef',
+10M haystacks, len <= 64 (mean 48), max_typos = 1 — weak scaling: rank r holds its own 10M-item shard with the indices
+[r*10M, (r+1)*10M); a step is the local pipeline on every GPU, ONE NCCL all-gather of the per-shard runs, the k-way
+merge, and every GPU copying its slice of the merged list into ONE pinned host buffer shared by the ranks.
+
+  value            whole-job haystacks/s, packed shards resident in HBM when the timed region starts, the ordered match
+                   list LANDED IN PINNED HOST MEMORY when a step ends; same definition at every N.
+  value_device_out the same step without the final device->host copy (the merged list left in HBM).
+  e2e              the same metric with the shard arriving as HOST Arrow buffers every step
+                   (frz_match_list_parallel_rank_host: streamed H2D + pack + match + D2H inside the timed region).
+Every loop runs a rank-identical, fixed number of steps (rank 0 decides the pre/post-roll length, everybody gets it by
+broadcast): ranks never issue different numbers of collectives.  Prints ONE JSON line on rank 0.
 """
 from __future__ import annotations
 
 import argparse
+import datetime
 import json
 import os
 import subprocess
 import sys
 import time
+import traceback
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
@@ -32,6 +36,7 @@ if ROOT not in sys.path:
 import numpy as np  # noqa: E402
 
 WORKLOAD = dict(needle="deadbeef", n=10_000_000, mu=48, max_len=64, max_typos=1, seed=12345)
+PUBLISHED_CALIBRATION_MS = 1.85   # /root/reference/BENCHMARKS.md:124 — "Partial Match", median length 64, 100k items, `1 Typo`, 1 thread
 
 
 def parse_args():
@@ -46,6 +51,7 @@ def parse_args():
                     help="Arrow offset width of the e2e input (32 = Utf8, 64 = LargeUtf8)")
     ap.add_argument("--cpu-sample", type=int, default=0, help="haystacks in the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the full-shard parity leg (profiling runs)")
     ap.add_argument("--lanes", type=int, default=0, help="emulate_lanes (0 = what the reference picks on this CPU)")
     # the other BASELINE.json configs are parity-test cases; these flags let profiles/ record their numbers too
     ap.add_argument("--needle", default=WORKLOAD["needle"])
@@ -103,6 +109,15 @@ def workload_config(args):
     return Config(max_typos=WORKLOAD["max_typos"], emulate_lanes=args.lanes)
 
 
+def reference_lanes(args) -> int:
+    """The lane width Matcher::get_backend (src/matcher/mod.rs:448-498) selects on THIS host for a u8-family needle —
+    the oracle's own CPUID rule (no CUDA library involved)."""
+    if args.lanes:
+        return args.lanes
+    from oracle import pyoracle as O
+    return O.auto_lanes()
+
+
 def config_block(args, world, extra=None):
     default = (WORKLOAD["needle"], WORKLOAD["max_typos"], WORKLOAD["mu"], WORKLOAD["max_len"]) == ("deadbeef", 1, 48, 64)
     c = {"workload": f"needle '{WORKLOAD['needle']}' (len {len(WORKLOAD['needle'])}) vs {args.n} synthetic ASCII haystacks per GPU, "
@@ -116,6 +131,30 @@ def config_block(args, world, extra=None):
     return c
 
 
+def pick_threads(cb, needle, cfg, data, off, trials=3):
+    """Thread count of the CPU arm: the reference's final k-way merge is single-threaded, so more threads is not always
+    faster — the fastest of all / half / quarter of the host threads, decided on `trials` timed runs each."""
+    threads = cb.host_threads()
+    best = None
+    for cand in sorted({threads, max(1, threads // 2), max(1, threads // 4)}, reverse=True):
+        dt, _ = cb.timed([needle], cfg, data, off, cand, repeats=trials)
+        if best is None or dt < best[0]:
+            best = (dt, cand)
+    return best[1]
+
+
+def calibration(cb, cfg):
+    """the restated CPU path, ONE thread, on the reference's own published shape (100k haystacks, median
+    length 64, needle 'deadbeef', max_typos 1: 1.85 ms on a Ryzen 9 9950X3D, BENCHMARKS.md:124)."""
+    from frizbee_b200 import synth
+    data, off = synth.generate("deadbeef", 100_000, 64, 128, 12345)
+    c1 = cfg.with_(max_typos=1)
+    dt, _ = cb.timed(["deadbeef"], c1, data, off, 1, repeats=7)
+    return {"ours_ms_1thread": dt * 1e3, "published_ms": PUBLISHED_CALIBRATION_MS, "ratio_ours_over_published": dt * 1e3 / PUBLISHED_CALIBRATION_MS,
+            "what": "100k haystacks, median len 64, 'deadbeef', max_typos=1, 1 thread, best of 7; published: Ryzen 9 9950X3D "
+                    "(BENCHMARKS.md:124)"}
+
+
 def run_reference(args):
     """The reference's own CPU implementation of the path (restated; no Rust toolchain here), all host threads,
     on a bounded sample of the same workload."""
@@ -125,42 +164,68 @@ def run_reference(args):
     from frizbee_b200 import synth
     from oracle import cpu_baseline as cb
     cfg = workload_config(args)
-    threads = cb.host_threads()
     sample = args.cpu_sample or args.n   # the whole single-GPU workload: large enough to amortise thread start-up
     data, off = synth.generate(WORKLOAD["needle"], sample, WORKLOAD["mu"], WORKLOAD["max_len"], WORKLOAD["seed"])
-    lanes = args.lanes or detect_lanes(cfg)
+    lanes = reference_lanes(args)
     cfg = cfg.with_(emulate_lanes=lanes)
-    # be generous to the CPU: the reference's final k-way merge is single-threaded, so more threads is not
-    # always faster — use the thread count (all / half / quarter of the host threads) that runs fastest
-    best = None
-    for cand_threads in sorted({threads, max(1, threads // 2), max(1, threads // 4)}, reverse=True):
-        dt, _ = cb.timed([WORKLOAD["needle"]], cfg, data, off, cand_threads, repeats=max(1, args.warmup))
-        if best is None or dt < best[0]:
-            best = (dt, cand_threads)
-    threads = best[1]
+    threads = pick_threads(cb, WORKLOAD["needle"], cfg, data, off, trials=max(3, args.warmup))
+    for _ in range(max(args.warmup, 3)):
+        cb.match_list_parallel([WORKLOAD["needle"]], cfg, data, off, threads)
+    per_step = []
     t0 = time.perf_counter()
     for _ in range(args.steps):
+        t1 = time.perf_counter()
         res = cb.match_list_parallel([WORKLOAD["needle"]], cfg, data, off, threads)
+        per_step.append(time.perf_counter() - t1)
     dt = time.perf_counter() - t0
     value = sample * args.steps / dt
     line = {"impl": "reference", "metric": "haystacks/sec", "value": value, "unit": "haystacks/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * dt / args.steps,
+            "ms_per_step_min": 1e3 * min(per_step), "ms_per_step_median": 1e3 * float(np.median(per_step)),
+            "value_at_median_step": sample / float(np.median(per_step)),
+            "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": config_block(args, args.gpus, {"sample_haystacks_per_step": sample, "matches_per_step": int(len(res))}),
             "cpu_baseline": {"value": value, "unit": "haystacks/s", "cores": threads, "kind": "port",
                              "sample": f"{sample} haystacks of the same workload per step; {cb.describe()}, "
-                                       f"threaded like match_list_parallel (2048-item work claiming), emulating the "
-                                       f"{lanes}-lane reference backend"},
+                                       f"threaded like match_list_parallel (2048-item work claiming, workers pinned to "
+                                       f"the process's CPUs round-robin), emulating the {lanes}-lane reference backend",
+                             "calibration": calibration(cb, cfg)},
             "e2e": {"value": value, "unit": "haystacks/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
 
-def detect_lanes(cfg) -> int:
-    import frizbee_b200 as F
-    m = F.Matcher(WORKLOAD["needle"], cfg)
-    lanes = m.backend_info()["prefilter_lanes"]
-    m.close()
-    return lanes
+def check_parity(cb, O, needle, cfg, data_np, off_np, index_offset, merged, rank, n_local, n_total):
+    from frizbee_b200.types import SortStrategy
+    """Full-shard parity: this rank's shard through the SIMD CPU restatement (validated bit-exact against the scalar
+    oracle in tests/test_cpu_baseline.py) vs the entries of the MERGED list that fall into this rank's index range;
+    rank 0 additionally checks the global order of the merged list and a 200k prefix against the scalar oracle."""
+    threads = max(1, cb.host_threads() // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1")))))
+    want = cb.match_list_parallel([needle], cfg.with_(sort=SortStrategy.IndexAsc), data_np, off_np, threads)   # IndexAsc: the shard's matches in index order
+    want = want.copy()
+    want["index"] += np.uint32(index_offset)
+    lo, hi = index_offset, index_offset + n_local
+    mine = merged[(merged["index"] >= lo) & (merged["index"] < hi)]
+    mine = mine[np.argsort(mine["index"], kind="stable")]
+    if len(mine) != len(want):
+        mism = max(1, abs(len(mine) - len(want)))
+    else:
+        mism = int(sum(int(np.count_nonzero(want[f] != mine[f])) for f in ("index", "score", "exact")))
+    info = {"haystacks_checked": int(n_local), "matches_checked": int(len(want)), "mismatches": mism}
+    if rank == 0:
+        s = merged["score"].astype(np.int64)
+        i = merged["index"].astype(np.int64)
+        bad = int(np.count_nonzero((s[1:] > s[:-1]) | ((s[1:] == s[:-1]) & (i[1:] <= i[:-1]))))
+        info["order_violations"] = bad
+        info["index_out_of_range"] = int(np.count_nonzero(i >= n_total))
+        sub = min(n_local, 200_000)
+        w2 = O.match_list_packed([needle], cfg.with_(sort=SortStrategy.IndexAsc), data_np[: int(off_np[sub])], off_np[: sub + 1])
+        g2 = mine[mine["index"] < sub + index_offset]
+        ok = len(w2) == len(g2) and all(np.array_equal(w2[f], g2[f] if f != "index" else g2[f] - np.uint32(index_offset))
+                                        for f in ("index", "score", "exact"))
+        info["scalar_oracle_prefix"] = {"haystacks": int(sub), "matches": int(len(w2)), "equal": bool(ok)}
+        info["mismatches"] += bad + info["index_out_of_range"] + (0 if ok else 1)
+    return info
 
 
 def run_ours(args):
@@ -176,17 +241,43 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device — the CUDA path has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    os.environ.setdefault("FRZ_PARALLEL_TIMEOUT_S", "90")   # a missing peer fails the step with a message, not a hang
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        os.environ.setdefault("TORCH_NCCL_ASYNC_ERROR_HANDLING", "1")
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def bcast_int(v: int) -> int:
+        if world == 1:
+            return int(v)
+        t = torch.tensor([int(v)], dtype=torch.int64, device=dev)
+        dist.broadcast(t, 0)
+        return int(t.item())
+
+    def max_over_ranks(x: float) -> float:
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x: int) -> int:
+        t = torch.tensor([int(x)], dtype=torch.int64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return int(t.item())
 
     cfg = workload_config(args)
     n = args.n
+    needle = WORKLOAD["needle"]
     # each rank holds its own shard (weak scaling); shard r covers indices [r*n, (r+1)*n)
-    data_np, off_np = synth.generate(WORKLOAD["needle"], n, WORKLOAD["mu"], WORKLOAD["max_len"], WORKLOAD["seed"] + rank)
-    # pinned host buffers (inputs of the e2e call, and the output of every step)
+    data_np, off_np = synth.generate(needle, n, WORKLOAD["mu"], WORKLOAD["max_len"], WORKLOAD["seed"] + rank)
+    # pinned host buffers: the inputs of the e2e call
     data_pin = torch.empty(data_np.size, dtype=torch.uint8, pin_memory=True)
     off_pin = torch.empty(off_np.size, dtype=torch.int64, pin_memory=True)
-    out_pin = torch.empty(max(n * world, 1), dtype=torch.int64, pin_memory=True)
     data_h = data_pin.numpy(); data_h[:] = data_np
     off_h = off_pin.numpy().view(np.uint64); off_h[:] = off_np
     if args.e2e_offsets == 32 and int(off_np[-1]) < 2 ** 31:   # Arrow Utf8: int32 offsets
@@ -194,121 +285,113 @@ def run_ours(args):
         off_e2e = off32_pin.numpy(); off_e2e[:] = off_np
     else:
         off_e2e = off_h
-    out_h = out_pin.numpy().view(F.MATCH_DTYPE)
 
+    comm = parallel.Comm.from_torch_distributed(local)   # the data path's own NCCL communicator, behind the C ABI
     corpus = F.Corpus.from_arrow(data_h, off_h, device=local)
-    matcher = F.Matcher(WORKLOAD["needle"], cfg)
+    matcher = F.Matcher(needle, cfg)
     info = matcher.backend_info()
     index_offset = rank * n
 
-    runner = parallel.ShardRunner(matcher, corpus, index_offset, device=local)
+    # one device-only step sizes the shared host buffer (capacity = 1.25 x the observed total + slack)
+    total0, _ = comm.match_list_parallel_rank(matcher, corpus, index_offset, None)
+    cap = bcast_int(int(total0 * 1.25) + (1 << 20))
+    out_h = comm.host_alloc_matches(cap)   # ONE pinned host buffer shared by all ranks (memfd segment for N > 1)
 
-    def step():
-        # Matcher::match_list (N = 1) / match_list_parallel (N > 1): local pipeline, one all-gather of the
-        # per-shard runs, device merge; the ordered list stays in HBM
-        merged, total = runner.step()
-        return total
+    def step():          # Matcher::match_list_parallel, the merged list landed in pinned host memory
+        return comm.match_list_parallel_rank(matcher, corpus, index_offset, out_h)[0]
 
-    def step_host_out():
-        return len(matcher.match_list_array(corpus, device=local, out=out_h))
+    def step_dev():      # the same without the final copy
+        return comm.match_list_parallel_rank(matcher, corpus, index_offset, None)[0]
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
+    def step_e2e():      # the shard arrives as host Arrow buffers
+        return comm.match_list_parallel_rank_host(matcher, data_h, off_e2e, index_offset, out_h)
 
     for _ in range(max(args.warmup, 3)):
         n_matches = step()
-    if world == 1:
-        n_matches = step_host_out()
 
-    # ---- parity in the same run (outside the timed region): a prefix sample against the oracle
+    # ---- parity in the same run (outside the timed region): every rank checks its whole shard
     parity = None
-    if rank == 0 and world == 1:
+    if not args.no_parity:
+        from oracle import cpu_baseline as cb
         from oracle import pyoracle as O
-        sub = min(n, 200_000)
-        want = O.match_list_packed([WORKLOAD["needle"]], cfg.with_(emulate_lanes=info["prefilter_lanes"]),
-                                   data_np[: int(off_np[sub])], off_np[: sub + 1])
-        got = out_h[:n_matches]
-        got = got[got["index"] < sub]
-        want_s, got_s = np.sort(want, order=["index"]), np.sort(got, order=["index"])
-        mism = int(len(want_s) != len(got_s)) if len(want_s) != len(got_s) else int(
-            sum(int(np.count_nonzero(want_s[f] != got_s[f])) for f in ("index", "score", "exact")))
-        parity = {"haystacks_checked": sub, "matches_checked": int(len(want_s)), "mismatches": mism}
+        barrier()
+        merged = np.array(out_h[:n_matches])   # every rank reads the whole shared buffer
+        pcfg = cfg.with_(emulate_lanes=info["prefilter_lanes"])
+        pi = check_parity(cb, O, needle, pcfg, data_np, off_np, index_offset, merged, rank, n, n * world)
+        mism = sum_over_ranks(pi["mismatches"])
+        checked = sum_over_ranks(pi["matches_checked"])
+        parity = dict(pi, mismatches=mism, matches_checked=checked, haystacks_checked=n * world,
+                      matches_in_merged_list=int(n_matches),
+                      checker="oracle/cpu_baseline (SIMD restatement, bit-exact with the scalar oracle: tests/test_cpu_baseline.py), "
+                              "every rank its whole shard; rank 0: global order + scalar-oracle 200k prefix")
+        if checked != n_matches:
+            parity["mismatches"] = mism + abs(checked - n_matches)
+        del merged
 
-    # ---- timed region: device value
-    sampler = ClockSampler(local)
-    stage_ms = np.zeros(4)
-    launches = 0
+    # ---- how many steps make 0.4 s (rank 0 decides, everybody runs the same number)
     barrier()
-    sampler.start()
-    # nvidia-smi needs ~100 ms per sample: keep the GPU under the same load before (pre-roll) and after
-    # (post-roll) the timed steps so that the samples describe the clocks the timed region ran at
-    t_pre = time.perf_counter()
-    while time.perf_counter() - t_pre < 0.4:
+    t0 = time.perf_counter()
+    for _ in range(5):
         step()
     barrier()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    for _ in range(args.steps):
-        n_matches = step()
-    ev1.record()
-    barrier()
-    t_post = time.perf_counter()
-    while time.perf_counter() - t_post < 0.4:
-        step()
-    barrier()
-    # per-stage CUDA-event timings (recorded inside the library on the launching stream) from separate,
-    # identical steps, so that reading them back does not put a host sync inside the timed region
+    est = (time.perf_counter() - t0) / 5
+    n_roll = bcast_int(min(4000, max(5, int(0.4 / max(est, 1e-5)))))
+
+    def timed(fn, steps, clocks=False):
+        """pre-roll, K timed steps between CUDA events, post-roll — all fixed counts; max over ranks."""
+        sampler = ClockSampler(local) if clocks and rank == 0 else None
+        barrier()
+        if sampler:
+            sampler.start()
+            # nvidia-smi needs ~100 ms per sample: keep the GPU under the same load before (pre-roll) and after
+            # (post-roll) the timed steps so that the samples describe the clocks the timed region ran at
+            for _ in range(n_roll):
+                fn()
+        elif clocks:
+            for _ in range(n_roll):
+                fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        r = None
+        for _ in range(steps):
+            r = fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if clocks:
+            for _ in range(n_roll):
+                fn()
+            barrier()
+        c = sampler.stop() if sampler else None
+        return max_over_ranks(ms), r, c
+
+    ms, n_matches, clocks = timed(step, args.steps, clocks=True)
+    if clocks is not None:
+        clocks["window"] = f"{n_roll} identical pre-roll steps + timed region + {n_roll} identical post-roll steps"
+    value = n * world * args.steps / (ms / 1e3)
+    ms_dev, _, _ = timed(step_dev, args.steps)
+
+    # per-stage CUDA-event timings (recorded inside the library on the launching stream) from separate, identical steps
     stage_steps = 10
+    stage = {k: 0.0 for k in ("prefilter_ms", "sw_ms", "sort_ms", "pipeline_ms", "local_ms", "gather_merge_ms", "d2h_ms", "total_ms")}
+    launches = 0
     for _ in range(stage_steps):
         step()
-        t = matcher.last_timings()
-        stage_ms += np.array([t["prefilter_ms"], t["sw_ms"], t["sort_ms"], t["total_ms"]])
-        launches += t["launches"]
-    stage_ms *= args.steps / stage_steps
-    launches = int(launches * args.steps / stage_steps)
-    clocks = sampler.stop()
-    clocks["window"] = "0.4 s identical pre-roll + timed region + 0.4 s identical post-roll"
-    if world == 1:
-        n_matches = int(runner.count.item())
-    ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms = float(ms.item())
-    value = n * world * args.steps / (ms / 1e3)
+        t = comm.last_timings(0)
+        for k in stage:
+            stage[k] += t.get(k, 0.0) / stage_steps
+        launches += t.get("launches", 0)
+    # kernels of this repo per step: the local pipeline + count publish + (N > 1: 3 merge kernels + copy-out flag)
+    launches_per_step = launches / stage_steps + 1 + (4 if world > 1 else 0)
 
-    # ---- N = 1 only: the same call with the match list landing in pinned host memory
-    host_out = None
-    if world == 1:
-        h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        torch.cuda.synchronize(dev)
-        h0.record()
-        for _ in range(args.steps):
-            step_host_out()
-        h1.record()
-        torch.cuda.synchronize(dev)
-        hms = h0.elapsed_time(h1)
-        host_out = {"value": n * args.steps / (hms / 1e3), "unit": "haystacks/s", "ms_per_step": hms / args.steps,
-                    "d2h_bytes_per_step": int(n_matches * 8 + 64)}
-
-    # ---- timed region: end to end (host buffers in, host matches out), single-GPU API per rank
+    # ---- timed region: end to end (host buffers in, host matches out)
     e2e_steps = args.e2e_steps or min(args.steps, 5)
-    matcher.match_list_host_array(data_h, off_e2e, device=local, out=out_h)  # warm
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(e2e_steps):
-        r = matcher.match_list_host_array(data_h, off_e2e, device=local, out=out_h)
-    e1.record()
-    barrier()
-    e_ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-    if world > 1:
-        dist.all_reduce(e_ms, op=dist.ReduceOp.MAX)
-    e_ms = float(e_ms.item())
+    step_e2e()   # warm
+    e_ms, n_e2e, _ = timed(step_e2e, e2e_steps)
     e2e_value = n * world * e2e_steps / (e_ms / 1e3)
     h2d = int(data_h.nbytes + off_e2e.nbytes)
-    d2h = int(len(r) * 8 + 64)
+    d2h_rank = int(n_e2e * 8 / world + 64)
 
     if rank == 0:
         peaks = {}
@@ -317,13 +400,13 @@ def run_ours(args):
         except Exception:
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
-        pf_ms = stage_ms[0] / args.steps
+        pf_ms = stage["prefilter_ms"]
         alg_bytes = int(corpus.total_bytes + 8 * n + 8 * n_matches / world)
         achieved = alg_bytes / (pf_ms / 1e3) / 1e9 if pf_ms > 0 else None
         traffic = None
         try:
             tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-            if (WORKLOAD["needle"], WORKLOAD["max_typos"], WORKLOAD["mu"], WORKLOAD["max_len"], n) == ("deadbeef", 1, 48, 64, 10_000_000):
+            if (needle, WORKLOAD["max_typos"], WORKLOAD["mu"], WORKLOAD["max_len"], n) == ("deadbeef", 1, 48, 64, 10_000_000):
                 traffic = int(tj["dram_bytes_read"] + tj["dram_bytes_write"])   # from the committed ncu capture
         except Exception:
             pass
@@ -331,43 +414,52 @@ def run_ours(args):
                     "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "traffic": traffic,
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
                     "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": pf_ms,
-                    "stage_ms_per_step": {"prefilter": pf_ms, "smith_waterman": stage_ms[1] / args.steps,
-                                          "sort": stage_ms[2] / args.steps, "device_total": stage_ms[3] / args.steps}}
+                    "whole_step_frac": (alg_bytes / (ms / args.steps / 1e3) / 1e9 / peak),
+                    "stage_ms_per_step": {"prefilter": pf_ms, "smith_waterman": stage["sw_ms"], "sort": stage["sort_ms"],
+                                          "local_pipeline": stage["local_ms"], "all_gather_merge": stage["gather_merge_ms"],
+                                          "d2h_slice": stage["d2h_ms"], "device_total": stage["total_ms"]}}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             from oracle import cpu_baseline as cb
-            threads = cb.host_threads()
             sample = args.cpu_sample or n
             ccfg = cfg.with_(emulate_lanes=info["prefilter_lanes"])
             sd, so = data_np[: int(off_np[sample])], off_np[: sample + 1]
-            best = None
-            for cand_threads in sorted({threads, max(1, threads // 2), max(1, threads // 4)}, reverse=True):
-                dt_c, _ = cb.timed([WORKLOAD["needle"]], ccfg, sd, so, cand_threads, repeats=2)
-                if best is None or dt_c < best[0]:
-                    best = (dt_c, cand_threads)
-            dt, threads = best
+            threads = pick_threads(cb, needle, ccfg, sd, so, trials=3)
+            per = [cb.timed([needle], ccfg, sd, so, threads, repeats=1)[0] for _ in range(7)]
+            dt = float(np.median(per))
             cpu = {"value": sample / dt, "unit": "haystacks/s", "cores": threads, "kind": "port",
-                   "sample": f"first {sample} haystacks of the same list, best of 2 at the fastest of all/half/quarter "
+                   "value_best": sample / min(per),
+                   "sample": f"first {sample} haystacks of the same list, median of 7 at the fastest of all/half/quarter "
                              f"of the {cb.host_threads()} host threads; {cb.describe()}, threaded like "
-                             f"match_list_parallel; emulating the {info['prefilter_lanes']}-lane reference backend"}
+                             f"match_list_parallel; emulating the {info['prefilter_lanes']}-lane reference backend",
+                   "calibration": calibration(cb, ccfg)}
         line = {"metric": "haystacks/sec", "value": value, "unit": "haystacks/s", "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "u8", "data": "synthetic",
                 "config": config_block(args, world, {"matches_per_step": int(n_matches),
+                                                     "output": "ordered frz_match[] landed in ONE pinned host buffer "
+                                                               "(shared by the ranks; every GPU copies its slice)",
                                                      "emulated_reference_backend": info}),
                 "clocks": clocks,
-                "e2e": {"value": e2e_value, "unit": "haystacks/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "value_device_out": {"value": n * world * args.steps / (ms_dev / 1e3), "unit": "haystacks/s",
+                                     "ms_per_step": ms_dev / args.steps, "what": "same step, merged list left in HBM"},
+                "d2h_bytes_per_step": int(n_matches * 8),
+                "e2e": {"value": e2e_value, "unit": "haystacks/s", "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h_rank * world,
                         "steps": e2e_steps, "ms_per_step": e_ms / e2e_steps,
                         "input": f"Arrow {'Utf8 (int32' if off_e2e.dtype.itemsize == 4 else 'LargeUtf8 (int64'} offsets) "
-                                 "value+offset buffers in pinned host memory; H2D chunks overlap the pack kernels"},
-                "value_host_out": host_out,
-                "gpu_launches": int(launches),
+                                 "value+offset buffers in pinned host memory, one shard per rank; H2D chunks overlap the pack kernels"},
+                "gpu_launches": int(round(launches_per_step * args.steps)),
                 "roofline": roofline, "cpu_baseline": cpu, "parity": parity}
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
+    barrier()
+    comm.host_free(out_h)
     corpus.close()
     matcher.close()
+    comm.close()
     if world > 1:
         dist.destroy_process_group()
+    if parity is not None and parity["mismatches"] != 0:
+        raise SystemExit(f"bench.py: parity FAILED: {parity}")
 
 
 def main():
@@ -375,8 +467,14 @@ def main():
     WORKLOAD.update(needle=args.needle, max_typos=args.max_typos, mu=args.mu, max_len=args.max_len)
     if args.impl == "reference":
         run_reference(args)
-    else:
+        return
+    try:
         run_ours(args)
+    except BaseException:
+        # print the failing rank's traceback and leave at once: a rank that dies quietly would make its peers wait
+        sys.stderr.write(f"[bench.py rank {os.environ.get('RANK', '0')}] failed:\n{traceback.format_exc()}\n")
+        sys.stderr.flush()
+        os._exit(1)
 
 
 if __name__ == "__main__":

@@ -25,7 +25,7 @@ MATCH_DTYPE = np.dtype([("index", "<u4"), ("score", "<u2"), ("exact", "u1"), ("_
 
 STATUS_NAMES = {0: "FRZ_OK", 1: "FRZ_ERR_INVALID_ARG", 2: "FRZ_ERR_NEEDLE_TOO_LONG", 3: "FRZ_ERR_GAP_OVERFLOW",
                 4: "FRZ_ERR_TOO_MANY_ITEMS", 5: "FRZ_ERR_THREADS_ZERO", 6: "FRZ_ERR_CAPACITY", 7: "FRZ_ERR_CUDA",
-                8: "FRZ_ERR_NO_DEVICE", 9: "FRZ_ERR_UNSUPPORTED", 10: "FRZ_ERR_OOM"}
+                8: "FRZ_ERR_NO_DEVICE", 9: "FRZ_ERR_UNSUPPORTED", 10: "FRZ_ERR_OOM", 11: "FRZ_ERR_NCCL"}
 
 
 class FrizbeeError(RuntimeError):
@@ -332,7 +332,7 @@ class Matcher:
             if out_cnt[j] == 0xFFFFFFFF:
                 res.append(None)
             else:
-                res.append((int(out_m[j]["score"]), bool(out_m[j]["exact"]), out_idx[j, : int(out_cnt[j])].tolist()))
+                res.append((int(out_m[j]["score"]), bool(out_m[j]["exact"]), out_idx[j, : min(int(out_cnt[j]), stride)].tolist()))
         return res
 
     def match_list_host_array(self, data: np.ndarray, offsets: np.ndarray, device: int = 0,

@@ -151,3 +151,25 @@ frz_status frz_launch_sort_by_score_dev(const FrzMatchDev* d_in, FrzMatchDev* d_
                                         const unsigned long long* n_ptr, uint32_t score_bound, FrzWorkspace& ws,
                                         cudaStream_t stream, FrzLaunchStats* st);
 size_t frz_sort_hist_words();
+
+// k-way merge of per-shard runs (host.cu) with caller-owned scratch — one per concurrent user (parallel.cu: one per rank)
+#define FRZ_MERGE_MAX_RUNS 64
+struct FrzMergeScratch {
+    uint32_t* hist = nullptr;      // sort scratch of the concatenate-and-sort fallback
+    uint32_t* tables = nullptr;    // gt / pos0 tables of the scatter merge
+    FrzMatchDev* cat = nullptr;
+    FrzMatchDev* tmp = nullptr;
+    unsigned long long* d_total = nullptr;
+    uint64_t cap = 0;
+    int device = -1;
+    void release();
+};
+frz_status frz_merge_runs_ex(FrzMergeScratch& ms, const FrzMatchDev* runs, uint64_t run_stride, const uint64_t* run_counts_host,
+                             int n_runs, uint8_t sort, uint32_t score_bound, FrzMatchDev* d_out, cudaStream_t stream);
+
+// Matcher internals the multi-GPU layer needs (host.cu)
+uint64_t frz_matcher_epoch(const frz_matcher* m);                  // changes whenever the compiled patterns change
+uint8_t frz_matcher_sort(const frz_matcher* m);
+// host Arrow buffers → the matcher's reusable packed corpus (the ingest half of frz_match_list_host_arrow)
+frz_status frz_matcher_ingest_e2e(frz_matcher* m, const uint8_t* bytes, const void* offsets, int offset_width, uint64_t n, int device,
+                                  const frz_corpus** out);

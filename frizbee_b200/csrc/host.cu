@@ -15,7 +15,9 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
 #include <memory>
+#include <mutex>
 
 #include "frz_device.cuh"
 #include "frz_host.h"
@@ -49,6 +51,7 @@ extern "C" const char* frz_status_str(frz_status s) {
         case FRZ_ERR_NO_DEVICE: return "no usable CUDA device";
         case FRZ_ERR_UNSUPPORTED: return "not supported on the GPU path";
         case FRZ_ERR_OOM: return "out of device memory";
+        case FRZ_ERR_NCCL: return "NCCL error";
     }
     return "?";
 }
@@ -473,8 +476,10 @@ frz_status compile_pattern(const OwnedPattern& src, const frz_config& mcfg, bool
         *out = c;
         return FRZ_OK;
     }
-    // MatcherImpl::guard_against_score_overflow (src/matcher/algo.rs:311-325): byte length on the ascii path
-    FRZ_TRY(guard_against_score_overflow(sc, n, max_per_char_bonus(sc), max_one_time_bonus(sc)));
+    // MatcherImpl::guard_against_score_overflow (src/matcher/algo.rs:311-325): byte length on the ascii path,
+    // (needle.chars().count() when the unicode specialisation is selected, algo.rs:318-321)
+    const size_t guard_len = needs_unicode ? nchars : n;
+    FRZ_TRY(guard_against_score_overflow(sc, guard_len, max_per_char_bonus(sc), max_one_time_bonus(sc)));
     const bool use_u8 = score_fits_in_u8(n, sc);
     int pf_lanes, sw_lanes;
     if (em == 0) {
@@ -536,7 +541,7 @@ frz_status compile_pattern(const OwnedPattern& src, const frz_config& mcfg, bool
     else if (max_typos == 2) d.typo_mode = FRZ_T_2;
     else {
         d.typo_mode = FRZ_T_MANY;
-        if (max_typos > 15 && (size_t)max_typos < n)
+        if (max_typos > 15 && (size_t)max_typos < guard_len)
             return frz_fail(FRZ_ERR_UNSUPPORTED, "max_typos > 15 is not on the GPU path yet");
     }
     {   // Phase-A necessary condition.  A byte class that fills more than k needle positions must occur in the
@@ -563,7 +568,7 @@ frz_status compile_pattern(const OwnedPattern& src, const frz_config& mcfg, bool
             for (int j = 0; j <= k && j < 3; j++) { d.probe_om[j] = d.om[j]; d.probe_tg[j] = d.tg[j]; d.probe_n++; }
         }
     }
-    d.max_typos = max_typos < 0 ? 0 : std::min(max_typos, (int)n);  // budget >= needle length matches everything
+    d.max_typos = max_typos < 0 ? 0 : std::min(max_typos, (int)guard_len);  // budget >= needle length matches everything
     // min_haystack_len (src/matcher/algo.rs:62-65)
     d.min_hay_len = max_typos >= 0 ? (int)(nchars > (size_t)max_typos ? nchars - max_typos : 0) : 0;
     uint64_t b = std::min<uint64_t>(cell_bound, use_u8 ? 255 : 0xFFFF) + sc.exact_match_bonus;
@@ -608,6 +613,7 @@ struct frz_matcher {
     cudaEvent_t count_ev = nullptr;        // recorded once the count is in early_count_dst
     bool count_published = false;
     bool timings_pending = false;
+    uint64_t epoch = 0;                    // identity of the compiled patterns (clones made for another epoch are stale)
     ~frz_matcher() {
         if (ws.device >= 0) { cudaSetDevice(ws.device); cudaFree(multi_a); cudaFree(multi_b); if (count_ev) cudaEventDestroy(count_ev); }
         if (e2e_ingest.d_bytes || e2e_ingest.copy_stream || e2e_corpus.st.data) {
@@ -621,7 +627,10 @@ struct frz_matcher {
 
 namespace {
 
+std::atomic<uint64_t> g_matcher_epoch{1};
+
 frz_status build_patterns(frz_matcher* m) {
+    m->epoch = g_matcher_epoch.fetch_add(1);
     std::vector<Compiled> comp;
     for (const auto& p : m->raw) {
         bool none = false;
@@ -645,6 +654,13 @@ frz_status validate_config(const frz_config* c) {
 extern "C" frz_status frz_matcher_create(const frz_pattern* patterns, size_t n_patterns, const frz_config* config, frz_matcher** out) {
     if (!out || (n_patterns && !patterns)) return frz_fail(FRZ_ERR_INVALID_ARG, "null argument");
     FRZ_TRY(validate_config(config));
+    for (size_t i = 0; i < n_patterns; i++) {   // PatternConfig overrides (src/pattern.rs:230-246): -1 = inherit, else the enum range
+        const frz_pattern& p = patterns[i];
+        if (p.needle_len && !p.needle) return frz_fail(FRZ_ERR_INVALID_ARG, "pattern %zu: null needle", i);
+        if (p.casing < -1 || p.casing > 2 || p.unicode < -1 || p.unicode > 2 || p.matching < -1 || p.matching > 4)
+            return frz_fail(FRZ_ERR_INVALID_ARG, "pattern %zu: bad enum value in the per-pattern overrides", i);
+        if (p.max_typos < -1 || p.max_typos > 65535) return frz_fail(FRZ_ERR_INVALID_ARG, "pattern %zu: max_typos out of range", i);
+    }
     auto m = std::make_unique<frz_matcher>();
     m->config = *config;
     for (size_t i = 0; i < n_patterns; i++) {
@@ -683,6 +699,20 @@ extern "C" frz_status frz_matcher_set_config(frz_matcher* m, const frz_config* c
     if (s != FRZ_OK) { m->config = old; build_patterns(m); }
     return s;
 }
+
+// `Matcher: Clone` (src/matcher/mod.rs:76): same patterns and config, fresh device scratch.  match_list_parallel clones
+// the matcher once per worker (src/matcher/parallel.rs:46); frz_match_list_parallel does the same once per GPU.
+extern "C" frz_status frz_matcher_clone(const frz_matcher* src, frz_matcher** out) {
+    if (!src || !out) return frz_fail(FRZ_ERR_INVALID_ARG, "null argument");
+    auto m = std::make_unique<frz_matcher>();
+    m->config = src->config;
+    m->raw = src->raw;
+    FRZ_TRY(build_patterns(m.get()));
+    *out = m.release();
+    return FRZ_OK;
+}
+uint64_t frz_matcher_epoch(const frz_matcher* m) { return m ? m->epoch : 0; }
+uint8_t frz_matcher_sort(const frz_matcher* m) { return m ? m->config.sort : 0; }
 
 extern "C" void frz_matcher_destroy(frz_matcher* m) { delete m; }
 extern "C" size_t frz_matcher_num_patterns(const frz_matcher* m) { return m ? m->compiled.size() : 0; }
@@ -852,6 +882,18 @@ frz_status ensure_workspace(frz_matcher* m, const FrzCorpusStorage& cs, uint64_t
     return FRZ_OK;
 }
 
+// multi-pattern candidate ping-pong / two-pass sort scratch: grow-only, always >= n entries after this call
+frz_status ensure_multi_buffers(frz_matcher* m, uint64_t n) {
+    if (m->multi_a && m->multi_b && m->multi_cap >= std::max<uint64_t>(n, 1)) return FRZ_OK;
+    cudaFree(m->multi_a); cudaFree(m->multi_b);
+    m->multi_a = m->multi_b = nullptr; m->multi_cap = 0;
+    const uint64_t want = std::max<uint64_t>(n, 1);
+    FRZ_CUDA_TRY(cudaMalloc(&m->multi_a, (size_t)want * sizeof(FrzMatchDev)));
+    FRZ_CUDA_TRY(cudaMalloc(&m->multi_b, (size_t)want * sizeof(FrzMatchDev)));
+    m->multi_cap = want;
+    return FRZ_OK;
+}
+
 uint64_t initial_survivor_cap(const FrzCorpusStorage& cs, const FrzPatternDev& d) {
     if (d.typo_mode == FRZ_T_NONE) return std::max<uint64_t>(cs.n, 1);
     return std::min<uint64_t>(std::max<uint64_t>(cs.n / 4, 1 << 16), std::max<uint64_t>(cs.n, 1));
@@ -942,13 +984,7 @@ frz_status match_into_device(frz_matcher* m, const FrzCorpusStorage& cs, uint32_
     }
     // CompiledPatterns::Multi (src/matcher/multi.rs:84-152).  Counts are read back between patterns.
     FRZ_TRY(ensure_workspace(m, cs, initial_survivor_cap(cs, pats[0].dev)));
-    if (m->multi_cap < cs.n) {
-        cudaFree(m->multi_a); cudaFree(m->multi_b);
-        m->multi_a = m->multi_b = nullptr; m->multi_cap = 0;
-        FRZ_CUDA_TRY(cudaMalloc(&m->multi_a, (size_t)std::max<uint64_t>(cs.n, 1) * sizeof(FrzMatchDev)));
-        FRZ_CUDA_TRY(cudaMalloc(&m->multi_b, (size_t)std::max<uint64_t>(cs.n, 1) * sizeof(FrzMatchDev)));
-        m->multi_cap = cs.n;
-    }
+    FRZ_TRY(ensure_multi_buffers(m, cs.n));
     int base = -1;
     for (size_t i = 0; i < pats.size(); i++) if (!pats[i].negated) { base = (int)i; break; }
     FrzMatchDev* cand = m->multi_a;
@@ -1044,13 +1080,11 @@ frz_status match_list_device(frz_matcher* m, const FrzCorpusStorage& cs, uint32_
     // `!self.patterns.is_empty() && sort.is_by_score()` (src/matcher/mod.rs:218)
     if (will_sort) {
         FrzMatchDev* other = final_out ? final_out : (d_list == ws.matches_a ? ws.matches_b : ws.matches_a);
-        FrzMatchDev* tmp = m->multi_a ? m->multi_a : nullptr;
-        if (bound >= 1024 && !tmp) {
-            if (m->multi_cap < cs.n) {
-                FRZ_CUDA_TRY(cudaMalloc(&m->multi_a, (size_t)std::max<uint64_t>(cs.n, 1) * sizeof(FrzMatchDev)));
-                FRZ_CUDA_TRY(cudaMalloc(&m->multi_b, (size_t)std::max<uint64_t>(cs.n, 1) * sizeof(FrzMatchDev)));
-                m->multi_cap = cs.n;
-            }
+        // two-pass sort (score bound >= 1024) needs a scratch list of the corpus size: the multi-pattern ping-pong
+        // buffer is free at this point (d_list is never multi_a); grow it whenever THIS corpus is larger
+        FrzMatchDev* tmp = nullptr;
+        if (bound >= 1024) {
+            FRZ_TRY(ensure_multi_buffers(m, cs.n));
             tmp = m->multi_a;
         }
         FRZ_TRY(frz_launch_sort_by_score_dev(d_list, tmp, other, &ws.counters->total, bound, ws, stream, st));
@@ -1140,6 +1174,18 @@ extern "C" frz_status frz_match_list_host_arrow(frz_matcher* m, const uint8_t* b
     if (!m || !offsets) return frz_fail(FRZ_ERR_INVALID_ARG, "null argument");
     if (offset_width != 4 && offset_width != 8) return frz_fail(FRZ_ERR_INVALID_ARG, "offset_width must be 4 or 8");
     if (n > 0xFFFFFFFFull) return frz_fail(FRZ_ERR_TOO_MANY_ITEMS, "too many items in haystack: %llu", (unsigned long long)n);
+    const frz_corpus* c = nullptr;
+    FRZ_TRY(frz_matcher_ingest_e2e(m, bytes, offsets, offset_width, n, device, &c));
+    return frz_match_list(m, c, out, cap, n_out);
+}
+
+// The ingest half of the end-to-end call: host Arrow buffers → the matcher's reusable packed corpus (grow-only staging
+// arena, streamed H2D overlapped with the pack kernels; asynchronous on the legacy default stream).
+frz_status frz_matcher_ingest_e2e(frz_matcher* m, const uint8_t* bytes, const void* offsets, int offset_width, uint64_t n, int device,
+                                  const frz_corpus** out) {
+    if (!m || !offsets || !out) return frz_fail(FRZ_ERR_INVALID_ARG, "null argument");
+    if (offset_width != 4 && offset_width != 8) return frz_fail(FRZ_ERR_INVALID_ARG, "offset_width must be 4 or 8");
+    if (n > 0xFFFFFFFFull) return frz_fail(FRZ_ERR_TOO_MANY_ITEMS, "too many items in haystack: %llu", (unsigned long long)n);
     FRZ_TRY(ensure_device(device));
     cudaStream_t stream = nullptr;
     frz_corpus& c = m->e2e_corpus;
@@ -1151,7 +1197,8 @@ extern "C" frz_status frz_match_list_host_arrow(frz_matcher* m, const uint8_t* b
     }
     c.st.device = device;
     FRZ_TRY(frz_ingest_host(m->e2e_ingest, bytes, offsets, offset_width, n, stream, &c.st));
-    return frz_match_list(m, &c, out, cap, n_out);
+    *out = &c;
+    return FRZ_OK;
 }
 
 extern "C" frz_status frz_match_list_host(frz_matcher* m, const uint8_t* bytes, const uint64_t* offsets, uint64_t n, int device,
@@ -1203,13 +1250,16 @@ extern "C" frz_status frz_match_indices(frz_matcher* m, const frz_corpus* corpus
         return match_indices_one(m->compiled[0], corpus, which, n, out_matches, out_indices, stride, out_counts);
     // CompiledPatterns::Multi → match_one_indices_multi (src/matcher/multi.rs:56-79): a negated atom that matches drops the
     // row, the others add their scores, OR their exact flags and pool their indices (sorted descending, de-duplicated)
+    // every atom yields at most one index per needle scalar (<= FRZ_MAX_NEEDLE): pool with an internal stride that
+    // cannot truncate an atom, cut the pooled (sorted, de-duplicated) list at the caller's stride afterwards
+    const uint32_t istride = std::max<uint32_t>(stride, FRZ_MAX_NEEDLE);
     std::vector<frz_match> pm(n);
-    std::vector<uint32_t> pi((size_t)n * stride), pc(n);
+    std::vector<uint32_t> pi((size_t)n * istride), pc(n);
     std::vector<std::vector<uint32_t>> pooled(n);
     std::vector<uint8_t> alive(n, 1);
     for (uint64_t j = 0; j < n; j++) out_matches[j] = frz_match{which[j], 0, 0, 0};
     for (const Compiled& c : m->compiled) {
-        FRZ_TRY(match_indices_one(c, corpus, which, n, pm.data(), pi.data(), stride, pc.data()));
+        FRZ_TRY(match_indices_one(c, corpus, which, n, pm.data(), pi.data(), istride, pc.data()));
         for (uint64_t j = 0; j < n; j++) {
             if (!alive[j]) continue;
             const bool hit = pc[j] != 0xFFFFFFFFu;
@@ -1218,7 +1268,8 @@ extern "C" frz_status frz_match_indices(frz_matcher* m, const frz_corpus* corpus
             const uint32_t sum = (uint32_t)out_matches[j].score + pm[j].score;
             out_matches[j].score = (uint16_t)std::min<uint32_t>(sum, 0xFFFF);
             out_matches[j].exact |= pm[j].exact;
-            pooled[j].insert(pooled[j].end(), pi.begin() + (size_t)j * stride, pi.begin() + (size_t)j * stride + pc[j]);
+            const size_t got = std::min<size_t>(pc[j], istride);
+            pooled[j].insert(pooled[j].end(), pi.begin() + (size_t)j * istride, pi.begin() + (size_t)j * istride + got);
         }
     }
     for (uint64_t j = 0; j < n; j++) {
@@ -1226,8 +1277,8 @@ extern "C" frz_status frz_match_indices(frz_matcher* m, const frz_corpus* corpus
         auto& v = pooled[j];
         std::sort(v.begin(), v.end(), [](uint32_t a, uint32_t b) { return a > b; });
         v.erase(std::unique(v.begin(), v.end()), v.end());
-        out_counts[j] = (uint32_t)std::min<size_t>(v.size(), stride);
-        for (uint32_t k = 0; k < out_counts[j]; k++) out_indices[(size_t)j * stride + k] = v[k];
+        out_counts[j] = (uint32_t)v.size();   // untruncated: a value > stride tells the caller the row was cut
+        for (uint32_t k = 0; k < std::min<uint32_t>(out_counts[j], stride); k++) out_indices[(size_t)j * stride + k] = v[k];
     }
     return FRZ_OK;
 }
@@ -1268,12 +1319,21 @@ extern "C" frz_status frz_matcher_wait_count(frz_matcher* m, void* stream) {
 }
 
 namespace {
-__global__ void k_gather_runs(const FrzMatchDev* runs, uint64_t stride, const uint64_t* counts, const uint64_t* bases, int n_runs,
-                              int reverse_runs, FrzMatchDev* out) {
+// Run metadata travels BY VALUE as a kernel parameter (1 KB of the 4 KB parameter space): no staging buffer, so
+// back-to-back merges with different counts cannot race and the entry point needs no per-call H2D copy.
+struct MergeMeta {
+    uint64_t counts[FRZ_MERGE_MAX_RUNS];   // valid entries of run r
+    uint64_t bases[FRZ_MERGE_MAX_RUNS];    // concatenation offset of the r-th run in merge order
+    uint64_t total;
+};
+
+__global__ void k_gather_runs(const FrzMatchDev* runs, uint64_t stride, const __grid_constant__ MergeMeta meta, int n_runs,
+                              int reverse_runs, FrzMatchDev* out, unsigned long long* d_total) {
+    if (blockIdx.x == 0 && threadIdx.x == 0 && d_total) *d_total = meta.total;
     for (int r = 0; r < n_runs; r++) {
         const int src_run = reverse_runs ? n_runs - 1 - r : r;
         const FrzMatchDev* src = runs + (uint64_t)src_run * stride;
-        const uint64_t cnt = counts[src_run], base = bases[r];
+        const uint64_t cnt = meta.counts[src_run], base = meta.bases[r];
         for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += (uint64_t)gridDim.x * blockDim.x)
             out[base + i] = src[i];
     }
@@ -1286,14 +1346,14 @@ __global__ void k_gather_runs(const FrzMatchDev* runs, uint64_t stride, const ui
 // same-score blocks of the runs that come earlier in the merge order; one scatter pass places the elements.
 constexpr int kMergeMaxBins = 4096;
 
-__global__ void k_merge_bounds(const FrzMatchDev* __restrict__ runs, uint64_t stride, const uint64_t* __restrict__ counts,
+__global__ void k_merge_bounds(const FrzMatchDev* __restrict__ runs, uint64_t stride, const __grid_constant__ MergeMeta meta,
                                int n_runs, int bins, uint32_t* __restrict__ gt) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_runs * bins) return;
     const int r = t / bins;
     const uint32_t s = (uint32_t)(t - r * bins);
     const FrzMatchDev* run = runs + (uint64_t)r * stride;
-    uint64_t lo = 0, hi = counts[r];   // first index whose score <= s
+    uint64_t lo = 0, hi = meta.counts[r];   // first index whose score <= s
     while (lo < hi) {
         const uint64_t mid = (lo + hi) >> 1;
         if (run[mid].score > s) lo = mid + 1; else hi = mid;
@@ -1302,7 +1362,7 @@ __global__ void k_merge_bounds(const FrzMatchDev* __restrict__ runs, uint64_t st
 }
 
 // pos0[r][s] = merged position of the first element of run r's score-s block.  One thread per score.
-__global__ void k_merge_bases(const uint32_t* __restrict__ gt, const uint64_t* __restrict__ counts, int n_runs, int bins,
+__global__ void k_merge_bases(const uint32_t* __restrict__ gt, const __grid_constant__ MergeMeta meta, int n_runs, int bins,
                               int reverse_runs, uint32_t* __restrict__ pos0) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= bins) return;
@@ -1312,22 +1372,26 @@ __global__ void k_merge_bases(const uint32_t* __restrict__ gt, const uint64_t* _
     for (int k = 0; k < n_runs; k++) {
         const int r = reverse_runs ? n_runs - 1 - k : k;
         pos0[r * bins + s] = acc;
-        const uint32_t ge = s == 0 ? (uint32_t)counts[r] : gt[r * bins + s - 1];   // #elements with score >= s
+        const uint32_t ge = s == 0 ? (uint32_t)meta.counts[r] : gt[r * bins + s - 1];   // #elements with score >= s
         acc += ge - gt[r * bins + s];
     }
 }
 
-__global__ void k_merge_scatter(const FrzMatchDev* __restrict__ runs, uint64_t stride, const uint64_t* __restrict__ counts,
-                                int n_runs, int bins, const uint32_t* __restrict__ gt, const uint32_t* __restrict__ pos0,
-                                FrzMatchDev* __restrict__ out) {
-    for (int r = 0; r < n_runs; r++) {
-        const FrzMatchDev* run = runs + (uint64_t)r * stride;
-        const uint64_t cnt = counts[r];
-        for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += (uint64_t)gridDim.x * blockDim.x) {
-            const FrzMatchDev m = run[i];
-            const uint32_t s = min((uint32_t)m.score, (uint32_t)bins - 1);
-            out[pos0[r * bins + s] + ((uint32_t)i - gt[r * bins + s])] = m;
-        }
+// One pass over the gathered runs: gridDim.y = n_runs rows of blocks, one row per run, so every run streams at
+// full width (the first version looped over the runs inside one grid: short runs left most blocks idle).
+__global__ void __launch_bounds__(256) k_merge_scatter(const FrzMatchDev* __restrict__ runs, uint64_t stride,
+                                                       const __grid_constant__ MergeMeta meta, int bins,
+                                                       const uint32_t* __restrict__ gt, const uint32_t* __restrict__ pos0,
+                                                       FrzMatchDev* __restrict__ out) {
+    const int r = blockIdx.y;
+    const FrzMatchDev* run = runs + (uint64_t)r * stride;
+    const uint64_t cnt = meta.counts[r];
+    const uint32_t* gtr = gt + (size_t)r * bins;
+    const uint32_t* p0r = pos0 + (size_t)r * bins;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += (uint64_t)gridDim.x * blockDim.x) {
+        const FrzMatchDev m = run[i];
+        const uint32_t s = min((uint32_t)m.score, (uint32_t)bins - 1);
+        out[p0r[s] + ((uint32_t)i - gtr[s])] = m;
     }
 }
 }  // namespace
@@ -1351,47 +1415,49 @@ extern "C" uint32_t frz_matcher_score_bound(const frz_matcher* m) {
     return (uint32_t)std::min<uint64_t>(b, 0xFFFF);
 }
 
-extern "C" frz_status frz_merge_runs_device(const frz_match* d_runs, uint64_t run_stride, const uint64_t* run_counts_host,
-                                            int n_runs, uint8_t sort, uint32_t score_bound_in, frz_match* d_out, int device, void* stream_) {
-    if (!d_runs || !run_counts_host || !d_out || n_runs <= 0 || n_runs > 64) return frz_fail(FRZ_ERR_INVALID_ARG, "bad argument");
-    FRZ_TRY(ensure_device(device));
-    cudaStream_t stream = (cudaStream_t)stream_;
+void FrzMergeScratch::release() {
+    if (device >= 0) cudaSetDevice(device);
+    cudaFree(hist); cudaFree(tables); cudaFree(cat); cudaFree(tmp); cudaFree(d_total);
+    hist = tables = nullptr; cat = tmp = nullptr; d_total = nullptr; cap = 0; device = -1;
+}
+
+// k_merge_matches_by on `stream` with caller-owned scratch (one per concurrent user; grow-only).
+frz_status frz_merge_runs_ex(FrzMergeScratch& ms, const FrzMatchDev* runs, uint64_t run_stride, const uint64_t* run_counts_host,
+                             int n_runs, uint8_t sort, uint32_t score_bound_in, FrzMatchDev* d_out, cudaStream_t stream) {
+    if (!runs || !run_counts_host || !d_out || n_runs <= 0 || n_runs > FRZ_MERGE_MAX_RUNS) return frz_fail(FRZ_ERR_INVALID_ARG, "bad argument");
     const bool reversed = sort == FRZ_SORT_INDEX_DESC || sort == FRZ_SORT_SCORE_THEN_INDEX_DESC;
     const bool by_score = sort == FRZ_SORT_SCORE_THEN_INDEX_ASC || sort == FRZ_SORT_SCORE_THEN_INDEX_DESC;
     const uint32_t score_bound = score_bound_in ? score_bound_in : 0xFFFF;
-    uint64_t h[2 * 64 + 1];
+    MergeMeta meta;
+    memset(&meta, 0, sizeof meta);
     uint64_t total = 0;
     for (int r = 0; r < n_runs; r++) {
-        h[r] = run_counts_host[r];
+        meta.counts[r] = run_counts_host[r];
         const int src_run = reversed ? n_runs - 1 - r : r;
-        h[64 + r] = total;
+        meta.bases[r] = total;
         total += run_counts_host[src_run];
     }
-    h[128] = total;
-    // grow-only per-device scratch (no allocation on the steady-state path)
-    struct MergeScratch { uint64_t* meta = nullptr; uint64_t* h_meta = nullptr; FrzMatchDev* cat = nullptr; FrzMatchDev* tmp = nullptr;
-                          uint32_t* hist = nullptr; uint32_t* tables = nullptr; uint64_t cap = 0; };
-    static MergeScratch scratch[64];
-    if (device >= 64) return frz_fail(FRZ_ERR_INVALID_ARG, "device index too large");
-    MergeScratch& ms = scratch[device];
-    if (!ms.meta) {
-        FRZ_CUDA_TRY(cudaMalloc(&ms.meta, sizeof h));
-        FRZ_CUDA_TRY(cudaMallocHost(&ms.h_meta, sizeof h));
+    meta.total = total;
+    if (ms.device < 0) {
+        int dev = 0;
+        FRZ_CUDA_TRY(cudaGetDevice(&dev));
         FRZ_CUDA_TRY(cudaMalloc(&ms.hist, frz_sort_hist_words() * sizeof(uint32_t)));
-        FRZ_CUDA_TRY(cudaMalloc(&ms.tables, (size_t)2 * 64 * kMergeMaxBins * sizeof(uint32_t)));
+        FRZ_CUDA_TRY(cudaMalloc(&ms.tables, (size_t)2 * FRZ_MERGE_MAX_RUNS * kMergeMaxBins * sizeof(uint32_t)));
+        FRZ_CUDA_TRY(cudaMalloc(&ms.d_total, sizeof(unsigned long long)));
+        ms.device = dev;
     }
-    memcpy(ms.h_meta, h, sizeof h);
-    FRZ_CUDA_TRY(cudaMemcpyAsync(ms.meta, ms.h_meta, sizeof h, cudaMemcpyHostToDevice, stream));
     const int bins = (int)std::min<uint32_t>(score_bound, 0xFFFFu) + 1;
+    if (total == 0) return FRZ_OK;
     if (by_score && bins <= kMergeMaxBins && total <= 0xFFFFFFFFull) {
         // score-sorted runs: boundaries by binary search, one scatter pass (no concatenation, no re-sort)
         uint32_t* gt = ms.tables;
-        uint32_t* pos0 = ms.tables + (size_t)64 * kMergeMaxBins;
-        const FrzMatchDev* runs = reinterpret_cast<const FrzMatchDev*>(d_runs);
-        k_merge_bounds<<<(n_runs * bins + 255) / 256, 256, 0, stream>>>(runs, run_stride, ms.meta, n_runs, bins, gt);
-        k_merge_bases<<<(bins + 127) / 128, 128, 0, stream>>>(gt, ms.meta, n_runs, bins, reversed ? 1 : 0, pos0);
-        k_merge_scatter<<<grid_for(total / std::max(n_runs, 1) + 1, 256), 256, 0, stream>>>(runs, run_stride, ms.meta, n_runs, bins, gt,
-                                                                                           pos0, reinterpret_cast<FrzMatchDev*>(d_out));
+        uint32_t* pos0 = ms.tables + (size_t)FRZ_MERGE_MAX_RUNS * kMergeMaxBins;
+        k_merge_bounds<<<(n_runs * bins + 255) / 256, 256, 0, stream>>>(runs, run_stride, meta, n_runs, bins, gt);
+        k_merge_bases<<<(bins + 127) / 128, 128, 0, stream>>>(gt, meta, n_runs, bins, reversed ? 1 : 0, pos0);
+        uint64_t longest = 0;
+        for (int r = 0; r < n_runs; r++) longest = std::max(longest, run_counts_host[r]);
+        const dim3 grid((unsigned)std::max<uint64_t>(1, std::min<uint64_t>((longest + 255) / 256, 148 * 8 / std::max(n_runs, 1) + 1)), (unsigned)n_runs);
+        k_merge_scatter<<<grid, 256, 0, stream>>>(runs, run_stride, meta, bins, gt, pos0, d_out);
         FRZ_CUDA_TRY(cudaGetLastError());
         return FRZ_OK;  // asynchronous on `stream`
     }
@@ -1402,17 +1468,30 @@ extern "C" frz_status frz_merge_runs_device(const frz_match* d_runs, uint64_t ru
         FRZ_CUDA_TRY(cudaMalloc(&ms.tmp, want * sizeof(FrzMatchDev)));
         ms.cap = want;
     }
-    FrzMatchDev* dst = by_score ? ms.cat : reinterpret_cast<FrzMatchDev*>(d_out);
-    k_gather_runs<<<grid_for(total / std::max(n_runs, 1) + 1, 256), 256, 0, stream>>>(
-        reinterpret_cast<const FrzMatchDev*>(d_runs), run_stride, ms.meta, ms.meta + 64, n_runs, reversed ? 1 : 0, dst);
+    FrzMatchDev* dst = by_score ? ms.cat : d_out;
+    k_gather_runs<<<grid_for(total / std::max(n_runs, 1) + 1, 256), 256, 0, stream>>>(runs, run_stride, meta, n_runs, reversed ? 1 : 0, dst,
+                                                                                     ms.d_total);
     if (by_score) {
         FrzWorkspace ws;  // only the sort scratch is used
         ws.sort_hist = ms.hist;
-        FRZ_TRY(frz_launch_sort_by_score_dev(ms.cat, ms.tmp, reinterpret_cast<FrzMatchDev*>(d_out),
-                                             reinterpret_cast<const unsigned long long*>(ms.meta + 128), score_bound, ws, stream, nullptr));
+        FRZ_TRY(frz_launch_sort_by_score_dev(ms.cat, ms.tmp, d_out, ms.d_total, score_bound, ws, stream, nullptr));
     }
     FRZ_CUDA_TRY(cudaGetLastError());
     return FRZ_OK;  // asynchronous on `stream`
+}
+
+extern "C" frz_status frz_merge_runs_device(const frz_match* d_runs, uint64_t run_stride, const uint64_t* run_counts_host,
+                                            int n_runs, uint8_t sort, uint32_t score_bound_in, frz_match* d_out, int device, void* stream_) {
+    if (!d_runs || !run_counts_host || !d_out || n_runs <= 0 || n_runs > FRZ_MERGE_MAX_RUNS) return frz_fail(FRZ_ERR_INVALID_ARG, "bad argument");
+    FRZ_TRY(ensure_device(device));
+    if (device >= 64) return frz_fail(FRZ_ERR_INVALID_ARG, "device index too large");
+    // grow-only per-device scratch (tables only: the run metadata travels as kernel parameters).  Calls for one device
+    // must be stream-ordered with each other, as documented in the header.
+    static FrzMergeScratch scratch[64];
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lock(mu);
+    return frz_merge_runs_ex(scratch[device], reinterpret_cast<const FrzMatchDev*>(d_runs), run_stride, run_counts_host, n_runs, sort,
+                             score_bound_in, reinterpret_cast<FrzMatchDev*>(d_out), (cudaStream_t)stream_);
 }
 
 extern "C" frz_status frz_radix_sort_matches(frz_match* matches, uint64_t n, int device) {

@@ -1,0 +1,723 @@
+// parallel.cu — Matcher::match_list_parallel (src/matcher/parallel.rs:18-89) across the GPUs of one node, behind
+// the C ABI (include/frz_cuda.h: frz_comm_*, frz_match_list_parallel*).
+//
+// Reference shape                                        here
+//   threads claim 2048-item chunks (parallel.rs:33-63)    GPUs own contiguous index-range shards
+//   matcher.clone() per thread (parallel.rs:46)           frz_matcher_clone per GPU, cached per communicator rank
+//   per-thread reverse + radix sort (parallel.rs:67-73)   frz_match_shard_device: the local run stays in HBM
+//   join, Vec<Vec<Match>> (parallel.rs:77)                ONE ncclAllGather of the runs padded to the longest
+//   k_merge_matches_by_* (src/k_merge.rs:90-131)          frz_merge_runs_ex on every GPU (bit-identical order)
+//   returned Vec<Match>                                   every GPU copies ITS slice of the merged list to the host
+//                                                         buffer: the D2H runs over all PCIe links at once
+//
+// The only per-step collective is that all-gather.  The match counts (the `Vec` lengths the k-merge reads) are
+// published by each GPU into a small pinned host block shared by all ranks — a 1-thread kernel right after the tile
+// scan, i.e. BEFORE the scoring kernels — and every rank's host thread polls the block; the same block carries the
+// "my slice has landed" flags that end a host-out step.  In the multi-process form the block (and the output
+// buffer) is a memfd segment that every rank maps and pins.
+//
+// NCCL is resolved with dlopen at the first multi-GPU use: the library itself has no NCCL link dependency, a
+// process that already carries PyTorch's libnccl.so.2 shares it, and single-GPU users never need it.
+#include <dlfcn.h>
+#include <fcntl.h>
+#include <nccl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <time.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <condition_variable>
+#include <functional>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "frz_device.cuh"
+#include "frz_host.h"
+
+#if defined(__x86_64__)
+#include <immintrin.h>
+#define FRZ_CPU_RELAX() _mm_pause()
+#else
+#define FRZ_CPU_RELAX() ((void)0)
+#endif
+
+namespace {
+
+// ------------------------------------------------------------------------------------- NCCL, loaded lazily
+struct NcclApi {
+    void* handle = nullptr;
+    std::string error;
+    decltype(&ncclGetUniqueId) GetUniqueId = nullptr;
+    decltype(&ncclCommInitRank) CommInitRank = nullptr;
+    decltype(&ncclCommInitAll) CommInitAll = nullptr;
+    decltype(&ncclCommDestroy) CommDestroy = nullptr;
+    decltype(&ncclAllGather) AllGather = nullptr;
+    decltype(&ncclGetErrorString) GetErrorString = nullptr;
+    decltype(&ncclGetVersion) GetVersion = nullptr;
+};
+
+NcclApi& nccl_api() {
+    static NcclApi api;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        const char* names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char* n : names) {
+            api.handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+            if (api.handle) break;
+        }
+        if (!api.handle) {
+            const char* e = dlerror();
+            api.error = std::string("cannot load libnccl.so.2: ") + (e ? e : "?");
+            return;
+        }
+        auto sym = [&](const char* name) -> void* {
+            void* p = dlsym(api.handle, name);
+            if (!p && api.error.empty()) api.error = std::string("libnccl lacks ") + name;
+            return p;
+        };
+        api.GetUniqueId = reinterpret_cast<decltype(api.GetUniqueId)>(sym("ncclGetUniqueId"));
+        api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(sym("ncclCommInitRank"));
+        api.CommInitAll = reinterpret_cast<decltype(api.CommInitAll)>(sym("ncclCommInitAll"));
+        api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(sym("ncclCommDestroy"));
+        api.AllGather = reinterpret_cast<decltype(api.AllGather)>(sym("ncclAllGather"));
+        api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(sym("ncclGetErrorString"));
+        api.GetVersion = reinterpret_cast<decltype(api.GetVersion)>(sym("ncclGetVersion"));
+    });
+    return api;
+}
+
+frz_status nccl_ready() {
+    NcclApi& a = nccl_api();
+    if (!a.handle || !a.error.empty()) return frz_fail(FRZ_ERR_NCCL, "%s", a.error.empty() ? "NCCL unavailable" : a.error.c_str());
+    return FRZ_OK;
+}
+
+#define FRZ_NCCL_TRY(expr)                                                                                       \
+    do {                                                                                                         \
+        ncclResult_t _r = (expr);                                                                                \
+        if (_r != ncclSuccess)                                                                                   \
+            return frz_fail(FRZ_ERR_NCCL, "%s failed: %s (%s:%d)", #expr, nccl_api().GetErrorString(_r), __FILE__, __LINE__); \
+    } while (0)
+
+// ------------------------------------------------------------------------- shared pinned host memory
+// A host allocation every rank's GPU can write.  Local form: cudaHostAlloc(portable | mapped).  Multi-process form:
+// rank 0 creates a memfd, the other ranks open it through /proc/<pid>/fd/<n>, everybody maps it MAP_SHARED and
+// registers the mapping with CUDA.  The (pid, fd) pair travels over the communicator itself.
+struct HostBlock {
+    void* ptr = nullptr;
+    uint64_t bytes = 0;
+    int fd = -1;          // memfd (owner) or the opened peer fd; -1 for cudaHostAlloc memory
+    bool registered = false;
+};
+
+constexpr uint64_t kCtrlBytes = 8192;
+constexpr int kMaxWorld = FRZ_MERGE_MAX_RUNS;   // 64
+// control block layout (uint64 words): [parity][rank] for each of the three flag families
+constexpr int kCtrlCount = 0;                   // (seq << 32) | match count of the rank's run
+constexpr int kCtrlDone = 2 * kMaxWorld;        // seq: the rank's slice of the merged list is in host memory
+constexpr int kCtrlBarrier = 4 * kMaxWorld;     // seq: frz_comm_barrier
+constexpr int kCtrlMeta = 6 * kMaxWorld;        // bootstrap words (pid, fd, bytes)
+
+__global__ void k_publish(volatile unsigned long long* slot, const unsigned long long* d_count, unsigned long long seq) {
+    const unsigned long long c = d_count ? *d_count : 0ull;
+    *slot = (seq << 32) | (c & 0xFFFFFFFFull);
+    __threadfence_system();
+}
+
+double now_s() {
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
+
+double poll_timeout_s() {
+    static double t = -1;
+    if (t < 0) { const char* e = getenv("FRZ_PARALLEL_TIMEOUT_S"); t = e ? atof(e) : 120.0; if (t <= 0) t = 120.0; }
+    return t;
+}
+
+// waits until every slot carries `seq` in its upper half; lower halves → vals (optional)
+frz_status wait_slots(const volatile uint64_t* slots, int world, uint64_t seq, uint64_t* vals, const char* what) {
+    const double t0 = now_s();
+    for (int r = 0; r < world; r++) {
+        uint32_t spins = 0;
+        for (;;) {
+            const uint64_t v = __atomic_load_n(const_cast<const uint64_t*>(slots + r), __ATOMIC_ACQUIRE);
+            if ((v >> 32) == (seq & 0xFFFFFFFFull)) { if (vals) vals[r] = v & 0xFFFFFFFFull; break; }
+            FRZ_CPU_RELAX();
+            if ((++spins & 0x3FFF) == 0 && now_s() - t0 > poll_timeout_s())
+                return frz_fail(FRZ_ERR_NCCL, "rank %d did not publish its %s within %.0f s (peer failed or ranks made different calls)", r, what,
+                                poll_timeout_s());
+        }
+    }
+    return FRZ_OK;
+}
+
+struct RankCtx {
+    int rank = 0;        // global rank
+    int device = 0;
+    ncclComm_t nccl = nullptr;
+    cudaStream_t side = nullptr;           // non-blocking: publishes the count while the main stream scores
+    frz_matcher* clone = nullptr;
+    uint64_t clone_epoch = 0;
+    FrzMatchDev* run = nullptr;            // this rank's locally ordered run
+    uint64_t run_cap = 0;
+    unsigned long long* d_count = nullptr;
+    FrzMatchDev* gathered = nullptr;
+    uint64_t gathered_cap = 0;
+    FrzMatchDev* merged = nullptr;
+    uint64_t merged_cap = 0;
+    FrzMergeScratch merge;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    bool ev_valid = false;
+    uint64_t* ctrl_dev = nullptr;          // device-side address of the shared control block
+};
+
+struct Worker {
+    std::thread th;
+    std::mutex mu;
+    std::condition_variable cv;
+    std::function<void()> job;
+    bool has_job = false, done = false, quit = false;
+};
+
+}  // namespace
+
+struct frz_comm {
+    int world = 1;
+    int rank = 0;                 // multi-process: this process's rank; local: 0
+    bool local_form = true;
+    bool force_nccl = false;      // test hook: FRZ_PARALLEL_FORCE_NCCL=1 runs the all-gather + merge even at world 1
+    std::vector<RankCtx> ranks;   // the ranks this process drives (local: all; multi-process: one)
+    std::vector<std::unique_ptr<Worker>> workers;   // local form, world > 1: one per GPU
+    HostBlock ctrl;
+    volatile uint64_t* ctrl_host = nullptr;
+    uint64_t seq = 0;             // step sequence number (identical on all ranks as long as they make the same calls)
+    uint64_t barrier_seq = 0;
+    uint64_t alloc_seq = 0;
+    std::vector<HostBlock> blocks;   // frz_comm_host_alloc
+    std::mutex mu;
+};
+
+namespace {
+
+frz_status set_device(int device) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return frz_fail(FRZ_ERR_NO_DEVICE, "no CUDA device available (%s); this library has no CPU fallback",
+                        e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    }
+    if (device < 0 || device >= n) return frz_fail(FRZ_ERR_INVALID_ARG, "device %d out of range (have %d)", device, n);
+    FRZ_CUDA_TRY(cudaSetDevice(device));
+    return FRZ_OK;
+}
+
+void rank_release(RankCtx& r) {
+    cudaSetDevice(r.device);
+    if (r.clone) frz_matcher_destroy(r.clone);
+    r.clone = nullptr;
+    cudaFree(r.run); cudaFree(r.d_count); cudaFree(r.gathered); cudaFree(r.merged);
+    r.run = nullptr; r.d_count = nullptr; r.gathered = nullptr; r.merged = nullptr;
+    r.merge.release();
+    for (auto& e : r.ev) { if (e) cudaEventDestroy(e); e = nullptr; }
+    if (r.side) cudaStreamDestroy(r.side);
+    r.side = nullptr;
+    if (r.nccl) nccl_api().CommDestroy(r.nccl);
+    r.nccl = nullptr;
+}
+
+frz_status rank_init(RankCtx& r) {
+    FRZ_TRY(set_device(r.device));
+    FRZ_CUDA_TRY(cudaStreamCreateWithFlags(&r.side, cudaStreamNonBlocking));
+    FRZ_CUDA_TRY(cudaMalloc(&r.d_count, 2 * sizeof(unsigned long long)));
+    FRZ_CUDA_TRY(cudaMemset(r.d_count, 0, 2 * sizeof(unsigned long long)));
+    for (auto& e : r.ev) FRZ_CUDA_TRY(cudaEventCreate(&e));
+    return FRZ_OK;
+}
+
+// ---- shared host blocks ----------------------------------------------------------------------------------
+void host_block_release(HostBlock& b) {
+    if (!b.ptr) return;
+    if (b.fd >= 0 || b.registered) {
+        if (b.registered) cudaHostUnregister(b.ptr);
+        munmap(b.ptr, b.bytes);
+        if (b.fd >= 0) close(b.fd);
+    } else {
+        cudaFreeHost(b.ptr);
+    }
+    b = HostBlock();
+}
+
+// exchange of a few host words between the ranks of a multi-process communicator, over NCCL (set-up time only)
+frz_status exchange_words(frz_comm* c, const uint64_t* mine, int n_words, uint64_t* all /* [world * n_words] */) {
+    RankCtx& r = c->ranks[0];
+    FRZ_TRY(set_device(r.device));
+    unsigned long long *d_in = nullptr, *d_out = nullptr;
+    frz_status st = [&]() -> frz_status {
+        FRZ_CUDA_TRY(cudaMalloc(&d_in, n_words * sizeof(uint64_t)));
+        FRZ_CUDA_TRY(cudaMalloc(&d_out, (size_t)c->world * n_words * sizeof(uint64_t)));
+        FRZ_CUDA_TRY(cudaMemcpyAsync(d_in, mine, n_words * sizeof(uint64_t), cudaMemcpyHostToDevice, r.side));
+        FRZ_NCCL_TRY(nccl_api().AllGather(d_in, d_out, (size_t)n_words, ncclUint64, r.nccl, r.side));
+        FRZ_CUDA_TRY(cudaMemcpyAsync(all, d_out, (size_t)c->world * n_words * sizeof(uint64_t), cudaMemcpyDeviceToHost, r.side));
+        FRZ_CUDA_TRY(cudaStreamSynchronize(r.side));
+        return FRZ_OK;
+    }();
+    cudaFree(d_in); cudaFree(d_out);
+    return st;
+}
+
+frz_status host_block_alloc(frz_comm* c, uint64_t bytes, HostBlock* out) {
+    HostBlock b;
+    bytes = (bytes + 4095) & ~4095ull;
+    if (bytes == 0) bytes = 4096;
+    b.bytes = bytes;
+    if (c->local_form) {
+        FRZ_TRY(set_device(c->ranks[0].device));
+        FRZ_CUDA_TRY(cudaHostAlloc(&b.ptr, bytes, cudaHostAllocPortable | cudaHostAllocMapped));
+        memset(b.ptr, 0, std::min<uint64_t>(bytes, kCtrlBytes));
+        *out = b;
+        return FRZ_OK;
+    }
+    // multi-process: rank 0 owns a memfd; every rank learns (pid, fd, status) from the exchange
+    uint64_t mine[3] = {0, 0, 0};
+    if (c->rank == 0) {
+        b.fd = memfd_create("frz_comm", MFD_CLOEXEC);
+        if (b.fd >= 0 && ftruncate(b.fd, (off_t)bytes) != 0) { close(b.fd); b.fd = -1; }
+        mine[0] = (uint64_t)getpid(); mine[1] = (uint64_t)(int64_t)b.fd; mine[2] = b.fd >= 0 ? 1 : 0;
+    }
+    std::vector<uint64_t> all((size_t)c->world * 3);
+    FRZ_TRY(exchange_words(c, mine, 3, all.data()));
+    if (all[2] != 1) { if (b.fd >= 0) close(b.fd); return frz_fail(FRZ_ERR_OOM, "rank 0 could not create a %llu-byte shared memory segment", (unsigned long long)bytes); }
+    if (c->rank != 0) {
+        char path[64];
+        snprintf(path, sizeof path, "/proc/%llu/fd/%lld", (unsigned long long)all[0], (long long)(int64_t)all[1]);
+        b.fd = open(path, O_RDWR | O_CLOEXEC);
+    }
+    uint64_t ok = b.fd >= 0 ? 1 : 0;
+    if (ok) {
+        b.ptr = mmap(nullptr, bytes, PROT_READ | PROT_WRITE, MAP_SHARED, b.fd, 0);
+        if (b.ptr == MAP_FAILED) { b.ptr = nullptr; ok = 0; }
+    }
+    if (ok) {
+        FRZ_TRY(set_device(c->ranks[0].device));
+        if (cudaHostRegister(b.ptr, bytes, cudaHostRegisterPortable | cudaHostRegisterMapped) == cudaSuccess) b.registered = true;
+        else { cudaGetLastError(); ok = 0; }
+    }
+    // everybody must agree before anybody uses it (and before rank 0 could drop the fd)
+    std::vector<uint64_t> oks(c->world);
+    FRZ_TRY(exchange_words(c, &ok, 1, oks.data()));
+    bool all_ok = true;
+    for (uint64_t v : oks) all_ok = all_ok && v == 1;
+    if (!all_ok) {
+        if (b.ptr) { if (b.registered) cudaHostUnregister(b.ptr); munmap(b.ptr, bytes); }
+        if (b.fd >= 0) close(b.fd);
+        return frz_fail(FRZ_ERR_OOM, "could not map and pin the %llu-byte shared host segment on every rank", (unsigned long long)bytes);
+    }
+    if (c->rank == 0) memset(b.ptr, 0, std::min<uint64_t>(bytes, kCtrlBytes));
+    FRZ_TRY(exchange_words(c, &ok, 1, oks.data()));   // barrier: the zeroing is visible before anybody polls
+    *out = b;
+    return FRZ_OK;
+}
+
+frz_status comm_finish_setup(frz_comm* c) {
+    { const char* e = getenv("FRZ_PARALLEL_FORCE_NCCL"); c->force_nccl = e && atoi(e) != 0; }
+    FRZ_TRY(host_block_alloc(c, kCtrlBytes, &c->ctrl));
+    c->ctrl_host = reinterpret_cast<volatile uint64_t*>(c->ctrl.ptr);
+    for (RankCtx& r : c->ranks) {
+        FRZ_TRY(set_device(r.device));
+        void* dp = nullptr;
+        FRZ_CUDA_TRY(cudaHostGetDevicePointer(&dp, c->ctrl.ptr, 0));
+        r.ctrl_dev = reinterpret_cast<uint64_t*>(dp);
+    }
+    return FRZ_OK;
+}
+
+void worker_main(Worker* w, int device) {
+    cudaSetDevice(device);
+    for (;;) {
+        std::function<void()> job;
+        {
+            std::unique_lock<std::mutex> lk(w->mu);
+            w->cv.wait(lk, [&] { return w->has_job || w->quit; });
+            if (w->quit) return;
+            job = std::move(w->job);
+            w->has_job = false;
+        }
+        job();
+        {
+            std::lock_guard<std::mutex> lk(w->mu);
+            w->done = true;
+        }
+        w->cv.notify_all();
+    }
+}
+
+// ------------------------------------------------------------------------------------------ one rank's step
+struct StepResult {
+    frz_status status = FRZ_OK;
+    std::string error;
+    uint64_t total = 0;
+    const FrzMatchDev* d_merged = nullptr;
+};
+
+// Everything one GPU does for one match_list_parallel call.  `seq` is the step number shared by all ranks.
+frz_status rank_step(frz_comm* c, RankCtx& r, frz_matcher* m, const frz_corpus* shard, uint32_t index_offset, uint64_t seq,
+                     frz_match* out_host, uint64_t cap, bool want_host, StepResult* res) {
+    FRZ_TRY(set_device(r.device));
+    cudaStream_t main = nullptr;   // the device's legacy default stream: ordered with the caller's own default-stream work
+    const int world = c->world;
+    const int parity = (int)(seq & 1);
+    if (!m || !shard) return frz_fail(FRZ_ERR_INVALID_ARG, "null argument");
+    if (frz_corpus_device(shard) != r.device)
+        return frz_fail(FRZ_ERR_INVALID_ARG, "shard of rank %d lives on device %d, the communicator expects device %d", r.rank,
+                        frz_corpus_device(shard), r.device);
+    if (!r.clone || r.clone_epoch != frz_matcher_epoch(m)) {   // parallel.rs:46 — `matcher.clone()` per worker
+        if (r.clone) frz_matcher_destroy(r.clone);
+        r.clone = nullptr;
+        FRZ_TRY(frz_matcher_clone(m, &r.clone));
+        r.clone_epoch = frz_matcher_epoch(m);
+    }
+    const uint64_t n_local = frz_corpus_len(shard);
+    if (r.run_cap < std::max<uint64_t>(n_local, 1)) {
+        cudaFree(r.run); r.run = nullptr; r.run_cap = 0;
+        const uint64_t want = std::max<uint64_t>(n_local, 1);
+        FRZ_CUDA_TRY(cudaMalloc(&r.run, want * sizeof(FrzMatchDev)));
+        r.run_cap = want;
+    }
+    FRZ_CUDA_TRY(cudaEventRecord(r.ev[0], main));
+    // ---- local pipeline (asynchronous): prefilter → count published → scoring → local order
+    FRZ_TRY(frz_match_shard_device(r.clone, shard, index_offset, reinterpret_cast<frz_match*>(r.run), r.run_cap,
+                                   reinterpret_cast<uint64_t*>(r.d_count), main));
+    FRZ_TRY(frz_matcher_wait_count(r.clone, r.side));
+    k_publish<<<1, 1, 0, r.side>>>(reinterpret_cast<volatile unsigned long long*>(r.ctrl_dev + kCtrlCount + parity * kMaxWorld + r.rank),
+                                   r.d_count, seq);
+    FRZ_CUDA_TRY(cudaGetLastError());
+    FRZ_CUDA_TRY(cudaEventRecord(r.ev[1], main));
+    // ---- the Vec lengths of all workers (k_merge.rs:96-104): polled from the shared block while the GPU scores
+    uint64_t counts[kMaxWorld];
+    FRZ_TRY(wait_slots(c->ctrl_host + kCtrlCount + parity * kMaxWorld, world, seq, counts, "match count"));
+    uint64_t stride = 1, total = 0;
+    for (int k = 0; k < world; k++) { stride = std::max(stride, counts[k]); total += counts[k]; }
+    res->total = total;
+    const bool collective = world > 1 || c->force_nccl;
+    const FrzMatchDev* d_final = r.run;
+    if (collective) {
+        if (r.run_cap < stride) {
+            // another rank's run is longer than this rank's whole shard (ceil partitioning leaves the last shard short, or
+            // empty): the all-gather reads `stride` elements from every rank, so move the run into a buffer that long
+            FrzMatchDev* bigger = nullptr;
+            FRZ_CUDA_TRY(cudaMalloc(&bigger, stride * sizeof(FrzMatchDev)));
+            FRZ_CUDA_TRY(cudaMemcpyAsync(bigger, r.run, counts[r.rank] * sizeof(FrzMatchDev), cudaMemcpyDeviceToDevice, main));
+            FRZ_CUDA_TRY(cudaStreamSynchronize(main));
+            cudaFree(r.run);
+            r.run = bigger;
+            r.run_cap = stride;
+        }
+        const uint64_t need = (uint64_t)world * stride;
+        if (r.gathered_cap < need) {
+            cudaFree(r.gathered); r.gathered = nullptr; r.gathered_cap = 0;
+            const uint64_t want = need + need / 4 + 1024;
+            FRZ_CUDA_TRY(cudaMalloc(&r.gathered, want * sizeof(FrzMatchDev)));
+            r.gathered_cap = want;
+        }
+        if (r.merged_cap < total) {
+            cudaFree(r.merged); r.merged = nullptr; r.merged_cap = 0;
+            const uint64_t want = total + total / 4 + 1024;
+            FRZ_CUDA_TRY(cudaMalloc(&r.merged, want * sizeof(FrzMatchDev)));
+            r.merged_cap = want;
+        }
+        // ---- THE collective: one all-gather of the per-shard (score, index) runs over NVLink
+        if (r.nccl) {
+            FRZ_NCCL_TRY(nccl_api().AllGather(r.run, r.gathered, (size_t)stride, ncclUint64, r.nccl, main));
+        } else {   // world 1 without a communicator (local form + force flag): the gather of one run is a copy
+            FRZ_CUDA_TRY(cudaMemcpyAsync(r.gathered, r.run, stride * sizeof(FrzMatchDev), cudaMemcpyDeviceToDevice, main));
+        }
+        // ---- k_merge_matches_by on this GPU
+        FRZ_TRY(frz_merge_runs_ex(r.merge, r.gathered, stride, counts, world, frz_matcher_sort(m), frz_matcher_score_bound(m), r.merged, main));
+        d_final = r.merged;
+    }
+    res->d_merged = d_final;
+    FRZ_CUDA_TRY(cudaEventRecord(r.ev[2], main));
+    if (want_host) {
+        if (total > cap) {   // every rank sees the same counts, so every rank takes this exit: no collective is left unbalanced
+            FRZ_CUDA_TRY(cudaStreamSynchronize(main));
+            return frz_fail(FRZ_ERR_CAPACITY, "output capacity %llu < %llu matches", (unsigned long long)cap, (unsigned long long)total);
+        }
+        if (total && !out_host) return frz_fail(FRZ_ERR_INVALID_ARG, "null out");
+        // this rank's slice of the merged list → host (all ranks hold the whole list: the copy uses every PCIe link)
+        const uint64_t lo = total * (uint64_t)r.rank / (uint64_t)world, hi = total * (uint64_t)(r.rank + 1) / (uint64_t)world;
+        if (hi > lo)
+            FRZ_CUDA_TRY(cudaMemcpyAsync(out_host + lo, d_final + lo, (hi - lo) * sizeof(FrzMatchDev), cudaMemcpyDeviceToHost, main));
+    }
+    FRZ_CUDA_TRY(cudaEventRecord(r.ev[3], main));
+    r.ev_valid = true;
+    if (want_host && !c->local_form && world > 1) {
+        // "my slice has landed", stream-ordered after the copy; the call returns once every rank has said so
+        k_publish<<<1, 1, 0, main>>>(reinterpret_cast<volatile unsigned long long*>(r.ctrl_dev + kCtrlDone + parity * kMaxWorld + r.rank), nullptr, seq);
+        FRZ_CUDA_TRY(cudaGetLastError());
+    }
+    FRZ_CUDA_TRY(cudaStreamSynchronize(main));
+    if (want_host && !c->local_form && world > 1)
+        FRZ_TRY(wait_slots(c->ctrl_host + kCtrlDone + parity * kMaxWorld, world, seq, nullptr, "copy-out flag"));
+    return FRZ_OK;
+}
+
+void run_job(frz_comm* c, RankCtx& r, frz_matcher* m, const frz_corpus* shard, uint32_t offset, uint64_t seq, frz_match* out,
+             uint64_t cap, bool want_host, StepResult* res) {
+    res->status = rank_step(c, r, m, shard, offset, seq, out, cap, want_host, res);
+    if (res->status != FRZ_OK) res->error = frz_last_error();
+}
+
+}  // namespace
+
+// ================================================================================================ C ABI
+
+extern "C" frz_status frz_comm_unique_id(uint8_t id[FRZ_UNIQUE_ID_BYTES]) {
+    if (!id) return frz_fail(FRZ_ERR_INVALID_ARG, "null id");
+    FRZ_TRY(nccl_ready());
+    static_assert(sizeof(ncclUniqueId) == FRZ_UNIQUE_ID_BYTES, "ncclUniqueId size");
+    ncclUniqueId u;
+    FRZ_NCCL_TRY(nccl_api().GetUniqueId(&u));
+    memcpy(id, &u, sizeof u);
+    return FRZ_OK;
+}
+
+extern "C" void frz_comm_destroy(frz_comm* c) {
+    if (!c) return;
+    for (auto& w : c->workers) {
+        { std::lock_guard<std::mutex> lk(w->mu); w->quit = true; }
+        w->cv.notify_all();
+        if (w->th.joinable()) w->th.join();
+    }
+    for (HostBlock& b : c->blocks) host_block_release(b);
+    host_block_release(c->ctrl);
+    for (RankCtx& r : c->ranks) rank_release(r);
+    delete c;
+}
+
+extern "C" frz_status frz_comm_create_local(int n_gpus, const int* devices, frz_comm** out) {
+    if (!out) return frz_fail(FRZ_ERR_INVALID_ARG, "null out");
+    if (n_gpus <= 0) return frz_fail(FRZ_ERR_THREADS_ZERO, "threads must be positive");   // parallel.rs:24
+    if (n_gpus > kMaxWorld) return frz_fail(FRZ_ERR_INVALID_ARG, "at most %d GPUs per communicator", kMaxWorld);
+    std::unique_ptr<frz_comm, void (*)(frz_comm*)> c(new frz_comm(), frz_comm_destroy);
+    c->world = n_gpus;
+    c->local_form = true;
+    c->ranks.resize(n_gpus);
+    std::vector<int> devs(n_gpus);
+    for (int g = 0; g < n_gpus; g++) {
+        devs[g] = devices ? devices[g] : g;
+        for (int h = 0; h < g; h++)
+            if (devs[h] == devs[g]) return frz_fail(FRZ_ERR_INVALID_ARG, "device %d listed twice", devs[g]);
+        c->ranks[g].rank = g;
+        c->ranks[g].device = devs[g];
+        FRZ_TRY(rank_init(c->ranks[g]));
+    }
+    if (n_gpus > 1) {
+        FRZ_TRY(nccl_ready());
+        std::vector<ncclComm_t> comms(n_gpus);
+        FRZ_NCCL_TRY(nccl_api().CommInitAll(comms.data(), n_gpus, devs.data()));
+        for (int g = 0; g < n_gpus; g++) c->ranks[g].nccl = comms[g];
+    }
+    FRZ_TRY(comm_finish_setup(c.get()));
+    if (n_gpus > 1) {
+        for (int g = 0; g < n_gpus; g++) {
+            c->workers.emplace_back(new Worker());
+            Worker* w = c->workers.back().get();
+            w->th = std::thread(worker_main, w, devs[g]);
+        }
+    }
+    *out = c.release();
+    return FRZ_OK;
+}
+
+extern "C" frz_status frz_comm_create_rank(const uint8_t id[FRZ_UNIQUE_ID_BYTES], int world, int rank, int device, frz_comm** out) {
+    if (!out || !id) return frz_fail(FRZ_ERR_INVALID_ARG, "null argument");
+    if (world <= 0) return frz_fail(FRZ_ERR_THREADS_ZERO, "threads must be positive");
+    if (world > kMaxWorld || rank < 0 || rank >= world) return frz_fail(FRZ_ERR_INVALID_ARG, "bad world/rank %d/%d", rank, world);
+    FRZ_TRY(nccl_ready());
+    std::unique_ptr<frz_comm, void (*)(frz_comm*)> c(new frz_comm(), frz_comm_destroy);
+    c->world = world;
+    c->rank = rank;
+    c->local_form = false;
+    c->ranks.resize(1);
+    c->ranks[0].rank = rank;
+    c->ranks[0].device = device;
+    FRZ_TRY(rank_init(c->ranks[0]));
+    ncclUniqueId u;
+    memcpy(&u, id, sizeof u);
+    FRZ_NCCL_TRY(nccl_api().CommInitRank(&c->ranks[0].nccl, world, u, rank));
+    FRZ_TRY(comm_finish_setup(c.get()));
+    *out = c.release();
+    return FRZ_OK;
+}
+
+extern "C" int frz_comm_world(const frz_comm* c) { return c ? c->world : 0; }
+extern "C" int frz_comm_rank(const frz_comm* c) { return c ? c->rank : -1; }
+extern "C" int frz_comm_device(const frz_comm* c, int i) { return (c && i >= 0 && i < (int)c->ranks.size()) ? c->ranks[i].device : -1; }
+
+extern "C" frz_status frz_comm_host_alloc(frz_comm* c, uint64_t bytes, void** out) {
+    if (!c || !out) return frz_fail(FRZ_ERR_INVALID_ARG, "null argument");
+    HostBlock b;
+    FRZ_TRY(host_block_alloc(c, bytes, &b));
+    c->blocks.push_back(b);
+    *out = b.ptr;
+    return FRZ_OK;
+}
+
+extern "C" frz_status frz_comm_host_free(frz_comm* c, void* p) {
+    if (!c || !p) return FRZ_OK;
+    for (size_t i = 0; i < c->blocks.size(); i++)
+        if (c->blocks[i].ptr == p) {
+            for (RankCtx& r : c->ranks) { cudaSetDevice(r.device); cudaDeviceSynchronize(); }
+            host_block_release(c->blocks[i]);
+            c->blocks.erase(c->blocks.begin() + (long)i);
+            return FRZ_OK;
+        }
+    return frz_fail(FRZ_ERR_INVALID_ARG, "pointer was not allocated by frz_comm_host_alloc on this communicator");
+}
+
+extern "C" frz_status frz_comm_barrier(frz_comm* c) {
+    if (!c) return frz_fail(FRZ_ERR_INVALID_ARG, "null communicator");
+    if (c->local_form || c->world == 1) return FRZ_OK;
+    const uint64_t seq = ++c->barrier_seq;
+    const int parity = (int)(seq & 1);
+    volatile uint64_t* slots = c->ctrl_host + kCtrlBarrier + parity * kMaxWorld;
+    __atomic_store_n(const_cast<uint64_t*>(slots + c->rank), seq << 32, __ATOMIC_RELEASE);
+    return wait_slots(slots, c->world, seq, nullptr, "barrier flag");
+}
+
+extern "C" frz_status frz_corpus_create_sharded(const uint8_t* bytes, const void* offsets, int offset_width, uint64_t n, frz_comm* c,
+                                                frz_corpus** shards_out) {
+    if (!c || !shards_out || !offsets) return frz_fail(FRZ_ERR_INVALID_ARG, "null argument");
+    if (!c->local_form) return frz_fail(FRZ_ERR_INVALID_ARG, "frz_corpus_create_sharded needs a local (single-process) communicator");
+    if (offset_width != 4 && offset_width != 8) return frz_fail(FRZ_ERR_INVALID_ARG, "offset_width must be 4 or 8");
+    if (n > 0xFFFFFFFFull) return frz_fail(FRZ_ERR_TOO_MANY_ITEMS, "too many items in haystack, will overflow the u32 index: %llu", (unsigned long long)n);
+    const int world = c->world;
+    const uint64_t per = (n + world - 1) / world;   // shard g = [g * ceil(N/G), (g+1) * ceil(N/G))   
+    for (int g = 0; g < world; g++) shards_out[g] = nullptr;
+    for (int g = 0; g < world; g++) {
+        const uint64_t lo = std::min<uint64_t>((uint64_t)g * per, n), hi = std::min<uint64_t>((uint64_t)(g + 1) * per, n);
+        // an Arrow slice: the offsets pointer moves, the value buffer does not (offsets stay absolute)
+        const void* off_g = static_cast<const uint8_t*>(offsets) + lo * (uint64_t)offset_width;
+        frz_status s = frz_corpus_create_arrow(bytes, off_g, offset_width, hi - lo, c->ranks[g].device, &shards_out[g]);
+        if (s != FRZ_OK) {
+            for (int h = 0; h < g; h++) { frz_corpus_destroy(shards_out[h]); shards_out[h] = nullptr; }
+            return s;
+        }
+    }
+    return FRZ_OK;
+}
+
+extern "C" frz_status frz_match_list_parallel(frz_matcher* m, const frz_corpus* const* shards, int n_shards, frz_comm* c, frz_match* out,
+                                              uint64_t cap, uint64_t* n_out) {
+    if (!m || !c || !shards) return frz_fail(FRZ_ERR_INVALID_ARG, "null argument");
+    if (!c->local_form) return frz_fail(FRZ_ERR_INVALID_ARG, "multi-process communicator: call frz_match_list_parallel_rank on every rank");
+    if (n_shards != c->world) return frz_fail(FRZ_ERR_INVALID_ARG, "%d shards for a communicator of %d GPUs", n_shards, c->world);
+    std::lock_guard<std::mutex> lock(c->mu);
+    uint64_t offs[kMaxWorld], total_items = 0;
+    for (int g = 0; g < n_shards; g++) {
+        if (!shards[g]) return frz_fail(FRZ_ERR_INVALID_ARG, "null shard %d", g);
+        offs[g] = total_items;
+        total_items += frz_corpus_len(shards[g]);
+    }
+    // Matcher::guard_against_haystack_overflow (src/matcher/mod.rs:438-446)
+    if (total_items > 0xFFFFFFFFull)
+        return frz_fail(FRZ_ERR_TOO_MANY_ITEMS, "too many items in haystack, will overflow the u32 index: %llu > %u (index offset: 0)",
+                        (unsigned long long)total_items, 0xFFFFFFFFu);
+    const uint64_t seq = ++c->seq;
+    std::vector<StepResult> res(c->world);
+    if (c->world == 1) {
+        run_job(c, c->ranks[0], m, shards[0], 0, seq, out, cap, true, &res[0]);
+    } else {
+        for (int g = 0; g < c->world; g++) {
+            Worker* w = c->workers[g].get();
+            {
+                std::lock_guard<std::mutex> lk(w->mu);
+                w->job = [c, g, m, shards, &offs, seq, out, cap, &res] {
+                    run_job(c, c->ranks[g], m, shards[g], (uint32_t)offs[g], seq, out, cap, true, &res[g]);
+                };
+                w->done = false;
+                w->has_job = true;
+            }
+            w->cv.notify_all();
+        }
+        for (int g = 0; g < c->world; g++) {
+            Worker* w = c->workers[g].get();
+            std::unique_lock<std::mutex> lk(w->mu);
+            w->cv.wait(lk, [&] { return w->done; });
+        }
+    }
+    if (n_out) *n_out = res[0].total;
+    for (int g = 0; g < c->world; g++)
+        if (res[g].status != FRZ_OK) return frz_fail(res[g].status, "GPU %d: %s", c->ranks[g].device, res[g].error.c_str());
+    return FRZ_OK;
+}
+
+extern "C" frz_status frz_match_list_parallel_rank(frz_matcher* m, const frz_corpus* shard, uint32_t index_offset, frz_comm* c, frz_match* out,
+                                                   uint64_t cap, uint64_t* n_out, const frz_match** d_out) {
+    if (!m || !c || !shard) return frz_fail(FRZ_ERR_INVALID_ARG, "null argument");
+    if (c->local_form && c->world != 1) return frz_fail(FRZ_ERR_INVALID_ARG, "local communicator: call frz_match_list_parallel");
+    if ((uint64_t)index_offset + frz_corpus_len(shard) > 0xFFFFFFFFull)
+        return frz_fail(FRZ_ERR_TOO_MANY_ITEMS, "too many items in haystack, will overflow the u32 index: %llu > %u (index offset: %u)",
+                        (unsigned long long)index_offset + frz_corpus_len(shard), 0xFFFFFFFFu, index_offset);
+    std::lock_guard<std::mutex> lock(c->mu);
+    const uint64_t seq = ++c->seq;
+    StepResult res;
+    const bool want_host = out != nullptr || cap != 0;
+    const frz_status s = rank_step(c, c->ranks[0], m, shard, index_offset, seq, out, cap, want_host, &res);
+    if (n_out) *n_out = res.total;
+    if (d_out) *d_out = reinterpret_cast<const frz_match*>(res.d_merged);
+    return s;
+}
+
+// End to end on one rank: the shard arrives as HOST Arrow buffers (streamed H2D + pack into the clone's reusable arena),
+// then the collective match.  The ingest is asynchronous on the same stream as the local pipeline.
+extern "C" frz_status frz_match_list_parallel_rank_host(frz_matcher* m, const uint8_t* bytes, const void* offsets, int offset_width, uint64_t n,
+                                                        uint32_t index_offset, frz_comm* c, frz_match* out, uint64_t cap, uint64_t* n_out) {
+    if (!m || !c || !offsets) return frz_fail(FRZ_ERR_INVALID_ARG, "null argument");
+    if (c->local_form && c->world != 1) return frz_fail(FRZ_ERR_INVALID_ARG, "local communicator: shard with frz_corpus_create_sharded and call frz_match_list_parallel");
+    if ((uint64_t)index_offset + n > 0xFFFFFFFFull)
+        return frz_fail(FRZ_ERR_TOO_MANY_ITEMS, "too many items in haystack, will overflow the u32 index: %llu > %u (index offset: %u)",
+                        (unsigned long long)index_offset + n, 0xFFFFFFFFu, index_offset);
+    std::lock_guard<std::mutex> lock(c->mu);
+    RankCtx& r = c->ranks[0];
+    FRZ_TRY(set_device(r.device));
+    if (!r.clone || r.clone_epoch != frz_matcher_epoch(m)) {
+        if (r.clone) frz_matcher_destroy(r.clone);
+        r.clone = nullptr;
+        FRZ_TRY(frz_matcher_clone(m, &r.clone));
+        r.clone_epoch = frz_matcher_epoch(m);
+    }
+    const frz_corpus* shard = nullptr;
+    FRZ_TRY(frz_matcher_ingest_e2e(r.clone, bytes, offsets, offset_width, n, r.device, &shard));
+    const uint64_t seq = ++c->seq;
+    StepResult res;
+    const frz_status s = rank_step(c, r, m, shard, index_offset, seq, out, cap, true, &res);
+    if (n_out) *n_out = res.total;
+    return s;
+}
+
+extern "C" frz_status frz_comm_last_timings(frz_comm* c, int local_index, float* ms4, const frz_matcher** clone) {
+    if (!c || local_index < 0 || local_index >= (int)c->ranks.size()) return frz_fail(FRZ_ERR_INVALID_ARG, "bad argument");
+    RankCtx& r = c->ranks[local_index];
+    if (clone) *clone = r.clone;
+    if (ms4) {
+        ms4[0] = ms4[1] = ms4[2] = ms4[3] = 0;
+        if (r.ev_valid) {
+            FRZ_TRY(set_device(r.device));
+            FRZ_CUDA_TRY(cudaEventSynchronize(r.ev[3]));
+            cudaEventElapsedTime(&ms4[0], r.ev[0], r.ev[1]);
+            cudaEventElapsedTime(&ms4[1], r.ev[1], r.ev[2]);
+            cudaEventElapsedTime(&ms4[2], r.ev[2], r.ev[3]);
+            cudaEventElapsedTime(&ms4[3], r.ev[0], r.ev[3]);
+            cudaGetLastError();
+        }
+    }
+    return FRZ_OK;
+}

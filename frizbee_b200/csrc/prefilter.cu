@@ -738,7 +738,7 @@ __global__ void __launch_bounds__(128) k_match_indices(const FrzCorpusView cv, c
         FrzMatchDev m;
         m.index = idx; m.score = (uint16_t)score; m.exact = exact ? 1 : 0; m.pad = 0;
         out_matches[j] = m;
-        out_cnt[j] = (uint32_t)(cnt < (int)stride ? cnt : (int)stride);
+        out_cnt[j] = (uint32_t)cnt;   // untruncated (only the first `stride` offsets were stored)
     }
 }
 

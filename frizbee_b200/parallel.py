@@ -1,22 +1,195 @@
-"""Multi-GPU `match_list_parallel` (src/matcher/parallel.rs:18-89): one process per GPU, the haystack
-list sharded by contiguous index range (shard g holds indices [offset_g, offset_g + n_g)), each rank
-scores its shard into a locally ordered run that stays in HBM, one NCCL all-gather moves the runs,
-and a device merge reproduces the reference's k-way merge (src/k_merge.rs:90-131) bit for bit.
+"""Multi-GPU `match_list_parallel` (src/matcher/parallel.rs:18-89) — ctypes callers of the C ABI.
 
-torch / torch.distributed are plumbing here (device buffers, NCCL); the compute is the C ABI.
-The shard/merge host logic is backend-agnostic and is covered on CPU with gloo (tests/test_parallel_gloo.py)
-by substituting the run producer.
+The path itself lives in the library (frizbee_b200/csrc/parallel.cu): a communicator (`frz_comm`), one clone of the
+matcher per GPU, the haystack list sharded by contiguous index range (shard g holds indices [offset_g, offset_g + n_g)),
+each GPU's locally ordered run kept in HBM, ONE ncclAllGather of the runs, the k-way merge (src/k_merge.rs:90-131) on
+every GPU, every GPU copying its slice of the merged list to the host buffer.  This module only wraps the entry points:
+
+  Comm.local(n_gpus)                       single process driving n GPUs (what a Rust caller does)
+  Comm.from_torch_distributed(device)      one rank per process (torchrun); torch.distributed only ships the 128-byte id
+  comm.match_list_parallel(matcher, shards)            frz_match_list_parallel
+  comm.match_list_parallel_rank(matcher, shard, off)   frz_match_list_parallel_rank
+
+The numpy helpers at the bottom (shard_bounds, merge_runs_host, all_gather_runs, match_list_parallel_host) are the
+host-side SPECIFICATION of the shard/merge logic; the world-size-2 gloo tests (tests/test_parallel_gloo.py) run them on
+CPU with the oracle as the run producer.
 """
 from __future__ import annotations
 
 import ctypes as C
-from typing import Callable, List, Optional, Tuple
+from typing import List, Optional, Sequence, Tuple
 
 import numpy as np
 
-from . import MATCH_DTYPE, Corpus, FrizbeeError, Matcher, _check, lib
+from . import MATCH_DTYPE, Corpus, FrizbeeError, Matcher, _arrow_offsets, _check, lib
 from .types import SortStrategy
 
+UNIQUE_ID_BYTES = 128
+
+
+def _bind(L):
+    if getattr(L, "_frz_parallel_bound", False):
+        return L
+    vp, u64, u32 = C.c_void_p, C.c_uint64, C.c_uint32
+    L.frz_comm_create_local.argtypes = [C.c_int, vp, C.POINTER(vp)]
+    L.frz_comm_unique_id.argtypes = [vp]
+    L.frz_comm_create_rank.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]
+    L.frz_comm_destroy.argtypes = [vp]
+    L.frz_comm_destroy.restype = None
+    L.frz_comm_world.argtypes = [vp]
+    L.frz_comm_rank.argtypes = [vp]
+    L.frz_comm_device.argtypes = [vp, C.c_int]
+    L.frz_comm_host_alloc.argtypes = [vp, u64, C.POINTER(vp)]
+    L.frz_comm_host_free.argtypes = [vp, vp]
+    L.frz_comm_barrier.argtypes = [vp]
+    L.frz_corpus_create_sharded.argtypes = [vp, vp, C.c_int, u64, vp, C.POINTER(vp)]
+    L.frz_match_list_parallel.argtypes = [vp, C.POINTER(vp), C.c_int, vp, vp, u64, C.POINTER(u64)]
+    L.frz_match_list_parallel_rank.argtypes = [vp, vp, u32, vp, vp, u64, C.POINTER(u64), C.POINTER(vp)]
+    L.frz_match_list_parallel_rank_host.argtypes = [vp, vp, vp, C.c_int, u64, u32, vp, vp, u64, C.POINTER(u64)]
+    L.frz_comm_last_timings.argtypes = [vp, C.c_int, C.POINTER(C.c_float), C.POINTER(vp)]
+    L.frz_matcher_clone.argtypes = [vp, C.POINTER(vp)]
+    L._frz_parallel_bound = True
+    return L
+
+
+def plib():
+    return _bind(lib())
+
+
+class Comm:
+    """`frz_comm`: the GPUs one match_list_parallel call runs on."""
+
+    def __init__(self, handle, world: int, rank: int, local_form: bool):
+        self._h, self.world, self.rank, self.local_form = handle, world, rank, local_form
+
+    @classmethod
+    def local(cls, n_gpus: int, devices: Optional[Sequence[int]] = None) -> "Comm":
+        h = C.c_void_p()
+        arr = (C.c_int * n_gpus)(*devices) if devices is not None else None
+        _check(plib().frz_comm_create_local(n_gpus, arr, C.byref(h)))
+        return cls(h, n_gpus, 0, True)
+
+    @staticmethod
+    def unique_id() -> bytes:
+        buf = (C.c_uint8 * UNIQUE_ID_BYTES)()
+        _check(plib().frz_comm_unique_id(buf))
+        return bytes(buf)
+
+    @classmethod
+    def from_rank(cls, unique_id: bytes, world: int, rank: int, device: int) -> "Comm":
+        h = C.c_void_p()
+        buf = (C.c_uint8 * UNIQUE_ID_BYTES).from_buffer_copy(unique_id)
+        _check(plib().frz_comm_create_rank(buf, world, rank, device, C.byref(h)))
+        return cls(h, world, rank, False)
+
+    @classmethod
+    def from_torch_distributed(cls, device: int, group=None) -> "Comm":
+        """One rank per process: rank 0 draws the NCCL unique id, torch.distributed broadcasts its 128 bytes (the only
+        thing torch.distributed does for the data path), every rank joins."""
+        import torch
+        import torch.distributed as dist
+        if not dist.is_initialized():
+            return cls.from_rank(cls.unique_id(), 1, 0, device)
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        on_gpu = dist.get_backend(group) == "nccl"
+        t = torch.zeros(UNIQUE_ID_BYTES, dtype=torch.uint8, device=torch.device("cuda", device) if on_gpu else "cpu")
+        if rank == 0:
+            t.copy_(torch.frombuffer(bytearray(cls.unique_id()), dtype=torch.uint8))
+        dist.broadcast(t, 0, group=group)
+        return cls.from_rank(bytes(t.cpu().numpy().tobytes()), world, rank, device)
+
+    # ---- shared pinned host memory ----
+    def host_alloc_matches(self, n: int) -> np.ndarray:
+        """A MATCH_DTYPE array in host memory every rank's GPU can write (multi-process: one shared segment; collective)."""
+        p = C.c_void_p()
+        n = max(int(n), 1)
+        _check(plib().frz_comm_host_alloc(self._h, n * MATCH_DTYPE.itemsize, C.byref(p)))
+        buf = (C.c_uint8 * (n * MATCH_DTYPE.itemsize)).from_address(p.value)   # memory owned by the communicator
+        return np.frombuffer(buf, dtype=MATCH_DTYPE)
+
+    def host_free(self, arr: np.ndarray):
+        _check(plib().frz_comm_host_free(self._h, arr.ctypes.data))
+
+    def barrier(self):
+        _check(plib().frz_comm_barrier(self._h))
+
+    def device(self, local_index: int = 0) -> int:
+        return plib().frz_comm_device(self._h, local_index)
+
+    # ---- sharding (local form) ----
+    def shard_arrow(self, data: np.ndarray, offsets: np.ndarray) -> List[Corpus]:
+        data = np.ascontiguousarray(data, dtype=np.uint8)
+        offsets, width = _arrow_offsets(offsets)
+        n = len(offsets) - 1
+        hs = (C.c_void_p * self.world)()
+        _check(plib().frz_corpus_create_sharded(data.ctypes.data if data.size else None, offsets.ctypes.data, width, n, self._h, hs))
+        bounds = shard_bounds(n, self.world)
+        return [Corpus(C.c_void_p(hs[g]), hi - lo) for g, (lo, hi) in enumerate(bounds)]
+
+    # ---- match_list_parallel ----
+    def match_list_parallel(self, matcher: Matcher, shards: Sequence[Corpus], out: Optional[np.ndarray] = None) -> np.ndarray:
+        """Local form (frz_match_list_parallel): shards[g] on the communicator's g-th GPU.  Returns the ordered matches."""
+        total = sum(len(s) for s in shards)
+        if out is None:
+            out = np.empty(max(total, 1), dtype=MATCH_DTYPE)
+        hs = (C.c_void_p * len(shards))(*[s._h for s in shards])
+        n = C.c_uint64()
+        _check(plib().frz_match_list_parallel(matcher._h, hs, len(shards), self._h, out.ctypes.data, len(out), C.byref(n)))
+        return out[: n.value]
+
+    def match_list_parallel_rank(self, matcher: Matcher, shard: Corpus, index_offset: int, out: Optional[np.ndarray] = None
+                                 ) -> Tuple[int, int]:
+        """Multi-process form (frz_match_list_parallel_rank), collective.  `out`: the SHARED host array from
+        host_alloc_matches (every rank passes its mapping) or None for a device-only result.
+        Returns (total matches, device pointer of this rank's merged list)."""
+        n = C.c_uint64()
+        d = C.c_void_p()
+        _check(plib().frz_match_list_parallel_rank(matcher._h, shard._h, index_offset, self._h,
+                                                   out.ctypes.data if out is not None else None,
+                                                   len(out) if out is not None else 0, C.byref(n), C.byref(d)))
+        return n.value, d.value or 0
+
+    def match_list_parallel_rank_host(self, matcher: Matcher, data: np.ndarray, offsets: np.ndarray, index_offset: int,
+                                      out: np.ndarray) -> int:
+        """End to end on one rank: this rank's shard arrives as HOST Arrow buffers (streamed H2D + pack), then the parallel
+        match; the merged list lands in the shared host array.  Collective."""
+        if offsets.dtype.itemsize == 4 and offsets.flags.c_contiguous:
+            width = 4
+        else:
+            offsets, width = _arrow_offsets(offsets)
+        n = C.c_uint64()
+        _check(plib().frz_match_list_parallel_rank_host(matcher._h, data.ctypes.data if data.size else None, offsets.ctypes.data,
+                                                        width, len(offsets) - 1, index_offset, self._h, out.ctypes.data, len(out),
+                                                        C.byref(n)))
+        return n.value
+
+    def last_timings(self, local_index: int = 0) -> dict:
+        """Device timings of the last parallel call on one local rank + the per-stage timings of the clone that ran it."""
+        ms = (C.c_float * 4)()
+        clone = C.c_void_p()
+        _check(plib().frz_comm_last_timings(self._h, local_index, ms, C.byref(clone)))
+        r = {"local_ms": ms[0], "gather_merge_ms": ms[1], "d2h_ms": ms[2], "total_ms": ms[3]}
+        if clone.value:
+            st = (C.c_float * 4)()
+            launches = C.c_uint64()
+            _check(lib().frz_matcher_last_timings(clone, st, C.byref(launches)))
+            r.update(prefilter_ms=st[0], sw_ms=st[1], sort_ms=st[2], pipeline_ms=st[3], launches=launches.value)
+        return r
+
+    def close(self):
+        if getattr(self, "_h", None):
+            plib().frz_comm_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+# ------------------------------------------------------------------------------------------------------------
+# Host-side specification of the shard / merge logic (numpy; used by the gloo tests and as the checker of the device merge)
 
 def shard_bounds(n: int, world: int) -> List[Tuple[int, int]]:
     """Contiguous index ranges, shard g = [g*ceil(n/world), ...)."""
@@ -25,8 +198,8 @@ def shard_bounds(n: int, world: int) -> List[Tuple[int, int]]:
 
 
 def merge_runs_host(runs: List[np.ndarray], sort: SortStrategy) -> np.ndarray:
-    """Reference semantics of k_merge_matches_by_* on host arrays (used by the gloo tests and as the
-    specification of the device merge): runs are index-range shards in rank order, each ordered per `sort`."""
+    """Reference semantics of k_merge_matches_by_* on host arrays: runs are index-range shards in rank order, each
+    ordered per `sort`."""
     if not runs:
         return np.zeros(0, dtype=MATCH_DTYPE)
     cat = np.concatenate(runs[::-1] if sort.is_reversed() else runs)
@@ -37,9 +210,8 @@ def merge_runs_host(runs: List[np.ndarray], sort: SortStrategy) -> np.ndarray:
 
 
 def all_gather_runs(run, count: int, group=None):
-    """The collective step, backend-agnostic (NCCL on device tensors, gloo on CPU tensors): one all-gather of the
-    counts and ONE all-gather of the runs padded to the longest.  `run` is a 1-D int64 tensor of 8-byte match records.
-    Returns (gathered [world * stride], counts list, stride)."""
+    """The collective step on torch tensors (gloo on CPU in the tests): the counts, then ONE all-gather of the runs padded
+    to the longest.  `run` is a 1-D int64 tensor of 8-byte match records.  Returns (gathered [world * stride], counts, stride)."""
     import torch
     import torch.distributed as dist
     world = dist.get_world_size(group)
@@ -48,6 +220,7 @@ def all_gather_runs(run, count: int, group=None):
     dist.all_gather_into_tensor(counts, cnt, group=group)
     counts_h = [int(c) for c in counts.cpu().tolist()]
     stride = max(max(counts_h), 1)
+    # a rank whose whole shard is shorter than the longest run (ceil partitioning: the last shard) pads its send buffer
     send = run[:stride].contiguous() if run.numel() >= stride else torch.nn.functional.pad(run, (0, stride - run.numel()))
     gathered = torch.empty(world * stride, dtype=torch.int64, device=run.device)
     dist.all_gather_into_tensor(gathered, send, group=group)
@@ -62,73 +235,3 @@ def match_list_parallel_host(run: np.ndarray, sort: SortStrategy, group=None) ->
     g = gathered.numpy().view(MATCH_DTYPE)
     runs = [g[r * stride: r * stride + counts[r]] for r in range(len(counts))]
     return merge_runs_host(runs, sort)
-
-
-class ShardRunner:
-    """Persistent device buffers for repeated match_list_parallel calls on one shard (no allocation per call)."""
-
-    def __init__(self, matcher: Matcher, shard: Corpus, index_offset: int, group=None, device: Optional[int] = None):
-        import torch
-        import torch.distributed as dist
-        self.matcher, self.shard, self.index_offset, self.group = matcher, shard, index_offset, group
-        self.dev = torch.device("cuda", torch.cuda.current_device() if device is None else device)
-        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
-        n_local = max(len(shard), 1)
-        self.run = torch.empty(n_local, dtype=torch.int64, device=self.dev)   # 8-byte frz_match records
-        self.count = torch.zeros(1, dtype=torch.int64, device=self.dev)
-        self.counts = torch.zeros(self.world, dtype=torch.int64, device=self.dev)
-        self.gathered = None
-        self.merged = None
-        self.bound = matcher.score_bound()
-        self.side = torch.cuda.Stream(self.dev) if self.world > 1 else None   # count exchange overlaps scoring
-
-    def local(self):
-        """This rank's shard → locally ordered run in HBM (asynchronous).  Returns (run tensor, count tensor)."""
-        import torch
-        stream = torch.cuda.current_stream(self.dev)
-        _check(lib().frz_match_shard_device(self.matcher._h, self.shard._h, self.index_offset, self.run.data_ptr(),
-                                            self.run.numel(), self.count.data_ptr(), stream.cuda_stream))
-        return self.run, self.count
-
-    def step(self):
-        """Matcher::match_list_parallel: local run, ONE all-gather of the padded runs, device merge.
-        Returns (merged tensor view, total)."""
-        import torch
-        import torch.distributed as dist
-        run, count = self.local()
-        if self.world == 1:
-            return run, None
-        # the count is final once the prefilter has run: exchange it on a side stream while the shard is scored
-        _check(lib().frz_matcher_wait_count(self.matcher._h, self.side.cuda_stream))
-        with torch.cuda.stream(self.side):
-            dist.all_gather_into_tensor(self.counts, count, group=self.group)
-            counts_h = np.asarray(self.counts.cpu().tolist(), dtype=np.uint64)  # the one host sync of the step
-        torch.cuda.current_stream(self.dev).wait_stream(self.side)
-        stride = max(int(counts_h.max()), 1)
-        total = int(counts_h.sum())
-        need = self.world * stride
-        if self.gathered is None or self.gathered.numel() < need:
-            self.gathered = torch.empty(int(need * 1.25) + 1024, dtype=torch.int64, device=self.dev)
-        if self.merged is None or self.merged.numel() < total:
-            self.merged = torch.empty(int(total * 1.25) + 1024, dtype=torch.int64, device=self.dev)
-        g = self.gathered[:need]
-        dist.all_gather_into_tensor(g, run[:stride], group=self.group)          # run is shard-sized >= stride
-        stream = torch.cuda.current_stream(self.dev)
-        _check(lib().frz_merge_runs_device(g.data_ptr(), stride, counts_h.ctypes.data, self.world, int(self.matcher.config.sort),
-                                           self.bound, self.merged.data_ptr(), self.dev.index, stream.cuda_stream))
-        return self.merged[:total], total
-
-
-def match_list_parallel(matcher: Matcher, shard: Corpus, index_offset: int, group=None, device: Optional[int] = None):
-    """Runs this rank's shard, all-gathers the runs over NCCL and merges them on every rank.
-    Returns (merged matches as an int64 torch tensor of 8-byte records on the device, total count)."""
-    r = ShardRunner(matcher, shard, index_offset, group, device)
-    merged, total = r.step()
-    if total is None:
-        total = int(r.count.item())
-        merged = merged[:total]
-    return merged, total
-
-
-def matches_from_tensor(t) -> np.ndarray:
-    return t.cpu().numpy().view(MATCH_DTYPE)

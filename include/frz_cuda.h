@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define FRZ_ABI_VERSION 1
+#define FRZ_ABI_VERSION 2
 #if defined(__GNUC__)
 #define FRZ_API __attribute__((visibility("default")))
 #else
@@ -53,7 +53,9 @@ typedef enum frz_status {
     FRZ_ERR_NO_DEVICE = 8,
     /* feature of the reference not built on the GPU path yet (never a silent CPU fallback) */
     FRZ_ERR_UNSUPPORTED = 9,
-    FRZ_ERR_OOM = 10
+    FRZ_ERR_OOM = 10,
+    /* NCCL missing / failed, or a peer rank did not answer (multi-GPU entry points only) */
+    FRZ_ERR_NCCL = 11
 } frz_status;
 
 /* thread-local, human-readable detail for the last non-OK status */
@@ -191,6 +193,8 @@ FRZ_API frz_status frz_matcher_from_query(const uint8_t* query, size_t len, cons
                                   frz_matcher** out);
 /* Matcher::set_config (src/matcher/mod.rs:154-160) */
 FRZ_API frz_status frz_matcher_set_config(frz_matcher* m, const frz_config* config);
+/* `impl Clone for Matcher` (src/matcher/mod.rs:76): same patterns and config, its own device scratch */
+FRZ_API frz_status frz_matcher_clone(const frz_matcher* m, frz_matcher** out);
 FRZ_API void frz_matcher_destroy(frz_matcher* m);
 
 /* Introspection of what `get_backend` selected for pattern i (src/matcher/mod.rs:448-498):
@@ -221,10 +225,71 @@ FRZ_API frz_status frz_match_list_host_arrow(frz_matcher* m, const uint8_t* byte
 /* Matcher::match_list_indices (src/matcher/mod.rs:234-262) for CHOSEN haystacks — the rows a UI is about to display:
  * for haystack which[j] (corpus-relative index) writes its Match to out_matches[j] and the byte offsets of the
  * matched characters, in the reference's descending order, to out_indices[j * stride ...]; out_counts[j] = how many
- * (capped at stride), or UINT32_MAX when that haystack does not match.  Host pointers.  Multi-pattern matchers pool
+ * the haystack has (UNtruncated: when it exceeds `stride` only the first `stride` offsets were stored — call again with
+ * a larger stride), or UINT32_MAX when that haystack does not match.  Host pointers.  Multi-pattern matchers pool
  * the atoms' indices like match_one_indices_multi (src/matcher/multi.rs:56-79).  Like the reference's, not a tuned path. */
 FRZ_API frz_status frz_match_indices(frz_matcher* m, const frz_corpus* corpus, const uint32_t* which, uint64_t n,
                              frz_match* out_matches, uint32_t* out_indices, uint32_t stride, uint32_t* out_counts);
+
+/* ------------------------------------------------ multi-GPU: match_list_parallel
+ *
+ * Matcher::match_list_parallel (src/matcher/parallel.rs:18-89) with GPUs in place of worker threads: the haystack list
+ * is sharded by contiguous index range (shard g = [g*ceil(N/G), ...)), every GPU runs the whole local
+ * pipeline on its shard with its own clone of the matcher (parallel.rs:46) and leaves a locally ordered run in HBM
+ * (parallel.rs:67-73), ONE ncclAllGather moves the runs (padded to the longest) over NVLink, every GPU merges them
+ * (k_merge_matches_by, src/k_merge.rs:90-131) and copies ITS slice of the merged list to the host buffer, so the
+ * device->host copy runs over all PCIe links in parallel.  The match counts (the Vec lengths the k-merge reads) travel
+ * through a small pinned host block shared by the ranks, published by each GPU as soon as its prefilter has run —
+ * no second collective, and the exchange overlaps the scoring kernels.
+ *
+ * NCCL is loaded at run time (dlopen "libnccl.so.2", so a process that already carries PyTorch's NCCL shares it);
+ * a communicator over ONE GPU never touches NCCL. */
+typedef struct frz_comm frz_comm;
+#define FRZ_UNIQUE_ID_BYTES 128
+
+/* Single-process form — what a Rust caller of match_list_parallel uses: one communicator over `n_gpus` devices of this
+ * process (`devices` NULL = 0..n_gpus-1), ncclCommInitAll, one worker thread per GPU inside the library (the
+ * std::thread::scope pool of parallel.rs:39-66). */
+FRZ_API frz_status frz_comm_create_local(int n_gpus, const int* devices, frz_comm** out);
+/* Multi-process form (one rank per process: torchrun, MPI): rank 0 gets an id, the host program ships those 128 bytes
+ * to every rank, every rank joins.  Collective: all ranks must call frz_comm_create_rank. */
+FRZ_API frz_status frz_comm_unique_id(uint8_t id[FRZ_UNIQUE_ID_BYTES]);
+FRZ_API frz_status frz_comm_create_rank(const uint8_t id[FRZ_UNIQUE_ID_BYTES], int world, int rank, int device, frz_comm** out);
+FRZ_API void frz_comm_destroy(frz_comm* c);
+FRZ_API int frz_comm_world(const frz_comm* c);
+FRZ_API int frz_comm_rank(const frz_comm* c);      /* rank of this process (multi-process form), 0 for the local form */
+FRZ_API int frz_comm_device(const frz_comm* c, int local_index);
+/* Host buffer every rank's GPU can write: pinned; in the multi-process form ONE shared-memory segment mapped and pinned
+ * by every rank (collective: every rank calls it with the same size and gets its own mapping of the same memory). */
+FRZ_API frz_status frz_comm_host_alloc(frz_comm* c, uint64_t bytes, void** out);
+FRZ_API frz_status frz_comm_host_free(frz_comm* c, void* p);
+/* host-side barrier over the ranks of the communicator (no-op for the local form) */
+FRZ_API frz_status frz_comm_barrier(frz_comm* c);
+
+/* Contiguous index-range shards of one host Arrow list, shard g resident on the communicator's g-th GPU (local form).
+ * `shards_out` receives frz_comm_world(c) corpora (empty shards are valid). */
+FRZ_API frz_status frz_corpus_create_sharded(const uint8_t* bytes, const void* offsets, int offset_width, uint64_t n,
+                                     frz_comm* c, frz_corpus** shards_out);
+
+/* Matcher::match_list_parallel (src/matcher/parallel.rs:18-89), local form: shards[g] lives on the communicator's g-th
+ * GPU and covers the indices after shards[0..g).  Blocking; `out` is host memory (frz_comm_host_alloc memory lets all
+ * GPUs copy concurrently; any other memory works).  On FRZ_ERR_CAPACITY *n_out = needed. */
+FRZ_API frz_status frz_match_list_parallel(frz_matcher* m, const frz_corpus* const* shards, int n_shards, frz_comm* c,
+                                   frz_match* out, uint64_t cap, uint64_t* n_out);
+/* One rank of the multi-process form.  Collective: every rank calls it with its shard and the index of its first
+ * haystack.  `out` must be the buffer returned by frz_comm_host_alloc (every rank writes its slice of the merged list
+ * into the shared segment; on return the WHOLE list is there) — or NULL with cap 0 to skip the host copy.
+ * *d_out (optional) receives this rank's device copy of the merged list, valid until the next call on `c`. */
+FRZ_API frz_status frz_match_list_parallel_rank(frz_matcher* m, const frz_corpus* shard, uint32_t index_offset, frz_comm* c,
+                                        frz_match* out, uint64_t cap, uint64_t* n_out, const frz_match** d_out);
+/* same, end to end: this rank's shard arrives as HOST Arrow buffers (streamed H2D + pack, as frz_match_list_host_arrow) */
+FRZ_API frz_status frz_match_list_parallel_rank_host(frz_matcher* m, const uint8_t* bytes, const void* offsets, int offset_width,
+                                             uint64_t n, uint32_t index_offset, frz_comm* c, frz_match* out, uint64_t cap,
+                                             uint64_t* n_out);
+/* Device timings (ms) of the last parallel call on local rank `local_index`: [0] local pipeline (prefilter, scoring,
+ * sort) [1] all-gather + merge [2] device->host slice [3] total; and the matcher clone that ran it (for
+ * frz_matcher_last_timings).  Blocks until that rank's stream is idle. */
+FRZ_API frz_status frz_comm_last_timings(frz_comm* c, int local_index, float* ms4, const frz_matcher** clone);
 
 /* Device-resident variant used by the multi-GPU path (Matcher::match_list_parallel,
  * src/matcher/parallel.rs:18-89): this rank's shard → a locally ordered run left in HBM.

@@ -2,6 +2,9 @@
 // src/sort.rs:6-40, src/k_merge.rs:90-131).  MEASUREMENT INFRASTRUCTURE ONLY.
 #include "driver.h"
 
+#include <pthread.h>
+#include <sched.h>
+
 #include <algorithm>
 #include <cstring>
 #include <thread>
@@ -13,6 +16,27 @@ bool has_avx512() {
            __builtin_cpu_supports("bmi") && __builtin_cpu_supports("bmi2");
 }
 bool has_avx2() { __builtin_cpu_init(); return __builtin_cpu_supports("avx2") && __builtin_cpu_supports("bmi2"); }
+
+// Worker ti runs on the ti-th CPU of the process's affinity mask (round-robin): rayon-style "one worker per core"
+// placement, and the same placement on every call, which keeps the timing of the CPU arm repeatable on 2-socket hosts.
+void pin_worker(size_t ti) {
+    cpu_set_t all;
+    CPU_ZERO(&all);
+    if (sched_getaffinity(0, sizeof all, &all) != 0) return;
+    const int ncpu = CPU_COUNT(&all);
+    if (ncpu <= 0) return;
+    int want = (int)(ti % (size_t)ncpu), seen = 0;
+    for (int c = 0; c < CPU_SETSIZE; c++) {
+        if (!CPU_ISSET(c, &all)) continue;
+        if (seen++ == want) {
+            cpu_set_t one;
+            CPU_ZERO(&one);
+            CPU_SET(c, &one);
+            pthread_setaffinity_np(pthread_self(), sizeof one, &one);
+            return;
+        }
+    }
+}
 
 void radix_sort_matches(std::vector<frz_match>& m) {  // src/sort.rs:6-40
     size_t n = m.size();
@@ -88,9 +112,9 @@ extern "C" uint64_t frzb_match_list_parallel(const frz_pattern* patterns, size_t
         if (by_score) radix_sort_matches(local);
         runs[ti] = std::move(local);
     };
+    // all workers are spawned threads (the calling thread keeps its own affinity and only joins and merges)
     std::vector<std::thread> ths;
-    for (size_t ti = 1; ti < t; ti++) ths.emplace_back(body, ti);
-    body(0);
+    for (size_t ti = 0; ti < t; ti++) ths.emplace_back([&body, ti] { pin_worker(ti); body(ti); });
     for (auto& th : ths) th.join();
     // k-way merge (src/k_merge.rs:90-131): binary heap of run cursors that carry their head Match inline,
     // advance-in-place + sift-down, and a bulk copy once a single run remains — as in the reference

@@ -168,6 +168,25 @@ def match_greedy(needle, haystack, scoring: Scoring = Scoring(), case_sensitive:
     return None if r < 0 else int(r)
 
 
+def auto_lanes() -> int:
+    """Lane width of the u8-family backend Matcher::get_backend (src/matcher/mod.rs:448-498) selects on THIS CPU:
+    AVX-512 (F+BW+VBMI, BMI1/2 for the prefilter) -> 64, AVX2 -> 32, otherwise (SSE / NEON / scalar) 16."""
+    flags = set()
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("flags"):
+                    flags = set(line.split(":", 1)[1].split())
+                    break
+    except OSError:
+        pass
+    if {"avx512f", "avx512bw", "avx512vbmi", "bmi1", "bmi2"} <= flags:
+        return 64
+    if "avx2" in flags:
+        return 32
+    return 16
+
+
 def score_fits_in_u8(needle_len: int, scoring: Scoring = Scoring()) -> bool:
     sc = CScoring.of(scoring)
     return bool(lib().frzo_score_fits_in_u8(needle_len, C.byref(sc)))

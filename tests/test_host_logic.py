@@ -20,7 +20,7 @@ def test_library_exports_every_declared_symbol():
     lib = ctypes.CDLL(F.lib_path())
     missing = [n for n in sorted(names) if not hasattr(lib, n)]
     assert not missing, missing
-    assert F.lib().frz_abi_version() == 1
+    assert F.lib().frz_abi_version() == 2
 
 
 def test_parse_atom_reference_vectors():
