@@ -37,6 +37,8 @@ struct FrzCorpusView {
     const FrzGroupDesc* groups;   // [n_tiles * 32]
     const uint32_t* slot_meta;    // [n_tiles * 1024]  len << 10 | local index, or FRZ_INVALID_SLOT
     const uint16_t* slot_of;      // [n_tiles * 1024]  inverse permutation: local index → slot
+    const uint2* slot_sig;        // [n_tiles * 1024]  byte-class signature of the slot's haystack (frz_sig_bucket): .x = classes
+                                  //                   that occur, .y = classes that occur at least twice
     uint64_t n;                   // haystacks
     uint32_t n_tiles;
     uint32_t max_gunits;          // longest haystack in 16-byte units
@@ -86,13 +88,44 @@ struct FrzPatternDev {
     int32_t n_distinct;                 // 0 → too many distinct bytes, use the scanning fallback
     uint8_t dc_om[16], dc_tg[16];       // probe of distinct class d
     uint8_t cid[FRZ_MAX_NEEDLE];        // needle index → distinct class
-    // phase-A probes (host-chosen necessary condition): up to 3 byte classes, combined with AND or OR
-    int32_t probe_n;                    // 0 → no probing (every length-gated haystack is a candidate)
-    int32_t probe_and;                  // 1: all probed classes must occur; 0: at least one must
-    uint8_t probe_om[4], probe_tg[4];
+    // phase-A signature test (necessary condition, host-chosen): a haystack can only pass the prefilter when at most
+    // `sig_k` needle bytes have no partner in it, so  popc(sig_need1 & ~sig.x) + popc(sig_need2 & ~sig.y) <= sig_k
+    int32_t sig_on;                     // 0 → no test (NO_PREFILTER): every length-gated haystack is a candidate
+    int32_t sig_k;
+    uint32_t sig_need1, sig_need2;      // byte classes the needle holds at least once / at least twice
     // untruncated scoring for the literal matcher / greedy fallback (u16 arithmetic)
     int32_t raw_match, raw_mismatch, raw_gap_open, raw_gap_extend, raw_prefix, raw_cap, raw_case, raw_delim;
 };
+
+// Byte class of the signature index (32 classes).  ASCII letters fold case (a needle byte and its case flip share a
+// class, so the class test is valid for case-sensitive and case-insensitive needles alike); digits and the remaining
+// bytes share a few classes each (a coarser class only weakens the test, never invalidates it).
+#if defined(__CUDACC__)
+#define FRZ_HD __host__ __device__
+#else
+#define FRZ_HD
+#endif
+FRZ_HD inline uint32_t frz_sig_bucket(uint32_t b) {
+    const uint32_t t = (b | 0x20u) - 'a';
+    if (t < 26u) return t;
+    const uint32_t d = b - '0';
+    if (d < 10u) return 26u + d % 3u;
+    return 29u + (b + (b >> 5)) % 3u;
+}
+// one more haystack byte: p1 = classes seen, p2 = classes seen at least twice
+FRZ_HD inline void frz_sig_add(uint32_t& p1, uint32_t& p2, uint32_t byte) {
+    const uint32_t bit = 1u << frz_sig_bucket(byte);
+    p2 |= p1 & bit;
+    p1 |= bit;
+}
+// lower bound of the number of needle bytes without a partner in the haystack <= typo budget?
+FRZ_HD inline bool frz_sig_pass(uint32_t need1, uint32_t need2, int k, uint32_t p1, uint32_t p2) {
+#if defined(__CUDA_ARCH__)
+    return __popc(need1 & ~p1) + __popc(need2 & ~p2) <= k;
+#else
+    return __builtin_popcount(need1 & ~p1) + __builtin_popcount(need2 & ~p2) <= k;
+#endif
+}
 
 // Survivor of the prefilter, input of the Smith-Waterman stage (16 bytes).
 // A prefilter survivor.  Two layouts share the 16 bytes:

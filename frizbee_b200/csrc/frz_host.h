@@ -36,6 +36,7 @@ struct FrzCorpusStorage {
     FrzGroupDesc* groups = nullptr;
     uint32_t* slot_meta = nullptr;
     uint16_t* slot_of = nullptr;
+    uint2* slot_sig = nullptr;
     uint64_t n = 0;
     uint32_t n_tiles = 0;
     uint64_t total_units = 0;
@@ -54,14 +55,15 @@ struct FrzCorpusStorage {
         v.groups = groups;
         v.slot_meta = slot_meta;
         v.slot_of = slot_of;
+        v.slot_sig = slot_sig;
         v.n = n;
         v.n_tiles = n_tiles;
         v.max_gunits = max_gunits;
         return v;
     }
     void release() {
-        cudaFree(data); cudaFree(tile_base); cudaFree(groups); cudaFree(slot_meta); cudaFree(slot_of); cudaFree(scratch_tile_units);
-        data = nullptr; tile_base = nullptr; groups = nullptr; slot_meta = nullptr; slot_of = nullptr; scratch_tile_units = nullptr;
+        cudaFree(data); cudaFree(tile_base); cudaFree(groups); cudaFree(slot_meta); cudaFree(slot_of); cudaFree(slot_sig); cudaFree(scratch_tile_units);
+        data = nullptr; tile_base = nullptr; groups = nullptr; slot_meta = nullptr; slot_of = nullptr; slot_sig = nullptr; scratch_tile_units = nullptr;
         cap_tiles = 0; cap_units = 0;
     }
 };
@@ -130,8 +132,8 @@ struct FrzLaunchStats {
     uint64_t launches = 0;
 };
 
-frz_status frz_launch_prefilter(const FrzCorpusView& cv, const FrzPatternDev& pat, const uint32_t* cand_bitmap,
-                                FrzWorkspace& ws, cudaStream_t stream, FrzLaunchStats* st);
+frz_status frz_launch_prefilter(const FrzCorpusView& cv, const FrzPatternDev& pat, FrzWorkspace& ws, cudaStream_t stream,
+                                FrzLaunchStats* st);
 frz_status frz_launch_unicode(const FrzCorpusView& cv, const FrzPatternDev& pat, const FrzUNeedle& un, const FrzUScoring& usc,
                               const FrzMatchDev* cand, uint64_t n_cand, uint32_t index_offset, FrzWorkspace& ws,
                               cudaStream_t stream, FrzLaunchStats* st);

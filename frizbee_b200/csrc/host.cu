@@ -293,7 +293,7 @@ extern "C" uint64_t frz_corpus_total_bytes(const frz_corpus* c) { return c ? c->
 extern "C" uint64_t frz_corpus_device_bytes(const frz_corpus* c) {
     if (!c) return 0;
     const auto& s = c->st;
-    return (s.total_units + 1) * 16 + (uint64_t)s.n_tiles * (8 + FRZ_GROUPS_PER_TILE * 16 + FRZ_TILE * 6);
+    return (s.total_units + 1) * 16 + (uint64_t)s.n_tiles * (8 + FRZ_GROUPS_PER_TILE * 16 + FRZ_TILE * (6 + 8));
 }
 extern "C" int frz_corpus_device(const frz_corpus* c) { return c ? c->st.device : -1; }
 extern "C" void frz_corpus_destroy(frz_corpus* c) {
@@ -470,6 +470,16 @@ frz_status compile_pattern(const OwnedPattern& src, const frz_config& mcfg, bool
         FRZ_TRY(guard_against_score_overflow(sc, n, sat_add16(maxb, sc.matching_case_bonus), 0));
         d.typo_mode = FRZ_T_LITERAL;
         d.min_hay_len = 0;
+        {   // a literal match holds every needle byte (either case): signature test with no typo budget
+            uint32_t cnt[32] = {0};
+            for (size_t i = 0; i < n; i++) cnt[frz_sig_bucket(d.c[i])]++;
+            for (int b2 = 0; b2 < 32; b2++) {
+                if (cnt[b2] >= 1) d.sig_need1 |= 1u << b2;
+                if (cnt[b2] >= 2) d.sig_need2 |= 1u << b2;
+            }
+            d.sig_on = 1;
+            d.sig_k = 0;
+        }
         d.pf_lanes = 64; d.sw_lanes = 64; d.score_bits = 16;
         uint64_t b = (uint64_t)n * ((uint64_t)sc.match_score + sc.matching_case_bonus + maxb) + sc.prefix_bonus + sc.exact_match_bonus;
         c.score_bound = (uint32_t)std::min<uint64_t>(b, 0xFFFF);
@@ -544,29 +554,19 @@ frz_status compile_pattern(const OwnedPattern& src, const frz_config& mcfg, bool
         if (max_typos > 15 && (size_t)max_typos < guard_len)
             return frz_fail(FRZ_ERR_UNSUPPORTED, "max_typos > 15 is not on the GPU path yet");
     }
-    {   // Phase-A necessary condition.  A byte class that fills more than k needle positions must occur in the
-        // haystack (k deletions cannot remove it): probe up to two such classes, rarest first, with AND.
-        // If no class is that frequent, fall back to "one of needle[0..k] occurs" (no path of the reference's
-        // state machine can start otherwise).
-        d.probe_n = 0; d.probe_and = 0;
-        const int k = max_typos;
-        if (k >= 0 && k <= 2 && (int)n > k && d.n_distinct > 0) {
-            int cnt[16] = {0};
-            for (size_t i = 0; i < n; i++) cnt[d.cid[i]]++;
-            int order[16], no = 0;
-            for (int c2 = 0; c2 < d.n_distinct; c2++) if (cnt[c2] > k) order[no++] = c2;
-            std::sort(order, order + no, [&](int a, int b) { return cnt[a] != cnt[b] ? cnt[a] < cnt[b] : a < b; });
-            const int want = k == 0 ? 1 : 2;
-            if (no > 0) {
-                d.probe_and = 1;
-                for (int j = 0; j < no && j < want; j++) { d.probe_om[j] = d.dc_om[order[j]]; d.probe_tg[j] = d.dc_tg[order[j]]; d.probe_n++; }
-            } else {
-                d.probe_and = 0;
-                for (int j = 0; j <= k && j < 3; j++) { d.probe_om[j] = d.om[j]; d.probe_tg[j] = d.tg[j]; d.probe_n++; }
-            }
-        } else if (k >= 0 && k <= 2 && (int)n > k) {   // too many distinct classes for the table: first-bytes rule
-            for (int j = 0; j <= k && j < 3; j++) { d.probe_om[j] = d.om[j]; d.probe_tg[j] = d.tg[j]; d.probe_n++; }
+    {   // Phase-A necessary condition on the signature index (frz_device.cuh: frz_sig_bucket).  A haystack accepted with
+        // k typos holds a common subsequence of n - k needle bytes (the k >= 1 trackers never accept what LCS rejects,
+        // DESIGN.md §2), so per byte class at most k needle bytes in total may lack a partner:
+        //     sum_c max(0, m_c - cnt_c) <= k     >=     popc(need1 & ~occurs) + popc(need2 & ~occurs_twice)
+        uint32_t cnt[32] = {0};
+        for (size_t i = 0; i < n; i++) cnt[frz_sig_bucket(d.c[i])]++;
+        d.sig_need1 = d.sig_need2 = 0;
+        for (int b2 = 0; b2 < 32; b2++) {
+            if (cnt[b2] >= 1) d.sig_need1 |= 1u << b2;
+            if (cnt[b2] >= 2) d.sig_need2 |= 1u << b2;
         }
+        d.sig_on = max_typos >= 0 ? 1 : 0;                       // NO_PREFILTER scores everything
+        d.sig_k = max_typos < 0 ? 0 : std::min<int>(max_typos, 64);
     }
     d.max_typos = max_typos < 0 ? 0 : std::min(max_typos, (int)guard_len);  // budget >= needle length matches everything
     // min_haystack_len (src/matcher/algo.rs:62-65)
@@ -912,7 +912,7 @@ frz_status run_pattern(frz_matcher* m, const FrzCorpusStorage& cs, const Compile
     if (record_events) { cudaEventRecord(ws.ev[0], stream); ws.ev_rec[0] = true; }
     if (c.unicode) FRZ_TRY(frz_launch_unicode(cv, c.dev, c.un, c.usc, cand_list, n_cand, index_offset, ws, stream, st));
     else if (cand_list) FRZ_TRY(frz_launch_prefilter_list(cv, c.dev, cand_list, n_cand, index_offset, ws, stream, st));
-    else FRZ_TRY(frz_launch_prefilter(cv, c.dev, cand_bitmap, ws, stream, st));
+    else FRZ_TRY(frz_launch_prefilter(cv, c.dev, ws, stream, st));
     FRZ_TRY(frz_launch_tile_scan(cv, ws, stream, st));
     if (record_events) { cudaEventRecord(ws.ev[1], stream); ws.ev_rec[1] = true; }
     if (m->early_count_dst && !cand_list && !cand_bitmap && m->compiled.size() == 1) {

@@ -191,6 +191,33 @@ __global__ void __launch_bounds__(256) k_pack_copy(const uint8_t* __restrict__ b
     }
 }
 
+// ---- signature index: one warp per group, lane per slot; classifies the packed bytes of the slot's haystack ----
+// .x = byte classes (frz_sig_bucket) that occur, .y = classes that occur at least twice.  The prefilter reads these
+// 8 bytes per haystack first and touches the haystack's own bytes only when the needle's classes are all there
+// (up to the typo budget) — prefilter.cu, phase A.
+__global__ void __launch_bounds__(256) k_pack_sig(const uint4* __restrict__ data, const FrzGroupDesc* __restrict__ groups,
+                                                  const uint32_t* __restrict__ slot_meta, uint32_t group0, uint32_t group1,
+                                                  uint2* __restrict__ slot_sig) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t g = group0 + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5); g < group1; g += warps) {
+        const FrzGroupDesc gd = groups[g];
+        const uint32_t meta = slot_meta[(uint64_t)g * FRZ_GROUP + lane];
+        const uint32_t len = meta == FRZ_INVALID_SLOT ? 0u : meta >> FRZ_TILE_SHIFT;
+        uint32_t p1 = 0, p2 = 0;
+        const uint4* gp = data + gd.abs_off + lane;
+        for (uint32_t k = 0; k < gd.gunits; k++) {   // warp-uniform trip count, coalesced 512-byte lines
+            const uint4 v = __ldg(gp + (size_t)k * FRZ_GROUP);
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int j = 0; j < 16; j++) {
+                if (k * FRZ_UNIT + j < len) frz_sig_add(p1, p2, (w[j >> 2] >> ((j & 3) * 8)) & 0xffu);
+            }
+        }
+        slot_sig[(uint64_t)g * FRZ_GROUP + lane] = make_uint2(p1, p2);
+    }
+}
+
 }  // namespace
 
 // ---- append support: the partial last tile is turned back into raw (bytes, offsets) so that it can be
@@ -265,9 +292,10 @@ frz_status pack_reserve(FrzCorpusStorage* out, uint32_t n_tiles, uint32_t keep_t
     const uint32_t want = keep_tiles ? std::max<uint32_t>(n_tiles, out->cap_tiles + out->cap_tiles / 2) : n_tiles;
     const size_t slots = (size_t)want * FRZ_TILE;
     uint32_t* slot_meta = nullptr; uint16_t* slot_of = nullptr; FrzGroupDesc* groups = nullptr;
-    uint64_t* tile_base = nullptr; uint64_t* scratch = nullptr;
+    uint64_t* tile_base = nullptr; uint64_t* scratch = nullptr; uint2* slot_sig = nullptr;
     FRZ_CUDA_TRY(cudaMalloc(&slot_meta, slots * sizeof(uint32_t)));
     FRZ_CUDA_TRY(cudaMalloc(&slot_of, slots * sizeof(uint16_t)));
+    FRZ_CUDA_TRY(cudaMalloc(&slot_sig, slots * sizeof(uint2)));
     FRZ_CUDA_TRY(cudaMalloc(&groups, (size_t)want * FRZ_GROUPS_PER_TILE * sizeof(FrzGroupDesc)));
     FRZ_CUDA_TRY(cudaMalloc(&tile_base, (size_t)want * sizeof(uint64_t)));
     FRZ_CUDA_TRY(cudaMalloc(&scratch, ((size_t)want + 2) * sizeof(uint64_t)));
@@ -275,12 +303,13 @@ frz_status pack_reserve(FrzCorpusStorage* out, uint32_t n_tiles, uint32_t keep_t
         const size_t ks = (size_t)keep_tiles * FRZ_TILE;
         FRZ_CUDA_TRY(cudaMemcpyAsync(slot_meta, out->slot_meta, ks * sizeof(uint32_t), cudaMemcpyDeviceToDevice, stream));
         FRZ_CUDA_TRY(cudaMemcpyAsync(slot_of, out->slot_of, ks * sizeof(uint16_t), cudaMemcpyDeviceToDevice, stream));
+        FRZ_CUDA_TRY(cudaMemcpyAsync(slot_sig, out->slot_sig, ks * sizeof(uint2), cudaMemcpyDeviceToDevice, stream));
         FRZ_CUDA_TRY(cudaMemcpyAsync(groups, out->groups, (size_t)keep_tiles * FRZ_GROUPS_PER_TILE * sizeof(FrzGroupDesc), cudaMemcpyDeviceToDevice, stream));
         FRZ_CUDA_TRY(cudaMemcpyAsync(tile_base, out->tile_base, (size_t)keep_tiles * sizeof(uint64_t), cudaMemcpyDeviceToDevice, stream));
         FRZ_CUDA_TRY(cudaStreamSynchronize(stream));
     }
-    cudaFree(out->slot_meta); cudaFree(out->slot_of); cudaFree(out->groups); cudaFree(out->tile_base); cudaFree(out->scratch_tile_units);
-    out->slot_meta = slot_meta; out->slot_of = slot_of; out->groups = groups; out->tile_base = tile_base; out->scratch_tile_units = scratch;
+    cudaFree(out->slot_meta); cudaFree(out->slot_of); cudaFree(out->slot_sig); cudaFree(out->groups); cudaFree(out->tile_base); cudaFree(out->scratch_tile_units);
+    out->slot_meta = slot_meta; out->slot_of = slot_of; out->slot_sig = slot_sig; out->groups = groups; out->tile_base = tile_base; out->scratch_tile_units = scratch;
     out->cap_tiles = want;
     return FRZ_OK;
 }
@@ -325,6 +354,10 @@ frz_status pack_copy(FrzCorpusStorage* out, const uint8_t* d_bytes, const OffT* 
     (void)tile0;
     k_pack_copy<OffT><<<t1 - t0, 256, 0, stream>>>(d_bytes, d_offsets, t0, idx0, off0, total_bytes, out->slot_meta, out->groups,
                                                   out->tile_base, out->data);
+    // signature index of the same tiles, from the bytes just interleaved (L2-resident for a streamed chunk)
+    const uint32_t g0 = t0 * FRZ_GROUPS_PER_TILE, g1 = t1 * FRZ_GROUPS_PER_TILE;
+    const uint32_t sig_blocks = std::min<uint32_t>((g1 - g0 + 7) / 8, 148 * 8);
+    k_pack_sig<<<sig_blocks, 256, 0, stream>>>(out->data, out->groups, out->slot_meta, g0, g1, out->slot_sig);
     FRZ_CUDA_TRY(cudaGetLastError());
     return FRZ_OK;
 }

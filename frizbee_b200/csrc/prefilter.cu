@@ -9,12 +9,14 @@
 //
 // Structure (persistent, warp-autonomous, no block barriers — the first version synchronised a
 // block per tile and spent 65% of its issue slots waiting at barriers, profiles/r01a_*):
-//   phase A  warp per group, lane per haystack: coalesced LDG.128 of the interleaved units and a
-//            word-parallel "does it contain needle[0] (or needle[1])" probe — a necessary condition
-//            that rejects most haystacks at ~3 integer ops per 4 bytes; passing lanes push their
-//            bytes into the warp's private shared-memory ring.
+//   phase A  warp per group, lane per haystack: length gate + the byte-class SIGNATURE test (8 bytes per
+//            haystack, written at pack time — pack.cu: k_pack_sig): "at most k needle bytes lack a partner
+//            in this haystack", a necessary condition of every prefilter of the reference.  The haystack bytes
+//            are not read for rejected haystacks.  Passing lanes queue in the warp's shared-memory ring.
+//            (Rounds 1's phase A streamed every haystack byte through word-parallel probes: 0.35 of the HBM
+//            roofline, ALU-issue-bound; the signature test reads 12 bytes per haystack instead of len + 8.)
 //   phase B  whenever 32 candidates are queued: lane per candidate, the exact reference window
-//            (chunk-emulating for k >= 1) on the shared-memory copy, all lanes busy.
+//            (chunk-emulating for k >= 1) from occurrence masks of the candidate's bytes, all lanes busy.
 //   emit     survivors go to per-SW-class lists (warp-aggregated atomics) and set their bit in a
 //            per-tile bitmap; k_tile_rank turns the bitmap into index-order ranks so that the
 //            scoring stage can write each match straight to its index-ordered position.
@@ -448,16 +450,18 @@ __device__ __forceinline__ void process_candidate(const FrzCorpusView& cv, const
     }
 }
 
-// Warp-autonomous, barrier-free: every warp strides over groups, probes (phase A), queues the
-// passing haystacks' bytes in its own shared-memory ring and, whenever 32 are queued, runs the
-// exact window on them with all lanes busy (phase B).
-// SLICE: units per lane held in registers per prefetched group (4 when no haystack of the corpus exceeds 64 bytes:
-// half the buffer registers, one more resident block per SM).
-template <int MODE, int SLICE>
-__global__ void __launch_bounds__(kThreads, SLICE == 4 ? 5 : 4) k_prefilter(const FrzCorpusView cv, const __grid_constant__ FrzPatternDev pat,
-                                                        const uint32_t* __restrict__ cand_bitmap,
-                                                        const FrzSurvLists lists, unsigned long long surv_cap,
-                                                        uint32_t* __restrict__ surv_bitmap, FrzCounters* __restrict__ ctr) {
+// Warp-autonomous, barrier-free: every warp strides over groups.
+//   phase A  lane per haystack: ONE coalesced 4-byte load (length) and ONE coalesced 8-byte load (the byte-class
+//            signature written at pack time) decide "can this haystack hold the needle up to the typo budget?" —
+//            two POPCs.  The haystack's own bytes are not touched: a rejected haystack costs 12 bytes of HBM traffic
+//            instead of len + 8.  Passing lanes push (tile, slot, len) into the warp's shared-memory ring.
+//   phase B  whenever 32 candidates are queued: lane per candidate, occurrence masks + the reference's window state
+//            machine on the candidate's bytes (process_candidate), all lanes busy.
+// Loads are software-pipelined two groups ahead (a warp has no other way to keep HBM busy).
+template <int MODE>
+__global__ void __launch_bounds__(kThreads, 6) k_prefilter(const FrzCorpusView cv, const __grid_constant__ FrzPatternDev pat,
+                                                           const FrzSurvLists lists, unsigned long long surv_cap,
+                                                           uint32_t* __restrict__ surv_bitmap, FrzCounters* __restrict__ ctr) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const uint32_t lane = frz_lane(), warp = threadIdx.x >> 5;
     WarpQueue& q = reinterpret_cast<WarpQueue*>(smem_raw)[warp];
@@ -466,120 +470,61 @@ __global__ void __launch_bounds__(kThreads, SLICE == 4 ? 5 : 4) k_prefilter(cons
     if (threadIdx.x < FRZ_MAX_NEEDLE) cid_s[threadIdx.x] = pat.cid[threadIdx.x];
     __syncthreads();
 
-    // host-chosen probes (compile_pattern): NP byte classes, all (AND) or any (OR) of which must occur
-    const uint32_t om0 = splat4(pat.probe_om[0]), tg0 = splat4(pat.probe_tg[0]);
-    const uint32_t om1 = splat4(pat.probe_om[1]), tg1 = splat4(pat.probe_tg[1]);
-    const uint32_t om2 = splat4(pat.probe_om[2]), tg2 = splat4(pat.probe_tg[2]);
-    const int NP = pat.probe_n;
-    const bool probe = (MODE == FRZ_T_0 || MODE == FRZ_T_1 || MODE == FRZ_T_2) && NP > 0;
+    const bool use_sig = MODE != FRZ_T_NONE && pat.sig_on != 0;
+    const uint32_t need1 = pat.sig_need1, need2 = pat.sig_need2;
+    const int sig_k = pat.sig_k;
+    const int min_len = pat.min_hay_len;
 
     const uint32_t n_warps = gridDim.x * kWarps;
+    const uint32_t total_groups = cv.n_tiles * FRZ_GROUPS_PER_TILE;
     uint32_t head = 0, count = 0;  // ring state (warp-uniform)
 
-    // Software pipeline (the warp has no other way to keep HBM busy at 16 warps/SM): descriptors of
-    // group i+2 and the haystack units of group i+1 are in flight while group i is probed.  The loop is
-    // unrolled by two so that the unit buffers ping-pong instead of being copied.
-    struct Desc {
-        FrzGroupDesc gd;
+    struct Grp {
         uint32_t meta;
+        uint2 sig;
         uint32_t gidx;
     };
-    const uint32_t total_groups = cv.n_tiles * FRZ_GROUPS_PER_TILE;
     uint32_t gen = blockIdx.x * kWarps + warp;   // this warp's next group (stride n_warps)
-    auto load_desc = [&](Desc& d) {
+    auto load_grp = [&](Grp& g) {
+        g.gidx = gen;
+        g.meta = FRZ_INVALID_SLOT;
+        g.sig = make_uint2(0u, 0u);
         if (gen < total_groups) {
-            d.gd = cv.groups[gen];  // one 16-byte load
-            d.meta = cv.slot_meta[(uint64_t)(gen >> 5) * FRZ_TILE + (gen & 31) * FRZ_GROUP + lane];
-            d.gidx = gen;
+            const uint64_t idx = (uint64_t)gen * FRZ_GROUP + lane;   // == tile * 1024 + group * 32 + lane
+            g.meta = __ldg(cv.slot_meta + idx);
+            if (use_sig) g.sig = __ldg(cv.slot_sig + idx);
         } else {
-            d.gd = FrzGroupDesc{0ull, 0u, 0u};
-            d.meta = FRZ_INVALID_SLOT;
-            d.gidx = 0xFFFFFFFFu;
+            g.gidx = 0xFFFFFFFFu;
         }
         gen += n_warps;
     };
-    auto load_units = [&](const Desc& d, uint4 (&u)[SLICE]) {
-        const uint4* gp = cv.data + d.gd.abs_off + lane;
-#pragma unroll
-        for (int k = 0; k < SLICE; k++) {
-            if (k < (int)d.gd.gunits && d.gd.gunits <= SLICE) u[k] = __ldg(gp + (size_t)k * FRZ_GROUP);
-        }
-    };
-    // phase A on one group whose units are in `u`
-    auto phase_a = [&](const Desc& dc, const uint4 (&u)[SLICE]) {
-        const uint32_t tile = dc.gidx >> 5, g = dc.gidx & 31;
-        const FrzGroupDesc gd = dc.gd;
-        const uint32_t slot = g * FRZ_GROUP + lane;
-        const uint32_t meta = dc.meta;
+    auto phase_a = [&](const Grp& g) {
+        const uint32_t meta = g.meta;
         const bool valid = meta != FRZ_INVALID_SLOT;
         const uint32_t len = valid ? meta >> FRZ_TILE_SHIFT : 0;
-        bool pass = valid && (int)len >= pat.min_hay_len;
-        if (cand_bitmap != nullptr && valid) {
-            const uint64_t idx = (uint64_t)tile * FRZ_TILE + (meta & (FRZ_TILE - 1));
-            pass = pass && ((cand_bitmap[idx >> 5] >> (idx & 31)) & 1);
-        }
-        uint32_t acc = 0, acc1 = 0, acc2 = 0;
-        const bool in_regs = gd.gunits <= SLICE;  // units prefetched into registers
-        const bool skip_group = gd.gunits == 0 && MODE != FRZ_T_NONE && MODE != FRZ_T_LITERAL && pat.min_hay_len > 0;
-        if (probe && !skip_group) {
-            if (in_regs) {
-#pragma unroll
-                for (int k = 0; k < SLICE; k++) {
-                    if (k >= (int)gd.gunits) break;  // warp-uniform
-                    const uint32_t w[4] = {u[k].x, u[k].y, u[k].z, u[k].w};
-#pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        uint32_t x = (w[j] | om0) ^ tg0;
-                        acc |= (x - 0x01010101u) & ~x;
-                        if (MODE >= FRZ_T_1 && NP > 1) { x = (w[j] | om1) ^ tg1; acc1 |= (x - 0x01010101u) & ~x; }
-                        if (MODE >= FRZ_T_2 && NP > 2) { x = (w[j] | om2) ^ tg2; acc2 |= (x - 0x01010101u) & ~x; }
-                    }
-                }
-            } else {
-                const uint4* gp = cv.data + gd.abs_off + lane;
-                for (uint32_t k = 0; k < gd.gunits; k++) {
-                    const uint4 v = __ldg(gp + (size_t)k * FRZ_GROUP);
-                    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        uint32_t x = (w[j] | om0) ^ tg0;
-                        acc |= (x - 0x01010101u) & ~x;
-                        if (MODE >= FRZ_T_1 && NP > 1) { x = (w[j] | om1) ^ tg1; acc1 |= (x - 0x01010101u) & ~x; }
-                        if (MODE >= FRZ_T_2 && NP > 2) { x = (w[j] | om2) ^ tg2; acc2 |= (x - 0x01010101u) & ~x; }
-                    }
-                }
-            }
-            const bool h0 = (acc & 0x80808080u) != 0, h1 = (acc1 & 0x80808080u) != 0, h2 = (acc2 & 0x80808080u) != 0;
-            const bool hit = pat.probe_and ? (h0 && (NP < 2 || h1) && (NP < 3 || h2)) : (h0 || (NP > 1 && h1) || (NP > 2 && h2));
-            pass = pass && hit;
-        }
-        if (skip_group) pass = false;
+        bool pass = valid && (int)len >= min_len;
+        if (use_sig) pass = pass && frz_sig_pass(need1, need2, sig_k, g.sig.x, g.sig.y);
         const uint32_t ballot = __ballot_sync(0xffffffffu, pass);
         if (ballot) {
             if (pass) {
                 const uint32_t e = (head + count + __popc(ballot & ((1u << lane) - 1))) & (kQueueCap - 1);
-                q.meta[e] = (tile << FRZ_TILE_SHIFT) | slot;
+                q.meta[e] = (g.gidx << 5) | lane;   // (tile << 10) | slot, slot = group-in-tile * 32 + lane
                 q.info[e] = len;
             }
             count += __popc(ballot);
         }
     };
-    Desc d0, d1, d2;
-    uint4 ua[SLICE], ub[SLICE];
-    load_desc(d0);
-    load_desc(d1);
-    load_units(d0, ua);
+    Grp g0, g1, g2;
+    load_grp(g0);
+    load_grp(g1);
+    load_grp(g2);
     for (;;) {
-        const bool done = d0.gidx == 0xFFFFFFFFu;
+        const bool done = g0.gidx == 0xFFFFFFFFu;
         if (!done) {
-            load_desc(d2);
-            load_units(d1, ub);
-            phase_a(d0, ua);
-            load_desc(d0);
-            load_units(d2, ua);
-            if (d1.gidx != 0xFFFFFFFFu) phase_a(d1, ub);
-            d1 = d0;
-            d0 = d2;
+            phase_a(g0);
+            g0 = g1;
+            g1 = g2;
+            load_grp(g2);
         }
         // -------------------------------------------------------- phase B on full batches; the partial
         // batch is flushed through the same (single inlined) call site once the groups are exhausted
@@ -779,40 +724,35 @@ frz_status frz_launch_prefilter_list(const FrzCorpusView& cv, const FrzPatternDe
     return FRZ_OK;
 }
 
-frz_status frz_launch_prefilter(const FrzCorpusView& cv, const FrzPatternDev& pat, const uint32_t* cand_bitmap,
-                                FrzWorkspace& ws, cudaStream_t stream, FrzLaunchStats* st) {
+frz_status frz_launch_prefilter(const FrzCorpusView& cv, const FrzPatternDev& pat, FrzWorkspace& ws, cudaStream_t stream,
+                                FrzLaunchStats* st) {
     if (cv.n_tiles == 0) return FRZ_OK;
     const size_t smem = sizeof(WarpQueue) * kWarps;
     int sms = 0, dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (sms <= 0) sms = 148;
-    // persistent warps: 4 blocks of 4 warps per SM (shared-memory bound), capped by the work
     const uint32_t total_groups = cv.n_tiles * FRZ_GROUPS_PER_TILE;
-    static int slice_knob = -1;   // experiment knob: FRZ_PF_SLICE=8 forces the wide variant
-    if (slice_knob < 0) { const char* e = getenv("FRZ_PF_SLICE"); slice_knob = e ? atoi(e) : 0; }
-    const bool narrow = cv.max_gunits <= 4 && slice_knob != 8 && (pat.typo_mode == FRZ_T_0 || pat.typo_mode == FRZ_T_1);
-    static int bps_knob = -1;     // experiment knob: FRZ_PF_BLOCKS = resident blocks per SM of the narrow variant
-    if (bps_knob < 0) { const char* e = getenv("FRZ_PF_BLOCKS"); bps_knob = e ? atoi(e) : 5; }
-    const uint32_t bps = narrow ? (uint32_t)bps_knob : 4;
-    const uint32_t grid = std::max<uint32_t>(1, std::min<uint32_t>((uint32_t)sms * bps, (total_groups + kWarps - 1) / kWarps));
     FRZ_CUDA_TRY(cudaMemsetAsync(ws.surv_bitmap, 0, (size_t)cv.n_tiles * 32 * sizeof(uint32_t), stream));
-#define FRZ_PF_LAUNCH(MODE) FRZ_PF_LAUNCH_S(MODE, 8)
-#define FRZ_PF_LAUNCH_N(MODE) do { if (narrow) FRZ_PF_LAUNCH_S(MODE, 4); else FRZ_PF_LAUNCH_S(MODE, 8); } while (0)
-#define FRZ_PF_LAUNCH_S(MODE, SL)                                                                                     \
-    do {                                                                                                        \
-        static bool attr_set_dev[64] = {};                                                                      \
-        bool& attr_set = attr_set_dev[frz_current_device() & 63];                                               \
-        if (!attr_set) {                                                                                        \
-            FRZ_CUDA_TRY(cudaFuncSetAttribute(k_prefilter<MODE, SL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-            attr_set = true;                                                                                    \
-        }                                                                                                       \
-        k_prefilter<MODE, SL><<<grid, kThreads, smem, stream>>>(cv, pat, cand_bitmap, ws.lists(), ws.survivor_cap,       \
-                                                            ws.surv_bitmap, ws.counters);                                   \
+    // persistent warps: as many blocks as fit on the SMs (registers / shared memory), capped by the work
+#define FRZ_PF_LAUNCH(MODE)                                                                                              \
+    do {                                                                                                                 \
+        static int bps_dev[64] = {};                                                                                     \
+        int& bps = bps_dev[frz_current_device() & 63];                                                                   \
+        if (!bps) {                                                                                                      \
+            FRZ_CUDA_TRY(cudaFuncSetAttribute(k_prefilter<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            FRZ_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_prefilter<MODE>, kThreads, smem));        \
+            static int knob = -1;   /* experiment knob: FRZ_PF_BLOCKS caps the resident blocks per SM */                 \
+            if (knob < 0) { const char* e = getenv("FRZ_PF_BLOCKS"); knob = e ? atoi(e) : 0; }                           \
+            if (knob > 0 && knob < bps) bps = knob;                                                                      \
+            if (bps < 1) bps = 1;                                                                                        \
+        }                                                                                                                \
+        const uint32_t grid = std::max<uint32_t>(1, std::min<uint32_t>((uint32_t)(sms * bps), (total_groups + kWarps - 1) / kWarps)); \
+        k_prefilter<MODE><<<grid, kThreads, smem, stream>>>(cv, pat, ws.lists(), ws.survivor_cap, ws.surv_bitmap, ws.counters); \
     } while (0)
     switch (pat.typo_mode) {
-        case FRZ_T_0: FRZ_PF_LAUNCH_N(FRZ_T_0); break;
-        case FRZ_T_1: FRZ_PF_LAUNCH_N(FRZ_T_1); break;
+        case FRZ_T_0: FRZ_PF_LAUNCH(FRZ_T_0); break;
+        case FRZ_T_1: FRZ_PF_LAUNCH(FRZ_T_1); break;
         case FRZ_T_2: FRZ_PF_LAUNCH(FRZ_T_2); break;
         case FRZ_T_MANY: FRZ_PF_LAUNCH(FRZ_T_MANY); break;
         case FRZ_T_NONE: FRZ_PF_LAUNCH(FRZ_T_NONE); break;
@@ -820,8 +760,6 @@ frz_status frz_launch_prefilter(const FrzCorpusView& cv, const FrzPatternDev& pa
         default: return frz_fail(FRZ_ERR_INVALID_ARG, "bad typo mode %d", pat.typo_mode);
     }
 #undef FRZ_PF_LAUNCH
-#undef FRZ_PF_LAUNCH_N
-#undef FRZ_PF_LAUNCH_S
     FRZ_CUDA_TRY(cudaGetLastError());
     if (st) st->launches++;
     return FRZ_OK;

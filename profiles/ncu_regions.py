@@ -4,6 +4,13 @@ instructions with similar execution counts are merged, so loops/phases show up a
 import csv, io, subprocess, sys
 out = subprocess.run(["ncu", "-i", sys.argv[1], "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
+# a report holds one section per captured launch: pick the first whose kernel name contains argv[2] (default: first)
+want = sys.argv[2] if len(sys.argv) > 2 else ""
+starts = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"]
+sel = next((i for i in starts if want in rows[i][1]), starts[0])
+end = next((i for i in starts if i > sel), len(rows))
+print(rows[sel][1][:100])
+rows = rows[sel:end]
 hdr = rows[1]
 ia, isrc, ie, it, isamp = (hdr.index(k) for k in ("Address", "Source", "Instructions Executed", "Thread Instructions Executed", "# Samples"))
 ins = [(r[ia], r[isrc].strip(), float(r[ie] or 0), float(r[it] or 0), float(r[isamp] or 0)) for r in rows[2:] if len(r) > it]

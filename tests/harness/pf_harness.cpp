@@ -34,4 +34,15 @@ int h_masks_window(const void* pat_bytes, const uint8_t* hay, int len, int mode,
     }
     return ok ? 1 : 0;
 }
+
+// Phase A of k_prefilter: the signature of the haystack (pack.cu: k_pack_sig uses the same frz_sig_add) against the
+// needle's class requirements (host.cu: compile_pattern).  Returns 1 = candidate, 0 = rejected without reading the bytes.
+int h_sig_pass(const void* pat_bytes, const uint8_t* hay, int len) {
+    FrzPatternDev pat;
+    memcpy(&pat, pat_bytes, sizeof pat);
+    if (!pat.sig_on) return 1;
+    uint32_t p1 = 0, p2 = 0;
+    for (int i = 0; i < len; i++) frz_sig_add(p1, p2, hay[i]);
+    return frz_sig_pass(pat.sig_need1, pat.sig_need2, pat.sig_k, p1, p2) ? 1 : 0;
+}
 }

@@ -178,6 +178,58 @@ def test_mask_prefilter_windows_equal_oracle(H, PF, lanes, k):
 
 
 @pytest.mark.parametrize("lanes", [16, 32, 64])
+def test_signature_test_is_a_necessary_condition(H, PF, lanes):
+    """Phase A of k_prefilter rejects a haystack from its 8-byte class signature alone.  That is only sound if the test is
+    a NECESSARY condition of the reference's prefilters (all typo budgets, both case modes) and of the literal modes:
+    whenever the oracle accepts, the signature test must pass — checked on dense alphabets (letters in both cases,
+    digits, punctuation, non-ASCII bytes, NUL) where class collisions and multiplicities are common."""
+    from frizbee_b200.types import Matching, Pattern
+    rng = random.Random(4200 + lanes)
+    F.lib().frz_matcher_debug_pattern.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]
+    PF.h_sig_pass.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
+    pools = POOLS + [b"0123456789", b"a1b2c3_-./ ", b"eeeddd", b"aAzZ@[`{|~!"]
+    accepted = rejected_by_sig = 0
+    for trial in range(900):
+        pool = rng.choice(pools)
+        needle = rand_bytes(rng, pool, rng.randint(1, 12))
+        k = rng.choice([0, 0, 1, 1, 2, 3, 5])
+        cs = rng.random() < 0.3
+        cfg = Config(max_typos=k, emulate_lanes=lanes, casing=CaseMatching.Respect if cs else CaseMatching.Ignore)
+        pat, info = device_pattern(H, needle, cfg)
+        for _ in range(16):
+            ln = rng.choice([0, 1, 2, 5, 9, 16, 17, 31, 40, 64, 65, 100, 130])
+            hay = rand_bytes(rng, pool + rng.choice([b"", b"x", b"XY9", HAY_EXTRA]), ln)
+            ok = O.prefilter(needle, hay, k, lanes, cs)[0]
+            sig = PF.h_sig_pass(pat, hay, len(hay))
+            if ok:
+                assert sig == 1, (needle, hay, k, lanes, cs)
+                accepted += 1
+            elif not sig:
+                rejected_by_sig += 1
+    assert accepted > 1500 and rejected_by_sig > 1500
+    # literal modes: a literal match contains every needle byte (either case when case-insensitive)
+    lit_ok = 0
+    for trial in range(400):
+        pool = rng.choice(pools)
+        needle = rand_bytes(rng, pool, rng.randint(1, 6))
+        if 0 in needle or any(b >= 0x80 for b in needle):
+            continue
+        cs = rng.random() < 0.3
+        mode = rng.choice([Matching.Exact, Matching.Prefix, Matching.Suffix, Matching.Substring])
+        cfg = Config(matching=mode, casing=CaseMatching.Respect if cs else CaseMatching.Ignore)
+        pat, _ = device_pattern(H, needle, cfg)
+        for _ in range(10):
+            pre, post = rand_bytes(rng, pool, rng.randint(0, 5)), rand_bytes(rng, pool, rng.randint(0, 5))
+            mid = bytes((b ^ 0x20) if (not cs and chr(b).isalpha() and rng.random() < 0.5) else b for b in needle)
+            hay = {Matching.Exact: mid, Matching.Prefix: mid + post, Matching.Suffix: pre + mid, Matching.Substring: pre + mid + post}[mode]
+            got = O.match_list([Pattern(needle.decode("latin-1"), matching=mode)], [hay.decode("latin-1")], cfg)
+            if got:
+                assert PF.h_sig_pass(pat, hay, len(hay)) == 1, (needle, hay, mode, cs)
+                lit_ok += 1
+    assert lit_ok > 500
+
+
+@pytest.mark.parametrize("lanes", [16, 32, 64])
 @pytest.mark.parametrize("k", [1, 2, 3, 5])
 def test_mask_prefilter_groundwork_2_and_n_typos(H, PF, lanes, k):
     """masks_paths<NP> / masks_many (prefilter_masks.cuh, not yet wired into the kernels) vs match_haystack_1_typo /

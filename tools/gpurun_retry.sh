@@ -1,0 +1,11 @@
+#!/bin/bash
+# usage: tools/gpurun_retry.sh <log> [gpurun args...] -- <command>
+# retries while the pod answers "busy / no box" (exit 3, nothing charged), up to 12 times
+log=$1; shift
+for attempt in $(seq 1 12); do
+  /usr/local/graft/bin/gpurun "$@" > "$log" 2>&1
+  rc=$?
+  if [ $rc -ne 3 ] && ! grep -q "status=transient" "$log"; then exit $rc; fi
+  sleep 120
+done
+exit 3
