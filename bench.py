@@ -58,6 +58,13 @@ def parse_args():
     ap.add_argument("--max-typos", type=int, default=WORKLOAD["max_typos"])
     ap.add_argument("--mu", type=int, default=WORKLOAD["mu"])
     ap.add_argument("--max-len", type=int, default=WORKLOAD["max_len"])
+    ap.add_argument("--query", default=None, help="a multi-pattern query (Matcher::from_query), e.g. 'foo !^bar' (configs[4]); "
+                                                  "the haystacks are generated around its first positive atom")
+    ap.add_argument("--unicode-frac", type=float, default=0.0, help="fraction of haystacks with multibyte scalars spliced in")
+    ap.add_argument("--prefix-frac", type=float, default=0.0, help="fraction of haystacks starting with 'bar'/'Bar'")
+    ap.add_argument("--shards-per-gpu", type=int, default=1,
+                    help="each GPU holds this many consecutive logical shards of --n haystacks (seeds consecutive): "
+                         "`--gpus 1 --shards-per-gpu 8` matches the very list `--gpus 8` shards over 8 GPUs (strong scaling)")
     return ap.parse_args()
 
 
@@ -104,6 +111,52 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def _gen_one(job):
+    from frizbee_b200 import synth
+    needle, n, mu, max_len, seed, ufrac, pfrac = job
+    return synth.generate(needle, n, mu, max_len, seed, unicode_frac=ufrac, prefix_frac=pfrac)
+
+
+def gen_needle(args) -> str:
+    """The string the synthetic haystacks are built around: the needle, or the first positive atom of --query."""
+    if not args.query:
+        return WORKLOAD["needle"]
+    for atom in args.query.split():
+        if not atom.startswith("!"):
+            return atom.strip("^$'")
+    return "foo"
+
+
+def make_rank_data(args, rank):
+    """This rank's haystacks: `shards_per_gpu` logical shards of args.n items, logical shard j generated with seed + j
+    (so the list does not depend on how many GPUs it is spread over).  Several shards are generated in parallel processes
+    (called before torch / CUDA are initialised)."""
+    S = args.shards_per_gpu
+    jobs = [(gen_needle(args), args.n, WORKLOAD["mu"], WORKLOAD["max_len"], WORKLOAD["seed"] + rank * S + j, args.unicode_frac,
+             args.prefix_frac) for j in range(S)]
+    if S == 1:
+        return _gen_one(jobs[0])
+    import concurrent.futures as cf
+    import multiprocessing as mp
+    with cf.ProcessPoolExecutor(max_workers=min(S, 8), mp_context=mp.get_context("fork")) as ex:
+        parts = list(ex.map(_gen_one, jobs))
+    data = np.concatenate([p[0] for p in parts])
+    offs = [parts[0][1]]
+    base = int(parts[0][1][-1])
+    for d, o in parts[1:]:
+        offs.append(o[1:] + np.uint64(base))
+        base += int(o[-1])
+    return data, np.concatenate(offs)
+
+
+def workload_patterns(args):
+    """What the matcher is built from and what the CPU checker receives."""
+    if args.query:
+        import frizbee_b200 as F
+        return F.parse_query(args.query)
+    return [WORKLOAD["needle"]]
+
+
 def workload_config(args):
     from frizbee_b200.types import Config
     return Config(max_typos=WORKLOAD["max_typos"], emulate_lanes=args.lanes)
@@ -119,25 +172,27 @@ def reference_lanes(args) -> int:
 
 
 def config_block(args, world, extra=None):
-    default = (WORKLOAD["needle"], WORKLOAD["max_typos"], WORKLOAD["mu"], WORKLOAD["max_len"]) == ("deadbeef", 1, 48, 64)
-    c = {"workload": f"needle '{WORKLOAD['needle']}' (len {len(WORKLOAD['needle'])}) vs {args.n} synthetic ASCII haystacks per GPU, "
+    default = (WORKLOAD["needle"], WORKLOAD["max_typos"], WORKLOAD["mu"], WORKLOAD["max_len"], args.query, args.shards_per_gpu) == ("deadbeef", 1, 48, 64, None, 1)
+    what = f"query '{args.query}'" if args.query else f"needle '{WORKLOAD['needle']}' (len {len(WORKLOAD['needle'])})"
+    kind = "ASCII" if args.unicode_frac == 0 else f"mixed-unicode ({args.unicode_frac:.0%} with multibyte scalars, {args.prefix_frac:.0%} 'bar' prefixes)"
+    c = {"workload": f"{what} vs {args.n * args.shards_per_gpu} synthetic {kind} haystacks per GPU, "
                      f"len<={WORKLOAD['max_len']} (mean {WORKLOAD['mu']}, sd {WORKLOAD['mu'] // 4}), max_typos={WORKLOAD['max_typos']}, "
                      f"5% full / 20% partial matches, seed 12345"
                      + (" (BASELINE.json configs[2], the configuration the 10x target is quoted on)" if default else ""),
-         "haystacks_per_gpu": args.n, "n_gpus": world, "sort": "ScoreThenIndexAsc",
+         "haystacks_per_gpu": args.n * args.shards_per_gpu, "n_gpus": world, "sort": "ScoreThenIndexAsc",
          "l2": "inputs (~560 MB packed per GPU) are larger than the 126 MB L2; no explicit flush"}
     if extra:
         c.update(extra)
     return c
 
 
-def pick_threads(cb, needle, cfg, data, off, trials=3):
+def pick_threads(cb, patterns, cfg, data, off, trials=3):
     """Thread count of the CPU arm: the reference's final k-way merge is single-threaded, so more threads is not always
     faster — the fastest of all / half / quarter of the host threads, decided on `trials` timed runs each."""
     threads = cb.host_threads()
     best = None
     for cand in sorted({threads, max(1, threads // 2), max(1, threads // 4)}, reverse=True):
-        dt, _ = cb.timed([needle], cfg, data, off, cand, repeats=trials)
+        dt, _ = cb.timed(patterns, cfg, data, off, cand, repeats=trials)
         if best is None or dt < best[0]:
             best = (dt, cand)
     return best[1]
@@ -164,18 +219,20 @@ def run_reference(args):
     from frizbee_b200 import synth
     from oracle import cpu_baseline as cb
     cfg = workload_config(args)
-    sample = args.cpu_sample or args.n   # the whole single-GPU workload: large enough to amortise thread start-up
-    data, off = synth.generate(WORKLOAD["needle"], sample, WORKLOAD["mu"], WORKLOAD["max_len"], WORKLOAD["seed"])
+    patterns = workload_patterns(args)
+    sample = args.cpu_sample or args.n   # one logical shard of the workload: large enough to amortise thread start-up
+    data, off = synth.generate(gen_needle(args), sample, WORKLOAD["mu"], WORKLOAD["max_len"], WORKLOAD["seed"],
+                               unicode_frac=args.unicode_frac, prefix_frac=args.prefix_frac)
     lanes = reference_lanes(args)
     cfg = cfg.with_(emulate_lanes=lanes)
-    threads = pick_threads(cb, WORKLOAD["needle"], cfg, data, off, trials=max(3, args.warmup))
+    threads = pick_threads(cb, patterns, cfg, data, off, trials=max(3, args.warmup))
     for _ in range(max(args.warmup, 3)):
-        cb.match_list_parallel([WORKLOAD["needle"]], cfg, data, off, threads)
+        cb.match_list_parallel(patterns, cfg, data, off, threads)
     per_step = []
     t0 = time.perf_counter()
     for _ in range(args.steps):
         t1 = time.perf_counter()
-        res = cb.match_list_parallel([WORKLOAD["needle"]], cfg, data, off, threads)
+        res = cb.match_list_parallel(patterns, cfg, data, off, threads)
         per_step.append(time.perf_counter() - t1)
     dt = time.perf_counter() - t0
     value = sample * args.steps / dt
@@ -195,13 +252,13 @@ def run_reference(args):
     print(json.dumps(line))
 
 
-def check_parity(cb, O, needle, cfg, data_np, off_np, index_offset, merged, rank, n_local, n_total):
+def check_parity(cb, O, patterns, cfg, data_np, off_np, index_offset, merged, rank, n_local, n_total):
     from frizbee_b200.types import SortStrategy
     """Full-shard parity: this rank's shard through the SIMD CPU restatement (validated bit-exact against the scalar
     oracle in tests/test_cpu_baseline.py) vs the entries of the MERGED list that fall into this rank's index range;
     rank 0 additionally checks the global order of the merged list and a 200k prefix against the scalar oracle."""
     threads = max(1, cb.host_threads() // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1")))))
-    want = cb.match_list_parallel([needle], cfg.with_(sort=SortStrategy.IndexAsc), data_np, off_np, threads)   # IndexAsc: the shard's matches in index order
+    want = cb.match_list_parallel(patterns, cfg.with_(sort=SortStrategy.IndexAsc), data_np, off_np, threads)   # IndexAsc: the shard's matches in index order
     want = want.copy()
     want["index"] += np.uint32(index_offset)
     lo, hi = index_offset, index_offset + n_local
@@ -219,7 +276,7 @@ def check_parity(cb, O, needle, cfg, data_np, off_np, index_offset, merged, rank
         info["order_violations"] = bad
         info["index_out_of_range"] = int(np.count_nonzero(i >= n_total))
         sub = min(n_local, 200_000)
-        w2 = O.match_list_packed([needle], cfg.with_(sort=SortStrategy.IndexAsc), data_np[: int(off_np[sub])], off_np[: sub + 1])
+        w2 = O.match_list_packed(patterns, cfg.with_(sort=SortStrategy.IndexAsc), data_np[: int(off_np[sub])], off_np[: sub + 1])
         g2 = mine[mine["index"] < sub + index_offset]
         ok = len(w2) == len(g2) and all(np.array_equal(w2[f], g2[f] if f != "index" else g2[f] - np.uint32(index_offset))
                                         for f in ("index", "score", "exact"))
@@ -229,6 +286,8 @@ def check_parity(cb, O, needle, cfg, data_np, off_np, index_offset, merged, rank
 
 
 def run_ours(args):
+    rank0 = int(os.environ.get("RANK", "0"))
+    RANK_DATA = make_rank_data(args, rank0)   # before torch / CUDA are initialised (may fork worker processes)
     import torch
     import torch.distributed as dist
     import frizbee_b200 as F
@@ -271,10 +330,11 @@ def run_ours(args):
         return int(t.item())
 
     cfg = workload_config(args)
-    n = args.n
+    n = args.n * args.shards_per_gpu
     needle = WORKLOAD["needle"]
-    # each rank holds its own shard (weak scaling); shard r covers indices [r*n, (r+1)*n)
-    data_np, off_np = synth.generate(needle, n, WORKLOAD["mu"], WORKLOAD["max_len"], WORKLOAD["seed"] + rank)
+    patterns = workload_patterns(args)
+    # each rank holds its own shard (weak scaling); rank r covers indices [r*n, (r+1)*n)
+    data_np, off_np = RANK_DATA
     # pinned host buffers: the inputs of the e2e call
     data_pin = torch.empty(data_np.size, dtype=torch.uint8, pin_memory=True)
     off_pin = torch.empty(off_np.size, dtype=torch.int64, pin_memory=True)
@@ -288,7 +348,7 @@ def run_ours(args):
 
     comm = parallel.Comm.from_torch_distributed(local)   # the data path's own NCCL communicator, behind the C ABI
     corpus = F.Corpus.from_arrow(data_h, off_h, device=local)
-    matcher = F.Matcher(needle, cfg)
+    matcher = F.Matcher.from_query(args.query, cfg) if args.query else F.Matcher(needle, cfg)
     info = matcher.backend_info()
     index_offset = rank * n
 
@@ -317,13 +377,14 @@ def run_ours(args):
         barrier()
         merged = np.array(out_h[:n_matches])   # every rank reads the whole shared buffer
         pcfg = cfg.with_(emulate_lanes=info["prefilter_lanes"])
-        pi = check_parity(cb, O, needle, pcfg, data_np, off_np, index_offset, merged, rank, n, n * world)
+        pi = check_parity(cb, O, patterns, pcfg, data_np, off_np, index_offset, merged, rank, n, n * world)
         mism = sum_over_ranks(pi["mismatches"])
         checked = sum_over_ranks(pi["matches_checked"])
         parity = dict(pi, mismatches=mism, matches_checked=checked, haystacks_checked=n * world,
                       matches_in_merged_list=int(n_matches),
-                      checker="oracle/cpu_baseline (SIMD restatement, bit-exact with the scalar oracle: tests/test_cpu_baseline.py), "
-                              "every rank its whole shard; rank 0: global order + scalar-oracle 200k prefix")
+                      checker=("oracle/cpu_baseline (SIMD restatement, bit-exact with the scalar oracle: tests/test_cpu_baseline.py)"
+                               if (not args.query and WORKLOAD["max_typos"] in (0, 1)) else "the scalar oracle (oracle/frz_oracle.cpp), threaded over 2048-item chunks")
+                              + ", every rank its whole shard; rank 0: global order + scalar-oracle 200k prefix")
         if checked != n_matches:
             parity["mismatches"] = mism + abs(checked - n_matches)
         del merged
@@ -387,8 +448,11 @@ def run_ours(args):
 
     # ---- timed region: end to end (host buffers in, host matches out)
     e2e_steps = args.e2e_steps or min(args.steps, 5)
-    step_e2e()   # warm
-    e_ms, n_e2e, _ = timed(step_e2e, e2e_steps)
+    if e2e_steps > 0:
+        step_e2e()   # warm
+        e_ms, n_e2e, _ = timed(step_e2e, e2e_steps)
+    else:            # --e2e-steps -1: profiling / large strong-scaling runs skip the end-to-end leg
+        e_ms, n_e2e, e2e_steps = float("nan"), n_matches, 1
     e2e_value = n * world * e2e_steps / (e_ms / 1e3)
     h2d = int(data_h.nbytes + off_e2e.nbytes)
     d2h_rank = int(n_e2e * 8 / world + 64)
@@ -406,7 +470,7 @@ def run_ours(args):
         traffic = None
         try:
             tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-            if (needle, WORKLOAD["max_typos"], WORKLOAD["mu"], WORKLOAD["max_len"], n) == ("deadbeef", 1, 48, 64, 10_000_000):
+            if (needle, WORKLOAD["max_typos"], WORKLOAD["mu"], WORKLOAD["max_len"], n, args.query) == ("deadbeef", 1, 48, 64, 10_000_000, None):
                 traffic = int(tj["dram_bytes_read"] + tj["dram_bytes_write"])   # from the committed ncu capture
         except Exception:
             pass
@@ -424,8 +488,8 @@ def run_ours(args):
             sample = args.cpu_sample or n
             ccfg = cfg.with_(emulate_lanes=info["prefilter_lanes"])
             sd, so = data_np[: int(off_np[sample])], off_np[: sample + 1]
-            threads = pick_threads(cb, needle, ccfg, sd, so, trials=3)
-            per = [cb.timed([needle], ccfg, sd, so, threads, repeats=1)[0] for _ in range(7)]
+            threads = pick_threads(cb, patterns, ccfg, sd, so, trials=3)
+            per = [cb.timed(patterns, ccfg, sd, so, threads, repeats=1)[0] for _ in range(7)]
             dt = float(np.median(per))
             cpu = {"value": sample / dt, "unit": "haystacks/s", "cores": threads, "kind": "port",
                    "value_best": sample / min(per),

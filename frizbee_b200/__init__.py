@@ -36,7 +36,8 @@ class FrizbeeError(RuntimeError):
 
 
 def lib_path() -> str:
-    return os.path.join(_HERE, "libfrz_cuda.so")
+    """libfrz_cuda.so next to this file; FRZ_LIB names an A/B build instead (frizbee_b200/build.py --variant)."""
+    return os.environ.get("FRZ_LIB") or os.path.join(_HERE, "libfrz_cuda.so")
 
 
 _lib = None

@@ -48,7 +48,16 @@ __global__ void __launch_bounds__(kSortWarps * 32) k_sort_hist(const FrzMatchDev
     unsigned long long lo, hi;
     segment_of(*n_ptr, v, &lo, &hi);
     const uint32_t mask = (uint32_t)bins - 1;
-    for (unsigned long long i = lo + lane; i < hi; i += 32) atomicAdd(&cnt[digit_of(in[i], shift, mask)], 1u);
+    // four loads in flight per lane: the walk is latency-bound (one 256-byte line per trip)
+    unsigned long long i = lo + lane;
+    for (; i + 96 < hi; i += 128) {
+        const FrzMatchDev a = in[i], b = in[i + 32], c = in[i + 64], d = in[i + 96];
+        atomicAdd(&cnt[digit_of(a, shift, mask)], 1u);
+        atomicAdd(&cnt[digit_of(b, shift, mask)], 1u);
+        atomicAdd(&cnt[digit_of(c, shift, mask)], 1u);
+        atomicAdd(&cnt[digit_of(d, shift, mask)], 1u);
+    }
+    for (; i < hi; i += 32) atomicAdd(&cnt[digit_of(in[i], shift, mask)], 1u);
     __syncwarp();
     for (int d = lane; d < bins; d += 32) hist[(size_t)d * kV + v] = cnt[d];
 }
@@ -120,12 +129,18 @@ __global__ void __launch_bounds__(kSortWarps * 32) k_sort_scatter(const FrzMatch
     unsigned long long lo, hi;
     segment_of(*n_ptr, v, &lo, &hi);
     const uint32_t mask = (uint32_t)bins - 1;
+    // the element of the NEXT trip is loaded before this trip's rank / counter chain (software pipelining: the walk has
+    // to stay in order for stability, so the only parallelism inside a segment is load-ahead)
+    FrzMatchDev nxt;
+    nxt.index = 0; nxt.score = 0; nxt.exact = 0; nxt.pad = 0;
+    if (lo + lane < hi) nxt = in[lo + lane];
     for (unsigned long long base = lo; base < hi; base += 32) {
         const unsigned long long i = base + lane;
         const bool valid = i < hi;
-        FrzMatchDev m;
+        const FrzMatchDev m = nxt;
+        if (i + 32 < hi) nxt = in[i + 32];
         uint32_t d = (uint32_t)bins + lane;  // sentinel: matches nobody
-        if (valid) { m = in[i]; d = digit_of(m, shift, mask); }
+        if (valid) d = digit_of(m, shift, mask);
         const uint32_t peers = __match_any_sync(0xffffffffu, d);
         const uint32_t rank = __popc(peers & ((1u << lane) - 1));
         uint32_t pos = 0;

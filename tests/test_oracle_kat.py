@@ -109,6 +109,10 @@ def test_score_fits_in_u8():
 
 # ---- lane-dependence evidence; the oracle must show it, not hide it ----
 def test_sw_is_lane_dependent_on_known_vectors():
+    # PROVENANCE: restatement-derived.  No reference test holds these numbers (the reference's parity tests happen not to
+    # hit lane-dependent inputs); they were found by the surveyor's restatement and are reproduced by this one.  They pin
+    # the oracle against regressions and document the property (LANES is part of the specification), nothing more —
+    # re-verify with cargo on a box that has rustc.
     a = [score("ab_", "-1Abb1-aabB1-bbaAa-_bb/b0ABB/-0/Aa-a0a/1_/", l, 8) for l in (16, 32, 64)]
     assert a == [35, 34, 34]
     b = [score("eyqoof", "eA21viFrVA1k7gylcKJMa0amSvnEEVFU2YBOO9UgbFmrjkBzK0jo6ge", l, 8) for l in (16, 32, 64)]
