@@ -114,7 +114,17 @@ class ClockSampler:
 def _gen_one(job):
     from frizbee_b200 import synth
     needle, n, mu, max_len, seed, ufrac, pfrac = job
-    return synth.generate(needle, n, mu, max_len, seed, unicode_frac=ufrac, prefix_frac=pfrac)
+    cache = os.environ.get("FRZ_BENCH_CACHE")   # A/B sweeps: generate a list once per box, reload it afterwards
+    if cache:
+        key = os.path.join(cache, f"synth_{needle}_{n}_{mu}_{max_len}_{seed}_{ufrac}_{pfrac}")
+        if os.path.exists(key + "_o.npy"):
+            return np.load(key + "_d.npy"), np.load(key + "_o.npy")
+    data, off = synth.generate(needle, n, mu, max_len, seed, unicode_frac=ufrac, prefix_frac=pfrac)
+    if cache:
+        os.makedirs(cache, exist_ok=True)
+        np.save(key + "_d.npy", data)
+        np.save(key + "_o.npy", off)
+    return data, off
 
 
 def gen_needle(args) -> str:

@@ -458,7 +458,42 @@ __device__ __forceinline__ void process_candidate(const FrzCorpusView& cv, const
 //   phase B  whenever 32 candidates are queued: lane per candidate, occurrence masks + the reference's window state
 //            machine on the candidate's bytes (process_candidate), all lanes busy.
 // Loads are software-pipelined two groups ahead (a warp has no other way to keep HBM busy).
-template <int MODE>
+// ---- TMA variant of the phase-A loads (A/B: FRZ_PF_TMA=1) -----------------------------------------------------
+// The metadata and signature arrays are contiguous, so a warp's next CHUNK of kTmaGroups groups is two 1-D bulk copies
+// (cp.async.bulk global→shared, 512 + 1024 bytes) that complete on the warp's own mbarrier: still warp-autonomous, no
+// block barrier, no registers held by loads in flight.  Two stages per warp.
+constexpr int kTmaGroups = 4;
+struct __align__(16) TmaStage {
+    uint32_t meta[kTmaGroups * FRZ_GROUP];
+    uint2 sig[kTmaGroups * FRZ_GROUP];
+};
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
+                 "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+template <int MODE, bool TMA>
 __global__ void __launch_bounds__(kThreads, 6) k_prefilter(const FrzCorpusView cv, const __grid_constant__ FrzPatternDev pat,
                                                            const FrzSurvLists lists, unsigned long long surv_cap,
                                                            uint32_t* __restrict__ surv_bitmap, FrzCounters* __restrict__ ctr) {
@@ -514,28 +549,81 @@ __global__ void __launch_bounds__(kThreads, 6) k_prefilter(const FrzCorpusView c
             count += __popc(ballot);
         }
     };
-    Grp g0, g1, g2;
-    load_grp(g0);
-    load_grp(g1);
-    load_grp(g2);
-    for (;;) {
-        const bool done = g0.gidx == 0xFFFFFFFFu;
-        if (!done) {
-            phase_a(g0);
-            g0 = g1;
-            g1 = g2;
-            load_grp(g2);
+    if constexpr (!TMA) {
+        Grp g0, g1, g2;
+        load_grp(g0);
+        load_grp(g1);
+        load_grp(g2);
+        for (;;) {
+            const bool done = g0.gidx == 0xFFFFFFFFu;
+            if (!done) {
+                phase_a(g0);
+                g0 = g1;
+                g1 = g2;
+                load_grp(g2);
+            }
+            // -------------------------------------------------------- phase B on full batches; the partial
+            // batch is flushed through the same (single inlined) call site once the groups are exhausted
+            while (count >= 32 || (done && count > 0)) {
+                __syncwarp();
+                process_candidate<MODE>(cv, pat, cid_s, q, (head + lane) & (kQueueCap - 1), lane < count, lists, surv_cap, surv_bitmap, ctr);
+                head = (head + 32) & (kQueueCap - 1);
+                count = count > 32 ? count - 32 : 0;
+                __syncwarp();
+            }
+            if (done) break;
         }
-        // -------------------------------------------------------- phase B on full batches; the partial
-        // batch is flushed through the same (single inlined) call site once the groups are exhausted
-        while (count >= 32 || (done && count > 0)) {
-            __syncwarp();
-            process_candidate<MODE>(cv, pat, cid_s, q, (head + lane) & (kQueueCap - 1), lane < count, lists, surv_cap, surv_bitmap, ctr);
-            head = (head + 32) & (kQueueCap - 1);
-            count = count > 32 ? count - 32 : 0;
-            __syncwarp();
+    } else {
+        TmaStage* stages = reinterpret_cast<TmaStage*>(smem_raw + sizeof(WarpQueue) * kWarps) + warp * 2;
+        uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + sizeof(WarpQueue) * kWarps + sizeof(TmaStage) * 2 * kWarps) + warp * 2;
+        if (lane == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        __syncwarp();
+        const uint32_t total_chunks = total_groups / kTmaGroups;   // 32 groups per tile: chunks never straddle the end
+        const uint32_t tx_bytes = (uint32_t)sizeof(uint32_t) * kTmaGroups * FRZ_GROUP + (use_sig ? (uint32_t)sizeof(uint2) * kTmaGroups * FRZ_GROUP : 0u);
+        uint32_t chunk_next = blockIdx.x * kWarps + warp;   // next chunk to REQUEST (stride n_warps)
+        auto issue = [&](int st) {
+            if (chunk_next < total_chunks && lane == 0) {
+                const uint64_t slot0 = (uint64_t)chunk_next * kTmaGroups * FRZ_GROUP;
+                mbar_expect_tx(&bars[st], tx_bytes);
+                bulk_g2s(stages[st].meta, cv.slot_meta + slot0, (uint32_t)sizeof(uint32_t) * kTmaGroups * FRZ_GROUP, &bars[st]);
+                if (use_sig) bulk_g2s(stages[st].sig, cv.slot_sig + slot0, (uint32_t)sizeof(uint2) * kTmaGroups * FRZ_GROUP, &bars[st]);
+            }
+            chunk_next += n_warps;
+        };
+        uint32_t chunk_cur = chunk_next;
+        issue(0);
+        issue(1);
+        int st = 0;
+        uint32_t parity = 0;
+        for (;;) {
+            const bool done = chunk_cur >= total_chunks;
+            if (!done) {
+                mbar_wait(&bars[st], parity);
+#pragma unroll
+                for (int k = 0; k < kTmaGroups; k++) {
+                    Grp g;
+                    g.gidx = chunk_cur * kTmaGroups + k;
+                    g.meta = stages[st].meta[k * FRZ_GROUP + lane];
+                    g.sig = use_sig ? stages[st].sig[k * FRZ_GROUP + lane] : make_uint2(0u, 0u);
+                    phase_a(g);
+                }
+                __syncwarp();
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic reads of the stage before its async refill
+                issue(st);
+                chunk_cur += n_warps;
+                st ^= 1;
+                if (st == 0) parity ^= 1;
+            }
+            while (count >= 32 || (done && count > 0)) {
+                __syncwarp();
+                process_candidate<MODE>(cv, pat, cid_s, q, (head + lane) & (kQueueCap - 1), lane < count, lists, surv_cap, surv_bitmap, ctr);
+                head = (head + 32) & (kQueueCap - 1);
+                count = count > 32 ? count - 32 : 0;
+                __syncwarp();
+            }
+            if (done) break;
         }
-        if (done) break;
     }
 }
 
@@ -735,20 +823,28 @@ frz_status frz_launch_prefilter(const FrzCorpusView& cv, const FrzPatternDev& pa
     const uint32_t total_groups = cv.n_tiles * FRZ_GROUPS_PER_TILE;
     FRZ_CUDA_TRY(cudaMemsetAsync(ws.surv_bitmap, 0, (size_t)cv.n_tiles * 32 * sizeof(uint32_t), stream));
     // persistent warps: as many blocks as fit on the SMs (registers / shared memory), capped by the work
-#define FRZ_PF_LAUNCH(MODE)                                                                                              \
+    static int tma_knob = -1;   // A/B knob: FRZ_PF_TMA=1 stages the phase-A arrays with cp.async.bulk + mbarrier
+    if (tma_knob < 0) { const char* e = getenv("FRZ_PF_TMA"); tma_knob = e ? atoi(e) : 0; }
+    const size_t smem_tma = smem + (sizeof(TmaStage) * 2 + sizeof(uint64_t) * 2) * kWarps;
+#define FRZ_PF_LAUNCH_T(MODE, TMA, SMEM)                                                                                 \
     do {                                                                                                                 \
         static int bps_dev[64] = {};                                                                                     \
         int& bps = bps_dev[frz_current_device() & 63];                                                                   \
         if (!bps) {                                                                                                      \
-            FRZ_CUDA_TRY(cudaFuncSetAttribute(k_prefilter<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-            FRZ_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_prefilter<MODE>, kThreads, smem));        \
+            FRZ_CUDA_TRY(cudaFuncSetAttribute(k_prefilter<MODE, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMEM))); \
+            FRZ_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_prefilter<MODE, TMA>, kThreads, (SMEM)));  \
             static int knob = -1;   /* experiment knob: FRZ_PF_BLOCKS caps the resident blocks per SM */                 \
             if (knob < 0) { const char* e = getenv("FRZ_PF_BLOCKS"); knob = e ? atoi(e) : 0; }                           \
             if (knob > 0 && knob < bps) bps = knob;                                                                      \
             if (bps < 1) bps = 1;                                                                                        \
         }                                                                                                                \
         const uint32_t grid = std::max<uint32_t>(1, std::min<uint32_t>((uint32_t)(sms * bps), (total_groups + kWarps - 1) / kWarps)); \
-        k_prefilter<MODE><<<grid, kThreads, smem, stream>>>(cv, pat, ws.lists(), ws.survivor_cap, ws.surv_bitmap, ws.counters); \
+        k_prefilter<MODE, TMA><<<grid, kThreads, (SMEM), stream>>>(cv, pat, ws.lists(), ws.survivor_cap, ws.surv_bitmap, ws.counters); \
+    } while (0)
+#define FRZ_PF_LAUNCH(MODE)                                                       \
+    do {                                                                          \
+        if (tma_knob) FRZ_PF_LAUNCH_T(MODE, true, smem_tma);                      \
+        else FRZ_PF_LAUNCH_T(MODE, false, smem);                                  \
     } while (0)
     switch (pat.typo_mode) {
         case FRZ_T_0: FRZ_PF_LAUNCH(FRZ_T_0); break;
@@ -760,6 +856,7 @@ frz_status frz_launch_prefilter(const FrzCorpusView& cv, const FrzPatternDev& pa
         default: return frz_fail(FRZ_ERR_INVALID_ARG, "bad typo mode %d", pat.typo_mode);
     }
 #undef FRZ_PF_LAUNCH
+#undef FRZ_PF_LAUNCH_T
     FRZ_CUDA_TRY(cudaGetLastError());
     if (st) st->launches++;
     return FRZ_OK;
