@@ -366,7 +366,7 @@ template <int MODE>
 __device__ __forceinline__ void process_candidate(const FrzCorpusView& cv, const FrzPatternDev& pat, const uint8_t* __restrict__ cid_s,
                                                   WarpQueue& q, int entry, bool active, const FrzSurvLists& lists,
                                                   unsigned long long surv_cap, uint32_t* __restrict__ surv_bitmap,
-                                                  FrzCounters* __restrict__ ctr) {
+                                                  FrzCounters* __restrict__ ctr, bool single_chunk = false) {
     const uint32_t lane = frz_lane();
     bool ok = false;
     int cls = 0;
@@ -384,8 +384,13 @@ __device__ __forceinline__ void process_candidate(const FrzCorpusView& cv, const
     bool flat_done = false, flat_ok = false;
     int flat_start = 0, flat_end = 0;
     if ((MODE == FRZ_T_0 || MODE == FRZ_T_1) && pat.n_distinct > 0) {
-        if (MODE == FRZ_T_0) flat_ok = masks_k0(ga.base, pat, cid_s, q.occ, len, active, &flat_start, &flat_end);
-        else flat_ok = masks_k1(ga.base, pat, cid_s, q.occ, len, active, &flat_start, &flat_end);
+        if (single_chunk) {   // warp-uniform: corpus of <= 64-byte haystacks at the 64-lane width (prefilter_masks.cuh)
+            if (MODE == FRZ_T_0) flat_ok = masks_k0_single(ga.base, pat, q.occ, len, active, &flat_start, &flat_end);
+            else flat_ok = masks_k1_single(ga.base, pat, q.occ, len, active, &flat_start, &flat_end);
+        } else {
+            if (MODE == FRZ_T_0) flat_ok = masks_k0(ga.base, pat, cid_s, q.occ, len, active, &flat_start, &flat_end);
+            else flat_ok = masks_k1(ga.base, pat, cid_s, q.occ, len, active, &flat_start, &flat_end);
+        }
         flat_done = true;
     }
 #ifdef FRZ_PF_MASKS_K2   // experiment build: the CPU-checked mask forms of the 2-typo / N-typo trackers (prefilter_masks.cuh)
@@ -496,7 +501,8 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 template <int MODE, bool TMA>
 __global__ void __launch_bounds__(kThreads, 6) k_prefilter(const FrzCorpusView cv, const __grid_constant__ FrzPatternDev pat,
                                                            const FrzSurvLists lists, unsigned long long surv_cap,
-                                                           uint32_t* __restrict__ surv_bitmap, FrzCounters* __restrict__ ctr) {
+                                                           uint32_t* __restrict__ surv_bitmap, FrzCounters* __restrict__ ctr,
+                                                           uint32_t flags) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const uint32_t lane = frz_lane(), warp = threadIdx.x >> 5;
     WarpQueue& q = reinterpret_cast<WarpQueue*>(smem_raw)[warp];
@@ -506,6 +512,7 @@ __global__ void __launch_bounds__(kThreads, 6) k_prefilter(const FrzCorpusView c
     __syncthreads();
 
     const bool use_sig = MODE != FRZ_T_NONE && pat.sig_on != 0;
+    const bool single = (MODE == FRZ_T_0 || MODE == FRZ_T_1) && (flags & 1u) && single_chunk_ok(pat, cv.max_gunits);
     const uint32_t need1 = pat.sig_need1, need2 = pat.sig_need2;
     const int sig_k = pat.sig_k;
     const int min_len = pat.min_hay_len;
@@ -566,7 +573,7 @@ __global__ void __launch_bounds__(kThreads, 6) k_prefilter(const FrzCorpusView c
             // batch is flushed through the same (single inlined) call site once the groups are exhausted
             while (count >= 32 || (done && count > 0)) {
                 __syncwarp();
-                process_candidate<MODE>(cv, pat, cid_s, q, (head + lane) & (kQueueCap - 1), lane < count, lists, surv_cap, surv_bitmap, ctr);
+                process_candidate<MODE>(cv, pat, cid_s, q, (head + lane) & (kQueueCap - 1), lane < count, lists, surv_cap, surv_bitmap, ctr, single);
                 head = (head + 32) & (kQueueCap - 1);
                 count = count > 32 ? count - 32 : 0;
                 __syncwarp();
@@ -617,7 +624,7 @@ __global__ void __launch_bounds__(kThreads, 6) k_prefilter(const FrzCorpusView c
             }
             while (count >= 32 || (done && count > 0)) {
                 __syncwarp();
-                process_candidate<MODE>(cv, pat, cid_s, q, (head + lane) & (kQueueCap - 1), lane < count, lists, surv_cap, surv_bitmap, ctr);
+                process_candidate<MODE>(cv, pat, cid_s, q, (head + lane) & (kQueueCap - 1), lane < count, lists, surv_cap, surv_bitmap, ctr, single);
                 head = (head + 32) & (kQueueCap - 1);
                 count = count > 32 ? count - 32 : 0;
                 __syncwarp();
@@ -823,6 +830,9 @@ frz_status frz_launch_prefilter(const FrzCorpusView& cv, const FrzPatternDev& pa
     const uint32_t total_groups = cv.n_tiles * FRZ_GROUPS_PER_TILE;
     FRZ_CUDA_TRY(cudaMemsetAsync(ws.surv_bitmap, 0, (size_t)cv.n_tiles * 32 * sizeof(uint32_t), stream));
     // persistent warps: as many blocks as fit on the SMs (registers / shared memory), capped by the work
+    static int single_knob = -1;   // A/B knob: FRZ_PF_SINGLE=0 keeps the general (multi-chunk) mask forms
+    if (single_knob < 0) { const char* e = getenv("FRZ_PF_SINGLE"); single_knob = e ? atoi(e) : 1; }
+    const uint32_t pf_flags = single_knob ? 1u : 0u;
     static int tma_knob = -1;   // A/B knob: FRZ_PF_TMA=1 stages the phase-A arrays with cp.async.bulk + mbarrier
     if (tma_knob < 0) { const char* e = getenv("FRZ_PF_TMA"); tma_knob = e ? atoi(e) : 0; }
     const size_t smem_tma = smem + (sizeof(TmaStage) * 2 + sizeof(uint64_t) * 2) * kWarps;
@@ -839,7 +849,8 @@ frz_status frz_launch_prefilter(const FrzCorpusView& cv, const FrzPatternDev& pa
             if (bps < 1) bps = 1;                                                                                        \
         }                                                                                                                \
         const uint32_t grid = std::max<uint32_t>(1, std::min<uint32_t>((uint32_t)(sms * bps), (total_groups + kWarps - 1) / kWarps)); \
-        k_prefilter<MODE, TMA><<<grid, kThreads, (SMEM), stream>>>(cv, pat, ws.lists(), ws.survivor_cap, ws.surv_bitmap, ws.counters); \
+        k_prefilter<MODE, TMA><<<grid, kThreads, (SMEM), stream>>>(cv, pat, ws.lists(), ws.survivor_cap, ws.surv_bitmap, ws.counters, \
+                                                                   pf_flags);                                            \
     } while (0)
 #define FRZ_PF_LAUNCH(MODE)                                                       \
     do {                                                                          \

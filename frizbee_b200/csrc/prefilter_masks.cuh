@@ -203,6 +203,102 @@ FRZ_PF_FN bool masks_k1(const uint4* base, const FrzPatternDev& pat, const uint8
     return state == 1;
 }
 
+// ---- single-chunk forms -------------------------------------------------------------------------------------
+// When no haystack of the corpus exceeds 64 bytes and the emulated prefilter width is 64 lanes, a candidate is ONE block
+// and ONE chunk: the chunk loop, the `>> sh` alignment and the lane mask of the general forms disappear, and a step that
+// finds nothing rejects at once.  The masks are also re-indexed per needle POSITION (pos[i] = occ[cid[i]], stored behind
+// the distinct classes in the same shared-memory array when n_distinct + n <= kMaxDistinct), so every step of the state
+// machine costs one LDS.64 instead of two dependent loads (class id, then mask): phase B is latency-bound, the chain
+// length is what matters.  Bit-identical to masks_k0 / masks_k1 (tests/test_kernel_logic_cpu.py).
+FRZ_PF_FN bool single_chunk_ok(const FrzPatternDev& pat, uint32_t max_gunits) {
+    return max_gunits <= 4 && pat.pf_lanes == 64 && pat.n_distinct > 0 && pat.n_distinct + pat.n <= kMaxDistinct;
+}
+FRZ_PF_FN void build_position_masks(const FrzPatternDev& pat, uint2 (*occ)[32], uint32_t lane) {
+    const int nd = pat.n_distinct;
+    for (int i = 0; i < pat.n; i++) occ[nd + i][lane] = occ[pat.cid[i]][lane];   // a lane only ever touches its own column
+}
+
+FRZ_PF_FN bool masks_k0_single(const uint4* base, const FrzPatternDev& pat, uint2 (*occ)[32], int len, bool active,
+                               int* ostart, int* oend) {
+    const uint32_t lane = FRZ_PF_LANE;
+    const int n = pat.n, nd = pat.n_distinct;
+    build_block_masks(base, active ? (len + 15) >> 4 : 0, 0, pat, occ, lane);
+    build_position_masks(pat, occ, lane);
+    const uint64_t valid = len > 0 ? lowmask64(len) : 0ull;
+    const uint64_t lastm = u2_to_u64(occ[nd + n - 1][lane]) & valid;
+    int start = 0, ni = 0;
+    uint64_t fc = valid;
+    bool run = active && len > 0, found = false;
+    while (__any_sync(0xffffffffu, run)) {
+        if (run) {
+            const uint64_t x = u2_to_u64(occ[nd + ni][lane]) & fc;
+            if (x) {
+                if (ni == 0) start = __ffsll((long long)x) - 1;
+                fc &= ~(x ^ (x - 1));  // clear_through_lowest
+                if (++ni == n) { found = true; run = false; }
+            } else run = false;
+        }
+    }
+    *ostart = start;
+    *oend = lastm ? 64 - __clzll((long long)lastm) : 0;
+    return found;
+}
+
+FRZ_PF_FN bool masks_k1_single(const uint4* base, const FrzPatternDev& pat, uint2 (*occ)[32], int len, bool active,
+                               int* ostart, int* oend) {
+    const uint32_t lane = FRZ_PF_LANE;
+    const int n = pat.n, nd = pat.n_distinct;
+    build_block_masks(base, active ? (len + 15) >> 4 : 0, 0, pat, occ, lane);
+    build_position_masks(pat, occ, lane);
+    const uint64_t valid = len > 0 ? lowmask64(len) : 0ull;
+    int end = -1;
+    if (n >= 2) {   // find_end_pos_with_typos: 1 + last occurrence of either of the last two needle bytes, else len
+        const uint64_t lastm = (u2_to_u64(occ[nd + n - 1][lane]) | u2_to_u64(occ[nd + n - 2][lane])) & valid;
+        if (lastm) end = 64 - __clzll((long long)lastm);
+    }
+    int f = 0, s = 1, ms = 0x7fffffff;
+    int state = 2;   // 0 running, 1 found, 2 rejected / idle
+    if (active) state = n <= 1 ? 1 : (len == 0 ? 2 : 0);
+    if (active && n <= 1) ms = 0;
+    uint64_t fc = valid, sc = valid, fm = 0, sm = 0;
+    if (state == 0) { fm = u2_to_u64(occ[nd][lane]); sm = u2_to_u64(occ[nd + 1][lane]); }
+    while (__any_sync(0xffffffffu, state == 0)) {
+        if (state == 0) {
+            bool adv = false;
+            const int cand = f + 1;
+            if (cand > s) {
+                if (cand == n) state = 1;
+                else { s = cand; sc = fc; sm = u2_to_u64(occ[nd + s][lane]); }
+            } else if (cand == s && fc > sc) sc = fc;
+            if (state == 0) {
+                const uint64_t x = fm & fc;
+                if (x) {
+                    ms = min(ms, __ffsll((long long)x) - 1);
+                    f++;
+                    fc &= ~(x ^ (x - 1));
+                    fm = u2_to_u64(occ[nd + f][lane]);
+                    adv = true;
+                }
+                const uint64_t y = sm & sc;
+                if (y) {
+                    ms = min(ms, __ffsll((long long)y) - 1);
+                    s++;
+                    if (s >= n) state = 1;
+                    else {
+                        sc &= ~(y ^ (y - 1));
+                        sm = u2_to_u64(occ[nd + s][lane]);
+                        adv = true;
+                    }
+                }
+                if (state == 0 && !adv) state = 2;   // the next chunk would start at 64 >= len
+            }
+        }
+    }
+    *ostart = ms == 0x7fffffff ? 0 : ms;
+    *oend = end < 0 ? len : end;
+    return state == 1;
+}
+
 // ---- groundwork for the tuned 2-typo / N-typo paths.  Both are checked against the oracle on
 // the CPU (tests/test_kernel_logic_cpu.py) but NOT yet called by the kernels (FRZ_T_2 / FRZ_T_MANY still use the
 // scanning forms window_k2 / window_many of prefilter.cu): wiring them in needs a GPU run for registers and timing.

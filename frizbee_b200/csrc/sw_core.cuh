@@ -100,6 +100,7 @@ struct RowStore<R, true> {
 // VAR selects which one-lane shifts use IMAD/IMAD.HI (fma pipe) instead of PRMT (alu pipe):
 //   bit 0: diagonal shift of the previous row; bit 1: score shift of gap step 1; bit 2: mask shift of gap step 1;
 //   bit 3: the per-column bonus is classified on the packed bytes (4 at a time) instead of per 16-bit lane
+//   bit 4: gap step 1 folds the shifted match mask into the penalty with IMAD.HI + IMAD (no mask shift at all)
 //
 // CC (<= COLS, multiple of 8) is the number of columns actually evaluated.  Cells never depend on cells to
 // their right, and a cell in column >= W + needle_len can only hold a value that decayed from a cell to its
@@ -260,7 +261,8 @@ struct SwCore {
                         if (s == 1 && !WRAP8) {
                             if (VAR & 2) sh = r == 0 ? H[0] * 0x10000u : shl16(H[r - 1], H[r]);
                             else sh = r == 0 ? __byte_perm(0u, H[0], 0x5432) : __byte_perm(H[r - 1], H[r], 0x5432);
-                            if (VAR & 4) smm = r == 0 ? M[0] * 0x10000u : shl16(M[r - 1], M[r]);
+                            if (VAR & 16) smm = 0;   // folded into the penalty below
+                            else if (VAR & 4) smm = r == 0 ? M[0] * 0x10000u : shl16(M[r - 1], M[r]);
                             else smm = r == 0 ? __byte_perm(0u, M[0], 0x5432) : __byte_perm(M[r - 1], M[r], 0x5432);
                         } else if (s == 1) {
                             if (r == 0) { sh = __byte_perm(0u, H[0], 0x5432); smm = __byte_perm(0u, M[0], 0x5432); }
@@ -271,7 +273,16 @@ struct SwCore {
                             sh = H[src];
                             smm = M[src];
                         }
-                        const uint32_t pen = WRAP8 ? sel(smm, penB, penA) : penB + smm * gopx;
+                        uint32_t pen;
+                        if (WRAP8) pen = sel(smm, penB, penA);
+                        else if (s == 1 && (VAR & 16)) {
+                            // VAR bit 4: pen = penB + shifted(M) * gopx without materialising the shifted mask — the high
+                            // lane of M[r-1] reaches the low lane through IMAD.HI (addend penB), the low lane of M[r] reaches
+                            // the high lane through IMAD: two FMA-pipe instructions instead of PRMT (ALU pipe) + IMAD
+                            const uint32_t g16 = gopx << 16;
+                            const uint32_t t = (r == 0 ? 0u : __umulhi(M[r - 1], g16)) + penB;
+                            pen = M[r] * g16 + t;
+                        } else pen = penB + smm * gopx;
                         H[r] = addmax_relu(sh, pen, H[r]);
                     }
                 }

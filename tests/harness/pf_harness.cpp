@@ -25,6 +25,12 @@ int h_masks_window(const void* pat_bytes, const uint8_t* hay, int len, int mode,
     }
     static uint2 occ[kMaxDistinct][32];
     bool ok;
+    if (mode >= 100) {   // single-chunk forms (len <= 64, 64-lane emulation)
+        if (!single_chunk_ok(pat, (uint32_t)((len + 15) / 16))) return -2;
+        ok = mode == 100 ? masks_k0_single(data.data(), pat, occ, len, true, start, end)
+                         : masks_k1_single(data.data(), pat, occ, len, true, start, end);
+        return ok ? 1 : 0;
+    }
     switch (mode) {
         case 0: ok = masks_k0(data.data(), pat, pat.cid, occ, len, true, start, end); break;
         case 1: ok = masks_k1(data.data(), pat, pat.cid, occ, len, true, start, end); break;

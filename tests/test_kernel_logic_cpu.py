@@ -79,7 +79,7 @@ def test_swcore_column_classes_equal_oracle(H, lanes):
                 if cc < need or cc < W:
                     continue
                 eq = C.c_int()
-                var = rng.choice([0, 1, 3, 5, 7, 8, 11]) if lanes == 64 else 0
+                var = rng.choice([0, 1, 3, 5, 7, 8, 11, 16, 17, 18, 19, 26, 27]) if lanes == 64 else 0
                 got = H.h_swcore(pat, win, W, rng.randint(0, 15), int(pre), lanes, 64, cc, 0, var, C.byref(eq))
                 assert got == want, (needle, win, cs, pre, lanes, cc, var, got, want)
                 assert bool(eq.value) == (win == needle)
@@ -175,6 +175,35 @@ def test_mask_prefilter_windows_equal_oracle(H, PF, lanes, k):
                 matched += 1
             checked += 1
     assert checked > 5000 and matched > 500
+
+
+@pytest.mark.parametrize("k", [0, 1])
+def test_single_chunk_mask_forms_equal_oracle(H, PF, k):
+    """masks_k0_single / masks_k1_single (corpora of <= 64-byte haystacks at the 64-lane width: one block, one chunk,
+    per-position masks) vs the oracle's Prefilter::match_haystack / match_haystack_1_typo."""
+    rng = random.Random(9100 + k)
+    F.lib().frz_matcher_debug_pattern.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]
+    checked = matched = 0
+    for trial in range(900):
+        pool = rng.choice(POOLS)
+        needle = rand_bytes(rng, pool, rng.randint(1, 11))
+        cs = rng.random() < 0.3
+        cfg = Config(max_typos=k, emulate_lanes=64, casing=CaseMatching.Respect if cs else CaseMatching.Ignore)
+        pat, info = device_pattern(H, needle, cfg)
+        for _ in range(12):
+            ln = rng.choice([0, 1, 2, 3, 7, 15, 16, 17, 31, 32, 33, 47, 48, 50, 63, 64])
+            hay = rand_bytes(rng, pool + (HAY_EXTRA if rng.random() < 0.2 else b"x"), ln)
+            s, e = C.c_int(), C.c_int()
+            got = PF.h_masks_window(pat, hay, len(hay), 100 + k, C.byref(s), C.byref(e))
+            if got == -2:
+                continue   # needle too long for the position table: the kernel takes the general form
+            want = O.prefilter(needle, hay, k, 64, cs)
+            assert bool(got) == want[0], (needle, hay, k, cs, want)
+            if want[0]:
+                assert (s.value, e.value) == (want[1], want[2]), (needle, hay, k, cs, want, s.value, e.value)
+                matched += 1
+            checked += 1
+    assert checked > 6000 and matched > 800
 
 
 @pytest.mark.parametrize("lanes", [16, 32, 64])
