@@ -167,6 +167,9 @@ struct FrzCounters {
     unsigned int error;                             // sticky device-side error flags
     unsigned int sw_next;                           // next 32-survivor work item of the SW kernel
     unsigned int pad_;
+    unsigned long long cand_count;                  // candidate records written by k_sig_scan
+    unsigned int pf_next;                           // next 32-candidate work item of k_window
+    unsigned int pad2_;
 };
 
 #define FRZ_DEVERR_SURVIVOR_OVERFLOW 1u

@@ -114,8 +114,8 @@ struct FrzWorkspace {
     uint64_t match_cap = 0;
     uint32_t* sort_hist = nullptr;          // [256 * n_sort_blocks]
     uint64_t sort_hist_cap = 0;
-    uint32_t* cand_bitmap = nullptr;        // (unused by the list mode; kept for the bitmap-restricted scan)
-    uint64_t cand_cap = 0;
+    void* cand_list = nullptr;              // k_sig_scan → k_window candidate records (16 bytes each)
+    uint64_t cand_cap = 0;                  // in records
     uint32_t* retain_cnt = nullptr;         // multi-pattern stable compaction scratch
     uint64_t* retain_base = nullptr;
     uint8_t* retain_keep = nullptr;

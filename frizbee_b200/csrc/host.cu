@@ -585,10 +585,10 @@ void FrzWorkspace::release() {
     if (h_counters) cudaFreeHost(h_counters);
     for (auto& s : survivors) { cudaFree(s); s = nullptr; }
     cudaFree(surv_bitmap); cudaFree(word_prefix); surv_bitmap = nullptr; word_prefix = nullptr;
-    cudaFree(tile_count); cudaFree(tile_out_base); cudaFree(matches_a); cudaFree(matches_b); cudaFree(sort_hist); cudaFree(cand_bitmap);
+    cudaFree(tile_count); cudaFree(tile_out_base); cudaFree(matches_a); cudaFree(matches_b); cudaFree(sort_hist); cudaFree(cand_list);
     for (auto& e : ev) { if (e) cudaEventDestroy(e); e = nullptr; }
     counters = nullptr; h_counters = nullptr; tile_count = nullptr; tile_out_base = nullptr; matches_a = matches_b = nullptr;
-    sort_hist = nullptr; cand_bitmap = nullptr;
+    sort_hist = nullptr; cand_list = nullptr;
     cudaFree(retain_cnt); cudaFree(retain_base); cudaFree(retain_keep); retain_cnt = nullptr; retain_base = nullptr; retain_keep = nullptr; retain_cap = 0;
     cudaFree(unicode_scratch); unicode_scratch = nullptr; unicode_scratch_cap = 0;
     survivor_cap = match_cap = sort_hist_cap = cand_cap = 0; tiles_cap = 0; device = -1;
@@ -871,6 +871,12 @@ frz_status ensure_workspace(frz_matcher* m, const FrzCorpusStorage& cs, uint64_t
         ws.survivor_cap = 0;
         for (auto& s : ws.survivors) FRZ_CUDA_TRY(cudaMalloc(&s, (size_t)survivor_cap * sizeof(FrzSurvivor)));
         ws.survivor_cap = survivor_cap;
+    }
+    if (ws.cand_cap < std::max<uint64_t>(cs.n, 1)) {   // worst case: every haystack passes the signature test
+        cudaFree(ws.cand_list); ws.cand_list = nullptr; ws.cand_cap = 0;
+        const uint64_t want = std::max<uint64_t>(cs.n, 1);
+        FRZ_CUDA_TRY(cudaMalloc(&ws.cand_list, (size_t)want * 16));
+        ws.cand_cap = want;
     }
     if (ws.match_cap < cs.n) {
         cudaFree(ws.matches_a); cudaFree(ws.matches_b);

@@ -21,6 +21,7 @@
 //            per-tile bitmap; k_tile_rank turns the bitmap into index-order ranks so that the
 //            scoring stage can write each match straight to its index-ordered position.
 #include "frz_device.cuh"
+#include <cuda_pipeline.h>
 #include <algorithm>
 
 #include "frz_host.h"
@@ -337,11 +338,7 @@ __device__ bool lit_find(const A& a, const FrzPatternDev& p, int len, int* opos,
 }
 
 
-constexpr int kQueueCap = 128;  // per-warp candidate queue (31 left over + 2 x 32 new at most per loop trip)
-
-struct WarpQueue {
-    uint32_t meta[kQueueCap];                // tile << 10 | slot
-    uint32_t info[kQueueCap];                // len
+struct OccTable {
     uint2 occ[kMaxDistinct][32];             // per-lane occurrence masks of the distinct needle byte classes
 };
 
@@ -353,18 +350,34 @@ __device__ __forceinline__ int sw_class_of(int window, const FrzPatternDev& pat)
     // more than the chunks the reference evaluates
     const int chunk_cols = (window + pat.sw_lanes - 1) / pat.sw_lanes * pat.sw_lanes;
     const int need = min(window + pat.n, chunk_cols);
-#ifdef FRZ_SW_TWO_CLASSES   // experiment build: two column classes, half the SW kernel's dynamic instruction footprint
-    return need <= 48 ? FRZ_C_CC48 : FRZ_C_COLS64;
-#else
+    // four classes: two (48 / 64) were measured 3% SLOWER on B200 (the extra columns cost more than the smaller kernel saves)
     return need <= 40 ? FRZ_C_CC40 : need <= 48 ? FRZ_C_CC48 : need <= 56 ? FRZ_C_CC56 : FRZ_C_COLS64;
-#endif
 }
 
 // Exact window of one queued candidate (phase B) + survivor emission.  All 32 lanes of the warp call
 // this together (`active` lanes have an entry); emission uses warp-aggregated atomics.
+// One candidate as phase B sees it.  `units` is where the mask builders read the haystack's 16-byte units from (unit k at
+// units + 32 * k): the packed corpus itself, or this lane's column of a shared-memory stage filled by cp.async.
+struct Cand {
+    uint32_t tile, slot, li;   // li = index of the haystack inside its tile
+    int len;
+    const uint4* base;         // unit 0 of the slot in the packed corpus
+    const uint4* units;
+};
+// resolves (tile, slot) through the group descriptor and the slot metadata (candidate lists of the multi-pattern path)
+__device__ __forceinline__ Cand resolve_cand(const FrzCorpusView& cv, uint32_t tile, uint32_t slot, int len) {
+    Cand c;
+    c.tile = tile; c.slot = slot; c.len = len;
+    const FrzGroupDesc gd = cv.groups[tile * FRZ_GROUPS_PER_TILE + (slot >> 5)];
+    c.base = cv.data + gd.abs_off + (slot & 31);
+    c.units = c.base;
+    c.li = cv.slot_meta[(uint64_t)tile * FRZ_TILE + slot] & (FRZ_TILE - 1);
+    return c;
+}
+
 template <int MODE>
 __device__ __forceinline__ void process_candidate(const FrzCorpusView& cv, const FrzPatternDev& pat, const uint8_t* __restrict__ cid_s,
-                                                  WarpQueue& q, int entry, bool active, const FrzSurvLists& lists,
+                                                  uint2 (*occ)[32], const Cand& cd, bool active, const FrzSurvLists& lists,
                                                   unsigned long long surv_cap, uint32_t* __restrict__ surv_bitmap,
                                                   FrzCounters* __restrict__ ctr, bool single_chunk = false) {
     const uint32_t lane = frz_lane();
@@ -372,36 +385,33 @@ __device__ __forceinline__ void process_candidate(const FrzCorpusView& cv, const
     int cls = 0;
     FrzSurvivor rec;
     rec.tile = 0; rec.slot_rank = 0; rec.start = 0; rec.end = 0;
-    const uint32_t meta0 = active ? q.meta[entry] : 0u;
-    const uint32_t tile = meta0 >> FRZ_TILE_SHIFT, slot = meta0 & (FRZ_TILE - 1);
-    const int len = active ? (int)q.info[entry] : 0;
-    GlobalAcc ga{nullptr};
-    if (active) {
-        const FrzGroupDesc gd = cv.groups[tile * FRZ_GROUPS_PER_TILE + (slot >> 5)];
-        ga.base = cv.data + gd.abs_off + (slot & 31);
-    }
+    const uint32_t tile = cd.tile, slot = cd.slot;
+    const int len = active ? cd.len : 0;
+    GlobalAcc ga{active ? cd.base : nullptr};
+    const uint4* units = active ? cd.units : nullptr;
     // warp-wide occurrence-mask windows (uniform code) for the 0- and 1-typo modes
     bool flat_done = false, flat_ok = false;
     int flat_start = 0, flat_end = 0;
     if ((MODE == FRZ_T_0 || MODE == FRZ_T_1) && pat.n_distinct > 0) {
         if (single_chunk) {   // warp-uniform: corpus of <= 64-byte haystacks at the 64-lane width (prefilter_masks.cuh)
-            if (MODE == FRZ_T_0) flat_ok = masks_k0_single(ga.base, pat, q.occ, len, active, &flat_start, &flat_end);
-            else flat_ok = masks_k1_single(ga.base, pat, q.occ, len, active, &flat_start, &flat_end);
+            if (MODE == FRZ_T_0) flat_ok = masks_k0_single(units, pat, occ, len, active, &flat_start, &flat_end);
+            else flat_ok = masks_k1_single(units, pat, occ, len, active, &flat_start, &flat_end);
         } else {
-            if (MODE == FRZ_T_0) flat_ok = masks_k0(ga.base, pat, cid_s, q.occ, len, active, &flat_start, &flat_end);
-            else flat_ok = masks_k1(ga.base, pat, cid_s, q.occ, len, active, &flat_start, &flat_end);
+            if (MODE == FRZ_T_0) flat_ok = masks_k0(units, pat, cid_s, occ, len, active, &flat_start, &flat_end);
+            else flat_ok = masks_k1(units, pat, cid_s, occ, len, active, &flat_start, &flat_end);
         }
         flat_done = true;
     }
-#ifdef FRZ_PF_MASKS_K2   // experiment build: the CPU-checked mask forms of the 2-typo / N-typo trackers (prefilter_masks.cuh)
+    // 2-typo / N-typo trackers on the same occurrence masks (prefilter_masks.cuh: masks_paths<3>, masks_many).  Measured on
+    // B200 against the scanning forms window_k2 / window_many (profiles/r02b_sw_variants.txt, 10 M haystacks): k = 2
+    // 2.79 -> 0.21 ms, k = 3 2.25 -> 0.42 ms.  The scanning forms remain for needles with > 16 distinct byte classes.
     if ((MODE == FRZ_T_2 || MODE == FRZ_T_MANY) && pat.n_distinct > 0) {
-        if (MODE == FRZ_T_2) flat_ok = masks_paths<3>(ga.base, pat, cid_s, q.occ, len, active, &flat_start, &flat_end);
-        else flat_ok = masks_many(ga.base, pat, cid_s, q.occ, len, active, &flat_start, &flat_end);
+        if (MODE == FRZ_T_2) flat_ok = masks_paths<3>(units, pat, cid_s, occ, len, active, &flat_start, &flat_end);
+        else flat_ok = masks_many(units, pat, cid_s, occ, len, active, &flat_start, &flat_end);
         flat_done = true;
     }
-#endif
     if (active) {
-        const uint32_t li = cv.slot_meta[(uint64_t)tile * FRZ_TILE + slot] & (FRZ_TILE - 1);
+        const uint32_t li = cd.li;
         int start = 0, end = len;
         uint32_t lit_score = 0;
         if (flat_done) { ok = flat_ok; start = flat_start; end = flat_end; }
@@ -455,183 +465,190 @@ __device__ __forceinline__ void process_candidate(const FrzCorpusView& cv, const
     }
 }
 
-// Warp-autonomous, barrier-free: every warp strides over groups.
-//   phase A  lane per haystack: ONE coalesced 4-byte load (length) and ONE coalesced 8-byte load (the byte-class
-//            signature written at pack time) decide "can this haystack hold the needle up to the typo budget?" —
-//            two POPCs.  The haystack's own bytes are not touched: a rejected haystack costs 12 bytes of HBM traffic
-//            instead of len + 8.  Passing lanes push (tile, slot, len) into the warp's shared-memory ring.
-//   phase B  whenever 32 candidates are queued: lane per candidate, occurrence masks + the reference's window state
-//            machine on the candidate's bytes (process_candidate), all lanes busy.
-// Loads are software-pipelined two groups ahead (a warp has no other way to keep HBM busy).
-// ---- TMA variant of the phase-A loads (A/B: FRZ_PF_TMA=1) -----------------------------------------------------
-// The metadata and signature arrays are contiguous, so a warp's next CHUNK of kTmaGroups groups is two 1-D bulk copies
-// (cp.async.bulk global→shared, 512 + 1024 bytes) that complete on the warp's own mbarrier: still warp-autonomous, no
-// block barrier, no registers held by loads in flight.  Two stages per warp.
-constexpr int kTmaGroups = 4;
-struct __align__(16) TmaStage {
-    uint32_t meta[kTmaGroups * FRZ_GROUP];
-    uint2 sig[kTmaGroups * FRZ_GROUP];
+// ================================================================================================================
+// Stage 1a  k_sig_scan — the streaming half.  Lane per FOUR consecutive haystacks: one 16-byte load of their lengths and
+// two 16-byte loads of their byte-class signatures (written at pack time, pack.cu: k_pack_sig) decide "can this
+// haystack hold the needle up to the typo budget?" (two POPCs each).  The haystack bytes themselves are never touched
+// here: a rejected haystack costs 12 bytes of HBM traffic instead of len + 8.  Survivors of the test become 16-byte
+// candidate records {tile << 10 | slot, len << 10 | index-in-tile, address of unit 0}: the group descriptor is resolved
+// here (four contiguous 16-byte descriptors per trip, L2-resident), so stage 1b starts its unit loads straight from the
+// record.  Warp-autonomous: a per-warp ring in shared memory collects candidates, every 32 are flushed with ONE atomic
+// and one coalesced 512-byte store.  Small (about 40 registers): 12 blocks per SM keep enough bytes in flight to stream
+// at HBM speed — in the fused kernel the same loop sat at 47% of the stall samples waiting on its own loads behind
+// the 76-register window code (profiles/r02b_*).
+constexpr int kScanThreads = 128;
+constexpr int kScanWarps = kScanThreads / 32;
+constexpr int kScanRing = 256;   // entries per warp: up to 31 left over + up to 128 new per trip
+
+struct __align__(16) CandRec {
+    uint32_t tile_slot;   // tile << 10 | slot
+    uint32_t meta;        // len << 10 | index inside the tile
+    uint64_t unit0;       // unit index (16-byte units from the start of the packed data) of the slot's unit 0
 };
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
-                 "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE_%=;\n"
-        "bra WAIT_%=;\n"
-        "DONE_%=:\n"
-        "}\n" ::"r"(smem_u32(bar)),
-        "r"(parity)
-        : "memory");
+
+__global__ void __launch_bounds__(kScanThreads, 12) k_sig_scan(const FrzCorpusView cv, int use_sig, uint32_t need1, uint32_t need2,
+                                                               int sig_k, int min_len, CandRec* __restrict__ cand,
+                                                               unsigned long long cand_cap, FrzCounters* __restrict__ ctr) {
+    __shared__ CandRec ring_s[kScanWarps][kScanRing];
+    const uint32_t lane = frz_lane(), warp = threadIdx.x >> 5;
+    CandRec* ring = ring_s[warp];
+    const uint32_t n_warps = gridDim.x * kScanWarps;
+    const uint32_t total_chunks = cv.n_tiles * (FRZ_TILE / 128);   // 128 slots (4 groups) per chunk
+    uint32_t head = 0, count = 0;
+    struct Chunk {
+        uint4 meta;
+        uint4 sig0, sig1;
+        uint32_t idx;
+    };
+    uint32_t next = blockIdx.x * kScanWarps + warp;
+    auto load_chunk = [&](Chunk& c) {
+        c.idx = next;
+        c.meta = make_uint4(FRZ_INVALID_SLOT, FRZ_INVALID_SLOT, FRZ_INVALID_SLOT, FRZ_INVALID_SLOT);
+        c.sig0 = c.sig1 = make_uint4(0u, 0u, 0u, 0u);
+        if (next < total_chunks) {
+            const uint64_t slot0 = (uint64_t)next * 128 + lane * 4;
+            c.meta = __ldg(reinterpret_cast<const uint4*>(cv.slot_meta + slot0));
+            if (use_sig) {
+                const uint4* sp = reinterpret_cast<const uint4*>(cv.slot_sig + slot0);
+                c.sig0 = __ldg(sp);
+                c.sig1 = __ldg(sp + 1);
+            }
+        } else {
+            c.idx = 0xFFFFFFFFu;
+        }
+        next += n_warps;
+    };
+    auto flush = [&](uint32_t n_out) {   // the first n_out (<= 32) ring entries → global list
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(&ctr->cand_count, (unsigned long long)n_out);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (lane < n_out) {
+            const unsigned long long pos = base + lane;
+            if (pos < cand_cap) cand[pos] = ring[(head + lane) & (kScanRing - 1)];
+            else atomicOr(&ctr->error, FRZ_DEVERR_SURVIVOR_OVERFLOW);
+        }
+        head = (head + n_out) & (kScanRing - 1);
+        count -= n_out;
+    };
+    Chunk c0, c1;
+    load_chunk(c0);
+    load_chunk(c1);
+    while (c0.idx != 0xFFFFFFFFu) {
+        // group descriptors of this chunk's four groups: lanes 0-3 load one each (contiguous 64 bytes)
+        unsigned long long abs_off = 0;
+        if (lane < 4) abs_off = cv.groups[c0.idx * 4 + lane].abs_off;
+        const uint32_t m[4] = {c0.meta.x, c0.meta.y, c0.meta.z, c0.meta.w};
+        const uint32_t s1[4] = {c0.sig0.x, c0.sig0.z, c0.sig1.x, c0.sig1.z};
+        const uint32_t s2[4] = {c0.sig0.y, c0.sig0.w, c0.sig1.y, c0.sig1.w};
+        const unsigned long long my_off = __shfl_sync(0xffffffffu, abs_off, lane >> 3);   // slots 4*lane..4*lane+3 sit in group lane / 8
+        const uint32_t chunk_idx = c0.idx;
+        c0 = c1;
+        load_chunk(c1);
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const bool valid = m[j] != FRZ_INVALID_SLOT;
+            const int len = valid ? (int)(m[j] >> FRZ_TILE_SHIFT) : 0;
+            bool pass = valid && len >= min_len;
+            if (use_sig) pass = pass && frz_sig_pass(need1, need2, sig_k, s1[j], s2[j]);
+            const uint32_t ballot = __ballot_sync(0xffffffffu, pass);
+            if (pass) {
+                const uint32_t slot_in_chunk = lane * 4 + j;                       // 0..127
+                CandRec r;
+                r.tile_slot = chunk_idx * 128 + slot_in_chunk;                     // == tile << 10 | slot
+                r.meta = m[j];
+                r.unit0 = my_off + (slot_in_chunk & 31);
+                ring[(head + count + __popc(ballot & ((1u << lane) - 1))) & (kScanRing - 1)] = r;
+            }
+            count += __popc(ballot);
+        }
+        __syncwarp();
+        while (count >= 32) flush(32);
+        __syncwarp();
+    }
+    if (count) flush(count);
 }
 
-template <int MODE, bool TMA>
-__global__ void __launch_bounds__(kThreads, 6) k_prefilter(const FrzCorpusView cv, const __grid_constant__ FrzPatternDev pat,
+// ================================================================================================================
+// Stage 1b  k_window — the exact reference window (process_candidate) on the candidates, lane per candidate.
+// Work items are 32 consecutive candidate records, claimed from a device counter.  The loop is software-pipelined two
+// items deep: while item i is in the mask builders / state machine, item i+1's haystack units travel global → shared
+// with cp.async (the record carries the unit address: no dependent descriptor load) and item i+2's records are in
+// flight — the scattered unit loads are what phase B of the fused kernel stalled on.
+constexpr int kWinThreads = 128;
+constexpr int kWinWarps = kWinThreads / 32;
+struct WinStage {
+    uint4 units[4][32];   // [unit][lane]: conflict-free 16-byte columns, same 32-unit stride as the packed corpus
+};
+struct WinSmem {
+    uint2 occ[kMaxDistinct][32];
+    WinStage stage[2];
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(kWinThreads, 6) k_window(const FrzCorpusView cv, const __grid_constant__ FrzPatternDev pat,
+                                                           const CandRec* __restrict__ cand, unsigned long long cand_cap,
                                                            const FrzSurvLists lists, unsigned long long surv_cap,
                                                            uint32_t* __restrict__ surv_bitmap, FrzCounters* __restrict__ ctr,
                                                            uint32_t flags) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const uint32_t lane = frz_lane(), warp = threadIdx.x >> 5;
-    WarpQueue& q = reinterpret_cast<WarpQueue*>(smem_raw)[warp];
-    // needle index → distinct class, indexed per lane (a divergent index would serialise in the constant bank)
+    WinSmem& sm = reinterpret_cast<WinSmem*>(smem_raw)[warp];
     __shared__ uint8_t cid_s[FRZ_MAX_NEEDLE];
     if (threadIdx.x < FRZ_MAX_NEEDLE) cid_s[threadIdx.x] = pat.cid[threadIdx.x];
     __syncthreads();
-
-    const bool use_sig = MODE != FRZ_T_NONE && pat.sig_on != 0;
+    const unsigned long long n_cand = min(ctr->cand_count, cand_cap);
+    const uint32_t n_items = (uint32_t)((n_cand + 31) >> 5);
+    const bool staged = cv.max_gunits <= 4;   // every haystack fits the four staged units
     const bool single = (MODE == FRZ_T_0 || MODE == FRZ_T_1) && (flags & 1u) && single_chunk_ok(pat, cv.max_gunits);
-    const uint32_t need1 = pat.sig_need1, need2 = pat.sig_need2;
-    const int sig_k = pat.sig_k;
-    const int min_len = pat.min_hay_len;
 
-    const uint32_t n_warps = gridDim.x * kWarps;
-    const uint32_t total_groups = cv.n_tiles * FRZ_GROUPS_PER_TILE;
-    uint32_t head = 0, count = 0;  // ring state (warp-uniform)
-
-    struct Grp {
-        uint32_t meta;
-        uint2 sig;
-        uint32_t gidx;
+    auto claim = [&]() {
+        uint32_t t = 0;
+        if (lane == 0) t = atomicAdd(&ctr->pf_next, 1u);
+        return __shfl_sync(0xffffffffu, t, 0);
     };
-    uint32_t gen = blockIdx.x * kWarps + warp;   // this warp's next group (stride n_warps)
-    auto load_grp = [&](Grp& g) {
-        g.gidx = gen;
-        g.meta = FRZ_INVALID_SLOT;
-        g.sig = make_uint2(0u, 0u);
-        if (gen < total_groups) {
-            const uint64_t idx = (uint64_t)gen * FRZ_GROUP + lane;   // == tile * 1024 + group * 32 + lane
-            g.meta = __ldg(cv.slot_meta + idx);
-            if (use_sig) g.sig = __ldg(cv.slot_sig + idx);
-        } else {
-            g.gidx = 0xFFFFFFFFu;
-        }
-        gen += n_warps;
+    auto load_rec = [&](uint32_t item) {
+        CandRec r;
+        r.tile_slot = 0xFFFFFFFFu; r.meta = 0; r.unit0 = 0;
+        const unsigned long long j = (unsigned long long)item * 32 + lane;
+        if (item < n_items && j < n_cand) r = cand[j];
+        return r;
     };
-    auto phase_a = [&](const Grp& g) {
-        const uint32_t meta = g.meta;
-        const bool valid = meta != FRZ_INVALID_SLOT;
-        const uint32_t len = valid ? meta >> FRZ_TILE_SHIFT : 0;
-        bool pass = valid && (int)len >= min_len;
-        if (use_sig) pass = pass && frz_sig_pass(need1, need2, sig_k, g.sig.x, g.sig.y);
-        const uint32_t ballot = __ballot_sync(0xffffffffu, pass);
-        if (ballot) {
-            if (pass) {
-                const uint32_t e = (head + count + __popc(ballot & ((1u << lane) - 1))) & (kQueueCap - 1);
-                q.meta[e] = (g.gidx << 5) | lane;   // (tile << 10) | slot, slot = group-in-tile * 32 + lane
-                q.info[e] = len;
-            }
-            count += __popc(ballot);
-        }
-    };
-    if constexpr (!TMA) {
-        Grp g0, g1, g2;
-        load_grp(g0);
-        load_grp(g1);
-        load_grp(g2);
-        for (;;) {
-            const bool done = g0.gidx == 0xFFFFFFFFu;
-            if (!done) {
-                phase_a(g0);
-                g0 = g1;
-                g1 = g2;
-                load_grp(g2);
-            }
-            // -------------------------------------------------------- phase B on full batches; the partial
-            // batch is flushed through the same (single inlined) call site once the groups are exhausted
-            while (count >= 32 || (done && count > 0)) {
-                __syncwarp();
-                process_candidate<MODE>(cv, pat, cid_s, q, (head + lane) & (kQueueCap - 1), lane < count, lists, surv_cap, surv_bitmap, ctr, single);
-                head = (head + 32) & (kQueueCap - 1);
-                count = count > 32 ? count - 32 : 0;
-                __syncwarp();
-            }
-            if (done) break;
-        }
-    } else {
-        TmaStage* stages = reinterpret_cast<TmaStage*>(smem_raw + sizeof(WarpQueue) * kWarps) + warp * 2;
-        uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + sizeof(WarpQueue) * kWarps + sizeof(TmaStage) * 2 * kWarps) + warp * 2;
-        if (lane == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        __syncwarp();
-        const uint32_t total_chunks = total_groups / kTmaGroups;   // 32 groups per tile: chunks never straddle the end
-        const uint32_t tx_bytes = (uint32_t)sizeof(uint32_t) * kTmaGroups * FRZ_GROUP + (use_sig ? (uint32_t)sizeof(uint2) * kTmaGroups * FRZ_GROUP : 0u);
-        uint32_t chunk_next = blockIdx.x * kWarps + warp;   // next chunk to REQUEST (stride n_warps)
-        auto issue = [&](int st) {
-            if (chunk_next < total_chunks && lane == 0) {
-                const uint64_t slot0 = (uint64_t)chunk_next * kTmaGroups * FRZ_GROUP;
-                mbar_expect_tx(&bars[st], tx_bytes);
-                bulk_g2s(stages[st].meta, cv.slot_meta + slot0, (uint32_t)sizeof(uint32_t) * kTmaGroups * FRZ_GROUP, &bars[st]);
-                if (use_sig) bulk_g2s(stages[st].sig, cv.slot_sig + slot0, (uint32_t)sizeof(uint2) * kTmaGroups * FRZ_GROUP, &bars[st]);
-            }
-            chunk_next += n_warps;
-        };
-        uint32_t chunk_cur = chunk_next;
-        issue(0);
-        issue(1);
-        int st = 0;
-        uint32_t parity = 0;
-        for (;;) {
-            const bool done = chunk_cur >= total_chunks;
-            if (!done) {
-                mbar_wait(&bars[st], parity);
+    auto stage_units = [&](const CandRec& r, int st) {
+        if (staged && r.tile_slot != 0xFFFFFFFFu) {
+            const int units = ((int)(r.meta >> FRZ_TILE_SHIFT) + 15) >> 4;
+            const uint4* base = cv.data + r.unit0;
 #pragma unroll
-                for (int k = 0; k < kTmaGroups; k++) {
-                    Grp g;
-                    g.gidx = chunk_cur * kTmaGroups + k;
-                    g.meta = stages[st].meta[k * FRZ_GROUP + lane];
-                    g.sig = use_sig ? stages[st].sig[k * FRZ_GROUP + lane] : make_uint2(0u, 0u);
-                    phase_a(g);
-                }
-                __syncwarp();
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic reads of the stage before its async refill
-                issue(st);
-                chunk_cur += n_warps;
-                st ^= 1;
-                if (st == 0) parity ^= 1;
-            }
-            while (count >= 32 || (done && count > 0)) {
-                __syncwarp();
-                process_candidate<MODE>(cv, pat, cid_s, q, (head + lane) & (kQueueCap - 1), lane < count, lists, surv_cap, surv_bitmap, ctr, single);
-                head = (head + 32) & (kQueueCap - 1);
-                count = count > 32 ? count - 32 : 0;
-                __syncwarp();
-            }
-            if (done) break;
+            for (int k = 0; k < 4; k++)
+                if (k < units) __pipeline_memcpy_async(&sm.stage[st].units[k][lane], base + (size_t)k * FRZ_GROUP, 16);
         }
+        __pipeline_commit();
+    };
+    uint32_t item0 = claim(), item1 = claim();
+    CandRec rec0 = load_rec(item0);
+    stage_units(rec0, 0);
+    CandRec rec1 = load_rec(item1);
+    int st = 0;
+    while (item0 < n_items) {
+        const uint32_t item2 = claim();
+        stage_units(rec1, st ^ 1);              // next item's units start moving ...
+        const CandRec rec2 = load_rec(item2);   // ... and the one after that requests its records
+        __pipeline_wait_prior(1);               // this item's units have landed
+        __syncwarp();
+        const bool active = rec0.tile_slot != 0xFFFFFFFFu;
+        Cand cd;
+        cd.tile = rec0.tile_slot >> FRZ_TILE_SHIFT;
+        cd.slot = rec0.tile_slot & (FRZ_TILE - 1);
+        cd.li = rec0.meta & (FRZ_TILE - 1);
+        cd.len = (int)(rec0.meta >> FRZ_TILE_SHIFT);
+        cd.base = cv.data + rec0.unit0;
+        cd.units = staged ? &sm.stage[st].units[0][lane] : cd.base;
+        process_candidate<MODE>(cv, pat, cid_s, sm.occ, cd, active, lists, surv_cap, surv_bitmap, ctr, single);
+        __syncwarp();
+        item0 = item1; rec0 = rec1;
+        item1 = item2; rec1 = rec2;
+        st ^= 1;
     }
+    __pipeline_wait_prior(0);
 }
 
 // Candidate-list mode (multi-pattern, src/matcher/multi.rs:108-120): the extra patterns are evaluated only
@@ -645,7 +662,7 @@ __global__ void __launch_bounds__(kThreads) k_prefilter_list(const FrzCorpusView
                                                              uint32_t* __restrict__ surv_bitmap, FrzCounters* __restrict__ ctr) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const uint32_t lane = frz_lane(), warp = threadIdx.x >> 5;
-    WarpQueue& q = reinterpret_cast<WarpQueue*>(smem_raw)[warp];
+    uint2 (*occ)[32] = reinterpret_cast<OccTable*>(smem_raw)[warp].occ;
     __shared__ uint8_t cid_s[FRZ_MAX_NEEDLE];
     if (threadIdx.x < FRZ_MAX_NEEDLE) cid_s[threadIdx.x] = pat.cid[threadIdx.x];
     __syncthreads();
@@ -653,17 +670,18 @@ __global__ void __launch_bounds__(kThreads) k_prefilter_list(const FrzCorpusView
     for (unsigned long long base = ((unsigned long long)blockIdx.x * kWarps + warp) * 32; base < n_cand; base += n_warps * 32) {
         const unsigned long long i = base + lane;
         bool active = i < n_cand;
+        Cand cd;
+        cd.tile = 0; cd.slot = 0; cd.li = 0; cd.len = 0; cd.base = nullptr; cd.units = nullptr;
         if (active) {
             const uint32_t idx = cand[i].index - index_offset;
             const uint32_t tile = idx >> FRZ_TILE_SHIFT, li = idx & (FRZ_TILE - 1);
             const uint32_t slot = cv.slot_of[(uint64_t)tile * FRZ_TILE + li];
             const uint32_t len = cv.slot_meta[(uint64_t)tile * FRZ_TILE + slot] >> FRZ_TILE_SHIFT;
             active = (int)len >= pat.min_hay_len;   // length gate (src/matcher/algo.rs:88)
-            q.meta[lane] = (tile << FRZ_TILE_SHIFT) | slot;
-            q.info[lane] = len;
+            cd = resolve_cand(cv, tile, slot, (int)len);
         }
         __syncwarp();
-        process_candidate<MODE>(cv, pat, cid_s, q, lane, active, lists, surv_cap, surv_bitmap, ctr);
+        process_candidate<MODE>(cv, pat, cid_s, occ, cd, active, lists, surv_cap, surv_bitmap, ctr);
         __syncwarp();
     }
 }
@@ -788,22 +806,13 @@ frz_status frz_launch_prefilter_list(const FrzCorpusView& cv, const FrzPatternDe
                                      uint64_t n_cand, uint32_t index_offset, FrzWorkspace& ws, cudaStream_t stream,
                                      FrzLaunchStats* st) {
     if (cv.n_tiles == 0) return FRZ_OK;
-    const size_t smem = sizeof(WarpQueue) * kWarps;
+    const size_t smem = sizeof(OccTable) * kWarps;
     FRZ_CUDA_TRY(cudaMemsetAsync(ws.surv_bitmap, 0, (size_t)cv.n_tiles * 32 * sizeof(uint32_t), stream));
     if (n_cand == 0) return FRZ_OK;
     const uint32_t grid = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(148 * 4, (n_cand + kThreads - 1) / kThreads));
 #define FRZ_PFL_LAUNCH(MODE)                                                                                     \
-    do {                                                                                                         \
-        static bool attr_set_dev[64] = {};                                                                       \
-        bool& attr_set = attr_set_dev[frz_current_device() & 63];                                                \
-        if (!attr_set) {                                                                                         \
-            FRZ_CUDA_TRY(cudaFuncSetAttribute(k_prefilter_list<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-            attr_set = true;                                                                                     \
-        }                                                                                                        \
-        k_prefilter_list<MODE><<<grid, kThreads, smem, stream>>>(cv, pat, cand, n_cand, index_offset, ws.lists(),         \
-                                                                 ws.survivor_cap,                                         \
-                                                                 ws.surv_bitmap, ws.counters);                            \
-    } while (0)
+    k_prefilter_list<MODE><<<grid, kThreads, smem, stream>>>(cv, pat, cand, n_cand, index_offset, ws.lists(),    \
+                                                             ws.survivor_cap, ws.surv_bitmap, ws.counters)
     switch (pat.typo_mode) {
         case FRZ_T_0: FRZ_PFL_LAUNCH(FRZ_T_0); break;
         case FRZ_T_1: FRZ_PFL_LAUNCH(FRZ_T_1); break;
@@ -819,43 +828,48 @@ frz_status frz_launch_prefilter_list(const FrzCorpusView& cv, const FrzPatternDe
     return FRZ_OK;
 }
 
+// Stage 1 of match_list over the whole corpus: k_sig_scan (streaming signature test → candidate records) and
+// k_window (exact windows of the candidates → survivor records + per-tile survivor bitmap).
 frz_status frz_launch_prefilter(const FrzCorpusView& cv, const FrzPatternDev& pat, FrzWorkspace& ws, cudaStream_t stream,
                                 FrzLaunchStats* st) {
     if (cv.n_tiles == 0) return FRZ_OK;
-    const size_t smem = sizeof(WarpQueue) * kWarps;
     int sms = 0, dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (sms <= 0) sms = 148;
-    const uint32_t total_groups = cv.n_tiles * FRZ_GROUPS_PER_TILE;
     FRZ_CUDA_TRY(cudaMemsetAsync(ws.surv_bitmap, 0, (size_t)cv.n_tiles * 32 * sizeof(uint32_t), stream));
-    // persistent warps: as many blocks as fit on the SMs (registers / shared memory), capped by the work
     static int single_knob = -1;   // A/B knob: FRZ_PF_SINGLE=0 keeps the general (multi-chunk) mask forms
     if (single_knob < 0) { const char* e = getenv("FRZ_PF_SINGLE"); single_knob = e ? atoi(e) : 1; }
     const uint32_t pf_flags = single_knob ? 1u : 0u;
-    static int tma_knob = -1;   // A/B knob: FRZ_PF_TMA=1 stages the phase-A arrays with cp.async.bulk + mbarrier
-    if (tma_knob < 0) { const char* e = getenv("FRZ_PF_TMA"); tma_knob = e ? atoi(e) : 0; }
-    const size_t smem_tma = smem + (sizeof(TmaStage) * 2 + sizeof(uint64_t) * 2) * kWarps;
-#define FRZ_PF_LAUNCH_T(MODE, TMA, SMEM)                                                                                 \
+    CandRec* cand = reinterpret_cast<CandRec*>(ws.cand_list);
+    {   // 1a: persistent warps, as many blocks as fit
+        static int bps_dev[64] = {};
+        int& bps = bps_dev[frz_current_device() & 63];
+        if (!bps) {
+            FRZ_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_sig_scan, kScanThreads, 0));
+            if (bps < 1) bps = 1;
+        }
+        const uint32_t total_chunks = cv.n_tiles * (FRZ_TILE / 128);
+        const uint32_t grid = std::max<uint32_t>(1, std::min<uint32_t>((uint32_t)(sms * bps), (total_chunks + kScanWarps - 1) / kScanWarps));
+        const int use_sig = pat.typo_mode != FRZ_T_NONE && pat.sig_on;
+        k_sig_scan<<<grid, kScanThreads, 0, stream>>>(cv, use_sig, pat.sig_need1, pat.sig_need2, pat.sig_k, pat.min_hay_len, cand,
+                                                     ws.cand_cap, ws.counters);
+    }
+    const size_t smem = sizeof(WinSmem) * kWinWarps;
+#define FRZ_PF_LAUNCH(MODE)                                                                                              \
     do {                                                                                                                 \
         static int bps_dev[64] = {};                                                                                     \
         int& bps = bps_dev[frz_current_device() & 63];                                                                   \
         if (!bps) {                                                                                                      \
-            FRZ_CUDA_TRY(cudaFuncSetAttribute(k_prefilter<MODE, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMEM))); \
-            FRZ_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_prefilter<MODE, TMA>, kThreads, (SMEM)));  \
+            FRZ_CUDA_TRY(cudaFuncSetAttribute(k_window<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  \
+            FRZ_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_window<MODE>, kWinThreads, smem));        \
             static int knob = -1;   /* experiment knob: FRZ_PF_BLOCKS caps the resident blocks per SM */                 \
             if (knob < 0) { const char* e = getenv("FRZ_PF_BLOCKS"); knob = e ? atoi(e) : 0; }                           \
             if (knob > 0 && knob < bps) bps = knob;                                                                      \
             if (bps < 1) bps = 1;                                                                                        \
         }                                                                                                                \
-        const uint32_t grid = std::max<uint32_t>(1, std::min<uint32_t>((uint32_t)(sms * bps), (total_groups + kWarps - 1) / kWarps)); \
-        k_prefilter<MODE, TMA><<<grid, kThreads, (SMEM), stream>>>(cv, pat, ws.lists(), ws.survivor_cap, ws.surv_bitmap, ws.counters, \
-                                                                   pf_flags);                                            \
-    } while (0)
-#define FRZ_PF_LAUNCH(MODE)                                                       \
-    do {                                                                          \
-        if (tma_knob) FRZ_PF_LAUNCH_T(MODE, true, smem_tma);                      \
-        else FRZ_PF_LAUNCH_T(MODE, false, smem);                                  \
+        k_window<MODE><<<sms * bps, kWinThreads, smem, stream>>>(cv, pat, cand, ws.cand_cap, ws.lists(), ws.survivor_cap, \
+                                                                 ws.surv_bitmap, ws.counters, pf_flags);                 \
     } while (0)
     switch (pat.typo_mode) {
         case FRZ_T_0: FRZ_PF_LAUNCH(FRZ_T_0); break;
@@ -867,9 +881,8 @@ frz_status frz_launch_prefilter(const FrzCorpusView& cv, const FrzPatternDev& pa
         default: return frz_fail(FRZ_ERR_INVALID_ARG, "bad typo mode %d", pat.typo_mode);
     }
 #undef FRZ_PF_LAUNCH
-#undef FRZ_PF_LAUNCH_T
     FRZ_CUDA_TRY(cudaGetLastError());
-    if (st) st->launches++;
+    if (st) st->launches += 2;
     return FRZ_OK;
 }
 

@@ -58,15 +58,15 @@ FRZ_PF_FN uint32_t zero_flags(uint32_t x) {
 }
 
 // occ[d][lane] = occurrence mask of distinct class d over bytes [64*blk, 64*blk+64) of the lane's haystack.
-// `base` points at unit 0 of the lane's slot (unit k at base + 32*k); the units were streamed by this very
-// warp a few groups ago, so these loads hit L1/L2.  `units` = ceil(len / 16) bounds the reads.
+// `base` points at unit 0 of the lane's haystack, unit k at base + 32*k — in the packed corpus, or in the lane's column of
+// the shared-memory stage k_window fills with cp.async (same stride).  `units` = ceil(len / 16) bounds the reads.
 FRZ_PF_FN void build_block_masks(const uint4* base, int units, int blk, const FrzPatternDev& pat,
                                                   uint2 (*occ)[32], uint32_t lane) {
     uint32_t w[16];
 #pragma unroll
     for (int k = 0; k < 4; k++) {
         uint4 v = make_uint4(0u, 0u, 0u, 0u);
-        if (4 * blk + k < units) v = __ldg(base + (size_t)(4 * blk + k) * FRZ_GROUP);
+        if (4 * blk + k < units) v = base[(size_t)(4 * blk + k) * FRZ_GROUP];   // generic load: packed corpus or a shared-memory stage
         w[4 * k] = v.x; w[4 * k + 1] = v.y; w[4 * k + 2] = v.z; w[4 * k + 3] = v.w;
     }
     for (int d = 0; d < pat.n_distinct; d++) {
@@ -299,9 +299,9 @@ FRZ_PF_FN bool masks_k1_single(const uint4* base, const FrzPatternDev& pat, uint
     return state == 1;
 }
 
-// ---- groundwork for the tuned 2-typo / N-typo paths.  Both are checked against the oracle on
-// the CPU (tests/test_kernel_logic_cpu.py) but NOT yet called by the kernels (FRZ_T_2 / FRZ_T_MANY still use the
-// scanning forms window_k2 / window_many of prefilter.cu): wiring them in needs a GPU run for registers and timing.
+// ---- 2-typo / N-typo trackers on occurrence masks.  Checked against the oracle on the CPU
+// (tests/test_kernel_logic_cpu.py) and on the GPU (tests/test_gpu_parity.py, every typo budget); the kernels call them
+// whenever the needle has <= 16 distinct byte classes (13x / 5x faster than the scanning forms on B200, see prefilter.cu).
 
 // match_haystack_2_typos (src/prefilter/algo/ascii_typos.rs:113-251) on block masks: NP = 3 paths with their own
 // chunk masks; NP = 2 is match_haystack_1_typo again (== masks_k1, kept as a cross-check).

@@ -454,8 +454,7 @@ frz_status launch_sw_lanes(const FrzCorpusView& cv, const FrzPatternDev& pat, ui
             k_sw64<64, false, V><<<blocks64, kSwThreads, 0, stream>>>(cv, pat, ws.lists(), ws.survivor_cap, rank_view(ws),     \
                                                                       ws.counters, index_offset, rev, d_out);                 \
         } else
-        FRZ_SW_VAR_CASE(1) FRZ_SW_VAR_CASE(3) FRZ_SW_VAR_CASE(5) FRZ_SW_VAR_CASE(7) FRZ_SW_VAR_CASE(8) FRZ_SW_VAR_CASE(11)
-        FRZ_SW_VAR_CASE(16) FRZ_SW_VAR_CASE(17) FRZ_SW_VAR_CASE(18) FRZ_SW_VAR_CASE(19) FRZ_SW_VAR_CASE(26) FRZ_SW_VAR_CASE(27)
+        FRZ_SW_VAR_CASE(8) FRZ_SW_VAR_CASE(16) FRZ_SW_VAR_CASE(24)
 #undef FRZ_SW_VAR_CASE
             k_sw64<64, false, 0><<<blocks64, kSwThreads, 0, stream>>>(cv, pat, ws.lists(), ws.survivor_cap, rank_view(ws), ws.counters,
                                                                       index_offset, rev, d_out);

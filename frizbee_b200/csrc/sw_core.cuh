@@ -14,14 +14,12 @@
 // ---- host stand-ins of the device intrinsics (exact per-lane semantics) ----
 #define FRZ_SW_FN inline
 #define FRZ_SW_TID 0
-inline uint32_t __byte_perm(uint32_t x, uint32_t y, uint32_t s) {
+inline uint32_t __byte_perm(uint32_t x, uint32_t y, uint32_t s) {   // the CUDA intrinsic uses 3 bits per selector nibble
     const uint64_t v = ((uint64_t)y << 32) | x;
     uint32_t r = 0;
     for (int i = 0; i < 4; i++) {
-        const uint32_t sel = (s >> (4 * i)) & 0xf;
-        uint32_t b = (uint32_t)(v >> (8 * (sel & 7))) & 0xff;
-        if (sel & 8) b = (b & 0x80) ? 0xff : 0x00;   // sign-replicate mode
-        r |= b << (8 * i);
+        const uint32_t sel = (s >> (4 * i)) & 0x7;   // (nvcc masks bit 3: `__byte_perm(x, 0, 0xBB99)` is PRMT 0x3311)
+        r |= ((uint32_t)(v >> (8 * sel)) & 0xff) << (8 * i);
     }
     return r;
 }
@@ -60,9 +58,28 @@ constexpr bool kSw64RowsInSmem = FRZ_SW64_SMEM != 0;  // <= 64-byte windows: hay
 
 FRZ_SW_FN uint32_t splat16(int v) { return ((uint32_t)v & 0xffffu) * 0x00010001u; }
 
+// PRMT with the full selector: a nibble with bit 3 set replicates the SIGN bit of the selected byte (prmt.b32 default mode).
+// `__byte_perm` cannot express this (it masks the selector to 3 bits per nibble), hence the inline PTX.
+FRZ_SW_FN uint32_t prmt_sign(uint32_t x, uint32_t selector) {
+#if defined(__CUDA_ARCH__)
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(x), "r"(0u), "r"(selector));
+    return d;
+#else
+    uint32_t r = 0;
+    for (int i = 0; i < 4; i++) {
+        const uint32_t sel = (selector >> (4 * i)) & 0xf;
+        uint32_t b = (sel & 4) ? 0u : (x >> (8 * (sel & 3))) & 0xff;
+        if (sel & 8) b = (b & 0x80) ? 0xff : 0x00;
+        r |= b << (8 * i);
+    }
+    return r;
+#endif
+}
+
 // per-16-bit-lane: 0xFFFF where x == 0 else 0   (x lanes are in 0..255)
 FRZ_SW_FN uint32_t eqmask16(uint32_t x) {
-    return __byte_perm(__vadd2(x, 0xFFFFFFFFu), 0, 0xBB99);  // (x-1) sign → replicate
+    return __byte_perm(__vadd2(x, 0xFFFFFFFFu), 0, 0x3311);  // high byte of (x - 1): 0xFF only for x == 0 → both bytes
 }
 // bitwise select (mask ? a : b) as ONE LOP3 (nvcc otherwise emits and / and-not / or: three)
 FRZ_SW_FN uint32_t sel(uint32_t mask, uint32_t a, uint32_t b) {
@@ -97,10 +114,11 @@ struct RowStore<R, true> {
     FRZ_SW_FN void set(int r, uint32_t x) { base[r * kSwThreads] = x; }
 };
 
-// VAR selects which one-lane shifts use IMAD/IMAD.HI (fma pipe) instead of PRMT (alu pipe):
-//   bit 0: diagonal shift of the previous row; bit 1: score shift of gap step 1; bit 2: mask shift of gap step 1;
-//   bit 3: the per-column bonus is classified on the packed bytes (4 at a time) instead of per 16-bit lane
-//   bit 4: gap step 1 folds the shifted match mask into the penalty with IMAD.HI + IMAD (no mask shift at all)
+// VAR bits (A/B switches, each measured on B200 — profiles/r02_experiments.md):
+//   bit 3 (8):  the per-column bonus is classified on the packed bytes (4 at a time) instead of per 16-bit lane
+//   bit 4 (16): gap step 1 folds the shifted match mask into the penalty with IMAD.HI + IMAD (no mask shift at all)
+// (bits 0-2 moved the one-lane shifts of the row loop from PRMT to IMAD.HI + IMAD pairs; static pipe counts predicted
+//  -14%, the B200 measured +2% .. +16% — the pairs cost more issue slots than the ALU pipe saves — and they were removed.)
 //
 // CC (<= COLS, multiple of 8) is the number of columns actually evaluated.  Cells never depend on cells to
 // their right, and a cell in column >= W + needle_len can only hold a value that decayed from a cell to its
@@ -151,8 +169,8 @@ struct SwCore {
                 prev_dl = dl_f;
 #pragma unroll
                 for (int h = 0; h < 2; h++) {   // expand bit 7 of bytes (2h, 2h+1) to 16-bit lane masks
-                    const uint32_t sel = h ? 0xBBAAu : 0x9988u;
-                    const uint32_t cap_m = __byte_perm(cap_f, 0, sel), del_m = __byte_perm(del_f, 0, sel), up_m = __byte_perm(up_f, 0, sel);
+                    const uint32_t sgn = h ? 0xBBAAu : 0x9988u;   // sign bit of byte 2h → low lane, of byte 2h+1 → high lane
+                    const uint32_t cap_m = prmt_sign(cap_f, sgn), del_m = prmt_sign(del_f, sgn), up_m = prmt_sign(up_f, sgn);
                     uint32_t bonus = __vadd2(__vadd2(del_m & delb, cap_m & capb), base2);
                     if (k == 0 && h == 0 && include_prefix) bonus = __vadd2(bonus, (uint32_t)p.prefix_bonus & 0xffffu);
                     bonus = __vadd2(bonus, ~up_m & p.k_case);
@@ -169,12 +187,12 @@ struct SwCore {
                 auto in_range = [&](int lo, int hi) {
                     uint32_t t = __vadd2(b, splat16(-lo));
                     uint32_t d = __vadd2(b, splat16(-(hi + 1)));
-                    return __byte_perm(d & ~t, 0, 0xBB99);
+                    return __byte_perm(d & ~t, 0, 0x3311);   // high byte of each lane (0xFF or 0x00 here) → both bytes
                 };
                 const uint32_t upper = in_range('A', 'Z');
                 const uint32_t lower = in_range('a', 'z');
                 const uint32_t digit = in_range('0', '9');
-                const uint32_t high = __byte_perm(__vadd2(b, splat16(-128)), 0, 0xBB99) ^ 0xFFFFFFFFu;  // b >= 128
+                const uint32_t high = __byte_perm(__vadd2(b, splat16(-128)), 0, 0x3311) ^ 0xFFFFFFFFu;  // b >= 128
                 const uint32_t delim = ~(upper | lower | digit | high);
                 const uint32_t lower_sh = __byte_perm(prev_lower, lower, 0x5432);
                 const uint32_t delim_sh = __byte_perm(prev_delim, delim, 0x5432);
@@ -207,10 +225,6 @@ struct SwCore {
         // pipe idle (profiles/r01c).  Match masks are therefore kept as 0/1 per lane so that every
         // "penalty = base - mask * gap_open" is one IMAD, and lane shifts use IMAD / IMAD.HI too.
         const uint32_t gopx = (uint32_t)p.gap_open_x;
-        auto shl16 = [](uint32_t lo_src, uint32_t hi_src) {
-            // lanes: result.lo = lo_src.hi, result.hi = hi_src.lo   ( == __byte_perm(lo_src, hi_src, 0x5432) )
-            return hi_src * 0x10000u + __umulhi(lo_src, 0x10000u);
-        };
         for (int i = 0; i < p.n; i++) {
             const uint32_t om16 = p.om16[i], tg16 = p.tg16[i], c16 = p.c16[i];
             const bool folded = p.om[i] != 0;  // case-insensitive letter: exact-case mask differs from match mask
@@ -223,12 +237,11 @@ struct SwCore {
                     // nm: 0 where the haystack byte matches needle[i] (either case), else 1
                     const uint32_t nm = __vminu2((hv | om16) ^ tg16, 0x00010001u);
                     const uint32_t nmfull = nm * 0xFFFFu;
-                    const uint32_t prevs = (VAR & 1) ? (r > 0 ? shl16(H[r - 1], H[r]) : H[0] * 0x10000u)
-                                                    : (r > 0 ? __byte_perm(H[r - 1], H[r], 0x5432) : __byte_perm(0u, H[0], 0x5432));
+                    const uint32_t prevs = r > 0 ? __byte_perm(H[r - 1], H[r], 0x5432) : __byte_perm(0u, H[0], 0x5432);
                     uint32_t Dv = Bv;
                     if (upper_row) {  // rare: move the exact-case bonus from the non-upper to the upper haystack bytes
                         const uint32_t t = __vadd2(hv, splat16(-'A')), d = __vadd2(hv, splat16(-('Z' + 1)));
-                        const uint32_t up = __byte_perm(d & ~t, 0, 0xBB99);
+                        const uint32_t up = __byte_perm(d & ~t, 0, 0x3311);
                         Dv = __vadd2(Dv, sel(up, p.k_case, splat16(-p.case_bonus)));
                     }
                     const uint32_t diag = addmax_relu(prevs, sel(nmfull, neg_mis, Dv), 0u);
@@ -259,10 +272,8 @@ struct SwCore {
                     for (int r = hi - 1; r >= lo; r--) {
                         uint32_t sh, smm;
                         if (s == 1 && !WRAP8) {
-                            if (VAR & 2) sh = r == 0 ? H[0] * 0x10000u : shl16(H[r - 1], H[r]);
-                            else sh = r == 0 ? __byte_perm(0u, H[0], 0x5432) : __byte_perm(H[r - 1], H[r], 0x5432);
+                            sh = r == 0 ? __byte_perm(0u, H[0], 0x5432) : __byte_perm(H[r - 1], H[r], 0x5432);
                             if (VAR & 16) smm = 0;   // folded into the penalty below
-                            else if (VAR & 4) smm = r == 0 ? M[0] * 0x10000u : shl16(M[r - 1], M[r]);
                             else smm = r == 0 ? __byte_perm(0u, M[0], 0x5432) : __byte_perm(M[r - 1], M[r], 0x5432);
                         } else if (s == 1) {
                             if (r == 0) { sh = __byte_perm(0u, H[0], 0x5432); smm = __byte_perm(0u, M[0], 0x5432); }

@@ -53,18 +53,9 @@ int dispatch(const FrzPatternDev& pat, const uint8_t* w, int W, int startlo, boo
     if (wrap8) return dispatch_cc<LANES, true, 0>(pat, w, W, startlo, pre, cols, cc, eq);
     if (LANES == 64) {
         switch (var) {
-            case 1: return dispatch_cc<LANES, false, 1>(pat, w, W, startlo, pre, cols, cc, eq);
-            case 3: return dispatch_cc<LANES, false, 3>(pat, w, W, startlo, pre, cols, cc, eq);
-            case 5: return dispatch_cc<LANES, false, 5>(pat, w, W, startlo, pre, cols, cc, eq);
-            case 7: return dispatch_cc<LANES, false, 7>(pat, w, W, startlo, pre, cols, cc, eq);
             case 8: return dispatch_cc<LANES, false, 8>(pat, w, W, startlo, pre, cols, cc, eq);
-            case 11: return dispatch_cc<LANES, false, 11>(pat, w, W, startlo, pre, cols, cc, eq);
             case 16: return dispatch_cc<LANES, false, 16>(pat, w, W, startlo, pre, cols, cc, eq);
-            case 17: return dispatch_cc<LANES, false, 17>(pat, w, W, startlo, pre, cols, cc, eq);
-            case 18: return dispatch_cc<LANES, false, 18>(pat, w, W, startlo, pre, cols, cc, eq);
-            case 19: return dispatch_cc<LANES, false, 19>(pat, w, W, startlo, pre, cols, cc, eq);
-            case 26: return dispatch_cc<LANES, false, 26>(pat, w, W, startlo, pre, cols, cc, eq);
-            case 27: return dispatch_cc<LANES, false, 27>(pat, w, W, startlo, pre, cols, cc, eq);
+            case 24: return dispatch_cc<LANES, false, 24>(pat, w, W, startlo, pre, cols, cc, eq);
         }
     }
     return dispatch_cc<LANES, false, 0>(pat, w, W, startlo, pre, cols, cc, eq);
