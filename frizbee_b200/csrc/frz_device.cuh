@@ -168,7 +168,7 @@ struct FrzCounters {
     unsigned int sw_next;                           // next 32-survivor work item of the SW kernel
     unsigned int pad_;
     unsigned long long cand_count;                  // candidate records written by k_sig_scan
-    unsigned int pf_next;                           // next 32-candidate work item of k_window
+    unsigned int pf_next;                           // (spare)
     unsigned int pad2_;
 };
 

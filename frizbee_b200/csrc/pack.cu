@@ -72,12 +72,13 @@ __global__ void __launch_bounds__(256) k_pack_plan(const OffT* __restrict__ offs
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        uint32_t off = 0;
-        atomicMax(err + 1, gun[FRZ_GROUPS_PER_TILE - 1]);   // longest group of the corpus, in units (groups ascend)
+        uint32_t off = 0, longest = 0;
         for (int g = 0; g < FRZ_GROUPS_PER_TILE; g++) {
             groups[tile * FRZ_GROUPS_PER_TILE + g] = FrzGroupDesc{0ull, off, gun[g]};  // abs_off filled by k_pack_copy
             off += gun[g] * FRZ_GROUP;
+            longest = max(longest, gun[g]);   // (the groups ascend, but the trailing groups of a partial last tile are empty)
         }
+        atomicMax(err + 1, longest);   // longest haystack of the corpus, in units: kernels stage / specialise on it
         tile_units[tile] = off;
     }
 }

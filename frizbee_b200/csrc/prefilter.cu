@@ -375,12 +375,19 @@ __device__ __forceinline__ Cand resolve_cand(const FrzCorpusView& cv, uint32_t t
     return c;
 }
 
+// what process_candidate found for one lane's candidate, on its way to the per-class survivor lists
+struct Emit {
+    FrzSurvivor rec;
+    unsigned long long base_raw;   // leader lanes: the reserved list position (result of the atomic, may still be in flight)
+    uint32_t peers;                // lanes of the warp with the same SW class
+    int cls;
+    bool ok;
+};
+
 template <int MODE>
 __device__ __forceinline__ void process_candidate(const FrzCorpusView& cv, const FrzPatternDev& pat, const uint8_t* __restrict__ cid_s,
-                                                  uint2 (*occ)[32], const Cand& cd, bool active, const FrzSurvLists& lists,
-                                                  unsigned long long surv_cap, uint32_t* __restrict__ surv_bitmap,
-                                                  FrzCounters* __restrict__ ctr, bool single_chunk = false) {
-    const uint32_t lane = frz_lane();
+                                                  uint2 (*occ)[32], const Cand& cd, bool active,
+                                                  uint32_t* __restrict__ surv_bitmap, Emit* out, bool single_chunk = false) {
     bool ok = false;
     int cls = 0;
     FrzSurvivor rec;
@@ -450,18 +457,31 @@ __device__ __forceinline__ void process_candidate(const FrzCorpusView& cv, const
             atomicOr(&surv_bitmap[(uint64_t)tile * 32 + (li >> 5)], 1u << (li & 31));
         }
     }
-    // warp-aggregated append: the lowest lane of every class present reserves the slots for its peers
-    const uint32_t peers = __match_any_sync(0xffffffffu, ok ? cls : -1);
-    if (__any_sync(0xffffffffu, ok)) {
-        const int leader = __ffs(peers) - 1;
-        unsigned long long base = 0;
-        if (ok && (int)lane == leader) base = atomicAdd(&ctr->class_count[cls], (unsigned long long)__popc(peers));
-        base = __shfl_sync(0xffffffffu, base, leader);
-        if (ok) {
-            const unsigned long long pos = base + __popc(peers & ((1u << lane) - 1));
-            if (pos < surv_cap) lists.p[cls][pos] = rec;
-            else atomicOr(&ctr->error, FRZ_DEVERR_SURVIVOR_OVERFLOW);
-        }
+    out->rec = rec;
+    out->ok = ok;
+    out->cls = cls;
+}
+
+// Survivor emission, split in two so that the round trip of the list-space atomic overlaps the NEXT item's work:
+//   emit_request  the lowest lane of every SW class present reserves list slots for its peers (one atomic per class);
+//                 the result stays in flight
+//   emit_commit   (one item later) broadcast of the reserved base, then the 16-byte record stores
+__device__ __forceinline__ void emit_request(Emit& e, FrzCounters* __restrict__ ctr) {
+    const uint32_t lane = frz_lane();
+    e.peers = __match_any_sync(0xffffffffu, e.ok ? e.cls : -1);
+    e.base_raw = 0;
+    if (e.ok && (int)lane == __ffs(e.peers) - 1)
+        e.base_raw = atomicAdd(&ctr->class_count[e.cls], (unsigned long long)__popc(e.peers));
+}
+__device__ __forceinline__ void emit_commit(const Emit& e, const FrzSurvLists& lists, unsigned long long surv_cap,
+                                            FrzCounters* __restrict__ ctr) {
+    if (!__any_sync(0xffffffffu, e.ok)) return;
+    const uint32_t lane = frz_lane();
+    const unsigned long long base = __shfl_sync(0xffffffffu, e.base_raw, __ffs(e.peers) - 1);
+    if (e.ok) {
+        const unsigned long long pos = base + __popc(e.peers & ((1u << lane) - 1));
+        if (pos < surv_cap) lists.p[e.cls][pos] = e.rec;
+        else atomicOr(&ctr->error, FRZ_DEVERR_SURVIVOR_OVERFLOW);
     }
 }
 
@@ -486,7 +506,7 @@ struct __align__(16) CandRec {
     uint64_t unit0;       // unit index (16-byte units from the start of the packed data) of the slot's unit 0
 };
 
-__global__ void __launch_bounds__(kScanThreads, 12) k_sig_scan(const FrzCorpusView cv, int use_sig, uint32_t need1, uint32_t need2,
+__global__ void __launch_bounds__(kScanThreads, 10) k_sig_scan(const FrzCorpusView cv, int use_sig, uint32_t need1, uint32_t need2,
                                                                int sig_k, int min_len, CandRec* __restrict__ cand,
                                                                unsigned long long cand_cap, FrzCounters* __restrict__ ctr) {
     __shared__ CandRec ring_s[kScanWarps][kScanRing];
@@ -495,16 +515,19 @@ __global__ void __launch_bounds__(kScanThreads, 12) k_sig_scan(const FrzCorpusVi
     const uint32_t n_warps = gridDim.x * kScanWarps;
     const uint32_t total_chunks = cv.n_tiles * (FRZ_TILE / 128);   // 128 slots (4 groups) per chunk
     uint32_t head = 0, count = 0;
+    // one chunk = 128 consecutive slots (4 groups): lane L owns slots 4L .. 4L+3, all in group L / 8 of the chunk
     struct Chunk {
         uint4 meta;
         uint4 sig0, sig1;
+        unsigned long long abs_off;   // lanes 0-3: first unit of the chunk's group `lane`
         uint32_t idx;
     };
     uint32_t next = blockIdx.x * kScanWarps + warp;
     auto load_chunk = [&](Chunk& c) {
-        c.idx = next;
+        c.idx = next < total_chunks ? next : 0xFFFFFFFFu;
         c.meta = make_uint4(FRZ_INVALID_SLOT, FRZ_INVALID_SLOT, FRZ_INVALID_SLOT, FRZ_INVALID_SLOT);
         c.sig0 = c.sig1 = make_uint4(0u, 0u, 0u, 0u);
+        c.abs_off = 0;
         if (next < total_chunks) {
             const uint64_t slot0 = (uint64_t)next * 128 + lane * 4;
             c.meta = __ldg(reinterpret_cast<const uint4*>(cv.slot_meta + slot0));
@@ -513,8 +536,7 @@ __global__ void __launch_bounds__(kScanThreads, 12) k_sig_scan(const FrzCorpusVi
                 c.sig0 = __ldg(sp);
                 c.sig1 = __ldg(sp + 1);
             }
-        } else {
-            c.idx = 0xFFFFFFFFu;
+            if (lane < 4) c.abs_off = cv.groups[next * 4 + lane].abs_off;   // four contiguous 16-byte descriptors, L2-resident
         }
         next += n_warps;
     };
@@ -524,46 +546,45 @@ __global__ void __launch_bounds__(kScanThreads, 12) k_sig_scan(const FrzCorpusVi
         base = __shfl_sync(0xffffffffu, base, 0);
         if (lane < n_out) {
             const unsigned long long pos = base + lane;
-            if (pos < cand_cap) cand[pos] = ring[(head + lane) & (kScanRing - 1)];
+            if (pos < cand_cap) reinterpret_cast<uint4*>(cand)[pos] = reinterpret_cast<const uint4*>(ring)[(head + lane) & (kScanRing - 1)];
             else atomicOr(&ctr->error, FRZ_DEVERR_SURVIVOR_OVERFLOW);
         }
         head = (head + n_out) & (kScanRing - 1);
         count -= n_out;
     };
-    Chunk c0, c1;
-    load_chunk(c0);
-    load_chunk(c1);
-    while (c0.idx != 0xFFFFFFFFu) {
-        // group descriptors of this chunk's four groups: lanes 0-3 load one each (contiguous 64 bytes)
-        unsigned long long abs_off = 0;
-        if (lane < 4) abs_off = cv.groups[c0.idx * 4 + lane].abs_off;
-        const uint32_t m[4] = {c0.meta.x, c0.meta.y, c0.meta.z, c0.meta.w};
-        const uint32_t s1[4] = {c0.sig0.x, c0.sig0.z, c0.sig1.x, c0.sig1.z};
-        const uint32_t s2[4] = {c0.sig0.y, c0.sig0.w, c0.sig1.y, c0.sig1.w};
-        const unsigned long long my_off = __shfl_sync(0xffffffffu, abs_off, lane >> 3);   // slots 4*lane..4*lane+3 sit in group lane / 8
-        const uint32_t chunk_idx = c0.idx;
-        c0 = c1;
-        load_chunk(c1);
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const bool valid = m[j] != FRZ_INVALID_SLOT;
-            const int len = valid ? (int)(m[j] >> FRZ_TILE_SHIFT) : 0;
-            bool pass = valid && len >= min_len;
-            if (use_sig) pass = pass && frz_sig_pass(need1, need2, sig_k, s1[j], s2[j]);
-            const uint32_t ballot = __ballot_sync(0xffffffffu, pass);
-            if (pass) {
-                const uint32_t slot_in_chunk = lane * 4 + j;                       // 0..127
-                CandRec r;
-                r.tile_slot = chunk_idx * 128 + slot_in_chunk;                     // == tile << 10 | slot
-                r.meta = m[j];
-                r.unit0 = my_off + (slot_in_chunk & 31);
-                ring[(head + count + __popc(ballot & ((1u << lane) - 1))) & (kScanRing - 1)] = r;
-            }
-            count += __popc(ballot);
-        }
+    // length gate + signature test of one slot; passing lanes append their record to the ring
+    auto test_slot = [&](uint32_t m, uint32_t p1, uint32_t p2, uint32_t slot_global, unsigned long long unit0) {
+        bool pass = m != FRZ_INVALID_SLOT && (int)(m >> FRZ_TILE_SHIFT) >= min_len;
+        if (use_sig) pass = pass && frz_sig_pass(need1, need2, sig_k, p1, p2);
+        const uint32_t ballot = __ballot_sync(0xffffffffu, pass);
+        if (pass)   // one 16-byte shared-memory store (a CandRec, field by field)
+            reinterpret_cast<uint4*>(ring)[(head + count + __popc(ballot & ((1u << lane) - 1))) & (kScanRing - 1)] =
+                make_uint4(slot_global, m, (uint32_t)unit0, (uint32_t)(unit0 >> 32));
+        count += __popc(ballot);
+    };
+    auto process = [&](const Chunk& c) {
+        const unsigned long long grp_off = __shfl_sync(0xffffffffu, c.abs_off, lane >> 3);
+        const uint32_t slot_g = c.idx * 128 + lane * 4;                 // == tile << 10 | slot of this lane's first slot
+        const unsigned long long unit0 = grp_off + ((lane * 4) & 31);   // unit 0 of that slot (units of a group interleave by lane)
+        test_slot(c.meta.x, c.sig0.x, c.sig0.y, slot_g, unit0);
+        test_slot(c.meta.y, c.sig0.z, c.sig0.w, slot_g + 1, unit0 + 1);
+        test_slot(c.meta.z, c.sig1.x, c.sig1.y, slot_g + 2, unit0 + 2);
+        test_slot(c.meta.w, c.sig1.z, c.sig1.w, slot_g + 3, unit0 + 3);
         __syncwarp();
         while (count >= 32) flush(32);
         __syncwarp();
+    };
+    // two chunk buffers ping-pong (no struct copies): the other buffer's loads are in flight while one is tested
+    Chunk ca, cb;
+    load_chunk(ca);
+    load_chunk(cb);
+    for (;;) {
+        if (ca.idx == 0xFFFFFFFFu) break;
+        process(ca);
+        load_chunk(ca);
+        if (cb.idx == 0xFFFFFFFFu) break;
+        process(cb);
+        load_chunk(cb);
     }
     if (count) flush(count);
 }
@@ -601,53 +622,59 @@ __global__ void __launch_bounds__(kWinThreads, 6) k_window(const FrzCorpusView c
     const bool staged = cv.max_gunits <= 4;   // every haystack fits the four staged units
     const bool single = (MODE == FRZ_T_0 || MODE == FRZ_T_1) && (flags & 1u) && single_chunk_ok(pat, cv.max_gunits);
 
-    auto claim = [&]() {
-        uint32_t t = 0;
-        if (lane == 0) t = atomicAdd(&ctr->pf_next, 1u);
-        return __shfl_sync(0xffffffffu, t, 0);
-    };
+    // work items are strided statically over the warps of the grid (their cost is uniform): item indices are known ahead,
+    // so the records of item i+2 are requested while item i is processed — no ticket round trip in the loop
+    const uint32_t n_warps = gridDim.x * kWinWarps;
     auto load_rec = [&](uint32_t item) {
-        CandRec r;
-        r.tile_slot = 0xFFFFFFFFu; r.meta = 0; r.unit0 = 0;
+        uint4 r = make_uint4(0xFFFFFFFFu, 0u, 0u, 0u);
         const unsigned long long j = (unsigned long long)item * 32 + lane;
-        if (item < n_items && j < n_cand) r = cand[j];
-        return r;
+        if (item < n_items && j < n_cand) r = __ldg(reinterpret_cast<const uint4*>(cand) + j);
+        return r;   // {tile_slot, meta, unit0 lo, unit0 hi}
     };
-    auto stage_units = [&](const CandRec& r, int st) {
-        if (staged && r.tile_slot != 0xFFFFFFFFu) {
-            const int units = ((int)(r.meta >> FRZ_TILE_SHIFT) + 15) >> 4;
-            const uint4* base = cv.data + r.unit0;
+    auto unit0_of = [](const uint4& r) { return ((unsigned long long)r.w << 32) | r.z; };
+    auto stage_units = [&](const uint4& r, int st) {
+        if (staged && r.x != 0xFFFFFFFFu) {
+            const int units = ((int)(r.y >> FRZ_TILE_SHIFT) + 15) >> 4;
+            const uint4* base = cv.data + unit0_of(r);
 #pragma unroll
             for (int k = 0; k < 4; k++)
                 if (k < units) __pipeline_memcpy_async(&sm.stage[st].units[k][lane], base + (size_t)k * FRZ_GROUP, 16);
         }
         __pipeline_commit();
     };
-    uint32_t item0 = claim(), item1 = claim();
-    CandRec rec0 = load_rec(item0);
+    uint32_t item = blockIdx.x * kWinWarps + warp;
+    uint4 rec0 = load_rec(item);
     stage_units(rec0, 0);
-    CandRec rec1 = load_rec(item1);
+    uint4 rec1 = load_rec(item + n_warps);
+    Emit pending;
+    pending.ok = false; pending.cls = 0; pending.peers = 0; pending.base_raw = 0;
+    pending.rec.tile = 0; pending.rec.slot_rank = 0; pending.rec.start = 0; pending.rec.end = 0;
     int st = 0;
-    while (item0 < n_items) {
-        const uint32_t item2 = claim();
-        stage_units(rec1, st ^ 1);              // next item's units start moving ...
-        const CandRec rec2 = load_rec(item2);   // ... and the one after that requests its records
-        __pipeline_wait_prior(1);               // this item's units have landed
+    while (item < n_items) {
+        stage_units(rec1, st ^ 1);                            // next item's units start moving ...
+        const uint4 rec2 = load_rec(item + 2 * n_warps);      // ... and the one after that requests its records
+        __pipeline_wait_prior(1);                             // this item's units have landed
         __syncwarp();
-        const bool active = rec0.tile_slot != 0xFFFFFFFFu;
+        const bool active = rec0.x != 0xFFFFFFFFu;
         Cand cd;
-        cd.tile = rec0.tile_slot >> FRZ_TILE_SHIFT;
-        cd.slot = rec0.tile_slot & (FRZ_TILE - 1);
-        cd.li = rec0.meta & (FRZ_TILE - 1);
-        cd.len = (int)(rec0.meta >> FRZ_TILE_SHIFT);
-        cd.base = cv.data + rec0.unit0;
+        cd.tile = rec0.x >> FRZ_TILE_SHIFT;
+        cd.slot = rec0.x & (FRZ_TILE - 1);
+        cd.li = rec0.y & (FRZ_TILE - 1);
+        cd.len = (int)(rec0.y >> FRZ_TILE_SHIFT);
+        cd.base = cv.data + unit0_of(rec0);
         cd.units = staged ? &sm.stage[st].units[0][lane] : cd.base;
-        process_candidate<MODE>(cv, pat, cid_s, sm.occ, cd, active, lists, surv_cap, surv_bitmap, ctr, single);
+        Emit cur;
+        process_candidate<MODE>(cv, pat, cid_s, sm.occ, cd, active, surv_bitmap, &cur, single);
+        emit_commit(pending, lists, surv_cap, ctr);           // the previous item's list space has arrived by now
+        emit_request(cur, ctr);
+        pending = cur;
         __syncwarp();
-        item0 = item1; rec0 = rec1;
-        item1 = item2; rec1 = rec2;
+        item += n_warps;
+        rec0 = rec1;
+        rec1 = rec2;
         st ^= 1;
     }
+    emit_commit(pending, lists, surv_cap, ctr);
     __pipeline_wait_prior(0);
 }
 
@@ -681,7 +708,10 @@ __global__ void __launch_bounds__(kThreads) k_prefilter_list(const FrzCorpusView
             cd = resolve_cand(cv, tile, slot, (int)len);
         }
         __syncwarp();
-        process_candidate<MODE>(cv, pat, cid_s, occ, cd, active, lists, surv_cap, surv_bitmap, ctr);
+        Emit e;
+        process_candidate<MODE>(cv, pat, cid_s, occ, cd, active, surv_bitmap, &e);
+        emit_request(e, ctr);
+        emit_commit(e, lists, surv_cap, ctr);
         __syncwarp();
     }
 }
@@ -702,39 +732,38 @@ __global__ void __launch_bounds__(256) k_tile_rank(const uint32_t* __restrict__ 
     if (lane == 31) tile_count[tile] = x;
 }
 
-// exclusive scan of tile_count → tile_out_base; total → counters.total
+// exclusive scan of tile_count → tile_out_base; total → counters.total.  One block; every thread owns a CONTIGUOUS run
+// of ceil(n / 1024) tiles, so the block makes one pass (two for > 1 M tiles) instead of n / 1024 barrier rounds
+// (12 us → 3 us at 9766 tiles, profiles/r02b_launches.csv vs r02d).
 __global__ void __launch_bounds__(1024) k_tile_scan(const uint32_t* __restrict__ tile_count, uint64_t* __restrict__ out,
                                                     uint32_t n, FrzCounters* __restrict__ ctr) {
     __shared__ uint64_t warp_sum[32];
-    __shared__ uint64_t carry_s;
-    if (threadIdx.x == 0) carry_s = 0;
-    __syncthreads();
-    for (uint32_t base = 0; base < n; base += blockDim.x) {
-        uint32_t i = base + threadIdx.x;
-        uint64_t v = i < n ? tile_count[i] : 0;
-        uint64_t x = v;
-        for (int d = 1; d < 32; d <<= 1) {
-            uint64_t y = __shfl_up_sync(0xffffffffu, x, d);
-            if (frz_lane() >= (uint32_t)d) x += y;
-        }
-        if (frz_lane() == 31) warp_sum[threadIdx.x >> 5] = x;
-        __syncthreads();
-        if (threadIdx.x < 32) {
-            uint64_t w = warp_sum[threadIdx.x], xs = w;
-            for (int d = 1; d < 32; d <<= 1) {
-                uint64_t y = __shfl_up_sync(0xffffffffu, xs, d);
-                if (frz_lane() >= (uint32_t)d) xs += y;
-            }
-            warp_sum[threadIdx.x] = xs - w;
-        }
-        __syncthreads();
-        uint64_t incl = carry_s + warp_sum[threadIdx.x >> 5] + x;
-        if (i < n) out[i] = incl - v;
-        __syncthreads();
-        if (threadIdx.x == blockDim.x - 1) carry_s = incl;
-        __syncthreads();
+    const uint32_t per = (n + blockDim.x - 1) / blockDim.x;
+    const uint32_t lo = min(threadIdx.x * per, n), hi = min(lo + per, n);
+    uint64_t sum = 0;
+    for (uint32_t i = lo; i < hi; i++) sum += tile_count[i];
+    uint64_t x = sum;
+    for (int d = 1; d < 32; d <<= 1) {
+        uint64_t y = __shfl_up_sync(0xffffffffu, x, d);
+        if (frz_lane() >= (uint32_t)d) x += y;
     }
-    if (threadIdx.x == 0) ctr->total = carry_s;
+    if (frz_lane() == 31) warp_sum[threadIdx.x >> 5] = x;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        uint64_t w = warp_sum[threadIdx.x], xs = w;
+        for (int d = 1; d < 32; d <<= 1) {
+            uint64_t y = __shfl_up_sync(0xffffffffu, xs, d);
+            if (frz_lane() >= (uint32_t)d) xs += y;
+        }
+        warp_sum[threadIdx.x] = xs - w;
+    }
+    __syncthreads();
+    uint64_t run = warp_sum[threadIdx.x >> 5] + x - sum;   // exclusive prefix of this thread's run
+    for (uint32_t i = lo; i < hi; i++) {
+        out[i] = run;
+        run += tile_count[i];
+    }
+    if (threadIdx.x == blockDim.x - 1) ctr->total = run;   // the last thread's run ends at n (empty runs carry the total)
 }
 
 // Matcher::match_list_indices for chosen haystacks (src/matcher/mod.rs:234-262 → match_one_indices_impl,

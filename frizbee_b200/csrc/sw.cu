@@ -462,6 +462,8 @@ frz_status launch_sw_lanes(const FrzCorpusView& cv, const FrzPatternDev& pat, ui
         k_sw64<LANES, true><<<blocks64, kSwThreads, 0, stream>>>(cv, pat, ws.lists(), ws.survivor_cap, rank_view(ws), ws.counters, index_offset, rev, d_out);
     else
         k_sw64<LANES, false><<<blocks64, kSwThreads, 0, stream>>>(cv, pat, ws.lists(), ws.survivor_cap, rank_view(ws), ws.counters, index_offset, rev, d_out);
+    // windows of 65..128 bytes only exist when some haystack of the corpus is longer than 64 bytes (recorded at pack time)
+    if (cv.max_gunits <= 4) { FRZ_CUDA_TRY(cudaGetLastError()); return FRZ_OK; }
     const size_t smem = SwCore<LANES, 128, false>::smem_bytes;
     static bool attr_set_dev[64] = {};   // function attributes are per device
     bool& attr_set = attr_set_dev[frz_current_device() & 63];
@@ -499,9 +501,11 @@ frz_status frz_launch_sw(const FrzCorpusView& cv, const FrzPatternDev& pat, uint
         case 8: FRZ_TRY(launch_sw_lanes<8>(cv, pat, index_offset, reversed, ws, d_out, stream)); break;
         default: return frz_fail(FRZ_ERR_INVALID_ARG, "unsupported lane count %d", pat.sw_lanes);
     }
-    k_sw_generic<<<sm_count() * 2, 64, 0, stream>>>(cv, pat, ws.survivors[FRZ_C_GENERIC], ws.survivor_cap, FRZ_C_GENERIC, rank_view(ws),
-                                                    ws.counters, index_offset, reversed ? 1 : 0, d_out);
+    if (cv.max_gunits > 8) {   // windows > 128 bytes need a haystack > 128 bytes
+        k_sw_generic<<<sm_count() * 2, 64, 0, stream>>>(cv, pat, ws.survivors[FRZ_C_GENERIC], ws.survivor_cap, FRZ_C_GENERIC, rank_view(ws),
+                                                        ws.counters, index_offset, reversed ? 1 : 0, d_out);
+    }
     FRZ_CUDA_TRY(cudaGetLastError());
-    if (st) st->launches += 3;
+    if (st) st->launches += 1 + (cv.max_gunits > 4 ? 1 : 0) + (cv.max_gunits > 8 ? 1 : 0);
     return FRZ_OK;
 }

@@ -156,3 +156,35 @@ def test_host_entry_points_survive_random_input():
                 assert L.frz_matcher_backend_info(m, i, ctypes.byref(lanes), ctypes.byref(bits), ctypes.byref(pf), ctypes.byref(lit)) == 0
                 assert lanes.value in (8, 16, 32, 64) and bits.value in (8, 16) and pf.value in (16, 32, 64)
             L.frz_matcher_destroy(m)
+
+
+def test_parallel_entry_points_argument_errors_without_a_device():
+    """frz_comm_* / frz_match_list_parallel* (src/matcher/parallel.rs:18-89 behind the C ABI): argument errors mirror the
+    reference's panics (threads == 0 → "threads must be positive", parallel.rs:24), and without a device the
+    communicator constructors fail with FRZ_ERR_NO_DEVICE — never a CPU fallback."""
+    import torch
+    from frizbee_b200 import parallel
+    with pytest.raises(F.FrizbeeError) as e:
+        parallel.Comm.local(0)
+    assert e.value.status_name == "FRZ_ERR_THREADS_ZERO" and "threads must be positive" in str(e.value)
+    with pytest.raises(F.FrizbeeError) as e:
+        parallel.Comm.local(65)
+    assert e.value.status_name == "FRZ_ERR_INVALID_ARG"
+    with pytest.raises(F.FrizbeeError) as e:
+        parallel.Comm.from_rank(b"\0" * 128, 2, 5, 0)
+    assert e.value.status_name == "FRZ_ERR_INVALID_ARG"
+    L = parallel.plib()
+    n = ctypes.c_uint64()
+    assert L.frz_match_list_parallel(None, None, 0, None, None, 0, ctypes.byref(n)) == 1          # FRZ_ERR_INVALID_ARG
+    assert L.frz_match_list_parallel_rank(None, None, 0, None, None, 0, ctypes.byref(n), None) == 1
+    assert L.frz_comm_world(None) == 0 and L.frz_comm_rank(None) == -1
+    if not torch.cuda.is_available():
+        with pytest.raises(F.FrizbeeError) as e:
+            parallel.Comm.local(1)
+        assert e.value.status_name == "FRZ_ERR_NO_DEVICE" and "no CPU fallback" in str(e.value)
+    m = F.Matcher("foo", Config())
+    clone = ctypes.c_void_p()
+    assert L.frz_matcher_clone(m._h, ctypes.byref(clone)) == 0 and clone.value
+    assert F.lib().frz_matcher_score_bound(clone) == m.score_bound()
+    F.lib().frz_matcher_destroy(clone)
+    m.close()
