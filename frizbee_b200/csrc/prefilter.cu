@@ -506,49 +506,72 @@ struct __align__(16) CandRec {
     uint64_t unit0;       // unit index (16-byte units from the start of the packed data) of the slot's unit 0
 };
 
-__global__ void __launch_bounds__(kScanThreads, 10) k_sig_scan(const FrzCorpusView cv, int use_sig, uint32_t need1, uint32_t need2,
-                                                               int sig_k, int min_len, CandRec* __restrict__ cand,
-                                                               unsigned long long cand_cap, FrzCounters* __restrict__ ctr) {
-    __shared__ CandRec ring_s[kScanWarps][kScanRing];
+// ---- TMA staging (cp.async.bulk, 1-D) of the phase-A arrays ---------------------------------------------------------
+// The metadata, signature and group-descriptor arrays are contiguous, so a warp's next 128-slot chunk is three bulk
+// copies (512 + 1024 + 64 bytes) that complete on the warp's OWN mbarrier: warp-autonomous, no block barrier, and the
+// bytes in flight hold no registers (the register-prefetch form, kept below as the A/B partner, pays 14 registers per
+// chunk in flight and ptxas sinks such loads towards their use).  Three stages per warp.
+constexpr int kScanStages = 3;
+struct __align__(16) ScanStage {
+    uint32_t meta[128];
+    uint2 sig[128];
+    FrzGroupDesc desc[4];
+};
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
+                 "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+template <bool TMA>
+__global__ void __launch_bounds__(kScanThreads, TMA ? 6 : 10) k_sig_scan(const FrzCorpusView cv, int use_sig, uint32_t need1, uint32_t need2,
+                                                                         int sig_k, int min_len, CandRec* __restrict__ cand,
+                                                                         unsigned long long cand_cap, FrzCounters* __restrict__ ctr) {
+    extern __shared__ __align__(16) unsigned char scan_smem[];
     const uint32_t lane = frz_lane(), warp = threadIdx.x >> 5;
-    CandRec* ring = ring_s[warp];
+    CandRec* ring = reinterpret_cast<CandRec*>(scan_smem) + (size_t)warp * kScanRing;
     const uint32_t n_warps = gridDim.x * kScanWarps;
     const uint32_t total_chunks = cv.n_tiles * (FRZ_TILE / 128);   // 128 slots (4 groups) per chunk
     uint32_t head = 0, count = 0;
-    // one chunk = 128 consecutive slots (4 groups): lane L owns slots 4L .. 4L+3, all in group L / 8 of the chunk
-    struct Chunk {
-        uint4 meta;
-        uint4 sig0, sig1;
-        unsigned long long abs_off;   // lanes 0-3: first unit of the chunk's group `lane`
-        uint32_t idx;
-    };
-    uint32_t next = blockIdx.x * kScanWarps + warp;
-    auto load_chunk = [&](Chunk& c) {
-        c.idx = next < total_chunks ? next : 0xFFFFFFFFu;
-        c.meta = make_uint4(FRZ_INVALID_SLOT, FRZ_INVALID_SLOT, FRZ_INVALID_SLOT, FRZ_INVALID_SLOT);
-        c.sig0 = c.sig1 = make_uint4(0u, 0u, 0u, 0u);
-        c.abs_off = 0;
-        if (next < total_chunks) {
-            const uint64_t slot0 = (uint64_t)next * 128 + lane * 4;
-            c.meta = __ldg(reinterpret_cast<const uint4*>(cv.slot_meta + slot0));
-            if (use_sig) {
-                const uint4* sp = reinterpret_cast<const uint4*>(cv.slot_sig + slot0);
-                c.sig0 = __ldg(sp);
-                c.sig1 = __ldg(sp + 1);
-            }
-            if (lane < 4) c.abs_off = cv.groups[next * 4 + lane].abs_off;   // four contiguous 16-byte descriptors, L2-resident
-        }
-        next += n_warps;
-    };
-    auto flush = [&](uint32_t n_out) {   // the first n_out (<= 32) ring entries → global list
-        unsigned long long base = 0;
-        if (lane == 0) base = atomicAdd(&ctr->cand_count, (unsigned long long)n_out);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (lane < n_out) {
+    // ---- candidate ring → global list, in two steps so that the atomic's round trip overlaps the next chunk:
+    //      flush_request reserves list space for the 32 oldest entries (they stay in the ring), flush_commit stores them
+    unsigned long long pend_base = 0;
+    uint32_t pend_head = 0, pend_n = 0;
+    auto flush_commit = [&]() {
+        if (pend_n == 0) return;
+        const unsigned long long base = __shfl_sync(0xffffffffu, pend_base, 0);
+        if (lane < pend_n) {
             const unsigned long long pos = base + lane;
-            if (pos < cand_cap) reinterpret_cast<uint4*>(cand)[pos] = reinterpret_cast<const uint4*>(ring)[(head + lane) & (kScanRing - 1)];
+            if (pos < cand_cap) reinterpret_cast<uint4*>(cand)[pos] = reinterpret_cast<const uint4*>(ring)[(pend_head + lane) & (kScanRing - 1)];
             else atomicOr(&ctr->error, FRZ_DEVERR_SURVIVOR_OVERFLOW);
         }
+        pend_n = 0;
+    };
+    auto flush_request = [&](uint32_t n_out) {
+        flush_commit();   // at most one reservation in flight
+        if (lane == 0) pend_base = atomicAdd(&ctr->cand_count, (unsigned long long)n_out);
+        pend_head = head;
+        pend_n = n_out;
         head = (head + n_out) & (kScanRing - 1);
         count -= n_out;
     };
@@ -562,31 +585,100 @@ __global__ void __launch_bounds__(kScanThreads, 10) k_sig_scan(const FrzCorpusVi
                 make_uint4(slot_global, m, (uint32_t)unit0, (uint32_t)(unit0 >> 32));
         count += __popc(ballot);
     };
-    auto process = [&](const Chunk& c) {
-        const unsigned long long grp_off = __shfl_sync(0xffffffffu, c.abs_off, lane >> 3);
-        const uint32_t slot_g = c.idx * 128 + lane * 4;                 // == tile << 10 | slot of this lane's first slot
+    // one chunk = 128 consecutive slots (4 groups): lane L owns slots 4L .. 4L+3, all in group L / 8 of the chunk
+    auto process = [&](uint32_t idx, const uint4& meta, const uint4& sig0, const uint4& sig1, unsigned long long grp_off) {
+        const uint32_t slot_g = idx * 128 + lane * 4;                   // == tile << 10 | slot of this lane's first slot
         const unsigned long long unit0 = grp_off + ((lane * 4) & 31);   // unit 0 of that slot (units of a group interleave by lane)
-        test_slot(c.meta.x, c.sig0.x, c.sig0.y, slot_g, unit0);
-        test_slot(c.meta.y, c.sig0.z, c.sig0.w, slot_g + 1, unit0 + 1);
-        test_slot(c.meta.z, c.sig1.x, c.sig1.y, slot_g + 2, unit0 + 2);
-        test_slot(c.meta.w, c.sig1.z, c.sig1.w, slot_g + 3, unit0 + 3);
+        test_slot(meta.x, sig0.x, sig0.y, slot_g, unit0);
+        test_slot(meta.y, sig0.z, sig0.w, slot_g + 1, unit0 + 1);
+        test_slot(meta.z, sig1.x, sig1.y, slot_g + 2, unit0 + 2);
+        test_slot(meta.w, sig1.z, sig1.w, slot_g + 3, unit0 + 3);
         __syncwarp();
-        while (count >= 32) flush(32);
+        flush_commit();                       // the reservation made one chunk ago has arrived
+        while (count >= 32) flush_request(32);
         __syncwarp();
     };
-    // two chunk buffers ping-pong (no struct copies): the other buffer's loads are in flight while one is tested
-    Chunk ca, cb;
-    load_chunk(ca);
-    load_chunk(cb);
-    for (;;) {
-        if (ca.idx == 0xFFFFFFFFu) break;
-        process(ca);
+    if constexpr (TMA) {
+        ScanStage* stages = reinterpret_cast<ScanStage*>(scan_smem + sizeof(CandRec) * kScanRing * kScanWarps) + warp * kScanStages;
+        uint64_t* bars = reinterpret_cast<uint64_t*>(scan_smem + (sizeof(CandRec) * kScanRing + sizeof(ScanStage) * kScanStages) * kScanWarps) +
+                         warp * kScanStages;
+        if (lane == 0)
+            for (int i = 0; i < kScanStages; i++) mbar_init(&bars[i], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        __syncwarp();
+        const uint32_t tx_bytes = (uint32_t)(sizeof(uint32_t) * 128 + sizeof(FrzGroupDesc) * 4) + (use_sig ? (uint32_t)sizeof(uint2) * 128 : 0u);
+        uint32_t req = blockIdx.x * kScanWarps + warp;   // next chunk to REQUEST
+        auto issue = [&](int st) {
+            if (req < total_chunks && lane == 0) {
+                const uint64_t slot0 = (uint64_t)req * 128;
+                mbar_expect_tx(&bars[st], tx_bytes);
+                bulk_g2s(stages[st].meta, cv.slot_meta + slot0, (uint32_t)sizeof(uint32_t) * 128, &bars[st]);
+                if (use_sig) bulk_g2s(stages[st].sig, cv.slot_sig + slot0, (uint32_t)sizeof(uint2) * 128, &bars[st]);
+                bulk_g2s(stages[st].desc, cv.groups + (size_t)req * 4, (uint32_t)sizeof(FrzGroupDesc) * 4, &bars[st]);
+            }
+            req += n_warps;
+        };
+        uint32_t cur = req;
+#pragma unroll
+        for (int i = 0; i < kScanStages; i++) issue(i);
+        int st = 0;
+        uint32_t parity = 0;
+        while (cur < total_chunks) {
+            mbar_wait(&bars[st], parity);
+            const uint4 meta = reinterpret_cast<const uint4*>(stages[st].meta)[lane];
+            uint4 sig0 = make_uint4(0u, 0u, 0u, 0u), sig1 = sig0;
+            if (use_sig) {
+                sig0 = reinterpret_cast<const uint4*>(stages[st].sig)[2 * lane];
+                sig1 = reinterpret_cast<const uint4*>(stages[st].sig)[2 * lane + 1];
+            }
+            const unsigned long long grp_off = stages[st].desc[lane >> 3].abs_off;
+            __syncwarp();
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic reads of the stage before its async refill
+            issue(st);
+            process(cur, meta, sig0, sig1, grp_off);
+            cur += n_warps;
+            if (++st == kScanStages) { st = 0; parity ^= 1; }
+        }
+    } else {
+        // register prefetch: two chunk buffers ping-pong, the other buffer's loads are in flight while one is tested
+        struct Chunk {
+            uint4 meta;
+            uint4 sig0, sig1;
+            unsigned long long abs_off;   // lanes 0-3: first unit of the chunk's group `lane`
+            uint32_t idx;
+        };
+        uint32_t next = blockIdx.x * kScanWarps + warp;
+        auto load_chunk = [&](Chunk& c) {
+            c.idx = next < total_chunks ? next : 0xFFFFFFFFu;
+            c.meta = make_uint4(FRZ_INVALID_SLOT, FRZ_INVALID_SLOT, FRZ_INVALID_SLOT, FRZ_INVALID_SLOT);
+            c.sig0 = c.sig1 = make_uint4(0u, 0u, 0u, 0u);
+            c.abs_off = 0;
+            if (next < total_chunks) {
+                const uint64_t slot0 = (uint64_t)next * 128 + lane * 4;
+                c.meta = __ldg(reinterpret_cast<const uint4*>(cv.slot_meta + slot0));
+                if (use_sig) {
+                    const uint4* sp = reinterpret_cast<const uint4*>(cv.slot_sig + slot0);
+                    c.sig0 = __ldg(sp);
+                    c.sig1 = __ldg(sp + 1);
+                }
+                if (lane < 4) c.abs_off = cv.groups[next * 4 + lane].abs_off;   // four contiguous 16-byte descriptors, L2-resident
+            }
+            next += n_warps;
+        };
+        Chunk ca, cb;
         load_chunk(ca);
-        if (cb.idx == 0xFFFFFFFFu) break;
-        process(cb);
         load_chunk(cb);
+        for (;;) {
+            if (ca.idx == 0xFFFFFFFFu) break;
+            process(ca.idx, ca.meta, ca.sig0, ca.sig1, __shfl_sync(0xffffffffu, ca.abs_off, lane >> 3));
+            load_chunk(ca);
+            if (cb.idx == 0xFFFFFFFFu) break;
+            process(cb.idx, cb.meta, cb.sig0, cb.sig1, __shfl_sync(0xffffffffu, cb.abs_off, lane >> 3));
+            load_chunk(cb);
+        }
     }
-    if (count) flush(count);
+    flush_commit();
+    if (count) { flush_request(count); flush_commit(); }
 }
 
 // ================================================================================================================
@@ -603,10 +695,11 @@ struct WinStage {
 struct WinSmem {
     uint2 occ[kMaxDistinct][32];
     WinStage stage[2];
+    uint4 rec[3][32];     // candidate records of items k, k+1, k+2 (ring), also filled by cp.async
 };
 
 template <int MODE>
-__global__ void __launch_bounds__(kWinThreads, 6) k_window(const FrzCorpusView cv, const __grid_constant__ FrzPatternDev pat,
+__global__ void __launch_bounds__(kWinThreads, 5) k_window(const FrzCorpusView cv, const __grid_constant__ FrzPatternDev pat,
                                                            const CandRec* __restrict__ cand, unsigned long long cand_cap,
                                                            const FrzSurvLists lists, unsigned long long surv_cap,
                                                            uint32_t* __restrict__ surv_bitmap, FrzCounters* __restrict__ ctr,
@@ -622,17 +715,21 @@ __global__ void __launch_bounds__(kWinThreads, 6) k_window(const FrzCorpusView c
     const bool staged = cv.max_gunits <= 4;   // every haystack fits the four staged units
     const bool single = (MODE == FRZ_T_0 || MODE == FRZ_T_1) && (flags & 1u) && single_chunk_ok(pat, cv.max_gunits);
 
-    // work items are strided statically over the warps of the grid (their cost is uniform): item indices are known ahead,
-    // so the records of item i+2 are requested while item i is processed — no ticket round trip in the loop
+    // Work items are strided statically over the warps of the grid (their cost is uniform), so the item sequence of a warp
+    // is known ahead: item k's units AND item k+1's records were requested with cp.async one iteration earlier (records
+    // fetched into registers were sunk by ptxas to their first use: 27% of the stall samples, profiles/r02e).
+    //   group G_k (committed in iteration k) = { units of item k+1 , records of item k+2 }
     const uint32_t n_warps = gridDim.x * kWinWarps;
-    auto load_rec = [&](uint32_t item) {
-        uint4 r = make_uint4(0xFFFFFFFFu, 0u, 0u, 0u);
+    const uint32_t item0 = blockIdx.x * kWinWarps + warp;
+    auto fetch_rec = [&](uint32_t k) {   // records of this warp's k-th item → ring slot k % 3
+        const uint32_t item = item0 + k * n_warps;
         const unsigned long long j = (unsigned long long)item * 32 + lane;
-        if (item < n_items && j < n_cand) r = __ldg(reinterpret_cast<const uint4*>(cand) + j);
-        return r;   // {tile_slot, meta, unit0 lo, unit0 hi}
+        uint4* dst = &sm.rec[k % 3][lane];
+        if (item < n_items && j < n_cand) __pipeline_memcpy_async(dst, reinterpret_cast<const uint4*>(cand) + j, 16);
+        else *dst = make_uint4(0xFFFFFFFFu, 0u, 0u, 0u);
     };
     auto unit0_of = [](const uint4& r) { return ((unsigned long long)r.w << 32) | r.z; };
-    auto stage_units = [&](const uint4& r, int st) {
+    auto fetch_units = [&](const uint4& r, int st) {
         if (staged && r.x != 0xFFFFFFFFu) {
             const int units = ((int)(r.y >> FRZ_TILE_SHIFT) + 15) >> 4;
             const uint4* base = cv.data + unit0_of(r);
@@ -640,21 +737,25 @@ __global__ void __launch_bounds__(kWinThreads, 6) k_window(const FrzCorpusView c
             for (int k = 0; k < 4; k++)
                 if (k < units) __pipeline_memcpy_async(&sm.stage[st].units[k][lane], base + (size_t)k * FRZ_GROUP, 16);
         }
-        __pipeline_commit();
     };
-    uint32_t item = blockIdx.x * kWinWarps + warp;
-    uint4 rec0 = load_rec(item);
-    stage_units(rec0, 0);
-    uint4 rec1 = load_rec(item + n_warps);
+    fetch_rec(0);
+    fetch_rec(1);
+    __pipeline_commit();
+    __pipeline_wait_prior(0);
+    __syncwarp();
+    fetch_units(sm.rec[0][lane], 0);
+    __pipeline_commit();
     Emit pending;
     pending.ok = false; pending.cls = 0; pending.peers = 0; pending.base_raw = 0;
     pending.rec.tile = 0; pending.rec.slot_rank = 0; pending.rec.start = 0; pending.rec.end = 0;
-    int st = 0;
-    while (item < n_items) {
-        stage_units(rec1, st ^ 1);                            // next item's units start moving ...
-        const uint4 rec2 = load_rec(item + 2 * n_warps);      // ... and the one after that requests its records
-        __pipeline_wait_prior(1);                             // this item's units have landed
+    for (uint32_t k = 0; item0 + k * n_warps < n_items; k++) {
+        __pipeline_wait_prior(0);                        // G_{k-1}: this item's units and the next item's records
         __syncwarp();
+        const uint4 rec0 = sm.rec[k % 3][lane];
+        fetch_units(sm.rec[(k + 1) % 3][lane], (k + 1) & 1);
+        fetch_rec(k + 2);
+        __pipeline_commit();                             // G_k flies while item k is processed
+        const int st = k & 1;
         const bool active = rec0.x != 0xFFFFFFFFu;
         Cand cd;
         cd.tile = rec0.x >> FRZ_TILE_SHIFT;
@@ -665,14 +766,10 @@ __global__ void __launch_bounds__(kWinThreads, 6) k_window(const FrzCorpusView c
         cd.units = staged ? &sm.stage[st].units[0][lane] : cd.base;
         Emit cur;
         process_candidate<MODE>(cv, pat, cid_s, sm.occ, cd, active, surv_bitmap, &cur, single);
-        emit_commit(pending, lists, surv_cap, ctr);           // the previous item's list space has arrived by now
+        emit_commit(pending, lists, surv_cap, ctr);      // the previous item's list space has arrived by now
         emit_request(cur, ctr);
         pending = cur;
         __syncwarp();
-        item += n_warps;
-        rec0 = rec1;
-        rec1 = rec2;
-        st ^= 1;
     }
     emit_commit(pending, lists, surv_cap, ctr);
     __pipeline_wait_prior(0);
@@ -872,17 +969,28 @@ frz_status frz_launch_prefilter(const FrzCorpusView& cv, const FrzPatternDev& pa
     const uint32_t pf_flags = single_knob ? 1u : 0u;
     CandRec* cand = reinterpret_cast<CandRec*>(ws.cand_list);
     {   // 1a: persistent warps, as many blocks as fit
-        static int bps_dev[64] = {};
-        int& bps = bps_dev[frz_current_device() & 63];
-        if (!bps) {
-            FRZ_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_sig_scan, kScanThreads, 0));
-            if (bps < 1) bps = 1;
-        }
+        static int tma_knob = -1;   // A/B knob: FRZ_PF_TMA=0 selects the register-prefetch form of the phase-A loads
+        if (tma_knob < 0) { const char* e = getenv("FRZ_PF_TMA"); tma_knob = e ? atoi(e) : 1; }
         const uint32_t total_chunks = cv.n_tiles * (FRZ_TILE / 128);
-        const uint32_t grid = std::max<uint32_t>(1, std::min<uint32_t>((uint32_t)(sms * bps), (total_chunks + kScanWarps - 1) / kScanWarps));
         const int use_sig = pat.typo_mode != FRZ_T_NONE && pat.sig_on;
-        k_sig_scan<<<grid, kScanThreads, 0, stream>>>(cv, use_sig, pat.sig_need1, pat.sig_need2, pat.sig_k, pat.min_hay_len, cand,
-                                                     ws.cand_cap, ws.counters);
+        const size_t ring_bytes = sizeof(CandRec) * kScanRing * kScanWarps;
+        const size_t smem_tma = ring_bytes + (sizeof(ScanStage) * kScanStages + sizeof(uint64_t) * kScanStages) * kScanWarps;
+#define FRZ_SCAN_LAUNCH(TMA, SMEM)                                                                                       \
+        do {                                                                                                             \
+            static int bps_dev[64] = {};                                                                                 \
+            int& bps = bps_dev[frz_current_device() & 63];                                                               \
+            if (!bps) {                                                                                                  \
+                FRZ_CUDA_TRY(cudaFuncSetAttribute(k_sig_scan<TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMEM))); \
+                FRZ_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_sig_scan<TMA>, kScanThreads, (SMEM))); \
+                if (bps < 1) bps = 1;                                                                                    \
+            }                                                                                                            \
+            const uint32_t grid = std::max<uint32_t>(1, std::min<uint32_t>((uint32_t)(sms * bps), (total_chunks + kScanWarps - 1) / kScanWarps)); \
+            k_sig_scan<TMA><<<grid, kScanThreads, (SMEM), stream>>>(cv, use_sig, pat.sig_need1, pat.sig_need2, pat.sig_k,  \
+                                                                   pat.min_hay_len, cand, ws.cand_cap, ws.counters);     \
+        } while (0)
+        if (tma_knob) FRZ_SCAN_LAUNCH(true, smem_tma);
+        else FRZ_SCAN_LAUNCH(false, ring_bytes);
+#undef FRZ_SCAN_LAUNCH
     }
     const size_t smem = sizeof(WinSmem) * kWinWarps;
 #define FRZ_PF_LAUNCH(MODE)                                                                                              \

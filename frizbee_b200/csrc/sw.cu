@@ -446,22 +446,14 @@ frz_status launch_sw_lanes(const FrzCorpusView& cv, const FrzPatternDev& pat, ui
     const int blocks64 = sm_count() * kSw64MinBlocks;
     const int rev = reversed ? 1 : 0;
     if (LANES == 64 && !pat.wrap8) {
-        // pipe-balance experiment knob: FRZ_SW_VARIANT = SwCore's VAR bits, default 0
-        static int var = -1;
-        if (var < 0) { const char* e = getenv("FRZ_SW_VARIANT"); var = e ? atoi(e) : 0; }
-#define FRZ_SW_VAR_CASE(V)                                                                                                    \
-        if (var == V) {                                                                                                       \
-            k_sw64<64, false, V><<<blocks64, kSwThreads, 0, stream>>>(cv, pat, ws.lists(), ws.survivor_cap, rank_view(ws),     \
-                                                                      ws.counters, index_offset, rev, d_out);                 \
-        } else
-        FRZ_SW_VAR_CASE(8) FRZ_SW_VAR_CASE(16) FRZ_SW_VAR_CASE(24)
-#undef FRZ_SW_VAR_CASE
-            k_sw64<64, false, 0><<<blocks64, kSwThreads, 0, stream>>>(cv, pat, ws.lists(), ws.survivor_cap, rank_view(ws), ws.counters,
-                                                                      index_offset, rev, d_out);
+        // VAR 8: the per-column bonus is classified on the packed window bytes (SwCore) — measured -4.4% on B200 against
+        // the per-lane form (profiles/r02e_variants.txt); the other VAR bits of rounds 1-2 lost their A/Bs and are gone
+        k_sw64<64, false, 8><<<blocks64, kSwThreads, 0, stream>>>(cv, pat, ws.lists(), ws.survivor_cap, rank_view(ws), ws.counters,
+                                                                  index_offset, rev, d_out);
     } else if (pat.wrap8)
         k_sw64<LANES, true><<<blocks64, kSwThreads, 0, stream>>>(cv, pat, ws.lists(), ws.survivor_cap, rank_view(ws), ws.counters, index_offset, rev, d_out);
     else
-        k_sw64<LANES, false><<<blocks64, kSwThreads, 0, stream>>>(cv, pat, ws.lists(), ws.survivor_cap, rank_view(ws), ws.counters, index_offset, rev, d_out);
+        k_sw64<LANES, false, 8><<<blocks64, kSwThreads, 0, stream>>>(cv, pat, ws.lists(), ws.survivor_cap, rank_view(ws), ws.counters, index_offset, rev, d_out);
     // windows of 65..128 bytes only exist when some haystack of the corpus is longer than 64 bytes (recorded at pack time)
     if (cv.max_gunits <= 4) { FRZ_CUDA_TRY(cudaGetLastError()); return FRZ_OK; }
     const size_t smem = SwCore<LANES, 128, false>::smem_bytes;

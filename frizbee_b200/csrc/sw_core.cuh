@@ -114,11 +114,10 @@ struct RowStore<R, true> {
     FRZ_SW_FN void set(int r, uint32_t x) { base[r * kSwThreads] = x; }
 };
 
-// VAR bits (A/B switches, each measured on B200 — profiles/r02_experiments.md):
-//   bit 3 (8):  the per-column bonus is classified on the packed bytes (4 at a time) instead of per 16-bit lane
-//   bit 4 (16): gap step 1 folds the shifted match mask into the penalty with IMAD.HI + IMAD (no mask shift at all)
-// (bits 0-2 moved the one-lane shifts of the row loop from PRMT to IMAD.HI + IMAD pairs; static pipe counts predicted
-//  -14%, the B200 measured +2% .. +16% — the pairs cost more issue slots than the ALU pipe saves — and they were removed.)
+// VAR bit 3 (8): the per-column bonus is classified on the packed bytes (4 at a time) instead of per 16-bit lane — the
+// default of the non-wrapping 64-lane kernel (-4.4% on B200).  A/Bs that LOST on B200 and were removed (profiles/
+// r02_experiments.md): one-lane shifts as IMAD.HI + IMAD pairs instead of PRMT (static pipe counts predicted -14%,
+// measured +2% .. +16%), the shifted match mask folded into the gap penalty with IMAD.HI (+2%), two column classes (+3%).
 //
 // CC (<= COLS, multiple of 8) is the number of columns actually evaluated.  Cells never depend on cells to
 // their right, and a cell in column >= W + needle_len can only hold a value that decayed from a cell to its
@@ -273,8 +272,7 @@ struct SwCore {
                         uint32_t sh, smm;
                         if (s == 1 && !WRAP8) {
                             sh = r == 0 ? __byte_perm(0u, H[0], 0x5432) : __byte_perm(H[r - 1], H[r], 0x5432);
-                            if (VAR & 16) smm = 0;   // folded into the penalty below
-                            else smm = r == 0 ? __byte_perm(0u, M[0], 0x5432) : __byte_perm(M[r - 1], M[r], 0x5432);
+                            smm = r == 0 ? __byte_perm(0u, M[0], 0x5432) : __byte_perm(M[r - 1], M[r], 0x5432);
                         } else if (s == 1) {
                             if (r == 0) { sh = __byte_perm(0u, H[0], 0x5432); smm = __byte_perm(0u, M[0], 0x5432); }
                             else { sh = __byte_perm(H[r - 1], H[r], 0x5432); smm = __byte_perm(M[r - 1], M[r], 0x5432); }
@@ -284,16 +282,7 @@ struct SwCore {
                             sh = H[src];
                             smm = M[src];
                         }
-                        uint32_t pen;
-                        if (WRAP8) pen = sel(smm, penB, penA);
-                        else if (s == 1 && (VAR & 16)) {
-                            // VAR bit 4: pen = penB + shifted(M) * gopx without materialising the shifted mask — the high
-                            // lane of M[r-1] reaches the low lane through IMAD.HI (addend penB), the low lane of M[r] reaches
-                            // the high lane through IMAD: two FMA-pipe instructions instead of PRMT (ALU pipe) + IMAD
-                            const uint32_t g16 = gopx << 16;
-                            const uint32_t t = (r == 0 ? 0u : __umulhi(M[r - 1], g16)) + penB;
-                            pen = M[r] * g16 + t;
-                        } else pen = penB + smm * gopx;
+                        const uint32_t pen = WRAP8 ? sel(smm, penB, penA) : penB + smm * gopx;
                         H[r] = addmax_relu(sh, pen, H[r]);
                     }
                 }

@@ -51,11 +51,9 @@ int dispatch_cc(const FrzPatternDev& pat, const uint8_t* w, int W, int startlo, 
 template <int LANES>
 int dispatch(const FrzPatternDev& pat, const uint8_t* w, int W, int startlo, bool pre, int cols, int cc, int wrap8, int var, int* eq) {
     if (wrap8) return dispatch_cc<LANES, true, 0>(pat, w, W, startlo, pre, cols, cc, eq);
-    if (LANES == 64) {
+    {
         switch (var) {
             case 8: return dispatch_cc<LANES, false, 8>(pat, w, W, startlo, pre, cols, cc, eq);
-            case 16: return dispatch_cc<LANES, false, 16>(pat, w, W, startlo, pre, cols, cc, eq);
-            case 24: return dispatch_cc<LANES, false, 24>(pat, w, W, startlo, pre, cols, cc, eq);
         }
     }
     return dispatch_cc<LANES, false, 0>(pat, w, W, startlo, pre, cols, cc, eq);
