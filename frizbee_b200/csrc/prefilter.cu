@@ -699,7 +699,7 @@ struct WinSmem {
 };
 
 template <int MODE>
-__global__ void __launch_bounds__(kWinThreads, 5) k_window(const FrzCorpusView cv, const __grid_constant__ FrzPatternDev pat,
+__global__ void __launch_bounds__(kWinThreads, 4) k_window(const FrzCorpusView cv, const __grid_constant__ FrzPatternDev pat,
                                                            const CandRec* __restrict__ cand, unsigned long long cand_cap,
                                                            const FrzSurvLists lists, unsigned long long surv_cap,
                                                            uint32_t* __restrict__ surv_bitmap, FrzCounters* __restrict__ ctr,
@@ -1002,6 +1002,9 @@ frz_status frz_launch_prefilter(const FrzCorpusView& cv, const FrzPatternDev& pa
             FRZ_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_window<MODE>, kWinThreads, smem));        \
             static int knob = -1;   /* experiment knob: FRZ_PF_BLOCKS caps the resident blocks per SM */                 \
             if (knob < 0) { const char* e = getenv("FRZ_PF_BLOCKS"); knob = e ? atoi(e) : 0; }                           \
+            /* measured on B200 (profiles/r02f_variants.txt): 4 resident blocks per SM beat 5 and 3 (0.141 / 0.157 / 0.143 ms */ \
+            /* for the stage) — the scattered unit fetches of more warps thrash each other in L1 / the LSU queues */       \
+            if (bps > 4) bps = 4;                                                                                        \
             if (knob > 0 && knob < bps) bps = knob;                                                                      \
             if (bps < 1) bps = 1;                                                                                        \
         }                                                                                                                \
