@@ -45,7 +45,8 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=WORKLOAD["n"], help="haystacks per GPU")
+    ap.add_argument("--n", "--haystacks-per-gpu", dest="n", type=int, default=WORKLOAD["n"],
+                    help="haystacks per GPU (under torchrun spell it --haystacks-per-gpu: torchrun's own parser treats --n as an abbreviation)")
     ap.add_argument("--e2e-steps", type=int, default=0, help="default: min(steps, 5)")
     ap.add_argument("--e2e-offsets", type=int, default=32, choices=[32, 64],
                     help="Arrow offset width of the e2e input (32 = Utf8, 64 = LargeUtf8)")
@@ -513,6 +514,11 @@ def run_ours(args):
                 "config": config_block(args, world, {"matches_per_step": int(n_matches),
                                                      "output": "ordered frz_match[] landed in ONE pinned host buffer "
                                                                "(shared by the ranks; every GPU copies its slice)",
+                                                     "exchange": ("n/a (1 GPU)" if world == 1 else
+                                                                  "all-gather of whole runs (FRZ_PARALLEL_EXCHANGE=allgather)"
+                                                                  if os.environ.get("FRZ_PARALLEL_EXCHANGE") == "allgather" else
+                                                                  "slice exchange: one grouped ncclSend/ncclRecv of exactly the ranges each rank copies out "
+                                                                  "(value); all-gather of whole runs (value_device_out)"),
                                                      "emulated_reference_backend": info}),
                 "clocks": clocks,
                 "value_device_out": {"value": n * world * args.steps / (ms_dev / 1e3), "unit": "haystacks/s",

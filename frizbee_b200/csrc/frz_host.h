@@ -153,6 +153,8 @@ frz_status frz_launch_sort_by_score_dev(const FrzMatchDev* d_in, FrzMatchDev* d_
                                         const unsigned long long* n_ptr, uint32_t score_bound, FrzWorkspace& ws,
                                         cudaStream_t stream, FrzLaunchStats* st);
 size_t frz_sort_hist_words();
+const uint32_t* frz_sort_digit_base(const FrzWorkspace& ws);
+int frz_sort_single_pass_bins(uint32_t score_bound);   // bins of the single-pass sort for this bound, 0 = two passes
 
 // k-way merge of per-shard runs (host.cu) with caller-owned scratch — one per concurrent user (parallel.cu: one per rank)
 #define FRZ_MERGE_MAX_RUNS 64
@@ -172,6 +174,9 @@ frz_status frz_merge_runs_ex(FrzMergeScratch& ms, const FrzMatchDev* runs, uint6
 // Matcher internals the multi-GPU layer needs (host.cu)
 uint64_t frz_matcher_epoch(const frz_matcher* m);                  // changes whenever the compiled patterns change
 uint8_t frz_matcher_sort(const frz_matcher* m);
+// After a match_list / shard call: the per-score "how many matches score higher" table of the run just produced (device
+// pointer, valid until the next call on m) and its length; bins = 0 when the run was not ordered by a single-pass score sort.
+const uint32_t* frz_matcher_last_sort_table(const frz_matcher* m, int* bins);
 // host Arrow buffers → the matcher's reusable packed corpus (the ingest half of frz_match_list_host_arrow)
 frz_status frz_matcher_ingest_e2e(frz_matcher* m, const uint8_t* bytes, const void* offsets, int offset_width, uint64_t n, int device,
                                   const frz_corpus** out);

@@ -614,6 +614,7 @@ struct frz_matcher {
     bool count_published = false;
     bool timings_pending = false;
     uint64_t epoch = 0;                    // identity of the compiled patterns (clones made for another epoch are stale)
+    int last_sort_bins = 0;                // bins of the single-pass score sort of the last call (0: none / two passes)
     ~frz_matcher() {
         if (ws.device >= 0) { cudaSetDevice(ws.device); cudaFree(multi_a); cudaFree(multi_b); if (count_ev) cudaEventDestroy(count_ev); }
         if (e2e_ingest.d_bytes || e2e_ingest.copy_stream || e2e_corpus.st.data) {
@@ -713,6 +714,10 @@ extern "C" frz_status frz_matcher_clone(const frz_matcher* src, frz_matcher** ou
 }
 uint64_t frz_matcher_epoch(const frz_matcher* m) { return m ? m->epoch : 0; }
 uint8_t frz_matcher_sort(const frz_matcher* m) { return m ? m->config.sort : 0; }
+const uint32_t* frz_matcher_last_sort_table(const frz_matcher* m, int* bins) {
+    if (bins) *bins = m ? m->last_sort_bins : 0;
+    return (m && m->last_sort_bins) ? frz_sort_digit_base(m->ws) : nullptr;
+}
 
 extern "C" void frz_matcher_destroy(frz_matcher* m) { delete m; }
 extern "C" size_t frz_matcher_num_patterns(const frz_matcher* m) { return m ? m->compiled.size() : 0; }
@@ -1080,6 +1085,7 @@ frz_status match_list_device(frz_matcher* m, const FrzCorpusStorage& cs, uint32_
     const bool by_score = sort == FRZ_SORT_SCORE_THEN_INDEX_ASC || sort == FRZ_SORT_SCORE_THEN_INDEX_DESC;
     const bool will_sort = by_score && !m->compiled.empty();
     for (bool& f : ws.ev_rec) f = false;
+    m->last_sort_bins = 0;
     FrzMatchDev* d_list = nullptr;
     uint32_t bound = 0;
     FRZ_TRY(match_into_device(m, cs, index_offset, reversed, &d_list, &bound, stream, st, will_sort ? nullptr : final_out));
@@ -1094,6 +1100,7 @@ frz_status match_list_device(frz_matcher* m, const FrzCorpusStorage& cs, uint32_
             tmp = m->multi_a;
         }
         FRZ_TRY(frz_launch_sort_by_score_dev(d_list, tmp, other, &ws.counters->total, bound, ws, stream, st));
+        m->last_sort_bins = frz_sort_single_pass_bins(bound);
         d_list = other;
     } else if (final_out && d_list != final_out) {
         k_copy_n<<<grid_for(cs.n, 256), 256, 0, stream>>>(d_list, final_out, &ws.counters->total);

@@ -137,16 +137,20 @@ class Comm:
         _check(plib().frz_match_list_parallel(matcher._h, hs, len(shards), self._h, out.ctypes.data, len(out), C.byref(n)))
         return out[: n.value]
 
-    def match_list_parallel_rank(self, matcher: Matcher, shard: Corpus, index_offset: int, out: Optional[np.ndarray] = None
-                                 ) -> Tuple[int, int]:
+    def match_list_parallel_rank(self, matcher: Matcher, shard: Corpus, index_offset: int, out: Optional[np.ndarray] = None,
+                                 want_device: Optional[bool] = None) -> Tuple[int, int]:
         """Multi-process form (frz_match_list_parallel_rank), collective.  `out`: the SHARED host array from
-        host_alloc_matches (every rank passes its mapping) or None for a device-only result.
-        Returns (total matches, device pointer of this rank's merged list)."""
+        host_alloc_matches (every rank passes its mapping) or None for a device-only result.  `want_device` (default: only
+        when `out` is None) also asks for this rank's device copy of the WHOLE merged list — that forces the all-gather form;
+        host-only calls use the slice exchange.  Returns (total matches, device pointer of the merged list or 0)."""
+        if want_device is None:
+            want_device = out is None
         n = C.c_uint64()
         d = C.c_void_p()
         _check(plib().frz_match_list_parallel_rank(matcher._h, shard._h, index_offset, self._h,
                                                    out.ctypes.data if out is not None else None,
-                                                   len(out) if out is not None else 0, C.byref(n), C.byref(d)))
+                                                   len(out) if out is not None else 0, C.byref(n),
+                                                   C.byref(d) if want_device else None))
         return n.value, d.value or 0
 
     def match_list_parallel_rank_host(self, matcher: Matcher, data: np.ndarray, offsets: np.ndarray, index_offset: int,

@@ -127,13 +127,17 @@ def test_c_client_on_the_gpu(tmp_path):
     assert f"match_list_parallel over {n} GPU(s)" in r.stdout and "parallel == sequential: yes" in r.stdout
 
 
-def test_local_form_two_gpus():
-    """Single process, two GPUs (frz_comm_create_local: ncclCommInitAll + one worker thread per GPU)."""
+@pytest.mark.parametrize("exchange", ["slices", "allgather"])
+def test_local_form_two_gpus(exchange, monkeypatch):
+    """Single process, two GPUs (frz_comm_create_local: ncclCommInitAll + one worker thread per GPU), with both forms of
+    the collective step: the slice exchange (grouped ncclSend/ncclRecv of exactly what each rank copies out) and the
+    all-gather of whole runs."""
     if _gpus() < 2:
         pytest.skip("needs >= 2 GPUs")
     import frizbee_b200 as F
     from frizbee_b200 import parallel, synth
     from frizbee_b200.types import Config, SortStrategy
+    monkeypatch.setenv("FRZ_PARALLEL_EXCHANGE", exchange)
     comm = parallel.Comm.local(2)
     data, off = synth.generate("deadbeef", 300_001, 48, 64, seed=33)
     shards = comm.shard_arrow(data, off)
@@ -157,12 +161,14 @@ def test_local_form_two_gpus():
     whole.close(); comm.close()
 
 
-def test_match_list_parallel_two_gpus_torchrun():
-    """One rank per GPU under torchrun (the bench's launch mode): tests/_multi_gpu_worker.py."""
+@pytest.mark.parametrize("exchange", ["slices", "allgather"])
+def test_match_list_parallel_two_gpus_torchrun(exchange):
+    """One rank per GPU under torchrun (the bench's launch mode): tests/_multi_gpu_worker.py, with both forms of the
+    collective step for the host-out calls (device-only calls always all-gather)."""
     if _gpus() < 2:
         pytest.skip("needs >= 2 GPUs")
     world = 2
-    env = dict(os.environ, FRZ_PARALLEL_TIMEOUT_S="60")
+    env = dict(os.environ, FRZ_PARALLEL_TIMEOUT_S="60", FRZ_PARALLEL_EXCHANGE=exchange)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr", "127.0.0.1",
            "--master-port", "29533", os.path.join(ROOT, "tests", "_multi_gpu_worker.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env)
