@@ -122,6 +122,9 @@ struct FrzWorkspace {
     uint64_t retain_cap = 0;
     uint16_t* unicode_scratch = nullptr;    // unicode.cu: per-thread row state of the per-scalar Smith-Waterman
     uint64_t unicode_scratch_cap = 0;       // in uint16 elements
+    cudaEvent_t table_ev = nullptr;         // recorded right after the sort's scan kernel: the per-score table is final there,
+    bool arm_table_ev = false;              //   one kernel (the scatter) before the run itself (shard calls arm it)
+    bool table_ev_recorded = false;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     bool ev_rec[6] = {false, false, false, false, false, false};  // recorded during the current call
     void release();
@@ -153,6 +156,7 @@ frz_status frz_launch_sort_by_score_dev(const FrzMatchDev* d_in, FrzMatchDev* d_
                                         const unsigned long long* n_ptr, uint32_t score_bound, FrzWorkspace& ws,
                                         cudaStream_t stream, FrzLaunchStats* st);
 size_t frz_sort_hist_words();
+frz_status frz_sort_hist_alloc(uint32_t** out);
 const uint32_t* frz_sort_digit_base(const FrzWorkspace& ws);
 int frz_sort_single_pass_bins(uint32_t score_bound);   // bins of the single-pass sort for this bound, 0 = two passes
 
@@ -177,6 +181,8 @@ uint8_t frz_matcher_sort(const frz_matcher* m);
 // After a match_list / shard call: the per-score "how many matches score higher" table of the run just produced (device
 // pointer, valid until the next call on m) and its length; bins = 0 when the run was not ordered by a single-pass score sort.
 const uint32_t* frz_matcher_last_sort_table(const frz_matcher* m, int* bins);
+// event recorded when that table became final (before the sort's scatter kernel), or nullptr
+cudaEvent_t frz_matcher_table_event(const frz_matcher* m);
 // host Arrow buffers → the matcher's reusable packed corpus (the ingest half of frz_match_list_host_arrow)
 frz_status frz_matcher_ingest_e2e(frz_matcher* m, const uint8_t* bytes, const void* offsets, int offset_width, uint64_t n, int device,
                                   const frz_corpus** out);

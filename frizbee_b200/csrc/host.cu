@@ -587,6 +587,8 @@ void FrzWorkspace::release() {
     cudaFree(surv_bitmap); cudaFree(word_prefix); surv_bitmap = nullptr; word_prefix = nullptr;
     cudaFree(tile_count); cudaFree(tile_out_base); cudaFree(matches_a); cudaFree(matches_b); cudaFree(sort_hist); cudaFree(cand_list);
     for (auto& e : ev) { if (e) cudaEventDestroy(e); e = nullptr; }
+    if (table_ev) cudaEventDestroy(table_ev);
+    table_ev = nullptr;
     counters = nullptr; h_counters = nullptr; tile_count = nullptr; tile_out_base = nullptr; matches_a = matches_b = nullptr;
     sort_hist = nullptr; cand_list = nullptr;
     cudaFree(retain_cnt); cudaFree(retain_base); cudaFree(retain_keep); retain_cnt = nullptr; retain_base = nullptr; retain_keep = nullptr; retain_cap = 0;
@@ -714,6 +716,7 @@ extern "C" frz_status frz_matcher_clone(const frz_matcher* src, frz_matcher** ou
 }
 uint64_t frz_matcher_epoch(const frz_matcher* m) { return m ? m->epoch : 0; }
 uint8_t frz_matcher_sort(const frz_matcher* m) { return m ? m->config.sort : 0; }
+cudaEvent_t frz_matcher_table_event(const frz_matcher* m) { return (m && m->last_sort_bins && m->ws.table_ev_recorded) ? m->ws.table_ev : nullptr; }
 const uint32_t* frz_matcher_last_sort_table(const frz_matcher* m, int* bins) {
     if (bins) *bins = m ? m->last_sort_bins : 0;
     return (m && m->last_sort_bins) ? frz_sort_digit_base(m->ws) : nullptr;
@@ -858,9 +861,9 @@ frz_status ensure_workspace(frz_matcher* m, const FrzCorpusStorage& cs, uint64_t
         FRZ_CUDA_TRY(cudaMalloc(&ws.counters, sizeof(FrzCounters)));
         FRZ_CUDA_TRY(cudaMallocHost(&ws.h_counters, sizeof(FrzCounters)));
         for (auto& e : ws.ev) FRZ_CUDA_TRY(cudaEventCreate(&e));
-        size_t words = frz_sort_hist_words();
-        FRZ_CUDA_TRY(cudaMalloc(&ws.sort_hist, words * sizeof(uint32_t)));
-        ws.sort_hist_cap = words;
+        FRZ_CUDA_TRY(cudaEventCreateWithFlags(&ws.table_ev, cudaEventDisableTiming));
+        FRZ_TRY(frz_sort_hist_alloc(&ws.sort_hist));
+        ws.sort_hist_cap = frz_sort_hist_words();
     }
     if (ws.tiles_cap < cs.n_tiles) {
         cudaFree(ws.tile_count); cudaFree(ws.tile_out_base); cudaFree(ws.surv_bitmap); cudaFree(ws.word_prefix);
@@ -1310,8 +1313,11 @@ extern "C" frz_status frz_match_shard_device(frz_matcher* m, const frz_corpus* s
     if (!m->count_ev) FRZ_CUDA_TRY(cudaEventCreateWithFlags(&m->count_ev, cudaEventDisableTiming));
     m->early_count_dst = d_count;
     m->count_published = false;
+    m->ws.arm_table_ev = true;
+    m->ws.table_ev_recorded = false;
     const frz_status ms = match_list_device(m, shard->st, index_offset, m->config.sort, &d_list, stream, &st, reinterpret_cast<FrzMatchDev*>(d_out));
     m->early_count_dst = nullptr;
+    m->ws.arm_table_ev = false;
     FRZ_TRY(ms);
     if (!m->count_published) {   // multi-pattern / empty pattern: the count exists only at the end
         FRZ_CUDA_TRY(cudaMemcpyAsync(d_count, &m->ws.counters->total, sizeof(uint64_t), cudaMemcpyDeviceToDevice, stream));
@@ -1454,7 +1460,7 @@ frz_status frz_merge_runs_ex(FrzMergeScratch& ms, const FrzMatchDev* runs, uint6
     if (ms.device < 0) {
         int dev = 0;
         FRZ_CUDA_TRY(cudaGetDevice(&dev));
-        FRZ_CUDA_TRY(cudaMalloc(&ms.hist, frz_sort_hist_words() * sizeof(uint32_t)));
+        FRZ_TRY(frz_sort_hist_alloc(&ms.hist));
         FRZ_CUDA_TRY(cudaMalloc(&ms.tables, (size_t)2 * FRZ_MERGE_MAX_RUNS * kMergeMaxBins * sizeof(uint32_t)));
         FRZ_CUDA_TRY(cudaMalloc(&ms.d_total, sizeof(unsigned long long)));
         ms.device = dev;
@@ -1520,7 +1526,7 @@ extern "C" frz_status frz_radix_sort_matches(frz_match* matches, uint64_t n, int
         FRZ_CUDA_TRY(cudaMalloc(&d_b, n * sizeof(FrzMatchDev)));
         FRZ_CUDA_TRY(cudaMalloc(&d_c, n * sizeof(FrzMatchDev)));
         FRZ_CUDA_TRY(cudaMalloc(&d_n, sizeof(unsigned long long)));
-        FRZ_CUDA_TRY(cudaMalloc(&ws.sort_hist, frz_sort_hist_words() * sizeof(uint32_t)));
+        FRZ_TRY(frz_sort_hist_alloc(&ws.sort_hist));
         unsigned long long hn = n;
         FRZ_CUDA_TRY(cudaMemcpyAsync(d_n, &hn, sizeof hn, cudaMemcpyHostToDevice, stream));
         FRZ_CUDA_TRY(cudaMemcpyAsync(d_a, matches, n * sizeof(FrzMatchDev), cudaMemcpyHostToDevice, stream));

@@ -223,8 +223,8 @@ struct RankCtx {
     // slice exchange (host-out calls): pieces received from every run, device copies of the gt / pos0 tables, pinned staging
     FrzMatchDev* recv = nullptr;
     uint64_t recv_cap = 0;
-    uint32_t* d_gt = nullptr;
-    unsigned long long* d_pos0 = nullptr;
+    uint32_t* d_gt = nullptr;               // (d_pos0 and d_gt are one allocation, h_pos0 and h_gt one pinned staging block:
+    unsigned long long* d_pos0 = nullptr;   //  the tables travel in ONE host→device copy)
     uint32_t* h_gt = nullptr;
     unsigned long long* h_pos0 = nullptr;
     uint32_t* table_dev = nullptr;          // device-side address of the shared table block
@@ -281,8 +281,7 @@ void rank_release(RankCtx& r) {
     cudaSetDevice(r.device);
     if (r.clone) frz_matcher_destroy(r.clone);
     r.clone = nullptr;
-    cudaFree(r.run); cudaFree(r.d_count); cudaFree(r.gathered); cudaFree(r.merged); cudaFree(r.recv); cudaFree(r.d_gt); cudaFree(r.d_pos0);
-    if (r.h_gt) cudaFreeHost(r.h_gt);
+    cudaFree(r.run); cudaFree(r.d_count); cudaFree(r.gathered); cudaFree(r.merged); cudaFree(r.recv); cudaFree(r.d_pos0);
     if (r.h_pos0) cudaFreeHost(r.h_pos0);
     r.run = nullptr; r.d_count = nullptr; r.gathered = nullptr; r.merged = nullptr; r.recv = nullptr; r.d_gt = nullptr; r.d_pos0 = nullptr;
     r.h_gt = nullptr; r.h_pos0 = nullptr;
@@ -465,10 +464,10 @@ frz_status comm_finish_setup(frz_comm* c) {
             FRZ_CUDA_TRY(cudaHostGetDevicePointer(&dp, c->tables.ptr, 0));
             r.table_dev = reinterpret_cast<uint32_t*>(dp);
             const size_t entries = (size_t)c->world * kTableBins;
-            FRZ_CUDA_TRY(cudaMalloc(&r.d_gt, entries * sizeof(uint32_t)));
-            FRZ_CUDA_TRY(cudaMalloc(&r.d_pos0, entries * sizeof(unsigned long long)));
-            FRZ_CUDA_TRY(cudaMallocHost(&r.h_gt, entries * sizeof(uint32_t)));
-            FRZ_CUDA_TRY(cudaMallocHost(&r.h_pos0, entries * sizeof(unsigned long long)));
+            FRZ_CUDA_TRY(cudaMalloc(&r.d_pos0, entries * (sizeof(unsigned long long) + sizeof(uint32_t))));
+            r.d_gt = reinterpret_cast<uint32_t*>(r.d_pos0 + entries);
+            FRZ_CUDA_TRY(cudaMallocHost(&r.h_pos0, entries * (sizeof(unsigned long long) + sizeof(uint32_t))));
+            r.h_gt = reinterpret_cast<uint32_t*>(r.h_pos0 + entries);
         }
     }
     return FRZ_OK;
@@ -567,8 +566,15 @@ frz_status rank_step(frz_comm* c, RankCtx& r, frz_matcher* m, const frz_corpus* 
         // 1. my table → shared block (after the local pipeline on the main stream), everybody's tables ← shared block
         volatile uint32_t* tab_host = c->tables_host + ((size_t)parity * world) * kTableBins;
         if (by_score) {
-            k_publish_table<<<1, 256, 0, main>>>(r.table_dev + ((size_t)parity * world + r.rank) * kTableBins, d_table, bins,
-                                                 reinterpret_cast<volatile unsigned long long*>(r.ctrl_dev + kCtrlTable + parity * kMaxWorld + r.rank), seq);
+            // the table is final one kernel before the run (after the sort's scan, before its scatter): publish it from the side
+            // stream at that point, so the tables cross the host block — and the host prepares the exchange — while the scatter runs
+            cudaStream_t pub = main;
+            if (cudaEvent_t tev = frz_matcher_table_event(r.clone)) {
+                FRZ_CUDA_TRY(cudaStreamWaitEvent(r.side, tev, 0));
+                pub = r.side;
+            }
+            k_publish_table<<<1, 256, 0, pub>>>(r.table_dev + ((size_t)parity * world + r.rank) * kTableBins, d_table, bins,
+                                                reinterpret_cast<volatile unsigned long long*>(r.ctrl_dev + kCtrlTable + parity * kMaxWorld + r.rank), seq);
             FRZ_CUDA_TRY(cudaGetLastError());
             FRZ_TRY(wait_slots(c->ctrl_host + kCtrlTable + parity * kMaxWorld, world, seq, nullptr, "score table"));
         }
@@ -626,8 +632,8 @@ frz_status rank_step(frz_comm* c, RankCtx& r, frz_matcher* m, const frz_corpus* 
         }
         if (off != mine) return frz_fail(FRZ_ERR_NCCL, "slice exchange: the ranks' score tables are inconsistent (%llu != %llu)",
                                          (unsigned long long)off, (unsigned long long)mine);
-        FRZ_CUDA_TRY(cudaMemcpyAsync(r.d_gt, r.h_gt, (size_t)world * bins * sizeof(uint32_t), cudaMemcpyHostToDevice, main));
-        FRZ_CUDA_TRY(cudaMemcpyAsync(r.d_pos0, r.h_pos0, (size_t)world * bins * sizeof(unsigned long long), cudaMemcpyHostToDevice, main));
+        FRZ_CUDA_TRY(cudaMemcpyAsync(r.d_pos0, r.h_pos0, (size_t)world * kTableBins * (sizeof(unsigned long long) + sizeof(uint32_t)),
+                                     cudaMemcpyHostToDevice, main));   // pos0 and gt in one copy (fixed layout, <= 96 KB)
         FRZ_NCCL_TRY(nccl_api().GroupStart());
         for (int p2 = 0; p2 < world; p2++) {
             const uint64_t a = A[(size_t)r.rank * (world + 1) + p2], b = A[(size_t)r.rank * (world + 1) + p2 + 1];

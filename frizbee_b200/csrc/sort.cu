@@ -6,8 +6,8 @@
 // the whole score when the score bound allows it (one pass), else the reference's two 8-bit passes.
 //
 //   k_sort_hist     each "virtual warp" owns a contiguous segment and counts its digits in smem
-//   k_sort_scan_rows / k_sort_digit_base
-//                   per-digit exclusive prefix over the segments + descending exclusive prefix over digits
+//   k_sort_scan_rows per-digit exclusive prefix over the segments; its last block adds the descending exclusive prefix
+//                   over the digits (digit_base)
 //   k_sort_scatter  each virtual warp re-walks its segment IN ORDER, 32 elements at a time;
 //                   __match_any_sync gives the in-warp stable rank, a per-warp counter array the rest
 //
@@ -64,42 +64,54 @@ __global__ void __launch_bounds__(kSortWarps * 32) k_sort_hist(const FrzMatchDev
     for (int d = lane; d < bins; d += 32) hist[(size_t)d * kV + v] = cnt[d];
 }
 
-// hist[d][v] → exclusive prefix over v (in place), one warp per digit row; totals[d] = row sum
-__global__ void __launch_bounds__(256) k_sort_scan_rows(uint32_t* __restrict__ hist, int bins, uint32_t* __restrict__ totals) {
+// hist[d][v] → exclusive prefix over v (in place), one warp per digit row; totals[d] = row sum.  The LAST block to
+// finish (device counter, self-resetting) then turns the row totals into digit_base[d] = #elements with digit > d
+// (descending exclusive prefix over the digits) — one launch instead of two.
+__global__ void __launch_bounds__(256) k_sort_scan_rows(uint32_t* __restrict__ hist, int bins, uint32_t* __restrict__ totals,
+                                                        uint32_t* __restrict__ digit_base, unsigned int* __restrict__ done_counter) {
+    __shared__ bool is_last;
+    __shared__ uint32_t wsum[8];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int d = blockIdx.x * 8 + warp;
-    if (d >= bins) return;
-    constexpr int PER = kV / 32;  // contiguous entries per lane
-    uint4* row = reinterpret_cast<uint4*>(hist + (size_t)d * kV + lane * PER);
-    uint4 v[PER / 4];
-    uint32_t s = 0;
+    if (d < bins) {
+        constexpr int PER = kV / 32;  // contiguous entries per lane
+        uint4* row = reinterpret_cast<uint4*>(hist + (size_t)d * kV + lane * PER);
+        uint4 v[PER / 4];
+        uint32_t s = 0;
 #pragma unroll
-    for (int k = 0; k < PER / 4; k++) { v[k] = row[k]; s += v[k].x + v[k].y + v[k].z + v[k].w; }
-    uint32_t x = s;
-    for (int o = 1; o < 32; o <<= 1) {
-        uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
-        if (lane >= o) x += y;
-    }
-    uint32_t run = x - s;
+        for (int k = 0; k < PER / 4; k++) { v[k] = row[k]; s += v[k].x + v[k].y + v[k].z + v[k].w; }
+        uint32_t x = s;
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += y;
+        }
+        uint32_t run = x - s;
 #pragma unroll
-    for (int k = 0; k < PER / 4; k++) {
-        uint4 o4;
-        o4.x = run; run += v[k].x;
-        o4.y = run; run += v[k].y;
-        o4.z = run; run += v[k].z;
-        o4.w = run; run += v[k].w;
-        row[k] = o4;
+        for (int k = 0; k < PER / 4; k++) {
+            uint4 o4;
+            o4.x = run; run += v[k].x;
+            o4.y = run; run += v[k].y;
+            o4.z = run; run += v[k].z;
+            o4.w = run; run += v[k].w;
+            row[k] = o4;
+        }
+        if (lane == 31) totals[d] = x;
     }
-    if (lane == 31) totals[d] = x;
-}
-
-// digit_base[d] = #elements with digit > d (descending exclusive prefix over the row totals)
-__global__ void __launch_bounds__(1024) k_sort_digit_base(const uint32_t* __restrict__ totals, int bins, uint32_t* __restrict__ digit_base) {
-    __shared__ uint32_t wsum[32];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int t = threadIdx.x;
-    uint32_t v = t < bins ? totals[bins - 1 - t] : 0;
-    uint32_t x = v;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = atomicAdd(done_counter, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    // digit_base over bins <= 1024 entries: thread t owns the PERT digits t*PERT .. of the DESCENDING sequence
+    const int PERT = (bins + 255) / 256;
+    uint32_t loc[4] = {0, 0, 0, 0}, sum = 0;
+    for (int k = 0; k < PERT; k++) {
+        const int t = threadIdx.x * PERT + k;
+        loc[k] = t < bins ? __ldcg(&totals[bins - 1 - t]) : 0u;
+        sum += loc[k];
+    }
+    uint32_t x = sum;
     for (int o = 1; o < 32; o <<= 1) {
         uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
         if (lane >= o) x += y;
@@ -107,15 +119,21 @@ __global__ void __launch_bounds__(1024) k_sort_digit_base(const uint32_t* __rest
     if (lane == 31) wsum[warp] = x;
     __syncthreads();
     if (warp == 0) {
-        uint32_t w = wsum[lane], xs = w;
-        for (int o = 1; o < 32; o <<= 1) {
+        uint32_t w = lane < 8 ? wsum[lane] : 0u, xs = w;
+        for (int o = 1; o < 8; o <<= 1) {
             uint32_t y = __shfl_up_sync(0xffffffffu, xs, o);
             if (lane >= o) xs += y;
         }
-        wsum[lane] = xs - w;
+        if (lane < 8) wsum[lane] = xs - w;
     }
     __syncthreads();
-    if (t < bins) digit_base[bins - 1 - t] = wsum[warp] + x - v;
+    uint32_t run = wsum[warp] + x - sum;
+    for (int k = 0; k < PERT; k++) {
+        const int t = threadIdx.x * PERT + k;
+        if (t < bins) digit_base[bins - 1 - t] = run;
+        run += loc[k];
+    }
+    if (threadIdx.x == 0) *done_counter = 0;   // ready for the next pass
 }
 
 __global__ void __launch_bounds__(kSortWarps * 32) k_sort_scatter(const FrzMatchDev* __restrict__ in, FrzMatchDev* __restrict__ out,
@@ -165,11 +183,15 @@ frz_status frz_launch_sort_by_score_dev(const FrzMatchDev* d_in, FrzMatchDev* d_
         k_sort_hist<<<kSortBlocks, kSortWarps * 32, smem, stream>>>(src, n_ptr, shift, bins, ws.sort_hist);
         uint32_t* totals = ws.sort_hist + (size_t)kMaxBins * kV;
         uint32_t* digit_base = totals + kMaxBins;
-        k_sort_scan_rows<<<(bins + 7) / 8, 256, 0, stream>>>(ws.sort_hist, bins, totals);
-        k_sort_digit_base<<<1, 1024, 0, stream>>>(totals, bins, digit_base);
+        unsigned int* done_counter = reinterpret_cast<unsigned int*>(digit_base + kMaxBins);   // zeroed at allocation, self-resetting
+        k_sort_scan_rows<<<(bins + 7) / 8, 256, 0, stream>>>(ws.sort_hist, bins, totals, digit_base, done_counter);
+        if (ws.arm_table_ev && ws.table_ev) {   // digit_base is final: the multi-GPU layer publishes it while the scatter runs
+            FRZ_CUDA_TRY(cudaEventRecord(ws.table_ev, stream));
+            ws.table_ev_recorded = true;
+        }
         k_sort_scatter<<<kSortBlocks, kSortWarps * 32, smem, stream>>>(src, dst, n_ptr, shift, bins, ws.sort_hist, digit_base);
         FRZ_CUDA_TRY(cudaGetLastError());
-        if (st) st->launches += 4;
+        if (st) st->launches += 3;
         return FRZ_OK;
     };
     if (score_bound < 256) return pass(d_in, d_out, 0, 256);
@@ -180,7 +202,13 @@ frz_status frz_launch_sort_by_score_dev(const FrzMatchDev* d_in, FrzMatchDev* d_
     return pass(d_tmp, d_out, 8, 256);
 }
 
-size_t frz_sort_hist_words() { return (size_t)kMaxBins * kV + 2 * kMaxBins; }
+size_t frz_sort_hist_words() { return (size_t)kMaxBins * kV + 2 * kMaxBins + 4; }   // + the pass-completion counter (must start at zero)
+// allocates the sort scratch on the current device (the completion counter of k_sort_scan_rows starts at zero)
+frz_status frz_sort_hist_alloc(uint32_t** out) {
+    FRZ_CUDA_TRY(cudaMalloc(out, frz_sort_hist_words() * sizeof(uint32_t)));
+    FRZ_CUDA_TRY(cudaMemset(*out + (size_t)kMaxBins * kV + 2 * kMaxBins, 0, 4 * sizeof(uint32_t)));
+    return FRZ_OK;
+}
 
 // digit_base[d] of the LAST pass run on this workspace = number of elements whose digit is greater than d.  After a
 // single-pass sort (score bound < 1024) that is, per score s, how many matches of the run score higher than s — the table
