@@ -518,7 +518,11 @@ def run_ours(args):
                                                                   "all-gather of whole runs (FRZ_PARALLEL_EXCHANGE=allgather)"
                                                                   if os.environ.get("FRZ_PARALLEL_EXCHANGE") == "allgather" else
                                                                   "slice exchange: one grouped ncclSend/ncclRecv of exactly the ranges each rank copies out "
-                                                                  "(value); all-gather of whole runs (value_device_out)"),
+                                                                  "(value); all-gather of whole runs (value_device_out)"
+                                                                  if os.environ.get("FRZ_PARALLEL_EXCHANGE") == "slices" or not comm.p2p_active() else
+                                                                  "P2P placement: every GPU stores its matches at their merged positions in the peers' slice "
+                                                                  "buffers over NVLink (k_place, cudaIpc-mapped peer memory), no NCCL kernel (value); "
+                                                                  "all-gather of whole runs (value_device_out)"),
                                                      "emulated_reference_backend": info}),
                 "clocks": clocks,
                 "value_device_out": {"value": n * world * args.steps / (ms_dev / 1e3), "unit": "haystacks/s",

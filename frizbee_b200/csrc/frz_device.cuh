@@ -4,11 +4,14 @@
 //   * haystacks are taken in input order in TILES of FRZ_TILE = 1024;
 //   * inside a tile the haystacks are stably sorted by their 16-byte unit count
 //     (length bucketing) and laid out in GROUPS of 32 slots — one slot per warp lane;
-//   * a group is stored unit-interleaved (SoA): unit k of lanes 0..31 is one contiguous
-//     512-byte line, so the warp's k-th load is a single fully coalesced LDG.128 and every
-//     lane gets its bytes 16-byte aligned in registers (no alignment fix-ups, no shared memory);
-//   * a group holds `gunits` units per lane = the longest haystack of the group (zero padded);
-//     after bucketing almost every group is uniform, so padding is the 16-byte rounding only.
+//   * a group is stored SLOT-MAJOR: slot s of the group owns the `gunits` consecutive 16-byte units
+//     [abs_off + s * gunits, abs_off + (s + 1) * gunits) — one haystack is one contiguous, 16-byte aligned
+//     run of bytes, so the 48-64 bytes of a prefilter candidate or a Smith-Waterman window are ONE or TWO
+//     64-byte DRAM accesses.  (Rounds 1-2a interleaved the units of the 32 slots, which coalesces a warp that
+//     streams every haystack; since the signature index nothing streams them any more, and a scattered
+//     candidate cost four 64-byte accesses for its four units.)
+//   * `gunits` = the longest haystack of the group (zero padded); after bucketing almost every group is
+//     uniform, so padding is the 16-byte rounding only.
 //   Per slot: one u32 of metadata (len << 10 | index-within-tile).  Per group: 16 bytes.
 #pragma once
 #include <cuda_runtime.h>
@@ -27,8 +30,13 @@
 struct __align__(16) FrzGroupDesc {
     uint64_t abs_off;   // first unit of the group, in 16-byte units from the start of the packed data
     uint32_t unit_off;  // same, relative to the tile's data base
-    uint32_t gunits;    // units per lane in this group
+    uint32_t gunits;    // units per slot in this group
 };
+// first unit (index into the packed data, 16-byte units) of slot `s` (0..31) of a group; unit k of the slot follows at + k
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+inline uint64_t frz_slot_unit0(const FrzGroupDesc& gd, uint32_t s) { return gd.abs_off + (uint64_t)s * gd.gunits; }
 
 // Device view of a packed corpus.
 struct FrzCorpusView {
@@ -101,11 +109,11 @@ struct FrzPatternDev {
 // class, so the class test is valid for case-sensitive and case-insensitive needles alike); digits and the remaining
 // bytes share a few classes each (a coarser class only weakens the test, never invalidates it).
 #if defined(__CUDACC__)
-#define FRZ_HD __host__ __device__
+#define FRZ_DEV_HD __host__ __device__
 #else
-#define FRZ_HD
+#define FRZ_DEV_HD
 #endif
-FRZ_HD inline uint32_t frz_sig_bucket(uint32_t b) {
+FRZ_DEV_HD inline uint32_t frz_sig_bucket(uint32_t b) {
     const uint32_t t = (b | 0x20u) - 'a';
     if (t < 26u) return t;
     const uint32_t d = b - '0';
@@ -113,13 +121,13 @@ FRZ_HD inline uint32_t frz_sig_bucket(uint32_t b) {
     return 29u + (b + (b >> 5)) % 3u;
 }
 // one more haystack byte: p1 = classes seen, p2 = classes seen at least twice
-FRZ_HD inline void frz_sig_add(uint32_t& p1, uint32_t& p2, uint32_t byte) {
+FRZ_DEV_HD inline void frz_sig_add(uint32_t& p1, uint32_t& p2, uint32_t byte) {
     const uint32_t bit = 1u << frz_sig_bucket(byte);
     p2 |= p1 & bit;
     p1 |= bit;
 }
 // lower bound of the number of needle bytes without a partner in the haystack <= typo budget?
-FRZ_HD inline bool frz_sig_pass(uint32_t need1, uint32_t need2, int k, uint32_t p1, uint32_t p2) {
+FRZ_DEV_HD inline bool frz_sig_pass(uint32_t need1, uint32_t need2, int k, uint32_t p1, uint32_t p2) {
 #if defined(__CUDA_ARCH__)
     return __popc(need1 & ~p1) + __popc(need2 & ~p2) <= k;
 #else
@@ -178,19 +186,19 @@ struct FrzCounters {
 __device__ __forceinline__ uint32_t frz_lane() { return threadIdx.x & 31; }
 
 // Byte accessor of one packed haystack for the per-thread correctness paths (unicode.cu, k_match_indices):
-// `base` is the lane-resolved pointer to unit 0 of the slot (unit k at base + FRZ_GROUP * k), `shift` the window start.
+// `base` is the pointer to unit 0 of the slot (its units are contiguous), `shift` the window start.
 struct FrzPackedHay {
     const uint4* base;
     int shift;
     __device__ __forceinline__ uint8_t operator()(int i) const {
         const uint32_t j = (uint32_t)(i + shift);
-        return (uint8_t)((reinterpret_cast<const uint32_t*>(base + (size_t)(j >> 4) * FRZ_GROUP)[(j >> 2) & 3] >> ((j & 3) * 8)) & 0xff);
+        return (uint8_t)((reinterpret_cast<const uint32_t*>(base)[j >> 2] >> ((j & 3) * 8)) & 0xff);
     }
 };
 
 // address of unit k of (tile, slot)
 __device__ __forceinline__ const uint4* frz_unit_ptr(const FrzCorpusView& cv, uint32_t tile, uint32_t slot, uint32_t k) {
     const FrzGroupDesc gd = cv.groups[tile * FRZ_GROUPS_PER_TILE + (slot >> 5)];
-    return cv.data + gd.abs_off + (uint64_t)k * FRZ_GROUP + (slot & 31);
+    return cv.data + frz_slot_unit0(gd, slot & 31) + k;
 }
 #endif  // __CUDACC__

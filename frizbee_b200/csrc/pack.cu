@@ -1,4 +1,4 @@
-// pack.cu — Arrow-style (bytes, offsets) → tile-bucketed, unit-interleaved corpus (frz_device.cuh).
+// pack.cu — Arrow-style (bytes, offsets) → tile-bucketed, slot-major corpus (frz_device.cuh).
 //
 // Replaces the `&[S: AsRef<str>]` argument of Matcher::match_list (src/matcher/mod.rs:212):
 // the reference chases one fat pointer per haystack; here the list is packed once and stays
@@ -161,8 +161,9 @@ __global__ void __launch_bounds__(256) k_pack_copy(const uint8_t* __restrict__ b
         }
         // skip empty groups that start at the same offset: pick the one whose range contains u
         while (lo < FRZ_GROUPS_PER_TILE - 1 && goff[lo + 1] <= u) lo++;
-        uint32_t rel = u - goff[lo];
-        uint32_t k = rel >> 5, lane = rel & 31;
+        // slot-major group: unit `rel` of the group is unit k of slot `lane`, gunits units per slot
+        const uint32_t rel = u - goff[lo], gunits = (goff[lo + 1] - goff[lo]) >> 5;
+        const uint32_t lane = rel / gunits, k = rel - lane * gunits;
         uint32_t meta = slot_meta[(uint64_t)tile * FRZ_TILE + lo * FRZ_GROUP + lane];
         uint4 v = make_uint4(0, 0, 0, 0);
         if (meta != FRZ_INVALID_SLOT) {
@@ -206,9 +207,9 @@ __global__ void __launch_bounds__(256) k_pack_sig(const uint4* __restrict__ data
         const uint32_t meta = slot_meta[(uint64_t)g * FRZ_GROUP + lane];
         const uint32_t len = meta == FRZ_INVALID_SLOT ? 0u : meta >> FRZ_TILE_SHIFT;
         uint32_t p1 = 0, p2 = 0;
-        const uint4* gp = data + gd.abs_off + lane;
-        for (uint32_t k = 0; k < gd.gunits; k++) {   // warp-uniform trip count, coalesced 512-byte lines
-            const uint4 v = __ldg(gp + (size_t)k * FRZ_GROUP);
+        const uint4* gp = data + frz_slot_unit0(gd, lane);
+        for (uint32_t k = 0; k < gd.gunits; k++) {   // warp-uniform trip count; the warp walks one contiguous 32 * gunits * 16-byte block
+            const uint4 v = __ldg(gp + k);
             const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
             for (int j = 0; j < 16; j++) {
@@ -266,9 +267,9 @@ __global__ void __launch_bounds__(256) k_tail_bytes(const uint4* __restrict__ da
         const uint32_t slot = slot_of[(uint64_t)tile * FRZ_TILE + i];
         const uint32_t len = slot_meta[(uint64_t)tile * FRZ_TILE + slot] >> FRZ_TILE_SHIFT;
         const FrzGroupDesc gd = groups[tile * FRZ_GROUPS_PER_TILE + (slot >> 5)];
-        const uint8_t* base = reinterpret_cast<const uint8_t*>(data + gd.abs_off + (slot & 31));
+        const uint8_t* base = reinterpret_cast<const uint8_t*>(data + frz_slot_unit0(gd, slot & 31));
         uint8_t* dst = out_bytes + offsets[i];
-        for (uint32_t b = lane; b < len; b += 32) dst[b] = base[(size_t)(b >> 4) * FRZ_GROUP * FRZ_UNIT + (b & 15)];
+        for (uint32_t b = lane; b < len; b += 32) dst[b] = base[b];
     }
 }
 
@@ -285,7 +286,7 @@ __global__ void k_rebase_offsets(const OffT* __restrict__ in, uint64_t n_new, co
 //   pack_reserve   metadata arrays for tiles [0, n_tiles)
 //   pack_plan      bucket tiles [tile0, n_tiles) + running scan of the unit counts → total units (one small
 //                  D2H + wait: the packed size is needed to size the data buffer) → grow the data buffer
-//   pack_copy      tiles [t0, t1) from the staged bytes into the interleaved layout
+//   pack_copy      tiles [t0, t1) from the staged bytes into the slot-major layout
 namespace {
 
 frz_status pack_reserve(FrzCorpusStorage* out, uint32_t n_tiles, uint32_t keep_tiles, cudaStream_t stream) {

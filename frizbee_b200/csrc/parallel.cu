@@ -10,6 +10,13 @@
 //   returned Vec<Match>                                   every GPU copies ITS slice of the merged list to the host
 //                                                         buffer: the D2H runs over all PCIe links at once
 //
+// Host-out calls (the caller wants the list in host memory, the bench's `value`) do better than gather-then-merge:
+// every rank's per-score table crosses the shared host block, after which every rank KNOWS the merged position of each
+// of its matches, and ONE kernel (k_place) stores them straight into the peer GPUs' slice buffers over NVLink (P2P
+// stores into cudaIpc-mapped / peer-enabled memory) — the k-way merge and the exchange are the same pass, no NCCL
+// kernel, no receive buffer, no second scatter.  The all-gather form remains for device-out calls and as the fallback
+// (FRZ_PARALLEL_EXCHANGE=allgather|slices|p2p).
+//
 // The only per-step collective is that all-gather.  The match counts (the `Vec` lengths the k-merge reads) are
 // published by each GPU into a small pinned host block shared by all ranks — a 1-thread kernel right after the tile
 // scan, i.e. BEFORE the scoring kernels — and every rank's host thread polls the block; the same block carries the
@@ -29,6 +36,7 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <chrono>
 #include <condition_variable>
 #include <functional>
 #include <memory>
@@ -131,6 +139,7 @@ constexpr int kCtrlCount = 0;                   // (seq << 32) | match count of 
 constexpr int kCtrlDone = 2 * kMaxWorld;        // seq: the rank's slice of the merged list is in host memory
 constexpr int kCtrlBarrier = 4 * kMaxWorld;     // seq: frz_comm_barrier
 constexpr int kCtrlTable = 6 * kMaxWorld;       // seq: the rank's score table is in the shared table block
+constexpr int kCtrlPlaceErr = 8 * kMaxWorld;    // [rank]: seq of a k_place launch whose wait for the peers timed out
 constexpr int kTableBins = 1024;                // longest single-pass score table (sort.cu)
 
 __global__ void k_publish(volatile unsigned long long* slot, const unsigned long long* d_count, unsigned long long seq) {
@@ -174,6 +183,75 @@ __global__ void __launch_bounds__(256) k_slice_scatter(const FrzMatchDev* __rest
         const uint32_t s = bins > 1 ? min((uint32_t)m.score, (uint32_t)bins - 1) : 0u;
         out[p0q[s] + (a + i - gtq[s]) - meta.lo] = m;
     }
+}
+
+// ---- P2P placement: the exchange and the k-way merge in one pass over peer memory ------------------------------------
+// Rank q holds run q sorted; with every rank's score table it knows pos0[s] (merged position of the first element of its
+// score-s block) and gt[s] (how many of its elements score higher), so element i with score s belongs at merged position
+// pos0[s] + (i - gt[s]).  Position x lives in the slice of rank p with lo[p] <= x < lo[p + 1] (lo[p] = total * p / world): the
+// element is stored into rank p's slice buffer, which is this GPU's own memory for p == q and NVLink peer memory otherwise.
+// Consecutive elements of a score block land on consecutive addresses, so the stores coalesce.  The block that finishes
+// last raises this rank's flag in every peer's header (after a system-scope fence) and then waits for every peer's flag
+// in its OWN header: when the kernel ends, this rank's slice is complete and the stream-ordered device→host copy may run.
+constexpr size_t kPlaceHeaderBytes = 2048;
+struct PlaceHeader {
+    unsigned long long arrived[2][kMaxWorld];   // [step parity][source rank] = step sequence number
+    unsigned int blocks_done;                   // last-block detection of the owner's own k_place launch
+};
+static_assert(sizeof(PlaceHeader) <= kPlaceHeaderBytes, "place header");
+struct PlaceMeta {
+    unsigned char* peer[kMaxWorld];             // every rank's place buffer (header + slice elements) as mapped on THIS device
+    unsigned long long lo[kMaxWorld + 1];       // slice boundaries in the merged list
+    unsigned long long total;
+    int world, rank, bins, parity;
+};
+__global__ void __launch_bounds__(256) k_place(const FrzMatchDev* __restrict__ run, unsigned long long n, const __grid_constant__ PlaceMeta meta,
+                                               const unsigned long long* __restrict__ pos0, const uint32_t* __restrict__ gt,
+                                               unsigned long long seq, unsigned long long timeout_ns, volatile unsigned long long* err_slot) {
+    __shared__ unsigned long long lo_s[kMaxWorld + 1];
+    __shared__ FrzMatchDev* dst_s[kMaxWorld];
+    __shared__ int last_s;
+    for (int i = threadIdx.x; i <= meta.world; i += blockDim.x) lo_s[i] = meta.lo[i];
+    for (int i = threadIdx.x; i < meta.world; i += blockDim.x) dst_s[i] = reinterpret_cast<FrzMatchDev*>(meta.peer[i] + kPlaceHeaderBytes);
+    __syncthreads();
+    const int world = meta.world, bins = meta.bins;
+    const unsigned long long total = meta.total;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {
+        const FrzMatchDev m = run[i];
+        const uint32_t s = bins > 1 ? min((uint32_t)m.score, (uint32_t)bins - 1) : 0u;
+        const unsigned long long x = pos0[s] + (i - gt[s]);
+        int p = (int)min((unsigned long long)(world - 1), x * (unsigned long long)world / total);   // lo[p] = floor(total * p / world): at most one off
+        while (p > 0 && x < lo_s[p]) p--;
+        while (p + 1 < world && x >= lo_s[p + 1]) p++;
+        dst_s[p][x - lo_s[p]] = m;
+    }
+    __threadfence_system();   // this thread's peer stores are performed before the block signs off
+    __syncthreads();
+    PlaceHeader* mine = reinterpret_cast<PlaceHeader*>(meta.peer[meta.rank]);
+    if (threadIdx.x == 0) last_s = atomicAdd(&mine->blocks_done, 1u) == gridDim.x - 1 ? 1 : 0;
+    __syncthreads();
+    if (!last_s) return;
+    __threadfence_system();   // every block fenced its stores before its increment; order them before the flags below
+    if (threadIdx.x == 0) mine->blocks_done = 0;   // ready for the next launch
+    for (int q = threadIdx.x; q < world; q += blockDim.x) {
+        volatile unsigned long long* f = &reinterpret_cast<PlaceHeader*>(meta.peer[q])->arrived[meta.parity][meta.rank];
+        *f = seq;
+    }
+    __threadfence_system();
+    unsigned long long t0 = 0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (int q = threadIdx.x; q < world; q += blockDim.x) {
+        volatile unsigned long long* f = &mine->arrived[meta.parity][q];
+        uint32_t spins = 0;
+        while (*f != seq) {
+            if ((++spins & 0x3ff) == 0) {
+                unsigned long long t1;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                if (t1 - t0 > timeout_ns) { *err_slot = seq; break; }   // a peer never arrived: reported by the host, not a hang
+            }
+        }
+    }
+    __threadfence_system();   // acquire side: the peers' stores are visible to whatever follows this kernel on the stream
 }
 
 double now_s() {
@@ -227,6 +305,11 @@ struct RankCtx {
     unsigned long long* d_pos0 = nullptr;   //  the tables travel in ONE host→device copy)
     uint32_t* h_gt = nullptr;
     unsigned long long* h_pos0 = nullptr;
+    // P2P placement (host-out calls): my slice buffer (header + elements), exported to the peers; theirs mapped here
+    unsigned char* place_raw = nullptr;
+    uint64_t place_cap = 0;                 // elements
+    unsigned char* peer_raw[kMaxWorld] = {};
+    bool peer_ipc[kMaxWorld] = {};          // opened with cudaIpcOpenMemHandle (multi-process form)
     uint32_t* table_dev = nullptr;          // device-side address of the shared table block
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     bool ev_valid = false;
@@ -255,6 +338,14 @@ struct frz_comm {
     HostBlock tables;             // [parity][rank][kTableBins] uint32: every rank's score table of the current step
     volatile uint32_t* tables_host = nullptr;
     bool slice_exchange = true;   // FRZ_PARALLEL_EXCHANGE=allgather forces the all-gather form for host-out calls too
+    bool p2p_exchange = true;     // host-out calls place matches straight into the peers' slice buffers (k_place); cleared by
+                                  // FRZ_PARALLEL_EXCHANGE=slices|allgather, or when peer access / cudaIpc is unavailable
+    // local form: rendezvous of the worker threads (allgather_words)
+    std::mutex tb_mu;
+    std::condition_variable tb_cv;
+    int tb_count = 0;
+    uint64_t tb_gen = 0;
+    std::vector<uint64_t> tb_words;
     uint64_t seq = 0;             // step sequence number (identical on all ranks as long as they make the same calls)
     uint64_t barrier_seq = 0;
     uint64_t alloc_seq = 0;
@@ -281,6 +372,11 @@ void rank_release(RankCtx& r) {
     cudaSetDevice(r.device);
     if (r.clone) frz_matcher_destroy(r.clone);
     r.clone = nullptr;
+    for (int q = 0; q < kMaxWorld; q++) {
+        if (r.peer_ipc[q] && r.peer_raw[q]) cudaIpcCloseMemHandle(r.peer_raw[q]);
+        r.peer_raw[q] = nullptr; r.peer_ipc[q] = false;
+    }
+    cudaFree(r.place_raw); r.place_raw = nullptr; r.place_cap = 0;
     cudaFree(r.run); cudaFree(r.d_count); cudaFree(r.gathered); cudaFree(r.merged); cudaFree(r.recv); cudaFree(r.d_pos0);
     if (r.h_pos0) cudaFreeHost(r.h_pos0);
     r.run = nullptr; r.d_count = nullptr; r.gathered = nullptr; r.merged = nullptr; r.recv = nullptr; r.d_gt = nullptr; r.d_pos0 = nullptr;
@@ -327,6 +423,91 @@ frz_status exchange_words(frz_comm* c, const uint64_t* mine, int n_words, uint64
     }();
     cudaFree(d_in); cudaFree(d_out);
     return st;
+}
+
+// every rank contributes n_words (<= 16) host words and receives everybody's: NCCL in the multi-process form, a
+// rendezvous of the worker threads in the local form.  Collective; set-up paths only.
+constexpr int kGatherWords = 16;
+frz_status allgather_words(frz_comm* c, RankCtx& r, const uint64_t* mine, int n_words, uint64_t* all) {
+    if (!c->local_form) return exchange_words(c, mine, n_words, all);
+    if (c->world == 1) { memcpy(all, mine, n_words * sizeof(uint64_t)); return FRZ_OK; }
+    auto rendezvous = [&]() -> bool {
+        std::unique_lock<std::mutex> lk(c->tb_mu);
+        const uint64_t gen = c->tb_gen;
+        if (++c->tb_count == c->world) { c->tb_count = 0; c->tb_gen++; c->tb_cv.notify_all(); return true; }
+        return c->tb_cv.wait_for(lk, std::chrono::duration<double>(poll_timeout_s()), [&] { return c->tb_gen != gen; });
+    };
+    {
+        std::lock_guard<std::mutex> lk(c->tb_mu);
+        if (c->tb_words.size() < (size_t)c->world * kGatherWords) c->tb_words.resize((size_t)c->world * kGatherWords);
+        memcpy(&c->tb_words[(size_t)r.rank * kGatherWords], mine, n_words * sizeof(uint64_t));
+    }
+    if (!rendezvous()) return frz_fail(FRZ_ERR_NCCL, "a GPU worker did not reach the rendezvous within %.0f s", poll_timeout_s());
+    for (int q = 0; q < c->world; q++) memcpy(all + (size_t)q * n_words, &c->tb_words[(size_t)q * kGatherWords], n_words * sizeof(uint64_t));
+    if (!rendezvous()) return frz_fail(FRZ_ERR_NCCL, "a GPU worker did not reach the rendezvous within %.0f s", poll_timeout_s());
+    return FRZ_OK;
+}
+
+// Slice buffers of the P2P placement: every rank owns `header + cap elements`, every other rank maps it (local form: peer
+// access between the devices of one process; multi-process form: cudaIpc handles exchanged over the communicator).
+// Grow-only and COLLECTIVE: `need` is derived from the step's total match count, which every rank knows, so all ranks
+// take the same branch.  On any failure every rank clears c->p2p_exchange and the caller falls back to the NCCL forms.
+frz_status ensure_place_buffers(frz_comm* c, RankCtx& r, uint64_t need, bool* ready) {
+    *ready = false;
+    if (!c->p2p_exchange) return FRZ_OK;
+    if (r.place_cap >= need) { *ready = true; return FRZ_OK; }
+    const int world = c->world;
+    FRZ_CUDA_TRY(cudaDeviceSynchronize());   // nothing of mine may still read or write the old buffers
+    for (int q = 0; q < world; q++) {
+        if (r.peer_ipc[q] && r.peer_raw[q]) cudaIpcCloseMemHandle(r.peer_raw[q]);
+        r.peer_raw[q] = nullptr; r.peer_ipc[q] = false;
+    }
+    uint64_t w[10], all[kMaxWorld * 10];
+    memset(w, 0, sizeof w);
+    FRZ_TRY(allgather_words(c, r, w, 1, all));   // everybody has dropped its mappings: the owners may free
+    cudaFree(r.place_raw); r.place_raw = nullptr; r.place_cap = 0;
+    const uint64_t want = need + need / 4 + 4096;
+    bool ok = cudaMalloc(&r.place_raw, kPlaceHeaderBytes + want * sizeof(FrzMatchDev)) == cudaSuccess &&
+              cudaMemset(r.place_raw, 0, kPlaceHeaderBytes) == cudaSuccess;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t size");
+    if (ok && !c->local_form) {
+        cudaIpcMemHandle_t h;
+        ok = cudaIpcGetMemHandle(&h, r.place_raw) == cudaSuccess;
+        if (ok) memcpy(&w[2], &h, sizeof h);
+    }
+    if (!ok) cudaGetLastError();
+    w[0] = ok ? 1 : 0;
+    w[1] = (uint64_t)reinterpret_cast<uintptr_t>(r.place_raw);
+    FRZ_TRY(allgather_words(c, r, w, 10, all));
+    for (int q = 0; q < world; q++) ok = ok && all[(size_t)q * 10] == 1;
+    if (ok) {
+        for (int q = 0; q < world && ok; q++) {
+            if (q == r.rank) { r.peer_raw[q] = r.place_raw; continue; }
+            if (c->local_form) { r.peer_raw[q] = reinterpret_cast<unsigned char*>((uintptr_t)all[(size_t)q * 10 + 1]); continue; }
+            cudaIpcMemHandle_t h;
+            memcpy(&h, &all[(size_t)q * 10 + 2], sizeof h);
+            void* mapped = nullptr;
+            if (cudaIpcOpenMemHandle(&mapped, h, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess) {
+                r.peer_raw[q] = static_cast<unsigned char*>(mapped);
+                r.peer_ipc[q] = true;
+            } else { cudaGetLastError(); ok = false; }
+        }
+    }
+    uint64_t okw = ok ? 1 : 0;
+    FRZ_TRY(allgather_words(c, r, &okw, 1, all));   // also: nobody stores into a buffer before its owner has zeroed the header
+    for (int q = 0; q < world; q++) ok = ok && all[q] == 1;
+    if (!ok) {   // every rank sees the same verdict: P2P placement is off for this communicator from now on
+        for (int q = 0; q < world; q++) {
+            if (r.peer_ipc[q] && r.peer_raw[q]) cudaIpcCloseMemHandle(r.peer_raw[q]);
+            r.peer_raw[q] = nullptr; r.peer_ipc[q] = false;
+        }
+        cudaFree(r.place_raw); r.place_raw = nullptr; r.place_cap = 0;
+        if (&r == &c->ranks[0]) c->p2p_exchange = false;   // one writer; the other workers read it at their next call
+        return FRZ_OK;
+    }
+    r.place_cap = want;
+    *ready = true;
+    return FRZ_OK;
 }
 
 // ---- NUMA placement of the shared host buffer ------------------------------------------------------------------
@@ -450,7 +631,24 @@ frz_status comm_finish_setup(frz_comm* c) {
     { const char* e = getenv("FRZ_PARALLEL_FORCE_NCCL"); c->force_nccl = e && atoi(e) != 0; }
     FRZ_TRY(host_block_alloc(c, kCtrlBytes, &c->ctrl));
     c->ctrl_host = reinterpret_cast<volatile uint64_t*>(c->ctrl.ptr);
-    { const char* e = getenv("FRZ_PARALLEL_EXCHANGE"); c->slice_exchange = !(e && strcmp(e, "allgather") == 0); }
+    {   // host-out exchange: p2p (default) → slices (NCCL send/recv) → allgather
+        const char* e = getenv("FRZ_PARALLEL_EXCHANGE");
+        c->slice_exchange = !(e && strcmp(e, "allgather") == 0);
+        c->p2p_exchange = c->slice_exchange && !(e && strcmp(e, "slices") == 0) && c->world > 1;
+    }
+    if (c->p2p_exchange && c->local_form) {   // one process: plain peer access between every pair of devices
+        for (RankCtx& a : c->ranks) {
+            FRZ_TRY(set_device(a.device));
+            for (RankCtx& b : c->ranks) {
+                if (a.device == b.device) continue;
+                int can = 0;
+                if (cudaDeviceCanAccessPeer(&can, a.device, b.device) != cudaSuccess || !can) { cudaGetLastError(); c->p2p_exchange = false; continue; }
+                const cudaError_t pe = cudaDeviceEnablePeerAccess(b.device, 0);
+                if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) c->p2p_exchange = false;
+                cudaGetLastError();
+            }
+        }
+    }
     if (c->world > 1) {
         FRZ_TRY(host_block_alloc(c, (uint64_t)2 * c->world * kTableBins * sizeof(uint32_t), &c->tables));
         c->tables_host = reinterpret_cast<volatile uint32_t*>(c->tables.ptr);
@@ -544,6 +742,7 @@ frz_status rank_step(frz_comm* c, RankCtx& r, frz_matcher* m, const frz_corpus* 
     const bool collective = world > 1 || c->force_nccl;
     const FrzMatchDev* d_final = r.run;
     uint64_t d_final_first = 0;   // merged position of d_final[0] (non-zero in the slice form)
+    bool placed = false;          // the P2P placement ran this step
     // ---- host-out calls: SLICE EXCHANGE.  A rank copies only its slice [lo, hi) of the merged list to the host, and the
     // elements of run q that land in that slice are ONE contiguous range of run q (a run's elements keep their order in the
     // merged list).  With every rank's per-score table (published like the counts) each rank computes those ranges on the
@@ -563,6 +762,9 @@ frz_status rank_step(frz_comm* c, RankCtx& r, frz_matcher* m, const frz_corpus* 
             return frz_fail(FRZ_ERR_CAPACITY, "output capacity %llu < %llu matches", (unsigned long long)cap, (unsigned long long)total);
         }
         if (!out_host) return frz_fail(FRZ_ERR_INVALID_ARG, "null out");
+        // slice buffers of the P2P placement (collective, grow-only; falls back to the NCCL slice exchange when unavailable)
+        bool place_ready = false;
+        FRZ_TRY(ensure_place_buffers(c, r, total / (uint64_t)world + 2, &place_ready));
         // 1. my table → shared block (after the local pipeline on the main stream), everybody's tables ← shared block
         volatile uint32_t* tab_host = c->tables_host + ((size_t)parity * world) * kTableBins;
         if (by_score) {
@@ -582,6 +784,38 @@ frz_status rank_step(frz_comm* c, RankCtx& r, frz_matcher* m, const frz_corpus* 
         //    that precede q in merge order; A[q][p] = how many elements of run q lie before slice boundary lo_p
         uint64_t lo_p[kMaxWorld + 1];
         for (int p2 = 0; p2 <= world; p2++) lo_p[p2] = total * (uint64_t)p2 / (uint64_t)world;
+      if (place_ready) {
+        // ---- P2P PLACEMENT: only MY run's rows of pos0 / gt are needed; k_place stores every element of my run at its merged
+        // position inside the owning rank's slice buffer (peer memory over NVLink) and ends when all peers have done the same
+        auto gt_at = [&](int q, int sc) -> uint64_t { return by_score ? (uint64_t)tab_host[(size_t)q * kTableBins + sc] : 0ull; };
+        uint64_t* hp = reinterpret_cast<uint64_t*>(r.h_pos0);
+        uint32_t* hg = reinterpret_cast<uint32_t*>(hp + bins);
+        for (int sc = bins - 1; sc >= 0; sc--) {
+            uint64_t acc = 0;
+            for (int q = 0; q < world; q++) acc += gt_at(q, sc);
+            for (int k = 0; k < world; k++) {
+                const int q = reversed ? world - 1 - k : k;
+                const uint64_t gtq = gt_at(q, sc);
+                if (q == r.rank) { hp[sc] = acc; hg[sc] = (uint32_t)gtq; break; }
+                acc += (sc == 0 ? counts[q] : gt_at(q, sc - 1)) - gtq;
+            }
+        }
+        FRZ_CUDA_TRY(cudaMemcpyAsync(r.d_pos0, r.h_pos0, (size_t)bins * (sizeof(uint64_t) + sizeof(uint32_t)), cudaMemcpyHostToDevice, main));
+        PlaceMeta meta;
+        memset(&meta, 0, sizeof meta);
+        for (int q = 0; q < world; q++) meta.peer[q] = r.peer_raw[q];
+        for (int p2 = 0; p2 <= world; p2++) meta.lo[p2] = lo_p[p2];
+        meta.total = total; meta.world = world; meta.rank = r.rank; meta.bins = bins; meta.parity = parity;
+        const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((counts[r.rank] + 255) / 256, 148 * 4));
+        k_place<<<grid, 256, 0, main>>>(r.run, counts[r.rank], meta, reinterpret_cast<const unsigned long long*>(r.d_pos0),
+                                         reinterpret_cast<const uint32_t*>(r.d_pos0 + bins), seq,
+                                         (unsigned long long)(poll_timeout_s() * 1e9),
+                                         reinterpret_cast<volatile unsigned long long*>(r.ctrl_dev + kCtrlPlaceErr + r.rank));
+        FRZ_CUDA_TRY(cudaGetLastError());
+        placed = true;
+        d_final = reinterpret_cast<const FrzMatchDev*>(r.place_raw + kPlaceHeaderBytes);
+        d_final_first = lo_p[r.rank];
+      } else {
         static thread_local std::vector<uint64_t> A;
         A.assign((size_t)world * (world + 1), 0);
         auto gt_of = [&](int q, int sc) -> uint64_t { return by_score ? (uint64_t)tab_host[(size_t)q * kTableBins + sc] : 0ull; };
@@ -650,6 +884,7 @@ frz_status rank_step(frz_comm* c, RankCtx& r, frz_matcher* m, const frz_corpus* 
         }
         d_final = r.merged;
         d_final_first = lo;
+      }
     } else if (collective) {
         if (r.run_cap < stride) {
             // another rank's run is longer than this rank's whole shard (ceil partitioning leaves the last shard short, or
@@ -706,6 +941,9 @@ frz_status rank_step(frz_comm* c, RankCtx& r, frz_matcher* m, const frz_corpus* 
         FRZ_CUDA_TRY(cudaGetLastError());
     }
     FRZ_CUDA_TRY(cudaStreamSynchronize(main));
+    if (placed && __atomic_load_n(const_cast<const uint64_t*>(c->ctrl_host + kCtrlPlaceErr + r.rank), __ATOMIC_ACQUIRE) == seq)
+        return frz_fail(FRZ_ERR_NCCL, "rank %d: a peer GPU did not place its matches within %.0f s (peer failed or ranks made different calls)",
+                        r.rank, poll_timeout_s());
     if (want_host && !c->local_form && world > 1)
         FRZ_TRY(wait_slots(c->ctrl_host + kCtrlDone + parity * kMaxWorld, world, seq, nullptr, "copy-out flag"));
     return FRZ_OK;
@@ -804,6 +1042,8 @@ extern "C" frz_status frz_comm_create_rank(const uint8_t id[FRZ_UNIQUE_ID_BYTES]
 extern "C" int frz_comm_world(const frz_comm* c) { return c ? c->world : 0; }
 extern "C" int frz_comm_rank(const frz_comm* c) { return c ? c->rank : -1; }
 extern "C" int frz_comm_device(const frz_comm* c, int i) { return (c && i >= 0 && i < (int)c->ranks.size()) ? c->ranks[i].device : -1; }
+
+extern "C" int frz_comm_exchange_mode(const frz_comm* c) { return !c ? -1 : (c->p2p_exchange && c->world > 1) ? 2 : c->slice_exchange ? 1 : 0; }
 
 extern "C" frz_status frz_comm_host_alloc(frz_comm* c, uint64_t bytes, void** out) {
     if (!c || !out) return frz_fail(FRZ_ERR_INVALID_ARG, "null argument");

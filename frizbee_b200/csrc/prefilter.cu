@@ -36,10 +36,8 @@ constexpr int kThreads = 128;
 constexpr int kWarps = kThreads / 32;
 
 struct GlobalAcc {
-    const uint4* base;  // unit 0 of this slot; unit k at base + 32*k
-    __device__ __forceinline__ uint32_t word(uint32_t w) const {
-        return reinterpret_cast<const uint32_t*>(base + (size_t)(w >> 2) * FRZ_GROUP)[w & 3];
-    }
+    const uint4* base;  // unit 0 of this slot; its units (and so its bytes) are contiguous
+    __device__ __forceinline__ uint32_t word(uint32_t w) const { return reinterpret_cast<const uint32_t*>(base)[w]; }
 };
 
 
@@ -357,7 +355,7 @@ __device__ __forceinline__ int sw_class_of(int window, const FrzPatternDev& pat)
 // Exact window of one queued candidate (phase B) + survivor emission.  All 32 lanes of the warp call
 // this together (`active` lanes have an entry); emission uses warp-aggregated atomics.
 // One candidate as phase B sees it.  `units` is where the mask builders read the haystack's 16-byte units from (unit k at
-// units + 32 * k): the packed corpus itself, or this lane's column of a shared-memory stage filled by cp.async.
+// units + k): the packed corpus itself, or this lane's row of a shared-memory stage filled by cp.async.
 struct Cand {
     uint32_t tile, slot, li;   // li = index of the haystack inside its tile
     int len;
@@ -369,7 +367,7 @@ __device__ __forceinline__ Cand resolve_cand(const FrzCorpusView& cv, uint32_t t
     Cand c;
     c.tile = tile; c.slot = slot; c.len = len;
     const FrzGroupDesc gd = cv.groups[tile * FRZ_GROUPS_PER_TILE + (slot >> 5)];
-    c.base = cv.data + gd.abs_off + (slot & 31);
+    c.base = cv.data + frz_slot_unit0(gd, slot & 31);
     c.units = c.base;
     c.li = cv.slot_meta[(uint64_t)tile * FRZ_TILE + slot] & (FRZ_TILE - 1);
     return c;
@@ -445,7 +443,7 @@ __device__ __forceinline__ void process_candidate(const FrzCorpusView& cv, const
                 if (cls < FRZ_C_GENERIC) {
                     // window record (frz_device.cuh): everything the SW kernel needs, including the address of the
                     // window's first 16-byte unit, so that it never touches the group descriptors
-                    const uint64_t addr = (uint64_t)(ga.base - cv.data) + (uint64_t)(start >> 4) * FRZ_GROUP;
+                    const uint64_t addr = (uint64_t)(ga.base - cv.data) + (uint64_t)(start >> 4);
                     rec.slot_rank |= (uint32_t)(end - start) << 20 | (uint32_t)(end == len) << 28 | (uint32_t)(start == 0) << 29;
                     rec.start = (uint32_t)addr;
                     rec.end = (uint32_t)(addr >> 32) | ((uint32_t)start & 15u) << 8;
@@ -586,13 +584,13 @@ __global__ void __launch_bounds__(kScanThreads, TMA ? 6 : 10) k_sig_scan(const F
         count += __popc(ballot);
     };
     // one chunk = 128 consecutive slots (4 groups): lane L owns slots 4L .. 4L+3, all in group L / 8 of the chunk
-    auto process = [&](uint32_t idx, const uint4& meta, const uint4& sig0, const uint4& sig1, unsigned long long grp_off) {
+    auto process = [&](uint32_t idx, const uint4& meta, const uint4& sig0, const uint4& sig1, unsigned long long grp_off, uint32_t gunits) {
         const uint32_t slot_g = idx * 128 + lane * 4;                   // == tile << 10 | slot of this lane's first slot
-        const unsigned long long unit0 = grp_off + ((lane * 4) & 31);   // unit 0 of that slot (units of a group interleave by lane)
+        const unsigned long long unit0 = grp_off + (unsigned long long)((lane * 4) & 31) * gunits;   // unit 0 of that slot (slot-major group)
         test_slot(meta.x, sig0.x, sig0.y, slot_g, unit0);
-        test_slot(meta.y, sig0.z, sig0.w, slot_g + 1, unit0 + 1);
-        test_slot(meta.z, sig1.x, sig1.y, slot_g + 2, unit0 + 2);
-        test_slot(meta.w, sig1.z, sig1.w, slot_g + 3, unit0 + 3);
+        test_slot(meta.y, sig0.z, sig0.w, slot_g + 1, unit0 + gunits);
+        test_slot(meta.z, sig1.x, sig1.y, slot_g + 2, unit0 + 2 * gunits);
+        test_slot(meta.w, sig1.z, sig1.w, slot_g + 3, unit0 + 3 * gunits);
         __syncwarp();
         flush_commit();                       // the reservation made one chunk ago has arrived
         while (count >= 32) flush_request(32);
@@ -632,10 +630,11 @@ __global__ void __launch_bounds__(kScanThreads, TMA ? 6 : 10) k_sig_scan(const F
                 sig1 = reinterpret_cast<const uint4*>(stages[st].sig)[2 * lane + 1];
             }
             const unsigned long long grp_off = stages[st].desc[lane >> 3].abs_off;
+            const uint32_t grp_units = stages[st].desc[lane >> 3].gunits;
             __syncwarp();
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic reads of the stage before its async refill
             issue(st);
-            process(cur, meta, sig0, sig1, grp_off);
+            process(cur, meta, sig0, sig1, grp_off, grp_units);
             cur += n_warps;
             if (++st == kScanStages) { st = 0; parity ^= 1; }
         }
@@ -645,6 +644,7 @@ __global__ void __launch_bounds__(kScanThreads, TMA ? 6 : 10) k_sig_scan(const F
             uint4 meta;
             uint4 sig0, sig1;
             unsigned long long abs_off;   // lanes 0-3: first unit of the chunk's group `lane`
+            uint32_t gunits;              // lanes 0-3: units per slot of that group
             uint32_t idx;
         };
         uint32_t next = blockIdx.x * kScanWarps + warp;
@@ -653,6 +653,7 @@ __global__ void __launch_bounds__(kScanThreads, TMA ? 6 : 10) k_sig_scan(const F
             c.meta = make_uint4(FRZ_INVALID_SLOT, FRZ_INVALID_SLOT, FRZ_INVALID_SLOT, FRZ_INVALID_SLOT);
             c.sig0 = c.sig1 = make_uint4(0u, 0u, 0u, 0u);
             c.abs_off = 0;
+            c.gunits = 0;
             if (next < total_chunks) {
                 const uint64_t slot0 = (uint64_t)next * 128 + lane * 4;
                 c.meta = __ldg(reinterpret_cast<const uint4*>(cv.slot_meta + slot0));
@@ -661,7 +662,11 @@ __global__ void __launch_bounds__(kScanThreads, TMA ? 6 : 10) k_sig_scan(const F
                     c.sig0 = __ldg(sp);
                     c.sig1 = __ldg(sp + 1);
                 }
-                if (lane < 4) c.abs_off = cv.groups[next * 4 + lane].abs_off;   // four contiguous 16-byte descriptors, L2-resident
+                if (lane < 4) {   // four contiguous 16-byte descriptors, L2-resident
+                    const FrzGroupDesc gd = cv.groups[next * 4 + lane];
+                    c.abs_off = gd.abs_off;
+                    c.gunits = gd.gunits;
+                }
             }
             next += n_warps;
         };
@@ -670,10 +675,10 @@ __global__ void __launch_bounds__(kScanThreads, TMA ? 6 : 10) k_sig_scan(const F
         load_chunk(cb);
         for (;;) {
             if (ca.idx == 0xFFFFFFFFu) break;
-            process(ca.idx, ca.meta, ca.sig0, ca.sig1, __shfl_sync(0xffffffffu, ca.abs_off, lane >> 3));
+            process(ca.idx, ca.meta, ca.sig0, ca.sig1, __shfl_sync(0xffffffffu, ca.abs_off, lane >> 3), __shfl_sync(0xffffffffu, ca.gunits, lane >> 3));
             load_chunk(ca);
             if (cb.idx == 0xFFFFFFFFu) break;
-            process(cb.idx, cb.meta, cb.sig0, cb.sig1, __shfl_sync(0xffffffffu, cb.abs_off, lane >> 3));
+            process(cb.idx, cb.meta, cb.sig0, cb.sig1, __shfl_sync(0xffffffffu, cb.abs_off, lane >> 3), __shfl_sync(0xffffffffu, cb.gunits, lane >> 3));
             load_chunk(cb);
         }
     }
@@ -690,7 +695,8 @@ __global__ void __launch_bounds__(kScanThreads, TMA ? 6 : 10) k_sig_scan(const F
 constexpr int kWinThreads = 128;
 constexpr int kWinWarps = kWinThreads / 32;
 struct WinStage {
-    uint4 units[4][32];   // [unit][lane]: conflict-free 16-byte columns, same 32-unit stride as the packed corpus
+    uint4 units[32][5];   // [lane][unit]: the lane's four units contiguous like in the packed corpus; the fifth pads the row
+                          // to 80 bytes, which makes the warp's 16-byte accesses bank-conflict-free (rows of 64 would be 4-way)
 };
 struct WinSmem {
     uint2 occ[kMaxDistinct][32];
@@ -735,7 +741,7 @@ __global__ void __launch_bounds__(kWinThreads, 4) k_window(const FrzCorpusView c
             const uint4* base = cv.data + unit0_of(r);
 #pragma unroll
             for (int k = 0; k < 4; k++)
-                if (k < units) __pipeline_memcpy_async(&sm.stage[st].units[k][lane], base + (size_t)k * FRZ_GROUP, 16);
+                if (k < units) __pipeline_memcpy_async(&sm.stage[st].units[lane][k], base + k, 16);
         }
     };
     fetch_rec(0);
@@ -763,7 +769,7 @@ __global__ void __launch_bounds__(kWinThreads, 4) k_window(const FrzCorpusView c
         cd.li = rec0.y & (FRZ_TILE - 1);
         cd.len = (int)(rec0.y >> FRZ_TILE_SHIFT);
         cd.base = cv.data + unit0_of(rec0);
-        cd.units = staged ? &sm.stage[st].units[0][lane] : cd.base;
+        cd.units = staged ? &sm.stage[st].units[lane][0] : cd.base;
         Emit cur;
         process_candidate<MODE>(cv, pat, cid_s, sm.occ, cd, active, surv_bitmap, &cur, single);
         emit_commit(pending, lists, surv_cap, ctr);      // the previous item's list space has arrived by now
@@ -887,7 +893,7 @@ __global__ void __launch_bounds__(128) k_match_indices(const FrzCorpusView cv, c
         const uint32_t meta = cv.slot_meta[(uint64_t)tile * FRZ_TILE + slot];
         const int len = (int)(meta >> FRZ_TILE_SHIFT);
         const FrzGroupDesc gd = cv.groups[tile * FRZ_GROUPS_PER_TILE + (slot >> 5)];
-        const GlobalAcc ga{cv.data + gd.abs_off + (slot & 31)};
+        const GlobalAcc ga{cv.data + frz_slot_unit0(gd, slot & 31)};
         const FrzPackedHay hay{ga.base, 0};
         uint32_t* my_out = out_idx + j * (unsigned long long)stride;
         uint32_t score = 0;
@@ -1004,8 +1010,8 @@ frz_status frz_launch_prefilter(const FrzCorpusView& cv, const FrzPatternDev& pa
             if (knob < 0) { const char* e = getenv("FRZ_PF_BLOCKS"); knob = e ? atoi(e) : 0; }                           \
             /* measured on B200 (profiles/r02f_variants.txt): 4 resident blocks per SM beat 5 and 3 (0.141 / 0.157 / 0.143 ms */ \
             /* for the stage) — the scattered unit fetches of more warps thrash each other in L1 / the LSU queues */       \
-            if (bps > 4) bps = 4;                                                                                        \
-            if (knob > 0 && knob < bps) bps = knob;                                                                      \
+            if (knob > 0) bps = std::min(bps, knob);                                                                     \
+            else if (bps > 4) bps = 4;                                                                                   \
             if (bps < 1) bps = 1;                                                                                        \
         }                                                                                                                \
         k_window<MODE><<<sms * bps, kWinThreads, smem, stream>>>(cv, pat, cand, ws.cand_cap, ws.lists(), ws.survivor_cap, \

@@ -58,15 +58,15 @@ FRZ_PF_FN uint32_t zero_flags(uint32_t x) {
 }
 
 // occ[d][lane] = occurrence mask of distinct class d over bytes [64*blk, 64*blk+64) of the lane's haystack.
-// `base` points at unit 0 of the lane's haystack, unit k at base + 32*k — in the packed corpus, or in the lane's column of
-// the shared-memory stage k_window fills with cp.async (same stride).  `units` = ceil(len / 16) bounds the reads.
+// `base` points at unit 0 of the lane's haystack, unit k at base + k — in the packed corpus, or in the lane's row of
+// the shared-memory stage k_window fills with cp.async (same layout).  `units` = ceil(len / 16) bounds the reads.
 FRZ_PF_FN void build_block_masks(const uint4* base, int units, int blk, const FrzPatternDev& pat,
                                                   uint2 (*occ)[32], uint32_t lane) {
     uint32_t w[16];
 #pragma unroll
     for (int k = 0; k < 4; k++) {
         uint4 v = make_uint4(0u, 0u, 0u, 0u);
-        if (4 * blk + k < units) v = base[(size_t)(4 * blk + k) * FRZ_GROUP];   // generic load: packed corpus or a shared-memory stage
+        if (4 * blk + k < units) v = base[4 * blk + k];   // generic load: packed corpus or a shared-memory stage
         w[4 * k] = v.x; w[4 * k + 1] = v.y; w[4 * k + 2] = v.z; w[4 * k + 3] = v.w;
     }
     for (int d = 0; d < pat.n_distinct; d++) {

@@ -118,7 +118,7 @@ __device__ __forceinline__ uint32_t score_survivor(const FrzCorpusView& cv, cons
 #pragma unroll
     for (int k = 0; k < NU; k++) {
         u[k] = make_uint4(0, 0, 0, 0);
-        if (k < nu) u[k] = __ldg(base + (size_t)k * FRZ_GROUP);
+        if (k < nu) u[k] = __ldg(base + k);
     }
     return score_window<LANES, COLS, WRAP8, CC>(pat, rec, wr, u, rv, ctr, index_offset, reversed, out, sw_smem);
 }
@@ -213,7 +213,7 @@ __global__ void __launch_bounds__(kSwThreads, kSw64MinBlocks) k_sw64(const FrzCo
             const uint4* base = cv.data + wr.addr;
 #pragma unroll
             for (int k = 0; k < kSw64Units; k++)
-                if (k < nu) __pipeline_memcpy_async(&stage.units[k][threadIdx.x], base + (size_t)k * FRZ_GROUP, 16);
+                if (k < nu) __pipeline_memcpy_async(&stage.units[k][threadIdx.x], base + k, 16);
         }
         __pipeline_commit();
     };
@@ -271,7 +271,7 @@ __global__ void __launch_bounds__(kSwThreads, kSw64MinBlocks) k_sw64(const FrzCo
 constexpr int kGenCols = FRZ_SW_MAX_WINDOW + 64;
 
 __device__ __forceinline__ uint32_t hay_byte(const uint4* base, uint32_t i) {
-    return (reinterpret_cast<const uint32_t*>(base + (size_t)(i >> 4) * FRZ_GROUP)[(i >> 2) & 3] >> ((i & 3) * 8)) & 0xff;
+    return (reinterpret_cast<const uint32_t*>(base)[i >> 2] >> ((i & 3) * 8)) & 0xff;
 }
 
 __device__ int greedy_score(const uint4* base, uint32_t start, int W, const FrzPatternDev& p, bool include_prefix) {

@@ -44,7 +44,7 @@ __global__ void __launch_bounds__(kUThreads) k_unicode(const FrzCorpusView cv, c
         const int len = (int)(meta >> FRZ_TILE_SHIFT);
         const uint32_t li = meta & (FRZ_TILE - 1);
         const FrzGroupDesc gd = cv.groups[tile * FRZ_GROUPS_PER_TILE + (slot >> 5)];
-        const PackedHay hay{cv.data + gd.abs_off + (slot & 31), 0};
+        const PackedHay hay{cv.data + frz_slot_unit0(gd, slot & 31), 0};
         bool ok = false, exact = false;
         uint32_t score = 0;
         if (pat.matching != FRZ_MATCHING_FUZZY) {

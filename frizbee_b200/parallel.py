@@ -42,6 +42,8 @@ def _bind(L):
     L.frz_comm_host_alloc.argtypes = [vp, u64, C.POINTER(vp)]
     L.frz_comm_host_free.argtypes = [vp, vp]
     L.frz_comm_barrier.argtypes = [vp]
+    L.frz_comm_exchange_mode.argtypes = [vp]
+    L.frz_comm_exchange_mode.restype = C.c_int
     L.frz_corpus_create_sharded.argtypes = [vp, vp, C.c_int, u64, vp, C.POINTER(vp)]
     L.frz_match_list_parallel.argtypes = [vp, C.POINTER(vp), C.c_int, vp, vp, u64, C.POINTER(u64)]
     L.frz_match_list_parallel_rank.argtypes = [vp, vp, u32, vp, vp, u64, C.POINTER(u64), C.POINTER(vp)]
@@ -112,6 +114,13 @@ class Comm:
 
     def barrier(self):
         _check(plib().frz_comm_barrier(self._h))
+
+    def exchange_mode(self) -> int:
+        """2 = P2P placement, 1 = NCCL slice exchange, 0 = all-gather (frz_comm_exchange_mode)."""
+        return int(plib().frz_comm_exchange_mode(self._h))
+
+    def p2p_active(self) -> bool:
+        return self.exchange_mode() == 2
 
     def device(self, local_index: int = 0) -> int:
         return plib().frz_comm_device(self._h, local_index)
@@ -211,6 +220,49 @@ def merge_runs_host(runs: List[np.ndarray], sort: SortStrategy) -> np.ndarray:
         return cat
     order = np.argsort(-cat["score"].astype(np.int64), kind="stable")
     return cat[order]
+
+
+def placement_host(runs: List[np.ndarray], sort: SortStrategy, bins: int = 1024) -> List[np.ndarray]:
+    """Host specification of the P2P placement (csrc/parallel.cu: k_place + the position arithmetic of rank_step): from every
+    run's per-score table gt[q][s] (how many elements of run q score higher than s) each rank derives, for ITS run only,
+    pos0[s] — the merged position of the first element of its score-s block = everything scoring higher in any run + the
+    score-s blocks of the runs that precede it in merge order — and stores element i (score s) at merged position
+    pos0[s] + (i - gt[s]), i.e. into slice p = the rank with lo[p] <= position < lo[p + 1], lo[p] = total * p // world.
+    Returns the world slices; their concatenation is the k-way merge (tests/test_parallel_gloo.py)."""
+    world = len(runs)
+    counts = [len(r) for r in runs]
+    total = sum(counts)
+    lo = [total * p // world for p in range(world + 1)]
+    slices = [np.zeros(lo[p + 1] - lo[p], dtype=MATCH_DTYPE) for p in range(world)]
+    if total == 0:
+        return slices
+    by_score = sort.is_by_score()
+    nb = bins if by_score else 1
+    gt = np.zeros((world, nb), dtype=np.int64)
+    if by_score:
+        for q, r in enumerate(runs):
+            sc = np.minimum(r["score"].astype(np.int64), nb - 1)
+            hist = np.bincount(sc, minlength=nb)
+            gt[q] = hist[::-1].cumsum()[::-1] - hist          # strictly higher
+    ge = np.concatenate([np.asarray(counts, dtype=np.int64)[:, None], gt[:, :-1]], axis=1)   # ge[q][s] = count(score >= s)
+    order = list(range(world))[::-1] if sort.is_reversed() else list(range(world))
+    for me, r in enumerate(runs):
+        pos0 = np.zeros(nb, dtype=np.int64)
+        for s in range(nb):
+            acc = int(gt[:, s].sum())
+            for q in order:
+                if q == me:
+                    break
+                acc += int(ge[q][s] - gt[q][s])
+            pos0[s] = acc
+        i = np.arange(len(r), dtype=np.int64)
+        s_of = np.minimum(r["score"].astype(np.int64), nb - 1) if by_score else np.zeros(len(r), dtype=np.int64)
+        x = pos0[s_of] + (i - gt[me][s_of])
+        p_of = np.searchsorted(np.asarray(lo[1:], dtype=np.int64), x, side="right")
+        for p in range(world):
+            sel = p_of == p
+            slices[p][x[sel] - lo[p]] = r[sel]
+    return slices
 
 
 def all_gather_runs(run, count: int, group=None):

@@ -1,6 +1,6 @@
 // Host build of frizbee_b200/csrc/prefilter_masks.cuh — the occurrence-mask prefilter windows (0 and 1 typo) the GPU
 // kernel runs per warp lane — for tests/test_kernel_logic_cpu.py.  One emulated lane; the haystack is laid out at the
-// packed corpus' unit stride.
+// packed corpus' layout (a haystack's 16-byte units are contiguous).
 #include <stdint.h>
 #include <string.h>
 
@@ -17,11 +17,11 @@ int h_masks_window(const void* pat_bytes, const uint8_t* hay, int len, int mode,
     memcpy(&pat, pat_bytes, sizeof pat);
     if (pat.n_distinct <= 0) return -1;
     const int units = (len + 15) / 16;
-    std::vector<uint4> data((size_t)(units + 8) * FRZ_GROUP, make_uint4(0, 0, 0, 0));
+    std::vector<uint4> data((size_t)units + 8, make_uint4(0, 0, 0, 0));
     for (int k = 0; k < units; k++) {
         uint8_t b[16] = {0};
         for (int i = 0; i < 16 && 16 * k + i < len; i++) b[i] = hay[16 * k + i];
-        memcpy(&data[(size_t)k * FRZ_GROUP], b, 16);
+        memcpy(&data[(size_t)k], b, 16);
     }
     static uint2 occ[kMaxDistinct][32];
     bool ok;

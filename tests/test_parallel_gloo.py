@@ -88,3 +88,33 @@ def test_shard_bounds_and_host_merge():
         if sort.is_by_score():
             want = O.radix_sort_matches(want)
         assert np.array_equal(parallel.merge_runs_host(runs, sort), want)
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_p2p_placement_arithmetic_equals_the_k_way_merge(world):
+    """The position arithmetic of the P2P placement (csrc/parallel.cu: k_place, restated in parallel.placement_host): every rank
+    stores its own matches straight at their merged positions inside the owning rank's slice; the concatenated slices are
+    the k-way merge for all four sort strategies, skewed runs, empty runs and clamped score bins."""
+    rng = np.random.default_rng(world)
+    for n, hi_score in ((1000, 40), (37, 3), (world - 1, 5), (0, 5), (5000, 600)):
+        full = np.zeros(n, dtype=O.MATCH_DTYPE)
+        full["index"] = np.arange(n)
+        full["score"] = rng.integers(0, hi_score, n)
+        full["exact"] = rng.integers(0, 2, n)
+        for sort in SortStrategy:
+            runs = []
+            for lo, hi in parallel.shard_bounds(n, world):
+                r = full[lo:hi]
+                if lo < hi and rng.random() < 0.3:       # a skewed shard: drop most of its matches
+                    r = r[rng.random(len(r)) < 0.1]
+                if sort.is_reversed():
+                    r = r[::-1]
+                if sort.is_by_score():
+                    r = O.radix_sort_matches(r)
+                runs.append(np.ascontiguousarray(r))
+            want = parallel.merge_runs_host(runs, sort)
+            for bins in (1024, 512):                     # 512 < 600: the top bin is shared by several scores
+                if bins <= hi_score and sort.is_by_score():
+                    continue                             # (the device path only uses a table that separates all scores)
+                got = np.concatenate(parallel.placement_host(runs, sort, bins=bins))
+                assert np.array_equal(got, want), (world, n, sort, bins)
