@@ -471,8 +471,11 @@ frz_status compile_pattern(const OwnedPattern& src, const frz_config& mcfg, bool
         d.typo_mode = FRZ_T_LITERAL;
         d.min_hay_len = 0;
         {   // a literal match holds every needle byte (either case): signature test with no typo budget
+            // (unicode path: only the needle's ASCII scalars count — a non-ASCII scalar and its case flip may differ in
+            // every byte, an ASCII scalar is matched by the same letter in either case, which the classes fold)
             uint32_t cnt[32] = {0};
-            for (size_t i = 0; i < n; i++) cnt[frz_sig_bucket(d.c[i])]++;
+            for (size_t i = 0; i < n; i++)
+                if (!needs_unicode || d.c[i] < 0x80) cnt[frz_sig_bucket(d.c[i])]++;
             for (int b2 = 0; b2 < 32; b2++) {
                 if (cnt[b2] >= 1) d.sig_need1 |= 1u << b2;
                 if (cnt[b2] >= 2) d.sig_need2 |= 1u << b2;
@@ -558,8 +561,11 @@ frz_status compile_pattern(const OwnedPattern& src, const frz_config& mcfg, bool
         // k typos holds a common subsequence of n - k needle bytes (the k >= 1 trackers never accept what LCS rejects,
         // DESIGN.md §2), so per byte class at most k needle bytes in total may lack a partner:
         //     sum_c max(0, m_c - cnt_c) <= k     >=     popc(need1 & ~occurs) + popc(need2 & ~occurs_twice)
+        // The unicode trackers are the same trackers over needle SCALARS; there only the ASCII scalars are counted (see the
+        // literal branch above), which keeps the sum a lower bound.
         uint32_t cnt[32] = {0};
-        for (size_t i = 0; i < n; i++) cnt[frz_sig_bucket(d.c[i])]++;
+        for (size_t i = 0; i < n; i++)
+            if (!needs_unicode || d.c[i] < 0x80) cnt[frz_sig_bucket(d.c[i])]++;
         d.sig_need1 = d.sig_need2 = 0;
         for (int b2 = 0; b2 < 32; b2++) {
             if (cnt[b2] >= 1) d.sig_need1 |= 1u << b2;

@@ -960,21 +960,16 @@ frz_status frz_launch_prefilter_list(const FrzCorpusView& cv, const FrzPatternDe
     return FRZ_OK;
 }
 
-// Stage 1 of match_list over the whole corpus: k_sig_scan (streaming signature test → candidate records) and
-// k_window (exact windows of the candidates → survivor records + per-tile survivor bitmap).
-frz_status frz_launch_prefilter(const FrzCorpusView& cv, const FrzPatternDev& pat, FrzWorkspace& ws, cudaStream_t stream,
-                                FrzLaunchStats* st) {
+// Stage 1a alone: the streaming signature scan over the whole corpus → candidate records in ws.cand_list, their number in
+// ws.counters->cand_count.  Shared by the byte path (k_window consumes the records) and the unicode path (k_unicode does).
+frz_status frz_launch_sig_scan(const FrzCorpusView& cv, const FrzPatternDev& pat, FrzWorkspace& ws, cudaStream_t stream, FrzLaunchStats* st) {
     if (cv.n_tiles == 0) return FRZ_OK;
     int sms = 0, dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (sms <= 0) sms = 148;
-    FRZ_CUDA_TRY(cudaMemsetAsync(ws.surv_bitmap, 0, (size_t)cv.n_tiles * 32 * sizeof(uint32_t), stream));
-    static int single_knob = -1;   // A/B knob: FRZ_PF_SINGLE=0 keeps the general (multi-chunk) mask forms
-    if (single_knob < 0) { const char* e = getenv("FRZ_PF_SINGLE"); single_knob = e ? atoi(e) : 1; }
-    const uint32_t pf_flags = single_knob ? 1u : 0u;
     CandRec* cand = reinterpret_cast<CandRec*>(ws.cand_list);
-    {   // 1a: persistent warps, as many blocks as fit
+    {   // persistent warps, as many blocks as fit
         static int tma_knob = -1;   // A/B knob: FRZ_PF_TMA=0 selects the register-prefetch form of the phase-A loads
         if (tma_knob < 0) { const char* e = getenv("FRZ_PF_TMA"); tma_knob = e ? atoi(e) : 1; }
         const uint32_t total_chunks = cv.n_tiles * (FRZ_TILE / 128);
@@ -998,6 +993,26 @@ frz_status frz_launch_prefilter(const FrzCorpusView& cv, const FrzPatternDev& pa
         else FRZ_SCAN_LAUNCH(false, ring_bytes);
 #undef FRZ_SCAN_LAUNCH
     }
+    FRZ_CUDA_TRY(cudaGetLastError());
+    if (st) st->launches++;
+    return FRZ_OK;
+}
+
+// Stage 1 of match_list over the whole corpus: k_sig_scan (streaming signature test → candidate records) and
+// k_window (exact windows of the candidates → survivor records + per-tile survivor bitmap).
+frz_status frz_launch_prefilter(const FrzCorpusView& cv, const FrzPatternDev& pat, FrzWorkspace& ws, cudaStream_t stream,
+                                FrzLaunchStats* st) {
+    if (cv.n_tiles == 0) return FRZ_OK;
+    int sms = 0, dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+    FRZ_CUDA_TRY(cudaMemsetAsync(ws.surv_bitmap, 0, (size_t)cv.n_tiles * 32 * sizeof(uint32_t), stream));
+    static int single_knob = -1;   // A/B knob: FRZ_PF_SINGLE=0 keeps the general (multi-chunk) mask forms
+    if (single_knob < 0) { const char* e = getenv("FRZ_PF_SINGLE"); single_knob = e ? atoi(e) : 1; }
+    const uint32_t pf_flags = single_knob ? 1u : 0u;
+    CandRec* cand = reinterpret_cast<CandRec*>(ws.cand_list);
+    FRZ_TRY(frz_launch_sig_scan(cv, pat, ws, stream, st));   // 1a
     const size_t smem = sizeof(WinSmem) * kWinWarps;
 #define FRZ_PF_LAUNCH(MODE)                                                                                              \
     do {                                                                                                                 \
@@ -1008,10 +1023,11 @@ frz_status frz_launch_prefilter(const FrzCorpusView& cv, const FrzPatternDev& pa
             FRZ_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_window<MODE>, kWinThreads, smem));        \
             static int knob = -1;   /* experiment knob: FRZ_PF_BLOCKS caps the resident blocks per SM */                 \
             if (knob < 0) { const char* e = getenv("FRZ_PF_BLOCKS"); knob = e ? atoi(e) : 0; }                           \
-            /* measured on B200 (profiles/r02f_variants.txt): 4 resident blocks per SM beat 5 and 3 (0.141 / 0.157 / 0.143 ms */ \
-            /* for the stage) — the scattered unit fetches of more warps thrash each other in L1 / the LSU queues */       \
+            /* measured on B200, slot-major layout (profiles/r02j_variants.txt): 5 / 4 / 3 resident blocks per SM give */ \
+            /* 0.1302 / 0.1328 / 0.1429 ms for the stage (with the interleaved layout 4 beat 5: each candidate touched */  \
+            /* four lines and more warps thrashed L1, profiles/r02f_variants.txt) */                                      \
             if (knob > 0) bps = std::min(bps, knob);                                                                     \
-            else if (bps > 4) bps = 4;                                                                                   \
+            else if (bps > 5) bps = 5;                                                                                   \
             if (bps < 1) bps = 1;                                                                                        \
         }                                                                                                                \
         k_window<MODE><<<sms * bps, kWinThreads, smem, stream>>>(cv, pat, cand, ws.cand_cap, ws.lists(), ws.survivor_cap, \
@@ -1028,7 +1044,7 @@ frz_status frz_launch_prefilter(const FrzCorpusView& cv, const FrzPatternDev& pa
     }
 #undef FRZ_PF_LAUNCH
     FRZ_CUDA_TRY(cudaGetLastError());
-    if (st) st->launches += 2;
+    if (st) st->launches++;
     return FRZ_OK;
 }
 

@@ -259,6 +259,57 @@ def test_signature_test_is_a_necessary_condition(H, PF, lanes):
 
 
 @pytest.mark.parametrize("lanes", [16, 32, 64])
+def test_signature_test_is_a_necessary_condition_for_unicode_needles(H, PF, lanes):
+    """The unicode-needle path runs the same signature scan before k_unicode, with only the needle's ASCII scalars counted
+    (host.cu: compile_pattern).  Necessary-condition check against the oracle's unicode prefilters (all typo budgets,
+    both case modes) and unicode literal modes, on alphabets that mix ASCII letters in both cases with multi-byte scalars
+    whose case flips differ in every byte."""
+    from frizbee_b200.types import Matching, Pattern, UnicodeMatching
+    rng = random.Random(9100 + lanes)
+    F.lib().frz_matcher_debug_pattern.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]
+    PF.h_sig_pass.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
+    pools = ["aéAÉ_다", "abé✓😀", "éÉeE-/x", "нНaя_Я", "ab", "aAbBkK", "sSßxX09"]
+    accepted = rejected_by_sig = 0
+    for trial in range(700):
+        pool = rng.choice(pools)
+        needle = "".join(rng.choice(pool) for _ in range(rng.randint(1, 7)))
+        k = rng.choice([0, 0, 1, 1, 2, 3, 5])
+        cs = rng.random() < 0.3
+        cfg = Config(max_typos=k, emulate_lanes=lanes, unicode=UnicodeMatching.Always,
+                     casing=CaseMatching.Respect if cs else CaseMatching.Ignore)
+        pat, info = device_pattern(H, needle, cfg)
+        for _ in range(16):
+            hay = "".join(rng.choice(pool + rng.choice(["", "xyz", "XY9", "ÉЯ"])) for _ in range(rng.choice([0, 1, 2, 5, 9, 17, 31, 40, 70])))
+            hb = hay.encode()
+            ok = O.prefilter_unicode(needle, hay, k, lanes, cs)[0]
+            sig = PF.h_sig_pass(pat, hb, len(hb))
+            if ok:
+                assert sig == 1, (needle, hay, k, lanes, cs)
+                accepted += 1
+            elif not sig:
+                rejected_by_sig += 1
+    assert accepted > 1200 and rejected_by_sig > 800, (accepted, rejected_by_sig)
+    lit_ok = 0
+    for trial in range(300):
+        pool = rng.choice(pools)
+        needle = "".join(rng.choice(pool) for _ in range(rng.randint(1, 5)))
+        cs = rng.random() < 0.3
+        mode = rng.choice([Matching.Exact, Matching.Prefix, Matching.Suffix, Matching.Substring])
+        cfg = Config(matching=mode, unicode=UnicodeMatching.Always, casing=CaseMatching.Respect if cs else CaseMatching.Ignore)
+        pat, _ = device_pattern(H, needle, cfg)
+        for _ in range(10):
+            pre = "".join(rng.choice(pool) for _ in range(rng.randint(0, 4)))
+            post = "".join(rng.choice(pool) for _ in range(rng.randint(0, 4)))
+            mid = "".join((ch.swapcase() if (not cs and rng.random() < 0.5 and len(ch.swapcase().encode()) == len(ch.encode())) else ch) for ch in needle)
+            hay = {Matching.Exact: mid, Matching.Prefix: mid + post, Matching.Suffix: pre + mid, Matching.Substring: pre + mid + post}[mode]
+            if O.match_list([Pattern(needle, matching=mode)], [hay], cfg):
+                hb = hay.encode()
+                assert PF.h_sig_pass(pat, hb, len(hb)) == 1, (needle, hay, mode, cs)
+                lit_ok += 1
+    assert lit_ok > 400, lit_ok
+
+
+@pytest.mark.parametrize("lanes", [16, 32, 64])
 @pytest.mark.parametrize("k", [1, 2, 3, 5])
 def test_mask_prefilter_groundwork_2_and_n_typos(H, PF, lanes, k):
     """masks_paths<NP> / masks_many (prefilter_masks.cuh, not yet wired into the kernels) vs match_haystack_1_typo /
