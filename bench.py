@@ -379,6 +379,7 @@ def run_ours(args):
 
     for _ in range(max(args.warmup, 3)):
         n_matches = step()
+    resident_result = np.array(out_h[:n_matches]) if rank == 0 else None   # the e2e call must land the very same list
 
     # ---- parity in the same run (outside the timed region): every rank checks its whole shard
     parity = None
@@ -464,6 +465,9 @@ def run_ours(args):
         e_ms, n_e2e, _ = timed(step_e2e, e2e_steps)
     else:            # --e2e-steps -1: profiling / large strong-scaling runs skip the end-to-end leg
         e_ms, n_e2e, e2e_steps = float("nan"), n_matches, 1
+    e2e_equal = None
+    if args.e2e_steps >= 0 and rank == 0 and resident_result is not None:
+        e2e_equal = bool(n_e2e == n_matches and np.array_equal(np.array(out_h[:n_e2e]), resident_result))
     e2e_value = n * world * e2e_steps / (e_ms / 1e3)
     h2d = int(data_h.nbytes + off_e2e.nbytes)
     d2h_rank = int(n_e2e * 8 / world + 64)
@@ -529,9 +533,11 @@ def run_ours(args):
                                      "ms_per_step": ms_dev / args.steps, "what": "same step, merged list left in HBM"},
                 "d2h_bytes_per_step": int(n_matches * 8),
                 "e2e": {"value": e2e_value, "unit": "haystacks/s", "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h_rank * world,
-                        "steps": e2e_steps, "ms_per_step": e_ms / e2e_steps,
+                        "steps": e2e_steps, "ms_per_step": e_ms / e2e_steps, "result_equals_resident_call": e2e_equal,
+                        "streamed": os.environ.get("FRZ_E2E_STREAM", "1") != "0",
                         "input": f"Arrow {'Utf8 (int32' if off_e2e.dtype.itemsize == 4 else 'LargeUtf8 (int64'} offsets) "
-                                 "value+offset buffers in pinned host memory, one shard per rank; H2D chunks overlap the pack kernels"},
+                                 "value+offset buffers in pinned host memory, one shard per rank; H2D chunks overlap the pack kernels "
+                                 "AND the match pipeline (tile ranges are matched as they land; only the sort waits for the last chunk)"},
                 "gpu_launches": int(round(launches_per_step * args.steps)),
                 "roofline": roofline, "cpu_baseline": cpu, "parity": parity}
         print(json.dumps(line), flush=True)
@@ -544,6 +550,8 @@ def run_ours(args):
         dist.destroy_process_group()
     if parity is not None and parity["mismatches"] != 0:
         raise SystemExit(f"bench.py: parity FAILED: {parity}")
+    if e2e_equal is False:
+        raise SystemExit("bench.py: the end-to-end call's list differs from the resident call's")
 
 
 def main():

@@ -93,14 +93,18 @@ frz_status frz_pack_corpus_device(const uint8_t* d_bytes, const void* d_offsets,
                                   cudaStream_t stream, FrzCorpusStorage* out);
 frz_status frz_append_host(FrzIngest& ing, const uint8_t* h_bytes, const void* h_offsets, int offset_width, uint64_t n_new,
                            cudaStream_t stream, FrzCorpusStorage* st);
+// `after_chunk` (optional) is called on the host right after the pack kernels of tiles [t0, t1) have been enqueued on
+// `stream` (chunks arrive in tile order; `last` marks the final one): the caller may enqueue work on those tiles at once.
+typedef frz_status (*FrzChunkFn)(void* ctx, uint32_t t0, uint32_t t1, bool last);
 frz_status frz_ingest_host(FrzIngest& ing, const uint8_t* h_bytes, const void* h_offsets, int offset_width, uint64_t n,
-                           cudaStream_t stream, FrzCorpusStorage* out);
+                           cudaStream_t stream, FrzCorpusStorage* out, FrzChunkFn after_chunk = nullptr, void* ctx = nullptr);
 
 // Per-matcher device workspace (grown on demand, reused across calls).
 struct FrzWorkspace {
     int device = -1;
     FrzCounters* counters = nullptr;        // device
     FrzCounters* h_counters = nullptr;      // pinned host mirror
+    unsigned long long* stream_total = nullptr;   // device: running match count of a streamed call (tile-scan carry)
     FrzSurvivor* survivors[FRZ_N_CLASSES] = {};
     FrzSurvLists lists() const { FrzSurvLists l; for (int c = 0; c < FRZ_N_CLASSES; c++) l.p[c] = survivors[c]; return l; }
     uint64_t survivor_cap = 0;              // per class
@@ -149,7 +153,8 @@ frz_status frz_launch_match_indices(const FrzCorpusView& cv, const FrzPatternDev
 frz_status frz_launch_prefilter_list(const FrzCorpusView& cv, const FrzPatternDev& pat, const FrzMatchDev* cand,
                                      uint64_t n_cand, uint32_t index_offset, FrzWorkspace& ws, cudaStream_t stream,
                                      FrzLaunchStats* st);
-frz_status frz_launch_tile_scan(const FrzCorpusView& cv, FrzWorkspace& ws, cudaStream_t stream, FrzLaunchStats* st);
+frz_status frz_launch_tile_scan(const FrzCorpusView& cv, FrzWorkspace& ws, cudaStream_t stream, FrzLaunchStats* st,
+                                unsigned long long* carry = nullptr);
 frz_status frz_launch_sw(const FrzCorpusView& cv, const FrzPatternDev& pat, uint32_t index_offset, bool reversed,
                          FrzWorkspace& ws, FrzMatchDev* d_out, cudaStream_t stream, FrzLaunchStats* st);
 // stable sort by descending score; the element count is read from device memory (*n_ptr).
@@ -188,3 +193,7 @@ cudaEvent_t frz_matcher_table_event(const frz_matcher* m);
 // host Arrow buffers → the matcher's reusable packed corpus (the ingest half of frz_match_list_host_arrow)
 frz_status frz_matcher_ingest_e2e(frz_matcher* m, const uint8_t* bytes, const void* offsets, int offset_width, uint64_t n, int device,
                                   const frz_corpus** out);
+// frz_matcher_ingest_e2e + frz_match_shard_device in one pass: the match pipeline runs over consecutive tile ranges as their
+// H2D chunks land (prefilter → scan with carry → scoring append to one list), only the sort waits for the last chunk.
+frz_status frz_match_shard_streamed(frz_matcher* m, const uint8_t* bytes, const void* offsets, int offset_width, uint64_t n, int device,
+                                    uint32_t index_offset, frz_match* d_out, uint64_t cap, uint64_t* d_count, void* stream);

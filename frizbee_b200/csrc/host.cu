@@ -588,6 +588,7 @@ frz_status compile_pattern(const OwnedPattern& src, const frz_config& mcfg, bool
 void FrzWorkspace::release() {
     if (device >= 0) cudaSetDevice(device);
     cudaFree(counters);
+    cudaFree(stream_total); stream_total = nullptr;
     if (h_counters) cudaFreeHost(h_counters);
     for (auto& s : survivors) { cudaFree(s); s = nullptr; }
     cudaFree(surv_bitmap); cudaFree(word_prefix); surv_bitmap = nullptr; word_prefix = nullptr;
@@ -865,6 +866,7 @@ frz_status ensure_workspace(frz_matcher* m, const FrzCorpusStorage& cs, uint64_t
         FRZ_CUDA_TRY(cudaSetDevice(cs.device));
         ws.device = cs.device;
         FRZ_CUDA_TRY(cudaMalloc(&ws.counters, sizeof(FrzCounters)));
+        FRZ_CUDA_TRY(cudaMalloc(&ws.stream_total, sizeof(unsigned long long)));
         FRZ_CUDA_TRY(cudaMallocHost(&ws.h_counters, sizeof(FrzCounters)));
         for (auto& e : ws.ev) FRZ_CUDA_TRY(cudaEventCreate(&e));
         FRZ_CUDA_TRY(cudaEventCreateWithFlags(&ws.table_ev, cudaEventDisableTiming));
@@ -1340,6 +1342,135 @@ extern "C" frz_status frz_matcher_wait_count(frz_matcher* m, void* stream) {
     if (!m) return frz_fail(FRZ_ERR_INVALID_ARG, "null matcher");
     if (!m->count_ev) return frz_fail(FRZ_ERR_INVALID_ARG, "no shard call has been made on this matcher");
     FRZ_CUDA_TRY(cudaStreamWaitEvent((cudaStream_t)stream, m->count_ev, 0));
+    return FRZ_OK;
+}
+
+// ---- streamed shard call: host Arrow buffers in, locally ordered run out, the match pipeline overlapped with the H2D copy ----
+// The tiles of a packed corpus are independent, so the pipeline can run on tiles [t0, t1) through a SUB-VIEW of the corpus
+// (array pointers advanced to tile t0; unit addresses are absolute) as soon as their H2D chunk has been packed: length gate →
+// signature scan → exact windows → tile scan (carrying the running match count, so every range appends to the same
+// index-ordered list) → scoring.  Only the score sort waits for the last chunk.  The copy engine stays busy from the first
+// byte to the last; what is left after the last chunk lands is one range's pipeline + the sort instead of the whole list's.
+namespace {
+struct StreamedCtx {
+    frz_matcher* m;
+    const Compiled* c;
+    uint32_t index_offset;
+    FrzMatchDev* dst;       // index-ordered matches (pre-sort)
+    cudaStream_t stream;
+    FrzLaunchStats* st;
+    uint32_t pending_t0;    // first tile not yet matched
+    int chunks_pending;     // packed chunks since the last range
+    int group;              // chunks per range
+};
+frz_status streamed_range(StreamedCtx& x, uint32_t t0, uint32_t t1, bool last) {
+    frz_matcher* m = x.m;
+    FrzWorkspace& ws = m->ws;
+    const FrzCorpusStorage& cs = m->e2e_corpus.st;
+    FrzCorpusView cv = cs.view();
+    cv.tile_base += t0;
+    cv.groups += (size_t)t0 * FRZ_GROUPS_PER_TILE;
+    cv.slot_meta += (size_t)t0 * FRZ_TILE;
+    cv.slot_of += (size_t)t0 * FRZ_TILE;
+    cv.slot_sig += (size_t)t0 * FRZ_TILE;
+    cv.n = std::min<uint64_t>(cs.n, (uint64_t)t1 * FRZ_TILE) - (uint64_t)t0 * FRZ_TILE;
+    cv.n_tiles = t1 - t0;
+    const uint32_t off = x.index_offset + t0 * FRZ_TILE;
+    FRZ_CUDA_TRY(cudaMemsetAsync(ws.counters, 0, sizeof(FrzCounters), x.stream));
+    FRZ_TRY(frz_launch_prefilter(cv, x.c->dev, ws, x.stream, x.st));
+    FRZ_TRY(frz_launch_tile_scan(cv, ws, x.stream, x.st, ws.stream_total));
+    if (last) {
+        cudaEventRecord(ws.ev[1], x.stream); ws.ev_rec[1] = true;
+        if (m->early_count_dst) {   // the running count is final: publish it before the last range is scored
+            FRZ_CUDA_TRY(cudaMemcpyAsync(m->early_count_dst, &ws.counters->total, sizeof(uint64_t), cudaMemcpyDeviceToDevice, x.stream));
+            FRZ_CUDA_TRY(cudaEventRecord(m->count_ev, x.stream));
+            m->count_published = true;
+        }
+    }
+    FRZ_TRY(frz_launch_sw(cv, x.c->dev, off, false, ws, x.dst, x.stream, x.st));
+    return FRZ_OK;
+}
+frz_status streamed_after_chunk(void* ctx, uint32_t t0, uint32_t t1, bool last) {
+    StreamedCtx& x = *static_cast<StreamedCtx*>(ctx);
+    (void)t0;
+    x.chunks_pending++;
+    if (!last && x.chunks_pending < x.group) return FRZ_OK;
+    const uint32_t r0 = x.pending_t0;
+    x.pending_t0 = t1;
+    x.chunks_pending = 0;
+    if (t1 <= r0) return FRZ_OK;
+    return streamed_range(x, r0, t1, last);
+}
+}  // namespace
+
+frz_status frz_match_shard_streamed(frz_matcher* m, const uint8_t* bytes, const void* offsets, int offset_width, uint64_t n, int device,
+                                    uint32_t index_offset, frz_match* d_out, uint64_t cap, uint64_t* d_count, void* stream_) {
+    if (!m || !offsets || !d_out || !d_count) return frz_fail(FRZ_ERR_INVALID_ARG, "null argument");
+    static int knob = -1;   // FRZ_E2E_STREAM=0: ingest first, then match (the A/B partner)
+    if (knob < 0) { const char* e = getenv("FRZ_E2E_STREAM"); knob = e ? atoi(e) : 1; }
+    const uint8_t sort = m->config.sort;
+    const bool eligible = knob != 0 && m->compiled.size() == 1 && !m->compiled[0].negated && !m->compiled[0].unicode &&
+                          (sort == FRZ_SORT_INDEX_ASC || sort == FRZ_SORT_SCORE_THEN_INDEX_ASC) &&   // reversed lists need the final total per element
+                          n >= 64 * FRZ_TILE && (uint64_t)n + index_offset <= 0xFFFFFFFFull;
+    if (!eligible) {
+        const frz_corpus* shard = nullptr;
+        FRZ_TRY(frz_matcher_ingest_e2e(m, bytes, offsets, offset_width, n, device, &shard));
+        return frz_match_shard_device(m, shard, index_offset, d_out, cap, d_count, stream_);
+    }
+    if (offset_width != 4 && offset_width != 8) return frz_fail(FRZ_ERR_INVALID_ARG, "offset_width must be 4 or 8");
+    if (cap < n) return frz_fail(FRZ_ERR_CAPACITY, "d_out must hold the whole shard (%llu)", (unsigned long long)n);
+    FRZ_TRY(ensure_device(device));
+    cudaStream_t stream = (cudaStream_t)stream_;
+    frz_corpus& c = m->e2e_corpus;
+    if (c.st.device != device && (m->e2e_ingest.d_bytes || m->e2e_ingest.copy_stream || c.st.data)) {  // arena lives on another device
+        cudaSetDevice(c.st.device);
+        m->e2e_ingest.release();
+        c.st.release();
+        FRZ_CUDA_TRY(cudaSetDevice(device));
+    }
+    c.st.device = device;
+    c.st.n = n;
+    c.st.n_tiles = (uint32_t)((n + FRZ_TILE - 1) / FRZ_TILE);
+    FrzWorkspace& ws = m->ws;
+    FRZ_TRY(ensure_workspace(m, c.st, std::max<uint64_t>(n, 1)));   // nobody reads the overflow flag back: worst-case lists
+    if (!m->count_ev) FRZ_CUDA_TRY(cudaEventCreateWithFlags(&m->count_ev, cudaEventDisableTiming));
+    const Compiled& pat = m->compiled[0];
+    const bool will_sort = sort == FRZ_SORT_SCORE_THEN_INDEX_ASC;
+    FrzMatchDev* final_out = reinterpret_cast<FrzMatchDev*>(d_out);
+    FrzLaunchStats st;
+    for (bool& f : ws.ev_rec) f = false;
+    m->last_sort_bins = 0;
+    m->early_count_dst = d_count;
+    m->count_published = false;
+    ws.arm_table_ev = true;
+    ws.table_ev_recorded = false;
+    StreamedCtx x;
+    x.m = m; x.c = &pat; x.index_offset = index_offset; x.dst = will_sort ? ws.matches_a : final_out; x.stream = stream; x.st = &st;
+    x.pending_t0 = 0; x.chunks_pending = 0;
+    x.group = 4;   // a range per four H2D chunks (about 1/8 of the list): the tail after the last chunk is one range + the sort
+    const frz_status ms = [&]() -> frz_status {
+        FRZ_CUDA_TRY(cudaMemsetAsync(ws.stream_total, 0, sizeof(unsigned long long), stream));
+        cudaEventRecord(ws.ev[0], stream); ws.ev_rec[0] = true;
+        FRZ_TRY(frz_ingest_host(m->e2e_ingest, bytes, offsets, offset_width, n, stream, &c.st, streamed_after_chunk, &x));
+        cudaEventRecord(ws.ev[2], stream); ws.ev_rec[2] = true;
+        if (will_sort) {
+            FrzMatchDev* tmp = nullptr;
+            if (pat.score_bound >= 1024) { FRZ_TRY(ensure_multi_buffers(m, n)); tmp = m->multi_a; }
+            FRZ_TRY(frz_launch_sort_by_score_dev(ws.matches_a, tmp, final_out, &ws.counters->total, pat.score_bound, ws, stream, &st));
+            m->last_sort_bins = frz_sort_single_pass_bins(pat.score_bound);
+        }
+        cudaEventRecord(ws.ev[3], stream); ws.ev_rec[3] = true;
+        return FRZ_OK;
+    }();
+    m->early_count_dst = nullptr;
+    ws.arm_table_ev = false;
+    FRZ_TRY(ms);
+    if (!m->count_published) {   // (cannot happen with >= 1 chunk; kept for symmetry with frz_match_shard_device)
+        FRZ_CUDA_TRY(cudaMemcpyAsync(d_count, &ws.counters->total, sizeof(uint64_t), cudaMemcpyDeviceToDevice, stream));
+        FRZ_CUDA_TRY(cudaEventRecord(m->count_ev, stream));
+    }
+    m->last_launches = st.launches;
+    m->timings_pending = true;
     return FRZ_OK;
 }
 

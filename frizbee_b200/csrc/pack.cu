@@ -381,7 +381,7 @@ frz_status pack_device_t(const uint8_t* d_bytes, const OffT* d_offsets, uint64_t
 // while the first chunks are in flight and every chunk is interleaved as soon as it has landed.
 template <typename OffT>
 frz_status ingest_host_t(FrzIngest& ing, const uint8_t* h_bytes, const OffT* h_offsets, uint64_t n, cudaStream_t stream,
-                         FrzCorpusStorage* out) {
+                         FrzCorpusStorage* out, FrzChunkFn after_chunk, void* ctx) {
     const uint64_t off0 = (uint64_t)h_offsets[0];
     const uint64_t total = (uint64_t)h_offsets[n] - off0;
     const uint32_t n_tiles = (uint32_t)((n + FRZ_TILE - 1) / FRZ_TILE);
@@ -417,6 +417,7 @@ frz_status ingest_host_t(FrzIngest& ing, const uint8_t* h_bytes, const OffT* h_o
     for (int c = 0; c < n_chunks; c++) {
         FRZ_CUDA_TRY(cudaStreamWaitEvent(stream, ing.ev[c], 0));
         FRZ_TRY(pack_copy<OffT>(out, ing.d_bytes, d_off, 0, 0, off0, total, bounds[c], bounds[c + 1], stream));
+        if (after_chunk) FRZ_TRY(after_chunk(ctx, bounds[c], bounds[c + 1], c == n_chunks - 1));
     }
     return FRZ_OK;
 }
@@ -507,9 +508,9 @@ frz_status frz_pack_corpus_device(const uint8_t* d_bytes, const void* d_offsets,
 
 // Streams host Arrow buffers (ideally pinned) into a packed corpus: H2D chunks overlap the bucketing kernels.
 frz_status frz_ingest_host(FrzIngest& ing, const uint8_t* h_bytes, const void* h_offsets, int offset_width, uint64_t n,
-                           cudaStream_t stream, FrzCorpusStorage* out) {
-    if (offset_width == 4) return ingest_host_t<uint32_t>(ing, h_bytes, static_cast<const uint32_t*>(h_offsets), n, stream, out);
-    return ingest_host_t<uint64_t>(ing, h_bytes, static_cast<const uint64_t*>(h_offsets), n, stream, out);
+                           cudaStream_t stream, FrzCorpusStorage* out, FrzChunkFn after_chunk, void* ctx) {
+    if (offset_width == 4) return ingest_host_t<uint32_t>(ing, h_bytes, static_cast<const uint32_t*>(h_offsets), n, stream, out, after_chunk, ctx);
+    return ingest_host_t<uint64_t>(ing, h_bytes, static_cast<const uint64_t*>(h_offsets), n, stream, out, after_chunk, ctx);
 }
 
 // Appends host Arrow buffers to a packed corpus; indices of the new haystacks continue at the old length.

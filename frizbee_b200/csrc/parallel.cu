@@ -699,16 +699,25 @@ struct StepResult {
     const FrzMatchDev* d_merged = nullptr;
 };
 
+// a shard that arrives as HOST Arrow buffers (end-to-end calls): matched while it streams in (host.cu: frz_match_shard_streamed)
+struct HostShard {
+    const uint8_t* bytes;
+    const void* offsets;
+    int offset_width;
+    uint64_t n;
+};
+
 // Everything one GPU does for one match_list_parallel call.  `seq` is the step number shared by all ranks.
 // `want_slices`: the caller only needs the list in host memory (no device copy of the whole merged list): slice exchange allowed.
-frz_status rank_step(frz_comm* c, RankCtx& r, frz_matcher* m, const frz_corpus* shard, uint32_t index_offset, uint64_t seq,
+// Exactly one of `shard` (resident packed corpus) and `hs` (host buffers) is given.
+frz_status rank_step(frz_comm* c, RankCtx& r, frz_matcher* m, const frz_corpus* shard, const HostShard* hs, uint32_t index_offset, uint64_t seq,
                      frz_match* out_host, uint64_t cap, bool want_host, bool want_slices, StepResult* res) {
     FRZ_TRY(set_device(r.device));
     cudaStream_t main = nullptr;   // the device's legacy default stream: ordered with the caller's own default-stream work
     const int world = c->world;
     const int parity = (int)(seq & 1);
-    if (!m || !shard) return frz_fail(FRZ_ERR_INVALID_ARG, "null argument");
-    if (frz_corpus_device(shard) != r.device)
+    if (!m || (!shard && !hs)) return frz_fail(FRZ_ERR_INVALID_ARG, "null argument");
+    if (shard && frz_corpus_device(shard) != r.device)
         return frz_fail(FRZ_ERR_INVALID_ARG, "shard of rank %d lives on device %d, the communicator expects device %d", r.rank,
                         frz_corpus_device(shard), r.device);
     if (!r.clone || r.clone_epoch != frz_matcher_epoch(m)) {   // parallel.rs:46 — `matcher.clone()` per worker
@@ -717,7 +726,7 @@ frz_status rank_step(frz_comm* c, RankCtx& r, frz_matcher* m, const frz_corpus* 
         FRZ_TRY(frz_matcher_clone(m, &r.clone));
         r.clone_epoch = frz_matcher_epoch(m);
     }
-    const uint64_t n_local = frz_corpus_len(shard);
+    const uint64_t n_local = hs ? hs->n : frz_corpus_len(shard);
     if (r.run_cap < std::max<uint64_t>(n_local, 1)) {
         cudaFree(r.run); r.run = nullptr; r.run_cap = 0;
         const uint64_t want = std::max<uint64_t>(n_local, 1);
@@ -726,8 +735,12 @@ frz_status rank_step(frz_comm* c, RankCtx& r, frz_matcher* m, const frz_corpus* 
     }
     FRZ_CUDA_TRY(cudaEventRecord(r.ev[0], main));
     // ---- local pipeline (asynchronous): prefilter → count published → scoring → local order
-    FRZ_TRY(frz_match_shard_device(r.clone, shard, index_offset, reinterpret_cast<frz_match*>(r.run), r.run_cap,
-                                   reinterpret_cast<uint64_t*>(r.d_count), main));
+    if (hs)
+        FRZ_TRY(frz_match_shard_streamed(r.clone, hs->bytes, hs->offsets, hs->offset_width, hs->n, r.device, index_offset,
+                                         reinterpret_cast<frz_match*>(r.run), r.run_cap, reinterpret_cast<uint64_t*>(r.d_count), main));
+    else
+        FRZ_TRY(frz_match_shard_device(r.clone, shard, index_offset, reinterpret_cast<frz_match*>(r.run), r.run_cap,
+                                       reinterpret_cast<uint64_t*>(r.d_count), main));
     FRZ_TRY(frz_matcher_wait_count(r.clone, r.side));
     k_publish<<<1, 1, 0, r.side>>>(reinterpret_cast<volatile unsigned long long*>(r.ctrl_dev + kCtrlCount + parity * kMaxWorld + r.rank),
                                    r.d_count, seq);
@@ -951,7 +964,7 @@ frz_status rank_step(frz_comm* c, RankCtx& r, frz_matcher* m, const frz_corpus* 
 
 void run_job(frz_comm* c, RankCtx& r, frz_matcher* m, const frz_corpus* shard, uint32_t offset, uint64_t seq, frz_match* out,
              uint64_t cap, bool want_host, StepResult* res) {
-    res->status = rank_step(c, r, m, shard, offset, seq, out, cap, want_host, true, res);
+    res->status = rank_step(c, r, m, shard, nullptr, offset, seq, out, cap, want_host, true, res);
     if (res->status != FRZ_OK) res->error = frz_last_error();
 }
 
@@ -1154,7 +1167,7 @@ extern "C" frz_status frz_match_list_parallel_rank(frz_matcher* m, const frz_cor
     const uint64_t seq = ++c->seq;
     StepResult res;
     const bool want_host = out != nullptr || cap != 0;
-    const frz_status s = rank_step(c, c->ranks[0], m, shard, index_offset, seq, out, cap, want_host, d_out == nullptr, &res);
+    const frz_status s = rank_step(c, c->ranks[0], m, shard, nullptr, index_offset, seq, out, cap, want_host, d_out == nullptr, &res);
     if (n_out) *n_out = res.total;
     if (d_out) *d_out = reinterpret_cast<const frz_match*>(res.d_merged);
     return s;
@@ -1178,11 +1191,11 @@ extern "C" frz_status frz_match_list_parallel_rank_host(frz_matcher* m, const ui
         FRZ_TRY(frz_matcher_clone(m, &r.clone));
         r.clone_epoch = frz_matcher_epoch(m);
     }
-    const frz_corpus* shard = nullptr;
-    FRZ_TRY(frz_matcher_ingest_e2e(r.clone, bytes, offsets, offset_width, n, r.device, &shard));
+    if (offset_width != 4 && offset_width != 8) return frz_fail(FRZ_ERR_INVALID_ARG, "offset_width must be 4 or 8");
+    const HostShard hs{bytes, offsets, offset_width, n};
     const uint64_t seq = ++c->seq;
     StepResult res;
-    const frz_status s = rank_step(c, r, m, shard, index_offset, seq, out, cap, true, true, &res);
+    const frz_status s = rank_step(c, r, m, nullptr, &hs, index_offset, seq, out, cap, true, true, &res);
     if (n_out) *n_out = res.total;
     return s;
 }

@@ -838,8 +838,10 @@ __global__ void __launch_bounds__(256) k_tile_rank(const uint32_t* __restrict__ 
 // exclusive scan of tile_count → tile_out_base; total → counters.total.  One block; every thread owns a CONTIGUOUS run
 // of ceil(n / 1024) tiles, so the block makes one pass (two for > 1 M tiles) instead of n / 1024 barrier rounds
 // (12 us → 3 us at 9766 tiles, profiles/r02b_launches.csv vs r02d).
+// `carry` (optional): the scan starts at *carry and leaves the new total there too — streamed calls (host.cu:
+// frz_match_shard_streamed) run the pipeline over consecutive tile ranges and append each range's matches to the same list.
 __global__ void __launch_bounds__(1024) k_tile_scan(const uint32_t* __restrict__ tile_count, uint64_t* __restrict__ out,
-                                                    uint32_t n, FrzCounters* __restrict__ ctr) {
+                                                    uint32_t n, FrzCounters* __restrict__ ctr, unsigned long long* carry) {
     __shared__ uint64_t warp_sum[32];
     const uint32_t per = (n + blockDim.x - 1) / blockDim.x;
     const uint32_t lo = min(threadIdx.x * per, n), hi = min(lo + per, n);
@@ -861,12 +863,17 @@ __global__ void __launch_bounds__(1024) k_tile_scan(const uint32_t* __restrict__
         warp_sum[threadIdx.x] = xs - w;
     }
     __syncthreads();
-    uint64_t run = warp_sum[threadIdx.x >> 5] + x - sum;   // exclusive prefix of this thread's run
+    const uint64_t start = carry ? *carry : 0ull;
+    __syncthreads();                                        // everybody has read the carry before the last thread replaces it
+    uint64_t run = start + warp_sum[threadIdx.x >> 5] + x - sum;   // exclusive prefix of this thread's run
     for (uint32_t i = lo; i < hi; i++) {
         out[i] = run;
         run += tile_count[i];
     }
-    if (threadIdx.x == blockDim.x - 1) ctr->total = run;   // the last thread's run ends at n (empty runs carry the total)
+    if (threadIdx.x == blockDim.x - 1) {   // the last thread's run ends at n (empty runs carry the total)
+        ctr->total = run;
+        if (carry) *carry = run;
+    }
 }
 
 // Matcher::match_list_indices for chosen haystacks (src/matcher/mod.rs:234-262 → match_one_indices_impl,
@@ -1048,12 +1055,13 @@ frz_status frz_launch_prefilter(const FrzCorpusView& cv, const FrzPatternDev& pa
     return FRZ_OK;
 }
 
-frz_status frz_launch_tile_scan(const FrzCorpusView& cv, FrzWorkspace& ws, cudaStream_t stream, FrzLaunchStats* st) {
+frz_status frz_launch_tile_scan(const FrzCorpusView& cv, FrzWorkspace& ws, cudaStream_t stream, FrzLaunchStats* st,
+                                unsigned long long* carry) {
     if (cv.n_tiles) {
         k_tile_rank<<<(cv.n_tiles * 32 + 255) / 256, 256, 0, stream>>>(ws.surv_bitmap, ws.word_prefix, ws.tile_count, cv.n_tiles);
         if (st) st->launches++;
     }
-    k_tile_scan<<<1, 1024, 0, stream>>>(ws.tile_count, ws.tile_out_base, cv.n_tiles, ws.counters);
+    k_tile_scan<<<1, 1024, 0, stream>>>(ws.tile_count, ws.tile_out_base, cv.n_tiles, ws.counters, carry);
     FRZ_CUDA_TRY(cudaGetLastError());
     if (st) st->launches++;
     return FRZ_OK;

@@ -92,6 +92,33 @@ def test_parallel_rank_api_world1_nccl_comm():
     shard.close(); m.close(); comm.close()
 
 
+def test_streamed_end_to_end_call_equals_resident_corpus():
+    """frz_match_list_parallel_rank_host matches the list WHILE it streams in (host.cu: frz_match_shard_streamed — the
+    pipeline runs over consecutive tile ranges as their H2D chunks land, the tile scan carries the running count, only
+    the sort waits for the last chunk).  2 M haystacks = 12 chunks = 3 ranges; the result must equal match_list on the
+    resident corpus for the two sort strategies the streamed form serves, and for the ones that fall back (reversed)."""
+    import frizbee_b200 as F
+    from frizbee_b200 import parallel, synth
+    from frizbee_b200.types import Config, SortStrategy
+    comm = parallel.Comm.from_rank(parallel.Comm.unique_id(), 1, 0, 0)
+    n = 2_000_000
+    data, off = synth.generate("deadbeef", n, 48, 64, seed=17)
+    off32 = off.astype(np.int32)
+    whole = F.Corpus.from_arrow(data, off)
+    out = comm.host_alloc_matches(n)
+    for sort in (SortStrategy.ScoreThenIndexAsc, SortStrategy.IndexAsc, SortStrategy.ScoreThenIndexDesc):
+        for k in (1, 0):
+            m = F.Matcher("deadbeef", Config(max_typos=k, sort=sort))
+            want = m.match_list_array(whole)
+            for offsets in (off32, off):
+                total = comm.match_list_parallel_rank_host(m, data, offsets, 7, out)
+                w = want.copy(); w["index"] += 7
+                assert total == len(w) and np.array_equal(np.array(out[:total]), w), (sort, k, offsets.dtype)
+            m.close()
+    comm.host_free(out)
+    whole.close(); comm.close()
+
+
 def test_sort_scratch_regrows_for_a_larger_corpus():
     """a matcher whose score bound needs the two-pass sort sized its scratch by the FIRST corpus; a later,
     larger corpus must regrow it (was a device out-of-bounds write)."""
