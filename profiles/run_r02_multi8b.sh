@@ -1,5 +1,5 @@
 #!/bin/bash
-# round 2, second 8-GPU call: weak-scaling bench at N=8 (and N=4) with the P2P placement exchange; BASELINE configs[3]
+# round 2, second 8-GPU call: weak-scaling bench at N=8 with the P2P placement exchange; BASELINE configs[3]
 # (C4: 100 M haystacks, k=0, 8 shards of 12.5 M) and configs[4] (C5: 'foo !^bar' on 10 M mixed-unicode haystacks <= 128 B,
 # 8 shards of 1.25 M) — every run with the full-shard parity leg (each rank checks its whole shard against the CPU restatement).
 export FRZ_BENCH_CACHE=/tmp/frz_cache
@@ -13,11 +13,9 @@ tail -c 400 gpurun_out/r02l_c4_n8.err
 tr 8 --steps 20 --warmup 5 --haystacks-per-gpu 1250000 --query 'foo !^bar' --max-typos 0 --mu 96 --max-len 128 --unicode-frac 0.3 --prefix-frac 0.1 --e2e-steps 3 \
    > gpurun_out/r02l_c5_n8.json 2> gpurun_out/r02l_c5_n8.err; echo "c5 rc=$?"
 tail -c 400 gpurun_out/r02l_c5_n8.err
-tr 4 --steps 20 --warmup 5 --e2e-steps 3 > gpurun_out/r02l_bench_n4.json 2> gpurun_out/r02l_bench_n4.err; echo "n4 rc=$?"
-tail -c 300 gpurun_out/r02l_bench_n4.err
 python - <<'PY'
 import json
-for tag in ("bench_n8", "c4_n8", "c5_n8", "bench_n4"):
+for tag in ("bench_n8", "c4_n8", "c5_n8"):
     try:
         d = json.loads(open(f"gpurun_out/r02l_{tag}.json").read().strip().splitlines()[-1])
         s = d["roofline"]["stage_ms_per_step"]
