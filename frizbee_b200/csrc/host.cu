@@ -866,7 +866,7 @@ frz_status ensure_workspace(frz_matcher* m, const FrzCorpusStorage& cs, uint64_t
         FRZ_CUDA_TRY(cudaSetDevice(cs.device));
         ws.device = cs.device;
         FRZ_CUDA_TRY(cudaMalloc(&ws.counters, sizeof(FrzCounters)));
-        FRZ_CUDA_TRY(cudaMalloc(&ws.stream_total, sizeof(unsigned long long)));
+        FRZ_CUDA_TRY(cudaMalloc(&ws.stream_total, 2 * sizeof(unsigned long long)));   // [0] tile-scan carry, [1] spare count slot
         FRZ_CUDA_TRY(cudaMallocHost(&ws.h_counters, sizeof(FrzCounters)));
         for (auto& e : ws.ev) FRZ_CUDA_TRY(cudaEventCreate(&e));
         FRZ_CUDA_TRY(cudaEventCreateWithFlags(&ws.table_ev, cudaEventDisableTiming));
@@ -1192,12 +1192,27 @@ extern "C" frz_status frz_match_list_into(frz_matcher* m, const frz_corpus* corp
     return s;
 }
 
+namespace {   // defined with the shard calls below
+bool streamed_eligible(const frz_matcher* m, uint64_t n, uint32_t index_offset);
+frz_status match_streamed_impl(frz_matcher* m, const uint8_t* bytes, const void* offsets, int offset_width, uint64_t n, int device,
+                               uint32_t index_offset, FrzMatchDev* d_out, uint64_t* d_count, cudaStream_t stream, FrzMatchDev** d_result);
+}  // namespace
+
 // End to end from host Arrow buffers: streamed H2D + pack (pack.cu: ingest_host_t), match, D2H of the matches.
 extern "C" frz_status frz_match_list_host_arrow(frz_matcher* m, const uint8_t* bytes, const void* offsets, int offset_width, uint64_t n,
                                                 int device, frz_match* out, uint64_t cap, uint64_t* n_out) {
     if (!m || !offsets) return frz_fail(FRZ_ERR_INVALID_ARG, "null argument");
     if (offset_width != 4 && offset_width != 8) return frz_fail(FRZ_ERR_INVALID_ARG, "offset_width must be 4 or 8");
     if (n > 0xFFFFFFFFull) return frz_fail(FRZ_ERR_TOO_MANY_ITEMS, "too many items in haystack: %llu", (unsigned long long)n);
+    if (streamed_eligible(m, n, 0)) {   // the match pipeline runs while the list streams in (frz_match_shard_streamed)
+        FrzMatchDev* d_list = nullptr;
+        FRZ_TRY(match_streamed_impl(m, bytes, offsets, offset_width, n, device, 0, nullptr, nullptr, nullptr, &d_list));
+        const frz_status s = copy_out(m, d_list, out, cap, n_out, nullptr);
+        m->timings_pending = false;
+        FrzLaunchStats st; st.launches = m->last_launches;
+        collect_timings(m, st);
+        return s;
+    }
     const frz_corpus* c = nullptr;
     FRZ_TRY(frz_matcher_ingest_e2e(m, bytes, offsets, offset_width, n, device, &c));
     return frz_match_list(m, c, out, cap, n_out);
@@ -1403,24 +1418,38 @@ frz_status streamed_after_chunk(void* ctx, uint32_t t0, uint32_t t1, bool last) 
 }
 }  // namespace
 
-frz_status frz_match_shard_streamed(frz_matcher* m, const uint8_t* bytes, const void* offsets, int offset_width, uint64_t n, int device,
-                                    uint32_t index_offset, frz_match* d_out, uint64_t cap, uint64_t* d_count, void* stream_) {
-    if (!m || !offsets || !d_out || !d_count) return frz_fail(FRZ_ERR_INVALID_ARG, "null argument");
+namespace {
+bool streamed_eligible(const frz_matcher* m, uint64_t n, uint32_t index_offset) {
     static int knob = -1;   // FRZ_E2E_STREAM=0: ingest first, then match (the A/B partner)
     if (knob < 0) { const char* e = getenv("FRZ_E2E_STREAM"); knob = e ? atoi(e) : 1; }
     const uint8_t sort = m->config.sort;
-    const bool eligible = knob != 0 && m->compiled.size() == 1 && !m->compiled[0].negated && !m->compiled[0].unicode &&
-                          (sort == FRZ_SORT_INDEX_ASC || sort == FRZ_SORT_SCORE_THEN_INDEX_ASC) &&   // reversed lists need the final total per element
-                          n >= 64 * FRZ_TILE && (uint64_t)n + index_offset <= 0xFFFFFFFFull;
-    if (!eligible) {
+    return knob != 0 && m->compiled.size() == 1 && !m->compiled[0].negated && !m->compiled[0].unicode &&
+           (sort == FRZ_SORT_INDEX_ASC || sort == FRZ_SORT_SCORE_THEN_INDEX_ASC) &&   // reversed lists need the final total per element
+           n >= 64 * FRZ_TILE && (uint64_t)n + index_offset <= 0xFFFFFFFFull;
+}
+}  // namespace
+// (match_streamed_impl: d_out == nullptr leaves the list in the matcher's own buffer, returned through d_result;
+//  d_count == nullptr uses a spare device slot)
+
+frz_status frz_match_shard_streamed(frz_matcher* m, const uint8_t* bytes, const void* offsets, int offset_width, uint64_t n, int device,
+                                    uint32_t index_offset, frz_match* d_out, uint64_t cap, uint64_t* d_count, void* stream_) {
+    if (!m || !offsets || !d_out || !d_count) return frz_fail(FRZ_ERR_INVALID_ARG, "null argument");
+    if (offset_width != 4 && offset_width != 8) return frz_fail(FRZ_ERR_INVALID_ARG, "offset_width must be 4 or 8");
+    if (!streamed_eligible(m, n, index_offset)) {
         const frz_corpus* shard = nullptr;
         FRZ_TRY(frz_matcher_ingest_e2e(m, bytes, offsets, offset_width, n, device, &shard));
         return frz_match_shard_device(m, shard, index_offset, d_out, cap, d_count, stream_);
     }
-    if (offset_width != 4 && offset_width != 8) return frz_fail(FRZ_ERR_INVALID_ARG, "offset_width must be 4 or 8");
     if (cap < n) return frz_fail(FRZ_ERR_CAPACITY, "d_out must hold the whole shard (%llu)", (unsigned long long)n);
+    return match_streamed_impl(m, bytes, offsets, offset_width, n, device, index_offset, reinterpret_cast<FrzMatchDev*>(d_out), d_count,
+                               (cudaStream_t)stream_, nullptr);
+}
+
+namespace {
+frz_status match_streamed_impl(frz_matcher* m, const uint8_t* bytes, const void* offsets, int offset_width, uint64_t n, int device,
+                               uint32_t index_offset, FrzMatchDev* d_out, uint64_t* d_count, cudaStream_t stream, FrzMatchDev** d_result) {
+    const uint8_t sort = m->config.sort;
     FRZ_TRY(ensure_device(device));
-    cudaStream_t stream = (cudaStream_t)stream_;
     frz_corpus& c = m->e2e_corpus;
     if (c.st.device != device && (m->e2e_ingest.d_bytes || m->e2e_ingest.copy_stream || c.st.data)) {  // arena lives on another device
         cudaSetDevice(c.st.device);
@@ -1436,7 +1465,9 @@ frz_status frz_match_shard_streamed(frz_matcher* m, const uint8_t* bytes, const 
     if (!m->count_ev) FRZ_CUDA_TRY(cudaEventCreateWithFlags(&m->count_ev, cudaEventDisableTiming));
     const Compiled& pat = m->compiled[0];
     const bool will_sort = sort == FRZ_SORT_SCORE_THEN_INDEX_ASC;
-    FrzMatchDev* final_out = reinterpret_cast<FrzMatchDev*>(d_out);
+    FrzMatchDev* final_out = d_out ? d_out : ws.matches_b;
+    if (!d_count) d_count = reinterpret_cast<uint64_t*>(ws.stream_total + 1);
+    if (d_result) *d_result = final_out;
     FrzLaunchStats st;
     for (bool& f : ws.ev_rec) f = false;
     m->last_sort_bins = 0;
@@ -1473,6 +1504,7 @@ frz_status frz_match_shard_streamed(frz_matcher* m, const uint8_t* bytes, const 
     m->timings_pending = true;
     return FRZ_OK;
 }
+}  // namespace
 
 namespace {
 // Run metadata travels BY VALUE as a kernel parameter (1 KB of the 4 KB parameter space): no staging buffer, so

@@ -32,6 +32,7 @@
 #include <sched.h>
 #include <sys/mman.h>
 #include <sys/stat.h>
+#include <sys/syscall.h>
 #include <time.h>
 #include <unistd.h>
 
@@ -511,10 +512,11 @@ frz_status ensure_place_buffers(frz_comm* c, RankCtx& r, uint64_t need, bool* re
 }
 
 // ---- NUMA placement of the shared host buffer ------------------------------------------------------------------
-// Rank r writes the r-th part of the merged list, so the r-th part of the buffer should live on the memory node of
-// GPU r's PCIe root: a page belongs to the node of the CPU that touches it first.  Each rank therefore touches its own
-// part — from a CPU of its GPU's node — before the segment is pinned.  (Measured at 8 GPUs with every page on rank 0's
-// node: the eight concurrent 6 MB slice copies took 0.28 ms instead of 0.11 ms, profiles/r02g_bench_n8.json.)
+// All G GPUs copy their slices into the buffer at the same moment: G x 52 GB/s of inbound DMA writes.  With every page on
+// one memory node that node's DRAM write bandwidth and the socket interconnect are the limit (measured at 8 GPUs: the
+// eight concurrent 6 MB slice copies took 0.28 ms instead of 0.11 ms, profiles/r02g_bench_n8.json; 0.21 ms with the
+// first-touch placement below, whose parts only line up with the slices when the list fills the buffer,
+// profiles/r02l_bench_n8.json).  See numa_policy().
 int gpu_numa_node(int device) {
     char bus[32] = {0};
     if (cudaDeviceGetPCIBusId(bus, sizeof bus, device) != cudaSuccess) { cudaGetLastError(); return -1; }
@@ -546,19 +548,72 @@ bool node_cpus(int node, cpu_set_t* set) {   // parses /sys/devices/system/node/
     fclose(f);
     return n > 0;
 }
+// Page placement policy of the shared host buffers (FRZ_HOST_NUMA):
+//   interleave (default)  pages alternate over the memory nodes (mbind MPOL_INTERLEAVE before the first touch): every GPU's
+//                         slice is half local, half remote, wherever the slice boundaries of a step fall, and the DRAM
+//                         write load of G concurrent slice copies is spread evenly over the sockets
+//   touch                 rank r first-touches the r-th part of the buffer from a CPU of its GPU's node (exact only when the
+//                         list fills the buffer: slices are fractions of the USED part)
+//   none                  wherever the kernel puts them
+enum { kNumaInterleave = 0, kNumaTouch = 1, kNumaNone = 2 };
+int numa_policy() {
+    static int p = -1;
+    if (p < 0) {
+        const char* e = getenv("FRZ_HOST_NUMA");
+        p = !e ? kNumaInterleave : strcmp(e, "touch") == 0 ? kNumaTouch : strcmp(e, "none") == 0 ? kNumaNone : kNumaInterleave;
+    }
+    return p;
+}
+bool numa_debug() { static int d = -1; if (d < 0) { const char* e = getenv("FRZ_PARALLEL_DEBUG"); d = e && atoi(e) ? 1 : 0; } return d == 1; }
+// nodes that have memory: /sys/devices/system/node/has_memory ("0-1"); 0 when unknown
+unsigned long memory_node_mask() {
+    FILE* f = fopen("/sys/devices/system/node/has_memory", "r");
+    if (!f) f = fopen("/sys/devices/system/node/online", "r");
+    if (!f) return 0;
+    unsigned long mask = 0;
+    int a = 0, b = 0;
+    for (;;) {
+        if (fscanf(f, "%d", &a) != 1) break;
+        b = a;
+        int ch = fgetc(f);
+        if (ch == '-') { if (fscanf(f, "%d", &b) != 1) break; ch = fgetc(f); }
+        for (int n = a; n <= b && n < (int)(8 * sizeof mask); n++) mask |= 1ul << n;
+        if (ch != ',') break;
+    }
+    fclose(f);
+    return mask;
+}
+// mbind(MPOL_INTERLEAVE) over the memory nodes; raw syscall (no libnuma in the image).  false = unavailable (one node, no permission)
+bool interleave_pages(void* ptr, uint64_t bytes) {
+    const unsigned long mask = memory_node_mask();
+    if (__builtin_popcountl(mask) < 2) return false;
+    constexpr int kMpolInterleave = 3;
+    return syscall(SYS_mbind, ptr, (unsigned long)bytes, kMpolInterleave, &mask, (unsigned long)(8 * sizeof mask + 1), 0u) == 0;
+}
+// node of the page holding `addr` (move_pages with a null target = query), -1 when unknown
+int page_node(void* addr) {
+    void* page = reinterpret_cast<void*>(reinterpret_cast<uintptr_t>(addr) & ~4095ull);
+    int status = -1;
+    if (syscall(SYS_move_pages, 0, 1ul, &page, nullptr, &status, 0) != 0) return -1;
+    return status;
+}
 // touches [lo, hi) of `ptr` (one byte per page, value preserved as zero) from a CPU near `device`, then restores the affinity
-void first_touch_near(int device, unsigned char* ptr, uint64_t lo, uint64_t hi) {
+void first_touch_near(int device, unsigned char* ptr, uint64_t lo, uint64_t hi, bool pin_near) {
     cpu_set_t old_set, near_set;
     const bool have_old = sched_getaffinity(0, sizeof old_set, &old_set) == 0;
     const int node = gpu_numa_node(device);
     bool moved = false;
-    if (have_old && node >= 0 && node_cpus(node, &near_set)) {
+    if (pin_near && have_old && node >= 0 && node_cpus(node, &near_set)) {
         cpu_set_t both;
         CPU_AND(&both, &near_set, &old_set);   // stay inside whatever the launcher allowed
         if (CPU_COUNT(&both) > 0) moved = sched_setaffinity(0, sizeof both, &both) == 0;
     }
     for (uint64_t off = lo & ~4095ull; off < hi; off += 4096) ptr[off] = 0;
     if (moved) sched_setaffinity(0, sizeof old_set, &old_set);
+    if (numa_debug() && hi > lo)
+        fprintf(stderr, "[frz numa] device %d: sysfs node %d, affinity %s, policy %d; pages of [%llu, %llu): first on node %d, middle %d, last %d\n",
+                device, node, moved ? "moved" : "unchanged", numa_policy(), (unsigned long long)lo, (unsigned long long)hi,
+                page_node(ptr + lo), page_node(ptr + (lo + hi) / 2), page_node(ptr + hi - 1));
 }
 
 frz_status host_block_alloc(frz_comm* c, uint64_t bytes, HostBlock* out) {
@@ -571,8 +626,10 @@ frz_status host_block_alloc(frz_comm* c, uint64_t bytes, HostBlock* out) {
         b.ptr = mmap(nullptr, bytes, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
         if (b.ptr == MAP_FAILED) return frz_fail(FRZ_ERR_OOM, "cannot map %llu bytes of host memory", (unsigned long long)bytes);
         const int world = c->world;
+        const bool inter = numa_policy() == kNumaInterleave && interleave_pages(b.ptr, bytes);
         for (int g = 0; g < world; g++)
-            first_touch_near(c->ranks[g].device, static_cast<unsigned char*>(b.ptr), bytes * (uint64_t)g / world, bytes * (uint64_t)(g + 1) / world);
+            first_touch_near(c->ranks[g].device, static_cast<unsigned char*>(b.ptr), bytes * (uint64_t)g / world, bytes * (uint64_t)(g + 1) / world,
+                             !inter && numa_policy() == kNumaTouch);
         FRZ_TRY(set_device(c->ranks[0].device));
         if (cudaHostRegister(b.ptr, bytes, cudaHostRegisterPortable | cudaHostRegisterMapped) != cudaSuccess) {
             cudaGetLastError();
@@ -603,9 +660,13 @@ frz_status host_block_alloc(frz_comm* c, uint64_t bytes, HostBlock* out) {
         b.ptr = mmap(nullptr, bytes, PROT_READ | PROT_WRITE, MAP_SHARED, b.fd, 0);
         if (b.ptr == MAP_FAILED) { b.ptr = nullptr; ok = 0; }
     }
-    // every rank touches ITS part of the segment from a CPU near its GPU (page placement), everybody waits, then everybody pins
-    if (ok) first_touch_near(c->ranks[0].device, static_cast<unsigned char*>(b.ptr), bytes * (uint64_t)c->rank / c->world,
-                             bytes * (uint64_t)(c->rank + 1) / c->world);
+    // page placement (numa_policy above): the policy is set on every rank's mapping, every rank touches ITS part of the
+    // segment (shared-memory pages follow the policy of the mapping that faults them in), everybody waits, then everybody pins
+    if (ok) {
+        const bool inter = numa_policy() == kNumaInterleave && interleave_pages(b.ptr, bytes);
+        first_touch_near(c->ranks[0].device, static_cast<unsigned char*>(b.ptr), bytes * (uint64_t)c->rank / c->world,
+                         bytes * (uint64_t)(c->rank + 1) / c->world, !inter && numa_policy() == kNumaTouch);
+    }
     std::vector<uint64_t> oks(c->world);
     FRZ_TRY(exchange_words(c, &ok, 1, oks.data()));
     if (ok) {
