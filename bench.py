@@ -526,7 +526,10 @@ def run_ours(args):
                                                                   if os.environ.get("FRZ_PARALLEL_EXCHANGE") == "slices" or not comm.p2p_active() else
                                                                   "P2P placement: every GPU stores its matches at their merged positions in the peers' slice "
                                                                   "buffers over NVLink (k_place, cudaIpc-mapped peer memory), no NCCL kernel (value); "
-                                                                  "all-gather of whole runs (value_device_out)"),
+                                                                  "all-gather of whole runs (value_device_out)" if comm.exchange_mode() == 2 else
+                                                                  "direct placement: every GPU stores its matches at their merged positions straight into "
+                                                                  "the shared pinned host buffer (k_place<DIRECT>, zero-copy over its own PCIe link; no "
+                                                                  "NCCL kernel, no separate D2H copy) (value); all-gather of whole runs (value_device_out)"),
                                                      "emulated_reference_backend": info}),
                 "clocks": clocks,
                 "value_device_out": {"value": n * world * args.steps / (ms_dev / 1e3), "unit": "haystacks/s",

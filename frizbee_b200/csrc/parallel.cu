@@ -12,10 +12,12 @@
 //
 // Host-out calls (the caller wants the list in host memory, the bench's `value`) do better than gather-then-merge:
 // every rank's per-score table crosses the shared host block, after which every rank KNOWS the merged position of each
-// of its matches, and ONE kernel (k_place) stores them straight into the peer GPUs' slice buffers over NVLink (P2P
-// stores into cudaIpc-mapped / peer-enabled memory) — the k-way merge and the exchange are the same pass, no NCCL
-// kernel, no receive buffer, no second scatter.  The all-gather form remains for device-out calls and as the fallback
-// (FRZ_PARALLEL_EXCHANGE=allgather|slices|p2p).
+// of its matches, and ONE kernel (k_place) stores them straight to where they belong — into the caller's pinned + mapped
+// HOST buffer itself (direct form: zero-copy stores over each GPU's own PCIe link, no peer traffic and no separate
+// device→host copy at all), or, when the buffer is not mapped, into the peer GPUs' slice buffers over NVLink (P2P stores
+// into cudaIpc-mapped / peer-enabled memory, then every GPU copies its slice out) — the k-way merge and the exchange are
+// the same pass, no NCCL kernel, no receive buffer, no second scatter.  The all-gather form remains for device-out calls
+// and as the fallback (FRZ_PARALLEL_EXCHANGE=direct|p2p|slices|allgather).
 //
 // The only per-step collective is that all-gather.  The match counts (the `Vec` lengths the k-merge reads) are
 // published by each GPU into a small pinned host block shared by all ranks — a 1-thread kernel right after the tile
@@ -206,16 +208,30 @@ struct PlaceMeta {
     unsigned long long total;
     int world, rank, bins, parity;
 };
+// DIRECT form (template): the destination is the caller's HOST buffer itself (pinned + mapped, zero-copy stores over this GPU's
+// own PCIe link): element i goes to host_out[pos0[s] + (i - gt[s])].  No peer memory, no flags, no separate device→host copy,
+// and no rank waits for another rank's run before its own bytes move — the G concurrent slice copies of the peer form
+// (which all start at the same moment, after the slowest rank) become G independent streams of posted writes.
+template <bool DIRECT>
 __global__ void __launch_bounds__(256) k_place(const FrzMatchDev* __restrict__ run, unsigned long long n, const __grid_constant__ PlaceMeta meta,
                                                const unsigned long long* __restrict__ pos0, const uint32_t* __restrict__ gt,
-                                               unsigned long long seq, unsigned long long timeout_ns, volatile unsigned long long* err_slot) {
+                                               unsigned long long seq, unsigned long long timeout_ns, volatile unsigned long long* err_slot,
+                                               FrzMatchDev* __restrict__ host_out) {
     __shared__ unsigned long long lo_s[kMaxWorld + 1];
     __shared__ FrzMatchDev* dst_s[kMaxWorld];
     __shared__ int last_s;
+    const int world = meta.world, bins = meta.bins;
+    if constexpr (DIRECT) {
+        for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {
+            const FrzMatchDev m = run[i];
+            const uint32_t s = bins > 1 ? min((uint32_t)m.score, (uint32_t)bins - 1) : 0u;
+            host_out[pos0[s] + (i - gt[s])] = m;
+        }
+        return;   // kernel completion + the stream-ordered "landed" flag make the stores visible to the host
+    }
     for (int i = threadIdx.x; i <= meta.world; i += blockDim.x) lo_s[i] = meta.lo[i];
     for (int i = threadIdx.x; i < meta.world; i += blockDim.x) dst_s[i] = reinterpret_cast<FrzMatchDev*>(meta.peer[i] + kPlaceHeaderBytes);
     __syncthreads();
-    const int world = meta.world, bins = meta.bins;
     const unsigned long long total = meta.total;
     for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {
         const FrzMatchDev m = run[i];
@@ -311,6 +327,9 @@ struct RankCtx {
     uint64_t place_cap = 0;                 // elements
     unsigned char* peer_raw[kMaxWorld] = {};
     bool peer_ipc[kMaxWorld] = {};          // opened with cudaIpcOpenMemHandle (multi-process form)
+    const void* direct_for = nullptr;       // host `out` pointer (and capacity) the direct form was last negotiated for
+    uint64_t direct_cap = 0;
+    FrzMatchDev* direct_dev = nullptr;      // its device-side address (nullptr: not mapped on some rank → peer / NCCL forms)
     uint32_t* table_dev = nullptr;          // device-side address of the shared table block
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     bool ev_valid = false;
@@ -341,6 +360,8 @@ struct frz_comm {
     bool slice_exchange = true;   // FRZ_PARALLEL_EXCHANGE=allgather forces the all-gather form for host-out calls too
     bool p2p_exchange = true;     // host-out calls place matches straight into the peers' slice buffers (k_place); cleared by
                                   // FRZ_PARALLEL_EXCHANGE=slices|allgather, or when peer access / cudaIpc is unavailable
+    bool direct_exchange = true;  // host-out calls store matches straight into the caller's mapped host buffer (k_place<DIRECT>);
+                                  // needs `out` to be pinned + mapped on every rank (frz_comm_host_alloc memory is)
     // local form: rendezvous of the worker threads (allgather_words)
     std::mutex tb_mu;
     std::condition_variable tb_cv;
@@ -446,6 +467,31 @@ frz_status allgather_words(frz_comm* c, RankCtx& r, const uint64_t* mine, int n_
     if (!rendezvous()) return frz_fail(FRZ_ERR_NCCL, "a GPU worker did not reach the rendezvous within %.0f s", poll_timeout_s());
     for (int q = 0; q < c->world; q++) memcpy(all + (size_t)q * n_words, &c->tb_words[(size_t)q * kGatherWords], n_words * sizeof(uint64_t));
     if (!rendezvous()) return frz_fail(FRZ_ERR_NCCL, "a GPU worker did not reach the rendezvous within %.0f s", poll_timeout_s());
+    return FRZ_OK;
+}
+
+// Direct form: is the caller's `out` buffer addressable from every rank's GPU?  Negotiated once per buffer (collective: the
+// ranks make the same calls with the same shared buffer, so they reach this together); any rank that cannot map it turns
+// the form off for that buffer on all ranks.
+frz_status negotiate_direct(frz_comm* c, RankCtx& r, const frz_match* out_host, uint64_t cap, FrzMatchDev** dev) {
+    *dev = nullptr;
+    if (!c->direct_exchange || !out_host) return FRZ_OK;
+    if (r.direct_for == out_host && r.direct_cap == cap) { *dev = r.direct_dev; return FRZ_OK; }
+    void* dp = nullptr;
+    uint64_t ok = cudaHostGetDevicePointer(&dp, const_cast<frz_match*>(out_host), 0) == cudaSuccess && dp ? 1 : 0;
+    if (ok && cap) {   // the whole buffer, not just its first page
+        void* dp2 = nullptr;
+        ok = cudaHostGetDevicePointer(&dp2, const_cast<frz_match*>(out_host + (cap - 1)), 0) == cudaSuccess &&
+             dp2 == static_cast<void*>(static_cast<FrzMatchDev*>(dp) + (cap - 1)) ? 1 : 0;
+    }
+    if (!ok) cudaGetLastError();
+    uint64_t all[kMaxWorld];
+    FRZ_TRY(allgather_words(c, r, &ok, 1, all));
+    for (int q = 0; q < c->world; q++) ok = ok && all[q] == 1;
+    r.direct_for = out_host;
+    r.direct_cap = cap;
+    r.direct_dev = ok ? static_cast<FrzMatchDev*>(dp) : nullptr;
+    *dev = r.direct_dev;
     return FRZ_OK;
 }
 
@@ -696,6 +742,7 @@ frz_status comm_finish_setup(frz_comm* c) {
         const char* e = getenv("FRZ_PARALLEL_EXCHANGE");
         c->slice_exchange = !(e && strcmp(e, "allgather") == 0);
         c->p2p_exchange = c->slice_exchange && !(e && strcmp(e, "slices") == 0) && c->world > 1;
+        c->direct_exchange = c->slice_exchange && c->world > 1 && (!e || strcmp(e, "direct") == 0);
     }
     if (c->p2p_exchange && c->local_form) {   // one process: plain peer access between every pair of devices
         for (RankCtx& a : c->ranks) {
@@ -817,6 +864,7 @@ frz_status rank_step(frz_comm* c, RankCtx& r, frz_matcher* m, const frz_corpus* 
     const FrzMatchDev* d_final = r.run;
     uint64_t d_final_first = 0;   // merged position of d_final[0] (non-zero in the slice form)
     bool placed = false;          // the P2P placement ran this step
+    bool direct_done = false;     // the direct form ran: this rank's matches went straight into the host buffer
     // ---- host-out calls: SLICE EXCHANGE.  A rank copies only its slice [lo, hi) of the merged list to the host, and the
     // elements of run q that land in that slice are ONE contiguous range of run q (a run's elements keep their order in the
     // merged list).  With every rank's per-score table (published like the counts) each rank computes those ranges on the
@@ -836,9 +884,12 @@ frz_status rank_step(frz_comm* c, RankCtx& r, frz_matcher* m, const frz_corpus* 
             return frz_fail(FRZ_ERR_CAPACITY, "output capacity %llu < %llu matches", (unsigned long long)cap, (unsigned long long)total);
         }
         if (!out_host) return frz_fail(FRZ_ERR_INVALID_ARG, "null out");
-        // slice buffers of the P2P placement (collective, grow-only; falls back to the NCCL slice exchange when unavailable)
-        bool place_ready = false;
-        FRZ_TRY(ensure_place_buffers(c, r, total / (uint64_t)world + 2, &place_ready));
+        // direct form: the caller's buffer mapped on every GPU?  Else the slice buffers of the P2P placement (collective,
+        // grow-only), else the NCCL slice exchange
+        FrzMatchDev* direct_out = nullptr;
+        FRZ_TRY(negotiate_direct(c, r, out_host, cap, &direct_out));
+        bool place_ready = direct_out != nullptr;
+        if (!direct_out) FRZ_TRY(ensure_place_buffers(c, r, total / (uint64_t)world + 2, &place_ready));
         // 1. my table → shared block (after the local pipeline on the main stream), everybody's tables ← shared block
         volatile uint32_t* tab_host = c->tables_host + ((size_t)parity * world) * kTableBins;
         if (by_score) {
@@ -881,14 +932,21 @@ frz_status rank_step(frz_comm* c, RankCtx& r, frz_matcher* m, const frz_corpus* 
         for (int p2 = 0; p2 <= world; p2++) meta.lo[p2] = lo_p[p2];
         meta.total = total; meta.world = world; meta.rank = r.rank; meta.bins = bins; meta.parity = parity;
         const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((counts[r.rank] + 255) / 256, 148 * 4));
-        k_place<<<grid, 256, 0, main>>>(r.run, counts[r.rank], meta, reinterpret_cast<const unsigned long long*>(r.d_pos0),
-                                         reinterpret_cast<const uint32_t*>(r.d_pos0 + bins), seq,
-                                         (unsigned long long)(poll_timeout_s() * 1e9),
-                                         reinterpret_cast<volatile unsigned long long*>(r.ctrl_dev + kCtrlPlaceErr + r.rank));
-        FRZ_CUDA_TRY(cudaGetLastError());
-        placed = true;
-        d_final = reinterpret_cast<const FrzMatchDev*>(r.place_raw + kPlaceHeaderBytes);
-        d_final_first = lo_p[r.rank];
+        if (direct_out) {
+            k_place<true><<<grid, 256, 0, main>>>(r.run, counts[r.rank], meta, reinterpret_cast<const unsigned long long*>(r.d_pos0),
+                                                  reinterpret_cast<const uint32_t*>(r.d_pos0 + bins), seq, 0ull, nullptr, direct_out);
+            FRZ_CUDA_TRY(cudaGetLastError());
+            direct_done = true;   // my part of the list is already on its way to the host buffer: no slice copy
+        } else {
+            k_place<false><<<grid, 256, 0, main>>>(r.run, counts[r.rank], meta, reinterpret_cast<const unsigned long long*>(r.d_pos0),
+                                                   reinterpret_cast<const uint32_t*>(r.d_pos0 + bins), seq,
+                                                   (unsigned long long)(poll_timeout_s() * 1e9),
+                                                   reinterpret_cast<volatile unsigned long long*>(r.ctrl_dev + kCtrlPlaceErr + r.rank), nullptr);
+            FRZ_CUDA_TRY(cudaGetLastError());
+            placed = true;
+            d_final = reinterpret_cast<const FrzMatchDev*>(r.place_raw + kPlaceHeaderBytes);
+            d_final_first = lo_p[r.rank];
+        }
       } else {
         static thread_local std::vector<uint64_t> A;
         A.assign((size_t)world * (world + 1), 0);
@@ -1004,7 +1062,7 @@ frz_status rank_step(frz_comm* c, RankCtx& r, frz_matcher* m, const frz_corpus* 
         if (total && !out_host) return frz_fail(FRZ_ERR_INVALID_ARG, "null out");
         // this rank's slice of the merged list → host (all ranks hold the whole list: the copy uses every PCIe link)
         const uint64_t lo = total * (uint64_t)r.rank / (uint64_t)world, hi = total * (uint64_t)(r.rank + 1) / (uint64_t)world;
-        if (hi > lo)
+        if (hi > lo && !direct_done)
             FRZ_CUDA_TRY(cudaMemcpyAsync(out_host + lo, d_final + (lo - d_final_first), (hi - lo) * sizeof(FrzMatchDev), cudaMemcpyDeviceToHost, main));
     }
     FRZ_CUDA_TRY(cudaEventRecord(r.ev[3], main));
@@ -1117,7 +1175,9 @@ extern "C" int frz_comm_world(const frz_comm* c) { return c ? c->world : 0; }
 extern "C" int frz_comm_rank(const frz_comm* c) { return c ? c->rank : -1; }
 extern "C" int frz_comm_device(const frz_comm* c, int i) { return (c && i >= 0 && i < (int)c->ranks.size()) ? c->ranks[i].device : -1; }
 
-extern "C" int frz_comm_exchange_mode(const frz_comm* c) { return !c ? -1 : (c->p2p_exchange && c->world > 1) ? 2 : c->slice_exchange ? 1 : 0; }
+extern "C" int frz_comm_exchange_mode(const frz_comm* c) {
+    return !c ? -1 : (c->direct_exchange && c->world > 1) ? 3 : (c->p2p_exchange && c->world > 1) ? 2 : c->slice_exchange ? 1 : 0;
+}
 
 extern "C" frz_status frz_comm_host_alloc(frz_comm* c, uint64_t bytes, void** out) {
     if (!c || !out) return frz_fail(FRZ_ERR_INVALID_ARG, "null argument");
@@ -1132,7 +1192,7 @@ extern "C" frz_status frz_comm_host_free(frz_comm* c, void* p) {
     if (!c || !p) return FRZ_OK;
     for (size_t i = 0; i < c->blocks.size(); i++)
         if (c->blocks[i].ptr == p) {
-            for (RankCtx& r : c->ranks) { cudaSetDevice(r.device); cudaDeviceSynchronize(); }
+            for (RankCtx& r : c->ranks) { cudaSetDevice(r.device); cudaDeviceSynchronize(); r.direct_for = nullptr; r.direct_dev = nullptr; }
             host_block_release(c->blocks[i]);
             c->blocks.erase(c->blocks.begin() + (long)i);
             return FRZ_OK;

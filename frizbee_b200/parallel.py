@@ -116,11 +116,11 @@ class Comm:
         _check(plib().frz_comm_barrier(self._h))
 
     def exchange_mode(self) -> int:
-        """2 = P2P placement, 1 = NCCL slice exchange, 0 = all-gather (frz_comm_exchange_mode)."""
+        """3 = direct placement into the mapped host buffer, 2 = P2P placement, 1 = NCCL slice exchange, 0 = all-gather."""
         return int(plib().frz_comm_exchange_mode(self._h))
 
     def p2p_active(self) -> bool:
-        return self.exchange_mode() == 2
+        return self.exchange_mode() >= 2
 
     def device(self, local_index: int = 0) -> int:
         return plib().frz_comm_device(self._h, local_index)
