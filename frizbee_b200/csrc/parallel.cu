@@ -208,10 +208,11 @@ struct PlaceMeta {
     unsigned long long total;
     int world, rank, bins, parity;
 };
-// DIRECT form (template): the destination is the caller's HOST buffer itself (pinned + mapped, zero-copy stores over this GPU's
-// own PCIe link): element i goes to host_out[pos0[s] + (i - gt[s])].  No peer memory, no flags, no separate device→host copy,
-// and no rank waits for another rank's run before its own bytes move — the G concurrent slice copies of the peer form
-// (which all start at the same moment, after the slowest rank) become G independent streams of posted writes.
+// DIRECT form (template, opt-in with FRZ_PARALLEL_EXCHANGE=direct): the destination is the caller's HOST buffer itself (pinned +
+// mapped, zero-copy stores over this GPU's own PCIe link): element i goes to host_out[pos0[s] + (i - gt[s])].  No peer
+// memory, no flags, no separate device→host copy, and no rank waits for another rank's run before its own bytes move.
+// Measured slower than the peer form on B200 (SM-issued posted writes reach ~30 GB/s, the copy engine ~52 GB/s:
+// profiles/r02o_bench_n2_direct.json vs r02o_bench_n2_p2p.json), so it is not the default.
 template <bool DIRECT>
 __global__ void __launch_bounds__(256) k_place(const FrzMatchDev* __restrict__ run, unsigned long long n, const __grid_constant__ PlaceMeta meta,
                                                const unsigned long long* __restrict__ pos0, const uint32_t* __restrict__ gt,
@@ -595,18 +596,20 @@ bool node_cpus(int node, cpu_set_t* set) {   // parses /sys/devices/system/node/
     return n > 0;
 }
 // Page placement policy of the shared host buffers (FRZ_HOST_NUMA):
-//   interleave (default)  pages alternate over the memory nodes (mbind MPOL_INTERLEAVE before the first touch): every GPU's
-//                         slice is half local, half remote, wherever the slice boundaries of a step fall, and the DRAM
-//                         write load of G concurrent slice copies is spread evenly over the sockets
-//   touch                 rank r first-touches the r-th part of the buffer from a CPU of its GPU's node (exact only when the
-//                         list fills the buffer: slices are fractions of the USED part)
-//   none                  wherever the kernel puts them
+//   touch (default)  rank r first-touches the r-th part of the buffer from a CPU of its GPU's node (exact only when the list
+//                    fills the buffer: slices are fractions of the USED part)
+//   interleave       pages alternate over the memory nodes (mbind MPOL_INTERLEAVE before the first touch): every GPU's slice
+//                    is half local, half remote, wherever the slice boundaries of a step fall
+//   none             wherever the kernel puts them
+// Measured at 8 GPUs (profiles/r02n_*, FRZ_PARALLEL_DEBUG=1 prints where the pages are): rank 0's 6 MB slice copy takes
+// 0.19 ms with touch or none (the ranks happened to run on their GPU's node) and 0.26 ms interleaved, against 0.115 ms alone —
+// and the step is 0.711-0.717 ms with all three: page placement is not what slows eight concurrent slice copies down.
 enum { kNumaInterleave = 0, kNumaTouch = 1, kNumaNone = 2 };
 int numa_policy() {
     static int p = -1;
     if (p < 0) {
         const char* e = getenv("FRZ_HOST_NUMA");
-        p = !e ? kNumaInterleave : strcmp(e, "touch") == 0 ? kNumaTouch : strcmp(e, "none") == 0 ? kNumaNone : kNumaInterleave;
+        p = !e ? kNumaTouch : strcmp(e, "interleave") == 0 ? kNumaInterleave : strcmp(e, "none") == 0 ? kNumaNone : kNumaTouch;
     }
     return p;
 }
@@ -742,7 +745,9 @@ frz_status comm_finish_setup(frz_comm* c) {
         const char* e = getenv("FRZ_PARALLEL_EXCHANGE");
         c->slice_exchange = !(e && strcmp(e, "allgather") == 0);
         c->p2p_exchange = c->slice_exchange && !(e && strcmp(e, "slices") == 0) && c->world > 1;
-        c->direct_exchange = c->slice_exchange && c->world > 1 && (!e || strcmp(e, "direct") == 0);
+        // direct form: opt-in.  Measured on 2 B200s (profiles/r02o_*): the SMs' zero-copy stores move the 6 MB of a rank at
+        // ~30 GB/s against ~52 GB/s for the copy engine, 0.211 ms against 0.045 (k_place) + 0.115 (slice copy) for the P2P form
+        c->direct_exchange = c->slice_exchange && c->world > 1 && e && strcmp(e, "direct") == 0;
     }
     if (c->p2p_exchange && c->local_form) {   // one process: plain peer access between every pair of devices
         for (RankCtx& a : c->ranks) {
