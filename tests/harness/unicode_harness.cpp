@@ -31,6 +31,9 @@ FrzUScoring scoring_of(const uint16_t* s9, bool u8) {
 extern "C" {
 int h_build_needle(const uint8_t* needle, size_t n, int case_sensitive, FrzUNeedle* out) { return frz_build_uneedle(needle, n, case_sensitive != 0, out) ? 1 : 0; }
 int h_needle_has_uppercase(const uint8_t* needle, size_t n) { return frz_needle_has_uppercase(needle, n) ? 1 : 0; }
+// the product's case tables, scalar by scalar (tests/test_unicode_device_code.py checks them against an independent derivation)
+uint32_t h_scalar_flip(uint32_t cp) { return frz_unicode_detail::scalar_flip(cp); }
+int h_scalar_is_uppercase(uint32_t cp) { return frz_unicode_detail::scalar_is_uppercase(cp) ? 1 : 0; }
 int h_prefilter(const uint8_t* needle, size_t n, int case_sensitive, const uint8_t* hay, int len, int lanes, int max_typos,
                 int* start, int* end) {
     FrzUNeedle nd;
