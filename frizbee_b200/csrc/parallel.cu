@@ -5,8 +5,9 @@
 //   threads claim 2048-item chunks (parallel.rs:33-63)    GPUs own contiguous index-range shards
 //   matcher.clone() per thread (parallel.rs:46)           frz_matcher_clone per GPU, cached per communicator rank
 //   per-thread reverse + radix sort (parallel.rs:67-73)   frz_match_shard_device: the local run stays in HBM
-//   join, Vec<Vec<Match>> (parallel.rs:77)                ONE ncclAllGather of the runs padded to the longest
-//   k_merge_matches_by_* (src/k_merge.rs:90-131)          frz_merge_runs_ex on every GPU (bit-identical order)
+//   join, Vec<Vec<Match>> (parallel.rs:77)                host-out: k_place — every GPU stores its matches at their merged
+//   k_merge_matches_by_* (src/k_merge.rs:90-131)            positions in the peers' slice buffers (merge + exchange in one pass)
+//                                                         device-out: ONE ncclAllGather of the runs + frz_merge_runs_ex
 //   returned Vec<Match>                                   every GPU copies ITS slice of the merged list to the host
 //                                                         buffer: the D2H runs over all PCIe links at once
 //

@@ -178,6 +178,8 @@ def test_parallel_entry_points_argument_errors_without_a_device():
     assert L.frz_match_list_parallel(None, None, 0, None, None, 0, ctypes.byref(n)) == 1          # FRZ_ERR_INVALID_ARG
     assert L.frz_match_list_parallel_rank(None, None, 0, None, None, 0, ctypes.byref(n), None) == 1
     assert L.frz_comm_world(None) == 0 and L.frz_comm_rank(None) == -1
+    assert L.frz_comm_exchange_mode(None) == -1
+    assert L.frz_match_list_parallel_rank_host(None, None, None, 4, 0, 0, None, None, 0, ctypes.byref(n)) == 1
     if not torch.cuda.is_available():
         with pytest.raises(F.FrizbeeError) as e:
             parallel.Comm.local(1)
