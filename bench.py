@@ -7,8 +7,10 @@
 A "step" is one blocking Matcher::match_list_parallel call (frz_match_list_parallel_rank; at N = 1 this is
 Matcher::match_list) over one synthetic haystack list of BASELINE.json configs[2] shape per GPU — needle 'deadbeef',
 10M haystacks, len <= 64 (mean 48), max_typos = 1 — weak scaling: rank r holds its own 10M-item shard with the indices
-[r*10M, (r+1)*10M); a step is the local pipeline on every GPU, ONE NCCL all-gather of the per-shard runs, the k-way
-merge, and every GPU copying its slice of the merged list into ONE pinned host buffer shared by the ranks.
+[r*10M, (r+1)*10M); a step is the local pipeline on every GPU, the k-way merge + exchange (host-out: ONE kernel per GPU that
+stores its matches at their merged positions in the peers' slice buffers over NVLink; device-out: ONE NCCL all-gather of the
+per-shard runs + the merge on every GPU), and every GPU copying its slice of the merged list into ONE pinned host buffer
+shared by the ranks.
 
   value            whole-job haystacks/s, packed shards resident in HBM when the timed region starts, the ordered match
                    list LANDED IN PINNED HOST MEMORY when a step ends; same definition at every N.
@@ -489,7 +491,7 @@ def run_ours(args):
                 traffic = int(tj["dram_bytes_read"] + tj["dram_bytes_write"])   # from the committed ncu capture
         except Exception:
             pass
-        roofline = {"bound": "hbm", "kernel": "k_prefilter (+ tile rank/scan)", "achieved": achieved, "peak": peak,
+        roofline = {"bound": "hbm", "kernel": "prefilter stage: k_sig_scan + k_window (+ tile rank/scan)", "achieved": achieved, "peak": peak,
                     "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "traffic": traffic,
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
                     "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": pf_ms,
