@@ -265,6 +265,66 @@ def placement_host(runs: List[np.ndarray], sort: SortStrategy, bins: int = 1024)
     return slices
 
 
+def match_list_parallel_placement_gloo(run: np.ndarray, sort: SortStrategy, bins: int = 1024, group=None) -> np.ndarray:
+    """The P2P placement protocol of csrc/parallel.cu on torch.distributed (gloo on CPU in the tests), rank-local like on the
+    GPUs: (1) every rank publishes its count and its per-score table (all_gather — the shared host block of the device path),
+    (2) computes pos0[] for ITS run only, (3) sends every element, tagged with its slice-relative position, to the rank that
+    owns that slice of the merged list (all_to_all — the NVLink peer stores of k_place), (4) every rank assembles its slice.
+    Returns this rank's slice [total * r // G, total * (r + 1) // G) of the merged list."""
+    import torch
+    import torch.distributed as dist
+    world, me = dist.get_world_size(group), dist.get_rank(group)
+    by_score = sort.is_by_score()
+    nb = bins if by_score else 1
+    mine = np.zeros(nb + 1, dtype=np.int64)            # [count, gt[0..nb)]
+    mine[0] = len(run)
+    if by_score:
+        hist = np.bincount(np.minimum(run["score"].astype(np.int64), nb - 1), minlength=nb)
+        mine[1:] = hist[::-1].cumsum()[::-1] - hist
+    allt = [torch.zeros(nb + 1, dtype=torch.int64) for _ in range(world)]
+    dist.all_gather(allt, torch.from_numpy(mine), group=group)
+    tab = np.stack([t.numpy() for t in allt])          # [world][1 + nb]
+    counts, gt = tab[:, 0], tab[:, 1:]
+    total = int(counts.sum())
+    lo = [total * p // world for p in range(world + 1)]
+    ge = np.concatenate([counts[:, None], gt[:, :-1]], axis=1)
+    order = list(range(world))[::-1] if sort.is_reversed() else list(range(world))
+    pos0 = np.zeros(nb, dtype=np.int64)
+    for s in range(nb):
+        acc = int(gt[:, s].sum())
+        for q in order:
+            if q == me:
+                break
+            acc += int(ge[q][s] - gt[q][s])
+        pos0[s] = acc
+    i = np.arange(len(run), dtype=np.int64)
+    s_of = np.minimum(run["score"].astype(np.int64), nb - 1) if by_score else np.zeros(len(run), dtype=np.int64)
+    x = pos0[s_of] + (i - gt[me][s_of])
+    p_of = np.searchsorted(np.asarray(lo[1:], dtype=np.int64), x, side="right")
+    rec = np.ascontiguousarray(run).view(np.int64)
+    send = []
+    for p in range(world):
+        sel = p_of == p
+        send.append(torch.from_numpy(np.stack([x[sel] - lo[p], rec[sel]], axis=1).reshape(-1).copy()))   # (position, record) pairs
+    sizes = torch.tensor([len(t) for t in send], dtype=torch.int64)
+    all_sizes = [torch.zeros(world, dtype=torch.int64) for _ in range(world)]
+    dist.all_gather(all_sizes, sizes, group=group)
+    recv = [torch.zeros(int(all_sizes[q][me]), dtype=torch.int64) for q in range(world)]
+    reqs = [dist.isend(send[p], p, group=group) for p in range(world) if p != me]
+    for q in range(world):
+        if q == me:
+            recv[q] = send[me]
+        else:
+            dist.recv(recv[q], q, group=group)
+    for r in reqs:
+        r.wait()
+    out = np.zeros(lo[me + 1] - lo[me], dtype=np.int64)
+    for t in recv:
+        pairs = t.numpy().reshape(-1, 2)
+        out[pairs[:, 0]] = pairs[:, 1]
+    return out.view(MATCH_DTYPE)
+
+
 def all_gather_runs(run, count: int, group=None):
     """The collective step on torch tensors (gloo on CPU in the tests): the counts, then ONE all-gather of the runs padded
     to the longest.  `run` is a 1-D int64 tensor of 8-byte match records.  Returns (gathered [world * stride], counts, stride)."""

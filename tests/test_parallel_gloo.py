@@ -118,3 +118,43 @@ def test_p2p_placement_arithmetic_equals_the_k_way_merge(world):
                     continue                             # (the device path only uses a table that separates all scores)
                 got = np.concatenate(parallel.placement_host(runs, sort, bins=bins))
                 assert np.array_equal(got, want), (world, n, sort, bins)
+
+
+def _placement_worker(rank, world, port, sort_value, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        hs = _haystacks()
+        lo, hi = parallel.shard_bounds(len(hs), world)[rank]
+        data, off = O.pack(hs[lo:hi])
+        cfg = Config(sort=SortStrategy(sort_value))
+        run = O.match_list_into_packed(["foo"], cfg, data, off, index_offset=lo)
+        if cfg.sort.is_reversed():
+            run = run[::-1]
+        if cfg.sort.is_by_score():
+            run = O.radix_sort_matches(run)
+        piece = parallel.match_list_parallel_placement_gloo(np.ascontiguousarray(run), cfg.sort)
+        q.put((rank, piece.tobytes()))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("sort", list(SortStrategy))
+def test_parallel_placement_protocol_gloo(sort):
+    """World-size-2 run of the P2P placement protocol (tables published → every rank positions its own run → elements go to
+    the rank that owns their slice): the concatenated slices equal the sequential match_list, for every sort strategy, on
+    the reference's own parallel test list (src/matcher/parallel.rs:104-130)."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_placement_worker, args=(r, 2, port, int(sort), q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    pieces = dict(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    got = np.concatenate([np.frombuffer(pieces[r], dtype=O.MATCH_DTYPE) for r in range(2)])
+    data, off = O.pack(_haystacks())
+    want = O.match_list_packed(["foo"], Config(sort=sort), data, off)
+    assert np.array_equal(got, want)
